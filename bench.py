@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""Benchmark of the MPM substep (bin + P2G + grid update + G2P).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload 3d16m|2d1m] [--impl reference]
+
+Prints ONE JSON line (rank 0).  ``value`` = particle-substeps/s with the state
+resident in HBM; ``e2e`` = the same through host buffers (pinned H2D of the full
+particle state + one substep + D2H of x, v, C, F every step); ``roofline`` = the
+dominant kernel against the measured HBM peak; ``cpu_baseline`` = the oracle port
+timed on this box's host cores on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle-substeps/sec (P2G+grid+G2P)"
+UNIT = "particle-substeps/s"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_scene(workload: str, seed: int = 0, cells_x=None, res_x=None):
+    from femflow_b200 import scenes
+    if workload == "2d1m":
+        return scenes.config_2d_1m(seed)
+    if workload == "3d16m":
+        return scenes.config_3d_16m(seed)
+    if workload.startswith("3d:"):        # 3d:<res>:<cells>  (tests / quick runs)
+        _, res, cells = workload.split(":")
+        return scenes.elastic_block(3, int(res), int(cells), 2, seed)
+    raise SystemExit(f"unknown workload {workload}")
+
+
+# ----------------------------------------------------------------------------- #
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for nm, val in zip(names, r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- #
+def cpu_baseline(scene, budget_s: float = 15.0, threads=None):
+    """Oracle port on the host cores, bounded sample of the same workload: the first
+    ``m`` cells-worth of the block (same density, same grid resolution)."""
+    from oracle import native as onative
+    return onative.time_sample(scene, budget_s=budget_s, threads=threads)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the reference is
+    pure Python/numba and cannot travel to the GPU box) on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    scene = make_scene(args.workload)
+    from oracle import native as onative
+    vals = []
+    info = None
+    for i in range(args.warmup + args.steps):
+        info = onative.time_sample(scene, budget_s=max(2.0, 40.0 / max(1, args.steps + args.warmup)),
+                                   threads=None, substeps=1)
+        if i >= args.warmup:
+            vals.append(info["value"])
+    v = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * info["sample_particles"] / v, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": scene.name, "sample": info["sample"]},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
+                         "sample": info["sample"]},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- #
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--workload", default="3d16m")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--p2g-mode", default="auto")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from femflow_b200.mpm import MpmSolver
+
+    scene = make_scene(args.workload, seed=rank)
+    n = scene.n
+    if world > 1:
+        from femflow_b200.distributed import SlabSolver
+        solver = SlabSolver.from_scene(scene, rank, world, dev, p2g_mode=args.p2g_mode)
+    else:
+        solver = MpmSolver(scene.dim, scene.res, scene.dt, scene.volume, scene.gravity, scene.hardening,
+                           capacity=n, device=dev, mass=scene.mass, mu_0=scene.mu_0, lambda_0=scene.lambda_0,
+                           p2g_mode=args.p2g_mode)
+        solver.set_particles(scene.x, scene.v, scene.F, scene.C, None,
+                             *( (scene.mass, scene.mu_0, scene.lambda_0) if scene.dim == 3 else (None, None, None)))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- warm-up ----
+    for _ in range(args.warmup):
+        solver.substep(1)
+    barrier()
+    if solver.poll_error():
+        raise SystemExit("warm-up left particles outside the grid")
+
+    # ---- timed region: K substeps, state resident in HBM ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = solver.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        solver.substep(1)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = solver.launch_count() - l0
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        cnt = torch.tensor([solver.num_particles], device=dev, dtype=torch.float64)
+        dist.all_reduce(cnt)
+        n_total = int(cnt.item())
+    else:
+        n_total = n
+    clocks = sampler.stop() if rank == 0 else None
+    n_oob = solver.poll_error()
+    value = n_total * args.steps / (ms * 1e-3)
+
+    # ---- per-phase timing (same stream, CUDA events) for the roofline of the dominant kernel ----
+    phases = {}
+    if world == 1:
+        names = (["bin"] if (scene.dim == 3 and solver.reorder) else []) + ["p2g", "grid_op", "g2p"]
+        acc = {k: 0.0 for k in ["clear"] + names}
+        reps = max(3, min(args.steps, 10))
+        for _ in range(reps):
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 2)]
+            evs[0].record()
+            solver.clear_grid()
+            evs[1].record()
+            for i, nm in enumerate(names):
+                getattr(solver, nm)()
+                evs[i + 2].record()
+            torch.cuda.synchronize(dev)
+            acc["clear"] += evs[0].elapsed_time(evs[1])
+            for i, nm in enumerate(names):
+                acc[nm] += evs[i + 1].elapsed_time(evs[i + 2])
+        phases = {k: v / reps for k, v in acc.items()}
+
+    # ---- end to end through host buffers (pinned), every step: H2D state, substep, D2H result ----
+    e2e = None
+    if world == 1:
+        d = scene.dim
+        b = solver.buffers[0]
+        host_in = {k: torch.empty_like(getattr(b, k)[..., :n], device="cpu").pin_memory()
+                   for k in ("x", "v", "C", "F") }
+        for k in ("mass", "mu0", "lam0"):
+            if getattr(b, k) is not None:
+                host_in[k] = torch.empty(n, dtype=b.x.dtype).pin_memory()
+        live = solver.live
+        for k in host_in:
+            host_in[k].copy_(getattr(live, k)[..., :n])
+        host_out = {k: torch.empty_like(host_in[k]).pin_memory() for k in ("x", "v", "C", "F")}
+        h2d = sum(t.numel() * t.element_size() for t in host_in.values())
+        d2h = sum(t.numel() * t.element_size() for t in host_out.values())
+
+        def e2e_step():
+            bb = solver.buffers[0]
+            for k, t in host_in.items():
+                getattr(bb, k)[..., :n].copy_(t, non_blocking=True)
+            if bb.id is not None:
+                bb.id[:n] = torch.arange(n, dtype=torch.int32, device=dev)
+            solver._bind(n)
+            solver.substep(1)
+            lv = solver.live
+            for k, t in host_out.items():
+                t.copy_(getattr(lv, k)[..., :n], non_blocking=True)
+
+        e2e_step()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        e_ms = e0.elapsed_time(e1)
+        e2e = {"value": n * args.e2e_steps / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": e_ms / args.e2e_steps,
+               "api": "ffmpm C ABI via MpmSolver (host SoA pinned buffers in, x/v/C/F out, every step)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ----
+    peak, peak_src = peaks()
+    roofline = None
+    if phases:
+        N_, A = n, scene.active_nodes
+        if scene.dim == 3:
+            alg = {"p2g": 108 * N_ + 16 * A, "g2p": (48 + 96) * N_ + 12 * A, "grid_op": 28 * A, "clear": 16 * A}
+        else:
+            alg = {"p2g": 48 * N_ + 12 * A, "g2p": (28 + 52) * N_ + 8 * A, "grid_op": 20 * A, "clear": 12 * A}
+        dom = max((k for k in phases if k in alg), key=lambda k: phases[k])
+        achieved = alg[dom] / (phases[dom] * 1e-3) / 1e9
+        total_alg = (252 * N_ + 72 * A) if scene.dim == 3 else (128 * N_ + 52 * A)
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg[dom],
+                    "phase_ms": {k: round(v, 4) for k, v in phases.items()},
+                    "substep_frac_of_hbm_roofline": (total_alg / (ms * 1e-3 / args.steps) / 1e9) / peak}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            cpu = cpu_baseline(scene)
+        except Exception as e:  # the baseline is reported, never the product path
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 storage, f64 constitutive (polar/stress)", "data": "synthetic",
+        "config": {"workload": scene.name, "particles_per_gpu": n, "particles_total": n_total,
+                   "grid": f"{scene.res}^{scene.dim}", "dt": scene.dt, "p2g_mode": args.p2g_mode,
+                   "l2": "inputs larger than L2 (no flush)" if n * 252 > 256e6 else "state fits in L2 (flagged)",
+                   "n_oob": n_oob},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

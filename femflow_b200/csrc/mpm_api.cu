@@ -1,0 +1,375 @@
+// C ABI of the MPM substep library (see include/femflow_mpm.h).
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/femflow_mpm.h"
+#include "mpm_bin.cuh"
+#include "mpm_common.cuh"
+#include "mpm_direct.cuh"
+#include "mpm_tiled.cuh"
+
+using namespace ffmpm;
+
+static thread_local char g_last_error[512] = "";
+
+static int set_err(int code, const char* fmt, const char* detail = "") {
+  snprintf(g_last_error, sizeof(g_last_error), fmt, detail);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                          \
+  do {                                                                          \
+    cudaError_t e__ = (expr);                                                   \
+    if (e__ != cudaSuccess) return set_err(FFMPM_E_CUDA, #expr ": %s", cudaGetErrorString(e__)); \
+  } while (0)
+
+static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+struct FfMpmHandle {
+  FfMpmConfig cfg;
+  DevCfg dev;
+  int device;
+  int sm_count;
+  int64_t n_nodes;
+  // workspace carve-up
+  char* ws;
+  int64_t ws_bytes;
+  ErrRec* err;
+  void* grid;
+  BinBuffers bin;
+  // state
+  FfMpmState st[2];
+  bool have_alt;
+  int live;
+  int64_t n;
+  int64_t capacity;   // capacity the workspace was sized for (derived from ws_bytes)
+  bool binned;        // bin buffers describe the live buffer
+  int64_t launches;
+};
+
+static size_t elem_size(const FfMpmConfig& c) { return c.dtype == FFMPM_F64 ? 8 : 4; }
+
+static int validate(const FfMpmConfig* c) {
+  if (!c) return set_err(FFMPM_E_INVALID, "null config");
+  if (c->dim != 2 && c->dim != 3) return set_err(FFMPM_E_INVALID, "dim must be 2 or 3");
+  if (c->dtype != FFMPM_F32 && c->dtype != FFMPM_F64) return set_err(FFMPM_E_INVALID, "bad dtype");
+  if (c->model != FFMPM_NEO_HOOKEAN && c->model != FFMPM_SNOW) return set_err(FFMPM_E_INVALID, "bad model");
+  for (int d = 0; d < c->dim; ++d) {
+    if (c->n[d] < 3 || c->res[d] < 2) return set_err(FFMPM_E_INVALID, "grid too small");
+  }
+  if (c->dim == 2 && c->n[2] != 1) return set_err(FFMPM_E_INVALID, "2D needs n[2] == 1");
+  int64_t nodes = (int64_t)c->n[0] * c->n[1] * c->n[2];
+  if (nodes >= (1LL << 31)) return set_err(FFMPM_E_INVALID, "more than 2^31 nodes per GPU");
+  if (!(c->dt > 0) || !(c->dx > 0) || !(c->inv_dx > 0)) return set_err(FFMPM_E_INVALID, "dt, dx, inv_dx must be > 0");
+  return FFMPM_OK;
+}
+
+struct WsLayout {
+  int64_t err_off, grid_off, bin_off, total;
+};
+
+static WsLayout layout(const FfMpmConfig& c, int64_t capacity) {
+  WsLayout L;
+  int64_t nodes = (int64_t)c.n[0] * c.n[1] * c.n[2];
+  L.err_off = 0;
+  L.grid_off = 256;
+  L.bin_off = align_up(L.grid_off + nodes * 4 * (int64_t)elem_size(c), 256);
+  L.total = L.bin_off + bin_workspace_bytes(c.dim, c.n, capacity);
+  return L;
+}
+
+// Definitions below pick up C linkage from their declarations in femflow_mpm.h.
+
+int32_t ffmpm_abi_version(void) { return FFMPM_ABI_VERSION; }
+const char* ffmpm_last_error(void) { return g_last_error; }
+
+int64_t ffmpm_workspace_bytes(const FfMpmConfig* cfg, int64_t capacity) {
+  int rc = validate(cfg);
+  if (rc) return rc;
+  if (capacity < 0) return set_err(FFMPM_E_INVALID, "negative capacity");
+  return layout(*cfg, capacity).total;
+}
+
+int ffmpm_create(const FfMpmConfig* cfg, int32_t device, FfMpmHandle** out) {
+  if (!out) return set_err(FFMPM_E_INVALID, "null out");
+  int rc = validate(cfg);
+  if (rc) return rc;
+  int count = 0;
+  CUDA_TRY(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) return set_err(FFMPM_E_INVALID, "no such CUDA device");
+  FfMpmHandle* h = new (std::nothrow) FfMpmHandle();
+  if (!h) return set_err(FFMPM_E_INVALID, "out of host memory");
+  memset(h, 0, sizeof(*h));
+  h->cfg = *cfg;
+  h->device = device;
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) { delete h; return set_err(FFMPM_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
+  h->sm_count = prop.multiProcessorCount;
+  DevCfg& d = h->dev;
+  d.dim = cfg->dim; d.model = cfg->model;
+  for (int i = 0; i < 3; ++i) {
+    d.n[i] = cfg->n[i]; d.origin[i] = cfg->origin[i]; d.res[i] = cfg->res[i];
+    d.wall_lo[i] = cfg->wall_lo[i]; d.wall_hi[i] = cfg->wall_hi[i];
+  }
+  if (cfg->dim == 2) { d.n[2] = 1; d.origin[2] = 0; d.res[2] = 2; }
+  d.inv_dx = cfg->inv_dx; d.dx = cfg->dx; d.dt = cfg->dt; d.volume = cfg->volume;
+  d.gravity = cfg->gravity; d.hardening = cfg->hardening;
+  d.mass = cfg->mass; d.mu0 = cfg->mu_0; d.lam0 = cfg->lambda_0;
+  h->n_nodes = (int64_t)d.n[0] * d.n[1] * d.n[2];
+  *out = h;
+  return FFMPM_OK;
+}
+
+void ffmpm_destroy(FfMpmHandle* h) { delete h; }
+
+int ffmpm_set_workspace(FfMpmHandle* h, void* workspace, int64_t bytes) {
+  if (!h || !workspace) return set_err(FFMPM_E_INVALID, "null handle/workspace");
+  if (((uintptr_t)workspace & 255) != 0) return set_err(FFMPM_E_INVALID, "workspace must be 256-byte aligned");
+  WsLayout L0 = layout(h->cfg, 0);
+  if (bytes < L0.total) return set_err(FFMPM_E_STATE, "workspace too small for the grid");
+  // largest capacity that fits
+  int64_t lo = 0, hi = (int64_t)1 << 40;
+  while (lo < hi) {
+    int64_t mid = lo + (hi - lo + 1) / 2;
+    if (layout(h->cfg, mid).total <= bytes) lo = mid; else hi = mid - 1;
+  }
+  h->capacity = lo;
+  WsLayout L = layout(h->cfg, lo);
+  h->ws = (char*)workspace;
+  h->ws_bytes = bytes;
+  h->err = (ErrRec*)(h->ws + L.err_off);
+  h->grid = h->ws + L.grid_off;
+  bin_carve(h->bin, h->ws + L.bin_off, h->cfg.dim, h->dev.n, lo);
+  h->binned = false;
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemset(h->err, 0, sizeof(ErrRec)));
+  return FFMPM_OK;
+}
+
+static bool state_ok(const FfMpmHandle* h, const FfMpmState* s) {
+  if (!s->x || !s->v || !s->C || !s->F) return false;
+  if (h->cfg.dim == 2 && !s->Jp) return false;
+  if (h->cfg.model == FFMPM_SNOW && !s->Jp) return false;
+  return true;
+}
+
+int ffmpm_bind_state(FfMpmHandle* h, const FfMpmState* cur, const FfMpmState* alt, int64_t n) {
+  if (!h || !cur) return set_err(FFMPM_E_INVALID, "null handle/state");
+  if (n < 0 || n > cur->stride) return set_err(FFMPM_E_INVALID, "n must be in [0, stride]");
+  if (!state_ok(h, cur)) return set_err(FFMPM_E_INVALID, "state is missing a required plane");
+  h->st[0] = *cur;
+  h->have_alt = false;
+  if (alt) {
+    if (!state_ok(h, alt) || alt->stride != cur->stride) return set_err(FFMPM_E_INVALID, "alt buffer layout mismatch");
+    if ((cur->mass != nullptr) != (alt->mass != nullptr) || (cur->mu0 != nullptr) != (alt->mu0 != nullptr) ||
+        (cur->lam0 != nullptr) != (alt->lam0 != nullptr) || (cur->id != nullptr) != (alt->id != nullptr) ||
+        (cur->Jp != nullptr) != (alt->Jp != nullptr))
+      return set_err(FFMPM_E_INVALID, "alt buffer must carry the same optional planes");
+    h->st[1] = *alt;
+    h->have_alt = true;
+  }
+  h->live = 0;
+  h->n = n;
+  h->binned = false;
+  return FFMPM_OK;
+}
+
+int ffmpm_live_buffer(const FfMpmHandle* h) { return h ? h->live : FFMPM_E_INVALID; }
+int64_t ffmpm_num_particles(const FfMpmHandle* h) { return h ? h->n : FFMPM_E_INVALID; }
+int ffmpm_set_num_particles(FfMpmHandle* h, int64_t n) {
+  if (!h || n < 0 || n > h->st[0].stride) return set_err(FFMPM_E_INVALID, "bad particle count");
+  h->n = n;
+  h->binned = false;
+  return FFMPM_OK;
+}
+
+template <typename T>
+static StateView<T> view(const FfMpmState& s) {
+  StateView<T> v;
+  v.x = (T*)s.x; v.v = (T*)s.v; v.C = (T*)s.C; v.F = (T*)s.F; v.Jp = (T*)s.Jp;
+  v.mass = (T*)s.mass; v.mu0 = (T*)s.mu0; v.lam0 = (T*)s.lam0; v.id = s.id; v.stride = s.stride;
+  return v;
+}
+
+static int ready(FfMpmHandle* h) {
+  if (!h) return set_err(FFMPM_E_INVALID, "null handle");
+  if (!h->ws) return set_err(FFMPM_E_STATE, "workspace not set");
+  if (!h->st[0].x) return set_err(FFMPM_E_STATE, "state not bound");
+  cudaError_t e = cudaSetDevice(h->device);  // callable from any host thread (simulation.py:117)
+  if (e != cudaSuccess) return set_err(FFMPM_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  return FFMPM_OK;
+}
+
+static int check_launch(FfMpmHandle* h, int n_launches) {
+  h->launches += n_launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_err(FFMPM_E_CUDA, "kernel launch: %s", cudaGetErrorString(e));
+  return FFMPM_OK;
+}
+
+int ffmpm_clear_grid(FfMpmHandle* h, void* stream) {
+  int rc = ready(h);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemsetAsync(h->grid, 0, (size_t)h->n_nodes * 4 * elem_size(h->cfg), (cudaStream_t)stream));
+  return FFMPM_OK;
+}
+
+template <typename T>
+static int bin_t(FfMpmHandle* h, cudaStream_t s) {
+  if (h->n > h->capacity) return set_err(FFMPM_E_STATE, "workspace too small for this particle count");
+  int nl = bin_particles<T>(h->dev, view<T>(h->st[h->live]), h->n, h->bin, h->err, s);
+  h->binned = true;
+  return check_launch(h, nl);
+}
+
+int ffmpm_bin(FfMpmHandle* h, void* stream) {
+  int rc = ready(h);
+  if (rc) return rc;
+  if (h->n == 0) { h->binned = true; return FFMPM_OK; }
+  return h->cfg.dtype == FFMPM_F64 ? bin_t<double>(h, (cudaStream_t)stream) : bin_t<float>(h, (cudaStream_t)stream);
+}
+
+template <typename T>
+static int p2g_t(FfMpmHandle* h, cudaStream_t s) {
+  StateView<T> sv = view<T>(h->st[h->live]);
+  int mode = h->cfg.p2g_mode;
+  if (mode == FFMPM_P2G_AUTO) mode = (h->binned && h->cfg.dim == 3) ? FFMPM_P2G_TILED : FFMPM_P2G_SCATTER;
+  if (mode == FFMPM_P2G_TILED) {
+    if (h->cfg.dim != 3) return set_err(FFMPM_E_INVALID, "tiled P2G is 3D only (2D uses the scatter kernel)");
+    if (!h->binned) return set_err(FFMPM_E_STATE, "tiled P2G needs ffmpm_bin first");
+    int nl = p2g_tiled<T>(h->dev, sv, h->n, h->bin, (T*)h->grid, h->err, h->sm_count, s);
+    return check_launch(h, nl);
+  }
+  unsigned blocks = (unsigned)((h->n + 127) / 128);
+  if (h->cfg.dim == 3)
+    p2g_scatter3_kernel<T><<<blocks, 128, 0, s>>>(h->dev, sv, h->n, (T*)h->grid, h->err);
+  else
+    p2g_scatter2_kernel<T><<<blocks, 128, 0, s>>>(h->dev, sv, h->n, (T*)h->grid, h->err);
+  return check_launch(h, 1);
+}
+
+int ffmpm_p2g(FfMpmHandle* h, void* stream) {
+  int rc = ready(h);
+  if (rc) return rc;
+  if (h->n == 0) return FFMPM_OK;
+  return h->cfg.dtype == FFMPM_F64 ? p2g_t<double>(h, (cudaStream_t)stream) : p2g_t<float>(h, (cudaStream_t)stream);
+}
+
+template <typename T>
+static int grid_op_t(FfMpmHandle* h, cudaStream_t s) {
+  unsigned blocks = (unsigned)((h->n_nodes + 255) / 256);
+  if (h->cfg.dim == 3)
+    grid_op3_kernel<T><<<blocks, 256, 0, s>>>(h->dev, (T*)h->grid, h->n_nodes);
+  else
+    grid_op2_kernel<T><<<blocks, 256, 0, s>>>(h->dev, (T*)h->grid, h->n_nodes);
+  return check_launch(h, 1);
+}
+
+int ffmpm_grid_op(FfMpmHandle* h, void* stream) {
+  int rc = ready(h);
+  if (rc) return rc;
+  return h->cfg.dtype == FFMPM_F64 ? grid_op_t<double>(h, (cudaStream_t)stream) : grid_op_t<float>(h, (cudaStream_t)stream);
+}
+
+template <typename T>
+static int g2p_t(FfMpmHandle* h, cudaStream_t s) {
+  StateView<T> sv = view<T>(h->st[h->live]);
+  if (h->binned && h->have_alt && h->cfg.dim == 3) {
+    // binned: gather through the permutation, write back in binned order into the other buffer
+    StateView<T> dst = view<T>(h->st[h->live ^ 1]);
+    int nl = g2p_tiled<T>(h->dev, sv, dst, h->n, h->bin, (const T*)h->grid, h->err, h->sm_count, s);
+    h->live ^= 1;
+    h->binned = false;  // positions moved: keys are stale
+    return check_launch(h, nl);
+  }
+  unsigned blocks = (unsigned)((h->n + 127) / 128);
+  if (h->cfg.dim == 3)
+    g2p_gather3_kernel<T><<<blocks, 128, 0, s>>>(h->dev, sv, h->n, (const T*)h->grid, h->err);
+  else
+    g2p_gather2_kernel<T><<<blocks, 128, 0, s>>>(h->dev, sv, h->n, (const T*)h->grid, h->err);
+  h->binned = false;
+  return check_launch(h, 1);
+}
+
+int ffmpm_g2p(FfMpmHandle* h, void* stream) {
+  int rc = ready(h);
+  if (rc) return rc;
+  if (h->cfg.dim == 3 && h->cfg.model == FFMPM_SNOW)
+    return set_err(FFMPM_E_INVALID,
+                   "3D snow G2P is not reproducible: three_d/g2p.py:55 multiplies by Vh^T, which depends on LAPACK's "
+                   "singular-vector signs (unreachable from solve_mls_mpm_3d, mls_mpm.py:58)");
+  if (h->n == 0) return FFMPM_OK;
+  return h->cfg.dtype == FFMPM_F64 ? g2p_t<double>(h, (cudaStream_t)stream) : g2p_t<float>(h, (cudaStream_t)stream);
+}
+
+int ffmpm_substep(FfMpmHandle* h, int32_t n_substeps, void* stream) {
+  int rc = ready(h);
+  if (rc) return rc;
+  for (int32_t it = 0; it < n_substeps; ++it) {
+    if ((rc = ffmpm_clear_grid(h, stream))) return rc;
+    if (h->cfg.dim == 3 && h->have_alt && h->cfg.p2g_mode != FFMPM_P2G_SCATTER) {
+      if ((rc = ffmpm_bin(h, stream))) return rc;
+    }
+    if ((rc = ffmpm_p2g(h, stream))) return rc;
+    if ((rc = ffmpm_grid_op(h, stream))) return rc;
+    if ((rc = ffmpm_g2p(h, stream))) return rc;
+  }
+  return FFMPM_OK;
+}
+
+int ffmpm_grid_ptr(FfMpmHandle* h, void** grid) {
+  if (!h || !grid || !h->ws) return set_err(FFMPM_E_STATE, "workspace not set");
+  *grid = h->grid;
+  return FFMPM_OK;
+}
+
+int ffmpm_bin_ptrs(FfMpmHandle* h, int32_t** keys, int32_t** perm, int32_t** cell_offsets, int64_t* n_cells) {
+  if (!h || !h->ws) return set_err(FFMPM_E_STATE, "workspace not set");
+  if (keys) *keys = h->bin.keys;
+  if (perm) *perm = h->bin.perm;
+  if (cell_offsets) *cell_offsets = h->bin.cell_off;
+  if (n_cells) *n_cells = h->bin.n_cells;
+  return FFMPM_OK;
+}
+
+int ffmpm_poll_error(FfMpmHandle* h, void* stream, int32_t* code, int64_t* n_oob) {
+  int rc = ready(h);
+  if (rc) return rc;
+  ErrRec rec;
+  CUDA_TRY(cudaMemcpyAsync(&rec, h->err, sizeof(rec), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  if (rec.code != 0 || rec.n_oob != 0) CUDA_TRY(cudaMemsetAsync(h->err, 0, sizeof(rec), (cudaStream_t)stream));
+  if (code) *code = (int32_t)rec.code;
+  if (n_oob) *n_oob = (int64_t)rec.n_oob;
+  if (rec.n_oob) return set_err(FFMPM_E_OOB, "particle stencil left the grid");
+  return FFMPM_OK;
+}
+
+template <typename T>
+__global__ void snapshot_kernel(StateView<T> s, long long n, int dim, double coeff, double* __restrict__ out) {
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  long long dst = s.id ? (long long)s.id[p] : p;
+  for (int c = 0; c < dim; ++c) out[dst * dim + c] = (double)s.x[c * s.stride + p] / coeff;
+}
+
+int ffmpm_snapshot(FfMpmHandle* h, double coeff, double* out, void* stream) {
+  int rc = ready(h);
+  if (rc) return rc;
+  if (!out || coeff == 0.0) return set_err(FFMPM_E_INVALID, "bad snapshot arguments");
+  if (h->n == 0) return FFMPM_OK;
+  unsigned blocks = (unsigned)((h->n + 255) / 256);
+  // particle.py:32 divides by coeff (x / coeff != x * (1/coeff) in general): divide on the device too
+  if (h->cfg.dtype == FFMPM_F64)
+    snapshot_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>(view<double>(h->st[h->live]), h->n, h->cfg.dim, coeff, out);
+  else
+    snapshot_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(view<float>(h->st[h->live]), h->n, h->cfg.dim, coeff, out);
+  return check_launch(h, 1);
+}
+
+int64_t ffmpm_launch_count(const FfMpmHandle* h) { return h ? h->launches : 0; }
+

@@ -1,0 +1,250 @@
+// Cell binning: a counting sort of the particles by the cell of their base node
+// (three_d/p2g.py:50 `base_coord`), once per substep.
+//
+// Key layout (tile-major): the base cells are grouped into tiles of 4x4x4 (3D) or
+// 8x8 (2D) cells = 64 cells, key = tile_id * 64 + cell_in_tile, so that one CTA of
+// the tiled P2G/G2P kernels owns one contiguous run of binned particles.  Particles
+// whose stencil would leave the grid get key = n_cells (a trailing bin) and are
+// reported through the error record.
+//
+// Passes: (1) key + warp-aggregated histogram, which also yields each particle's
+// rank inside its cell; (2) exclusive scan of the histogram (reduce / scan of block
+// sums / downsweep); (3) active-tile list; (4) perm[offset[key] + rank] = p.
+#pragma once
+#include "mpm_common.cuh"
+
+namespace ffmpm {
+
+constexpr int TILE3 = 4;   // cells per tile edge, 3D
+constexpr int TILE2 = 8;   // cells per tile edge, 2D
+constexpr int TILE_CELLS = 64;
+constexpr int SCAN_THREADS = 512;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+struct BinBuffers {
+  int32_t* counters;     // [16]: 0 = n_active_tiles, 1 = p2g work counter, 2 = g2p work counter
+  int32_t* cell_count;   // [n_cells + 2] histogram, bin n_cells = out-of-grid
+  int32_t* cell_off;     // [n_cells + 2] exclusive scan of cell_count
+  int32_t* block_sums;   // [n_scan_blocks + 1]
+  int32_t* active_tiles; // [n_tiles]
+  int32_t* keys;         // [capacity]
+  int32_t* rank;         // [capacity]
+  int32_t* perm;         // [capacity]
+  int tiles[3];
+  int n_tiles;
+  int n_cells;
+  int n_scan_blocks;
+  int64_t capacity;
+};
+
+inline void bin_geometry(int dim, const int* n, int* tiles, int& n_tiles, int& n_cells) {
+  const int te = dim == 3 ? TILE3 : TILE2;
+  n_tiles = 1;
+  for (int d = 0; d < 3; ++d) {
+    if (d < dim) {
+      int nb = n[d] - 2;  // valid base cells per axis: 0 .. n-3
+      tiles[d] = (nb + te - 1) / te;
+    } else {
+      tiles[d] = 1;
+    }
+    n_tiles *= tiles[d];
+  }
+  n_cells = n_tiles * TILE_CELLS;
+}
+
+inline int64_t bin_a256(int64_t v) { return (v + 255) / 256 * 256; }
+
+inline int64_t bin_workspace_bytes(int dim, const int* n, int64_t capacity) {
+  int tiles[3], n_tiles, n_cells;
+  bin_geometry(dim, n, tiles, n_tiles, n_cells);
+  int n_scan_blocks = (n_cells + 2 + SCAN_TILE - 1) / SCAN_TILE;
+  int64_t b = 0;
+  b += bin_a256(16 * 4);
+  b += bin_a256((int64_t)(n_cells + 2) * 4) * 2;
+  b += bin_a256((int64_t)(n_scan_blocks + 1) * 4);
+  b += bin_a256((int64_t)n_tiles * 4);
+  b += bin_a256(capacity * 4) * 3;
+  return b;
+}
+
+inline void bin_carve(BinBuffers& B, char* base, int dim, const int* n, int64_t capacity) {
+  bin_geometry(dim, n, B.tiles, B.n_tiles, B.n_cells);
+  B.n_scan_blocks = (B.n_cells + 2 + SCAN_TILE - 1) / SCAN_TILE;
+  B.capacity = capacity;
+  char* p = base;
+  B.counters = (int32_t*)p; p += bin_a256(16 * 4);
+  // counters and cell_count are contiguous so that one memset clears both
+  B.cell_count = (int32_t*)p; p += bin_a256((int64_t)(B.n_cells + 2) * 4);
+  B.cell_off = (int32_t*)p; p += bin_a256((int64_t)(B.n_cells + 2) * 4);
+  B.block_sums = (int32_t*)p; p += bin_a256((int64_t)(B.n_scan_blocks + 1) * 4);
+  B.active_tiles = (int32_t*)p; p += bin_a256((int64_t)B.n_tiles * 4);
+  B.keys = (int32_t*)p; p += bin_a256(capacity * 4);
+  B.rank = (int32_t*)p; p += bin_a256(capacity * 4);
+  B.perm = (int32_t*)p; p += bin_a256(capacity * 4);
+}
+
+// Tile-major key of a LOCAL base cell.
+__device__ __forceinline__ int bin_key3(int bx, int by, int bz, int ty, int tz) {
+  int tile = ((bx >> 2) * ty + (by >> 2)) * tz + (bz >> 2);
+  return tile * TILE_CELLS + ((bx & 3) << 4) + ((by & 3) << 2) + (bz & 3);
+}
+__device__ __forceinline__ int bin_key2(int bx, int by, int ty) {
+  int tile = (bx >> 3) * ty + (by >> 3);
+  return tile * TILE_CELLS + ((bx & 7) << 3) + (by & 7);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bin_count_kernel(DevCfg cfg, StateView<T> s, long long n, BinBuffers B) {
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int key = -1;
+  if (p < n) {
+    const long long st = s.stride;
+    int b[3] = {0, 0, 0};
+    bool ok = true;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      if (d < cfg.dim) {
+        T xs = s.x[d * st + p];
+        T fx;
+        int g;
+        base_fx(xs, cfg.inv_dx, g, fx);
+        b[d] = g - cfg.origin[d];
+        ok = ok && !isnan((double)xs) && b[d] >= 0 && b[d] + 2 < cfg.n[d];
+      }
+    }
+    if (!ok)
+      key = B.n_cells;
+    else
+      key = cfg.dim == 3 ? bin_key3(b[0], b[1], b[2], B.tiles[1], B.tiles[2]) : bin_key2(b[0], b[1], B.tiles[1]);
+    B.keys[p] = key;
+  }
+  // warp-aggregated histogram: one atomic per distinct key per warp; lanes of a group
+  // take consecutive ranks in lane order
+  unsigned lane = threadIdx.x & 31;
+  unsigned peers = __match_any_sync(0xffffffffu, key);
+  if (key >= 0) {
+    int leader = __ffs(peers) - 1;
+    int base = 0;
+    if ((int)lane == leader) base = atomicAdd(&B.cell_count[key], __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    B.rank[p] = base + __popc(peers & ((1u << lane) - 1u));
+  }
+}
+
+// ---- exclusive scan of cell_count[0 .. m) into cell_off, m = n_cells + 2 ----
+__device__ __forceinline__ int block_exclusive_scan(int v, int* total_out) {
+  __shared__ int warp_sums[32];
+  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= (unsigned)o) inc += t;
+  }
+  if (lane == 31) warp_sums[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    int nw = (blockDim.x + 31) >> 5;
+    int w = (int)lane < nw ? warp_sums[lane] : 0;
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= (unsigned)o) winc += t;
+    }
+    warp_sums[lane] = winc - w;  // exclusive
+    if ((int)lane == nw - 1 && total_out) *total_out = winc;
+  }
+  __syncthreads();
+  int r = warp_sums[wid] + inc - v;
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const int32_t* __restrict__ in, int m,
+                                                                   int32_t* __restrict__ block_sums) {
+  __shared__ int total;
+  int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  int sum = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i)
+    if (base + i < m) sum += in[base + i];
+  block_exclusive_scan(sum, &total);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) scan_block_sums_kernel(int32_t* __restrict__ block_sums, int nb) {
+  __shared__ int total;
+  int carry = 0;
+  for (int start = 0; start < nb; start += 1024) {
+    int i = start + threadIdx.x;
+    int v = i < nb ? block_sums[i] : 0;
+    int ex = block_exclusive_scan(v, &total);
+    if (i < nb) block_sums[i] = carry + ex;
+    carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) block_sums[nb] = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_downsweep_kernel(const int32_t* __restrict__ in, int m,
+                                                                      const int32_t* __restrict__ block_sums,
+                                                                      int32_t* __restrict__ out) {
+  int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  int v[SCAN_ITEMS];
+  int sum = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    v[i] = base + i < m ? in[base + i] : 0;
+    sum += v[i];
+  }
+  int ex = block_exclusive_scan(sum, nullptr) + block_sums[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    if (base + i < m) out[base + i] = ex;
+    ex += v[i];
+  }
+}
+
+// Compact list of tiles that hold at least one particle (nearly ordered: one atomic per warp).
+__global__ void __launch_bounds__(256) active_tiles_kernel(BinBuffers B) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  bool act = false;
+  if (t < B.n_tiles) act = B.cell_off[(t + 1) * TILE_CELLS] > B.cell_off[t * TILE_CELLS];
+  unsigned m = __ballot_sync(0xffffffffu, act);
+  if (m) {
+    unsigned lane = threadIdx.x & 31;
+    int leader = __ffs(m) - 1;
+    int base = 0;
+    if ((int)lane == leader) base = atomicAdd(&B.counters[0], __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (act) B.active_tiles[base + __popc(m & ((1u << lane) - 1u))] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) bin_scatter_kernel(long long n, BinBuffers B, ErrRec* err) {
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  int key = B.keys[p];
+  B.perm[B.cell_off[key] + B.rank[p]] = (int)p;
+  if (key == B.n_cells) atomicAdd(&err->n_oob, 1ULL);
+}
+
+// Returns the number of kernel launches issued.
+template <typename T>
+int bin_particles(const DevCfg& cfg, const StateView<T>& s, long long n, BinBuffers& B, ErrRec* err, cudaStream_t st) {
+  const int m = B.n_cells + 2;
+  // counters (16 ints, 256 B slot) + histogram in one clear
+  cudaMemsetAsync(B.counters, 0, (size_t)((char*)(B.cell_count + m) - (char*)B.counters), st);
+  unsigned pb = (unsigned)((n + 255) / 256);
+  bin_count_kernel<T><<<pb, 256, 0, st>>>(cfg, s, n, B);
+  scan_reduce_kernel<<<B.n_scan_blocks, SCAN_THREADS, 0, st>>>(B.cell_count, m, B.block_sums);
+  scan_block_sums_kernel<<<1, 1024, 0, st>>>(B.block_sums, B.n_scan_blocks);
+  scan_downsweep_kernel<<<B.n_scan_blocks, SCAN_THREADS, 0, st>>>(B.cell_count, m, B.block_sums, B.cell_off);
+  active_tiles_kernel<<<(B.n_tiles + 255) / 256, 256, 0, st>>>(B);
+  bin_scatter_kernel<<<pb, 256, 0, st>>>(n, B, err);
+  return 6;
+}
+
+}  // namespace ffmpm

@@ -1,0 +1,77 @@
+// Shared device-side types for the MPM kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mpm_math.cuh"
+
+namespace ffmpm {
+
+// Device copy of FfMpmConfig (passed by value as a kernel argument).
+struct DevCfg {
+  int dim, model;
+  int n[3], origin[3], res[3], wall_lo[3], wall_hi[3];
+  double inv_dx, dx, dt, volume, gravity, hardening;
+  double mass, mu0, lam0;
+};
+
+template <typename T>
+struct StateView {
+  T* x; T* v; T* C; T* F; T* Jp; T* mass; T* mu0; T* lam0;
+  int* id;
+  long long stride;
+};
+
+// Sticky error record in the workspace: [0] = code, [1] = number of out-of-grid particles.
+struct ErrRec {
+  unsigned long long code;
+  unsigned long long n_oob;
+};
+
+// base = trunc(x*inv_dx - 0.5) (C cast == numpy astype(int64): toward zero, quirk 1)
+// and fx = x*inv_dx - base, both evaluated in fp64 from the stored position so the
+// binning is bit-exact with the fp64 reference for any grid resolution (quirk 11).
+template <typename T>
+__device__ __forceinline__ void base_fx(T xs, double inv_dx, int& base, T& fx) {
+  double s = (double)xs * inv_dx;
+  long long b = (long long)(s - 0.5);
+  // clamp only to keep the int conversion defined for wild values; OOB is flagged by the caller
+  if (b > 1000000000LL) b = 1000000000LL;
+  if (b < -1000000000LL) b = -1000000000LL;
+  base = (int)b;
+  fx = (T)(s - (double)b);
+}
+
+// Quadratic B-spline weights (three_d/p2g.py:55).
+template <typename T>
+__device__ __forceinline__ void bspline(T fx, T& w0, T& w1, T& w2) {
+  T a = (T)1.5 - fx, b = fx - (T)1.0, c = fx - (T)0.5;
+  w0 = (T)0.5 * a * a;
+  w1 = (T)0.75 - b * b;
+  w2 = (T)0.5 * c * c;
+}
+
+// One vector reduction per node: {mom_x, mom_y, mom_z, mass} += val.
+__device__ __forceinline__ void red_add4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+__device__ __forceinline__ void red_add4(double* addr, double a, double b, double c, double d) {
+  atomicAdd(addr + 0, a);
+  atomicAdd(addr + 1, b);
+  atomicAdd(addr + 2, c);
+  atomicAdd(addr + 3, d);
+}
+
+template <typename T> struct Vec4;
+template <> struct Vec4<float> { using type = float4; };
+template <> struct Vec4<double> { using type = double4; };
+
+__device__ __forceinline__ float4 ld_node(const float* g) { return __ldg(reinterpret_cast<const float4*>(g)); }
+__device__ __forceinline__ double4 ld_node(const double* g) {
+  double2 a = __ldg(reinterpret_cast<const double2*>(g));
+  double2 b = __ldg(reinterpret_cast<const double2*>(g) + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
+}
+
+}  // namespace ffmpm

@@ -1,0 +1,346 @@
+// Direct (unbinned) kernels: one thread per particle / per node.  These are the
+// order-independent baseline of the path -- used for state that has not been
+// binned, for the fp64 build, and as the in-library cross-check of the tiled
+// kernels.  Reference loops: three_d/p2g.py:49-80, three_d/grid_op.py:27-47,
+// three_d/g2p.py:21-59 and the two_d/ equivalents.
+#pragma once
+#include "mpm_common.cuh"
+
+namespace ffmpm {
+
+// ----------------------------------------------------------------------------
+// Per-particle P2G payload, shared by the scatter and the tiled kernels.
+// ----------------------------------------------------------------------------
+template <typename T>
+struct P2GParticle3 {
+  int bx, by, bz;       // LOCAL base node
+  T fx, fy, fz;
+  T mvx, mvy, mvz, m;   // mass * v, mass
+  T a00, a01, a02, a10, a11, a12, a20, a21, a22;  // affine = stress + mass*C
+  bool ok;
+};
+
+template <typename T>
+__device__ __forceinline__ P2GParticle3<T> p2g_prepare3(const DevCfg& cfg, const StateView<T>& s, long long p) {
+  P2GParticle3<T> q;
+  const long long st = s.stride;
+  T x0 = s.x[p], x1 = s.x[st + p], x2 = s.x[2 * st + p];
+  int gx, gy, gz;
+  base_fx(x0, cfg.inv_dx, gx, q.fx);
+  base_fx(x1, cfg.inv_dx, gy, q.fy);
+  base_fx(x2, cfg.inv_dx, gz, q.fz);
+  q.bx = gx - cfg.origin[0]; q.by = gy - cfg.origin[1]; q.bz = gz - cfg.origin[2];
+  // utils.py:138-150 with res = G: base < 0 or base + 2 >= G  -> RuntimeError
+  q.ok = !(isnan((double)x0) || isnan((double)x1) || isnan((double)x2)) &&
+         q.bx >= 0 && q.by >= 0 && q.bz >= 0 && q.bx + 2 < cfg.n[0] && q.by + 2 < cfg.n[1] && q.bz + 2 < cfg.n[2];
+  if (!q.ok) return q;
+  double mass = s.mass ? (double)s.mass[p] : cfg.mass;
+  double mu = (s.mu0 ? (double)s.mu0[p] : cfg.mu0);
+  double lam = (s.lam0 ? (double)s.lam0[p] : cfg.lam0);
+  double e = cfg.hardening;                       // constant_hardening: a plain multiplier (quirk 8)
+  if (cfg.model == 1) e = exp(cfg.hardening * (1.0 - (double)s.Jp[p]));  // snow_hardening, utils.py:48
+  mu *= e; lam *= e;
+  Mat3<double> F, C;
+  F.a00 = s.F[0 * st + p]; F.a01 = s.F[1 * st + p]; F.a02 = s.F[2 * st + p];
+  F.a10 = s.F[3 * st + p]; F.a11 = s.F[4 * st + p]; F.a12 = s.F[5 * st + p];
+  F.a20 = s.F[6 * st + p]; F.a21 = s.F[7 * st + p]; F.a22 = s.F[8 * st + p];
+  C.a00 = s.C[0 * st + p]; C.a01 = s.C[1 * st + p]; C.a02 = s.C[2 * st + p];
+  C.a10 = s.C[3 * st + p]; C.a11 = s.C[4 * st + p]; C.a12 = s.C[5 * st + p];
+  C.a20 = s.C[6 * st + p]; C.a21 = s.C[7 * st + p]; C.a22 = s.C[8 * st + p];
+  double k = (cfg.dt * cfg.volume) * (4.0 * cfg.inv_dx * cfg.inv_dx);
+  Mat3<double> A = fixed_corotated_affine3(F, C, mu, lam, mass, k);
+  q.a00 = (T)A.a00; q.a01 = (T)A.a01; q.a02 = (T)A.a02;
+  q.a10 = (T)A.a10; q.a11 = (T)A.a11; q.a12 = (T)A.a12;
+  q.a20 = (T)A.a20; q.a21 = (T)A.a21; q.a22 = (T)A.a22;
+  q.m = (T)mass;
+  q.mvx = (T)(mass * (double)s.v[p]); q.mvy = (T)(mass * (double)s.v[st + p]); q.mvz = (T)(mass * (double)s.v[2 * st + p]);
+  return q;
+}
+
+template <typename T>
+struct P2GParticle2 {
+  int bx, by;
+  T fx, fy;
+  T mvx, mvy, m;
+  T a00, a01, a10, a11;
+  bool ok;
+};
+
+template <typename T>
+__device__ __forceinline__ P2GParticle2<T> p2g_prepare2(const DevCfg& cfg, const StateView<T>& s, long long p) {
+  P2GParticle2<T> q;
+  const long long st = s.stride;
+  T x0 = s.x[p], x1 = s.x[st + p];
+  int gx, gy;
+  base_fx(x0, cfg.inv_dx, gx, q.fx);
+  base_fx(x1, cfg.inv_dx, gy, q.fy);
+  q.bx = gx - cfg.origin[0]; q.by = gy - cfg.origin[1];
+  // The 2D reference has no bounds check (UB there); we flag and skip instead.
+  q.ok = !(isnan((double)x0) || isnan((double)x1)) && q.bx >= 0 && q.by >= 0 && q.bx + 2 < cfg.n[0] && q.by + 2 < cfg.n[1];
+  if (!q.ok) return q;
+  double mass = s.mass ? (double)s.mass[p] : cfg.mass;
+  double mu = (s.mu0 ? (double)s.mu0[p] : cfg.mu0);
+  double lam = (s.lam0 ? (double)s.lam0[p] : cfg.lam0);
+  double e = cfg.hardening;
+  if (cfg.model == 1) e = exp(cfg.hardening * (1.0 - (double)s.Jp[p]));
+  mu *= e; lam *= e;
+  Mat2<double> F, C;
+  F.a00 = s.F[p]; F.a01 = s.F[st + p]; F.a10 = s.F[2 * st + p]; F.a11 = s.F[3 * st + p];
+  C.a00 = s.C[p]; C.a01 = s.C[st + p]; C.a10 = s.C[2 * st + p]; C.a11 = s.C[3 * st + p];
+  double k = (cfg.dt * cfg.volume) * (4.0 * cfg.inv_dx * cfg.inv_dx);
+  Mat2<double> A = fixed_corotated_affine2(F, C, mu, lam, mass, k);
+  q.a00 = (T)A.a00; q.a01 = (T)A.a01; q.a10 = (T)A.a10; q.a11 = (T)A.a11;
+  q.m = (T)mass;
+  q.mvx = (T)(mass * (double)s.v[p]); q.mvy = (T)(mass * (double)s.v[st + p]);
+  return q;
+}
+
+// ----------------------------------------------------------------------------
+// P2G, scatter form
+// ----------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) p2g_scatter3_kernel(DevCfg cfg, StateView<T> s, long long n, T* __restrict__ grid,
+                                                           ErrRec* err) {
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  P2GParticle3<T> q = p2g_prepare3(cfg, s, p);
+  if (!q.ok) { atomicAdd(&err->n_oob, 1ULL); return; }
+  T wx[3], wy[3], wz[3];
+  bspline(q.fx, wx[0], wx[1], wx[2]);
+  bspline(q.fy, wy[0], wy[1], wy[2]);
+  bspline(q.fz, wz[0], wz[1], wz[2]);
+  const T dx = (T)cfg.dx;
+  const long long ny = cfg.n[1], nz = cfg.n[2];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    T dpx = ((T)i - q.fx) * dx;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      T dpy = ((T)j - q.fy) * dx;
+      T wij = wx[i] * wy[j];
+      T* row = grid + (((long long)(q.bx + i) * ny + (q.by + j)) * nz + q.bz) * 4;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        T dpz = ((T)k - q.fz) * dx;
+        T w = wij * wz[k];
+        T mx = q.mvx + (q.a00 * dpx + q.a01 * dpy + q.a02 * dpz);
+        T my = q.mvy + (q.a10 * dpx + q.a11 * dpy + q.a12 * dpz);
+        T mz = q.mvz + (q.a20 * dpx + q.a21 * dpy + q.a22 * dpz);
+        red_add4(row + 4 * k, w * mx, w * my, w * mz, w * q.m);
+      }
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) p2g_scatter2_kernel(DevCfg cfg, StateView<T> s, long long n, T* __restrict__ grid,
+                                                           ErrRec* err) {
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  P2GParticle2<T> q = p2g_prepare2(cfg, s, p);
+  if (!q.ok) { atomicAdd(&err->n_oob, 1ULL); return; }
+  T wx[3], wy[3];
+  bspline(q.fx, wx[0], wx[1], wx[2]);
+  bspline(q.fy, wy[0], wy[1], wy[2]);
+  const T dx = (T)cfg.dx;
+  const long long ny = cfg.n[1];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    T dpx = ((T)i - q.fx) * dx;
+    T* row = grid + ((long long)(q.bx + i) * ny + q.by) * 4;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      T dpy = ((T)j - q.fy) * dx;
+      T w = wx[i] * wy[j];
+      T mx = q.mvx + (q.a00 * dpx + q.a01 * dpy);
+      T my = q.mvy + (q.a10 * dpx + q.a11 * dpy);
+      red_add4(row + 4 * j, w * mx, w * my, w * q.m, (T)0);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// Grid update fused with the boundary projection
+// ----------------------------------------------------------------------------
+// 3D (three_d/grid_op.py:25-47): v = mom/mass, v.y += dt*g, clamp to +-0.9 dx/dt,
+// then zero component d on nodes with global index I[d] < 1 or I[d] >= R-1 (quirk 5).
+template <typename T>
+__global__ void __launch_bounds__(256) grid_op3_kernel(DevCfg cfg, T* __restrict__ grid, long long n_nodes) {
+  long long node = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (node >= n_nodes) return;
+  using V4 = typename Vec4<T>::type;
+  V4 g = reinterpret_cast<V4*>(grid)[node];
+  // empty node with zero momentum: velocity stays zero under the wall projection
+  if (!(g.w > (T)0) && g.x == (T)0 && g.y == (T)0 && g.z == (T)0) return;
+  int k = (int)(node % cfg.n[2]);
+  long long r = node / cfg.n[2];
+  int j = (int)(r % cfg.n[1]);
+  int i = (int)(r / cfg.n[1]);
+  if (g.w > (T)0) {
+    const T va = (T)(cfg.dx * 0.9 / cfg.dt);
+    const T dtg = (T)(cfg.dt * cfg.gravity);
+    T vx = g.x / g.w, vy = g.y / g.w, vz = g.z / g.w;
+    vy += dtg;
+    g.x = fmin(fmax(vx, -va), va);
+    g.y = fmin(fmax(vy, -va), va);
+    g.z = fmin(fmax(vz, -va), va);
+  }
+  const int boundary = 1;
+  int I0 = i + cfg.origin[0], I1 = j + cfg.origin[1], I2 = k + cfg.origin[2];
+  if (I0 < boundary || I0 >= cfg.res[0] - boundary) g.x = (T)0;
+  if (I1 < boundary || I1 >= cfg.res[1] - boundary) g.y = (T)0;
+  if (I2 < boundary || I2 >= cfg.res[2] - boundary) g.z = (T)0;
+  reinterpret_cast<V4*>(grid)[node] = g;
+}
+
+// 2D (two_d/grid_op.py:13-24): only nodes with mass > 0; walls are f64 predicates on
+// i/R against 0.05 and 1-0.05, evaluated here in f64 exactly as the reference (quirk 6).
+template <typename T>
+__global__ void __launch_bounds__(256) grid_op2_kernel(DevCfg cfg, T* __restrict__ grid, long long n_nodes) {
+  long long node = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (node >= n_nodes) return;
+  using V4 = typename Vec4<T>::type;
+  V4 g = reinterpret_cast<V4*>(grid)[node];
+  if (!(g.z > (T)0)) return;
+  int j = (int)(node % cfg.n[1]);
+  int i = (int)(node / cfg.n[1]);
+  T vx = g.x / g.z, vy = g.y / g.z;
+  vy += (T)(cfg.dt * cfg.gravity);
+  const double boundary = 0.05;
+  double x = (double)(i + cfg.origin[0]) / (double)cfg.res[0];
+  double y = (double)(j + cfg.origin[1]) / (double)cfg.res[1];
+  if (x < boundary || x > 1 - boundary || y > 1 - boundary) { vx = (T)0; vy = (T)0; }
+  if (y < boundary) vy = fmax((T)0, vy);
+  g.x = vx; g.y = vy;
+  reinterpret_cast<V4*>(grid)[node] = g;
+}
+
+// ----------------------------------------------------------------------------
+// G2P, gather form (in place)
+// ----------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) g2p_gather3_kernel(DevCfg cfg, StateView<T> s, long long n, const T* __restrict__ grid,
+                                                          ErrRec* err) {
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const long long st = s.stride;
+  T x0 = s.x[p], x1 = s.x[st + p], x2 = s.x[2 * st + p];
+  int gx, gy, gz;
+  T fx, fy, fz;
+  base_fx(x0, cfg.inv_dx, gx, fx);
+  base_fx(x1, cfg.inv_dx, gy, fy);
+  base_fx(x2, cfg.inv_dx, gz, fz);
+  int bx = gx - cfg.origin[0], by = gy - cfg.origin[1], bz = gz - cfg.origin[2];
+  bool ok = !(isnan((double)x0) || isnan((double)x1) || isnan((double)x2)) && bx >= 0 && by >= 0 && bz >= 0 &&
+            bx + 2 < cfg.n[0] && by + 2 < cfg.n[1] && bz + 2 < cfg.n[2];
+  if (!ok) { atomicAdd(&err->n_oob, 1ULL); return; }
+  T wx[3], wy[3], wz[3];
+  bspline(fx, wx[0], wx[1], wx[2]);
+  bspline(fy, wy[0], wy[1], wy[2]);
+  bspline(fz, wz[0], wz[1], wz[2]);
+  const long long ny = cfg.n[1], nz = cfg.n[2];
+  T vx = 0, vy = 0, vz = 0;
+  T c00 = 0, c01 = 0, c02 = 0, c10 = 0, c11 = 0, c12 = 0, c20 = 0, c21 = 0, c22 = 0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    T dpx = (T)i - fx;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      T dpy = (T)j - fy;
+      T wij = wx[i] * wy[j];
+      const T* row = grid + (((long long)(bx + i) * ny + (by + j)) * nz + bz) * 4;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        T dpz = (T)k - fz;
+        T w = wij * wz[k];
+        auto g = ld_node(row + 4 * k);
+        T ux = w * g.x, uy = w * g.y, uz = w * g.z;
+        vx += ux; vy += uy; vz += uz;
+        c00 += ux * dpx; c01 += ux * dpy; c02 += ux * dpz;
+        c10 += uy * dpx; c11 += uy * dpy; c12 += uy * dpz;
+        c20 += uz * dpx; c21 += uz * dpy; c22 += uz * dpz;
+      }
+    }
+  }
+  const T s4 = (T)(4.0 * cfg.inv_dx);
+  c00 *= s4; c01 *= s4; c02 *= s4; c10 *= s4; c11 *= s4; c12 *= s4; c20 *= s4; c21 *= s4; c22 *= s4;
+  const T dt = (T)cfg.dt;
+  T f00 = s.F[0 * st + p], f01 = s.F[1 * st + p], f02 = s.F[2 * st + p];
+  T f10 = s.F[3 * st + p], f11 = s.F[4 * st + p], f12 = s.F[5 * st + p];
+  T f20 = s.F[6 * st + p], f21 = s.F[7 * st + p], f22 = s.F[8 * st + p];
+  // F <- (I + dt C) F   (three_d/g2p.py:46)
+  T m00 = (T)1 + dt * c00, m01 = dt * c01, m02 = dt * c02;
+  T m10 = dt * c10, m11 = (T)1 + dt * c11, m12 = dt * c12;
+  T m20 = dt * c20, m21 = dt * c21, m22 = (T)1 + dt * c22;
+  s.F[0 * st + p] = m00 * f00 + m01 * f10 + m02 * f20;
+  s.F[1 * st + p] = m00 * f01 + m01 * f11 + m02 * f21;
+  s.F[2 * st + p] = m00 * f02 + m01 * f12 + m02 * f22;
+  s.F[3 * st + p] = m10 * f00 + m11 * f10 + m12 * f20;
+  s.F[4 * st + p] = m10 * f01 + m11 * f11 + m12 * f21;
+  s.F[5 * st + p] = m10 * f02 + m11 * f12 + m12 * f22;
+  s.F[6 * st + p] = m20 * f00 + m21 * f10 + m22 * f20;
+  s.F[7 * st + p] = m20 * f01 + m21 * f11 + m22 * f21;
+  s.F[8 * st + p] = m20 * f02 + m21 * f12 + m22 * f22;
+  s.C[0 * st + p] = c00; s.C[1 * st + p] = c01; s.C[2 * st + p] = c02;
+  s.C[3 * st + p] = c10; s.C[4 * st + p] = c11; s.C[5 * st + p] = c12;
+  s.C[6 * st + p] = c20; s.C[7 * st + p] = c21; s.C[8 * st + p] = c22;
+  s.v[p] = vx; s.v[st + p] = vy; s.v[2 * st + p] = vz;
+  s.x[p] = x0 + dt * vx; s.x[st + p] = x1 + dt * vy; s.x[2 * st + p] = x2 + dt * vz;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) g2p_gather2_kernel(DevCfg cfg, StateView<T> s, long long n, const T* __restrict__ grid,
+                                                          ErrRec* err) {
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const long long st = s.stride;
+  T x0 = s.x[p], x1 = s.x[st + p];
+  int gx, gy;
+  T fx, fy;
+  base_fx(x0, cfg.inv_dx, gx, fx);
+  base_fx(x1, cfg.inv_dx, gy, fy);
+  int bx = gx - cfg.origin[0], by = gy - cfg.origin[1];
+  bool ok = !(isnan((double)x0) || isnan((double)x1)) && bx >= 0 && by >= 0 && bx + 2 < cfg.n[0] && by + 2 < cfg.n[1];
+  if (!ok) { atomicAdd(&err->n_oob, 1ULL); return; }
+  T wx[3], wy[3];
+  bspline(fx, wx[0], wx[1], wx[2]);
+  bspline(fy, wy[0], wy[1], wy[2]);
+  const long long ny = cfg.n[1];
+  T vx = 0, vy = 0, c00 = 0, c01 = 0, c10 = 0, c11 = 0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    T dpx = (T)i - fx;
+    const T* row = grid + ((long long)(bx + i) * ny + by) * 4;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      T dpy = (T)j - fy;
+      T w = wx[i] * wy[j];
+      auto g = ld_node(row + 4 * j);
+      T ux = w * g.x, uy = w * g.y;
+      vx += ux; vy += uy;
+      c00 += ux * dpx; c01 += ux * dpy; c10 += uy * dpx; c11 += uy * dpy;
+    }
+  }
+  const T s4 = (T)(4.0 * cfg.inv_dx);
+  c00 *= s4; c01 *= s4; c10 *= s4; c11 *= s4;
+  const T dt = (T)cfg.dt;
+  T f00 = s.F[p], f01 = s.F[st + p], f10 = s.F[2 * st + p], f11 = s.F[3 * st + p];
+  T m00 = (T)1 + dt * c00, m01 = dt * c01, m10 = dt * c10, m11 = (T)1 + dt * c11;
+  Mat2<double> Fn;
+  Fn.a00 = m00 * f00 + m01 * f10; Fn.a01 = m00 * f01 + m01 * f11;
+  Fn.a10 = m10 * f00 + m11 * f10; Fn.a11 = m10 * f01 + m11 * f11;
+  // two_d/g2p.py:37-47: SVD round trip and Jp update for every model (quirk 7)
+  double old_J = Fn.a00 * Fn.a11 - Fn.a01 * Fn.a10;
+  double det_new;
+  Mat2<double> Fr = svd_roundtrip2(Fn, cfg.model == 1, det_new);
+  if (s.Jp) {
+    double jp = (double)s.Jp[p] * old_J / (det_new + 1e-10);
+    s.Jp[p] = (T)fmin(fmax(jp, 0.6), 20.0);
+  }
+  s.F[p] = (T)Fr.a00; s.F[st + p] = (T)Fr.a01; s.F[2 * st + p] = (T)Fr.a10; s.F[3 * st + p] = (T)Fr.a11;
+  s.C[p] = c00; s.C[st + p] = c01; s.C[2 * st + p] = c10; s.C[3 * st + p] = c11;
+  s.v[p] = vx; s.v[st + p] = vy;
+  s.x[p] = x0 + dt * vx; s.x[st + p] = x1 + dt * vy;
+}
+
+}  // namespace ffmpm

@@ -1,0 +1,168 @@
+// Small dense linear algebra and constitutive math for the MPM kernels.
+// Everything is register-resident (no local arrays with dynamic indexing).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace ffmpm {
+
+template <typename T>
+struct Mat3 {
+  T a00, a01, a02, a10, a11, a12, a20, a21, a22;
+};
+
+template <typename T>
+struct Mat2 {
+  T a00, a01, a10, a11;
+};
+
+template <typename T>
+__device__ __forceinline__ T det3(const Mat3<T>& m) {
+  return m.a00 * (m.a11 * m.a22 - m.a12 * m.a21) - m.a01 * (m.a10 * m.a22 - m.a12 * m.a20) +
+         m.a02 * (m.a10 * m.a21 - m.a11 * m.a20);
+}
+
+// Cofactor matrix cof(X) (so that X^{-T} = cof(X) / det X).
+__device__ __forceinline__ Mat3<double> cofactor3(const Mat3<double>& m) {
+  Mat3<double> c;
+  c.a00 = m.a11 * m.a22 - m.a12 * m.a21;
+  c.a01 = m.a12 * m.a20 - m.a10 * m.a22;
+  c.a02 = m.a10 * m.a21 - m.a11 * m.a20;
+  c.a10 = m.a02 * m.a21 - m.a01 * m.a22;
+  c.a11 = m.a00 * m.a22 - m.a02 * m.a20;
+  c.a12 = m.a01 * m.a20 - m.a00 * m.a21;
+  c.a20 = m.a01 * m.a12 - m.a02 * m.a11;
+  c.a21 = m.a02 * m.a10 - m.a00 * m.a12;
+  c.a22 = m.a00 * m.a11 - m.a01 * m.a10;
+  return c;
+}
+
+// Rotation factor of the polar decomposition F = R S, the unique U*Vh of the SVD
+// the reference takes (numerics/linear_algebra.py:131-132).  Newton iteration
+// X <- (g X + X^{-T} / g) / 2 with determinant scaling while far from orthogonal;
+// converges quadratically, det F < 0 converges to the det = -1 factor exactly as
+// U*Vh does.  F = I returns I exactly.
+__device__ __forceinline__ Mat3<double> polar_rotation3(const Mat3<double>& F, double& detF) {
+  Mat3<double> X = F;
+  Mat3<double> c = cofactor3(X);
+  double det = X.a00 * c.a00 + X.a01 * c.a01 + X.a02 * c.a02;
+  detF = det;
+#pragma unroll 1
+  for (int it = 0; it < 48; ++it) {
+    if (!(fabs(det) > 1e-300)) break;  // singular: R is not unique; keep the last iterate
+    double ad = fabs(det);
+    double g = 1.0;
+    if (ad < 0.7 || ad > 1.4) g = exp(-log(ad) * (1.0 / 3.0));  // |det|^(-1/3)
+    double hg = 0.5 * g;
+    double hi = 0.5 / (g * det);
+    Mat3<double> Y;
+    Y.a00 = hg * X.a00 + hi * c.a00; Y.a01 = hg * X.a01 + hi * c.a01; Y.a02 = hg * X.a02 + hi * c.a02;
+    Y.a10 = hg * X.a10 + hi * c.a10; Y.a11 = hg * X.a11 + hi * c.a11; Y.a12 = hg * X.a12 + hi * c.a12;
+    Y.a20 = hg * X.a20 + hi * c.a20; Y.a21 = hg * X.a21 + hi * c.a21; Y.a22 = hg * X.a22 + hi * c.a22;
+    double d2 = (Y.a00 - X.a00) * (Y.a00 - X.a00) + (Y.a01 - X.a01) * (Y.a01 - X.a01) +
+                (Y.a02 - X.a02) * (Y.a02 - X.a02) + (Y.a10 - X.a10) * (Y.a10 - X.a10) +
+                (Y.a11 - X.a11) * (Y.a11 - X.a11) + (Y.a12 - X.a12) * (Y.a12 - X.a12) +
+                (Y.a20 - X.a20) * (Y.a20 - X.a20) + (Y.a21 - X.a21) * (Y.a21 - X.a21) +
+                (Y.a22 - X.a22) * (Y.a22 - X.a22);
+    X = Y;
+    // quadratic convergence: |Y - R| ~ |Y - X|^2 once g == 1
+    if (g == 1.0 && d2 < 1e-17) break;
+    c = cofactor3(X);
+    det = X.a00 * c.a00 + X.a01 * c.a01 + X.a02 * c.a02;
+  }
+  return X;
+}
+
+// affine = -(dt*vol)*(4 inv_dx^2) * (2 mu (F-R) F^T + lam (J-1) J [on ALL entries]) + mass*C
+// (solvers/mpm/utils.py:120-135; the broadcast of the lambda term is quirk 2).
+__device__ __forceinline__ Mat3<double> fixed_corotated_affine3(const Mat3<double>& F, const Mat3<double>& C,
+                                                                double mu, double lam, double mass,
+                                                                double dt_vol_dinv) {
+  double J;
+  Mat3<double> R = polar_rotation3(F, J);
+  Mat3<double> D;
+  D.a00 = F.a00 - R.a00; D.a01 = F.a01 - R.a01; D.a02 = F.a02 - R.a02;
+  D.a10 = F.a10 - R.a10; D.a11 = F.a11 - R.a11; D.a12 = F.a12 - R.a12;
+  D.a20 = F.a20 - R.a20; D.a21 = F.a21 - R.a21; D.a22 = F.a22 - R.a22;
+  double l = lam * (J - 1.0) * J;
+  double m2 = 2.0 * mu;
+  Mat3<double> A;
+  // (D F^T)[r][c] = sum_k D[r][k] F[c][k]
+  A.a00 = -dt_vol_dinv * (m2 * (D.a00 * F.a00 + D.a01 * F.a01 + D.a02 * F.a02) + l) + mass * C.a00;
+  A.a01 = -dt_vol_dinv * (m2 * (D.a00 * F.a10 + D.a01 * F.a11 + D.a02 * F.a12) + l) + mass * C.a01;
+  A.a02 = -dt_vol_dinv * (m2 * (D.a00 * F.a20 + D.a01 * F.a21 + D.a02 * F.a22) + l) + mass * C.a02;
+  A.a10 = -dt_vol_dinv * (m2 * (D.a10 * F.a00 + D.a11 * F.a01 + D.a12 * F.a02) + l) + mass * C.a10;
+  A.a11 = -dt_vol_dinv * (m2 * (D.a10 * F.a10 + D.a11 * F.a11 + D.a12 * F.a12) + l) + mass * C.a11;
+  A.a12 = -dt_vol_dinv * (m2 * (D.a10 * F.a20 + D.a11 * F.a21 + D.a12 * F.a22) + l) + mass * C.a12;
+  A.a20 = -dt_vol_dinv * (m2 * (D.a20 * F.a00 + D.a21 * F.a01 + D.a22 * F.a02) + l) + mass * C.a20;
+  A.a21 = -dt_vol_dinv * (m2 * (D.a20 * F.a10 + D.a21 * F.a11 + D.a22 * F.a12) + l) + mass * C.a21;
+  A.a22 = -dt_vol_dinv * (m2 * (D.a20 * F.a20 + D.a21 * F.a21 + D.a22 * F.a22) + l) + mass * C.a22;
+  return A;
+}
+
+// 2D: closed-form rotation with the reference's +1e-10 in the norm
+// (numerics/linear_algebra.py:108-113; quirks 3 and 12), stress as utils.py:75-92.
+__device__ __forceinline__ Mat2<double> fixed_corotated_affine2(const Mat2<double>& F, const Mat2<double>& C,
+                                                                double mu, double lam, double mass,
+                                                                double dt_vol_dinv) {
+  double J = F.a00 * F.a11 - F.a01 * F.a10;
+  double x = F.a00 + F.a11;
+  double y = F.a10 - F.a01;
+  double scale = 1.0 / (sqrt(x * x + y * y) + 1e-10);
+  double c = x * scale, s = y * scale;
+  double d00 = F.a00 - c, d01 = F.a01 + s, d10 = F.a10 - s, d11 = F.a11 - c;
+  double l = lam * (J - 1.0) * J;
+  double m2 = 2.0 * mu;
+  Mat2<double> A;
+  A.a00 = -dt_vol_dinv * (m2 * (d00 * F.a00 + d01 * F.a01) + l) + mass * C.a00;
+  A.a01 = -dt_vol_dinv * (m2 * (d00 * F.a10 + d01 * F.a11) + l) + mass * C.a01;
+  A.a10 = -dt_vol_dinv * (m2 * (d10 * F.a00 + d11 * F.a01) + l) + mass * C.a10;
+  A.a11 = -dt_vol_dinv * (m2 * (d10 * F.a10 + d11 * F.a11) + l) + mass * C.a11;
+  return A;
+}
+
+// 2x2 SVD round trip of two_d/g2p.py:37-43: F <- U diag(sig) Vh^T with (U, sig, Vh)
+// LAPACK's SVD and "V.T" applied to what is already Vh.  Measured convention of
+// dgesdd on 2x2 input (tests/golden/quirk2d.npz): U is always a reflection; Vh is a
+// symmetric reflection when det F > 0 (so Vh^T = Vh and the round trip is the
+// identity) and a proper rotation [[c, s], [-s, c]] with (c, s) the principal right
+// singular vector when det F < 0, so that
+//     U S Vh^T = (U S Vh) (Vh^T)^2 = F * Rot(2 theta),
+// which is independent of the sign LAPACK picks for the singular vectors.
+// For `snow` the singular values are first clamped to [1-2.5e-2, 1+7.5e-3]:
+//     U S' Vh = F * (r0 v1 v1^T + r1 v2 v2^T),  r_i = clamp(s_i) / s_i.
+// Returns det of the result through `det_out` (sign follows det F).
+__device__ __forceinline__ Mat2<double> svd_roundtrip2(const Mat2<double>& F, bool snow, double& det_out) {
+  double detF = F.a00 * F.a11 - F.a01 * F.a10;
+  double m00 = F.a00 * F.a00 + F.a10 * F.a10;
+  double m01 = F.a00 * F.a01 + F.a10 * F.a11;
+  double m11 = F.a01 * F.a01 + F.a11 * F.a11;
+  double dm = m00 - m11, om = 2.0 * m01;
+  double h = sqrt(dm * dm + om * om);
+  double c2 = 1.0, s2 = 0.0;
+  if (h > 0.0) { c2 = dm / h; s2 = om / h; }
+  Mat2<double> G = F;
+  det_out = detF;
+  if (snow) {
+    double tr = m00 + m11;
+    double sg0 = sqrt(fmax(0.5 * (tr + h), 0.0)), sg1 = sqrt(fmax(0.5 * (tr - h), 0.0));
+    double c0 = fmin(fmax(sg0, 1.0 - 2.5e-2), 1.0 + 7.5e-3);
+    double c1 = fmin(fmax(sg1, 1.0 - 2.5e-2), 1.0 + 7.5e-3);
+    double r0 = sg0 > 0.0 ? c0 / sg0 : 0.0, r1 = sg1 > 0.0 ? c1 / sg1 : 0.0;
+    // P1 = v1 v1^T = [[(1+c2)/2, s2/2], [s2/2, (1-c2)/2]]
+    double p00 = 0.5 * (1.0 + c2), p01 = 0.5 * s2, p11 = 0.5 * (1.0 - c2);
+    double q00 = r0 * p00 + r1 * (1.0 - p00), q01 = (r0 - r1) * p01, q11 = r0 * p11 + r1 * (1.0 - p11);
+    G.a00 = F.a00 * q00 + F.a01 * q01; G.a01 = F.a00 * q01 + F.a01 * q11;
+    G.a10 = F.a10 * q00 + F.a11 * q01; G.a11 = F.a10 * q01 + F.a11 * q11;
+    det_out = (detF < 0.0 ? -1.0 : 1.0) * c0 * c1;
+  }
+  if (detF < 0.0) {
+    Mat2<double> Hm;
+    Hm.a00 = G.a00 * c2 + G.a01 * s2; Hm.a01 = -G.a00 * s2 + G.a01 * c2;
+    Hm.a10 = G.a10 * c2 + G.a11 * s2; Hm.a11 = -G.a10 * s2 + G.a11 * c2;
+    G = Hm;
+  }
+  return G;
+}
+
+}  // namespace ffmpm

@@ -1,0 +1,283 @@
+"""Host side of the CUDA MPM substep: owns the device tensors (torch is only the
+allocator / stream provider here) and drives the C ABI of include/femflow_mpm.h.
+
+The particle state lives on the GPU as SoA planes (one contiguous row per scalar
+component).  With ``reorder=True`` (3D default) two state buffers are kept and
+every substep G2P writes the particles back in cell order into the other one; the
+``id`` plane remembers each particle's original index so that callers always see
+the reference's fixed particle order.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+_MODEL = {"neo_hookean": N.FFMPM_NEO_HOOKEAN, "snow": N.FFMPM_SNOW}
+_P2G = {"auto": N.FFMPM_P2G_AUTO, "scatter": N.FFMPM_P2G_SCATTER, "tiled": N.FFMPM_P2G_TILED}
+
+
+def _as_tensor(a, dtype, device):
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device, dtype=dtype)
+    return torch.as_tensor(np.ascontiguousarray(a), device=device).to(dtype)
+
+
+class _StateBuffer:
+    """One SoA particle buffer."""
+
+    def __init__(self, dim, cap, dtype, device, per_particle_material, with_id, with_jp):
+        d = dim
+        self.cap = cap
+        self.x = torch.zeros((d, cap), dtype=dtype, device=device)
+        self.v = torch.zeros((d, cap), dtype=dtype, device=device)
+        self.C = torch.zeros((d * d, cap), dtype=dtype, device=device)
+        self.F = torch.zeros((d * d, cap), dtype=dtype, device=device)
+        self.Jp = torch.ones((cap,), dtype=dtype, device=device) if with_jp else None
+        if per_particle_material:
+            self.mass = torch.zeros((cap,), dtype=dtype, device=device)
+            self.mu0 = torch.zeros((cap,), dtype=dtype, device=device)
+            self.lam0 = torch.zeros((cap,), dtype=dtype, device=device)
+        else:
+            self.mass = self.mu0 = self.lam0 = None
+        self.id = torch.arange(cap, dtype=torch.int32, device=device) if with_id else None
+
+    def c_struct(self) -> N.FfMpmState:
+        def p(t):
+            return None if t is None else t.data_ptr()
+        return N.FfMpmState(p(self.x), p(self.v), p(self.C), p(self.F), p(self.Jp), p(self.mass), p(self.mu0),
+                            p(self.lam0), p(self.id), self.cap)
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in
+                   (self.x, self.v, self.C, self.F, self.Jp, self.mass, self.mu0, self.lam0, self.id) if t is not None)
+
+
+class MpmSolver:
+    """GPU-resident MLS-MPM solver for one (slab of a) grid.
+
+    Scalars follow ``solve_mls_mpm_3d`` (reference solvers/mpm/mls_mpm.py:40-53).
+    """
+
+    def __init__(self, dim: int, res, dt: float, volume: float, gravity: float, hardening: float, *,
+                 capacity: int, dx: Optional[float] = None, inv_dx: Optional[float] = None,
+                 model: str = "neo_hookean", dtype: torch.dtype = torch.float32, device="cuda:0",
+                 n_nodes: Optional[Sequence[int]] = None, origin: Sequence[int] = (0, 0, 0),
+                 mass: float = 0.0, mu_0: float = 0.0, lambda_0: float = 0.0,
+                 per_particle_material: Optional[bool] = None, p2g_mode: str = "auto",
+                 reorder: Optional[bool] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("femflow_b200 needs a CUDA device; there is no CPU fallback")
+        self.lib = N.lib()
+        self.dim = int(dim)
+        self.device = torch.device(device)
+        self.dtype = dtype
+        res3 = [int(r) for r in (res if isinstance(res, (list, tuple)) else [res] * self.dim)]
+        while len(res3) < 3:
+            res3.append(2)
+        self.res = res3
+        n3 = list(n_nodes) if n_nodes is not None else [r + 1 for r in res3[:self.dim]]
+        while len(n3) < 3:
+            n3.append(1)
+        self.n = [int(v) for v in n3]
+        self.origin = [int(o) for o in origin] + [0] * (3 - len(origin))
+        self.capacity = int(capacity)
+        self.model = model
+        if per_particle_material is None:
+            per_particle_material = self.dim == 3
+        if reorder is None:
+            reorder = self.dim == 3 and p2g_mode != "scatter"
+        self.reorder = bool(reorder)
+        cfg = N.FfMpmConfig()
+        cfg.dim = self.dim
+        cfg.dtype = N.FFMPM_F64 if dtype == torch.float64 else N.FFMPM_F32
+        cfg.model = _MODEL[model]
+        for i in range(3):
+            cfg.res[i] = self.res[i]
+            cfg.n[i] = self.n[i]
+            cfg.origin[i] = self.origin[i]
+            cfg.wall_lo[i] = 1
+            cfg.wall_hi[i] = 1
+        r0 = self.res[0]
+        cfg.dx = float(dx) if dx is not None else 1.0 / r0
+        cfg.inv_dx = float(inv_dx) if inv_dx is not None else 1.0 / cfg.dx
+        cfg.dt, cfg.volume, cfg.gravity, cfg.hardening = float(dt), float(volume), float(gravity), float(hardening)
+        cfg.mass, cfg.mu_0, cfg.lambda_0 = float(mass), float(mu_0), float(lambda_0)
+        cfg.p2g_mode = _P2G[p2g_mode]
+        self.cfg = cfg
+        self._h = N.H()
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.dev_index = dev_index
+        N.check(self.lib.ffmpm_create(C.byref(cfg), dev_index, C.byref(self._h)))
+        ws_bytes = self.lib.ffmpm_workspace_bytes(C.byref(cfg), self.capacity)
+        if ws_bytes < 0:
+            N.check(int(ws_bytes))
+        with torch.cuda.device(self.device):
+            self.workspace = torch.zeros((ws_bytes + 255) // 256 * 256, dtype=torch.uint8, device=self.device)
+            with_jp = self.dim == 2 or model == "snow"
+            self.buffers = [_StateBuffer(self.dim, self.capacity, dtype, self.device, per_particle_material,
+                                         self.reorder, with_jp)]
+            if self.reorder:
+                self.buffers.append(_StateBuffer(self.dim, self.capacity, dtype, self.device,
+                                                 per_particle_material, True, with_jp))
+        N.check(self.lib.ffmpm_set_workspace(self._h, self.workspace.data_ptr(), self.workspace.numel()))
+        self.num_particles = 0
+        self._bind(0)
+
+    # ------------------------------------------------------------------ #
+    def _bind(self, n: int) -> None:
+        cur = self.buffers[0].c_struct()
+        alt = self.buffers[1].c_struct() if self.reorder else None
+        N.check(self.lib.ffmpm_bind_state(self._h, C.byref(cur), C.byref(alt) if alt is not None else None, n))
+        self.num_particles = n
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self.lib.ffmpm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def live(self) -> _StateBuffer:
+        return self.buffers[self.lib.ffmpm_live_buffer(self._h)]
+
+    def _stream(self, stream=None):
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device)
+        return C.c_void_p(stream.cuda_stream)
+
+    # ------------------------------------------------------------------ #
+    def set_particles(self, x, v=None, F=None, C_=None, Jp=None, mass=None, mu0=None, lam0=None) -> None:
+        """Upload particle state given in the reference's layouts: ``x, v (N, d)``,
+        ``F, C (N, d, d)``, ``Jp (N, 1)``; per-particle ``mass, mu0, lam0 (N,)``."""
+        d = self.dim
+        x = _as_tensor(x, self.dtype, self.device).reshape(-1, d)
+        n = x.shape[0]
+        if n > self.capacity:
+            raise ValueError(f"{n} particles exceed the solver capacity {self.capacity}")
+        b = self.buffers[0]
+        b.x[:, :n] = x.t()
+        b.v[:, :n] = 0 if v is None else _as_tensor(v, self.dtype, self.device).reshape(n, d).t()
+        if F is None:
+            b.F[:, :n] = torch.eye(d, dtype=self.dtype, device=self.device).reshape(d * d, 1)
+        else:
+            b.F[:, :n] = _as_tensor(F, self.dtype, self.device).reshape(n, d * d).t()
+        b.C[:, :n] = 0 if C_ is None else _as_tensor(C_, self.dtype, self.device).reshape(n, d * d).t()
+        if b.Jp is not None:
+            b.Jp[:n] = 1 if Jp is None else _as_tensor(Jp, self.dtype, self.device).reshape(n)
+        if b.mass is not None:
+            for name, val in (("mass", mass), ("mu0", mu0), ("lam0", lam0)):
+                if val is None:
+                    raise ValueError(f"per-particle {name} is required")
+                t = _as_tensor(np.broadcast_to(np.asarray(val, dtype=np.float64), (n,)) if not isinstance(val, torch.Tensor) else val,
+                               self.dtype, self.device).reshape(n)
+                getattr(b, name)[:n] = t
+        if b.id is not None:
+            b.id[:n] = torch.arange(n, dtype=torch.int32, device=self.device)
+        self._bind(n)
+
+    def get_particles(self) -> Dict[str, torch.Tensor]:
+        """State in the ORIGINAL particle order, reference layouts, device tensors."""
+        b = self.live
+        n, d = self.num_particles, self.dim
+        if b.id is not None:
+            inv = torch.empty(n, dtype=torch.int64, device=self.device)
+            inv[b.id[:n].long()] = torch.arange(n, device=self.device)
+        else:
+            inv = slice(None)
+        out = {
+            "x": b.x[:, :n].t()[inv].contiguous(),
+            "v": b.v[:, :n].t()[inv].contiguous(),
+            "F": b.F[:, :n].t()[inv].reshape(n, d, d).contiguous(),
+            "C": b.C[:, :n].t()[inv].reshape(n, d, d).contiguous(),
+        }
+        if b.Jp is not None:
+            out["Jp"] = b.Jp[:n][inv].reshape(n, 1).contiguous()
+        return out
+
+    # ------------------------------------------------------------------ #
+    def clear_grid(self, stream=None):
+        N.check(self.lib.ffmpm_clear_grid(self._h, self._stream(stream)))
+
+    def bin(self, stream=None):
+        N.check(self.lib.ffmpm_bin(self._h, self._stream(stream)))
+
+    def p2g(self, stream=None):
+        N.check(self.lib.ffmpm_p2g(self._h, self._stream(stream)))
+
+    def grid_op(self, stream=None):
+        N.check(self.lib.ffmpm_grid_op(self._h, self._stream(stream)))
+
+    def g2p(self, stream=None):
+        N.check(self.lib.ffmpm_g2p(self._h, self._stream(stream)))
+
+    def substep(self, n_substeps: int = 1, stream=None):
+        N.check(self.lib.ffmpm_substep(self._h, int(n_substeps), self._stream(stream)))
+
+    def make_graph(self, n_substeps: int) -> "torch.cuda.CUDAGraph":
+        """Capture ``n_substeps`` substeps (rounded up to an even count when the state
+        ping-pongs, so that replay starts from the same buffer) in a CUDA graph."""
+        if self.reorder and n_substeps % 2:
+            n_substeps += 1
+        self.graph_substeps = n_substeps
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        before = self.launch_count()
+        with torch.cuda.graph(g):
+            self.substep(n_substeps)
+        self.graph_launches = self.launch_count() - before
+        return g
+
+    def launch_count(self) -> int:
+        return int(self.lib.ffmpm_launch_count(self._h))
+
+    def grid(self) -> torch.Tensor:
+        """Node-major grid ``(nx, ny, nz, 4)`` (view into the workspace)."""
+        ptr = C.c_void_p()
+        N.check(self.lib.ffmpm_grid_ptr(self._h, C.byref(ptr)))
+        off = ptr.value - self.workspace.data_ptr()
+        count = self.n[0] * self.n[1] * self.n[2] * 4
+        es = 8 if self.dtype == torch.float64 else 4
+        return self.workspace[off:off + count * es].view(self.dtype).view(self.n[0], self.n[1], self.n[2], 4)
+
+    def bin_results(self):
+        """(keys per live-order particle, perm, cell_offsets) as int32 device tensors."""
+        k, p, o = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        nc = C.c_int64()
+        N.check(self.lib.ffmpm_bin_ptrs(self._h, C.byref(k), C.byref(p), C.byref(o), C.byref(nc)))
+        base = self.workspace.data_ptr()
+
+        def view(ptr, count):
+            off = ptr.value - base
+            return self.workspace[off:off + 4 * count].view(torch.int32)
+        n = self.num_particles
+        return view(k, n), view(p, n), view(o, nc.value + 2), int(nc.value)
+
+    def poll_error(self, stream=None) -> int:
+        """Synchronises; returns the number of out-of-grid particle events (and clears it)."""
+        code, n_oob = C.c_int32(), C.c_int64()
+        rc = self.lib.ffmpm_poll_error(self._h, self._stream(stream), C.byref(code), C.byref(n_oob))
+        if rc not in (N.FFMPM_OK, N.FFMPM_E_OOB):
+            N.check(rc)
+        return int(n_oob.value)
+
+    def check_errors(self, stream=None) -> None:
+        """Mirror of the reference's error convention: a stencil outside the grid is a
+        bare ``RuntimeError`` (three_d/p2g.py:51-52)."""
+        n_oob = self.poll_error(stream)
+        if n_oob:
+            raise RuntimeError(f"{n_oob} particle stencil(s) left the grid")
+
+    def snapshot(self, coeff: float, out: torch.Tensor, stream=None) -> None:
+        """particle.py:30-33: flat f64 vector of pos / coeff in original particle order."""
+        assert out.dtype == torch.float64 and out.numel() >= self.num_particles * self.dim
+        N.check(self.lib.ffmpm_snapshot(self._h, float(coeff), out.data_ptr(), self._stream(stream)))

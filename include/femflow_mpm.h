@@ -1,0 +1,154 @@
+/*
+ * femflow_mpm.h -- C ABI of the B200-native MLS/APIC MPM substep.
+ *
+ * This is the drop-in boundary for the one hot path of jparr721/FEMFlow that
+ * this library replaces: P2G scatter -> grid update -> G2P gather.  The
+ * reference has no FFI of its own (it is pure Python + numba); each entry point
+ * below names the reference interface it stands in for (paths relative to the
+ * reference tree):
+ *
+ *   ffmpm_substep      femflow/solvers/mpm/mls_mpm.py:40-79    solve_mls_mpm_3d
+ *                      (+ the 2D phase sequence, SURVEY 3.4, which has no driver)
+ *   ffmpm_p2g          femflow/solvers/mpm/three_d/p2g.py:14-80, two_d/p2g.py:11-76
+ *   ffmpm_grid_op      femflow/solvers/mpm/three_d/grid_op.py:5-47, two_d/grid_op.py:5-24
+ *   ffmpm_g2p          femflow/solvers/mpm/three_d/g2p.py:9-59, two_d/g2p.py:5-47
+ *   ffmpm_clear_grid   the per-substep np.zeros of mls_mpm.py:55-56
+ *   ffmpm_bin          (new) cell binning of base_coord, three_d/p2g.py:50
+ *   ffmpm_poll_error   the RuntimeError of three_d/p2g.py:51-52,70-71, g2p.py:23-24,35-36
+ *   ffmpm_snapshot     femflow/solvers/mpm/particle.py:30-33   map_particles_to_pos
+ *
+ * Conventions
+ *   - Plain C, no torch types.  All array arguments are DEVICE pointers owned by
+ *     the caller (torch tensors' data_ptr()); the library never allocates or
+ *     frees device memory, so every call is CUDA-graph capturable.
+ *   - Every function returns 0 on success or a negative FFMPM_E_* code; nothing
+ *     throws across the boundary and nothing synchronises the device except
+ *     ffmpm_poll_error.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *   - Particle state is SoA with one contiguous plane per scalar component:
+ *     component c of particle p of a field with K components lives at
+ *     field[c * stride + p].  Matrices are row-major: F[r][c] is component r*d+c.
+ *   - Grid: node-major, 4 scalars per node, C order over (nx, ny, nz):
+ *     {mom_x, mom_y, mom_z, mass} after P2G, {v_x, v_y, v_z, mass} after the
+ *     grid update (2D: {mom_x, mom_y, mass, 0}, nz = 1).
+ */
+#ifndef FEMFLOW_MPM_H_
+#define FEMFLOW_MPM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FFMPM_ABI_VERSION 1
+
+enum {
+  FFMPM_OK = 0,
+  FFMPM_E_INVALID = -1,   /* bad argument / unsupported configuration      */
+  FFMPM_E_CUDA = -2,      /* a CUDA runtime call failed (see ffmpm_last_error) */
+  FFMPM_E_OOB = -3,       /* a particle stencil left the grid (RuntimeError in the reference) */
+  FFMPM_E_STATE = -4,     /* state not bound / workspace too small          */
+  FFMPM_E_NONFINITE = -5  /* reserved */
+};
+
+enum { FFMPM_F32 = 0, FFMPM_F64 = 1 };            /* storage type of state and grid   */
+enum { FFMPM_NEO_HOOKEAN = 0, FFMPM_SNOW = 1 };   /* `model` of three_d/p2g.py:28     */
+enum {
+  FFMPM_P2G_AUTO = 0,      /* tiled when the state is binned, else scatter */
+  FFMPM_P2G_SCATTER = 1,   /* one thread per particle, one vector red per node */
+  FFMPM_P2G_TILED = 2      /* shared-memory tile per CTA (needs ffmpm_bin)  */
+};
+
+/* Scalars of solve_mls_mpm_3d's argument list (mls_mpm.py:40-53) plus the slab
+ * extension (non-cubic local grid at an integer node offset inside a global
+ * grid; reduces to the reference when origin = 0 and n = res + 1). */
+typedef struct FfMpmConfig {
+  int32_t dim;            /* 2 or 3                                              */
+  int32_t dtype;          /* FFMPM_F32 / FFMPM_F64                               */
+  int32_t model;          /* FFMPM_NEO_HOOKEAN / FFMPM_SNOW                      */
+  int32_t res[3];         /* GLOBAL grid_resolution per axis (walls use it)      */
+  int32_t n[3];           /* LOCAL node counts per axis (res+1 for one GPU)      */
+  int32_t origin[3];      /* global index of local node 0 per axis               */
+  int32_t wall_lo[3];     /* 1: this rank owns the low global face of the axis   */
+  int32_t wall_hi[3];     /* 1: this rank owns the high global face              */
+  double inv_dx, dx, dt, volume, gravity, hardening;
+  /* 2D only (two_d/p2g.py:14-16 takes global material scalars); also used in
+   * 3D when the per-particle arrays of FfMpmState are NULL. */
+  double mass, mu_0, lambda_0;
+  int32_t p2g_mode;       /* FFMPM_P2G_*                                         */
+  int32_t reserved[7];
+} FfMpmConfig;
+
+/* One particle-state buffer (device pointers).  Planes as described above. */
+typedef struct FfMpmState {
+  void* x;        /* dim   planes */
+  void* v;        /* dim   planes */
+  void* C;        /* dim^2 planes */
+  void* F;        /* dim^2 planes */
+  void* Jp;       /* 1 plane (may be NULL for 3D neo-hookean: never touched, quirk 7) */
+  void* mass;     /* 1 plane, or NULL -> cfg.mass     */
+  void* mu0;      /* 1 plane, or NULL -> cfg.mu_0     */
+  void* lam0;     /* 1 plane, or NULL -> cfg.lambda_0 */
+  int32_t* id;    /* original particle index (carried through reordering), or NULL */
+  int64_t stride; /* elements between consecutive component planes (>= n)   */
+} FfMpmState;
+
+typedef struct FfMpmHandle FfMpmHandle;
+
+int32_t ffmpm_abi_version(void);
+const char* ffmpm_last_error(void);
+
+/* Bytes of caller-provided device workspace needed for `capacity` particles
+ * (grid + binning buffers + error flag).  Returns a negative code on error. */
+int64_t ffmpm_workspace_bytes(const FfMpmConfig* cfg, int64_t capacity);
+
+int ffmpm_create(const FfMpmConfig* cfg, int32_t device, FfMpmHandle** out);
+void ffmpm_destroy(FfMpmHandle* h);
+int ffmpm_set_workspace(FfMpmHandle* h, void* workspace, int64_t bytes);
+
+/* Bind the particle buffers.  `cur` holds the live state; `alt` (same layout,
+ * may be NULL) is the ping-pong target used when G2P writes particles back in
+ * binned order.  n <= capacity given to ffmpm_workspace_bytes. */
+int ffmpm_bind_state(FfMpmHandle* h, const FfMpmState* cur, const FfMpmState* alt, int64_t n);
+/* Which of the two bound buffers holds the live state (0 = cur, 1 = alt). */
+int ffmpm_live_buffer(const FfMpmHandle* h);
+int64_t ffmpm_num_particles(const FfMpmHandle* h);
+int ffmpm_set_num_particles(FfMpmHandle* h, int64_t n);
+
+/* Phase entry points (each asynchronous on `stream`). */
+int ffmpm_clear_grid(FfMpmHandle* h, void* stream);
+int ffmpm_bin(FfMpmHandle* h, void* stream);
+int ffmpm_p2g(FfMpmHandle* h, void* stream);
+int ffmpm_grid_op(FfMpmHandle* h, void* stream);
+int ffmpm_g2p(FfMpmHandle* h, void* stream);
+/* n_substeps x (clear, [bin,] p2g, grid_op, g2p). */
+int ffmpm_substep(FfMpmHandle* h, int32_t n_substeps, void* stream);
+
+/* Phase-level access for parity tests: device pointer of the node-major grid
+ * (n[0]*n[1]*n[2]*4 scalars of cfg.dtype). */
+int ffmpm_grid_ptr(FfMpmHandle* h, void** grid);
+/* Binning results (device pointers into the workspace, valid after ffmpm_bin):
+ *   keys[p]          bin key of particle p of the live buffer: tile-major cell id
+ *                    (tile = 4x4x4 base cells in 3D, 8x8 in 2D);
+ *                    key == n_cells marks a particle whose stencil leaves the grid
+ *   perm[s]          binned slot s -> particle index in the live buffer
+ *   cell_offsets[k]  first slot of cell k (n_cells + 2 entries, exclusive scan)   */
+int ffmpm_bin_ptrs(FfMpmHandle* h, int32_t** keys, int32_t** perm, int32_t** cell_offsets,
+                   int64_t* n_cells);
+
+/* Synchronises `stream`, reads and clears the sticky device error flag.
+ * Returns FFMPM_E_OOB when n_oob > 0. */
+int ffmpm_poll_error(FfMpmHandle* h, void* stream, int32_t* code, int64_t* n_oob);
+
+/* Position snapshot, particle.py:30-33: out[3*id + c] = x[c] / coeff as f64,
+ * `out` a device or pinned-host-mapped pointer of n*dim doubles. */
+int ffmpm_snapshot(FfMpmHandle* h, double coeff, double* out, void* stream);
+
+/* Number of kernel launches issued by this handle so far. */
+int64_t ffmpm_launch_count(const FfMpmHandle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEMFLOW_MPM_H_ */

@@ -1,0 +1,284 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle / goldens.
+
+Tolerances (BASELINE.json north_star): indexing bit-exact; grid mass / momentum /
+velocity and particle x, v, C, F within 1e-5 max-norm-relative per substep for the
+fp32 build (absolute floors from the reference's own neighbouring fields, SURVEY
+8d), 1e-11 for the fp64 build (only summation order differs).
+"""
+import numpy as np
+import pytest
+
+from conftest import dense_grid, load_golden, rel_err
+from oracle import mpm_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+TOL = {"float32": 1e-5, "float64": 1e-11}
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    yield
+    from femflow_b200.solvers.mpm import _runtime
+    _runtime.clear_cache()
+
+
+@pytest.fixture(params=["float32", "float64"])
+def dtype(request):
+    from femflow_b200.solvers.mpm import _runtime
+    _runtime.set_default_dtype(request.param)
+    yield request.param
+    _runtime.set_default_dtype("float32")
+
+
+def _p3(g):
+    return dict(res=int(g["res"]), inv_dx=float(g["inv_dx"]), dx=float(g["dx"]), dt=float(g["dt"]),
+                volume=float(g["volume"]), hardening=float(g["hardening"]), gravity=float(g["gravity"]))
+
+
+def _grid(g, name):
+    return dense_grid(g, name) if f"{name}_idx" in g else g[name]
+
+
+def _floors(p, mass, grid_velocity_ref):
+    """V = max(|v_grid,ref|_inf, dt*|g|); momentum floor max(m_p)*V; C floor 4*inv_dx*V."""
+    V = max(float(np.abs(grid_velocity_ref).max()), p["dt"] * abs(p["gravity"]))
+    return dict(vel=V, mom=float(np.max(mass)) * V, C=4 * p["inv_dx"] * V)
+
+
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("name", ["kat3d", "block3d", "rest3d", "walls3d"])
+def test_3d_phase_functions_match_reference(name, dtype):
+    """three_d.p2g / grid_op / g2p with the reference's signatures vs the reference's outputs."""
+    from femflow_b200.solvers.mpm import three_d
+    from femflow_b200.solvers.mpm.particle import ParticleArray
+    g = load_golden(name)
+    p = _p3(g)
+    tol = TOL[dtype]
+    G = p["res"] + 1
+    fl = _floors(p, g["mass"], _grid(g, "grid_velocity"))
+    particles = ParticleArray(g["x"].copy(), g["mass"], g["lam0"], g["mu0"])
+    v, F, C, Jp = (g[k].copy() for k in ("v", "F", "C", "Jp"))
+    gv = np.zeros((G, G, G, 3)); gm = np.zeros((G, G, G, 1))
+    three_d.p2g(p["inv_dx"], p["hardening"], p["dx"], p["dt"], p["volume"], gv, gm, particles, v, F, C, Jp,
+                "neo_hookean")
+    assert rel_err(gm, _grid(g, "grid_mass")) < tol
+    assert rel_err(gv, _grid(g, "grid_momentum"), fl["mom"]) < tol
+    # feed the reference's momentum to the grid update so each phase is judged on its own
+    gv = _grid(g, "grid_momentum").copy(); gm = _grid(g, "grid_mass").copy()
+    three_d.grid_op(p["res"], p["dx"], p["dt"], p["gravity"], gv, gm)
+    assert rel_err(gv, _grid(g, "grid_velocity"), fl["vel"]) < tol
+    gv = _grid(g, "grid_velocity").copy()
+    three_d.g2p(p["inv_dx"], p["dt"], gv, particles, v, F, C, Jp, "neo_hookean")
+    assert rel_err(particles.pos, g["x_out"], 1.0) < tol
+    assert rel_err(v, g["v_out"], fl["vel"]) < tol
+    assert rel_err(F, g["F_out"], 1.0) < tol
+    assert rel_err(C, g["C_out"], fl["C"]) < tol
+
+
+@pytest.mark.parametrize("mode", ["scatter", "auto"])
+def test_solve_mls_mpm_3d_c1_scene(mode, dtype):
+    """BASELINE config 1 (paper scene, every 8th particle): 10 substeps through
+    solve_mls_mpm_3d (reference signature) vs the reference's trajectory."""
+    from femflow_b200.solvers.mpm.mls_mpm import make_mls_mpm_coefficients, solve_mls_mpm_3d
+    from femflow_b200.solvers.mpm.particle import ParticleArray
+    g = load_golden("c1_scene")
+    x = np.concatenate([g["gyroid_vertices"], g["collider_vertices"]]).astype(np.float32)
+    x = (x * np.float32(float(g["tightening_coeff"]))).astype(np.float64)
+    particles = ParticleArray(x, g["mass"], g["lam0"], g["mu0"])
+    v, F, C, Jp = make_mls_mpm_coefficients(len(x), 3)
+    res = int(g["res"])
+    tol = TOL[dtype]
+    for step in range(1, 11):
+        solve_mls_mpm_3d(res, float(res), float(g["hardening"]), 1.0 / res, float(g["dt"]), float(g["volume"]),
+                         float(g["gravity"]), particles, v, F, C, Jp, p2g_mode=mode)
+        if step in (1, 10):
+            k = step  # error may accumulate linearly over substeps
+            V = max(np.abs(g[f"v_{step}"]).max(), float(g["dt"]) * 9.8)
+            assert rel_err(particles.pos, g[f"x_{step}"], 1.0) < tol * k
+            assert rel_err(v, g[f"v_{step}"], V) < tol * k
+            assert rel_err(F, g[f"F_{step}"], 1.0) < tol * k
+            assert rel_err(C, g[f"C_{step}"], 4 * res * V) < tol * k
+    assert np.all(Jp == 1.0)        # quirk 7: the 3D driver never touches Jp
+
+
+def _tile_keys_3d(base, n_nodes):
+    tiles = [(n - 2 + 3) // 4 for n in n_nodes]
+    t = ((base[:, 0] >> 2) * tiles[1] + (base[:, 1] >> 2)) * tiles[2] + (base[:, 2] >> 2)
+    return t * 64 + ((base[:, 0] & 3) << 4) + ((base[:, 1] & 3) << 2) + (base[:, 2] & 3), tiles
+
+
+def test_binning_is_bit_exact(dtype):
+    """Cell keys from the CUDA binning == keys from the fp64 oracle indexing (any
+    resolution, incl. non power of two), and perm is a valid counting-sort order."""
+    from femflow_b200.mpm import MpmSolver
+    rng = np.random.default_rng(11)
+    for res in (80, 64, 37):
+        n = 50_000
+        x = rng.uniform(0.0, (res - 1.5) / res, size=(n, 3)).astype(np.float32).astype(np.float64)
+        # positions one fp32 ulp either side of the (k + 0.5)/res cell boundaries
+        k = np.arange(100) % (res - 2)
+        edge = ((k + 0.5) / res).astype(np.float32)
+        x[:100] = np.nextafter(edge, np.float32(0)).astype(np.float64)[:, None]
+        x[100:200] = np.nextafter(edge, np.float32(1)).astype(np.float64)[:, None]
+        x[200:300] = edge.astype(np.float64)[:, None]
+        s = MpmSolver(3, res, 1e-4, 1.0, -9.8, 1.0, capacity=n, dtype=getattr(torch, dtype))
+        s.set_particles(x, mass=1.0, mu0=1.0, lam0=1.0)
+        s.bin()
+        keys, perm, off, n_cells = s.bin_results()
+        keys, perm, off = keys.cpu().numpy(), perm.cpu().numpy(), off.cpu().numpy()
+        base, _ = O.base_and_fx(x, float(res))
+        want, tiles = _tile_keys_3d(base, [res + 1] * 3)
+        assert n_cells == tiles[0] * tiles[1] * tiles[2] * 64
+        assert np.array_equal(keys, want.astype(np.int32))
+        assert np.array_equal(np.sort(perm), np.arange(n))
+        sorted_keys = keys[perm]
+        assert np.all(np.diff(sorted_keys) >= 0)
+        counts = np.bincount(want, minlength=n_cells + 2)
+        assert np.array_equal(off, np.concatenate([[0], np.cumsum(counts)[:-1]]))
+        assert s.poll_error() == 0
+        s.close()
+
+
+@pytest.mark.parametrize("mode", ["scatter", "tiled"])
+def test_large_block_vs_oracle(mode, dtype):
+    """200k-particle perturbed block, res 64: full substep vs the NumPy oracle, per phase."""
+    from femflow_b200.mpm import MpmSolver
+    rng = np.random.default_rng(5)
+    res, n = 64, 200_000
+    f32 = lambda a: np.asarray(a, dtype=np.float32).astype(np.float64)
+    x = f32(rng.uniform(0.2, 0.8, size=(n, 3)))
+    v = f32(rng.normal(0, 0.1, size=(n, 3)))
+    F = f32(np.eye(3) + rng.normal(0, 0.02, size=(n, 3, 3)))
+    C = f32(rng.normal(0, 0.5, size=(n, 3, 3)))
+    dx = 1.0 / res
+    vol = f32((dx / 2) ** 3)
+    mass = np.full(n, float(vol)); mu0 = np.full(n, f32(4166.67)); lam0 = np.full(n, f32(2777.78))
+    p = dict(dt=1e-4, gravity=-9.8, inv_dx=float(res))
+    s = MpmSolver(3, res, p["dt"], float(vol), p["gravity"], 1.0, capacity=n, dtype=getattr(torch, dtype),
+                  p2g_mode=mode)
+    s.set_particles(x, v, F, C, None, mass, mu0, lam0)
+    xo, vo, Fo, Co, Jp = x.copy(), v.copy(), F.copy(), C.copy(), np.ones((n, 1))
+    mom, gmass, vel = O.solve_mls_mpm_3d(res, float(res), 1.0, dx, p["dt"], float(vol), p["gravity"],
+                                         xo, mass, mu0, lam0, vo, Fo, Co, Jp, return_grids=True)
+    fl = _floors(p, mass, vel)
+    tol = TOL[dtype]
+    s.clear_grid()
+    if mode == "tiled":
+        s.bin()
+    s.p2g()
+    g = s.grid().double().cpu().numpy()
+    assert rel_err(g[..., 3:4], gmass) < tol
+    assert rel_err(g[..., :3], mom, fl["mom"]) < tol
+    s.grid_op()
+    g = s.grid().double().cpu().numpy()
+    assert rel_err(g[..., :3], vel, fl["vel"]) < tol
+    s.g2p()
+    assert s.poll_error() == 0
+    out = {k: t.double().cpu().numpy() for k, t in s.get_particles().items()}
+    assert rel_err(out["x"], xo, 1.0) < tol
+    assert rel_err(out["v"], vo, fl["vel"]) < tol
+    assert rel_err(out["F"], Fo, 1.0) < tol
+    assert rel_err(out["C"], Co, fl["C"]) < tol
+    # a second substep runs from the re-ordered buffer
+    O.solve_mls_mpm_3d(res, float(res), 1.0, dx, p["dt"], float(vol), p["gravity"], xo, mass, mu0, lam0, vo, Fo, Co, Jp)
+    s.substep(1)
+    out = {k: t.double().cpu().numpy() for k, t in s.get_particles().items()}
+    assert rel_err(out["x"], xo, 1.0) < 2 * tol
+    assert rel_err(out["v"], vo, fl["vel"]) < 2 * tol
+    assert rel_err(out["F"], Fo, 1.0) < 2 * tol
+    s.close()
+
+
+def test_snow_p2g_3d(dtype):
+    """Snow hardening in the 3D scatter (three_d/p2g.py:57-61, utils.py:27-49)."""
+    from femflow_b200.solvers.mpm import three_d
+    from femflow_b200.solvers.mpm.particle import ParticleArray
+    g = load_golden("snow3d")
+    p = _p3(g); G = p["res"] + 1
+    particles = ParticleArray(g["x"].copy(), g["mass"], g["lam0"], g["mu0"])
+    gv = np.zeros((G, G, G, 3)); gm = np.zeros((G, G, G, 1))
+    three_d.p2g(p["inv_dx"], p["hardening"], p["dx"], p["dt"], p["volume"], gv, gm, particles,
+                g["v"].copy(), g["F"].copy(), g["C"].copy(), g["Jp"].copy(), "snow")
+    assert rel_err(gm, dense_grid(g, "grid_mass")) < TOL[dtype]
+    assert rel_err(gv, dense_grid(g, "grid_momentum")) < TOL[dtype]
+
+
+def test_oob_raises_runtime_error(dtype):
+    """three_d/p2g.py:51-52: a stencil outside [0, R] is a RuntimeError."""
+    from femflow_b200.solvers.mpm.mls_mpm import make_mls_mpm_coefficients, solve_mls_mpm_3d
+    from femflow_b200.solvers.mpm.particle import ParticleArray
+    res = 8
+    x = np.array([[0.5, 0.5, 0.5], [0.5, 0.5, (res - 0.4) / res]])
+    particles = ParticleArray(x, 1.0, 1.0, 1.0)
+    v, F, C, Jp = make_mls_mpm_coefficients(2, 3)
+    for mode in ("scatter", "auto"):
+        with pytest.raises(RuntimeError):
+            solve_mls_mpm_3d(res, float(res), 1.0, 1 / res, 1e-4, 1.0, -9.8, particles, v, F, C, Jp, p2g_mode=mode)
+    # empty input is a no-op
+    e = ParticleArray(np.zeros((0, 3)), np.zeros(0), np.zeros(0), np.zeros(0))
+    ve, Fe, Ce, Jpe = make_mls_mpm_coefficients(0, 3)
+    solve_mls_mpm_3d(res, float(res), 1.0, 1 / res, 1e-4, 1.0, -9.8, e, ve, Fe, Ce, Jpe)
+
+
+# ------------------------------- 2D ---------------------------------------- #
+def _p2(g):
+    return dict(res=int(g["res"]), dt=float(g["dt"]), gravity=float(g["gravity"]), mass=float(g["mass"]),
+                volume=float(g["volume"]), hardening=float(g["hardening"]), mu_0=float(g["mu_0"]),
+                lambda_0=float(g["lambda_0"]))
+
+
+@pytest.mark.parametrize("name", ["test2d", "block2d"])
+def test_2d_phase_functions_match_reference(name, dtype):
+    from femflow_b200.solvers.mpm import two_d
+    g = load_golden(name)
+    p = _p2(g)
+    tol = TOL[dtype]
+    res = p["res"]; G = res + 1
+    x, v, F, C, Jp = (g[k].copy() for k in ("x", "v", "F", "C", "Jp"))
+    V = max(float(np.abs(g["grid_velocity"]).max()), p["dt"] * abs(p["gravity"]))
+    gv = np.zeros((G, G, 2)); gm = np.zeros((G, G, 1))
+    two_d.p2g(float(res), p["hardening"], p["mu_0"], p["lambda_0"], p["mass"], 1.0 / res, p["dt"], p["volume"],
+              gv, gm, x, v, F, C, Jp)
+    assert rel_err(gm, g["grid_mass"]) < tol
+    assert rel_err(gv, g["grid_momentum"], p["mass"] * V) < tol
+    gv = g["grid_momentum"].copy(); gm = g["grid_mass"].copy()
+    two_d.grid_op(res, p["dt"], p["gravity"], gv, gm)
+    assert rel_err(gv, g["grid_velocity"], V) < tol
+    gv = g["grid_velocity"].copy()
+    two_d.g2p(float(res), p["dt"], gv, x, v, F, C, Jp)
+    assert rel_err(x, g["x_out"], 1.0) < tol
+    assert rel_err(v, g["v_out"], V) < tol
+    assert rel_err(F, g["F_out"], 1.0) < tol
+    assert rel_err(C, g["C_out"], 4 * res * V) < tol
+    assert rel_err(Jp, g["Jp_out"], 1.0) < tol
+
+
+def test_2d_svd_roundtrip_quirk(dtype):
+    """two_d/g2p.py:37-43 ``U @ diag(sig) @ Vh.T`` incl. det F < 0 (tests/golden/quirk2d.npz)."""
+    from femflow_b200.solvers.mpm import two_d
+    g = load_golden("quirk2d")
+    res = int(g["res"]); G = res + 1
+    x = g["x"].copy(); F = g["F"].copy(); n = len(x)
+    v = np.zeros((n, 2)); C = np.zeros((n, 2, 2)); Jp = np.ones((n, 1))
+    two_d.g2p(float(res), 1e-4, np.zeros((G, G, 2)), x, v, F, C, Jp)
+    tol = 1e-6 if dtype == "float32" else 1e-12
+    assert rel_err(F, g["F_out"]) < tol
+    assert rel_err(Jp, g["Jp_out"]) < tol
+
+
+def test_2d_wall_masks_bit_exact():
+    """Quirk 6: the f64 wall predicates on i/R of two_d/grid_op.py:18-23, at R = 1024 and R = 80."""
+    from femflow_b200.solvers.mpm import two_d
+    for res in (80, 1024):
+        G = res + 1
+        gv = np.ones((G, G, 2)); gv[..., 1] = -1.0
+        gm = np.ones((G, G, 1))
+        ref = gv.copy()
+        O.grid_op_2d(res, 1.0, 0.0, ref, gm.copy())
+        two_d.grid_op(res, 1.0, 0.0, gv, gm)
+        assert np.array_equal(gv, ref)
