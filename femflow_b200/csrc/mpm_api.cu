@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -48,6 +49,7 @@ struct FfMpmHandle {
   int64_t capacity;   // capacity the workspace was sized for (derived from ws_bytes)
   bool binned;        // bin buffers describe the live buffer
   int64_t launches;
+  int p2g_blocks_per_sm, g2p_blocks_per_sm;   // persistent-grid sizing (tunable: FFMPM_P2G_BPS / FFMPM_G2P_BPS)
 };
 
 static size_t elem_size(const FfMpmConfig& c) { return c.dtype == FFMPM_F64 ? 8 : 4; }
@@ -120,6 +122,10 @@ int ffmpm_create(const FfMpmConfig* cfg, int32_t device, FfMpmHandle** out) {
   d.gravity = cfg->gravity; d.hardening = cfg->hardening;
   d.mass = cfg->mass; d.mu0 = cfg->mu_0; d.lam0 = cfg->lambda_0;
   h->n_nodes = (int64_t)d.n[0] * d.n[1] * d.n[2];
+  h->p2g_blocks_per_sm = 4;
+  h->g2p_blocks_per_sm = 8;
+  if (const char* e = getenv("FFMPM_P2G_BPS")) { int v = atoi(e); if (v > 0 && v <= 32) h->p2g_blocks_per_sm = v; }
+  if (const char* e = getenv("FFMPM_G2P_BPS")) { int v = atoi(e); if (v > 0 && v <= 32) h->g2p_blocks_per_sm = v; }
   *out = h;
   return FFMPM_OK;
 }
@@ -241,7 +247,7 @@ static int p2g_t(FfMpmHandle* h, cudaStream_t s) {
   if (mode == FFMPM_P2G_TILED) {
     if (h->cfg.dim != 3) return set_err(FFMPM_E_INVALID, "tiled P2G is 3D only (2D uses the scatter kernel)");
     if (!h->binned) return set_err(FFMPM_E_STATE, "tiled P2G needs ffmpm_bin first");
-    int nl = p2g_tiled<T>(h->dev, sv, h->n, h->bin, (T*)h->grid, h->err, h->sm_count, s);
+    int nl = p2g_tiled<T>(h->dev, sv, h->n, h->bin, (T*)h->grid, h->err, h->sm_count, h->p2g_blocks_per_sm, s);
     return check_launch(h, nl);
   }
   unsigned blocks = (unsigned)((h->n + 127) / 128);
@@ -281,7 +287,7 @@ static int g2p_t(FfMpmHandle* h, cudaStream_t s) {
   if (h->binned && h->have_alt && h->cfg.dim == 3) {
     // binned: gather through the permutation, write back in binned order into the other buffer
     StateView<T> dst = view<T>(h->st[h->live ^ 1]);
-    int nl = g2p_tiled<T>(h->dev, sv, dst, h->n, h->bin, (const T*)h->grid, h->err, h->sm_count, s);
+    int nl = g2p_tiled<T>(h->dev, sv, dst, h->n, h->bin, (const T*)h->grid, h->err, h->sm_count, h->g2p_blocks_per_sm, s);
     h->live ^= 1;
     h->binned = false;  // positions moved: keys are stale
     return check_launch(h, nl);

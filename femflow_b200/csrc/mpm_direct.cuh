@@ -216,6 +216,49 @@ __global__ void __launch_bounds__(256) grid_op2_kernel(DevCfg cfg, T* __restrict
 }
 
 // ----------------------------------------------------------------------------
+// G2P stencil sums (three_d/g2p.py:31-43): v = sum w gv,  C = sum (w gv) (x) dpos  (the
+// caller scales C by 4*inv_dx).  The weights and dpos are separable per axis, so the 27
+// node terms are folded axis by axis (z, then y, then x): ~40% fewer FMAs than the
+// node-by-node outer product, same sums up to round-off.
+// ----------------------------------------------------------------------------
+template <typename T, typename Fetch>
+__device__ __forceinline__ void g2p_accumulate3(Fetch fetch, T fx, T fy, T fz, T& vx, T& vy, T& vz, T& c00, T& c01,
+                                                T& c02, T& c10, T& c11, T& c12, T& c20, T& c21, T& c22) {
+  T wx[3], wy[3], wz[3];
+  bspline(fx, wx[0], wx[1], wx[2]);
+  bspline(fy, wy[0], wy[1], wy[2]);
+  bspline(fz, wz[0], wz[1], wz[2]);
+  T dz[3] = {wz[0] * ((T)0 - fz), wz[1] * ((T)1 - fz), wz[2] * ((T)2 - fz)};
+  T dy[3] = {wy[0] * ((T)0 - fy), wy[1] * ((T)1 - fy), wy[2] * ((T)2 - fy)};
+  T dxw[3] = {wx[0] * ((T)0 - fx), wx[1] * ((T)1 - fx), wx[2] * ((T)2 - fx)};
+  vx = vy = vz = (T)0;
+  c00 = c01 = c02 = c10 = c11 = c12 = c20 = c21 = c22 = (T)0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    T px = 0, py = 0, pz = 0;        // sum_j wy (sum_k wz gv)
+    T qx = 0, qy = 0, qz = 0;        // sum_j wy (j - fy) (sum_k wz gv)
+    T rx = 0, ry = 0, rz = 0;        // sum_j wy (sum_k wz (k - fz) gv)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      T tx = 0, ty = 0, tz = 0, ux = 0, uy = 0, uz = 0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const auto g = fetch(i, j, k);
+        tx += wz[k] * g.x; ty += wz[k] * g.y; tz += wz[k] * g.z;
+        ux += dz[k] * g.x; uy += dz[k] * g.y; uz += dz[k] * g.z;
+      }
+      px += wy[j] * tx; py += wy[j] * ty; pz += wy[j] * tz;
+      qx += dy[j] * tx; qy += dy[j] * ty; qz += dy[j] * tz;
+      rx += wy[j] * ux; ry += wy[j] * uy; rz += wy[j] * uz;
+    }
+    vx += wx[i] * px; vy += wx[i] * py; vz += wx[i] * pz;
+    c00 += dxw[i] * px; c10 += dxw[i] * py; c20 += dxw[i] * pz;
+    c01 += wx[i] * qx; c11 += wx[i] * qy; c21 += wx[i] * qz;
+    c02 += wx[i] * rx; c12 += wx[i] * ry; c22 += wx[i] * rz;
+  }
+}
+
+// ----------------------------------------------------------------------------
 // G2P, gather form (in place)
 // ----------------------------------------------------------------------------
 template <typename T>
@@ -234,34 +277,11 @@ __global__ void __launch_bounds__(128) g2p_gather3_kernel(DevCfg cfg, StateView<
   bool ok = !(isnan((double)x0) || isnan((double)x1) || isnan((double)x2)) && bx >= 0 && by >= 0 && bz >= 0 &&
             bx + 2 < cfg.n[0] && by + 2 < cfg.n[1] && bz + 2 < cfg.n[2];
   if (!ok) { atomicAdd(&err->n_oob, 1ULL); return; }
-  T wx[3], wy[3], wz[3];
-  bspline(fx, wx[0], wx[1], wx[2]);
-  bspline(fy, wy[0], wy[1], wy[2]);
-  bspline(fz, wz[0], wz[1], wz[2]);
   const long long ny = cfg.n[1], nz = cfg.n[2];
-  T vx = 0, vy = 0, vz = 0;
-  T c00 = 0, c01 = 0, c02 = 0, c10 = 0, c11 = 0, c12 = 0, c20 = 0, c21 = 0, c22 = 0;
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    T dpx = (T)i - fx;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      T dpy = (T)j - fy;
-      T wij = wx[i] * wy[j];
-      const T* row = grid + (((long long)(bx + i) * ny + (by + j)) * nz + bz) * 4;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        T dpz = (T)k - fz;
-        T w = wij * wz[k];
-        auto g = ld_node(row + 4 * k);
-        T ux = w * g.x, uy = w * g.y, uz = w * g.z;
-        vx += ux; vy += uy; vz += uz;
-        c00 += ux * dpx; c01 += ux * dpy; c02 += ux * dpz;
-        c10 += uy * dpx; c11 += uy * dpy; c12 += uy * dpz;
-        c20 += uz * dpx; c21 += uz * dpy; c22 += uz * dpz;
-      }
-    }
-  }
+  const T* gb = grid + (((long long)bx * ny + by) * nz + bz) * 4;
+  T vx, vy, vz, c00, c01, c02, c10, c11, c12, c20, c21, c22;
+  g2p_accumulate3<T>([&](int i, int j, int k) { return ld_node(gb + (((long long)i * ny + j) * nz + k) * 4); }, fx, fy, fz,
+                     vx, vy, vz, c00, c01, c02, c10, c11, c12, c20, c21, c22);
   const T s4 = (T)(4.0 * cfg.inv_dx);
   c00 *= s4; c01 *= s4; c02 *= s4; c10 *= s4; c11 *= s4; c12 *= s4; c20 *= s4; c21 *= s4; c22 *= s4;
   const T dt = (T)cfg.dt;

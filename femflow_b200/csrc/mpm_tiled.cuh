@@ -1,15 +1,6 @@
 // Tiled 3D kernels over binned particles (see mpm_bin.cuh for the key layout).
 //
-// P2G: persistent CTAs pull active tiles (4x4x4 base cells -> 6x6x6 nodes) from a
-// work counter.  Each warp takes 32 consecutive binned particles: lanes first
-// evaluate the per-particle payload (fp64 polar decomposition + fixed-corotated
-// stress, three_d/p2g.py:57-65) and park it in shared memory; then the warp walks
-// those 32 particles with ONE LANE PER STENCIL NODE (27 of 32 lanes), accumulating
-// the contributions of all particles of the same cell in registers -- particles are
-// cell-sorted, so same-node contributions are aggregated across the warp without a
-// single conflict -- and flushes into the CTA's shared-memory tile only when the
-// cell changes.  The tile is finally added to the global grid with one vector
-// reduction (red.global.add.v4.f32) per touched node.
+// P2G: see p2g_tiled3_kernel below.
 //
 // G2P: the CTA stages the tile's 6x6x6 velocity block in shared memory, each thread
 // gathers its particle's 3x3x3 stencil from there, and the updated state is written
@@ -24,53 +15,62 @@ namespace ffmpm {
 
 constexpr int TN3 = TILE3 + 2;            // nodes per tile edge
 constexpr int TNODES3 = TN3 * TN3 * TN3;  // 216
-constexpr int P2G_WARPS = 8;
+constexpr int P2G_THREADS = 288;          // 9 warps: 64 cells x 9 stencil columns = 2 x 288 work items per full tile
 constexpr int G2P_THREADS = 128;
 
+// Per-particle P2G payload parked in shared memory between the two phases.
 template <typename T>
 struct alignas(16) P2GPayload {
   T mvx, mvy, mvz, m;
-  T a00, a01, a02, fx;
+  T a00, a01, a02, fx;   // a = affine * dx
   T a10, a11, a12, fy;
   T a20, a21, a22, fz;
+  T wz0, wz1, wz2, pad;
 };
 
+template <typename T> struct P2GChunk { static constexpr int value = 512; };
+template <> struct P2GChunk<double> { static constexpr int value = 256; };
+
+// P2G over binned particles.  Persistent CTAs pull active tiles (4x4x4 base cells)
+// from a work counter and walk the tile's contiguous, cell-sorted particle run in
+// chunks:
+//   phase 1 (thread per particle)  gather the state through `perm`, evaluate the
+//           polar decomposition / fixed-corotated stress in fp64
+//           (three_d/p2g.py:57-65) and park {m v, m, affine*dx, fx, wz} in smem;
+//   phase 2 (thread per (cell, stencil column (i,j)))  walk the cell's particles,
+//           accumulating the column's three nodes x {momentum, mass} in registers
+//           (three_d/p2g.py:67-80) -- same-node contributions of all particles of a
+//           cell are summed before they leave the SM -- then ONE vector reduction
+//           (red.global.add.v4.f32) per node.
 template <typename T>
-__global__ void __launch_bounds__(P2G_WARPS * 32) p2g_tiled3_kernel(DevCfg cfg, StateView<T> s, BinBuffers B,
-                                                                    T* __restrict__ grid, ErrRec* err) {
-  __shared__ T tile[4][TNODES3];
-  __shared__ P2GPayload<T> stage[P2G_WARPS][32];
-  __shared__ int stage_cell[P2G_WARPS][32];
+__global__ void __launch_bounds__(P2G_THREADS) p2g_tiled3_kernel(DevCfg cfg, StateView<T> s, BinBuffers B,
+                                                                 T* __restrict__ grid, ErrRec* err) {
+  constexpr int CHUNK = P2GChunk<T>::value;
+  __shared__ P2GPayload<T> pay[CHUNK];
+  __shared__ int soff[TILE_CELLS + 1];
   __shared__ int s_work;
 
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n_active = B.counters[0];
-  // lane -> stencil node (i, j, k)
-  const int li = lane / 9, lj = (lane / 3) % 3, lk = lane % 3;
-  const bool node_lane = lane < 27;
-  const T ci = (T)li, cj = (T)lj, ck = (T)lk;
-  // B-spline piece of this lane per axis: w = s * (fx - c)^2 + o
-  const T sx = li == 1 ? (T)-1 : (T)0.5, cx_ = (T)1.5 - (T)0.5 * ci, ox_ = li == 1 ? (T)0.75 : (T)0;
-  const T sy = lj == 1 ? (T)-1 : (T)0.5, cy_ = (T)1.5 - (T)0.5 * cj, oy_ = lj == 1 ? (T)0.75 : (T)0;
-  const T sz = lk == 1 ? (T)-1 : (T)0.5, cz_ = (T)1.5 - (T)0.5 * ck, oz_ = lk == 1 ? (T)0.75 : (T)0;
-  const int lane_node = (li * TN3 + lj) * TN3 + lk;
   const T dx = (T)cfg.dx;
+  const long long ny = cfg.n[1], nz = cfg.n[2];
 
   for (;;) {
+    __syncthreads();
     if (threadIdx.x == 0) s_work = atomicAdd(&B.counters[1], 1);
-    for (int i = threadIdx.x; i < 4 * TNODES3; i += blockDim.x) (&tile[0][0])[i] = (T)0;
     __syncthreads();
     const int wi = s_work;
     if (wi >= n_active) break;
     const int t = B.active_tiles[wi];
-    const int start = B.cell_off[t * TILE_CELLS], end = B.cell_off[(t + 1) * TILE_CELLS];
+    if (threadIdx.x <= TILE_CELLS) soff[threadIdx.x] = B.cell_off[t * TILE_CELLS + threadIdx.x];
     const int tz = t % B.tiles[2], ty = (t / B.tiles[2]) % B.tiles[1], tx = t / (B.tiles[2] * B.tiles[1]);
     const int ox = tx * TILE3, oy = ty * TILE3, oz = tz * TILE3;
+    __syncthreads();
+    const int start = soff[0], end = soff[TILE_CELLS];
 
-    for (int chunk = start + warp * 32; chunk < end; chunk += P2G_WARPS * 32) {
-      const int slot = chunk + lane;
-      // ---- phase 1: one lane per particle ----
-      if (slot < end) {
+    for (int chunk = start; chunk < end; chunk += CHUNK) {
+      const int cend = min(chunk + CHUNK, end);
+      // ---- phase 1: one thread per particle ----
+      for (int slot = chunk + threadIdx.x; slot < cend; slot += P2G_THREADS) {
         const long long p = B.perm[slot];
         P2GParticle3<T> q = p2g_prepare3(cfg, s, p);
         P2GPayload<T> pl;
@@ -78,57 +78,56 @@ __global__ void __launch_bounds__(P2G_WARPS * 32) p2g_tiled3_kernel(DevCfg cfg, 
         pl.a00 = q.a00 * dx; pl.a01 = q.a01 * dx; pl.a02 = q.a02 * dx; pl.fx = q.fx;
         pl.a10 = q.a10 * dx; pl.a11 = q.a11 * dx; pl.a12 = q.a12 * dx; pl.fy = q.fy;
         pl.a20 = q.a20 * dx; pl.a21 = q.a21 * dx; pl.a22 = q.a22 * dx; pl.fz = q.fz;
-        stage[warp][lane] = pl;
-        // node index of the cell's base inside the tile
-        stage_cell[warp][lane] = ((q.bx - ox) * TN3 + (q.by - oy)) * TN3 + (q.bz - oz);
+        bspline(q.fz, pl.wz0, pl.wz1, pl.wz2);
+        pl.pad = (T)0;
+        pay[slot - chunk] = pl;
       }
-      __syncwarp();
-      // ---- phase 2: one lane per stencil node ----
-      const int cnt = min(32, end - chunk);
-      T ax = 0, ay = 0, az = 0, am = 0;
-      int cur = stage_cell[warp][0];
-      for (int qi = 0; qi < cnt; ++qi) {
-        const int c = stage_cell[warp][qi];
-        if (c != cur) {
-          if (node_lane) {
-            const int nd = cur + lane_node;
-            atomicAdd(&tile[0][nd], ax); atomicAdd(&tile[1][nd], ay);
-            atomicAdd(&tile[2][nd], az); atomicAdd(&tile[3][nd], am);
-          }
-          ax = ay = az = am = (T)0;
-          cur = c;
+      __syncthreads();
+      // ---- phase 2: one thread per (cell, column) ----
+      // cells intersecting this chunk: binary search of the first/last cell in soff
+      int c_lo = 0, c_hi = TILE_CELLS - 1;
+      {
+        int lo = 0, hi = TILE_CELLS;      // last c with soff[c] <= chunk
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (soff[mid] <= chunk) lo = mid; else hi = mid; }
+        c_lo = lo;
+        lo = 0; hi = TILE_CELLS;          // last c with soff[c] <= cend - 1
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (soff[mid] <= cend - 1) lo = mid; else hi = mid; }
+        c_hi = lo;
+      }
+      const int n_items = (c_hi - c_lo + 1) * 9;
+      for (int item = threadIdx.x; item < n_items; item += P2G_THREADS) {
+        const int c = c_lo + item / 9, col = item % 9;
+        const int r0 = max(soff[c], chunk) - chunk, r1 = min(soff[c + 1], cend) - chunk;
+        if (r0 >= r1) continue;
+        const int li = col / 3, lj = col % 3;
+        const T ci = (T)li, cj = (T)lj;
+        // B-spline piece of this column per axis: w = s * (f - c)^2 + o  (three_d/p2g.py:55)
+        const T sx = li == 1 ? (T)-1 : (T)0.5, cx_ = (T)1.5 - (T)0.5 * ci, ox_ = li == 1 ? (T)0.75 : (T)0;
+        const T sy = lj == 1 ? (T)-1 : (T)0.5, cy_ = (T)1.5 - (T)0.5 * cj, oy_ = lj == 1 ? (T)0.75 : (T)0;
+        T x0 = 0, y0 = 0, z0 = 0, m0 = 0, x1 = 0, y1 = 0, z1 = 0, m1 = 0, x2 = 0, y2 = 0, z2 = 0, m2 = 0;
+#pragma unroll 2
+        for (int qi = r0; qi < r1; ++qi) {
+          const P2GPayload<T> pl = pay[qi];
+          const T tx_ = pl.fx - cx_, ty_ = pl.fy - cy_;
+          const T wij = (sx * tx_ * tx_ + ox_) * (sy * ty_ * ty_ + oy_);
+          const T dpx = ci - pl.fx, dpy = cj - pl.fy;
+          const T bx = pl.mvx + (pl.a00 * dpx + pl.a01 * dpy);
+          const T by = pl.mvy + (pl.a10 * dpx + pl.a11 * dpy);
+          const T bz = pl.mvz + (pl.a20 * dpx + pl.a21 * dpy);
+          const T d0 = -pl.fz, d1 = (T)1 - pl.fz, d2 = (T)2 - pl.fz;
+          const T w0 = wij * pl.wz0, w1 = wij * pl.wz1, w2 = wij * pl.wz2;
+          x0 += w0 * (bx + pl.a02 * d0); y0 += w0 * (by + pl.a12 * d0); z0 += w0 * (bz + pl.a22 * d0); m0 += w0 * pl.m;
+          x1 += w1 * (bx + pl.a02 * d1); y1 += w1 * (by + pl.a12 * d1); z1 += w1 * (bz + pl.a22 * d1); m1 += w1 * pl.m;
+          x2 += w2 * (bx + pl.a02 * d2); y2 += w2 * (by + pl.a12 * d2); z2 += w2 * (bz + pl.a22 * d2); m2 += w2 * pl.m;
         }
-        const P2GPayload<T>& pl = stage[warp][qi];
-        const T tx_ = pl.fx - cx_, ty_ = pl.fy - cy_, tz_ = pl.fz - cz_;
-        const T wx = sx * tx_ * tx_ + ox_, wy = sy * ty_ * ty_ + oy_, wz = sz * tz_ * tz_ + oz_;
-        const T w = wx * wy * wz;
-        const T dpx = ci - pl.fx, dpy = cj - pl.fy, dpz = ck - pl.fz;
-        const T mx = pl.mvx + (pl.a00 * dpx + pl.a01 * dpy + pl.a02 * dpz);
-        const T my = pl.mvy + (pl.a10 * dpx + pl.a11 * dpy + pl.a12 * dpz);
-        const T mz = pl.mvz + (pl.a20 * dpx + pl.a21 * dpy + pl.a22 * dpz);
-        ax += w * mx; ay += w * my; az += w * mz; am += w * pl.m;
+        const int gx = ox + (c >> 4) + li, gy = oy + ((c >> 2) & 3) + lj, gz = oz + (c & 3);
+        T* g = grid + (((long long)gx * ny + gy) * nz + gz) * 4;
+        red_add4(g, x0, y0, z0, m0);
+        red_add4(g + 4, x1, y1, z1, m1);
+        red_add4(g + 8, x2, y2, z2, m2);
       }
-      if (node_lane) {
-        const int nd = cur + lane_node;
-        atomicAdd(&tile[0][nd], ax); atomicAdd(&tile[1][nd], ay);
-        atomicAdd(&tile[2][nd], az); atomicAdd(&tile[3][nd], am);
-      }
-      __syncwarp();
+      __syncthreads();   // phase 2 readers are done before the next chunk overwrites `pay`
     }
-    __syncthreads();
-    // ---- tile -> global grid: one vector reduction per touched node ----
-    for (int nd = threadIdx.x; nd < TNODES3; nd += blockDim.x) {
-      const T m = tile[3][nd];
-      if (m != (T)0) {
-        const int k = nd % TN3, j = (nd / TN3) % TN3, i = nd / (TN3 * TN3);
-        const int gx = ox + i, gy = oy + j, gz = oz + k;
-        if (gx < cfg.n[0] && gy < cfg.n[1] && gz < cfg.n[2]) {
-          T* g = grid + (((long long)gx * cfg.n[1] + gy) * cfg.n[2] + gz) * 4;
-          red_add4(g, tile[0][nd], tile[1][nd], tile[2][nd], m);
-        }
-      }
-    }
-    __syncthreads();
   }
 }
 
@@ -193,32 +192,9 @@ __global__ void __launch_bounds__(G2P_THREADS) g2p_tiled3_kernel(DevCfg cfg, Sta
       base_fx(x1, cfg.inv_dx, gy, fy);
       base_fx(x2, cfg.inv_dx, gz, fz);
       const int cb = ((gx - cfg.origin[0] - ox) * TN3 + (gy - cfg.origin[1] - oy)) * TN3 + (gz - cfg.origin[2] - oz);
-      T wx[3], wy[3], wz[3];
-      bspline(fx, wx[0], wx[1], wx[2]);
-      bspline(fy, wy[0], wy[1], wy[2]);
-      bspline(fz, wz[0], wz[1], wz[2]);
-      T vx = 0, vy = 0, vz = 0;
-      T c00 = 0, c01 = 0, c02 = 0, c10 = 0, c11 = 0, c12 = 0, c20 = 0, c21 = 0, c22 = 0;
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const T dpx = (T)i - fx;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const T dpy = (T)j - fy;
-          const T wij = wx[i] * wy[j];
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            const T dpz = (T)k - fz;
-            const T w = wij * wz[k];
-            const V4 g = tile[cb + (i * TN3 + j) * TN3 + k];
-            const T ux = w * g.x, uy = w * g.y, uz = w * g.z;
-            vx += ux; vy += uy; vz += uz;
-            c00 += ux * dpx; c01 += ux * dpy; c02 += ux * dpz;
-            c10 += uy * dpx; c11 += uy * dpy; c12 += uy * dpz;
-            c20 += uz * dpx; c21 += uz * dpy; c22 += uz * dpz;
-          }
-        }
-      }
+      T vx, vy, vz, c00, c01, c02, c10, c11, c12, c20, c21, c22;
+      g2p_accumulate3<T>([&](int i, int j, int k) { return tile[cb + (i * TN3 + j) * TN3 + k]; }, fx, fy, fz,
+                         vx, vy, vz, c00, c01, c02, c10, c11, c12, c20, c21, c22);
       const T s4 = (T)(4.0 * cfg.inv_dx);
       c00 *= s4; c01 *= s4; c02 *= s4; c10 *= s4; c11 *= s4; c12 *= s4; c20 *= s4; c21 *= s4; c22 *= s4;
       const T dt = (T)cfg.dt;
@@ -249,20 +225,20 @@ __global__ void __launch_bounds__(G2P_THREADS) g2p_tiled3_kernel(DevCfg cfg, Sta
 
 template <typename T>
 int p2g_tiled(const DevCfg& cfg, const StateView<T>& s, long long n, BinBuffers& B, T* grid, ErrRec* err, int sm_count,
-              cudaStream_t st) {
+              int blocks_per_sm, cudaStream_t st) {
   (void)n;
   cudaMemsetAsync(&B.counters[1], 0, sizeof(int32_t), st);
-  int blocks = min(B.n_tiles, sm_count * 4);
-  p2g_tiled3_kernel<T><<<blocks, P2G_WARPS * 32, 0, st>>>(cfg, s, B, grid, err);
+  int blocks = min(B.n_tiles, sm_count * blocks_per_sm);
+  p2g_tiled3_kernel<T><<<blocks, P2G_THREADS, 0, st>>>(cfg, s, B, grid, err);
   return 1;
 }
 
 template <typename T>
 int g2p_tiled(const DevCfg& cfg, const StateView<T>& src, const StateView<T>& dst, long long n, BinBuffers& B,
-              const T* grid, ErrRec* err, int sm_count, cudaStream_t st) {
+              const T* grid, ErrRec* err, int sm_count, int blocks_per_sm, cudaStream_t st) {
   (void)n;
   cudaMemsetAsync(&B.counters[2], 0, sizeof(int32_t), st);
-  int blocks = min(B.n_tiles + 1, sm_count * 8);
+  int blocks = min(B.n_tiles + 1, sm_count * blocks_per_sm);
   g2p_tiled3_kernel<T><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
   return 1;
 }

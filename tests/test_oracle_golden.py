@@ -206,3 +206,48 @@ def test_oob_raises_like_reference():
     O.p2g_3d(float(res), 1.0, 1 / res, 1e-4, 1.0, np.zeros((G, G, G, 3)), np.zeros((G, G, G, 1)),
              np.zeros((0, 3)), np.ones(0), np.ones(0), np.ones(0), np.zeros((0, 3)), np.zeros((0, 3, 3)),
              np.zeros((0, 3, 3)), np.ones((0, 1)))           # empty input is a no-op
+
+
+# ------------------- C restatement (oracle/mpm_oracle.c) -------------------- #
+@pytest.mark.parametrize("name", ["kat3d", "block3d", "rest3d", "walls3d"])
+def test_c_oracle_3d_matches_reference(name):
+    """The plain-C port (independent polar algorithm: one-sided Jacobi SVD) vs the reference."""
+    from oracle import native as ON
+    g = load_golden(name)
+    p = _p3(g); G = p["res"] + 1
+    x, v, F, C, Jp = (g[k].copy() for k in ("x", "v", "F", "C", "Jp"))
+    gv = np.zeros((G, G, G, 3)); gm = np.zeros((G, G, G, 1))
+    ON.p2g_3d(p["inv_dx"], p["hardening"], p["dx"], p["dt"], p["volume"], gv, gm, x, g["mass"], g["mu0"], g["lam0"], v, F, C, Jp)
+    # F - R cancels ~1/strain digits (rest3d: strain 1e-4), so two different SVD algorithms
+    # agree to ~1e-16/strain on stress-dominated momentum: 1e-10 bounds all four cases.
+    tol = 1e-10
+    assert rel_err(gv, _grid(g, "grid_momentum")) < tol
+    assert rel_err(gm, _grid(g, "grid_mass")) < TIGHT
+    ON.grid_op_3d(p["res"], p["dx"], p["dt"], p["gravity"], gv, gm)
+    assert rel_err(gv, _grid(g, "grid_velocity")) < tol
+    ON.g2p_3d(p["inv_dx"], p["dt"], gv, x, v, F, C)
+    for got, key in ((x, "x_out"), (v, "v_out"), (F, "F_out"), (C, "C_out")):
+        assert rel_err(got, g[key]) < tol, key
+
+
+def test_c_oracle_2d_and_drivers():
+    from oracle import native as ON
+    g = load_golden("block2d"); p = _p2(g)
+    x, v, F, C, Jp = (g[k].copy() for k in ("x", "v", "F", "C", "Jp"))
+    gv, gm = ON.solve_mls_mpm_2d(p["res"], float(p["res"]), p["hardening"], p["mu_0"], p["lambda_0"], p["mass"],
+                                 1.0 / p["res"], p["dt"], p["volume"], p["gravity"], x, v, F, C, Jp)
+    assert rel_err(gv, g["grid_velocity"]) < TIGHT
+    for got, key in ((x, "x_out"), (v, "v_out"), (F, "F_out"), (C, "C_out"), (Jp, "Jp_out")):
+        assert rel_err(got, g[key]) < 1e-11, key
+    # 3D driver vs the NumPy oracle on the drift scene, 20 substeps
+    g = load_golden("drift3d")
+    x = g["x"].copy(); n = len(x)
+    v = np.zeros((n, 3)); F = np.tile(np.eye(3), (n, 1, 1)); C = np.zeros((n, 3, 3))
+    res = int(g["res"])
+    for step in range(1, 11):
+        ON.solve_mls_mpm_3d(res, float(res), float(g["hardening"]), 1.0 / res, float(g["dt"]), float(g["volume"]),
+                            float(g["gravity"]), x, g["mass"], g["mu0"], g["lam0"], v, F, C)
+        if step in (1, 10):
+            assert rel_err(x, g[f"x_{step}"]) < 1e-12
+            assert rel_err(v, g[f"v_{step}"]) < 1e-9
+            assert rel_err(F, g[f"F_{step}"]) < 1e-11
