@@ -49,6 +49,7 @@ struct FfMpmHandle {
   int64_t capacity;   // capacity the workspace was sized for (derived from ws_bytes)
   bool binned;        // bin buffers describe the live buffer
   int64_t launches;
+  int p2g_variant;    // 0 = warp-autonomous cell runs (default), 1 = CTA-per-tile (FFMPM_P2G_VARIANT=tile)
   int p2g_blocks_per_sm, g2p_blocks_per_sm;   // persistent-grid sizing (tunable: FFMPM_P2G_BPS / FFMPM_G2P_BPS)
 };
 
@@ -123,6 +124,7 @@ int ffmpm_create(const FfMpmConfig* cfg, int32_t device, FfMpmHandle** out) {
   d.mass = cfg->mass; d.mu0 = cfg->mu_0; d.lam0 = cfg->lambda_0;
   h->n_nodes = (int64_t)d.n[0] * d.n[1] * d.n[2];
   h->p2g_blocks_per_sm = 4;
+  if (const char* e = getenv("FFMPM_P2G_VARIANT")) h->p2g_variant = (strcmp(e, "tile") == 0) ? 1 : 0;
   h->g2p_blocks_per_sm = 8;
   if (const char* e = getenv("FFMPM_P2G_BPS")) { int v = atoi(e); if (v > 0 && v <= 32) h->p2g_blocks_per_sm = v; }
   if (const char* e = getenv("FFMPM_G2P_BPS")) { int v = atoi(e); if (v > 0 && v <= 32) h->g2p_blocks_per_sm = v; }
@@ -247,7 +249,9 @@ static int p2g_t(FfMpmHandle* h, cudaStream_t s) {
   if (mode == FFMPM_P2G_TILED) {
     if (h->cfg.dim != 3) return set_err(FFMPM_E_INVALID, "tiled P2G is 3D only (2D uses the scatter kernel)");
     if (!h->binned) return set_err(FFMPM_E_STATE, "tiled P2G needs ffmpm_bin first");
-    int nl = p2g_tiled<T>(h->dev, sv, h->n, h->bin, (T*)h->grid, h->err, h->sm_count, h->p2g_blocks_per_sm, s);
+    int nl = h->p2g_variant == 1
+                 ? p2g_tiled<T>(h->dev, sv, h->n, h->bin, (T*)h->grid, h->err, h->sm_count, h->p2g_blocks_per_sm, s)
+                 : p2g_runs<T>(h->dev, sv, h->n, h->bin, (T*)h->grid, h->err, h->sm_count, h->p2g_blocks_per_sm, s);
     return check_launch(h, nl);
   }
   unsigned blocks = (unsigned)((h->n + 127) / 128);

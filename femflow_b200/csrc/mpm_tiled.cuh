@@ -10,6 +10,7 @@
 #include "mpm_bin.cuh"
 #include "mpm_common.cuh"
 #include "mpm_direct.cuh"
+#include "mpm_p2g_runs.cuh"
 
 namespace ffmpm {
 
