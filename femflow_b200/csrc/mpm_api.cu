@@ -49,7 +49,7 @@ struct FfMpmHandle {
   int64_t capacity;   // capacity the workspace was sized for (derived from ws_bytes)
   bool binned;        // bin buffers describe the live buffer
   int64_t launches;
-  int p2g_variant;    // 0 = warp-autonomous cell runs (default), 1 = CTA-per-tile (FFMPM_P2G_VARIANT=tile)
+  bool prebinned;     // keys/rank/histogram of the live buffer were emitted by the last tiled G2P
   int p2g_blocks_per_sm, g2p_blocks_per_sm;   // persistent-grid sizing (tunable: FFMPM_P2G_BPS / FFMPM_G2P_BPS)
 };
 
@@ -124,7 +124,6 @@ int ffmpm_create(const FfMpmConfig* cfg, int32_t device, FfMpmHandle** out) {
   d.mass = cfg->mass; d.mu0 = cfg->mu_0; d.lam0 = cfg->lambda_0;
   h->n_nodes = (int64_t)d.n[0] * d.n[1] * d.n[2];
   h->p2g_blocks_per_sm = 4;
-  if (const char* e = getenv("FFMPM_P2G_VARIANT")) h->p2g_variant = (strcmp(e, "tile") == 0) ? 1 : 0;
   h->g2p_blocks_per_sm = 8;
   if (const char* e = getenv("FFMPM_P2G_BPS")) { int v = atoi(e); if (v > 0 && v <= 32) h->p2g_blocks_per_sm = v; }
   if (const char* e = getenv("FFMPM_G2P_BPS")) { int v = atoi(e); if (v > 0 && v <= 32) h->g2p_blocks_per_sm = v; }
@@ -183,6 +182,7 @@ int ffmpm_bind_state(FfMpmHandle* h, const FfMpmState* cur, const FfMpmState* al
   h->live = 0;
   h->n = n;
   h->binned = false;
+  h->prebinned = false;
   return FFMPM_OK;
 }
 
@@ -192,6 +192,7 @@ int ffmpm_set_num_particles(FfMpmHandle* h, int64_t n) {
   if (!h || n < 0 || n > h->st[0].stride) return set_err(FFMPM_E_INVALID, "bad particle count");
   h->n = n;
   h->binned = false;
+  h->prebinned = false;
   return FFMPM_OK;
 }
 
@@ -229,8 +230,9 @@ int ffmpm_clear_grid(FfMpmHandle* h, void* stream) {
 template <typename T>
 static int bin_t(FfMpmHandle* h, cudaStream_t s) {
   if (h->n > h->capacity) return set_err(FFMPM_E_STATE, "workspace too small for this particle count");
-  int nl = bin_particles<T>(h->dev, view<T>(h->st[h->live]), h->n, h->bin, h->err, s);
+  int nl = bin_particles<T>(h->dev, view<T>(h->st[h->live]), h->n, h->bin, h->err, h->prebinned, s);
   h->binned = true;
+  h->prebinned = false;
   return check_launch(h, nl);
 }
 
@@ -249,9 +251,7 @@ static int p2g_t(FfMpmHandle* h, cudaStream_t s) {
   if (mode == FFMPM_P2G_TILED) {
     if (h->cfg.dim != 3) return set_err(FFMPM_E_INVALID, "tiled P2G is 3D only (2D uses the scatter kernel)");
     if (!h->binned) return set_err(FFMPM_E_STATE, "tiled P2G needs ffmpm_bin first");
-    int nl = h->p2g_variant == 1
-                 ? p2g_tiled<T>(h->dev, sv, h->n, h->bin, (T*)h->grid, h->err, h->sm_count, h->p2g_blocks_per_sm, s)
-                 : p2g_runs<T>(h->dev, sv, h->n, h->bin, (T*)h->grid, h->err, h->sm_count, h->p2g_blocks_per_sm, s);
+    int nl = p2g_runs<T>(h->dev, sv, h->n, h->bin, (T*)h->grid, h->err, h->sm_count, h->p2g_blocks_per_sm, s);
     return check_launch(h, nl);
   }
   unsigned blocks = (unsigned)((h->n + 127) / 128);
@@ -291,9 +291,11 @@ static int g2p_t(FfMpmHandle* h, cudaStream_t s) {
   if (h->binned && h->have_alt && h->cfg.dim == 3) {
     // binned: gather through the permutation, write back in binned order into the other buffer
     StateView<T> dst = view<T>(h->st[h->live ^ 1]);
+    bin_clear_histogram(h->bin, s);   // the kernel pre-bins the advected particles for the next substep
     int nl = g2p_tiled<T>(h->dev, sv, dst, h->n, h->bin, (const T*)h->grid, h->err, h->sm_count, h->g2p_blocks_per_sm, s);
     h->live ^= 1;
-    h->binned = false;  // positions moved: keys are stale
+    h->binned = false;  // positions moved: perm / cell offsets are stale ...
+    h->prebinned = true;  // ... but keys, ranks and the histogram of the new live buffer are ready
     return check_launch(h, nl);
   }
   unsigned blocks = (unsigned)((h->n + 127) / 128);
@@ -302,6 +304,7 @@ static int g2p_t(FfMpmHandle* h, cudaStream_t s) {
   else
     g2p_gather2_kernel<T><<<blocks, 128, 0, s>>>(h->dev, sv, h->n, (const T*)h->grid, h->err);
   h->binned = false;
+  h->prebinned = false;
   return check_launch(h, 1);
 }
 

@@ -94,42 +94,51 @@ __device__ __forceinline__ int bin_key2(int bx, int by, int ty) {
   return tile * TILE_CELLS + ((bx & 7) << 3) + (by & 7);
 }
 
+// Bin key of a particle position: tile-major id of its LOCAL base cell, or n_cells
+// when the stencil would leave the grid (utils.py:138-150) / the position is NaN.
+template <typename T>
+__device__ __forceinline__ int bin_key_of(const DevCfg& cfg, const BinBuffers& B, T x0, T x1, T x2) {
+  const T xs[3] = {x0, x1, x2};
+  int b[3] = {0, 0, 0};
+  bool ok = true;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    if (d < cfg.dim) {
+      T fx;
+      int g;
+      base_fx(xs[d], cfg.inv_dx, g, fx);
+      b[d] = g - cfg.origin[d];
+      ok = ok && !isnan((double)xs[d]) && b[d] >= 0 && b[d] + 2 < cfg.n[d];
+    }
+  }
+  if (!ok) return B.n_cells;
+  return cfg.dim == 3 ? bin_key3(b[0], b[1], b[2], B.tiles[1], B.tiles[2]) : bin_key2(b[0], b[1], B.tiles[1]);
+}
+
+// Warp-aggregated histogram: one atomic per distinct key per warp; the lanes of a group
+// take consecutive ranks in lane order.  Must be called by all 32 lanes; key < 0 = idle.
+__device__ __forceinline__ void bin_rank_warp(const BinBuffers& B, int key, long long slot) {
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned peers = __match_any_sync(0xffffffffu, key);
+  if (key >= 0) {
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if ((int)lane == leader) base = atomicAdd(&B.cell_count[key], __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    B.rank[slot] = base + __popc(peers & ((1u << lane) - 1u));
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) bin_count_kernel(DevCfg cfg, StateView<T> s, long long n, BinBuffers B) {
   long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int key = -1;
   if (p < n) {
     const long long st = s.stride;
-    int b[3] = {0, 0, 0};
-    bool ok = true;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      if (d < cfg.dim) {
-        T xs = s.x[d * st + p];
-        T fx;
-        int g;
-        base_fx(xs, cfg.inv_dx, g, fx);
-        b[d] = g - cfg.origin[d];
-        ok = ok && !isnan((double)xs) && b[d] >= 0 && b[d] + 2 < cfg.n[d];
-      }
-    }
-    if (!ok)
-      key = B.n_cells;
-    else
-      key = cfg.dim == 3 ? bin_key3(b[0], b[1], b[2], B.tiles[1], B.tiles[2]) : bin_key2(b[0], b[1], B.tiles[1]);
+    key = bin_key_of<T>(cfg, B, s.x[p], cfg.dim > 1 ? s.x[st + p] : (T)0, cfg.dim > 2 ? s.x[2 * st + p] : (T)0);
     B.keys[p] = key;
   }
-  // warp-aggregated histogram: one atomic per distinct key per warp; lanes of a group
-  // take consecutive ranks in lane order
-  unsigned lane = threadIdx.x & 31;
-  unsigned peers = __match_any_sync(0xffffffffu, key);
-  if (key >= 0) {
-    int leader = __ffs(peers) - 1;
-    int base = 0;
-    if ((int)lane == leader) base = atomicAdd(&B.cell_count[key], __popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    B.rank[p] = base + __popc(peers & ((1u << lane) - 1u));
-  }
+  bin_rank_warp(B, key, p);
 }
 
 // ---- exclusive scan of cell_count[0 .. m) into cell_off, m = n_cells + 2 ----
@@ -231,20 +240,33 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(long long n, BinBuffer
   if (key == B.n_cells) atomicAdd(&err->n_oob, 1ULL);
 }
 
-// Returns the number of kernel launches issued.
+// Clears the histogram (and nothing else): issued before a kernel that pre-bins.
+inline void bin_clear_histogram(BinBuffers& B, cudaStream_t st) {
+  cudaMemsetAsync(B.cell_count, 0, (size_t)(B.n_cells + 2) * sizeof(int32_t), st);
+}
+
+// Returns the number of kernel launches issued.  `prebinned`: keys / rank / histogram
+// of the live buffer were already produced by the previous G2P.
 template <typename T>
-int bin_particles(const DevCfg& cfg, const StateView<T>& s, long long n, BinBuffers& B, ErrRec* err, cudaStream_t st) {
+int bin_particles(const DevCfg& cfg, const StateView<T>& s, long long n, BinBuffers& B, ErrRec* err, bool prebinned,
+                  cudaStream_t st) {
   const int m = B.n_cells + 2;
-  // counters (16 ints, 256 B slot) + histogram in one clear
-  cudaMemsetAsync(B.counters, 0, (size_t)((char*)(B.cell_count + m) - (char*)B.counters), st);
   unsigned pb = (unsigned)((n + 255) / 256);
-  bin_count_kernel<T><<<pb, 256, 0, st>>>(cfg, s, n, B);
+  int launches = 5;
+  if (prebinned) {
+    cudaMemsetAsync(B.counters, 0, 16 * sizeof(int32_t), st);
+  } else {
+    // counters (16 ints, 256 B slot) + histogram in one clear
+    cudaMemsetAsync(B.counters, 0, (size_t)((char*)(B.cell_count + m) - (char*)B.counters), st);
+    bin_count_kernel<T><<<pb, 256, 0, st>>>(cfg, s, n, B);
+    launches = 6;
+  }
   scan_reduce_kernel<<<B.n_scan_blocks, SCAN_THREADS, 0, st>>>(B.cell_count, m, B.block_sums);
   scan_block_sums_kernel<<<1, 1024, 0, st>>>(B.block_sums, B.n_scan_blocks);
   scan_downsweep_kernel<<<B.n_scan_blocks, SCAN_THREADS, 0, st>>>(B.cell_count, m, B.block_sums, B.cell_off);
   active_tiles_kernel<<<(B.n_tiles + 255) / 256, 256, 0, st>>>(B);
   bin_scatter_kernel<<<pb, 256, 0, st>>>(n, B, err);
-  return 6;
+  return launches;
 }
 
 }  // namespace ffmpm

@@ -3,15 +3,20 @@
 // Every warp owns windows of P2G_WINDOW consecutive binned slots and never talks to
 // another warp (no block barrier, no shared grid tile, no work counter):
 //   phase 1 (lane per particle)   gather the state through `perm`, evaluate the polar
-//           decomposition / fixed-corotated stress in fp64 (three_d/p2g.py:57-65) and
-//           park {m v, m, affine*dx, fx, wz} in the warp's private smem slab;
-//   runs    a ballot over "my cell differs from my predecessor's" splits the window
-//           into runs of particles that share a base cell;
-//   phase 2 (lane per (run, stencil column (i,j)))   walk the run, accumulating the
-//           column's three nodes x {momentum, mass} in registers
-//           (three_d/p2g.py:67-80), then ONE red.global.add.v4.f32 per node.
+//           decomposition / fixed-corotated stress (three_d/p2g.py:57-65) and park
+//           {m v, m, affine*dx, fx} in the warp's private smem slab;
+//   runs    a ballot over "my base cell differs from my predecessor's" splits the
+//           window into runs of particles that share a base cell;
+//   phase 2 (lane per (run, x-slab i))   walk the run, accumulating the slab's nine
+//           nodes x {momentum, mass} in registers (three_d/p2g.py:67-80), then ONE
+//           red.global.add.v4.f32 per node.
 // Same-node contributions of all particles of a cell are therefore summed on chip and
 // leave the SM as 27 vector reductions per run instead of 27 per particle.
+//
+// Shared-memory layout: four float4 planes indexed by a padded slot q + q/8.  With
+// ~8 particles per cell the lanes of one LDS.128 read particles ~8 slots apart;
+// without the padding those 16-byte chunks fall on the same banks (measured: 5.3
+// wavefronts per LDS.128 against 3.0 ideal, profiles/r01c).
 #pragma once
 #include <cstdlib>
 
@@ -21,21 +26,20 @@
 
 namespace ffmpm {
 
-constexpr int P2G_WINDOW = 64;       // slots per warp window (2 per lane)
-constexpr int P2G_RUN_WARPS = 4;     // warps per CTA
+constexpr int P2G_WINDOW = 64;                           // slots per warp window (2 per lane)
+constexpr int P2G_PADDED = P2G_WINDOW + P2G_WINDOW / 8;  // padded slab length
+constexpr int P2G_RUN_WARPS = 4;                         // warps per CTA
+
+__device__ __forceinline__ int p2g_pad(int q) { return q + (q >> 3); }
 
 template <typename T>
-struct alignas(16) P2GRunPayload {
-  T mvx, mvy, mvz, m;
-  T a00, a01, a02, fx;   // a = affine * dx
-  T a10, a11, a12, fy;
-  T a20, a21, a22, fz;
-  T wz0, wz1, wz2, pad;
+struct alignas(16) P2GVec4 {
+  T x, y, z, w;
 };
 
 template <typename T>
 struct P2GWarpSlab {
-  P2GRunPayload<T> pay[P2G_WINDOW];
+  P2GVec4<T> pay[4][P2G_PADDED];  // {mvx,mvy,mvz,m} {a00,a01,a02,fx} {a10,a11,a12,fy} {a20,a21,a22,fz}, a = affine*dx
   int node0[P2G_WINDOW];          // linear LOCAL node id of the particle's base cell
   int run_start[P2G_WINDOW + 1];  // window-relative first slot of each run (+ sentinel)
 };
@@ -65,14 +69,11 @@ p2g_runs3_kernel(DevCfg cfg, StateView<T> s, BinBuffers B, T* __restrict__ grid,
       if (idx < cnt) {
         const long long p = B.perm[w0 + idx];
         P2GParticle3<T> q = p2g_prepare3(cfg, s, p);
-        P2GRunPayload<T> pl;
-        pl.mvx = q.mvx; pl.mvy = q.mvy; pl.mvz = q.mvz; pl.m = q.m;
-        pl.a00 = q.a00 * dx; pl.a01 = q.a01 * dx; pl.a02 = q.a02 * dx; pl.fx = q.fx;
-        pl.a10 = q.a10 * dx; pl.a11 = q.a11 * dx; pl.a12 = q.a12 * dx; pl.fy = q.fy;
-        pl.a20 = q.a20 * dx; pl.a21 = q.a21 * dx; pl.a22 = q.a22 * dx; pl.fz = q.fz;
-        bspline(q.fz, pl.wz0, pl.wz1, pl.wz2);
-        pl.pad = (T)0;
-        S.pay[idx] = pl;
+        const int ph = p2g_pad(idx);
+        S.pay[0][ph] = P2GVec4<T>{q.mvx, q.mvy, q.mvz, q.m};
+        S.pay[1][ph] = P2GVec4<T>{q.a00 * dx, q.a01 * dx, q.a02 * dx, q.fx};
+        S.pay[2][ph] = P2GVec4<T>{q.a10 * dx, q.a11 * dx, q.a12 * dx, q.fy};
+        S.pay[3][ph] = P2GVec4<T>{q.a20 * dx, q.a21 * dx, q.a22 * dx, q.fz};
         node[h] = (q.bx * ny + q.by) * nz + q.bz;
         S.node0[idx] = node[h];
       }
@@ -95,35 +96,50 @@ p2g_runs3_kernel(DevCfg cfg, StateView<T> s, BinBuffers B, T* __restrict__ grid,
       if (lane == 0) S.run_start[n_runs] = cnt;
     }
     __syncwarp();
-    // ---- phase 2 ----
-    const int n_items = n_runs * 9;
+    // ---- phase 2: lane per (run, x-slab) ----
+    const int n_items = n_runs * 3;
     for (int item = lane; item < n_items; item += 32) {
-      const int r = item / 9, col = item - r * 9;
+      const int r = item / 3, li = item - r * 3;
       const int r0 = S.run_start[r], r1 = S.run_start[r + 1];
-      const int li = col / 3, lj = col - li * 3;
-      const T ci = (T)li, cj = (T)lj;
-      // B-spline piece of this column per axis: w = s * (f - c)^2 + o  (three_d/p2g.py:55)
+      const T ci = (T)li;
+      // B-spline piece of this slab along x: w = s * (f - c)^2 + o  (three_d/p2g.py:55)
       const T sx = li == 1 ? (T)-1 : (T)0.5, cx_ = (T)1.5 - (T)0.5 * ci, ox_ = li == 1 ? (T)0.75 : (T)0;
-      const T sy = lj == 1 ? (T)-1 : (T)0.5, cy_ = (T)1.5 - (T)0.5 * cj, oy_ = lj == 1 ? (T)0.75 : (T)0;
-      T x0 = 0, y0 = 0, z0 = 0, m0 = 0, x1 = 0, y1 = 0, z1 = 0, m1 = 0, x2 = 0, y2 = 0, z2 = 0, m2 = 0;
+      T ax[9], ay[9], az[9], am[9];
+#pragma unroll
+      for (int e = 0; e < 9; ++e) ax[e] = ay[e] = az[e] = am[e] = (T)0;
       for (int qi = r0; qi < r1; ++qi) {
-        const P2GRunPayload<T> pl = S.pay[qi];
-        const T tx_ = pl.fx - cx_, ty_ = pl.fy - cy_;
-        const T wij = (sx * tx_ * tx_ + ox_) * (sy * ty_ * ty_ + oy_);
-        const T dpx = ci - pl.fx, dpy = cj - pl.fy;
-        const T bx = pl.mvx + (pl.a00 * dpx + pl.a01 * dpy);
-        const T by = pl.mvy + (pl.a10 * dpx + pl.a11 * dpy);
-        const T bz = pl.mvz + (pl.a20 * dpx + pl.a21 * dpy);
-        const T d0 = -pl.fz, d1 = (T)1 - pl.fz, d2 = (T)2 - pl.fz;
-        const T w0_ = wij * pl.wz0, w1_ = wij * pl.wz1, w2_ = wij * pl.wz2;
-        x0 += w0_ * (bx + pl.a02 * d0); y0 += w0_ * (by + pl.a12 * d0); z0 += w0_ * (bz + pl.a22 * d0); m0 += w0_ * pl.m;
-        x1 += w1_ * (bx + pl.a02 * d1); y1 += w1_ * (by + pl.a12 * d1); z1 += w1_ * (bz + pl.a22 * d1); m1 += w1_ * pl.m;
-        x2 += w2_ * (bx + pl.a02 * d2); y2 += w2_ * (by + pl.a12 * d2); z2 += w2_ * (bz + pl.a22 * d2); m2 += w2_ * pl.m;
+        const int ph = p2g_pad(qi);
+        const P2GVec4<T> p0 = S.pay[0][ph], p1 = S.pay[1][ph], p2 = S.pay[2][ph], p3 = S.pay[3][ph];
+        const T fx = p1.w, fy = p2.w, fz = p3.w;
+        T wy[3], wz[3];
+        bspline(fy, wy[0], wy[1], wy[2]);
+        bspline(fz, wz[0], wz[1], wz[2]);
+        const T tx_ = fx - cx_;
+        const T wxi = sx * tx_ * tx_ + ox_;
+        const T dpx = ci - fx;
+        const T bx = p0.x + p1.x * dpx, by = p0.y + p2.x * dpx, bz = p0.z + p3.x * dpx;
+        const T dz[3] = {-fz, (T)1 - fz, (T)2 - fz};
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const T dpy = (T)j - fy;
+          const T wij = wxi * wy[j];
+          const T cxj = bx + p1.y * dpy, cyj = by + p2.y * dpy, czj = bz + p3.y * dpy;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const T w = wij * wz[k];
+            ax[j * 3 + k] += w * (cxj + p1.z * dz[k]);
+            ay[j * 3 + k] += w * (cyj + p2.z * dz[k]);
+            az[j * 3 + k] += w * (czj + p3.z * dz[k]);
+            am[j * 3 + k] += w * p0.w;
+          }
+        }
       }
-      T* g = grid + ((long long)S.node0[r0] + (long long)(li * ny + lj) * nz) * 4;
-      red_add4(g, x0, y0, z0, m0);
-      red_add4(g + 4, x1, y1, z1, m1);
-      red_add4(g + 8, x2, y2, z2, m2);
+      T* g = grid + ((long long)S.node0[r0] + (long long)li * ny * nz) * 4;
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          red_add4(g + ((long long)j * nz + k) * 4, ax[j * 3 + k], ay[j * 3 + k], az[j * 3 + k], am[j * 3 + k]);
     }
     __syncwarp();   // the slab is rewritten by the next window
   }
@@ -137,14 +153,14 @@ int p2g_runs(const DevCfg& cfg, const StateView<T>& s, long long n, BinBuffers& 
   long long cap = (long long)sm_count * blocks_per_sm;
   int blocks = (int)(want < cap ? want : cap);
   if (blocks < 1) blocks = 1;
-  // MIN_BLOCKS trades registers (fp64 polar iteration) for resident warps; tunable via FFMPM_P2G_MINB
+  // MIN_BLOCKS trades registers for resident warps; tunable via FFMPM_P2G_MINB
   static int minb = [] { const char* e = getenv("FFMPM_P2G_MINB"); return e ? atoi(e) : 4; }();
-  if (minb >= 8)
-    p2g_runs3_kernel<T, 8><<<blocks, P2G_RUN_WARPS * 32, 0, st>>>(cfg, s, B, grid, err);
-  else if (minb >= 6)
+  if (minb >= 6)
     p2g_runs3_kernel<T, 6><<<blocks, P2G_RUN_WARPS * 32, 0, st>>>(cfg, s, B, grid, err);
   else if (minb == 5)
     p2g_runs3_kernel<T, 5><<<blocks, P2G_RUN_WARPS * 32, 0, st>>>(cfg, s, B, grid, err);
+  else if (minb == 3)
+    p2g_runs3_kernel<T, 3><<<blocks, P2G_RUN_WARPS * 32, 0, st>>>(cfg, s, B, grid, err);
   else
     p2g_runs3_kernel<T, 4><<<blocks, P2G_RUN_WARPS * 32, 0, st>>>(cfg, s, B, grid, err);
   return 1;
