@@ -53,6 +53,7 @@ PROTOTYPES = {
     "ffmpm_p2g": (C.c_int, [H, C.c_void_p]),
     "ffmpm_grid_op": (C.c_int, [H, C.c_void_p]),
     "ffmpm_g2p": (C.c_int, [H, C.c_void_p]),
+    "ffmpm_grid_op_halo": (C.c_int, [H, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     "ffmpm_substep": (C.c_int, [H, C.c_int32, C.c_void_p]),
     "ffmpm_grid_ptr": (C.c_int, [H, C.POINTER(C.c_void_p)]),
     "ffmpm_bin_ptrs": (C.c_int, [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),

@@ -270,10 +270,12 @@ int ffmpm_p2g(FfMpmHandle* h, void* stream) {
 }
 
 template <typename T>
-static int grid_op_t(FfMpmHandle* h, cudaStream_t s) {
+static int grid_op_t(FfMpmHandle* h, cudaStream_t s, const void* halo_lo = nullptr, long long nodes_lo = 0,
+                     const void* halo_hi = nullptr, long long nodes_hi = 0) {
   unsigned blocks = (unsigned)((h->n_nodes + 255) / 256);
   if (h->cfg.dim == 3)
-    grid_op3_kernel<T><<<blocks, 256, 0, s>>>(h->dev, (T*)h->grid, h->n_nodes);
+    grid_op3_kernel<T><<<blocks, 256, 0, s>>>(h->dev, (T*)h->grid, h->n_nodes, (const T*)halo_lo, nodes_lo,
+                                               (const T*)halo_hi, nodes_hi);
   else
     grid_op2_kernel<T><<<blocks, 256, 0, s>>>(h->dev, (T*)h->grid, h->n_nodes);
   return check_launch(h, 1);
@@ -283,6 +285,20 @@ int ffmpm_grid_op(FfMpmHandle* h, void* stream) {
   int rc = ready(h);
   if (rc) return rc;
   return h->cfg.dtype == FFMPM_F64 ? grid_op_t<double>(h, (cudaStream_t)stream) : grid_op_t<float>(h, (cudaStream_t)stream);
+}
+
+int ffmpm_grid_op_halo(FfMpmHandle* h, const void* recv_lo, int32_t planes_lo, const void* recv_hi, int32_t planes_hi,
+                       void* stream) {
+  int rc = ready(h);
+  if (rc) return rc;
+  if (h->cfg.dim != 3) return set_err(FFMPM_E_INVALID, "slab halos are 3D only");
+  if (planes_lo < 0 || planes_hi < 0 || planes_lo + planes_hi > h->dev.n[0] || (planes_lo && !recv_lo) ||
+      (planes_hi && !recv_hi))
+    return set_err(FFMPM_E_INVALID, "bad halo planes");
+  const long long plane = (long long)h->dev.n[1] * h->dev.n[2];
+  return h->cfg.dtype == FFMPM_F64
+             ? grid_op_t<double>(h, (cudaStream_t)stream, recv_lo, planes_lo * plane, recv_hi, planes_hi * plane)
+             : grid_op_t<float>(h, (cudaStream_t)stream, recv_lo, planes_lo * plane, recv_hi, planes_hi * plane);
 }
 
 template <typename T>

@@ -165,11 +165,23 @@ __global__ void __launch_bounds__(128) p2g_scatter2_kernel(DevCfg cfg, StateView
 // 3D (three_d/grid_op.py:25-47): v = mom/mass, v.y += dt*g, clamp to +-0.9 dx/dt,
 // then zero component d on nodes with global index I[d] < 1 or I[d] >= R-1 (quirk 5).
 template <typename T>
-__global__ void __launch_bounds__(256) grid_op3_kernel(DevCfg cfg, T* __restrict__ grid, long long n_nodes) {
+__global__ void __launch_bounds__(256) grid_op3_kernel(DevCfg cfg, T* __restrict__ grid, long long n_nodes,
+                                                       const T* __restrict__ halo_lo, long long nodes_lo,
+                                                       const T* __restrict__ halo_hi, long long nodes_hi) {
   long long node = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (node >= n_nodes) return;
   using V4 = typename Vec4<T>::type;
   V4 g = reinterpret_cast<V4*>(grid)[node];
+  // Halo SUM fused into the load: the neighbour slabs' partial {momentum, mass} of the
+  // shared node planes (first nodes_lo / last nodes_hi nodes of the C-order grid).
+  if (node < nodes_lo) {
+    const V4 h = reinterpret_cast<const V4*>(halo_lo)[node];
+    g.x += h.x; g.y += h.y; g.z += h.z; g.w += h.w;
+  }
+  if (node >= n_nodes - nodes_hi) {
+    const V4 h = reinterpret_cast<const V4*>(halo_hi)[node - (n_nodes - nodes_hi)];
+    g.x += h.x; g.y += h.y; g.z += h.z; g.w += h.w;
+  }
   // empty node with zero momentum: velocity stays zero under the wall projection
   if (!(g.w > (T)0) && g.x == (T)0 && g.y == (T)0 && g.z == (T)0) return;
   int k = (int)(node % cfg.n[2]);

@@ -1,0 +1,332 @@
+"""Slab decomposition of the MPM substep across the GPUs of one box (new: the
+reference is a single serial process).
+
+The global grid is cut into slabs of node planes along axis 0 (the slowest axis of
+the C-order grid, so a node plane is one contiguous block).  A particle belongs to
+the rank that owns its base cell ``base.x``.  Per substep each rank
+
+  1. scatters its particles into its local grid (bin + P2G),
+  2. exchanges the node planes it shares with its two neighbours and SUMS them
+     (the sum is fused into the grid update's load, ``ffmpm_grid_op_halo``),
+  3. runs the grid update on every local plane (the shared planes are computed
+     redundantly and bit-identically on both sides: a + b == b + a),
+  4. gathers (G2P),
+
+and every ``migrate_every`` substeps hands the particles whose base cell left its
+range to the +-1 neighbour.  The local grid carries ``margin`` extra cell layers on
+each side so that a particle may stray that far between migrations (the reference's
+CFL clamp, three_d/grid_op.py:25,34-36, bounds the motion to < 1 cell per substep).
+
+``SlabPlan`` and ``SlabDriver`` are pure host logic over an abstract local solver and
+``torch.distributed`` point-to-point ops, so the exchange protocol is unit-tested on
+CPU (gloo) with a NumPy stand-in; on GPUs the local solver is ``CudaSlab`` (NCCL).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+# --------------------------------------------------------------------------- #
+@dataclass
+class SlabPlan:
+    """Ownership and halo geometry of one rank."""
+    res: Tuple[int, int, int]
+    world: int
+    rank: int
+    margin: int
+    own_lo: int      # owned base cells [own_lo, own_hi) along x
+    own_hi: int
+    g_lo: int        # local node planes [g_lo, g_hi) (global indices)
+    g_hi: int
+    planes_lo: int   # planes shared with rank-1 (the first planes of the local grid)
+    planes_hi: int   # planes shared with rank+1 (the last planes of the local grid)
+
+    @property
+    def n_local_x(self) -> int:
+        return self.g_hi - self.g_lo
+
+    @staticmethod
+    def ranges(res_x: int, world: int) -> List[Tuple[int, int]]:
+        """Even split of the valid base cells 0 .. res_x-2 (utils.py:138-150)."""
+        cells = res_x - 1
+        base, rem = divmod(cells, world)
+        out, lo = [], 0
+        for r in range(world):
+            hi = lo + base + (1 if r < rem else 0)
+            out.append((lo, hi))
+            lo = hi
+        return out
+
+    @classmethod
+    def make(cls, res: Sequence[int], world: int, rank: int, margin: int = 2) -> "SlabPlan":
+        res = tuple(int(r) for r in res)
+        rng = cls.ranges(res[0], world)
+        G = res[0] + 1
+
+        def nodes(r):
+            lo, hi = rng[r]
+            return max(0, lo - margin), min(G, hi + margin + 2)
+        for lo, hi in rng:
+            if world > 1 and hi - lo < 2 * margin + 2:
+                raise ValueError("slabs are thinner than 2*margin+2 cells: halos would reach past the neighbour")
+        g_lo, g_hi = nodes(rank)
+        planes_lo = nodes(rank - 1)[1] - g_lo if rank > 0 else 0
+        planes_hi = g_hi - nodes(rank + 1)[0] if rank < world - 1 else 0
+        return cls(res, world, rank, margin, rng[rank][0], rng[rank][1], g_lo, g_hi, planes_lo, planes_hi)
+
+
+# --------------------------------------------------------------------------- #
+class LocalSlab:
+    """What SlabDriver needs from a rank-local solver (CudaSlab here, a NumPy
+    stand-in in tests/)."""
+    device: torch.device
+    dtype: torch.dtype
+    num_particles: int
+
+    def scatter(self) -> None:                      # clear grid, (bin,) P2G
+        raise NotImplementedError
+
+    def grid_planes(self, a: int, b: int) -> torch.Tensor:   # contiguous view of local planes [a, b)
+        raise NotImplementedError
+
+    def grid_update(self, recv_lo, planes_lo, recv_hi, planes_hi) -> None:
+        raise NotImplementedError
+
+    def gather(self) -> None:                       # G2P
+        raise NotImplementedError
+
+    def extract_leavers(self, own_lo: int, own_hi: int):     # -> (left, right) payloads; keeps the rest
+        raise NotImplementedError
+
+    def append(self, payload) -> None:
+        raise NotImplementedError
+
+    def payload_rows(self) -> int:
+        raise NotImplementedError
+
+
+class SlabDriver:
+    def __init__(self, plan: SlabPlan, local: LocalSlab, group=None, migrate_every: Optional[int] = None):
+        self.plan, self.local, self.group = plan, local, group
+        self.migrate_every = migrate_every if migrate_every is not None else max(1, plan.margin)
+        if self.migrate_every > max(1, plan.margin) and plan.world > 1:
+            raise ValueError("migrate_every must not exceed the halo margin (particles move < 1 cell per substep)")
+        self.steps = 0
+        p = plan
+        self.left = p.rank - 1 if p.rank > 0 else None
+        self.right = p.rank + 1 if p.rank < p.world - 1 else None
+        probe = local.grid_planes(0, 1)
+        shape_lo = (p.planes_lo,) + tuple(probe.shape[1:])
+        shape_hi = (p.planes_hi,) + tuple(probe.shape[1:])
+        self.recv_lo = torch.zeros(shape_lo, dtype=probe.dtype, device=probe.device)
+        self.recv_hi = torch.zeros(shape_hi, dtype=probe.dtype, device=probe.device)
+        self.halo_bytes = (self.recv_lo.numel() + self.recv_hi.numel()) * probe.element_size()
+        self.migrated = 0
+
+    # -- halo planes: exchange partial sums with both neighbours ------------------
+    def _exchange_halos(self) -> None:
+        p, L = self.plan, self.local
+        ops = []
+        if self.right is not None:
+            ops.append(dist.P2POp(dist.isend, L.grid_planes(p.n_local_x - p.planes_hi, p.n_local_x), self.right, self.group))
+            ops.append(dist.P2POp(dist.irecv, self.recv_hi, self.right, self.group))
+        if self.left is not None:
+            ops.append(dist.P2POp(dist.isend, L.grid_planes(0, p.planes_lo), self.left, self.group))
+            ops.append(dist.P2POp(dist.irecv, self.recv_lo, self.left, self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+    def substep(self, n: int = 1) -> None:
+        for _ in range(n):
+            self.local.scatter()
+            self._exchange_halos()
+            self.local.grid_update(self.recv_lo, self.plan.planes_lo, self.recv_hi, self.plan.planes_hi)
+            self.local.gather()
+            self.steps += 1
+            if self.plan.world > 1 and self.steps % self.migrate_every == 0:
+                self.migrate()
+
+    # -- particle migration to the +-1 neighbours -------------------------------
+    def migrate(self) -> None:
+        p, L = self.plan, self.local
+        left, right = L.extract_leavers(p.own_lo, p.own_hi)
+        dev = L.device
+        rows = L.payload_rows()
+        n_out = torch.tensor([left[0].shape[1] if self.left is not None else 0,
+                              right[0].shape[1] if self.right is not None else 0], dtype=torch.int64, device=dev)
+        n_in = torch.zeros(2, dtype=torch.int64, device=dev)
+        ops = []
+        if self.left is not None:
+            ops += [dist.P2POp(dist.isend, n_out[0:1], self.left, self.group),
+                    dist.P2POp(dist.irecv, n_in[0:1], self.left, self.group)]
+        if self.right is not None:
+            ops += [dist.P2POp(dist.isend, n_out[1:2], self.right, self.group),
+                    dist.P2POp(dist.irecv, n_in[1:2], self.right, self.group)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        cnt = n_in.tolist()
+        out_cnt = n_out.tolist()
+        recv = {}
+        ops = []
+        for side, nb, payload, k_out, k_in in (("l", self.left, left, out_cnt[0], cnt[0]),
+                                              ("r", self.right, right, out_cnt[1], cnt[1])):
+            if nb is None:
+                continue
+            if k_out:
+                ops += [dist.P2POp(dist.isend, payload[0].contiguous(), nb, self.group),
+                        dist.P2POp(dist.isend, payload[1].contiguous(), nb, self.group)]
+            if k_in:
+                recv[side] = (torch.empty((rows, k_in), dtype=L.dtype, device=dev),
+                              torch.empty((k_in,), dtype=torch.int32, device=dev))
+                ops += [dist.P2POp(dist.irecv, recv[side][0], nb, self.group),
+                        dist.P2POp(dist.irecv, recv[side][1], nb, self.group)]
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        for side in ("l", "r"):
+            if side in recv:
+                L.append(recv[side])
+                self.migrated += recv[side][0].shape[1]
+
+
+# --------------------------------------------------------------------------- #
+class CudaSlab(LocalSlab):
+    """Rank-local CUDA solver for one slab (wraps MpmSolver)."""
+
+    def __init__(self, plan: SlabPlan, dx: float, dt: float, volume: float, gravity: float, hardening: float, *,
+                 capacity: int, device, dtype=torch.float32, p2g_mode: str = "auto"):
+        from .mpm import MpmSolver
+        self.plan = plan
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.inv_dx = 1.0 / dx
+        self.solver = MpmSolver(3, list(plan.res), dt, volume, gravity, hardening, capacity=capacity, dx=dx,
+                                inv_dx=1.0 / dx, dtype=dtype, device=device,
+                                n_nodes=(plan.n_local_x, plan.res[1] + 1, plan.res[2] + 1),
+                                origin=(plan.g_lo, 0, 0), per_particle_material=True, p2g_mode=p2g_mode, reorder=True)
+
+    @property
+    def num_particles(self) -> int:
+        return self.solver.num_particles
+
+    def set_particles(self, x, v, F, C_, mass, mu0, lam0, ids) -> None:
+        s = self.solver
+        s.set_particles(x, v, F, C_, None, mass, mu0, lam0)
+        s.buffers[0].id[:s.num_particles] = torch.as_tensor(np.asarray(ids), device=self.device).to(torch.int32)
+
+    def scatter(self) -> None:
+        s = self.solver
+        s.clear_grid()
+        s.bin()
+        s.p2g()
+
+    def grid_planes(self, a: int, b: int) -> torch.Tensor:
+        return self.solver.grid()[a:b]
+
+    def grid_update(self, recv_lo, planes_lo, recv_hi, planes_hi) -> None:
+        from . import _native as N
+        s = self.solver
+        N.check(s.lib.ffmpm_grid_op_halo(s._h, recv_lo.data_ptr() if planes_lo else None, planes_lo,
+                                         recv_hi.data_ptr() if planes_hi else None, planes_hi, s._stream()))
+
+    def gather(self) -> None:
+        self.solver.g2p()
+
+    def payload_rows(self) -> int:
+        return 3 + 3 + 9 + 9 + 3
+
+    def _pack(self, b, idx):
+        rows = [b.x[:, idx], b.v[:, idx], b.C[:, idx], b.F[:, idx], b.mass[idx][None], b.mu0[idx][None], b.lam0[idx][None]]
+        return torch.cat(rows, 0), b.id[idx]
+
+    def extract_leavers(self, own_lo: int, own_hi: int):
+        """Host-synchronising stream compaction (round-1 plumbing in torch ops): split
+        the live buffer into (left leavers, right leavers, keepers) by the global base
+        cell of each particle, computed in f64 exactly as the kernels do."""
+        s = self.solver
+        b = s.live
+        n = s.num_particles
+        base = torch.trunc(b.x[0, :n].double() * self.inv_dx - 0.5)
+        left_idx = torch.nonzero(base < own_lo).flatten()
+        right_idx = torch.nonzero(base >= own_hi).flatten()
+        left, right = self._pack(b, left_idx), self._pack(b, right_idx)
+        if left_idx.numel() + right_idx.numel() > 0:
+            keep = torch.nonzero((base >= own_lo) & (base < own_hi)).flatten()
+            other = 1 - s.live_index
+            self._store(self._pack(b, keep), 0, other)     # compact the keepers into the idle buffer
+            s._bind(keep.numel(), cur=other)
+        return left, right
+
+    def _store(self, payload, at: int, buf: int) -> None:
+        data, ids = payload
+        k = data.shape[1]
+        b = self.solver.buffers[buf]
+        if at + k > b.cap:
+            raise RuntimeError(f"slab capacity {b.cap} exceeded by migration ({at + k} particles)")
+        b.x[:, at:at + k] = data[0:3]
+        b.v[:, at:at + k] = data[3:6]
+        b.C[:, at:at + k] = data[6:15]
+        b.F[:, at:at + k] = data[15:24]
+        b.mass[at:at + k] = data[24]
+        b.mu0[at:at + k] = data[25]
+        b.lam0[at:at + k] = data[26]
+        b.id[at:at + k] = ids
+
+    def append(self, payload) -> None:
+        s = self.solver
+        n = s.num_particles
+        live = s.live_index
+        self._store(payload, n, live)
+        s._bind(n + payload[0].shape[1], cur=live)
+
+    def state_by_id(self):
+        """(ids, x, v, F, C) of the local particles, for gathering / validation."""
+        s = self.solver
+        b, n = s.live, s.num_particles
+        return (b.id[:n].clone(), b.x[:, :n].t().contiguous(), b.v[:, :n].t().contiguous(),
+                b.F[:, :n].t().reshape(n, 3, 3).contiguous(), b.C[:, :n].t().reshape(n, 3, 3).contiguous())
+
+
+class SlabSolver:
+    """Convenience bundle used by bench.py: plan + CudaSlab + SlabDriver, with the
+    MpmSolver-like surface bench.py needs."""
+
+    def __init__(self, plan, local, driver):
+        self.plan, self.local, self.driver = plan, local, driver
+        self.reorder = True
+
+    @classmethod
+    def from_scene(cls, scene, rank: int, world: int, device, p2g_mode: str = "auto", margin: int = 2,
+                   capacity_factor: float = 1.25):
+        """Weak scaling (BASELINE configs[3]): the scene's block is replicated once per
+        rank along x; the global grid is (res*world) x res x res cells, dx = 1/res."""
+        res = scene.res
+        plan = SlabPlan.make((res * world, res, res), world, rank, margin)
+        dx = 1.0 / res
+        local = CudaSlab(plan, dx, scene.dt, scene.volume, scene.gravity, scene.hardening,
+                         capacity=int(scene.n * capacity_factor), device=device, p2g_mode=p2g_mode)
+        x = scene.x.copy()
+        x[:, 0] += np.float32(rank)          # shift the block into this rank's slab
+        ids = np.arange(scene.n, dtype=np.int64) + rank * scene.n
+        local.set_particles(x, scene.v, scene.F, scene.C, scene.mass, scene.mu_0, scene.lambda_0,
+                            (ids % (2 ** 31)).astype(np.int32))
+        return cls(plan, local, SlabDriver(plan, local))
+
+    @property
+    def num_particles(self) -> int:
+        return self.local.num_particles
+
+    def substep(self, n: int = 1) -> None:
+        self.driver.substep(n)
+
+    def poll_error(self) -> int:
+        return self.local.solver.poll_error()
+
+    def launch_count(self) -> int:
+        return self.local.solver.launch_count()

@@ -129,10 +129,13 @@ class MpmSolver:
         self._bind(0)
 
     # ------------------------------------------------------------------ #
-    def _bind(self, n: int) -> None:
-        cur = self.buffers[0].c_struct()
-        alt = self.buffers[1].c_struct() if self.reorder else None
-        N.check(self.lib.ffmpm_bind_state(self._h, C.byref(cur), C.byref(alt) if alt is not None else None, n))
+    def _bind(self, n: int, cur: int = 0) -> None:
+        """(Re)bind the particle buffers; ``cur`` picks which Python-side buffer holds
+        the live state (the other one becomes the ping-pong target)."""
+        self._order = [cur, 1 - cur] if self.reorder else [0]
+        c = self.buffers[self._order[0]].c_struct()
+        alt = self.buffers[self._order[1]].c_struct() if self.reorder else None
+        N.check(self.lib.ffmpm_bind_state(self._h, C.byref(c), C.byref(alt) if alt is not None else None, n))
         self.num_particles = n
 
     def close(self) -> None:
@@ -147,8 +150,12 @@ class MpmSolver:
             pass
 
     @property
+    def live_index(self) -> int:
+        return self._order[self.lib.ffmpm_live_buffer(self._h)]
+
+    @property
     def live(self) -> _StateBuffer:
-        return self.buffers[self.lib.ffmpm_live_buffer(self._h)]
+        return self.buffers[self.live_index]
 
     def _stream(self, stream=None):
         if stream is None:

@@ -122,6 +122,13 @@ int ffmpm_bin(FfMpmHandle* h, void* stream);
 int ffmpm_p2g(FfMpmHandle* h, void* stream);
 int ffmpm_grid_op(FfMpmHandle* h, void* stream);
 int ffmpm_g2p(FfMpmHandle* h, void* stream);
+/* Slab decomposition along axis 0 (new; the reference is single-process): the grid
+ * update with the halo SUM fused into its load.  recv_lo / recv_hi hold the
+ * neighbour ranks' partial {momentum, mass} for the first planes_lo / last planes_hi
+ * node planes of this rank's local grid (same node-major layout, contiguous because
+ * axis 0 is slowest).  With 0 planes it is ffmpm_grid_op. */
+int ffmpm_grid_op_halo(FfMpmHandle* h, const void* recv_lo, int32_t planes_lo, const void* recv_hi,
+                       int32_t planes_hi, void* stream);
 /* n_substeps x (clear, [bin,] p2g, grid_op, g2p). */
 int ffmpm_substep(FfMpmHandle* h, int32_t n_substeps, void* stream);
 
