@@ -146,6 +146,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--p2g-mode", default="auto")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--margin", type=int, default=4, help="slab halo margin in cells = substeps between migrations")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -171,7 +172,7 @@ def main():
     n = scene.n
     if world > 1:
         from femflow_b200.distributed import SlabSolver
-        solver = SlabSolver.from_scene(scene, rank, world, dev, p2g_mode=args.p2g_mode)
+        solver = SlabSolver.from_scene(scene, rank, world, dev, p2g_mode=args.p2g_mode, margin=args.margin)
     else:
         solver = MpmSolver(scene.dim, scene.res, scene.dt, scene.volume, scene.gravity, scene.hardening,
                            capacity=n, device=dev, mass=scene.mass, mu_0=scene.mu_0, lambda_0=scene.lambda_0,
@@ -240,44 +241,52 @@ def main():
 
     # ---- end to end through host buffers (pinned), every step: H2D state, substep, D2H result ----
     e2e = None
-    if world == 1:
+    if True:
         d = scene.dim
-        b = solver.buffers[0]
+        core = solver if world == 1 else solver.local.solver      # the MpmSolver that owns the buffers
+        n = core.num_particles
+        b = core.buffers[0]
         host_in = {k: torch.empty_like(getattr(b, k)[..., :n], device="cpu").pin_memory()
                    for k in ("x", "v", "C", "F") }
         for k in ("mass", "mu0", "lam0"):
             if getattr(b, k) is not None:
                 host_in[k] = torch.empty(n, dtype=b.x.dtype).pin_memory()
-        live = solver.live
+        live = core.live
         for k in host_in:
             host_in[k].copy_(getattr(live, k)[..., :n])
+        ids0 = live.id[:n].clone() if live.id is not None else None
         host_out = {k: torch.empty_like(host_in[k]).pin_memory() for k in ("x", "v", "C", "F")}
         h2d = sum(t.numel() * t.element_size() for t in host_in.values())
         d2h = sum(t.numel() * t.element_size() for t in host_out.values())
 
         def e2e_step():
-            bb = solver.buffers[0]
+            bb = core.buffers[0]
             for k, t in host_in.items():
                 getattr(bb, k)[..., :n].copy_(t, non_blocking=True)
             if bb.id is not None:
-                bb.id[:n] = torch.arange(n, dtype=torch.int32, device=dev)
-            solver._bind(n)
+                bb.id[:n] = ids0
+            core._bind(n)
             solver.substep(1)
-            lv = solver.live
+            lv = core.live
+            m = core.num_particles
             for k, t in host_out.items():
-                t.copy_(getattr(lv, k)[..., :n], non_blocking=True)
+                t[..., :m].copy_(getattr(lv, k)[..., :m], non_blocking=True)
 
         e2e_step()
-        torch.cuda.synchronize(dev)
+        barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.e2e_steps):
             e2e_step()
         e1.record()
-        torch.cuda.synchronize(dev)
+        barrier()
         e_ms = e0.elapsed_time(e1)
-        e2e = {"value": n * args.e2e_steps / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": e_ms / args.e2e_steps,
+        if world > 1:
+            t = torch.tensor([e_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_ms = float(t.item())
+        e2e = {"value": n_total * args.e2e_steps / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+               "d2h_bytes_per_step": d2h * world, "ms_per_step": e_ms / args.e2e_steps,
                "api": "ffmpm C ABI via MpmSolver (host SoA pinned buffers in, x/v/C/F out, every step)"}
 
     if rank != 0:
@@ -317,7 +326,9 @@ def main():
         "config": {"workload": scene.name, "particles_per_gpu": n, "particles_total": n_total,
                    "grid": f"{scene.res}^{scene.dim}", "dt": scene.dt, "p2g_mode": args.p2g_mode,
                    "l2": "inputs larger than L2 (no flush)" if n * 252 > 256e6 else "state fits in L2 (flagged)",
-                   "n_oob": n_oob},
+                   "n_oob": n_oob,
+                   "parallelism": (f"{world} slabs along x, halo sum over NCCL p2p every substep, migration every "
+                                   f"{args.margin} substeps") if world > 1 else "single GPU"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
     }
     print(json.dumps(line))

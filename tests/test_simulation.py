@@ -1,0 +1,74 @@
+"""Drop-in surface above the hot path: scene generators and MPMSimulation
+(reference femflow/simulation/mpm/{primitives,simulation}.py, paper_1.py:75-114)."""
+import os
+import time
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, rel_err
+
+
+class FakeMesh:
+    """What MPMSimulation.load reads from femflow.viz.mesh.Mesh: a flat float32 vertex vector."""
+
+    def __init__(self, pts):
+        self.vertices = np.asarray(pts, dtype=np.float32).reshape(-1)
+
+
+def test_scene_generators_reproduce_the_paper_scene():
+    """paper_1.multi_drop_experiment(0): 8321 gyroid + 27000 collider points."""
+    from femflow_b200.simulation.mpm import primitives as P
+    g = load_golden("c1_scene")
+    gy = P.generate_implicit_points("gyroid", 0.2, 0.3, 30).astype(np.float32)
+    gy[:, 1] += np.float32(0.1)
+    assert len(gy) == int(g["n_gyroid_full"]) == 8321
+    assert np.array_equal(gy[::8], g["gyroid_vertices"])
+    lo, hi = gy.min(0), gy.max(0)
+    c = P.generate_cube_points((lo[0], hi[0]), (lo[1], hi[1]), (lo[2], hi[2]), 30).astype(np.float32)
+    c[:, 1] += np.float32(3)
+    assert len(c) == int(g["n_collider_full"]) == 27000
+    assert np.array_equal(c[::8], g["collider_vertices"])
+    with pytest.raises(ValueError):
+        P.generate_implicit_points("nope", 0.2, 0.3, 4)
+    # numerics/geometry.py:101-116 lattice: axis 0 fastest, endpoints included
+    lat = P.grid(np.array((3, 2, 2)))
+    assert lat.shape == (12, 3) and np.allclose(lat[1], (0.5, 0, 0)) and np.allclose(lat[-1], (1, 1, 1))
+
+
+@pytest.mark.gpu
+def test_mpm_simulation_matches_reference_trajectory(tmp_path):
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from femflow_b200.simulation.mpm import MPMSimulation
+    g = load_golden("c1_scene")
+    outdir = str(tmp_path / "out")
+    # constructor arguments exactly as paper_1.py:52-67 passes them
+    sim = MPMSimulation(outdir, 10, float(g["dt"]), 1.0, 10.0, float(g["volume"]), float(g["gravity"]), 140, 1000,
+                        0.2, 0.4, float(g["hardening"]), int(g["res"]), float(g["tightening_coeff"]), progress=False)
+    sim.start()                       # not loaded yet: logs an error and returns (simulation.py:114-116)
+    assert not sim.running and not sim.loaded
+    meshes = [FakeMesh(g["gyroid_vertices"]), FakeMesh(g["collider_vertices"])]
+    with pytest.raises(ValueError):
+        sim.load(meshes=meshes, params=[(1.0, 140, 0.2)])
+    sim.load(meshes=meshes, params=[(1.0, 140, 0.2), (10.0, 1000, 0.4)])
+    assert sim.loaded and len(sim.displacements) == 1
+    n = len(sim.particles)
+    assert sim.displacements[0].shape == (3 * n,)
+    sim.start()
+    sim.join(120)
+    assert not sim.running and sim.error is None
+    assert len(sim.displacements) == 11
+    coeff = float(g["tightening_coeff"])
+    for step in (1, 10):
+        want = (g[f"x_{step}"] / coeff).reshape(-1)
+        assert rel_err(sim.displacements[step], want) < 1e-5 * step
+    assert rel_err(sim.particles.pos, g["x_10"], 1.0) < 1e-4
+    assert rel_err(sim.F, g["F_10"], 1.0) < 1e-4
+    files = sorted(os.listdir(outdir))
+    assert len(files) == 11 and "0.npy" in files and "10.npy" in files
+    assert np.array_equal(np.load(os.path.join(outdir, "10.npy")), sim.displacements[10])
+    # reset == load (simulation.py:119-120)
+    sim.reset(meshes=meshes, params=[(1.0, 140, 0.2), (10.0, 1000, 0.4)])
+    assert len(sim.displacements) == 1
