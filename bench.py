@@ -64,7 +64,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -139,8 +139,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--workload", default="3d16m")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -325,7 +325,8 @@ def main():
         "dtype": "f32 storage, f64 constitutive (polar/stress)", "data": "synthetic",
         "config": {"workload": scene.name, "particles_per_gpu": n, "particles_total": n_total,
                    "grid": f"{scene.res}^{scene.dim}", "dt": scene.dt, "p2g_mode": args.p2g_mode,
-                   "l2": "inputs larger than L2 (no flush)" if n * 252 > 256e6 else "state fits in L2 (flagged)",
+                   "l2": ("inputs larger than L2 (no flush)" if n * (112 if scene.dim == 3 else 52) > 2 * 126e6
+                          else "particle state fits in the 126 MB L2 (flagged: HBM fraction is not meaningful)"),
                    "n_oob": n_oob,
                    "parallelism": (f"{world} slabs along x, halo sum over NCCL p2p every substep, migration every "
                                    f"{args.margin} substeps") if world > 1 else "single GPU"},
