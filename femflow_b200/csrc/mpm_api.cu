@@ -10,6 +10,7 @@
 #include "mpm_bin.cuh"
 #include "mpm_common.cuh"
 #include "mpm_direct.cuh"
+#include "mpm_stream.cuh"
 #include "mpm_tiled.cuh"
 
 using namespace ffmpm;
@@ -49,7 +50,10 @@ struct FfMpmHandle {
   int64_t capacity;   // capacity the workspace was sized for (derived from ws_bytes)
   bool binned;        // bin buffers describe the live buffer
   int64_t launches;
-  bool prebinned;     // keys/rank/histogram of the live buffer were emitted by the last tiled G2P
+  bool prebinned;     // keys/rank/histogram of the live buffer were emitted by the last reordering G2P
+  bool have_perm;     // perm / active tiles are valid (full ffmpm_bin, not the light scan of the stream pipeline)
+  bool g2p_bulk;      // tiled G2P leaves through cp.async.bulk stores (FFMPM_G2P_BULK=1 enables)
+  int pipeline;       // 1 = tiled (perm + smem tiles, default), 0 = stream (physical order); FFMPM_PIPELINE
   int p2g_blocks_per_sm, g2p_blocks_per_sm;   // persistent-grid sizing (tunable: FFMPM_P2G_BPS / FFMPM_G2P_BPS)
 };
 
@@ -125,6 +129,10 @@ int ffmpm_create(const FfMpmConfig* cfg, int32_t device, FfMpmHandle** out) {
   h->n_nodes = (int64_t)d.n[0] * d.n[1] * d.n[2];
   h->p2g_blocks_per_sm = 4;
   h->g2p_blocks_per_sm = 8;
+  h->pipeline = 1;
+  h->g2p_bulk = false;   // measured slower than direct stores on B200 (profiles/r01f): opt-in
+  if (const char* e = getenv("FFMPM_PIPELINE")) h->pipeline = (strcmp(e, "stream") == 0) ? 0 : 1;
+  if (const char* e = getenv("FFMPM_G2P_BULK")) h->g2p_bulk = atoi(e) != 0;
   if (const char* e = getenv("FFMPM_P2G_BPS")) { int v = atoi(e); if (v > 0 && v <= 32) h->p2g_blocks_per_sm = v; }
   if (const char* e = getenv("FFMPM_G2P_BPS")) { int v = atoi(e); if (v > 0 && v <= 32) h->g2p_blocks_per_sm = v; }
   *out = h;
@@ -228,20 +236,27 @@ int ffmpm_clear_grid(FfMpmHandle* h, void* stream) {
 }
 
 template <typename T>
-static int bin_t(FfMpmHandle* h, cudaStream_t s) {
+static int bin_t(FfMpmHandle* h, cudaStream_t s, bool light) {
   if (h->n > h->capacity) return set_err(FFMPM_E_STATE, "workspace too small for this particle count");
-  int nl = bin_particles<T>(h->dev, view<T>(h->st[h->live]), h->n, h->bin, h->err, h->prebinned, s);
+  int nl = bin_particles<T>(h->dev, view<T>(h->st[h->live]), h->n, h->bin, h->err, h->prebinned, light, s);
   h->binned = true;
+  h->have_perm = !light;
   h->prebinned = false;
   return check_launch(h, nl);
 }
 
-int ffmpm_bin(FfMpmHandle* h, void* stream) {
+static int bin_impl(FfMpmHandle* h, void* stream, bool light) {
   int rc = ready(h);
   if (rc) return rc;
-  if (h->n == 0) { h->binned = true; return FFMPM_OK; }
-  return h->cfg.dtype == FFMPM_F64 ? bin_t<double>(h, (cudaStream_t)stream) : bin_t<float>(h, (cudaStream_t)stream);
+  if (h->n == 0) { h->binned = true; h->have_perm = true; return FFMPM_OK; }
+  return h->cfg.dtype == FFMPM_F64 ? bin_t<double>(h, (cudaStream_t)stream, light)
+                                   : bin_t<float>(h, (cudaStream_t)stream, light);
 }
+
+// Public entry point: the complete sort (keys, ranks, cell offsets, permutation, active tiles).
+int ffmpm_bin(FfMpmHandle* h, void* stream) { return bin_impl(h, stream, false); }
+// Keys, ranks and cell offsets only -- all the default (stream) pipeline consumes.
+int ffmpm_bin_offsets(FfMpmHandle* h, void* stream) { return bin_impl(h, stream, h && h->pipeline == 0); }
 
 template <typename T>
 static int p2g_t(FfMpmHandle* h, cudaStream_t s) {
@@ -251,7 +266,10 @@ static int p2g_t(FfMpmHandle* h, cudaStream_t s) {
   if (mode == FFMPM_P2G_TILED) {
     if (h->cfg.dim != 3) return set_err(FFMPM_E_INVALID, "tiled P2G is 3D only (2D uses the scatter kernel)");
     if (!h->binned) return set_err(FFMPM_E_STATE, "tiled P2G needs ffmpm_bin first");
-    int nl = p2g_runs<T>(h->dev, sv, h->n, h->bin, (T*)h->grid, h->err, h->sm_count, h->p2g_blocks_per_sm, s);
+    // tiled pipeline: through the permutation; stream pipeline: physical order (kept sorted by G2P)
+    const bool use_perm = h->pipeline == 1;
+    if (use_perm && !h->have_perm) return set_err(FFMPM_E_STATE, "the tiled pipeline needs the full ffmpm_bin");
+    int nl = p2g_runs<T>(h->dev, sv, h->n, h->bin, (T*)h->grid, h->err, h->sm_count, h->p2g_blocks_per_sm, use_perm, s);
     return check_launch(h, nl);
   }
   unsigned blocks = (unsigned)((h->n + 127) / 128);
@@ -305,10 +323,23 @@ template <typename T>
 static int g2p_t(FfMpmHandle* h, cudaStream_t s) {
   StateView<T> sv = view<T>(h->st[h->live]);
   if (h->binned && h->have_alt && h->cfg.dim == 3) {
-    // binned: gather through the permutation, write back in binned order into the other buffer
+    // binned: write the particles back in cell order into the other buffer
     StateView<T> dst = view<T>(h->st[h->live ^ 1]);
     bin_clear_histogram(h->bin, s);   // the kernel pre-bins the advected particles for the next substep
-    int nl = g2p_tiled<T>(h->dev, sv, dst, h->n, h->bin, (const T*)h->grid, h->err, h->sm_count, h->g2p_blocks_per_sm, s);
+    int nl;
+    if (h->pipeline == 1) {
+      if (!h->have_perm) return set_err(FFMPM_E_STATE, "the tiled pipeline needs the full ffmpm_bin");
+      // bulk (TMA) stores need 16-byte aligned plane segments
+      bool bulk = h->g2p_bulk && sizeof(T) == 4 && (dst.stride % 4) == 0;
+      const void* planes[] = {dst.x, dst.v, dst.C, dst.F, dst.Jp, dst.mass, dst.mu0, dst.lam0, dst.id};
+      for (const void* q : planes) bulk = bulk && (((uintptr_t)q & 15) == 0);
+      nl = g2p_tiled<T>(h->dev, sv, dst, h->n, h->bin, (const T*)h->grid, h->err, h->sm_count, h->g2p_blocks_per_sm, bulk, s);
+    } else {
+      nl = g2p_stream<T>(h->dev, sv, dst, h->n, h->bin, h->bin.keys, h->bin.rank, h->bin.keys_alt, h->bin.rank_alt,
+                         (const T*)h->grid, h->err, s);
+      int32_t* t = h->bin.keys; h->bin.keys = h->bin.keys_alt; h->bin.keys_alt = t;
+      t = h->bin.rank; h->bin.rank = h->bin.rank_alt; h->bin.rank_alt = t;
+    }
     h->live ^= 1;
     h->binned = false;  // positions moved: perm / cell offsets are stale ...
     h->prebinned = true;  // ... but keys, ranks and the histogram of the new live buffer are ready
@@ -341,7 +372,7 @@ int ffmpm_substep(FfMpmHandle* h, int32_t n_substeps, void* stream) {
   for (int32_t it = 0; it < n_substeps; ++it) {
     if ((rc = ffmpm_clear_grid(h, stream))) return rc;
     if (h->cfg.dim == 3 && h->have_alt && h->cfg.p2g_mode != FFMPM_P2G_SCATTER) {
-      if ((rc = ffmpm_bin(h, stream))) return rc;
+      if ((rc = bin_impl(h, stream, h->pipeline == 0))) return rc;
     }
     if ((rc = ffmpm_p2g(h, stream))) return rc;
     if ((rc = ffmpm_grid_op(h, stream))) return rc;

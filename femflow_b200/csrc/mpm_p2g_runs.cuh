@@ -44,16 +44,19 @@ struct P2GWarpSlab {
   int run_start[P2G_WINDOW + 1];  // window-relative first slot of each run (+ sentinel)
 };
 
-template <typename T, int MIN_BLOCKS>
+// USE_PERM: walk the particles through the counting-sort permutation (exactly cell-sorted);
+// otherwise in physical order, which the reordering G2P keeps sorted up to one substep of
+// motion (a particle that changed cell merely splits a run: correct for ANY order).
+template <typename T, int MIN_BLOCKS, bool USE_PERM>
 __global__ void __launch_bounds__(P2G_RUN_WARPS * 32, MIN_BLOCKS)
-p2g_runs3_kernel(DevCfg cfg, StateView<T> s, BinBuffers B, T* __restrict__ grid, ErrRec* err) {
+p2g_runs3_kernel(DevCfg cfg, StateView<T> s, long long n, BinBuffers B, T* __restrict__ grid, ErrRec* err) {
   __shared__ P2GWarpSlab<T> slabs[P2G_RUN_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   P2GWarpSlab<T>& S = slabs[warp];
   const T dx = (T)cfg.dx;
   const int ny = cfg.n[1], nz = cfg.n[2];
-  // slots [0, n_in) hold the particles that are inside the grid (the trailing bin is skipped)
-  const int n_in = B.cell_off[B.n_cells];
+  // with the permutation, slots [0, n_in) hold the particles inside the grid (the trailing bin is skipped)
+  const int n_in = USE_PERM ? B.cell_off[B.n_cells] : (int)n;
   const int n_windows = (n_in + P2G_WINDOW - 1) / P2G_WINDOW;
   const int total_warps = gridDim.x * P2G_RUN_WARPS;
 
@@ -67,14 +70,19 @@ p2g_runs3_kernel(DevCfg cfg, StateView<T> s, BinBuffers B, T* __restrict__ grid,
       const int idx = h * 32 + lane;
       node[h] = -1;
       if (idx < cnt) {
-        const long long p = B.perm[w0 + idx];
+        const long long p = USE_PERM ? (long long)B.perm[w0 + idx] : (long long)(w0 + idx);
         P2GParticle3<T> q = p2g_prepare3(cfg, s, p);
         const int ph = p2g_pad(idx);
+        if (!q.ok) {   // outside the grid (only reachable without the permutation): contributes nothing
+          q.mvx = q.mvy = q.mvz = q.m = (T)0;
+          q.a00 = q.a01 = q.a02 = q.a10 = q.a11 = q.a12 = q.a20 = q.a21 = q.a22 = (T)0;
+          q.fx = q.fy = q.fz = (T)0.5;
+        }
         S.pay[0][ph] = P2GVec4<T>{q.mvx, q.mvy, q.mvz, q.m};
         S.pay[1][ph] = P2GVec4<T>{q.a00 * dx, q.a01 * dx, q.a02 * dx, q.fx};
         S.pay[2][ph] = P2GVec4<T>{q.a10 * dx, q.a11 * dx, q.a12 * dx, q.fy};
         S.pay[3][ph] = P2GVec4<T>{q.a20 * dx, q.a21 * dx, q.a22 * dx, q.fz};
-        node[h] = (q.bx * ny + q.by) * nz + q.bz;
+        node[h] = q.ok ? (q.bx * ny + q.by) * nz + q.bz : -1;
         S.node0[idx] = node[h];
       }
     }
@@ -101,6 +109,7 @@ p2g_runs3_kernel(DevCfg cfg, StateView<T> s, BinBuffers B, T* __restrict__ grid,
     for (int item = lane; item < n_items; item += 32) {
       const int r = item / 3, li = item - r * 3;
       const int r0 = S.run_start[r], r1 = S.run_start[r + 1];
+      if (S.node0[r0] < 0) continue;   // a run of out-of-grid particles
       const T ci = (T)li;
       // B-spline piece of this slab along x: w = s * (f - c)^2 + o  (three_d/p2g.py:55)
       const T sx = li == 1 ? (T)-1 : (T)0.5, cx_ = (T)1.5 - (T)0.5 * ci, ox_ = li == 1 ? (T)0.75 : (T)0;
@@ -147,7 +156,7 @@ p2g_runs3_kernel(DevCfg cfg, StateView<T> s, BinBuffers B, T* __restrict__ grid,
 
 template <typename T>
 int p2g_runs(const DevCfg& cfg, const StateView<T>& s, long long n, BinBuffers& B, T* grid, ErrRec* err, int sm_count,
-             int blocks_per_sm, cudaStream_t st) {
+             int blocks_per_sm, bool use_perm, cudaStream_t st) {
   long long windows = (n + P2G_WINDOW - 1) / P2G_WINDOW;
   long long want = (windows + P2G_RUN_WARPS - 1) / P2G_RUN_WARPS;
   long long cap = (long long)sm_count * blocks_per_sm;
@@ -155,14 +164,18 @@ int p2g_runs(const DevCfg& cfg, const StateView<T>& s, long long n, BinBuffers& 
   if (blocks < 1) blocks = 1;
   // MIN_BLOCKS trades registers for resident warps; tunable via FFMPM_P2G_MINB
   static int minb = [] { const char* e = getenv("FFMPM_P2G_MINB"); return e ? atoi(e) : 4; }();
-  if (minb >= 6)
-    p2g_runs3_kernel<T, 6><<<blocks, P2G_RUN_WARPS * 32, 0, st>>>(cfg, s, B, grid, err);
-  else if (minb == 5)
-    p2g_runs3_kernel<T, 5><<<blocks, P2G_RUN_WARPS * 32, 0, st>>>(cfg, s, B, grid, err);
-  else if (minb == 3)
-    p2g_runs3_kernel<T, 3><<<blocks, P2G_RUN_WARPS * 32, 0, st>>>(cfg, s, B, grid, err);
-  else
-    p2g_runs3_kernel<T, 4><<<blocks, P2G_RUN_WARPS * 32, 0, st>>>(cfg, s, B, grid, err);
+#define FFMPM_LAUNCH_P2G(MB)                                                                              \
+  do {                                                                                                    \
+    if (use_perm)                                                                                         \
+      p2g_runs3_kernel<T, MB, true><<<blocks, P2G_RUN_WARPS * 32, 0, st>>>(cfg, s, n, B, grid, err);      \
+    else                                                                                                  \
+      p2g_runs3_kernel<T, MB, false><<<blocks, P2G_RUN_WARPS * 32, 0, st>>>(cfg, s, n, B, grid, err);     \
+  } while (0)
+  if (minb >= 6) FFMPM_LAUNCH_P2G(6);
+  else if (minb == 5) FFMPM_LAUNCH_P2G(5);
+  else if (minb == 3) FFMPM_LAUNCH_P2G(3);
+  else FFMPM_LAUNCH_P2G(4);
+#undef FFMPM_LAUNCH_P2G
   return 1;
 }
 

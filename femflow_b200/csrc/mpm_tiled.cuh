@@ -5,9 +5,14 @@
 // the tile's 6x6x6 velocity block in shared memory, each thread gathers its particle's
 // 3x3x3 stencil from there, and the updated state is written to the OTHER particle
 // buffer at the binned slot -- so the state is physically in cell order for the next
-// substep and every store is fully coalesced.  The kernel also emits the NEXT substep's
-// cell key and within-cell rank of every particle (it is the one place that knows the
-// advected position), which removes a whole pass over the positions from ffmpm_bin.
+// substep.  The kernel also emits the NEXT substep's cell key and within-cell rank of
+// every particle (it is the one place that knows the advected position), which removes
+// a whole pass over the positions from ffmpm_bin.
+//
+// BULK (fp32): the 128 results of a round are parked plane-major in shared memory and
+// leave the SM as one bulk async copy (cp.async.bulk.global.shared::cta, the TMA engine)
+// per state plane -- 512 contiguous bytes each -- instead of 29 scalar stores per thread;
+// two staging buffers let the copy engine drain round r while round r+1 computes.
 #pragma once
 #include "mpm_bin.cuh"
 #include "mpm_common.cuh"
@@ -19,6 +24,7 @@ namespace ffmpm {
 constexpr int TN3 = TILE3 + 2;            // nodes per tile edge
 constexpr int TNODES3 = TN3 * TN3 * TN3;  // 216
 constexpr int G2P_THREADS = 128;
+constexpr int G2P_PLANES = 29;            // x3 v3 C9 F9 mass mu0 lam0 id Jp
 
 // Moves the optional planes that G2P does not compute.
 template <typename T>
@@ -32,13 +38,36 @@ __device__ __forceinline__ void carry_planes(const StateView<T>& src, const Stat
 }
 
 template <typename T>
+__device__ __forceinline__ float* g2p_plane_ptr(const StateView<T>& d, int k) {
+  const long long ds = d.stride;
+  if (k < 3) return (float*)(d.x + k * ds);
+  if (k < 6) return (float*)(d.v + (k - 3) * ds);
+  if (k < 15) return (float*)(d.C + (k - 6) * ds);
+  if (k < 24) return (float*)(d.F + (k - 15) * ds);
+  if (k == 24) return (float*)d.mass;
+  if (k == 25) return (float*)d.mu0;
+  if (k == 26) return (float*)d.lam0;
+  if (k == 27) return reinterpret_cast<float*>(d.id);
+  return (float*)d.Jp;
+}
+
+__device__ __forceinline__ void bulk_store_g(void* gdst, const void* ssrc, unsigned bytes) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(sa), "r"(bytes) : "memory");
+}
+
+template <typename T, bool BULK>
 __global__ void __launch_bounds__(G2P_THREADS) g2p_tiled3_kernel(DevCfg cfg, StateView<T> src, StateView<T> dst,
                                                                  BinBuffers B, const T* __restrict__ grid, ErrRec* err) {
+  static_assert(!BULK || sizeof(T) == 4, "bulk staging is for the fp32 build");
   using V4 = typename Vec4<T>::type;
   __shared__ V4 tile[TNODES3];
   __shared__ int s_work;
+  // plane-major staging of one round's results, double buffered (BULK only; 1 element otherwise)
+  __shared__ __align__(128) float stage[BULK ? 2 : 1][BULK ? G2P_PLANES : 1][BULK ? G2P_THREADS : 1];
   const int n_active = B.counters[0];
   const long long ss = src.stride, ds = dst.stride;
+  int round_parity = 0;
 
   for (;;) {
     __syncthreads();
@@ -75,62 +104,121 @@ __global__ void __launch_bounds__(G2P_THREADS) g2p_tiled3_kernel(DevCfg cfg, Sta
       tile[nd] = g;
     }
     __syncthreads();
-    for (int sbase = start; sbase < end; sbase += blockDim.x) {
-      const int slot = sbase + threadIdx.x;
+    // rounds are aligned to multiples of 128 slots so that a round's plane segment is 16-byte aligned
+    for (int rbase = (start / G2P_THREADS) * G2P_THREADS; rbase < end; rbase += G2P_THREADS) {
+      const int slot = rbase + threadIdx.x;
+      const bool mine = slot >= start && slot < end;
       int next_key = -1;
-      if (slot < end) {
-      const long long p = B.perm[slot];
-      const T x0 = src.x[p], x1 = src.x[ss + p], x2 = src.x[2 * ss + p];
-      int gx, gy, gz;
-      T fx, fy, fz;
-      base_fx(x0, cfg.inv_dx, gx, fx);
-      base_fx(x1, cfg.inv_dx, gy, fy);
-      base_fx(x2, cfg.inv_dx, gz, fz);
-      const int cb = ((gx - cfg.origin[0] - ox) * TN3 + (gy - cfg.origin[1] - oy)) * TN3 + (gz - cfg.origin[2] - oz);
-      T vx, vy, vz, c00, c01, c02, c10, c11, c12, c20, c21, c22;
-      g2p_accumulate3<T>([&](int i, int j, int k) { return tile[cb + (i * TN3 + j) * TN3 + k]; }, fx, fy, fz,
-                         vx, vy, vz, c00, c01, c02, c10, c11, c12, c20, c21, c22);
-      const T s4 = (T)(4.0 * cfg.inv_dx);
-      c00 *= s4; c01 *= s4; c02 *= s4; c10 *= s4; c11 *= s4; c12 *= s4; c20 *= s4; c21 *= s4; c22 *= s4;
-      const T dt = (T)cfg.dt;
-      const T f00 = src.F[0 * ss + p], f01 = src.F[1 * ss + p], f02 = src.F[2 * ss + p];
-      const T f10 = src.F[3 * ss + p], f11 = src.F[4 * ss + p], f12 = src.F[5 * ss + p];
-      const T f20 = src.F[6 * ss + p], f21 = src.F[7 * ss + p], f22 = src.F[8 * ss + p];
-      const T m00 = (T)1 + dt * c00, m01 = dt * c01, m02 = dt * c02;
-      const T m10 = dt * c10, m11 = (T)1 + dt * c11, m12 = dt * c12;
-      const T m20 = dt * c20, m21 = dt * c21, m22 = (T)1 + dt * c22;
-      dst.F[0 * ds + slot] = m00 * f00 + m01 * f10 + m02 * f20;
-      dst.F[1 * ds + slot] = m00 * f01 + m01 * f11 + m02 * f21;
-      dst.F[2 * ds + slot] = m00 * f02 + m01 * f12 + m02 * f22;
-      dst.F[3 * ds + slot] = m10 * f00 + m11 * f10 + m12 * f20;
-      dst.F[4 * ds + slot] = m10 * f01 + m11 * f11 + m12 * f21;
-      dst.F[5 * ds + slot] = m10 * f02 + m11 * f12 + m12 * f22;
-      dst.F[6 * ds + slot] = m20 * f00 + m21 * f10 + m22 * f20;
-      dst.F[7 * ds + slot] = m20 * f01 + m21 * f11 + m22 * f21;
-      dst.F[8 * ds + slot] = m20 * f02 + m21 * f12 + m22 * f22;
-      dst.C[0 * ds + slot] = c00; dst.C[1 * ds + slot] = c01; dst.C[2 * ds + slot] = c02;
-      dst.C[3 * ds + slot] = c10; dst.C[4 * ds + slot] = c11; dst.C[5 * ds + slot] = c12;
-      dst.C[6 * ds + slot] = c20; dst.C[7 * ds + slot] = c21; dst.C[8 * ds + slot] = c22;
-      dst.v[slot] = vx; dst.v[ds + slot] = vy; dst.v[2 * ds + slot] = vz;
-      const T nx0 = x0 + dt * vx, nx1 = x1 + dt * vy, nx2 = x2 + dt * vz;
-      dst.x[slot] = nx0; dst.x[ds + slot] = nx1; dst.x[2 * ds + slot] = nx2;
-      carry_planes(src, dst, p, slot, true);
-      next_key = bin_key_of<T>(cfg, B, nx0, nx1, nx2);
-      B.keys[slot] = next_key;
+      T o[24];
+      T cm = 0, cmu = 0, cl = 0, cjp = 0;
+      int cid = 0;
+      if (mine) {
+        const long long p = B.perm[slot];
+        // carried planes first: their latency hides behind the gather
+        if (src.mass) cm = src.mass[p];
+        if (src.mu0) cmu = src.mu0[p];
+        if (src.lam0) cl = src.lam0[p];
+        if (src.id) cid = src.id[p];
+        if (src.Jp) cjp = src.Jp[p];
+        const T x0 = src.x[p], x1 = src.x[ss + p], x2 = src.x[2 * ss + p];
+        const T f00 = src.F[0 * ss + p], f01 = src.F[1 * ss + p], f02 = src.F[2 * ss + p];
+        const T f10 = src.F[3 * ss + p], f11 = src.F[4 * ss + p], f12 = src.F[5 * ss + p];
+        const T f20 = src.F[6 * ss + p], f21 = src.F[7 * ss + p], f22 = src.F[8 * ss + p];
+        int gx, gy, gz;
+        T fx, fy, fz;
+        base_fx(x0, cfg.inv_dx, gx, fx);
+        base_fx(x1, cfg.inv_dx, gy, fy);
+        base_fx(x2, cfg.inv_dx, gz, fz);
+        const int cb = ((gx - cfg.origin[0] - ox) * TN3 + (gy - cfg.origin[1] - oy)) * TN3 + (gz - cfg.origin[2] - oz);
+        T vx, vy, vz, c00, c01, c02, c10, c11, c12, c20, c21, c22;
+        g2p_accumulate3<T>([&](int i, int j, int k) { return tile[cb + (i * TN3 + j) * TN3 + k]; }, fx, fy, fz,
+                           vx, vy, vz, c00, c01, c02, c10, c11, c12, c20, c21, c22);
+        const T s4 = (T)(4.0 * cfg.inv_dx);
+        c00 *= s4; c01 *= s4; c02 *= s4; c10 *= s4; c11 *= s4; c12 *= s4; c20 *= s4; c21 *= s4; c22 *= s4;
+        const T dt = (T)cfg.dt;
+        // F <- (I + dt C) F   (three_d/g2p.py:46)
+        const T m00 = (T)1 + dt * c00, m01 = dt * c01, m02 = dt * c02;
+        const T m10 = dt * c10, m11 = (T)1 + dt * c11, m12 = dt * c12;
+        const T m20 = dt * c20, m21 = dt * c21, m22 = (T)1 + dt * c22;
+        o[0] = x0 + dt * vx; o[1] = x1 + dt * vy; o[2] = x2 + dt * vz;   // three_d/g2p.py:45
+        o[3] = vx; o[4] = vy; o[5] = vz;
+        o[6] = c00; o[7] = c01; o[8] = c02; o[9] = c10; o[10] = c11; o[11] = c12; o[12] = c20; o[13] = c21; o[14] = c22;
+        o[15] = m00 * f00 + m01 * f10 + m02 * f20;
+        o[16] = m00 * f01 + m01 * f11 + m02 * f21;
+        o[17] = m00 * f02 + m01 * f12 + m02 * f22;
+        o[18] = m10 * f00 + m11 * f10 + m12 * f20;
+        o[19] = m10 * f01 + m11 * f11 + m12 * f21;
+        o[20] = m10 * f02 + m11 * f12 + m12 * f22;
+        o[21] = m20 * f00 + m21 * f10 + m22 * f20;
+        o[22] = m20 * f01 + m21 * f11 + m22 * f21;
+        o[23] = m20 * f02 + m21 * f12 + m22 * f22;
+        next_key = bin_key_of<T>(cfg, B, o[0], o[1], o[2]);
+        B.keys[slot] = next_key;
+      }
+      if constexpr (BULK) {
+        float(*sb)[G2P_THREADS] = stage[round_parity];
+        __syncthreads();   // the copy engine has finished reading this buffer (the issuing lanes waited last round)
+        if (mine) {
+#pragma unroll
+          for (int k = 0; k < 24; ++k) sb[k][threadIdx.x] = (float)o[k];
+          sb[24][threadIdx.x] = (float)cm; sb[25][threadIdx.x] = (float)cmu; sb[26][threadIdx.x] = (float)cl;
+          sb[27][threadIdx.x] = __int_as_float(cid); sb[28][threadIdx.x] = (float)cjp;
+        }
+        __syncthreads();
+        if (threadIdx.x < G2P_PLANES) {
+          float* gp = g2p_plane_ptr(dst, threadIdx.x);
+          if (gp != nullptr) {
+            const int a = max(start, rbase), b = min(end, rbase + G2P_THREADS);   // this round's slots [a, b)
+            const int a4 = (a + 3) & ~3, b4 = b & ~3;
+            const float* sp = sb[threadIdx.x];
+            if (a4 < b4) {
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              bulk_store_g(gp + a4, sp + (a4 - rbase), (unsigned)(b4 - a4) * 4u);
+              for (int s2 = a; s2 < a4; ++s2) gp[s2] = sp[s2 - rbase];
+              for (int s2 = b4; s2 < b; ++s2) gp[s2] = sp[s2 - rbase];
+            } else {
+              for (int s2 = a; s2 < b; ++s2) gp[s2] = sp[s2 - rbase];
+            }
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the OTHER buffer is free again
+        }
+        round_parity ^= 1;
+      } else {
+        if (mine) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) { dst.x[k * ds + slot] = o[k]; dst.v[k * ds + slot] = o[3 + k]; }
+#pragma unroll
+          for (int k = 0; k < 9; ++k) { dst.C[k * ds + slot] = o[6 + k]; dst.F[k * ds + slot] = o[15 + k]; }
+          if (src.mass) dst.mass[slot] = cm;
+          if (src.mu0) dst.mu0[slot] = cmu;
+          if (src.lam0) dst.lam0[slot] = cl;
+          if (src.id) dst.id[slot] = cid;
+          if (src.Jp) dst.Jp[slot] = cjp;
+        }
       }
       // next substep's histogram + within-cell rank (same scheme as bin_count_kernel)
       bin_rank_warp(B, next_key, slot);
     }
   }
+  if constexpr (BULK) {
+    if (threadIdx.x < G2P_PLANES) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
 }
 
 template <typename T>
 int g2p_tiled(const DevCfg& cfg, const StateView<T>& src, const StateView<T>& dst, long long n, BinBuffers& B,
-              const T* grid, ErrRec* err, int sm_count, int blocks_per_sm, cudaStream_t st) {
+              const T* grid, ErrRec* err, int sm_count, int blocks_per_sm, bool bulk, cudaStream_t st) {
   (void)n;
   cudaMemsetAsync(&B.counters[2], 0, sizeof(int32_t), st);
   int blocks = min(B.n_tiles + 1, sm_count * blocks_per_sm);
-  g2p_tiled3_kernel<T><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
+  if constexpr (sizeof(T) == 4) {
+    if (bulk) {
+      g2p_tiled3_kernel<T, true><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
+      return 1;
+    }
+  }
+  g2p_tiled3_kernel<T, false><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
   return 1;
 }
 

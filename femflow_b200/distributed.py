@@ -223,7 +223,7 @@ class CudaSlab(LocalSlab):
     def scatter(self) -> None:
         s = self.solver
         s.clear_grid()
-        s.bin()
+        s.bin(offsets_only=True)
         s.p2g()
 
     def grid_planes(self, a: int, b: int) -> torch.Tensor:

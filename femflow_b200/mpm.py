@@ -85,7 +85,7 @@ class MpmSolver:
             n3.append(1)
         self.n = [int(v) for v in n3]
         self.origin = [int(o) for o in origin] + [0] * (3 - len(origin))
-        self.capacity = int(capacity)
+        self.capacity = (int(capacity) + 63) // 64 * 64      # plane stride: 16-byte aligned plane segments
         self.model = model
         if per_particle_material is None:
             per_particle_material = self.dim == 3
@@ -215,8 +215,9 @@ class MpmSolver:
     def clear_grid(self, stream=None):
         N.check(self.lib.ffmpm_clear_grid(self._h, self._stream(stream)))
 
-    def bin(self, stream=None):
-        N.check(self.lib.ffmpm_bin(self._h, self._stream(stream)))
+    def bin(self, stream=None, offsets_only: bool = False):
+        fn = self.lib.ffmpm_bin_offsets if offsets_only else self.lib.ffmpm_bin
+        N.check(fn(self._h, self._stream(stream)))
 
     def p2g(self, stream=None):
         N.check(self.lib.ffmpm_p2g(self._h, self._stream(stream)))
