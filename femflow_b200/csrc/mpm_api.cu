@@ -10,6 +10,7 @@
 #include "mpm_bin.cuh"
 #include "mpm_common.cuh"
 #include "mpm_direct.cuh"
+#include "mpm_p2g_bulk.cuh"
 #include "mpm_stream.cuh"
 #include "mpm_tiled.cuh"
 
@@ -52,6 +53,7 @@ struct FfMpmHandle {
   int64_t launches;
   bool prebinned;     // keys/rank/histogram of the live buffer were emitted by the last reordering G2P
   bool have_perm;     // perm / active tiles are valid (full ffmpm_bin, not the light scan of the stream pipeline)
+  int p2g_variant;    // see p2g_t (FFMPM_P2G_VARIANT)
   bool g2p_bulk;      // tiled G2P leaves through cp.async.bulk stores (FFMPM_G2P_BULK=1 enables)
   int pipeline;       // 1 = tiled (perm + smem tiles, default), 0 = stream (physical order); FFMPM_PIPELINE
   int p2g_blocks_per_sm, g2p_blocks_per_sm;   // persistent-grid sizing (tunable: FFMPM_P2G_BPS / FFMPM_G2P_BPS)
@@ -126,13 +128,17 @@ int ffmpm_create(const FfMpmConfig* cfg, int32_t device, FfMpmHandle** out) {
   d.inv_dx = cfg->inv_dx; d.dx = cfg->dx; d.dt = cfg->dt; d.volume = cfg->volume;
   d.gravity = cfg->gravity; d.hardening = cfg->hardening;
   d.mass = cfg->mass; d.mu0 = cfg->mu_0; d.lam0 = cfg->lambda_0;
+  d.fp32_stress = 1;
+  if (const char* e = getenv("FFMPM_FP32_STRESS")) d.fp32_stress = atoi(e) != 0;
   h->n_nodes = (int64_t)d.n[0] * d.n[1] * d.n[2];
-  h->p2g_blocks_per_sm = 4;
+  h->p2g_blocks_per_sm = 5;
   h->g2p_blocks_per_sm = 8;
   h->pipeline = 1;
   h->g2p_bulk = false;   // measured slower than direct stores on B200 (profiles/r01f): opt-in
   if (const char* e = getenv("FFMPM_PIPELINE")) h->pipeline = (strcmp(e, "stream") == 0) ? 0 : 1;
   if (const char* e = getenv("FFMPM_G2P_BULK")) h->g2p_bulk = atoi(e) != 0;
+  h->p2g_variant = 3;   // TMA-prefetched physical-order P2G when eligible (measured best: profiles/r01g)
+  if (const char* e = getenv("FFMPM_P2G_VARIANT")) h->p2g_variant = atoi(e);
   if (const char* e = getenv("FFMPM_P2G_BPS")) { int v = atoi(e); if (v > 0 && v <= 32) h->p2g_blocks_per_sm = v; }
   if (const char* e = getenv("FFMPM_G2P_BPS")) { int v = atoi(e); if (v > 0 && v <= 32) h->g2p_blocks_per_sm = v; }
   *out = h;
@@ -266,8 +272,19 @@ static int p2g_t(FfMpmHandle* h, cudaStream_t s) {
   if (mode == FFMPM_P2G_TILED) {
     if (h->cfg.dim != 3) return set_err(FFMPM_E_INVALID, "tiled P2G is 3D only (2D uses the scatter kernel)");
     if (!h->binned) return set_err(FFMPM_E_STATE, "tiled P2G needs ffmpm_bin first");
-    // tiled pipeline: through the permutation; stream pipeline: physical order (kept sorted by G2P)
-    const bool use_perm = h->pipeline == 1;
+    // P2G variant: 0 = through the permutation, 1 = physical order (kept sorted by G2P),
+    // 2 / 3 = physical order with TMA-prefetched state, double / single buffered (fp32 only)
+    if constexpr (sizeof(T) == 4) {
+      if (h->p2g_variant >= 2 && p2g_bulk_eligible(h->dev, sv)) {
+        bool ok;
+        const int bps = h->p2g_blocks_per_sm;
+        if (h->p2g_variant == 2) ok = p2g_bulk_launch<2, 2>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
+        else ok = p2g_bulk_launch<3, 1>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
+        if (!ok) return set_err(FFMPM_E_CUDA, "could not configure the bulk P2G kernel");
+        return check_launch(h, 1);
+      }
+    }
+    const bool use_perm = h->p2g_variant == 0 && h->pipeline == 1;
     if (use_perm && !h->have_perm) return set_err(FFMPM_E_STATE, "the tiled pipeline needs the full ffmpm_bin");
     int nl = p2g_runs<T>(h->dev, sv, h->n, h->bin, (T*)h->grid, h->err, h->sm_count, h->p2g_blocks_per_sm, use_perm, s);
     return check_launch(h, nl);

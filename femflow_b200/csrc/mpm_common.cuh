@@ -13,6 +13,7 @@ struct DevCfg {
   int n[3], origin[3], res[3], wall_lo[3], wall_hi[3];
   double inv_dx, dx, dt, volume, gravity, hardening;
   double mass, mu0, lam0;
+  int fp32_stress;   // fp32 build: evaluate the stress in perturbation form in fp32 when the strain allows
 };
 
 template <typename T>

@@ -20,11 +20,15 @@ struct P2GParticle3 {
   bool ok;
 };
 
-template <typename T>
-__device__ __forceinline__ P2GParticle3<T> p2g_prepare3(const DevCfg& cfg, const StateView<T>& s, long long p) {
+// Plane numbering of the 3D per-particle inputs (the order of the bulk-prefetch slab too).
+enum { P2G_X = 0, P2G_V = 3, P2G_C = 6, P2G_F = 15, P2G_MASS = 24, P2G_MU = 25, P2G_LAM = 26, P2G_NPLANES = 27 };
+
+// `get(k)` returns plane k of the particle (k is a literal at every call site, so a
+// loader that switches on k folds away); has_mat: per-particle mass/mu0/lam0 planes exist.
+template <typename T, typename Get>
+__device__ __forceinline__ P2GParticle3<T> p2g_prepare3_from(const DevCfg& cfg, Get get, bool has_mat, double jp) {
   P2GParticle3<T> q;
-  const long long st = s.stride;
-  T x0 = s.x[p], x1 = s.x[st + p], x2 = s.x[2 * st + p];
+  T x0 = get(P2G_X), x1 = get(P2G_X + 1), x2 = get(P2G_X + 2);
   int gx, gy, gz;
   base_fx(x0, cfg.inv_dx, gx, q.fx);
   base_fx(x1, cfg.inv_dx, gy, q.fy);
@@ -34,27 +38,59 @@ __device__ __forceinline__ P2GParticle3<T> p2g_prepare3(const DevCfg& cfg, const
   q.ok = !(isnan((double)x0) || isnan((double)x1) || isnan((double)x2)) &&
          q.bx >= 0 && q.by >= 0 && q.bz >= 0 && q.bx + 2 < cfg.n[0] && q.by + 2 < cfg.n[1] && q.bz + 2 < cfg.n[2];
   if (!q.ok) return q;
-  double mass = s.mass ? (double)s.mass[p] : cfg.mass;
-  double mu = (s.mu0 ? (double)s.mu0[p] : cfg.mu0);
-  double lam = (s.lam0 ? (double)s.lam0[p] : cfg.lam0);
+  double mass = has_mat ? (double)get(P2G_MASS) : cfg.mass;
+  double mu = has_mat ? (double)get(P2G_MU) : cfg.mu0;
+  double lam = has_mat ? (double)get(P2G_LAM) : cfg.lam0;
   double e = cfg.hardening;                       // constant_hardening: a plain multiplier (quirk 8)
-  if (cfg.model == 1) e = exp(cfg.hardening * (1.0 - (double)s.Jp[p]));  // snow_hardening, utils.py:48
+  if (cfg.model == 1) e = exp(cfg.hardening * (1.0 - jp));  // snow_hardening, utils.py:48
   mu *= e; lam *= e;
-  Mat3<double> F, C;
-  F.a00 = s.F[0 * st + p]; F.a01 = s.F[1 * st + p]; F.a02 = s.F[2 * st + p];
-  F.a10 = s.F[3 * st + p]; F.a11 = s.F[4 * st + p]; F.a12 = s.F[5 * st + p];
-  F.a20 = s.F[6 * st + p]; F.a21 = s.F[7 * st + p]; F.a22 = s.F[8 * st + p];
-  C.a00 = s.C[0 * st + p]; C.a01 = s.C[1 * st + p]; C.a02 = s.C[2 * st + p];
-  C.a10 = s.C[3 * st + p]; C.a11 = s.C[4 * st + p]; C.a12 = s.C[5 * st + p];
-  C.a20 = s.C[6 * st + p]; C.a21 = s.C[7 * st + p]; C.a22 = s.C[8 * st + p];
-  double k = (cfg.dt * cfg.volume) * (4.0 * cfg.inv_dx * cfg.inv_dx);
-  Mat3<double> A = fixed_corotated_affine3(F, C, mu, lam, mass, k);
-  q.a00 = (T)A.a00; q.a01 = (T)A.a01; q.a02 = (T)A.a02;
-  q.a10 = (T)A.a10; q.a11 = (T)A.a11; q.a12 = (T)A.a12;
-  q.a20 = (T)A.a20; q.a21 = (T)A.a21; q.a22 = (T)A.a22;
+  const double k = (cfg.dt * cfg.volume) * (4.0 * cfg.inv_dx * cfg.inv_dx);
+  const T f00 = get(P2G_F + 0), f01 = get(P2G_F + 1), f02 = get(P2G_F + 2);
+  const T f10 = get(P2G_F + 3), f11 = get(P2G_F + 4), f12 = get(P2G_F + 5);
+  const T f20 = get(P2G_F + 6), f21 = get(P2G_F + 7), f22 = get(P2G_F + 8);
+  const T c00 = get(P2G_C + 0), c01 = get(P2G_C + 1), c02 = get(P2G_C + 2);
+  const T c10 = get(P2G_C + 3), c11 = get(P2G_C + 4), c12 = get(P2G_C + 5);
+  const T c20 = get(P2G_C + 6), c21 = get(P2G_C + 7), c22 = get(P2G_C + 8);
+  bool done = false;
+  if constexpr (sizeof(T) == 4) {
+    // fp32 build, moderate strain: perturbation-form stress entirely in fp32 (mpm_math.cuh)
+    if (cfg.fp32_stress) {
+      Mat3<float> Ff{f00, f01, f02, f10, f11, f12, f20, f21, f22}, Cf{c00, c01, c02, c10, c11, c12, c20, c21, c22}, Af;
+      done = fixed_corotated_affine3_f32(Ff, Cf, (float)mu, (float)lam, (float)mass, (float)k, Af);
+      if (done) {
+        q.a00 = Af.a00; q.a01 = Af.a01; q.a02 = Af.a02;
+        q.a10 = Af.a10; q.a11 = Af.a11; q.a12 = Af.a12;
+        q.a20 = Af.a20; q.a21 = Af.a21; q.a22 = Af.a22;
+      }
+    }
+  }
+  if (!done) {
+    Mat3<double> F{f00, f01, f02, f10, f11, f12, f20, f21, f22}, C{c00, c01, c02, c10, c11, c12, c20, c21, c22};
+    Mat3<double> A = fixed_corotated_affine3(F, C, mu, lam, mass, k);
+    q.a00 = (T)A.a00; q.a01 = (T)A.a01; q.a02 = (T)A.a02;
+    q.a10 = (T)A.a10; q.a11 = (T)A.a11; q.a12 = (T)A.a12;
+    q.a20 = (T)A.a20; q.a21 = (T)A.a21; q.a22 = (T)A.a22;
+  }
   q.m = (T)mass;
-  q.mvx = (T)(mass * (double)s.v[p]); q.mvy = (T)(mass * (double)s.v[st + p]); q.mvz = (T)(mass * (double)s.v[2 * st + p]);
+  q.mvx = (T)(mass * (double)get(P2G_V)); q.mvy = (T)(mass * (double)get(P2G_V + 1)); q.mvz = (T)(mass * (double)get(P2G_V + 2));
   return q;
+}
+
+template <typename T>
+__device__ __forceinline__ P2GParticle3<T> p2g_prepare3(const DevCfg& cfg, const StateView<T>& s, long long p) {
+  const long long st = s.stride;
+  auto get = [&](int k) -> T {
+    if (k < P2G_V) return s.x[k * st + p];
+    if (k < P2G_C) return s.v[(k - P2G_V) * st + p];
+    if (k < P2G_F) return s.C[(k - P2G_C) * st + p];
+    if (k < P2G_MASS) return s.F[(k - P2G_F) * st + p];
+    if (k == P2G_MASS) return s.mass[p];
+    if (k == P2G_MU) return s.mu0[p];
+    return s.lam0[p];
+  };
+  const bool has_mat = s.mass != nullptr && s.mu0 != nullptr && s.lam0 != nullptr;
+  const double jp = cfg.model == 1 ? (double)s.Jp[p] : 1.0;
+  return p2g_prepare3_from<T>(cfg, get, has_mat, jp);
 }
 
 template <typename T>

@@ -100,6 +100,89 @@ __device__ __forceinline__ Mat3<double> fixed_corotated_affine3(const Mat3<doubl
   return A;
 }
 
+// ----------------------------------------------------------------------------
+// fp32 evaluation of the same affine matrix in PERTURBATION FORM (used by the fp32
+// build when the strain is moderate).  The cancellation that rules out a naive fp32
+// stress -- F - R and J - 1 for F close to I -- is removed
+// algebraically instead of being bought with fp64:
+//   E = F - I                      (exact in fp32 for entries near 1 / 0)
+//   G = F^T F - I = E + E^T + E^T E
+//   S = (I + G)^(1/2),  R = F S^-1  =>  (F - R) F^T = F (I - S^-1) F^T = F M F^T,
+//   M = I - (I + G)^(-1/2) = G/2 - 3G^2/8 + 5G^3/16 - ...   (binomial series, Horner)
+//   J - 1 = det(I + E) - 1 = tr E + (principal 2x2 minors of E) + det E
+// Every quantity is O(strain), so fp32 keeps ~1e-7 RELATIVE accuracy on the stress
+// (prototype vs LAPACK: 1.5e-7 for strains 1e-6 .. 1e-2).  The degree-8 series is used
+// for max|G| < 0.15 (truncation < 1e-7 there); larger strains take the fp64 path.
+// ----------------------------------------------------------------------------
+struct Sym3f {
+  float xx, xy, xz, yy, yz, zz;
+};
+
+// Product of two COMMUTING symmetric matrices (symmetric again).
+__device__ __forceinline__ Sym3f sym3_mul(const Sym3f& a, const Sym3f& b) {
+  Sym3f r;
+  r.xx = a.xx * b.xx + a.xy * b.xy + a.xz * b.xz;
+  r.xy = a.xx * b.xy + a.xy * b.yy + a.xz * b.yz;
+  r.xz = a.xx * b.xz + a.xy * b.yz + a.xz * b.zz;
+  r.yy = a.xy * b.xy + a.yy * b.yy + a.yz * b.yz;
+  r.yz = a.xy * b.xz + a.yy * b.yz + a.yz * b.zz;
+  r.zz = a.xz * b.xz + a.yz * b.yz + a.zz * b.zz;
+  return r;
+}
+
+constexpr float kPerturbationMaxG = 0.15f;
+
+// Returns false when the strain is too large for the series (caller falls back to fp64).
+__device__ __forceinline__ bool fixed_corotated_affine3_f32(const Mat3<float>& F, const Mat3<float>& C, float mu,
+                                                            float lam, float mass, float dt_vol_dinv, Mat3<float>& A) {
+  Mat3<float> E = F;
+  E.a00 -= 1.0f; E.a11 -= 1.0f; E.a22 -= 1.0f;
+  Sym3f G;
+  G.xx = 2.0f * E.a00 + (E.a00 * E.a00 + E.a10 * E.a10 + E.a20 * E.a20);
+  G.yy = 2.0f * E.a11 + (E.a01 * E.a01 + E.a11 * E.a11 + E.a21 * E.a21);
+  G.zz = 2.0f * E.a22 + (E.a02 * E.a02 + E.a12 * E.a12 + E.a22 * E.a22);
+  G.xy = (E.a01 + E.a10) + (E.a00 * E.a01 + E.a10 * E.a11 + E.a20 * E.a21);
+  G.xz = (E.a02 + E.a20) + (E.a00 * E.a02 + E.a10 * E.a12 + E.a20 * E.a22);
+  G.yz = (E.a12 + E.a21) + (E.a01 * E.a02 + E.a11 * E.a12 + E.a21 * E.a22);
+  const float gmax = fmaxf(fmaxf(fmaxf(fabsf(G.xx), fabsf(G.yy)), fmaxf(fabsf(G.zz), fabsf(G.xy))),
+                           fmaxf(fabsf(G.xz), fabsf(G.yz)));
+  if (!(gmax < kPerturbationMaxG)) return false;
+  // q(G) = M / G, Horner from the highest coefficient
+  const float c[8] = {0.5f, -0.375f, 0.3125f, -0.2734375f, 0.24609375f, -0.2255859375f, 0.20947265625f,
+                      -0.196380615234375f};
+  Sym3f q;
+  q.xx = q.yy = q.zz = c[7];
+  q.xy = q.xz = q.yz = 0.0f;
+#pragma unroll
+  for (int i = 6; i >= 0; --i) {
+    q = sym3_mul(G, q);
+    q.xx += c[i]; q.yy += c[i]; q.zz += c[i];
+  }
+  const Sym3f M = sym3_mul(G, q);
+  // W = F M,  X = W F^T (symmetric)
+  const float w00 = F.a00 * M.xx + F.a01 * M.xy + F.a02 * M.xz, w01 = F.a00 * M.xy + F.a01 * M.yy + F.a02 * M.yz,
+              w02 = F.a00 * M.xz + F.a01 * M.yz + F.a02 * M.zz;
+  const float w10 = F.a10 * M.xx + F.a11 * M.xy + F.a12 * M.xz, w11 = F.a10 * M.xy + F.a11 * M.yy + F.a12 * M.yz,
+              w12 = F.a10 * M.xz + F.a11 * M.yz + F.a12 * M.zz;
+  const float w20 = F.a20 * M.xx + F.a21 * M.xy + F.a22 * M.xz, w21 = F.a20 * M.xy + F.a21 * M.yy + F.a22 * M.yz,
+              w22 = F.a20 * M.xz + F.a21 * M.yz + F.a22 * M.zz;
+  const float x00 = w00 * F.a00 + w01 * F.a01 + w02 * F.a02, x01 = w00 * F.a10 + w01 * F.a11 + w02 * F.a12,
+              x02 = w00 * F.a20 + w01 * F.a21 + w02 * F.a22;
+  const float x11 = w10 * F.a10 + w11 * F.a11 + w12 * F.a12, x12 = w10 * F.a20 + w11 * F.a21 + w12 * F.a22;
+  const float x22 = w20 * F.a20 + w21 * F.a21 + w22 * F.a22;
+  // J - 1 without cancellation
+  const float trE = E.a00 + E.a11 + E.a22;
+  const float c2 = (E.a00 * E.a11 - E.a01 * E.a10) + (E.a00 * E.a22 - E.a02 * E.a20) + (E.a11 * E.a22 - E.a12 * E.a21);
+  const float dE = det3(E);
+  const float jm1 = trE + c2 + dE;
+  const float l = lam * jm1 * (1.0f + jm1);   // lam (J-1) J, broadcast onto ALL entries (quirk 2)
+  const float k2 = -dt_vol_dinv * 2.0f * mu, kl = -dt_vol_dinv * l;
+  A.a00 = k2 * x00 + kl + mass * C.a00; A.a01 = k2 * x01 + kl + mass * C.a01; A.a02 = k2 * x02 + kl + mass * C.a02;
+  A.a10 = k2 * x01 + kl + mass * C.a10; A.a11 = k2 * x11 + kl + mass * C.a11; A.a12 = k2 * x12 + kl + mass * C.a12;
+  A.a20 = k2 * x02 + kl + mass * C.a20; A.a21 = k2 * x12 + kl + mass * C.a21; A.a22 = k2 * x22 + kl + mass * C.a22;
+  return true;
+}
+
 // 2D: closed-form rotation with the reference's +1e-10 in the norm
 // (numerics/linear_algebra.py:108-113; quirks 3 and 12), stress as utils.py:75-92.
 __device__ __forceinline__ Mat2<double> fixed_corotated_affine2(const Mat2<double>& F, const Mat2<double>& C,

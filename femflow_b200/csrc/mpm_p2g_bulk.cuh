@@ -1,0 +1,155 @@
+// P2G in physical particle order with TMA-prefetched particle state (fp32 build).
+//
+// Same warp-autonomous algorithm as mpm_p2g_runs.cuh (lane per particle -> runs of
+// equal base cell -> lane per (run, x-slab) with register accumulation -> one vector
+// RED per node), but the 27 SoA state planes of a warp's 64-particle window are
+// brought into shared memory by the copy engine: one elected lane posts 27 bulk async
+// copies (cp.async.bulk.shared::cluster.global, 256 contiguous bytes each) against an
+// mbarrier, for window w+1 while the warp is still computing window w.  The loads
+// need no registers, no address arithmetic per lane, and their latency is off the
+// critical path regardless of occupancy.  Physical order is what makes this possible:
+// a window is a contiguous, 256-byte aligned segment of every plane (no permutation
+// gather); the reordering G2P keeps that order cell-sorted up to one substep of motion.
+#pragma once
+#include "mpm_p2g_runs.cuh"
+
+namespace ffmpm {
+
+template <int NBUF>
+struct P2GBulkWarp {
+  alignas(128) float raw[NBUF][P2G_NPLANES][P2G_WINDOW];
+  P2GWarpSlab<float> slab;
+  alignas(8) unsigned long long bar[NBUF];
+};
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(a), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load_s(void* sdst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(sdst), b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
+               "l"(gsrc), "r"(bytes), "r"(b)
+               : "memory");
+}
+
+__device__ __forceinline__ const float* p2g_plane_src(const StateView<float>& s, int k) {
+  const long long st = s.stride;
+  if (k < P2G_V) return s.x + k * st;
+  if (k < P2G_C) return s.v + (k - P2G_V) * st;
+  if (k < P2G_F) return s.C + (k - P2G_C) * st;
+  if (k < P2G_MASS) return s.F + (k - P2G_F) * st;
+  if (k == P2G_MASS) return s.mass;
+  if (k == P2G_MU) return s.mu0;
+  return s.lam0;
+}
+
+template <int WARPS, int NBUF>
+__global__ void __launch_bounds__(WARPS * 32)
+p2g_bulk3_kernel(DevCfg cfg, StateView<float> s, long long n, float* __restrict__ grid, ErrRec* err) {
+  using T = float;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  P2GBulkWarp<NBUF>* warps = reinterpret_cast<P2GBulkWarp<NBUF>*>(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  P2GBulkWarp<NBUF>& W = warps[warp];
+  P2GWarpSlab<T>& S = W.slab;
+  const T dx = (T)cfg.dx;
+  const int ny = cfg.n[1], nz = cfg.n[2];
+  const bool has_mat = s.mass != nullptr && s.mu0 != nullptr && s.lam0 != nullptr;
+  const int n_planes = has_mat ? P2G_NPLANES : P2G_MASS;
+  const int n_windows = (int)((n + P2G_WINDOW - 1) / P2G_WINDOW);
+  const int total_warps = gridDim.x * WARPS;
+  const int first = blockIdx.x * WARPS + warp;
+
+  if (lane == 0) {
+    for (int b = 0; b < NBUF; ++b) mbar_init(&W.bar[b], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+
+  auto issue = [&](int win, int buf) {
+    // one lane posts the whole window: n_planes x 256 B
+    if (lane == 0) {
+      mbar_expect_tx(&W.bar[buf], (unsigned)n_planes * P2G_WINDOW * 4u);
+      const long long w0 = (long long)win * P2G_WINDOW;
+      for (int k = 0; k < n_planes; ++k)
+        bulk_load_s(&W.raw[buf][k][0], p2g_plane_src(s, k) + w0, P2G_WINDOW * 4u, &W.bar[buf]);
+    }
+  };
+
+  if (first < n_windows) issue(first, 0);
+  int it = 0;
+  for (int win = first; win < n_windows; win += total_warps, ++it) {
+    const int buf = NBUF == 2 ? (it & 1) : 0;
+    const unsigned parity = NBUF == 2 ? ((it >> 1) & 1) : (it & 1);
+    const int w0 = win * P2G_WINDOW;
+    const int cnt = (int)min((long long)P2G_WINDOW, n - w0);
+    if (NBUF == 2 && win + total_warps < n_windows) issue(win + total_warps, buf ^ 1);
+    mbar_wait(&W.bar[buf], parity);
+    // ---- phase 1: lane per particle, state from the prefetched slab ----
+    int node[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int idx = h * 32 + lane;
+      node[h] = -1;
+      if (idx < cnt) {
+        P2GParticle3<T> q = p2g_prepare3_from<T>(cfg, [&](int k) -> T { return W.raw[buf][k][idx]; }, has_mat, 1.0);
+        node[h] = p2g_park(S, q, idx, dx, ny, nz);
+      }
+    }
+    __syncwarp();
+    // single buffer: the raw slab is free again -> prefetch the next window behind phase 2
+    if (NBUF == 1 && win + total_warps < n_windows) issue(win + total_warps, 0);
+    p2g_runs_phase2<T>(S, node, cnt, lane, ny, nz, grid);
+    __syncwarp();   // the payload slab is rewritten by the next window
+  }
+}
+
+template <int WARPS, int NBUF>
+static bool p2g_bulk_launch(const DevCfg& cfg, const StateView<float>& s, long long n, float* grid, ErrRec* err,
+                            int sm_count, int blocks_per_sm, cudaStream_t st) {
+  const size_t smem = sizeof(P2GBulkWarp<NBUF>) * WARPS;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(p2g_bulk3_kernel<WARPS, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return false;
+    configured = true;
+  }
+  long long windows = (n + P2G_WINDOW - 1) / P2G_WINDOW;
+  long long want = (windows + WARPS - 1) / WARPS;
+  long long cap = (long long)sm_count * blocks_per_sm;
+  int blocks = (int)(want < cap ? want : cap);
+  if (blocks < 1) blocks = 1;
+  p2g_bulk3_kernel<WARPS, NBUF><<<blocks, WARPS * 32, smem, st>>>(cfg, s, n, grid, err);
+  return true;
+}
+
+// True when the state layout allows bulk copies: 16-byte aligned planes, stride multiple of the window.
+inline bool p2g_bulk_eligible(const DevCfg& cfg, const StateView<float>& s) {
+  if (cfg.model != 0 || cfg.dim != 3) return false;
+  if ((s.stride % P2G_WINDOW) != 0) return false;
+  const void* planes[] = {s.x, s.v, s.C, s.F, s.mass, s.mu0, s.lam0};
+  for (const void* q : planes)
+    if (((uintptr_t)q & 15) != 0) return false;
+  return true;
+}
+
+}  // namespace ffmpm

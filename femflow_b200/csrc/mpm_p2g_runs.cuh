@@ -1,9 +1,9 @@
-// P2G over binned (cell-sorted) particles, warp-autonomous form.
+// P2G over cell-sorted particles, warp-autonomous form.
 //
-// Every warp owns windows of P2G_WINDOW consecutive binned slots and never talks to
-// another warp (no block barrier, no shared grid tile, no work counter):
-//   phase 1 (lane per particle)   gather the state through `perm`, evaluate the polar
-//           decomposition / fixed-corotated stress (three_d/p2g.py:57-65) and park
+// Every warp owns windows of P2G_WINDOW consecutive slots and never talks to another
+// warp (no block barrier, no shared grid tile, no work counter):
+//   phase 1 (lane per particle)   fetch the state (through `perm`, or in physical
+//           order), evaluate the fixed-corotated stress (three_d/p2g.py:57-65) and park
 //           {m v, m, affine*dx, fx} in the warp's private smem slab;
 //   runs    a ballot over "my base cell differs from my predecessor's" splits the
 //           window into runs of particles that share a base cell;
@@ -11,7 +11,9 @@
 //           nodes x {momentum, mass} in registers (three_d/p2g.py:67-80), then ONE
 //           red.global.add.v4.f32 per node.
 // Same-node contributions of all particles of a cell are therefore summed on chip and
-// leave the SM as 27 vector reductions per run instead of 27 per particle.
+// leave the SM as 27 vector reductions per run instead of 27 per particle.  The scheme
+// is correct for ANY particle order (an unsorted particle merely splits a run); sorted
+// order is what makes the runs long.
 //
 // Shared-memory layout: four float4 planes indexed by a padded slot q + q/8.  With
 // ~8 particles per cell the lanes of one LDS.128 read particles ~8 slots apart;
@@ -40,13 +42,100 @@ struct alignas(16) P2GVec4 {
 template <typename T>
 struct P2GWarpSlab {
   P2GVec4<T> pay[4][P2G_PADDED];  // {mvx,mvy,mvz,m} {a00,a01,a02,fx} {a10,a11,a12,fy} {a20,a21,a22,fz}, a = affine*dx
-  int node0[P2G_WINDOW];          // linear LOCAL node id of the particle's base cell
+  int node0[P2G_WINDOW];          // linear LOCAL node id of the particle's base cell (-1: outside the grid)
   int run_start[P2G_WINDOW + 1];  // window-relative first slot of each run (+ sentinel)
 };
 
+// Phase 1 tail: park one particle's payload.
+template <typename T>
+__device__ __forceinline__ int p2g_park(P2GWarpSlab<T>& S, P2GParticle3<T>& q, int idx, T dx, int ny, int nz) {
+  const int ph = p2g_pad(idx);
+  if (!q.ok) {   // outside the grid: contributes nothing (flagged by the binning / G2P)
+    q.mvx = q.mvy = q.mvz = q.m = (T)0;
+    q.a00 = q.a01 = q.a02 = q.a10 = q.a11 = q.a12 = q.a20 = q.a21 = q.a22 = (T)0;
+    q.fx = q.fy = q.fz = (T)0.5;
+  }
+  S.pay[0][ph] = P2GVec4<T>{q.mvx, q.mvy, q.mvz, q.m};
+  S.pay[1][ph] = P2GVec4<T>{q.a00 * dx, q.a01 * dx, q.a02 * dx, q.fx};
+  S.pay[2][ph] = P2GVec4<T>{q.a10 * dx, q.a11 * dx, q.a12 * dx, q.fy};
+  S.pay[3][ph] = P2GVec4<T>{q.a20 * dx, q.a21 * dx, q.a22 * dx, q.fz};
+  const int node = q.ok ? (q.bx * ny + q.by) * nz + q.bz : -1;
+  S.node0[idx] = node;
+  return node;
+}
+
+// Runs + phase 2 over a parked window (call after a __syncwarp() that follows phase 1).
+template <typename T>
+__device__ __forceinline__ void p2g_runs_phase2(P2GWarpSlab<T>& S, const int (&node)[2], int cnt, int lane, int ny,
+                                                int nz, T* __restrict__ grid) {
+  // run heads: first slot of the window, or base cell differs from the predecessor's
+  unsigned heads[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int idx = h * 32 + lane;
+    const int prev = idx > 0 ? S.node0[idx - 1] : -2;
+    heads[h] = __ballot_sync(0xffffffffu, idx < cnt && node[h] != prev);
+  }
+  const int n0 = __popc(heads[0]);
+  const int n_runs = n0 + __popc(heads[1]);
+  {
+    const unsigned below = (1u << lane) - 1u;
+    if (heads[0] & (1u << lane)) S.run_start[__popc(heads[0] & below)] = lane;
+    if (heads[1] & (1u << lane)) S.run_start[n0 + __popc(heads[1] & below)] = 32 + lane;
+    if (lane == 0) S.run_start[n_runs] = cnt;
+  }
+  __syncwarp();
+  // lane per (run, x-slab)
+  const int n_items = n_runs * 3;
+  for (int item = lane; item < n_items; item += 32) {
+    const int r = item / 3, li = item - r * 3;
+    const int r0 = S.run_start[r], r1 = S.run_start[r + 1];
+    if (S.node0[r0] < 0) continue;   // a run of out-of-grid particles
+    const T ci = (T)li;
+    // B-spline piece of this slab along x: w = s * (f - c)^2 + o  (three_d/p2g.py:55)
+    const T sx = li == 1 ? (T)-1 : (T)0.5, cx_ = (T)1.5 - (T)0.5 * ci, ox_ = li == 1 ? (T)0.75 : (T)0;
+    T ax[9], ay[9], az[9], am[9];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) ax[e] = ay[e] = az[e] = am[e] = (T)0;
+    for (int qi = r0; qi < r1; ++qi) {
+      const int ph = p2g_pad(qi);
+      const P2GVec4<T> p0 = S.pay[0][ph], p1 = S.pay[1][ph], p2 = S.pay[2][ph], p3 = S.pay[3][ph];
+      const T fx = p1.w, fy = p2.w, fz = p3.w;
+      T wy[3], wz[3];
+      bspline(fy, wy[0], wy[1], wy[2]);
+      bspline(fz, wz[0], wz[1], wz[2]);
+      const T tx_ = fx - cx_;
+      const T wxi = sx * tx_ * tx_ + ox_;
+      const T dpx = ci - fx;
+      const T bx = p0.x + p1.x * dpx, by = p0.y + p2.x * dpx, bz = p0.z + p3.x * dpx;
+      const T dz[3] = {-fz, (T)1 - fz, (T)2 - fz};
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const T dpy = (T)j - fy;
+        const T wij = wxi * wy[j];
+        const T cxj = bx + p1.y * dpy, cyj = by + p2.y * dpy, czj = bz + p3.y * dpy;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const T w = wij * wz[k];
+          ax[j * 3 + k] += w * (cxj + p1.z * dz[k]);
+          ay[j * 3 + k] += w * (cyj + p2.z * dz[k]);
+          az[j * 3 + k] += w * (czj + p3.z * dz[k]);
+          am[j * 3 + k] += w * p0.w;
+        }
+      }
+    }
+    T* g = grid + ((long long)S.node0[r0] + (long long)li * ny * nz) * 4;
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        red_add4(g + ((long long)j * nz + k) * 4, ax[j * 3 + k], ay[j * 3 + k], az[j * 3 + k], am[j * 3 + k]);
+  }
+}
+
 // USE_PERM: walk the particles through the counting-sort permutation (exactly cell-sorted);
 // otherwise in physical order, which the reordering G2P keeps sorted up to one substep of
-// motion (a particle that changed cell merely splits a run: correct for ANY order).
+// motion.
 template <typename T, int MIN_BLOCKS, bool USE_PERM>
 __global__ void __launch_bounds__(P2G_RUN_WARPS * 32, MIN_BLOCKS)
 p2g_runs3_kernel(DevCfg cfg, StateView<T> s, long long n, BinBuffers B, T* __restrict__ grid, ErrRec* err) {
@@ -63,7 +152,6 @@ p2g_runs3_kernel(DevCfg cfg, StateView<T> s, long long n, BinBuffers B, T* __res
   for (int win = blockIdx.x * P2G_RUN_WARPS + warp; win < n_windows; win += total_warps) {
     const int w0 = win * P2G_WINDOW;
     const int cnt = min(P2G_WINDOW, n_in - w0);
-    // ---- phase 1 ----
     int node[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -72,84 +160,11 @@ p2g_runs3_kernel(DevCfg cfg, StateView<T> s, long long n, BinBuffers B, T* __res
       if (idx < cnt) {
         const long long p = USE_PERM ? (long long)B.perm[w0 + idx] : (long long)(w0 + idx);
         P2GParticle3<T> q = p2g_prepare3(cfg, s, p);
-        const int ph = p2g_pad(idx);
-        if (!q.ok) {   // outside the grid (only reachable without the permutation): contributes nothing
-          q.mvx = q.mvy = q.mvz = q.m = (T)0;
-          q.a00 = q.a01 = q.a02 = q.a10 = q.a11 = q.a12 = q.a20 = q.a21 = q.a22 = (T)0;
-          q.fx = q.fy = q.fz = (T)0.5;
-        }
-        S.pay[0][ph] = P2GVec4<T>{q.mvx, q.mvy, q.mvz, q.m};
-        S.pay[1][ph] = P2GVec4<T>{q.a00 * dx, q.a01 * dx, q.a02 * dx, q.fx};
-        S.pay[2][ph] = P2GVec4<T>{q.a10 * dx, q.a11 * dx, q.a12 * dx, q.fy};
-        S.pay[3][ph] = P2GVec4<T>{q.a20 * dx, q.a21 * dx, q.a22 * dx, q.fz};
-        node[h] = q.ok ? (q.bx * ny + q.by) * nz + q.bz : -1;
-        S.node0[idx] = node[h];
+        node[h] = p2g_park(S, q, idx, dx, ny, nz);
       }
     }
     __syncwarp();
-    // run heads: first slot of the window, or base cell differs from the predecessor's
-    unsigned heads[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int idx = h * 32 + lane;
-      const int prev = idx > 0 ? S.node0[idx - 1] : -2;
-      heads[h] = __ballot_sync(0xffffffffu, idx < cnt && node[h] != prev);
-    }
-    const int n0 = __popc(heads[0]);
-    const int n_runs = n0 + __popc(heads[1]);
-    {
-      const unsigned below = (1u << lane) - 1u;
-      if (heads[0] & (1u << lane)) S.run_start[__popc(heads[0] & below)] = lane;
-      if (heads[1] & (1u << lane)) S.run_start[n0 + __popc(heads[1] & below)] = 32 + lane;
-      if (lane == 0) S.run_start[n_runs] = cnt;
-    }
-    __syncwarp();
-    // ---- phase 2: lane per (run, x-slab) ----
-    const int n_items = n_runs * 3;
-    for (int item = lane; item < n_items; item += 32) {
-      const int r = item / 3, li = item - r * 3;
-      const int r0 = S.run_start[r], r1 = S.run_start[r + 1];
-      if (S.node0[r0] < 0) continue;   // a run of out-of-grid particles
-      const T ci = (T)li;
-      // B-spline piece of this slab along x: w = s * (f - c)^2 + o  (three_d/p2g.py:55)
-      const T sx = li == 1 ? (T)-1 : (T)0.5, cx_ = (T)1.5 - (T)0.5 * ci, ox_ = li == 1 ? (T)0.75 : (T)0;
-      T ax[9], ay[9], az[9], am[9];
-#pragma unroll
-      for (int e = 0; e < 9; ++e) ax[e] = ay[e] = az[e] = am[e] = (T)0;
-      for (int qi = r0; qi < r1; ++qi) {
-        const int ph = p2g_pad(qi);
-        const P2GVec4<T> p0 = S.pay[0][ph], p1 = S.pay[1][ph], p2 = S.pay[2][ph], p3 = S.pay[3][ph];
-        const T fx = p1.w, fy = p2.w, fz = p3.w;
-        T wy[3], wz[3];
-        bspline(fy, wy[0], wy[1], wy[2]);
-        bspline(fz, wz[0], wz[1], wz[2]);
-        const T tx_ = fx - cx_;
-        const T wxi = sx * tx_ * tx_ + ox_;
-        const T dpx = ci - fx;
-        const T bx = p0.x + p1.x * dpx, by = p0.y + p2.x * dpx, bz = p0.z + p3.x * dpx;
-        const T dz[3] = {-fz, (T)1 - fz, (T)2 - fz};
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const T dpy = (T)j - fy;
-          const T wij = wxi * wy[j];
-          const T cxj = bx + p1.y * dpy, cyj = by + p2.y * dpy, czj = bz + p3.y * dpy;
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            const T w = wij * wz[k];
-            ax[j * 3 + k] += w * (cxj + p1.z * dz[k]);
-            ay[j * 3 + k] += w * (cyj + p2.z * dz[k]);
-            az[j * 3 + k] += w * (czj + p3.z * dz[k]);
-            am[j * 3 + k] += w * p0.w;
-          }
-        }
-      }
-      T* g = grid + ((long long)S.node0[r0] + (long long)li * ny * nz) * 4;
-#pragma unroll
-      for (int j = 0; j < 3; ++j)
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-          red_add4(g + ((long long)j * nz + k) * 4, ax[j * 3 + k], ay[j * 3 + k], az[j * 3 + k], am[j * 3 + k]);
-    }
+    p2g_runs_phase2<T>(S, node, cnt, lane, ny, nz, grid);
     __syncwarp();   // the slab is rewritten by the next window
   }
 }
@@ -163,7 +178,7 @@ int p2g_runs(const DevCfg& cfg, const StateView<T>& s, long long n, BinBuffers& 
   int blocks = (int)(want < cap ? want : cap);
   if (blocks < 1) blocks = 1;
   // MIN_BLOCKS trades registers for resident warps; tunable via FFMPM_P2G_MINB
-  static int minb = [] { const char* e = getenv("FFMPM_P2G_MINB"); return e ? atoi(e) : 4; }();
+  static int minb = [] { const char* e = getenv("FFMPM_P2G_MINB"); return e ? atoi(e) : 5; }();
 #define FFMPM_LAUNCH_P2G(MB)                                                                              \
   do {                                                                                                    \
     if (use_perm)                                                                                         \
@@ -172,9 +187,8 @@ int p2g_runs(const DevCfg& cfg, const StateView<T>& s, long long n, BinBuffers& 
       p2g_runs3_kernel<T, MB, false><<<blocks, P2G_RUN_WARPS * 32, 0, st>>>(cfg, s, n, B, grid, err);     \
   } while (0)
   if (minb >= 6) FFMPM_LAUNCH_P2G(6);
-  else if (minb == 5) FFMPM_LAUNCH_P2G(5);
-  else if (minb == 3) FFMPM_LAUNCH_P2G(3);
-  else FFMPM_LAUNCH_P2G(4);
+  else if (minb == 4) FFMPM_LAUNCH_P2G(4);
+  else FFMPM_LAUNCH_P2G(5);
 #undef FFMPM_LAUNCH_P2G
   return 1;
 }
