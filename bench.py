@@ -146,6 +146,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--p2g-mode", default="auto")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--slab-timing", action="store_true", help="N>1: print per-phase CUDA-event times per rank to stderr")
     ap.add_argument("--margin", type=int, default=4, help="slab halo margin in cells = substeps between migrations")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -216,6 +217,13 @@ def main():
     else:
         n_total = n
     clocks = sampler.stop() if rank == 0 else None
+    if world > 1 and args.slab_timing:
+        solver.driver.enable_timing()
+        for _ in range(20):
+            solver.substep(1)
+        tm = solver.driver.collect_timing()
+        print(f"[rank {rank}] slab phase ms/substep: " + ", ".join(f"{k} {v / 20:.3f}" for k, v in tm.items()),
+              file=sys.stderr, flush=True)
     n_oob = solver.poll_error()
     value = n_total * args.steps / (ms * 1e-3)
 

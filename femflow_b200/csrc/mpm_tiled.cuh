@@ -56,8 +56,8 @@ __device__ __forceinline__ void bulk_store_g(void* gdst, const void* ssrc, unsig
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(sa), "r"(bytes) : "memory");
 }
 
-template <typename T, bool BULK>
-__global__ void __launch_bounds__(G2P_THREADS) g2p_tiled3_kernel(DevCfg cfg, StateView<T> src, StateView<T> dst,
+template <typename T, bool BULK, int MIN_BLOCKS>
+__global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_tiled3_kernel(DevCfg cfg, StateView<T> src, StateView<T> dst,
                                                                  BinBuffers B, const T* __restrict__ grid, ErrRec* err) {
   static_assert(!BULK || sizeof(T) == 4, "bulk staging is for the fp32 build");
   using V4 = typename Vec4<T>::type;
@@ -212,13 +212,24 @@ int g2p_tiled(const DevCfg& cfg, const StateView<T>& src, const StateView<T>& ds
   (void)n;
   cudaMemsetAsync(&B.counters[2], 0, sizeof(int32_t), st);
   int blocks = min(B.n_tiles + 1, sm_count * blocks_per_sm);
+  static int minb = [] { const char* e = getenv("FFMPM_G2P_MINB"); return e ? atoi(e) : 8; }();
   if constexpr (sizeof(T) == 4) {
     if (bulk) {
-      g2p_tiled3_kernel<T, true><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
+      g2p_tiled3_kernel<T, true, 4><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
       return 1;
     }
+    if (minb >= 8) {
+      g2p_tiled3_kernel<T, false, 8><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
+      return 1;
+    }
+    if (minb == 7) {
+      g2p_tiled3_kernel<T, false, 7><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
+      return 1;
+    }
+    g2p_tiled3_kernel<T, false, 6><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
+    return 1;
   }
-  g2p_tiled3_kernel<T, false><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
+  g2p_tiled3_kernel<T, false, 4><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
   return 1;
 }
 

@@ -144,13 +144,42 @@ class SlabDriver:
 
     def substep(self, n: int = 1) -> None:
         for _ in range(n):
+            self._mark("start")
             self.local.scatter()
+            self._mark("scatter")
             self._exchange_halos()
+            self._mark("halo")
             self.local.grid_update(self.recv_lo, self.plan.planes_lo, self.recv_hi, self.plan.planes_hi)
+            self._mark("grid")
             self.local.gather()
+            self._mark("gather")
             self.steps += 1
             if self.plan.world > 1 and self.steps % self.migrate_every == 0:
                 self.migrate()
+                self._mark("migrate")
+
+    # -- optional per-phase CUDA-event timing (bench --slab-timing) ----------------
+    timing = None      # dict phase -> accumulated ms when enabled
+
+    def enable_timing(self) -> None:
+        self.timing, self._events = {}, []
+
+    def _mark(self, name: str) -> None:
+        if self.timing is None or self.local.device.type != "cuda":
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self._events.append((name, ev))
+
+    def collect_timing(self) -> dict:
+        torch.cuda.synchronize()
+        prev = None
+        for name, ev in self._events:
+            if name != "start" and prev is not None:
+                self.timing[name] = self.timing.get(name, 0.0) + prev.elapsed_time(ev)
+            prev = ev
+        self._events = []
+        return dict(self.timing)
 
     # -- particle migration to the +-1 neighbours -------------------------------
     def migrate(self) -> None:
@@ -252,16 +281,38 @@ class CudaSlab(LocalSlab):
         s = self.solver
         b = s.live
         n = s.num_particles
-        base = torch.trunc(b.x[0, :n].double() * self.inv_dx - 0.5)
-        left_idx = torch.nonzero(base < own_lo).flatten()
-        right_idx = torch.nonzero(base >= own_hi).flatten()
+        x0 = b.x[0, :n]
+        # base = trunc(x*inv_dx - 0.5) is monotone in x, so "base < own_lo" / "base >= own_hi" are plain
+        # comparisons against the smallest storage-precision x of the boundary cell (found on the
+        # host with the kernels' own fp64 expression): one pass over x, one scalar readback.
+        t_lo, t_hi = self._threshold(own_lo), self._threshold(own_hi)
+        out = (x0 < t_lo) | (x0 >= t_hi)
+        if int(torch.count_nonzero(out)) == 0:
+            empty = torch.empty(0, dtype=torch.int64, device=self.device)
+            return self._pack(b, empty), self._pack(b, empty)
+        left_idx = torch.nonzero(x0 < t_lo).flatten()
+        right_idx = torch.nonzero(x0 >= t_hi).flatten()
         left, right = self._pack(b, left_idx), self._pack(b, right_idx)
-        if left_idx.numel() + right_idx.numel() > 0:
-            keep = torch.nonzero((base >= own_lo) & (base < own_hi)).flatten()
-            other = 1 - s.live_index
-            self._store(self._pack(b, keep), 0, other)     # compact the keepers into the idle buffer
-            s._bind(keep.numel(), cur=other)
+        keep = torch.nonzero(~out).flatten()
+        other = 1 - s.live_index
+        self._store(self._pack(b, keep), 0, other)     # compact the keepers into the idle buffer
+        s._bind(keep.numel(), cur=other)
         return left, right
+
+    def _threshold(self, cell: int):
+        """Smallest value of the storage dtype whose base cell is >= ``cell``."""
+        np_dt = np.float64 if self.dtype == torch.float64 else np.float32
+        if cell <= 0:
+            return float("-inf")          # base 0 also holds x*inv_dx - 0.5 in (-1, 0): truncation toward zero (quirk 1)
+        x = np_dt((cell + 0.5) / self.inv_dx)
+
+        def base(v):
+            return int(np.float64(v) * self.inv_dx - 0.5)
+        while base(x) >= cell:
+            x = np.nextafter(x, np_dt(-np.inf))
+        while base(x) < cell:
+            x = np.nextafter(x, np_dt(np.inf))
+        return float(x)
 
     def _store(self, payload, at: int, buf: int) -> None:
         data, ids = payload
