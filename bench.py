@@ -169,9 +169,21 @@ def main():
 
     from femflow_b200.mpm import MpmSolver
 
-    scene = make_scene(args.workload, seed=rank)
+    dam = args.workload.startswith("dam")
+    scene = make_scene("3d:256:8" if dam else args.workload, seed=rank)
     n = scene.n
-    if world > 1:
+    if dam:
+        # BASELINE configs[4] (report only): --workload dam32m, or dam:<n_total> for smaller runs
+        from femflow_b200.distributed import SlabSolver
+        n_total_req = 33_554_432 if args.workload == "dam32m" else int(args.workload.split(":")[1])
+        if world == 1:
+            import torch.distributed as dist_  # noqa: F401  (single rank: the driver never communicates)
+        solver = SlabSolver.from_dam_break(rank, world, dev, n_total=n_total_req, margin=args.margin,
+                                           p2g_mode=args.p2g_mode)
+        scene.name = solver.scene_name
+        scene.dt = solver.local.solver.cfg.dt
+        n = solver.num_particles
+    elif world > 1:
         from femflow_b200.distributed import SlabSolver
         solver = SlabSolver.from_scene(scene, rank, world, dev, p2g_mode=args.p2g_mode, margin=args.margin)
     else:
@@ -229,7 +241,7 @@ def main():
 
     # ---- per-phase timing (same stream, CUDA events) for the roofline of the dominant kernel ----
     phases = {}
-    if world == 1:
+    if world == 1 and not dam:
         names = (["bin"] if (scene.dim == 3 and solver.reorder) else []) + ["p2g", "grid_op", "g2p"]
         acc = {k: 0.0 for k in ["clear"] + names}
         reps = max(3, min(args.steps, 10))
@@ -249,7 +261,7 @@ def main():
 
     # ---- end to end through host buffers (pinned), every step: H2D state, substep, D2H result ----
     e2e = None
-    if True:
+    if not dam:
         d = scene.dim
         core = solver if world == 1 else solver.local.solver      # the MpmSolver that owns the buffers
         n = core.num_particles
@@ -305,6 +317,11 @@ def main():
     # ---- roofline of the dominant kernel ----
     peak, peak_src = peaks()
     roofline = None
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(args.workload, {})
     if phases:
         N_, A = n, scene.active_nodes
         if scene.dim == 3:
@@ -315,7 +332,8 @@ def main():
         achieved = alg[dom] / (phases[dom] * 1e-3) / 1e9
         total_alg = (252 * N_ + 72 * A) if scene.dim == 3 else (128 * N_ + 52 * A)
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": traffic.get(dom), "peak_source": peak_src,
+                    "traffic_source": traffic.get("source") if traffic.get(dom) else None,
                     "algorithmic_bytes_per_launch": alg[dom],
                     "phase_ms": {k: round(v, 4) for k, v in phases.items()},
                     "substep_frac_of_hbm_roofline": (total_alg / (ms * 1e-3 / args.steps) / 1e9) / peak}

@@ -127,6 +127,11 @@ class SlabDriver:
         self.recv_hi = torch.zeros(shape_hi, dtype=probe.dtype, device=probe.device)
         self.halo_bytes = (self.recv_lo.numel() + self.recv_hi.numel()) * probe.element_size()
         self.migrated = 0
+        self._pending = None
+        if hasattr(local, "count_leavers_async") and plan.world > 1:
+            # the leaver count is acted upon one substep after it was taken
+            if self.migrate_every + 1 > max(2, plan.margin):
+                self.migrate_every = max(1, plan.margin - 1)
 
     # -- halo planes: exchange partial sums with both neighbours ------------------
     def _exchange_halos(self) -> None:
@@ -154,9 +159,31 @@ class SlabDriver:
             self.local.gather()
             self._mark("gather")
             self.steps += 1
-            if self.plan.world > 1 and self.steps % self.migrate_every == 0:
-                self.migrate()
+            if self.plan.world > 1:
+                self._maybe_migrate()
                 self._mark("migrate")
+
+    def _maybe_migrate(self) -> None:
+        """Migration cadence.  Local solvers that can count their leavers asynchronously
+        (``count_leavers_async``) are polled one substep late: the count of substep k -- max-reduced
+        over the ranks on the device, so that all ranks take the same decision -- is read after
+        substep k+1 has been queued: the host never drains the GPU."""
+        L = self.local
+        due = self.steps % self.migrate_every == 0
+        if not hasattr(L, "count_leavers_async"):
+            if due:
+                self.migrate()
+            return
+        if self._pending is not None:
+            k, handle = self._pending
+            if self.steps > k:                      # one substep of GPU work is queued behind the count
+                self._pending = None
+                if L.read_leaver_count(handle) > 0:     # already the max over all ranks
+                    self.migrate()
+        if due and self._pending is None:
+            cnt = L.count_leavers_async(self.plan.own_lo, self.plan.own_hi)      # (1,) int64 on the device
+            dist.all_reduce(cnt, op=dist.ReduceOp.MAX, group=self.group)         # every rank takes the same decision
+            self._pending = (self.steps, L.stage_leaver_count(cnt))
 
     # -- optional per-phase CUDA-event timing (bench --slab-timing) ----------------
     timing = None      # dict phase -> accumulated ms when enabled
@@ -299,6 +326,25 @@ class CudaSlab(LocalSlab):
         s._bind(keep.numel(), cur=other)
         return left, right
 
+    def count_leavers_async(self, own_lo: int, own_hi: int):
+        """Device-side count of the particles whose base cell left [own_lo, own_hi)."""
+        s = self.solver
+        x0 = s.live.x[0, :s.num_particles]
+        t_lo, t_hi = self._threshold(own_lo), self._threshold(own_hi)
+        return torch.count_nonzero((x0 < t_lo) | (x0 >= t_hi)).to(torch.int64).reshape(1)
+
+    def stage_leaver_count(self, cnt):
+        if not hasattr(self, "_cnt_host"):
+            self._cnt_host = torch.zeros(1, dtype=torch.int64).pin_memory()
+        self._cnt_host.copy_(cnt, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return ev
+
+    def read_leaver_count(self, handle) -> int:
+        handle.synchronize()
+        return int(self._cnt_host[0])
+
     def _threshold(self, cell: int):
         """Smallest value of the storage dtype whose base cell is >= ``cell``."""
         np_dt = np.float64 if self.dtype == torch.float64 else np.float32
@@ -368,6 +414,28 @@ class SlabSolver:
         local.set_particles(x, scene.v, scene.F, scene.C, scene.mass, scene.mu_0, scene.lambda_0,
                             (ids % (2 ** 31)).astype(np.int32))
         return cls(plan, local, SlabDriver(plan, local))
+
+    @classmethod
+    def from_dam_break(cls, rank: int, world: int, device, res: int = 256, n_total: int = 33_554_432,
+                       margin: int = 4, capacity: Optional[int] = None, p2g_mode: str = "auto"):
+        """BASELINE configs[4]: soft column at one x-end of a (res*world) x res x res domain;
+        every rank generates the particles of its own x interval.  Slabs are static (no
+        rebalancing yet), so ranks away from the column start empty."""
+        from . import scenes
+        plan = SlabPlan.make((res * world, res, res), world, rank, margin)
+        dx = 1.0 / res
+        lo = (plan.own_lo + 0.5) * dx if rank > 0 else -1.0
+        hi = (plan.own_hi + 0.5) * dx if rank < world - 1 else float(world) + 1.0
+        sc = scenes.dam_break_slab(world, rank, res, n_total, x_range=(lo, hi))
+        cap = capacity or max(int(n_total * 0.6), sc.n + 1024)
+        local = CudaSlab(plan, dx, sc.dt, sc.volume, sc.gravity, sc.hardening, capacity=cap, device=device,
+                         p2g_mode=p2g_mode)
+        ids = (np.arange(sc.n, dtype=np.int64) + rank * (2 ** 27)) % (2 ** 31)
+        if sc.n:
+            local.set_particles(sc.x, sc.v, sc.F, sc.C, sc.mass, sc.mu_0, sc.lambda_0, ids.astype(np.int32))
+        obj = cls(plan, local, SlabDriver(plan, local))
+        obj.scene_name = sc.name
+        return obj
 
     @property
     def num_particles(self) -> int:

@@ -84,3 +84,47 @@ def config_2d_1m(seed: int = 0) -> Scene:
 def config_3d_16m(seed: int = 0) -> Scene:
     """BASELINE configs[2]: 3D, 16 777 216 particles, 256^3 grid."""
     return elastic_block(3, 256, 128, 2, seed)
+
+
+def dam_break_slab(world: int, rank: int, res: int = 256, n_total: int = 33_554_432, seed: int = 0,
+                   x_range=None) -> Scene:
+    """BASELINE configs[4]: a tall soft column at one x-end of a (res*world) x res x res
+    domain, ~8.9 particles per cell, that collapses onto the floor (high atomic contention
+    near the floor, strong load imbalance between slabs).  Returns only the particles whose
+    x lies in ``x_range`` (this rank's owned interval); all ranks draw from the same
+    deterministic per-cell streams, so the union over ranks is one scene."""
+    dx = 1.0 / res
+    L = float(world)
+    x0, x1 = 0.05 * L, 0.20 * L
+    y0, y1, z0, z1 = 0.02, 0.92, 0.40, 0.60
+    cx0, cx1 = int(round(x0 * res)), int(round(x1 * res))
+    cy0, cy1 = int(round(y0 * res)), int(round(y1 * res))
+    cz0, cz1 = int(round(z0 * res)), int(round(z1 * res))
+    n_cells = (cx1 - cx0) * (cy1 - cy0) * (cz1 - cz0)
+    ppc = max(1, int(round(n_total / n_cells)))
+    if x_range is not None:
+        lo = max(cx0, int(np.floor(x_range[0] * res)))
+        hi = min(cx1, int(np.ceil(x_range[1] * res)))
+    else:
+        lo, hi = cx0, cx1
+    xs = np.arange(lo, max(lo, hi), dtype=np.float32)
+    ys = np.arange(cy0, cy1, dtype=np.float32)
+    zs = np.arange(cz0, cz1, dtype=np.float32)
+    rng = np.random.default_rng(seed * 1000003 + rank)
+    X, Y, Z = np.meshgrid(xs, ys, zs, indexing="ij")
+    cell = np.stack([X.reshape(-1), Y.reshape(-1), Z.reshape(-1)], -1)
+    cell = np.repeat(cell, ppc, axis=0)
+    pos = ((cell + rng.uniform(0.02, 0.98, size=cell.shape).astype(np.float32)) * np.float32(dx)).astype(np.float32)
+    if x_range is not None and len(pos):
+        keep = (pos[:, 0] >= x_range[0]) & (pos[:, 0] < x_range[1])
+        pos = pos[keep]
+    n = len(pos)
+    E, nu, rho = 1e3, 0.3, 1.0
+    mu, lam = _lame(E, nu)
+    volume = float(np.float32(dx ** 3 / ppc))
+    c_wave = np.sqrt((lam + 2 * mu) / rho)
+    dt = float(np.float32(0.2 * dx / c_wave))
+    return Scene(3, res, dt, volume, -9.8, 1.0, pos, np.zeros((n, 3), np.float32),
+                 np.tile(np.eye(3, dtype=np.float32), (n, 1, 1)), np.zeros((n, 3, 3), np.float32),
+                 float(np.float32(rho * volume)), float(np.float32(mu)), float(np.float32(lam)), 0,
+                 f"3D dam break, {ppc} ppc column {cx1 - cx0}x{cy1 - cy0}x{cz1 - cz0} cells on {res * world}x{res}x{res}")

@@ -401,11 +401,27 @@ def gen_snow3d(ref):
          x_out=positions(particles), v_out=vo, F_out=Fo, C_out=Co, Jp_out=Jpo)
 
 
+def gen_snow2d(ref):
+    """2D snow branch: hardening by exp(h (1 - Jp)) in P2G (utils.py:27-49) and the
+    singular-value clamp + Jp update in G2P (two_d/g2p.py:37-47), det F > 0 inputs."""
+    rng = np.random.default_rng(8)
+    n, res = 1500, 64
+    p = dict(TEST2D, res=res, dt=1e-4, gravity=-9.8, mass=float(f32(1.0 / 64 ** 2 / 4)),
+             volume=float(f32(1.0 / 64 ** 2 / 4)), hardening=10.0)
+    x = f32(rng.uniform(0.1, 0.9, size=(n, 2)))
+    v = f32(rng.normal(0, 0.5, size=(n, 2)))
+    F = f32(np.eye(2) + rng.normal(0, 0.03, size=(n, 2, 2)))
+    C = f32(rng.normal(0, 0.5, size=(n, 2, 2)))
+    Jp = f32(rng.uniform(0.9, 1.1, size=(n, 1)))
+    out = run_phases_2d(ref, p, x, v, F, C, Jp, model="snow")
+    save("snow2d", x=x, v=v, F=F, C=C, Jp=Jp, **{k: np.float64(val) for k, val in p.items()}, **out)
+
+
 def main(argv):
     ref = _import_reference()
     gens = dict(kat3d=gen_kat3d, block3d=gen_block3d, rest3d=gen_rest3d, walls3d=gen_walls3d,
                 c1=gen_c1, drift3d=gen_drift3d, test2d=gen_test2d, drift2d=gen_drift2d, block2d=gen_block2d,
-                quirk2d=gen_quirk2d, snow3d=gen_snow3d)
+                quirk2d=gen_quirk2d, snow3d=gen_snow3d, snow2d=gen_snow2d)
     which = argv[1:] or list(gens)
     for name in which:
         print(f"== {name}")

@@ -92,6 +92,24 @@ class OracleSlab(LocalSlab):
             setattr(self, name, getattr(self, name)[keep])
         return left, right
 
+    # optional asynchronous-count interface (exercises SlabDriver's lagged migration decision)
+    lagged = False
+
+    def __getattribute__(self, name):
+        if name in ("count_leavers_async", "stage_leaver_count", "read_leaver_count") and not object.__getattribute__(self, "lagged"):
+            raise AttributeError(name)
+        return object.__getattribute__(self, name)
+
+    def count_leavers_async(self, own_lo, own_hi):
+        base, _ = O.base_and_fx(self.x, self.p["inv_dx"])
+        return torch.tensor([int(np.count_nonzero((base[:, 0] < own_lo) | (base[:, 0] >= own_hi)))], dtype=torch.int64)
+
+    def stage_leaver_count(self, cnt):
+        return cnt.clone()
+
+    def read_leaver_count(self, handle):
+        return int(handle[0])
+
     def append(self, payload):
         data, ids = payload[0].numpy(), payload[1].numpy()
         n = data.shape[1]
@@ -116,7 +134,7 @@ def make_scene(res=24, n=1500, seed=3):
     return p, (x, v, F, C, mass, mu0, lam0, np.arange(n, dtype=np.int64))
 
 
-def _worker(rank, world, port, steps, margin, migrate_every, out):
+def _worker(rank, world, port, steps, margin, migrate_every, out, lagged=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -125,6 +143,7 @@ def _worker(rank, world, port, steps, margin, migrate_every, out):
         base, _ = O.base_and_fx(state[0], p["inv_dx"])
         mine = np.flatnonzero((base[:, 0] >= plan.own_lo) & (base[:, 0] < plan.own_hi))
         local = OracleSlab(plan, p, tuple(a[mine].copy() for a in state))
+        local.lagged = lagged
         drv = SlabDriver(plan, local, migrate_every=migrate_every)
         drv.substep(steps)
         gathered = [None] * world
@@ -146,11 +165,12 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("world,margin,migrate_every", [(2, 2, 2), (3, 1, 1), (2, 3, 2)])
-def test_slabs_match_single_domain(tmp_path, world, margin, migrate_every):
-    steps = 6
+@pytest.mark.parametrize("world,margin,migrate_every,lagged", [(2, 2, 2, False), (3, 1, 1, False), (2, 3, 2, False),
+                                                                  (2, 3, 2, True), (3, 2, 1, True)])
+def test_slabs_match_single_domain(tmp_path, world, margin, migrate_every, lagged):
+    steps = 7
     out = str(tmp_path / "res.pt")
-    mp.spawn(_worker, args=(world, _free_port(), steps, margin, migrate_every, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), steps, margin, migrate_every, out, lagged), nprocs=world, join=True)
     got = torch.load(out, weights_only=False)
     p, (x, v, F, C, mass, mu0, lam0, ids) = make_scene()
     Jp = np.ones((len(x), 1))

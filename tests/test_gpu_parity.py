@@ -282,3 +282,25 @@ def test_2d_wall_masks_bit_exact():
         O.grid_op_2d(res, 1.0, 0.0, ref, gm.copy())
         two_d.grid_op(res, 1.0, 0.0, gv, gm)
         assert np.array_equal(gv, ref)
+
+
+def test_2d_snow_matches_reference(dtype):
+    """2D snow model end to end: snow_hardening in P2G (utils.py:27-49), singular-value clamp
+    to [1-2.5e-2, 1+7.5e-3] and Jp update in G2P (two_d/g2p.py:37-47)."""
+    from femflow_b200.solvers.mpm import two_d
+    g = load_golden("snow2d")
+    p = _p2(g)
+    tol = TOL[dtype]
+    res = p["res"]; G = res + 1
+    x, v, F, C, Jp = (g[k].copy() for k in ("x", "v", "F", "C", "Jp"))
+    V = max(float(np.abs(g["grid_velocity"]).max()), p["dt"] * abs(p["gravity"]))
+    gv = np.zeros((G, G, 2)); gm = np.zeros((G, G, 1))
+    two_d.p2g(float(res), p["hardening"], p["mu_0"], p["lambda_0"], p["mass"], 1.0 / res, p["dt"], p["volume"],
+              gv, gm, x, v, F, C, Jp, "snow")
+    assert rel_err(gv, g["grid_momentum"], p["mass"] * V) < tol
+    gv = g["grid_velocity"].copy()
+    two_d.g2p(float(res), p["dt"], gv, x, v, F, C, Jp, "snow")
+    assert rel_err(x, g["x_out"], 1.0) < tol
+    assert rel_err(F, g["F_out"], 1.0) < tol
+    assert rel_err(C, g["C_out"], 4 * res * V) < tol
+    assert rel_err(Jp, g["Jp_out"], 1.0) < tol

@@ -251,3 +251,19 @@ def test_c_oracle_2d_and_drivers():
             assert rel_err(x, g[f"x_{step}"]) < 1e-12
             assert rel_err(v, g[f"v_{step}"]) < 1e-9
             assert rel_err(F, g[f"F_{step}"]) < 1e-11
+
+
+def test_snow2d_matches_reference():
+    """2D snow: exp hardening in P2G, singular-value clamp and Jp update in G2P."""
+    g = load_golden("snow2d")
+    p = _p2(g)
+    x, v, F, C, Jp = (g[k].copy() for k in ("x", "v", "F", "C", "Jp"))
+    mom, mass, vel = O.solve_mls_mpm_2d(p["res"], float(p["res"]), p["hardening"], p["mu_0"], p["lambda_0"], p["mass"],
+                                        1.0 / p["res"], p["dt"], p["volume"], p["gravity"], x, v, F, C, Jp,
+                                        model="snow", return_grids=True)
+    assert rel_err(mom, g["grid_momentum"]) < TIGHT
+    assert rel_err(vel, g["grid_velocity"]) < TIGHT
+    for got, key in ((x, "x_out"), (v, "v_out"), (C, "C_out"), (Jp, "Jp_out"), (F, "F_out")):
+        assert rel_err(got, g[key]) < 1e-11, key
+    # the clamp really acts in this fixture
+    assert np.abs(g["Jp_out"] - g["Jp"]).max() > 1e-3
