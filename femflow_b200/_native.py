@@ -55,6 +55,8 @@ PROTOTYPES = {
     "ffmpm_grid_op": (C.c_int, [H, C.c_void_p]),
     "ffmpm_g2p": (C.c_int, [H, C.c_void_p]),
     "ffmpm_grid_op_halo": (C.c_int, [H, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
+    "ffmpm_scatter": (C.c_int, [H, C.c_void_p]),
+    "ffmpm_gather": (C.c_int, [H, C.c_void_p]),
     "ffmpm_substep": (C.c_int, [H, C.c_int32, C.c_void_p]),
     "ffmpm_grid_ptr": (C.c_int, [H, C.POINTER(C.c_void_p)]),
     "ffmpm_bin_ptrs": (C.c_int, [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),

@@ -41,7 +41,15 @@ struct FfMpmHandle {
   char* ws;
   int64_t ws_bytes;
   ErrRec* err;
-  void* grid;
+  void* grid;          // grid of the current substep (one of grids[])
+  void* grids[2];      // ping-pong: the idle one is cleared behind G2P on the auxiliary stream
+  int grid_cur;
+  bool grid_clean[2];  // known to be all-zero
+  bool clear_pending;  // a clear of grids[grid_cur ^ 1] is in flight on `aux` (ev_clear)
+  bool bin_pending;    // the binning of this substep is in flight on `aux` (ev_join)
+  cudaStream_t aux;    // internal stream for work that overlaps the compute-bound P2G
+  cudaEvent_t ev_fork, ev_join, ev_clear;
+  int overlap;         // FFMPM_OVERLAP=0 disables the auxiliary stream
   BinBuffers bin;
   // state
   FfMpmState st[2];
@@ -77,7 +85,7 @@ static int validate(const FfMpmConfig* c) {
 }
 
 struct WsLayout {
-  int64_t err_off, grid_off, bin_off, total;
+  int64_t err_off, grid_off, grid2_off, bin_off, total;
 };
 
 static WsLayout layout(const FfMpmConfig& c, int64_t capacity) {
@@ -85,7 +93,8 @@ static WsLayout layout(const FfMpmConfig& c, int64_t capacity) {
   int64_t nodes = (int64_t)c.n[0] * c.n[1] * c.n[2];
   L.err_off = 0;
   L.grid_off = 256;
-  L.bin_off = align_up(L.grid_off + nodes * 4 * (int64_t)elem_size(c), 256);
+  L.grid2_off = align_up(L.grid_off + nodes * 4 * (int64_t)elem_size(c), 256);
+  L.bin_off = align_up(L.grid2_off + nodes * 4 * (int64_t)elem_size(c), 256);
   L.total = L.bin_off + bin_workspace_bytes(c.dim, c.n, capacity);
   return L;
 }
@@ -131,6 +140,16 @@ int ffmpm_create(const FfMpmConfig* cfg, int32_t device, FfMpmHandle** out) {
   d.fp32_stress = 1;
   if (const char* e = getenv("FFMPM_FP32_STRESS")) d.fp32_stress = atoi(e) != 0;
   h->n_nodes = (int64_t)d.n[0] * d.n[1] * d.n[2];
+  h->overlap = 1;
+  if (const char* e = getenv("FFMPM_OVERLAP")) h->overlap = atoi(e) != 0;
+  {
+    cudaError_t ce = cudaSetDevice(device);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->ev_clear, cudaEventDisableTiming);
+    if (ce != cudaSuccess) { delete h; return set_err(FFMPM_E_CUDA, "stream/event creation: %s", cudaGetErrorString(ce)); }
+  }
   h->p2g_blocks_per_sm = 5;
   h->g2p_blocks_per_sm = 8;
   h->pipeline = 1;
@@ -145,7 +164,15 @@ int ffmpm_create(const FfMpmConfig* cfg, int32_t device, FfMpmHandle** out) {
   return FFMPM_OK;
 }
 
-void ffmpm_destroy(FfMpmHandle* h) { delete h; }
+void ffmpm_destroy(FfMpmHandle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->aux) { cudaStreamSynchronize(h->aux); cudaStreamDestroy(h->aux); }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->ev_clear) cudaEventDestroy(h->ev_clear);
+  delete h;
+}
 
 int ffmpm_set_workspace(FfMpmHandle* h, void* workspace, int64_t bytes) {
   if (!h || !workspace) return set_err(FFMPM_E_INVALID, "null handle/workspace");
@@ -163,7 +190,12 @@ int ffmpm_set_workspace(FfMpmHandle* h, void* workspace, int64_t bytes) {
   h->ws = (char*)workspace;
   h->ws_bytes = bytes;
   h->err = (ErrRec*)(h->ws + L.err_off);
-  h->grid = h->ws + L.grid_off;
+  h->grids[0] = h->ws + L.grid_off;
+  h->grids[1] = h->ws + L.grid2_off;
+  h->grid_cur = 0;
+  h->grid = h->grids[0];
+  h->grid_clean[0] = h->grid_clean[1] = false;
+  h->clear_pending = h->bin_pending = false;
   bin_carve(h->bin, h->ws + L.bin_off, h->cfg.dim, h->dev.n, lo);
   h->binned = false;
   CUDA_TRY(cudaSetDevice(h->device));
@@ -238,6 +270,7 @@ int ffmpm_clear_grid(FfMpmHandle* h, void* stream) {
   int rc = ready(h);
   if (rc) return rc;
   CUDA_TRY(cudaMemsetAsync(h->grid, 0, (size_t)h->n_nodes * 4 * elem_size(h->cfg), (cudaStream_t)stream));
+  h->grid_clean[h->grid_cur] = true;
   return FFMPM_OK;
 }
 
@@ -300,6 +333,7 @@ static int p2g_t(FfMpmHandle* h, cudaStream_t s) {
 int ffmpm_p2g(FfMpmHandle* h, void* stream) {
   int rc = ready(h);
   if (rc) return rc;
+  h->grid_clean[h->grid_cur] = false;
   if (h->n == 0) return FFMPM_OK;
   return h->cfg.dtype == FFMPM_F64 ? p2g_t<double>(h, (cudaStream_t)stream) : p2g_t<float>(h, (cudaStream_t)stream);
 }
@@ -383,17 +417,79 @@ int ffmpm_g2p(FfMpmHandle* h, void* stream) {
   return h->cfg.dtype == FFMPM_F64 ? g2p_t<double>(h, (cudaStream_t)stream) : g2p_t<float>(h, (cudaStream_t)stream);
 }
 
+// True when P2G walks the particles in physical order, i.e. does not consume the binning:
+// the binning can then run on the auxiliary stream underneath it.
+static bool p2g_independent_of_bin(const FfMpmHandle* h) {
+  return h->cfg.dim == 3 && h->have_alt && h->cfg.p2g_mode != FFMPM_P2G_SCATTER && h->pipeline == 1 &&
+         h->p2g_variant >= 1;
+}
+
+int ffmpm_scatter(FfMpmHandle* h, void* stream) {
+  int rc = ready(h);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  // (1) a zeroed grid for this substep: the one cleared behind the previous G2P, if any
+  if (h->clear_pending) {
+    CUDA_TRY(cudaStreamWaitEvent(s, h->ev_clear, 0));
+    h->clear_pending = false;
+    h->grid_clean[h->grid_cur ^ 1] = true;
+  }
+  if (h->grid_clean[h->grid_cur ^ 1] && !h->grid_clean[h->grid_cur]) {
+    h->grid_cur ^= 1;
+    h->grid = h->grids[h->grid_cur];
+  }
+  if (!h->grid_clean[h->grid_cur] && (rc = ffmpm_clear_grid(h, stream))) return rc;
+  h->grid_clean[h->grid_cur] = false;   // about to be written
+  const bool binned_pipeline = h->cfg.dim == 3 && h->have_alt && h->cfg.p2g_mode != FFMPM_P2G_SCATTER;
+  // (2) binning: underneath P2G on the auxiliary stream when P2G does not need it
+  if (binned_pipeline) {
+    if (h->overlap && p2g_independent_of_bin(h) && h->n > 0) {
+      CUDA_TRY(cudaEventRecord(h->ev_fork, s));
+      CUDA_TRY(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
+      if ((rc = bin_impl(h, (void*)h->aux, false))) return rc;
+      CUDA_TRY(cudaEventRecord(h->ev_join, h->aux));
+      h->bin_pending = true;
+    } else if ((rc = bin_impl(h, stream, h->pipeline == 0))) {
+      return rc;
+    }
+  }
+  // (3) P2G
+  return ffmpm_p2g(h, stream);
+}
+
+int ffmpm_gather(FfMpmHandle* h, void* stream) {
+  int rc = ready(h);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (h->bin_pending) {
+    CUDA_TRY(cudaStreamWaitEvent(s, h->ev_join, 0));
+    h->bin_pending = false;
+  }
+  // clear the idle grid for the next substep while G2P reads the current one
+  const bool ahead = h->overlap && h->cfg.dim == 3 && h->have_alt && !h->grid_clean[h->grid_cur ^ 1] && !h->clear_pending;
+  if (ahead) {
+    CUDA_TRY(cudaEventRecord(h->ev_fork, s));
+    CUDA_TRY(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
+    CUDA_TRY(cudaMemsetAsync(h->grids[h->grid_cur ^ 1], 0, (size_t)h->n_nodes * 4 * elem_size(h->cfg), h->aux));
+    CUDA_TRY(cudaEventRecord(h->ev_clear, h->aux));
+    h->clear_pending = true;
+  }
+  return ffmpm_g2p(h, stream);
+}
+
 int ffmpm_substep(FfMpmHandle* h, int32_t n_substeps, void* stream) {
   int rc = ready(h);
   if (rc) return rc;
   for (int32_t it = 0; it < n_substeps; ++it) {
-    if ((rc = ffmpm_clear_grid(h, stream))) return rc;
-    if (h->cfg.dim == 3 && h->have_alt && h->cfg.p2g_mode != FFMPM_P2G_SCATTER) {
-      if ((rc = bin_impl(h, stream, h->pipeline == 0))) return rc;
-    }
-    if ((rc = ffmpm_p2g(h, stream))) return rc;
+    if ((rc = ffmpm_scatter(h, stream))) return rc;
     if ((rc = ffmpm_grid_op(h, stream))) return rc;
-    if ((rc = ffmpm_g2p(h, stream))) return rc;
+    if ((rc = ffmpm_gather(h, stream))) return rc;
+  }
+  // leave no work in flight on the internal stream when control returns to the caller's stream
+  if (h->clear_pending) {
+    CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, h->ev_clear, 0));
+    h->clear_pending = false;
+    h->grid_clean[h->grid_cur ^ 1] = true;
   }
   return FFMPM_OK;
 }
@@ -401,6 +497,7 @@ int ffmpm_substep(FfMpmHandle* h, int32_t n_substeps, void* stream) {
 int ffmpm_grid_ptr(FfMpmHandle* h, void** grid) {
   if (!h || !grid || !h->ws) return set_err(FFMPM_E_STATE, "workspace not set");
   *grid = h->grid;
+  h->grid_clean[h->grid_cur] = false;   // the caller may write through this pointer
   return FFMPM_OK;
 }
 

@@ -277,10 +277,7 @@ class CudaSlab(LocalSlab):
         s.buffers[0].id[:s.num_particles] = torch.as_tensor(np.asarray(ids), device=self.device).to(torch.int32)
 
     def scatter(self) -> None:
-        s = self.solver
-        s.clear_grid()
-        s.bin(offsets_only=True)
-        s.p2g()
+        self.solver.scatter()
 
     def grid_planes(self, a: int, b: int) -> torch.Tensor:
         return self.solver.grid()[a:b]
@@ -292,7 +289,7 @@ class CudaSlab(LocalSlab):
                                          recv_hi.data_ptr() if planes_hi else None, planes_hi, s._stream()))
 
     def gather(self) -> None:
-        self.solver.g2p()
+        self.solver.gather()
 
     def payload_rows(self) -> int:
         return 3 + 3 + 9 + 9 + 3

@@ -228,6 +228,14 @@ class MpmSolver:
     def g2p(self, stream=None):
         N.check(self.lib.ffmpm_g2p(self._h, self._stream(stream)))
 
+    def scatter(self, stream=None):
+        """Zeroed grid + binning + P2G (first half of a substep)."""
+        N.check(self.lib.ffmpm_scatter(self._h, self._stream(stream)))
+
+    def gather(self, stream=None):
+        """G2P (second half of a substep)."""
+        N.check(self.lib.ffmpm_gather(self._h, self._stream(stream)))
+
     def substep(self, n_substeps: int = 1, stream=None):
         N.check(self.lib.ffmpm_substep(self._h, int(n_substeps), self._stream(stream)))
 

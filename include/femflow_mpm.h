@@ -132,7 +132,16 @@ int ffmpm_g2p(FfMpmHandle* h, void* stream);
  * axis 0 is slowest).  With 0 planes it is ffmpm_grid_op. */
 int ffmpm_grid_op_halo(FfMpmHandle* h, const void* recv_lo, int32_t planes_lo, const void* recv_hi,
                        int32_t planes_hi, void* stream);
-/* n_substeps x (clear, [bin,] p2g, grid_op, g2p). */
+/* The two halves of a substep either side of the grid update, as ffmpm_substep issues
+ * them (slab drivers put the halo exchange in between):
+ *   ffmpm_scatter  zeroed grid + cell binning + P2G   (mls_mpm.py:54-73).  The library keeps
+ *                  two grids and an internal stream: the binning runs underneath the
+ *                  compute-bound P2G, the idle grid is cleared underneath G2P.
+ *   ffmpm_gather   G2P (mls_mpm.py:79), after joining the binning.
+ * Both are ordered on `stream` like any other call. */
+int ffmpm_scatter(FfMpmHandle* h, void* stream);
+int ffmpm_gather(FfMpmHandle* h, void* stream);
+/* n_substeps x (scatter, grid_op, gather). */
 int ffmpm_substep(FfMpmHandle* h, int32_t n_substeps, void* stream);
 
 /* Phase-level access for parity tests: device pointer of the node-major grid
