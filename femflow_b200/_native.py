@@ -11,7 +11,7 @@ FFMPM_OK = 0
 FFMPM_E_INVALID, FFMPM_E_CUDA, FFMPM_E_OOB, FFMPM_E_STATE = -1, -2, -3, -4
 FFMPM_F32, FFMPM_F64 = 0, 1
 FFMPM_NEO_HOOKEAN, FFMPM_SNOW = 0, 1
-FFMPM_P2G_AUTO, FFMPM_P2G_SCATTER, FFMPM_P2G_TILED = 0, 1, 2
+FFMPM_P2G_AUTO, FFMPM_P2G_SCATTER, FFMPM_P2G_TILED, FFMPM_P2G_FUSED = 0, 1, 2, 3
 ABI_VERSION = 1
 
 

@@ -13,6 +13,7 @@
 #include "mpm_p2g_bulk.cuh"
 #include "mpm_stream.cuh"
 #include "mpm_tiled.cuh"
+#include "mpm_g2p2g.cuh"
 
 using namespace ffmpm;
 
@@ -45,10 +46,12 @@ struct FfMpmHandle {
   void* grids[2];      // ping-pong: the idle one is cleared behind G2P on the auxiliary stream
   int grid_cur;
   bool grid_clean[2];  // known to be all-zero
-  bool clear_pending;  // a clear of grids[grid_cur ^ 1] is in flight on `aux` (ev_clear)
+  bool scatter_ahead;  // grids[grid_cur ^ 1] already holds P2G of the live state (fused G2P2G)
+  int fuse;            // FFMPM_FUSE=0 disables the fused G2P2G kernel
+  int gg_blocks_per_sm;
   bool bin_pending;    // the binning of this substep is in flight on `aux` (ev_join)
   cudaStream_t aux;    // internal stream for work that overlaps the compute-bound P2G
-  cudaEvent_t ev_fork, ev_join, ev_clear;
+  cudaEvent_t ev_fork, ev_join;
   int overlap;         // FFMPM_OVERLAP=0 disables the auxiliary stream
   BinBuffers bin;
   // state
@@ -142,12 +145,21 @@ int ffmpm_create(const FfMpmConfig* cfg, int32_t device, FfMpmHandle** out) {
   h->n_nodes = (int64_t)d.n[0] * d.n[1] * d.n[2];
   h->overlap = 1;
   if (const char* e = getenv("FFMPM_OVERLAP")) h->overlap = atoi(e) != 0;
+  // Fused G2P2G: opt-in (p2g_mode FUSED or FFMPM_FUSE=1).  Measured on B200 (profiles/r01i): the fused
+  // kernel needs 128 registers (16 warps/SM) and runs 1.61 ms against 0.78 + 0.83 ms for the two
+  // separate kernels whose binning/clear additionally hide under P2G, so it is not the default.
+  h->fuse = cfg->p2g_mode == FFMPM_P2G_FUSED ? 1 : 0;
+  if (const char* e = getenv("FFMPM_FUSE")) h->fuse = atoi(e) != 0;
+  h->gg_blocks_per_sm = 4;
+  if (const char* e = getenv("FFMPM_GG_BPS")) { int v = atoi(e); if (v > 0 && v <= 32) h->gg_blocks_per_sm = v; }
   {
     cudaError_t ce = cudaSetDevice(device);
-    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking);
+    int prio_lo = 0, prio_hi = 0;
+    if (ce == cudaSuccess) ce = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    // highest priority: its short memory-bound kernels slot in as CTAs of the compute-bound P2G retire
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithPriority(&h->aux, cudaStreamNonBlocking, prio_hi);
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
-    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->ev_clear, cudaEventDisableTiming);
     if (ce != cudaSuccess) { delete h; return set_err(FFMPM_E_CUDA, "stream/event creation: %s", cudaGetErrorString(ce)); }
   }
   h->p2g_blocks_per_sm = 5;
@@ -170,7 +182,6 @@ void ffmpm_destroy(FfMpmHandle* h) {
   if (h->aux) { cudaStreamSynchronize(h->aux); cudaStreamDestroy(h->aux); }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
-  if (h->ev_clear) cudaEventDestroy(h->ev_clear);
   delete h;
 }
 
@@ -195,7 +206,8 @@ int ffmpm_set_workspace(FfMpmHandle* h, void* workspace, int64_t bytes) {
   h->grid_cur = 0;
   h->grid = h->grids[0];
   h->grid_clean[0] = h->grid_clean[1] = false;
-  h->clear_pending = h->bin_pending = false;
+  h->bin_pending = false;
+  h->scatter_ahead = false;
   bin_carve(h->bin, h->ws + L.bin_off, h->cfg.dim, h->dev.n, lo);
   h->binned = false;
   CUDA_TRY(cudaSetDevice(h->device));
@@ -229,6 +241,8 @@ int ffmpm_bind_state(FfMpmHandle* h, const FfMpmState* cur, const FfMpmState* al
   h->n = n;
   h->binned = false;
   h->prebinned = false;
+  h->scatter_ahead = false;
+  h->grid_clean[0] = h->grid_clean[1] = false;
   return FFMPM_OK;
 }
 
@@ -239,6 +253,8 @@ int ffmpm_set_num_particles(FfMpmHandle* h, int64_t n) {
   h->n = n;
   h->binned = false;
   h->prebinned = false;
+  h->scatter_ahead = false;
+  h->grid_clean[0] = h->grid_clean[1] = false;
   return FFMPM_OK;
 }
 
@@ -301,6 +317,7 @@ template <typename T>
 static int p2g_t(FfMpmHandle* h, cudaStream_t s) {
   StateView<T> sv = view<T>(h->st[h->live]);
   int mode = h->cfg.p2g_mode;
+  if (mode == FFMPM_P2G_FUSED) mode = FFMPM_P2G_AUTO;
   if (mode == FFMPM_P2G_AUTO) mode = (h->binned && h->cfg.dim == 3) ? FFMPM_P2G_TILED : FFMPM_P2G_SCATTER;
   if (mode == FFMPM_P2G_TILED) {
     if (h->cfg.dim != 3) return set_err(FFMPM_E_INVALID, "tiled P2G is 3D only (2D uses the scatter kernel)");
@@ -420,41 +437,79 @@ int ffmpm_g2p(FfMpmHandle* h, void* stream) {
 // True when P2G walks the particles in physical order, i.e. does not consume the binning:
 // the binning can then run on the auxiliary stream underneath it.
 static bool p2g_independent_of_bin(const FfMpmHandle* h) {
-  return h->cfg.dim == 3 && h->have_alt && h->cfg.p2g_mode != FFMPM_P2G_SCATTER && h->pipeline == 1 &&
-         h->p2g_variant >= 1;
+  return h->pipeline == 1 && h->p2g_variant >= 1;
+}
+
+static bool binned_pipeline(const FfMpmHandle* h) {
+  return h->cfg.dim == 3 && h->have_alt && h->cfg.p2g_mode != FFMPM_P2G_SCATTER;
+}
+
+// Binning of the live buffer (+ a cleared idle grid for the fused G2P2G) on the auxiliary
+// stream, forked from `s` here and joined in ffmpm_gather.
+static int fork_bin(FfMpmHandle* h, cudaStream_t s, bool clear_idle) {
+  int rc;
+  cudaStream_t w = h->overlap ? h->aux : s;
+  if (h->overlap) {
+    CUDA_TRY(cudaEventRecord(h->ev_fork, s));
+    CUDA_TRY(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
+  }
+  if ((rc = bin_impl(h, (void*)w, h->pipeline == 0))) return rc;
+  if (clear_idle) {
+    CUDA_TRY(cudaMemsetAsync(h->grids[h->grid_cur ^ 1], 0, (size_t)h->n_nodes * 4 * elem_size(h->cfg), w));
+    h->grid_clean[h->grid_cur ^ 1] = true;
+  }
+  if (h->overlap) {
+    CUDA_TRY(cudaEventRecord(h->ev_join, h->aux));
+    h->bin_pending = true;
+  }
+  return FFMPM_OK;
 }
 
 int ffmpm_scatter(FfMpmHandle* h, void* stream) {
   int rc = ready(h);
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
-  // (1) a zeroed grid for this substep: the one cleared behind the previous G2P, if any
-  if (h->clear_pending) {
-    CUDA_TRY(cudaStreamWaitEvent(s, h->ev_clear, 0));
-    h->clear_pending = false;
-    h->grid_clean[h->grid_cur ^ 1] = true;
-  }
-  if (h->grid_clean[h->grid_cur ^ 1] && !h->grid_clean[h->grid_cur]) {
+  const bool binned = binned_pipeline(h) && h->n > 0;
+  const bool fuse = binned && h->fuse && h->pipeline == 1;
+  if (h->scatter_ahead) {
+    // the previous fused gather already scattered the live state into the idle grid
+    h->scatter_ahead = false;
     h->grid_cur ^= 1;
+    h->grid = h->grids[h->grid_cur];
+    return fork_bin(h, s, fuse);
+  }
+  if (!h->grid_clean[h->grid_cur] && h->grid_clean[h->grid_cur ^ 1]) {
+    h->grid_cur ^= 1;   // the grid that was cleared underneath the previous P2G
     h->grid = h->grids[h->grid_cur];
   }
   if (!h->grid_clean[h->grid_cur] && (rc = ffmpm_clear_grid(h, stream))) return rc;
-  h->grid_clean[h->grid_cur] = false;   // about to be written
-  const bool binned_pipeline = h->cfg.dim == 3 && h->have_alt && h->cfg.p2g_mode != FFMPM_P2G_SCATTER;
-  // (2) binning: underneath P2G on the auxiliary stream when P2G does not need it
-  if (binned_pipeline) {
-    if (h->overlap && p2g_independent_of_bin(h) && h->n > 0) {
-      CUDA_TRY(cudaEventRecord(h->ev_fork, s));
-      CUDA_TRY(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
-      if ((rc = bin_impl(h, (void*)h->aux, false))) return rc;
-      CUDA_TRY(cudaEventRecord(h->ev_join, h->aux));
-      h->bin_pending = true;
-    } else if ((rc = bin_impl(h, stream, h->pipeline == 0))) {
-      return rc;
+  if (binned) {
+    if (p2g_independent_of_bin(h)) {
+      // binning and the clear of the idle grid (next substep's, or the fused kernel's target): underneath P2G
+      if ((rc = fork_bin(h, s, true))) return rc;
+    } else {
+      if ((rc = bin_impl(h, stream, h->pipeline == 0))) return rc;
+      if (fuse) {
+        CUDA_TRY(cudaMemsetAsync(h->grids[h->grid_cur ^ 1], 0, (size_t)h->n_nodes * 4 * elem_size(h->cfg), s));
+        h->grid_clean[h->grid_cur ^ 1] = true;
+      }
     }
   }
-  // (3) P2G
   return ffmpm_p2g(h, stream);
+}
+
+template <typename T>
+static int g2p2g_t(FfMpmHandle* h, cudaStream_t s) {
+  StateView<T> sv = view<T>(h->st[h->live]), dst = view<T>(h->st[h->live ^ 1]);
+  bin_clear_histogram(h->bin, s);
+  int nl = g2p2g_tiled<T>(h->dev, sv, dst, h->bin, (const T*)h->grid, (T*)h->grids[h->grid_cur ^ 1], h->err, h->sm_count,
+                          h->gg_blocks_per_sm, s);
+  h->live ^= 1;
+  h->binned = false;
+  h->prebinned = true;
+  h->grid_clean[h->grid_cur ^ 1] = false;
+  h->scatter_ahead = true;
+  return check_launch(h, nl);
 }
 
 int ffmpm_gather(FfMpmHandle* h, void* stream) {
@@ -465,15 +520,10 @@ int ffmpm_gather(FfMpmHandle* h, void* stream) {
     CUDA_TRY(cudaStreamWaitEvent(s, h->ev_join, 0));
     h->bin_pending = false;
   }
-  // clear the idle grid for the next substep while G2P reads the current one
-  const bool ahead = h->overlap && h->cfg.dim == 3 && h->have_alt && !h->grid_clean[h->grid_cur ^ 1] && !h->clear_pending;
-  if (ahead) {
-    CUDA_TRY(cudaEventRecord(h->ev_fork, s));
-    CUDA_TRY(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
-    CUDA_TRY(cudaMemsetAsync(h->grids[h->grid_cur ^ 1], 0, (size_t)h->n_nodes * 4 * elem_size(h->cfg), h->aux));
-    CUDA_TRY(cudaEventRecord(h->ev_clear, h->aux));
-    h->clear_pending = true;
-  }
+  const bool can_fuse = h->fuse && binned_pipeline(h) && h->pipeline == 1 && h->n > 0 && h->binned && h->have_perm &&
+                        h->grid_clean[h->grid_cur ^ 1] && !(h->cfg.dim == 3 && h->cfg.model == FFMPM_SNOW);
+  if (can_fuse)
+    return h->cfg.dtype == FFMPM_F64 ? g2p2g_t<double>(h, s) : g2p2g_t<float>(h, s);
   return ffmpm_g2p(h, stream);
 }
 
@@ -484,12 +534,6 @@ int ffmpm_substep(FfMpmHandle* h, int32_t n_substeps, void* stream) {
     if ((rc = ffmpm_scatter(h, stream))) return rc;
     if ((rc = ffmpm_grid_op(h, stream))) return rc;
     if ((rc = ffmpm_gather(h, stream))) return rc;
-  }
-  // leave no work in flight on the internal stream when control returns to the caller's stream
-  if (h->clear_pending) {
-    CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, h->ev_clear, 0));
-    h->clear_pending = false;
-    h->grid_clean[h->grid_cur ^ 1] = true;
   }
   return FFMPM_OK;
 }

@@ -63,7 +63,7 @@ __device__ __forceinline__ const float* p2g_plane_src(const StateView<float>& s,
 
 template <int WARPS, int NBUF>
 __global__ void __launch_bounds__(WARPS * 32)
-p2g_bulk3_kernel(DevCfg cfg, StateView<float> s, long long n, float* __restrict__ grid, ErrRec* err) {
+p2g_bulk3_kernel(DevCfg cfg, StateView<float> s, long long n, float* __restrict__ grid, ErrRec* err, int wpw) {
   using T = float;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   P2GBulkWarp<NBUF>* warps = reinterpret_cast<P2GBulkWarp<NBUF>*>(smem_raw);
@@ -75,8 +75,12 @@ p2g_bulk3_kernel(DevCfg cfg, StateView<float> s, long long n, float* __restrict_
   const bool has_mat = s.mass != nullptr && s.mu0 != nullptr && s.lam0 != nullptr;
   const int n_planes = has_mat ? P2G_NPLANES : P2G_MASS;
   const int n_windows = (int)((n + P2G_WINDOW - 1) / P2G_WINDOW);
-  const int total_warps = gridDim.x * WARPS;
-  const int first = blockIdx.x * WARPS + warp;
+  // wpw > 0: every warp owns `wpw` consecutive windows and the CTA retires after them (a finite
+  // grid lets the block scheduler interleave CTAs of kernels running on other streams);
+  // wpw == 0: persistent, windows strided over the whole grid.
+  const int total_warps = wpw > 0 ? 1 : gridDim.x * WARPS;
+  const int first = wpw > 0 ? (blockIdx.x * WARPS + warp) * wpw : blockIdx.x * WARPS + warp;
+  const int last_excl = wpw > 0 ? min(n_windows, first + wpw) : n_windows;
 
   if (lane == 0) {
     for (int b = 0; b < NBUF; ++b) mbar_init(&W.bar[b], 1);
@@ -95,14 +99,14 @@ p2g_bulk3_kernel(DevCfg cfg, StateView<float> s, long long n, float* __restrict_
     }
   };
 
-  if (first < n_windows) issue(first, 0);
+  if (first < last_excl) issue(first, 0);
   int it = 0;
-  for (int win = first; win < n_windows; win += total_warps, ++it) {
+  for (int win = first; win < last_excl; win += total_warps, ++it) {
     const int buf = NBUF == 2 ? (it & 1) : 0;
     const unsigned parity = NBUF == 2 ? ((it >> 1) & 1) : (it & 1);
     const int w0 = win * P2G_WINDOW;
     const int cnt = (int)min((long long)P2G_WINDOW, n - w0);
-    if (NBUF == 2 && win + total_warps < n_windows) issue(win + total_warps, buf ^ 1);
+    if (NBUF == 2 && win + total_warps < last_excl) issue(win + total_warps, buf ^ 1);
     mbar_wait(&W.bar[buf], parity);
     // ---- phase 1: lane per particle, state from the prefetched slab ----
     int node[2];
@@ -117,7 +121,7 @@ p2g_bulk3_kernel(DevCfg cfg, StateView<float> s, long long n, float* __restrict_
     }
     __syncwarp();
     // single buffer: the raw slab is free again -> prefetch the next window behind phase 2
-    if (NBUF == 1 && win + total_warps < n_windows) issue(win + total_warps, 0);
+    if (NBUF == 1 && win + total_warps < last_excl) issue(win + total_warps, 0);
     p2g_runs_phase2<T>(S, node, cnt, lane, ny, nz, grid);
     __syncwarp();   // the payload slab is rewritten by the next window
   }
@@ -134,11 +138,17 @@ static bool p2g_bulk_launch(const DevCfg& cfg, const StateView<float>& s, long l
     configured = true;
   }
   long long windows = (n + P2G_WINDOW - 1) / P2G_WINDOW;
-  long long want = (windows + WARPS - 1) / WARPS;
-  long long cap = (long long)sm_count * blocks_per_sm;
-  int blocks = (int)(want < cap ? want : cap);
+  static int wpw = [] { const char* e = getenv("FFMPM_P2G_WPW"); return e ? atoi(e) : 16; }();
+  int blocks;
+  if (wpw > 0) {
+    blocks = (int)((windows + (long long)WARPS * wpw - 1) / ((long long)WARPS * wpw));
+  } else {
+    long long want = (windows + WARPS - 1) / WARPS;
+    long long cap = (long long)sm_count * blocks_per_sm;
+    blocks = (int)(want < cap ? want : cap);
+  }
   if (blocks < 1) blocks = 1;
-  p2g_bulk3_kernel<WARPS, NBUF><<<blocks, WARPS * 32, smem, st>>>(cfg, s, n, grid, err);
+  p2g_bulk3_kernel<WARPS, NBUF><<<blocks, WARPS * 32, smem, st>>>(cfg, s, n, grid, err, wpw);
   return true;
 }
 

@@ -18,7 +18,8 @@ import torch
 from . import _native as N
 
 _MODEL = {"neo_hookean": N.FFMPM_NEO_HOOKEAN, "snow": N.FFMPM_SNOW}
-_P2G = {"auto": N.FFMPM_P2G_AUTO, "scatter": N.FFMPM_P2G_SCATTER, "tiled": N.FFMPM_P2G_TILED}
+_P2G = {"auto": N.FFMPM_P2G_AUTO, "scatter": N.FFMPM_P2G_SCATTER, "tiled": N.FFMPM_P2G_TILED,
+        "fused": N.FFMPM_P2G_FUSED}
 
 
 def _as_tensor(a, dtype, device):

@@ -57,7 +57,8 @@ enum { FFMPM_NEO_HOOKEAN = 0, FFMPM_SNOW = 1 };   /* `model` of three_d/p2g.py:2
 enum {
   FFMPM_P2G_AUTO = 0,      /* tiled when the state is binned, else scatter */
   FFMPM_P2G_SCATTER = 1,   /* one thread per particle, one vector red per node */
-  FFMPM_P2G_TILED = 2      /* shared-memory tile per CTA (needs ffmpm_bin)  */
+  FFMPM_P2G_TILED = 2,     /* binned, warp-autonomous cell runs (needs ffmpm_bin) */
+  FFMPM_P2G_FUSED = 3      /* as AUTO, and ffmpm_gather runs G2P(k) + P2G(k+1) as ONE kernel */
 };
 
 /* Scalars of solve_mls_mpm_3d's argument list (mls_mpm.py:40-53) plus the slab

@@ -134,3 +134,32 @@ def time_sample(scene, budget_s: float = 15.0, threads=None, substeps=None):
                       f"{t2:.1f} s; C port of the reference loops with OpenMP over particles "
                       f"(the reference's numba path is serial: 1 core)",
             "sample_particles": m2, "seconds": t2}
+
+
+class SampleRunner:
+    """Repeated substeps of the C port on a fixed sample of a scene (bench.py --impl reference)."""
+
+    def __init__(self, scene, m: int, threads=None):
+        self.L = lib()
+        self.cores = threads or self.L.oracle_max_threads()
+        self.L.oracle_set_threads(self.cores)
+        self.scene, self.m = scene, int(min(m, scene.n))
+        d, res = scene.dim, scene.res
+        G = res + 1
+        self.gv = np.empty(G ** d * d)
+        self.gm = np.empty(G ** d)
+        m = self.m
+        self.x = _c(scene.x[:m]); self.v = _c(scene.v[:m]); self.F = _c(scene.F[:m]); self.C = _c(scene.C[:m])
+        self.mass = np.full(m, scene.mass); self.mu = np.full(m, scene.mu_0); self.lam = np.full(m, scene.lambda_0)
+        self.Jp = np.ones(m)
+
+    def step(self) -> float:
+        sc, res = self.scene, self.scene.res
+        t0 = time.perf_counter()
+        if sc.dim == 3:
+            self.L.oracle_substep_3d(self.m, res, float(res), sc.hardening, 1.0 / res, sc.dt, sc.volume, sc.gravity,
+                                     self.x, self.mass, self.mu, self.lam, self.v, self.F, self.C, self.gv, self.gm)
+        else:
+            self.L.oracle_substep_2d(self.m, res, float(res), sc.hardening, sc.mu_0, sc.lambda_0, sc.mass, 1.0 / res,
+                                     sc.dt, sc.volume, sc.gravity, self.x, self.v, self.F, self.C, self.Jp, self.gv, self.gm)
+        return time.perf_counter() - t0
