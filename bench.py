@@ -354,7 +354,8 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 storage, f64 constitutive (polar/stress)", "data": "synthetic",
+        "dtype": "f32 (cell indexing in f64; stress in f32 perturbation form, f64 fallback at large strain)",
+        "data": "synthetic",
         "config": {"workload": scene.name, "particles_per_gpu": n, "particles_total": n_total,
                    "grid": f"{scene.res}^{scene.dim}", "dt": scene.dt, "p2g_mode": args.p2g_mode,
                    "l2": ("inputs larger than L2 (no flush)" if n * (112 if scene.dim == 3 else 52) > 2 * 126e6
