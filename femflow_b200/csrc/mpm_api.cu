@@ -168,7 +168,7 @@ int ffmpm_create(const FfMpmConfig* cfg, int32_t device, FfMpmHandle** out) {
   h->g2p_bulk = false;   // measured slower than direct stores on B200 (profiles/r01f): opt-in
   if (const char* e = getenv("FFMPM_PIPELINE")) h->pipeline = (strcmp(e, "stream") == 0) ? 0 : 1;
   if (const char* e = getenv("FFMPM_G2P_BULK")) h->g2p_bulk = atoi(e) != 0;
-  h->p2g_variant = 3;   // TMA-prefetched physical-order P2G when eligible (measured best: profiles/r01g)
+  h->p2g_variant = 5;   // physical-order P2G with cp.async-prefetched state when eligible (profiles/r01j)
   if (const char* e = getenv("FFMPM_P2G_VARIANT")) h->p2g_variant = atoi(e);
   if (const char* e = getenv("FFMPM_P2G_BPS")) { int v = atoi(e); if (v > 0 && v <= 32) h->p2g_blocks_per_sm = v; }
   if (const char* e = getenv("FFMPM_G2P_BPS")) { int v = atoi(e); if (v > 0 && v <= 32) h->g2p_blocks_per_sm = v; }
@@ -323,13 +323,16 @@ static int p2g_t(FfMpmHandle* h, cudaStream_t s) {
     if (h->cfg.dim != 3) return set_err(FFMPM_E_INVALID, "tiled P2G is 3D only (2D uses the scatter kernel)");
     if (!h->binned) return set_err(FFMPM_E_STATE, "tiled P2G needs ffmpm_bin first");
     // P2G variant: 0 = through the permutation, 1 = physical order (kept sorted by G2P),
-    // 2 / 3 = physical order with TMA-prefetched state, double / single buffered (fp32 only)
+    // 2 / 3 = physical order with TMA-prefetched state, double / single buffered (fp32 only),
+    // 4 / 5 = the same prefetch through per-lane 16-byte cp.async (3 / 4 warps per CTA)
     if constexpr (sizeof(T) == 4) {
       if (h->p2g_variant >= 2 && p2g_bulk_eligible(h->dev, sv)) {
         bool ok;
         const int bps = h->p2g_blocks_per_sm;
-        if (h->p2g_variant == 2) ok = p2g_bulk_launch<2, 2>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
-        else ok = p2g_bulk_launch<3, 1>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
+        if (h->p2g_variant == 2) ok = p2g_bulk_launch<2, 2, 0>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
+        else if (h->p2g_variant == 4) ok = p2g_bulk_launch<3, 1, 1>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
+        else if (h->p2g_variant == 5) ok = p2g_bulk_launch<4, 1, 1>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
+        else ok = p2g_bulk_launch<3, 1, 0>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
         if (!ok) return set_err(FFMPM_E_CUDA, "could not configure the bulk P2G kernel");
         return check_launch(h, 1);
       }

@@ -50,20 +50,36 @@ __device__ __forceinline__ void bulk_load_s(void* sdst, const void* gsrc, unsign
                : "memory");
 }
 
-__device__ __forceinline__ const float* p2g_plane_src(const StateView<float>& s, int k) {
+// Base pointer of every state plane, resolved once on the host and passed as a kernel
+// parameter (constant bank): the per-window issue loop is then one uniform add + one
+// UBLKCP per plane instead of a pointer-selection sequence (17 % of the kernel's
+// instructions in profiles/r01_final before this).
+struct P2GPlanes {
+  const float* p[P2G_NPLANES];
+  int n;
+};
+
+inline P2GPlanes p2g_planes_of(const StateView<float>& s) {
+  P2GPlanes P;
   const long long st = s.stride;
-  if (k < P2G_V) return s.x + k * st;
-  if (k < P2G_C) return s.v + (k - P2G_V) * st;
-  if (k < P2G_F) return s.C + (k - P2G_C) * st;
-  if (k < P2G_MASS) return s.F + (k - P2G_F) * st;
-  if (k == P2G_MASS) return s.mass;
-  if (k == P2G_MU) return s.mu0;
-  return s.lam0;
+  for (int k = 0; k < 3; ++k) { P.p[P2G_X + k] = s.x + k * st; P.p[P2G_V + k] = s.v + k * st; }
+  for (int k = 0; k < 9; ++k) { P.p[P2G_C + k] = s.C + k * st; P.p[P2G_F + k] = s.F + k * st; }
+  P.p[P2G_MASS] = s.mass; P.p[P2G_MU] = s.mu0; P.p[P2G_LAM] = s.lam0;
+  P.n = (s.mass && s.mu0 && s.lam0) ? P2G_NPLANES : P2G_MASS;
+  return P;
 }
 
-template <int WARPS, int NBUF>
-__global__ void __launch_bounds__(WARPS * 32)
-p2g_bulk3_kernel(DevCfg cfg, StateView<float> s, long long n, float* __restrict__ grid, ErrRec* err, int wpw) {
+__device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(sdst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+// LDGSTS: 0 = bulk copies by the TMA engine (cp.async.bulk + mbarrier, one elected lane);
+//         1 = per-lane 16-byte cp.async (LDGSTS): two planes per warp instruction, 14
+//             instructions per window -- fewer issue slots than 27 elected UBLKCP sequences.
+template <int WARPS, int NBUF, int LDGSTS>
+__global__ void __launch_bounds__(WARPS * 32, 16 / WARPS)   // <= 128 registers: 16 warps per SM
+p2g_bulk3_kernel(DevCfg cfg, P2GPlanes planes, long long n, float* __restrict__ grid, ErrRec* err, int wpw) {
   using T = float;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   P2GBulkWarp<NBUF>* warps = reinterpret_cast<P2GBulkWarp<NBUF>*>(smem_raw);
@@ -72,8 +88,8 @@ p2g_bulk3_kernel(DevCfg cfg, StateView<float> s, long long n, float* __restrict_
   P2GWarpSlab<T>& S = W.slab;
   const T dx = (T)cfg.dx;
   const int ny = cfg.n[1], nz = cfg.n[2];
-  const bool has_mat = s.mass != nullptr && s.mu0 != nullptr && s.lam0 != nullptr;
-  const int n_planes = has_mat ? P2G_NPLANES : P2G_MASS;
+  const int n_planes = planes.n;
+  const bool has_mat = n_planes == P2G_NPLANES;
   const int n_windows = (int)((n + P2G_WINDOW - 1) / P2G_WINDOW);
   // wpw > 0: every warp owns `wpw` consecutive windows and the CTA retires after them (a finite
   // grid lets the block scheduler interleave CTAs of kernels running on other streams);
@@ -90,12 +106,26 @@ p2g_bulk3_kernel(DevCfg cfg, StateView<float> s, long long n, float* __restrict_
   __syncwarp();
 
   auto issue = [&](int win, int buf) {
+    if (LDGSTS) {
+      const long long w0 = (long long)win * P2G_WINDOW + (lane & 15) * 4;
+      const int hi = lane >> 4;
+#pragma unroll
+      for (int j = 0; j < (P2G_NPLANES + 1) / 2; ++j) {
+        const int k0 = 2 * j, k1 = 2 * j + 1;
+        const float* src = (hi && k1 < P2G_NPLANES) ? planes.p[k1 < P2G_NPLANES ? k1 : k0] : planes.p[k0];
+        const int k = hi ? k1 : k0;
+        if (k < n_planes) cp_async16(&W.raw[buf][k][(lane & 15) * 4], src + w0);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      return;
+    }
     // one lane posts the whole window: n_planes x 256 B
     if (lane == 0) {
       mbar_expect_tx(&W.bar[buf], (unsigned)n_planes * P2G_WINDOW * 4u);
       const long long w0 = (long long)win * P2G_WINDOW;
-      for (int k = 0; k < n_planes; ++k)
-        bulk_load_s(&W.raw[buf][k][0], p2g_plane_src(s, k) + w0, P2G_WINDOW * 4u, &W.bar[buf]);
+#pragma unroll
+      for (int k = 0; k < P2G_NPLANES; ++k)
+        if (k < n_planes) bulk_load_s(&W.raw[buf][k][0], planes.p[k] + w0, P2G_WINDOW * 4u, &W.bar[buf]);
     }
   };
 
@@ -107,7 +137,13 @@ p2g_bulk3_kernel(DevCfg cfg, StateView<float> s, long long n, float* __restrict_
     const int w0 = win * P2G_WINDOW;
     const int cnt = (int)min((long long)P2G_WINDOW, n - w0);
     if (NBUF == 2 && win + total_warps < last_excl) issue(win + total_warps, buf ^ 1);
-    mbar_wait(&W.bar[buf], parity);
+    if (LDGSTS) {
+      if (NBUF == 2 && win + total_warps < last_excl) asm volatile("cp.async.wait_group 1;" ::: "memory");
+      else asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+    } else {
+      mbar_wait(&W.bar[buf], parity);
+    }
     // ---- phase 1: lane per particle, state from the prefetched slab ----
     int node[2];
 #pragma unroll
@@ -127,13 +163,13 @@ p2g_bulk3_kernel(DevCfg cfg, StateView<float> s, long long n, float* __restrict_
   }
 }
 
-template <int WARPS, int NBUF>
+template <int WARPS, int NBUF, int LDGSTS>
 static bool p2g_bulk_launch(const DevCfg& cfg, const StateView<float>& s, long long n, float* grid, ErrRec* err,
                             int sm_count, int blocks_per_sm, cudaStream_t st) {
   const size_t smem = sizeof(P2GBulkWarp<NBUF>) * WARPS;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(p2g_bulk3_kernel<WARPS, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(p2g_bulk3_kernel<WARPS, NBUF, LDGSTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return false;
     configured = true;
   }
@@ -148,7 +184,7 @@ static bool p2g_bulk_launch(const DevCfg& cfg, const StateView<float>& s, long l
     blocks = (int)(want < cap ? want : cap);
   }
   if (blocks < 1) blocks = 1;
-  p2g_bulk3_kernel<WARPS, NBUF><<<blocks, WARPS * 32, smem, st>>>(cfg, s, n, grid, err, wpw);
+  p2g_bulk3_kernel<WARPS, NBUF, LDGSTS><<<blocks, WARPS * 32, smem, st>>>(cfg, p2g_planes_of(s), n, grid, err, wpw);
   return true;
 }
 
