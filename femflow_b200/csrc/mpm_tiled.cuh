@@ -56,7 +56,18 @@ __device__ __forceinline__ void bulk_store_g(void* gdst, const void* ssrc, unsig
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(sa), "r"(bytes) : "memory");
 }
 
-template <typename T, bool BULK, int MIN_BLOCKS>
+constexpr int G2P_PRE_PLANES = 17;   // x3 F9 mass mu0 lam0 id Jp
+
+__device__ __forceinline__ void cp_async4(void* sdst, const void* gsrc) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(sdst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+// PRE (fp32): every thread prefetches the 17 input scalars of ITS particle of the next round
+// into shared memory with 4-byte cp.async (the gather through `perm` rules out bulk copies)
+// while the current round computes; the permutation entry itself is fetched two rounds
+// ahead.  Each thread only ever reads what it copied itself, so no barrier is involved.
+template <typename T, bool BULK, int MIN_BLOCKS, bool PRE = false>
 __global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_tiled3_kernel(DevCfg cfg, StateView<T> src, StateView<T> dst,
                                                                  BinBuffers B, const T* __restrict__ grid, ErrRec* err) {
   static_assert(!BULK || sizeof(T) == 4, "bulk staging is for the fp32 build");
@@ -65,6 +76,9 @@ __global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_tiled3_kernel(Dev
   __shared__ int s_work;
   // plane-major staging of one round's results, double buffered (BULK only; 1 element otherwise)
   __shared__ __align__(128) float stage[BULK ? 2 : 1][BULK ? G2P_PLANES : 1][BULK ? G2P_THREADS : 1];
+  static_assert(!PRE || sizeof(T) == 4, "the cp.async prefetch is for the fp32 build");
+  __shared__ __align__(16) float pre[PRE ? 2 : 1][PRE ? G2P_PRE_PLANES : 1][PRE ? G2P_THREADS : 1];
+  int pre_buf = 0;
   const int n_active = B.counters[0];
   const long long ss = src.stride, ds = dst.stride;
   int round_parity = 0;
@@ -104,26 +118,81 @@ __global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_tiled3_kernel(Dev
       tile[nd] = g;
     }
     __syncthreads();
+    const int r_first = (start / G2P_THREADS) * G2P_THREADS;
+    // PRE: post this thread's cp.async for the particle at permutation entry q into pre[buf]
+    auto prefetch = [&](int q, int buf) {
+      if constexpr (PRE) {
+        if (q >= 0) {
+          const int tid = threadIdx.x;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) cp_async4(&pre[buf][c][tid], src.x + c * ss + q);
+#pragma unroll
+          for (int c = 0; c < 9; ++c) cp_async4(&pre[buf][3 + c][tid], src.F + c * ss + q);
+          if (src.mass) cp_async4(&pre[buf][12][tid], src.mass + q);
+          if (src.mu0) cp_async4(&pre[buf][13][tid], src.mu0 + q);
+          if (src.lam0) cp_async4(&pre[buf][14][tid], src.lam0 + q);
+          if (src.id) cp_async4(&pre[buf][15][tid], src.id + q);
+          if (src.Jp) cp_async4(&pre[buf][16][tid], src.Jp + q);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+    };
+    auto perm_at = [&](int rb) -> int {
+      const int sl = rb + (int)threadIdx.x;
+      return (sl >= start && sl < end) ? B.perm[sl] : -1;
+    };
+    int q_cur = -1, q_nxt = -1;
+    if constexpr (PRE) {
+      q_cur = perm_at(r_first);
+      q_nxt = r_first + G2P_THREADS < end ? perm_at(r_first + G2P_THREADS) : -1;
+      prefetch(q_cur, pre_buf);
+    }
     // rounds are aligned to multiples of 128 slots so that a round's plane segment is 16-byte aligned
-    for (int rbase = (start / G2P_THREADS) * G2P_THREADS; rbase < end; rbase += G2P_THREADS) {
+    for (int rbase = r_first; rbase < end; rbase += G2P_THREADS) {
       const int slot = rbase + threadIdx.x;
       const bool mine = slot >= start && slot < end;
       int next_key = -1;
       T o[24];
       T cm = 0, cmu = 0, cl = 0, cjp = 0;
       int cid = 0;
+      int q_nn = -1;
+      if constexpr (PRE) {
+        const bool more = rbase + G2P_THREADS < end;
+        if (more) {
+          prefetch(q_nxt, pre_buf ^ 1);                                   // next round's inputs
+          if (rbase + 2 * G2P_THREADS < end) q_nn = perm_at(rbase + 2 * G2P_THREADS);   // and the entry after that
+          asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+      }
       if (mine) {
-        const long long p = B.perm[slot];
-        // carried planes first: their latency hides behind the gather
-        if (src.mass) cm = src.mass[p];
-        if (src.mu0) cmu = src.mu0[p];
-        if (src.lam0) cl = src.lam0[p];
-        if (src.id) cid = src.id[p];
-        if (src.Jp) cjp = src.Jp[p];
-        const T x0 = src.x[p], x1 = src.x[ss + p], x2 = src.x[2 * ss + p];
-        const T f00 = src.F[0 * ss + p], f01 = src.F[1 * ss + p], f02 = src.F[2 * ss + p];
-        const T f10 = src.F[3 * ss + p], f11 = src.F[4 * ss + p], f12 = src.F[5 * ss + p];
-        const T f20 = src.F[6 * ss + p], f21 = src.F[7 * ss + p], f22 = src.F[8 * ss + p];
+        T x0, x1, x2, f00, f01, f02, f10, f11, f12, f20, f21, f22;
+        if constexpr (PRE) {
+          const int tid = threadIdx.x;
+          const float(*pb)[G2P_THREADS] = pre[pre_buf];
+          x0 = pb[0][tid]; x1 = pb[1][tid]; x2 = pb[2][tid];
+          f00 = pb[3][tid]; f01 = pb[4][tid]; f02 = pb[5][tid];
+          f10 = pb[6][tid]; f11 = pb[7][tid]; f12 = pb[8][tid];
+          f20 = pb[9][tid]; f21 = pb[10][tid]; f22 = pb[11][tid];
+          if (src.mass) cm = pb[12][tid];
+          if (src.mu0) cmu = pb[13][tid];
+          if (src.lam0) cl = pb[14][tid];
+          if (src.id) cid = __float_as_int(pb[15][tid]);
+          if (src.Jp) cjp = pb[16][tid];
+        } else {
+          const long long p = B.perm[slot];
+          // carried planes first: their latency hides behind the gather
+          if (src.mass) cm = src.mass[p];
+          if (src.mu0) cmu = src.mu0[p];
+          if (src.lam0) cl = src.lam0[p];
+          if (src.id) cid = src.id[p];
+          if (src.Jp) cjp = src.Jp[p];
+          x0 = src.x[p]; x1 = src.x[ss + p]; x2 = src.x[2 * ss + p];
+          f00 = src.F[0 * ss + p]; f01 = src.F[1 * ss + p]; f02 = src.F[2 * ss + p];
+          f10 = src.F[3 * ss + p]; f11 = src.F[4 * ss + p]; f12 = src.F[5 * ss + p];
+          f20 = src.F[6 * ss + p]; f21 = src.F[7 * ss + p]; f22 = src.F[8 * ss + p];
+        }
         int gx, gy, gz;
         T fx, fy, fz;
         base_fx(x0, cfg.inv_dx, gx, fx);
@@ -199,6 +268,10 @@ __global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_tiled3_kernel(Dev
       }
       // next substep's histogram + within-cell rank (same scheme as bin_count_kernel)
       bin_rank_warp(B, next_key, slot);
+      if constexpr (PRE) {
+        q_cur = q_nxt; q_nxt = q_nn;
+        pre_buf ^= 1;
+      }
     }
   }
   if constexpr (BULK) {
@@ -216,6 +289,15 @@ int g2p_tiled(const DevCfg& cfg, const StateView<T>& src, const StateView<T>& ds
   if constexpr (sizeof(T) == 4) {
     if (bulk) {
       g2p_tiled3_kernel<T, true, 4><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
+      return 1;
+    }
+    static int prefetch = [] { const char* e = getenv("FFMPM_G2P_PRE"); return e ? atoi(e) : 1; }();
+    if (prefetch == 1) {
+      g2p_tiled3_kernel<T, false, 8, true><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
+      return 1;
+    }
+    if (prefetch == 2) {
+      g2p_tiled3_kernel<T, false, 6, true><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
       return 1;
     }
     if (minb >= 8) {
