@@ -50,7 +50,6 @@ PROTOTYPES = {
     "ffmpm_set_num_particles": (C.c_int, [H, C.c_int64]),
     "ffmpm_clear_grid": (C.c_int, [H, C.c_void_p]),
     "ffmpm_bin": (C.c_int, [H, C.c_void_p]),
-    "ffmpm_bin_offsets": (C.c_int, [H, C.c_void_p]),
     "ffmpm_p2g": (C.c_int, [H, C.c_void_p]),
     "ffmpm_grid_op": (C.c_int, [H, C.c_void_p]),
     "ffmpm_g2p": (C.c_int, [H, C.c_void_p]),

@@ -11,7 +11,6 @@
 #include "mpm_common.cuh"
 #include "mpm_direct.cuh"
 #include "mpm_p2g_bulk.cuh"
-#include "mpm_stream.cuh"
 #include "mpm_tiled.cuh"
 #include "mpm_g2p2g.cuh"
 
@@ -63,10 +62,7 @@ struct FfMpmHandle {
   bool binned;        // bin buffers describe the live buffer
   int64_t launches;
   bool prebinned;     // keys/rank/histogram of the live buffer were emitted by the last reordering G2P
-  bool have_perm;     // perm / active tiles are valid (full ffmpm_bin, not the light scan of the stream pipeline)
   int p2g_variant;    // see p2g_t (FFMPM_P2G_VARIANT)
-  bool g2p_bulk;      // tiled G2P leaves through cp.async.bulk stores (FFMPM_G2P_BULK=1 enables)
-  int pipeline;       // 1 = tiled (perm + smem tiles, default), 0 = stream (physical order); FFMPM_PIPELINE
   int p2g_blocks_per_sm, g2p_blocks_per_sm;   // persistent-grid sizing (tunable: FFMPM_P2G_BPS / FFMPM_G2P_BPS)
 };
 
@@ -164,10 +160,6 @@ int ffmpm_create(const FfMpmConfig* cfg, int32_t device, FfMpmHandle** out) {
   }
   h->p2g_blocks_per_sm = 5;
   h->g2p_blocks_per_sm = 8;
-  h->pipeline = 1;
-  h->g2p_bulk = false;   // measured slower than direct stores on B200 (profiles/r01f): opt-in
-  if (const char* e = getenv("FFMPM_PIPELINE")) h->pipeline = (strcmp(e, "stream") == 0) ? 0 : 1;
-  if (const char* e = getenv("FFMPM_G2P_BULK")) h->g2p_bulk = atoi(e) != 0;
   h->p2g_variant = 5;   // physical-order P2G with cp.async-prefetched state when eligible (profiles/r01j)
   if (const char* e = getenv("FFMPM_P2G_VARIANT")) h->p2g_variant = atoi(e);
   if (const char* e = getenv("FFMPM_P2G_BPS")) { int v = atoi(e); if (v > 0 && v <= 32) h->p2g_blocks_per_sm = v; }
@@ -291,27 +283,20 @@ int ffmpm_clear_grid(FfMpmHandle* h, void* stream) {
 }
 
 template <typename T>
-static int bin_t(FfMpmHandle* h, cudaStream_t s, bool light) {
+static int bin_t(FfMpmHandle* h, cudaStream_t s) {
   if (h->n > h->capacity) return set_err(FFMPM_E_STATE, "workspace too small for this particle count");
-  int nl = bin_particles<T>(h->dev, view<T>(h->st[h->live]), h->n, h->bin, h->err, h->prebinned, light, s);
+  int nl = bin_particles<T>(h->dev, view<T>(h->st[h->live]), h->n, h->bin, h->err, h->prebinned, s);
   h->binned = true;
-  h->have_perm = !light;
   h->prebinned = false;
   return check_launch(h, nl);
 }
 
-static int bin_impl(FfMpmHandle* h, void* stream, bool light) {
+int ffmpm_bin(FfMpmHandle* h, void* stream) {
   int rc = ready(h);
   if (rc) return rc;
-  if (h->n == 0) { h->binned = true; h->have_perm = true; return FFMPM_OK; }
-  return h->cfg.dtype == FFMPM_F64 ? bin_t<double>(h, (cudaStream_t)stream, light)
-                                   : bin_t<float>(h, (cudaStream_t)stream, light);
+  if (h->n == 0) { h->binned = true; return FFMPM_OK; }
+  return h->cfg.dtype == FFMPM_F64 ? bin_t<double>(h, (cudaStream_t)stream) : bin_t<float>(h, (cudaStream_t)stream);
 }
-
-// Public entry point: the complete sort (keys, ranks, cell offsets, permutation, active tiles).
-int ffmpm_bin(FfMpmHandle* h, void* stream) { return bin_impl(h, stream, false); }
-// Keys, ranks and cell offsets only -- all the default (stream) pipeline consumes.
-int ffmpm_bin_offsets(FfMpmHandle* h, void* stream) { return bin_impl(h, stream, h && h->pipeline == 0); }
 
 template <typename T>
 static int p2g_t(FfMpmHandle* h, cudaStream_t s) {
@@ -323,22 +308,19 @@ static int p2g_t(FfMpmHandle* h, cudaStream_t s) {
     if (h->cfg.dim != 3) return set_err(FFMPM_E_INVALID, "tiled P2G is 3D only (2D uses the scatter kernel)");
     if (!h->binned) return set_err(FFMPM_E_STATE, "tiled P2G needs ffmpm_bin first");
     // P2G variant: 0 = through the permutation, 1 = physical order (kept sorted by G2P),
-    // 2 / 3 = physical order with TMA-prefetched state, double / single buffered (fp32 only),
-    // 4 / 5 = the same prefetch through per-lane 16-byte cp.async (3 / 4 warps per CTA)
+    // 3 = physical order, state prefetched by TMA bulk copies (fp32), 5 = by per-lane 16-byte cp.async
+    // (fp32, default: fewer issue slots than 27 elected UBLKCP sequences per window)
     if constexpr (sizeof(T) == 4) {
-      if (h->p2g_variant >= 2 && p2g_bulk_eligible(h->dev, sv)) {
+      if (h->p2g_variant >= 3 && p2g_bulk_eligible(h->dev, sv)) {
         bool ok;
         const int bps = h->p2g_blocks_per_sm;
-        if (h->p2g_variant == 2) ok = p2g_bulk_launch<2, 2, 0>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
-        else if (h->p2g_variant == 4) ok = p2g_bulk_launch<3, 1, 1>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
-        else if (h->p2g_variant == 5) ok = p2g_bulk_launch<4, 1, 1>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
-        else ok = p2g_bulk_launch<3, 1, 0>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
+        if (h->p2g_variant == 3) ok = p2g_bulk_launch<3, 1, 0>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
+        else ok = p2g_bulk_launch<4, 1, 1>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
         if (!ok) return set_err(FFMPM_E_CUDA, "could not configure the bulk P2G kernel");
         return check_launch(h, 1);
       }
     }
-    const bool use_perm = h->p2g_variant == 0 && h->pipeline == 1;
-    if (use_perm && !h->have_perm) return set_err(FFMPM_E_STATE, "the tiled pipeline needs the full ffmpm_bin");
+    const bool use_perm = h->p2g_variant == 0;
     int nl = p2g_runs<T>(h->dev, sv, h->n, h->bin, (T*)h->grid, h->err, h->sm_count, h->p2g_blocks_per_sm, use_perm, s);
     return check_launch(h, nl);
   }
@@ -397,20 +379,7 @@ static int g2p_t(FfMpmHandle* h, cudaStream_t s) {
     // binned: write the particles back in cell order into the other buffer
     StateView<T> dst = view<T>(h->st[h->live ^ 1]);
     bin_clear_histogram(h->bin, s);   // the kernel pre-bins the advected particles for the next substep
-    int nl;
-    if (h->pipeline == 1) {
-      if (!h->have_perm) return set_err(FFMPM_E_STATE, "the tiled pipeline needs the full ffmpm_bin");
-      // bulk (TMA) stores need 16-byte aligned plane segments
-      bool bulk = h->g2p_bulk && sizeof(T) == 4 && (dst.stride % 4) == 0;
-      const void* planes[] = {dst.x, dst.v, dst.C, dst.F, dst.Jp, dst.mass, dst.mu0, dst.lam0, dst.id};
-      for (const void* q : planes) bulk = bulk && (((uintptr_t)q & 15) == 0);
-      nl = g2p_tiled<T>(h->dev, sv, dst, h->n, h->bin, (const T*)h->grid, h->err, h->sm_count, h->g2p_blocks_per_sm, bulk, s);
-    } else {
-      nl = g2p_stream<T>(h->dev, sv, dst, h->n, h->bin, h->bin.keys, h->bin.rank, h->bin.keys_alt, h->bin.rank_alt,
-                         (const T*)h->grid, h->err, s);
-      int32_t* t = h->bin.keys; h->bin.keys = h->bin.keys_alt; h->bin.keys_alt = t;
-      t = h->bin.rank; h->bin.rank = h->bin.rank_alt; h->bin.rank_alt = t;
-    }
+    int nl = g2p_tiled<T>(h->dev, sv, dst, h->n, h->bin, (const T*)h->grid, h->err, h->sm_count, h->g2p_blocks_per_sm, s);
     h->live ^= 1;
     h->binned = false;  // positions moved: perm / cell offsets are stale ...
     h->prebinned = true;  // ... but keys, ranks and the histogram of the new live buffer are ready
@@ -440,7 +409,7 @@ int ffmpm_g2p(FfMpmHandle* h, void* stream) {
 // True when P2G walks the particles in physical order, i.e. does not consume the binning:
 // the binning can then run on the auxiliary stream underneath it.
 static bool p2g_independent_of_bin(const FfMpmHandle* h) {
-  return h->pipeline == 1 && h->p2g_variant >= 1;
+  return h->p2g_variant >= 1;
 }
 
 static bool binned_pipeline(const FfMpmHandle* h) {
@@ -456,7 +425,7 @@ static int fork_bin(FfMpmHandle* h, cudaStream_t s, bool clear_idle) {
     CUDA_TRY(cudaEventRecord(h->ev_fork, s));
     CUDA_TRY(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
   }
-  if ((rc = bin_impl(h, (void*)w, h->pipeline == 0))) return rc;
+  if ((rc = ffmpm_bin(h, (void*)w))) return rc;
   if (clear_idle) {
     CUDA_TRY(cudaMemsetAsync(h->grids[h->grid_cur ^ 1], 0, (size_t)h->n_nodes * 4 * elem_size(h->cfg), w));
     h->grid_clean[h->grid_cur ^ 1] = true;
@@ -473,7 +442,7 @@ int ffmpm_scatter(FfMpmHandle* h, void* stream) {
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   const bool binned = binned_pipeline(h) && h->n > 0;
-  const bool fuse = binned && h->fuse && h->pipeline == 1;
+  const bool fuse = binned && h->fuse;
   if (h->scatter_ahead) {
     // the previous fused gather already scattered the live state into the idle grid
     h->scatter_ahead = false;
@@ -491,7 +460,7 @@ int ffmpm_scatter(FfMpmHandle* h, void* stream) {
       // binning and the clear of the idle grid (next substep's, or the fused kernel's target): underneath P2G
       if ((rc = fork_bin(h, s, true))) return rc;
     } else {
-      if ((rc = bin_impl(h, stream, h->pipeline == 0))) return rc;
+      if ((rc = ffmpm_bin(h, stream))) return rc;
       if (fuse) {
         CUDA_TRY(cudaMemsetAsync(h->grids[h->grid_cur ^ 1], 0, (size_t)h->n_nodes * 4 * elem_size(h->cfg), s));
         h->grid_clean[h->grid_cur ^ 1] = true;
@@ -523,7 +492,7 @@ int ffmpm_gather(FfMpmHandle* h, void* stream) {
     CUDA_TRY(cudaStreamWaitEvent(s, h->ev_join, 0));
     h->bin_pending = false;
   }
-  const bool can_fuse = h->fuse && binned_pipeline(h) && h->pipeline == 1 && h->n > 0 && h->binned && h->have_perm &&
+  const bool can_fuse = h->fuse && binned_pipeline(h) && h->n > 0 && h->binned &&
                         h->grid_clean[h->grid_cur ^ 1] && !(h->cfg.dim == 3 && h->cfg.model == FFMPM_SNOW);
   if (can_fuse)
     return h->cfg.dtype == FFMPM_F64 ? g2p2g_t<double>(h, s) : g2p2g_t<float>(h, s);

@@ -31,8 +31,6 @@ struct BinBuffers {
   int32_t* keys;         // [capacity]
   int32_t* rank;         // [capacity]
   int32_t* perm;         // [capacity]
-  int32_t* keys_alt;     // [capacity] ping-pong partners of keys / rank: the stream G2P reads the current
-  int32_t* rank_alt;     // [capacity] pair while it emits the next substep's pair (the host swaps them)
   int tiles[3];
   int n_tiles;
   int n_cells;
@@ -66,7 +64,7 @@ inline int64_t bin_workspace_bytes(int dim, const int* n, int64_t capacity) {
   b += bin_a256((int64_t)(n_cells + 2) * 4) * 2;
   b += bin_a256((int64_t)(n_scan_blocks + 1) * 4);
   b += bin_a256((int64_t)n_tiles * 4);
-  b += bin_a256(capacity * 4) * 5;
+  b += bin_a256(capacity * 4) * 3;
   return b;
 }
 
@@ -84,8 +82,6 @@ inline void bin_carve(BinBuffers& B, char* base, int dim, const int* n, int64_t 
   B.keys = (int32_t*)p; p += bin_a256(capacity * 4);
   B.rank = (int32_t*)p; p += bin_a256(capacity * 4);
   B.perm = (int32_t*)p; p += bin_a256(capacity * 4);
-  B.keys_alt = (int32_t*)p; p += bin_a256(capacity * 4);
-  B.rank_alt = (int32_t*)p; p += bin_a256(capacity * 4);
 }
 
 // Tile-major key of a LOCAL base cell.
@@ -253,7 +249,7 @@ inline void bin_clear_histogram(BinBuffers& B, cudaStream_t st) {
 // of the live buffer were already produced by the previous G2P.
 template <typename T>
 int bin_particles(const DevCfg& cfg, const StateView<T>& s, long long n, BinBuffers& B, ErrRec* err, bool prebinned,
-                  bool light, cudaStream_t st) {
+                  cudaStream_t st) {
   const int m = B.n_cells + 2;
   unsigned pb = (unsigned)((n + 255) / 256);
   int launches = 5;
@@ -268,7 +264,6 @@ int bin_particles(const DevCfg& cfg, const StateView<T>& s, long long n, BinBuff
   scan_reduce_kernel<<<B.n_scan_blocks, SCAN_THREADS, 0, st>>>(B.cell_count, m, B.block_sums);
   scan_block_sums_kernel<<<1, 1024, 0, st>>>(B.block_sums, B.n_scan_blocks);
   scan_downsweep_kernel<<<B.n_scan_blocks, SCAN_THREADS, 0, st>>>(B.cell_count, m, B.block_sums, B.cell_off);
-  if (light) return launches - 2;   // the stream pipeline needs only the cell offsets
   active_tiles_kernel<<<(B.n_tiles + 255) / 256, 256, 0, st>>>(B);
   bin_scatter_kernel<<<pb, 256, 0, st>>>(n, B, err);
   return launches;

@@ -9,10 +9,9 @@
 // every particle (it is the one place that knows the advected position), which removes
 // a whole pass over the positions from ffmpm_bin.
 //
-// BULK (fp32): the 128 results of a round are parked plane-major in shared memory and
-// leave the SM as one bulk async copy (cp.async.bulk.global.shared::cta, the TMA engine)
-// per state plane -- 512 contiguous bytes each -- instead of 29 scalar stores per thread;
-// two staging buffers let the copy engine drain round r while round r+1 computes.
+// Stores are plain coalesced 32-bit stores: a variant that parked each round's results in
+// shared memory and drained them with cp.async.bulk (TMA) stores was measured slower
+// (1.09 ms against 0.84 ms, profiles/r01f) and removed.
 #pragma once
 #include "mpm_bin.cuh"
 #include "mpm_common.cuh"
@@ -24,7 +23,6 @@ namespace ffmpm {
 constexpr int TN3 = TILE3 + 2;            // nodes per tile edge
 constexpr int TNODES3 = TN3 * TN3 * TN3;  // 216
 constexpr int G2P_THREADS = 128;
-constexpr int G2P_PLANES = 29;            // x3 v3 C9 F9 mass mu0 lam0 id Jp
 
 // Moves the optional planes that G2P does not compute.
 template <typename T>
@@ -35,25 +33,6 @@ __device__ __forceinline__ void carry_planes(const StateView<T>& src, const Stat
   if (src.lam0) dst.lam0[slot] = src.lam0[p];
   if (src.id) dst.id[slot] = src.id[p];
   if (with_jp && src.Jp) dst.Jp[slot] = src.Jp[p];
-}
-
-template <typename T>
-__device__ __forceinline__ float* g2p_plane_ptr(const StateView<T>& d, int k) {
-  const long long ds = d.stride;
-  if (k < 3) return (float*)(d.x + k * ds);
-  if (k < 6) return (float*)(d.v + (k - 3) * ds);
-  if (k < 15) return (float*)(d.C + (k - 6) * ds);
-  if (k < 24) return (float*)(d.F + (k - 15) * ds);
-  if (k == 24) return (float*)d.mass;
-  if (k == 25) return (float*)d.mu0;
-  if (k == 26) return (float*)d.lam0;
-  if (k == 27) return reinterpret_cast<float*>(d.id);
-  return (float*)d.Jp;
-}
-
-__device__ __forceinline__ void bulk_store_g(void* gdst, const void* ssrc, unsigned bytes) {
-  unsigned sa = (unsigned)__cvta_generic_to_shared(ssrc);
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(sa), "r"(bytes) : "memory");
 }
 
 constexpr int G2P_PRE_PLANES = 17;   // x3 F9 mass mu0 lam0 id Jp
@@ -67,21 +46,17 @@ __device__ __forceinline__ void cp_async4(void* sdst, const void* gsrc) {
 // into shared memory with 4-byte cp.async (the gather through `perm` rules out bulk copies)
 // while the current round computes; the permutation entry itself is fetched two rounds
 // ahead.  Each thread only ever reads what it copied itself, so no barrier is involved.
-template <typename T, bool BULK, int MIN_BLOCKS, bool PRE = false>
+template <typename T, int MIN_BLOCKS, bool PRE = false>
 __global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_tiled3_kernel(DevCfg cfg, StateView<T> src, StateView<T> dst,
                                                                  BinBuffers B, const T* __restrict__ grid, ErrRec* err) {
-  static_assert(!BULK || sizeof(T) == 4, "bulk staging is for the fp32 build");
   using V4 = typename Vec4<T>::type;
   __shared__ V4 tile[TNODES3];
   __shared__ int s_work;
-  // plane-major staging of one round's results, double buffered (BULK only; 1 element otherwise)
-  __shared__ __align__(128) float stage[BULK ? 2 : 1][BULK ? G2P_PLANES : 1][BULK ? G2P_THREADS : 1];
   static_assert(!PRE || sizeof(T) == 4, "the cp.async prefetch is for the fp32 build");
   __shared__ __align__(16) float pre[PRE ? 2 : 1][PRE ? G2P_PRE_PLANES : 1][PRE ? G2P_THREADS : 1];
   int pre_buf = 0;
   const int n_active = B.counters[0];
   const long long ss = src.stride, ds = dst.stride;
-  int round_parity = 0;
 
   for (;;) {
     __syncthreads();
@@ -224,36 +199,7 @@ __global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_tiled3_kernel(Dev
         next_key = bin_key_of<T>(cfg, B, o[0], o[1], o[2]);
         B.keys[slot] = next_key;
       }
-      if constexpr (BULK) {
-        float(*sb)[G2P_THREADS] = stage[round_parity];
-        __syncthreads();   // the copy engine has finished reading this buffer (the issuing lanes waited last round)
-        if (mine) {
-#pragma unroll
-          for (int k = 0; k < 24; ++k) sb[k][threadIdx.x] = (float)o[k];
-          sb[24][threadIdx.x] = (float)cm; sb[25][threadIdx.x] = (float)cmu; sb[26][threadIdx.x] = (float)cl;
-          sb[27][threadIdx.x] = __int_as_float(cid); sb[28][threadIdx.x] = (float)cjp;
-        }
-        __syncthreads();
-        if (threadIdx.x < G2P_PLANES) {
-          float* gp = g2p_plane_ptr(dst, threadIdx.x);
-          if (gp != nullptr) {
-            const int a = max(start, rbase), b = min(end, rbase + G2P_THREADS);   // this round's slots [a, b)
-            const int a4 = (a + 3) & ~3, b4 = b & ~3;
-            const float* sp = sb[threadIdx.x];
-            if (a4 < b4) {
-              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-              bulk_store_g(gp + a4, sp + (a4 - rbase), (unsigned)(b4 - a4) * 4u);
-              for (int s2 = a; s2 < a4; ++s2) gp[s2] = sp[s2 - rbase];
-              for (int s2 = b4; s2 < b; ++s2) gp[s2] = sp[s2 - rbase];
-            } else {
-              for (int s2 = a; s2 < b; ++s2) gp[s2] = sp[s2 - rbase];
-            }
-          }
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the OTHER buffer is free again
-        }
-        round_parity ^= 1;
-      } else {
+      {
         if (mine) {
 #pragma unroll
           for (int k = 0; k < 3; ++k) { dst.x[k * ds + slot] = o[k]; dst.v[k * ds + slot] = o[3 + k]; }
@@ -274,44 +220,24 @@ __global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_tiled3_kernel(Dev
       }
     }
   }
-  if constexpr (BULK) {
-    if (threadIdx.x < G2P_PLANES) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-  }
 }
 
 template <typename T>
 int g2p_tiled(const DevCfg& cfg, const StateView<T>& src, const StateView<T>& dst, long long n, BinBuffers& B,
-              const T* grid, ErrRec* err, int sm_count, int blocks_per_sm, bool bulk, cudaStream_t st) {
+              const T* grid, ErrRec* err, int sm_count, int blocks_per_sm, cudaStream_t st) {
   (void)n;
   cudaMemsetAsync(&B.counters[2], 0, sizeof(int32_t), st);
   int blocks = min(B.n_tiles + 1, sm_count * blocks_per_sm);
-  static int minb = [] { const char* e = getenv("FFMPM_G2P_MINB"); return e ? atoi(e) : 8; }();
   if constexpr (sizeof(T) == 4) {
-    if (bulk) {
-      g2p_tiled3_kernel<T, true, 4><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
-      return 1;
-    }
+    // FFMPM_G2P_PRE=0 disables the cp.async input prefetch (64 registers, 8 CTAs per SM either way)
     static int prefetch = [] { const char* e = getenv("FFMPM_G2P_PRE"); return e ? atoi(e) : 1; }();
-    if (prefetch == 1) {
-      g2p_tiled3_kernel<T, false, 8, true><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
-      return 1;
-    }
-    if (prefetch == 2) {
-      g2p_tiled3_kernel<T, false, 6, true><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
-      return 1;
-    }
-    if (minb >= 8) {
-      g2p_tiled3_kernel<T, false, 8><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
-      return 1;
-    }
-    if (minb == 7) {
-      g2p_tiled3_kernel<T, false, 7><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
-      return 1;
-    }
-    g2p_tiled3_kernel<T, false, 6><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
-    return 1;
+    if (prefetch)
+      g2p_tiled3_kernel<T, 8, true><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
+    else
+      g2p_tiled3_kernel<T, 8, false><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
+  } else {
+    g2p_tiled3_kernel<T, 4, false><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
   }
-  g2p_tiled3_kernel<T, false, 4><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
   return 1;
 }
 

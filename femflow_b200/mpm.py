@@ -216,9 +216,8 @@ class MpmSolver:
     def clear_grid(self, stream=None):
         N.check(self.lib.ffmpm_clear_grid(self._h, self._stream(stream)))
 
-    def bin(self, stream=None, offsets_only: bool = False):
-        fn = self.lib.ffmpm_bin_offsets if offsets_only else self.lib.ffmpm_bin
-        N.check(fn(self._h, self._stream(stream)))
+    def bin(self, stream=None):
+        N.check(self.lib.ffmpm_bin(self._h, self._stream(stream)))
 
     def p2g(self, stream=None):
         N.check(self.lib.ffmpm_p2g(self._h, self._stream(stream)))

@@ -120,9 +120,6 @@ int ffmpm_set_num_particles(FfMpmHandle* h, int64_t n);
 /* Phase entry points (each asynchronous on `stream`). */
 int ffmpm_clear_grid(FfMpmHandle* h, void* stream);
 int ffmpm_bin(FfMpmHandle* h, void* stream);
-/* The part of ffmpm_bin a substep needs (keys, ranks, cell offsets; no permutation
- * array): what ffmpm_substep itself issues. */
-int ffmpm_bin_offsets(FfMpmHandle* h, void* stream);
 int ffmpm_p2g(FfMpmHandle* h, void* stream);
 int ffmpm_grid_op(FfMpmHandle* h, void* stream);
 int ffmpm_g2p(FfMpmHandle* h, void* stream);
