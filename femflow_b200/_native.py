@@ -19,7 +19,6 @@ class FfMpmConfig(C.Structure):
     _fields_ = [
         ("dim", C.c_int32), ("dtype", C.c_int32), ("model", C.c_int32),
         ("res", C.c_int32 * 3), ("n", C.c_int32 * 3), ("origin", C.c_int32 * 3),
-        ("wall_lo", C.c_int32 * 3), ("wall_hi", C.c_int32 * 3),
         ("inv_dx", C.c_double), ("dx", C.c_double), ("dt", C.c_double), ("volume", C.c_double),
         ("gravity", C.c_double), ("hardening", C.c_double),
         ("mass", C.c_double), ("mu_0", C.c_double), ("lambda_0", C.c_double),
@@ -57,6 +56,8 @@ PROTOTYPES = {
     "ffmpm_scatter": (C.c_int, [H, C.c_void_p]),
     "ffmpm_gather": (C.c_int, [H, C.c_void_p]),
     "ffmpm_substep": (C.c_int, [H, C.c_int32, C.c_void_p]),
+    "ffmpm_set_colliders": (C.c_int, [H, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int32]),
+    "ffmpm_collide": (C.c_int, [H, C.c_void_p]),
     "ffmpm_grid_ptr": (C.c_int, [H, C.POINTER(C.c_void_p)]),
     "ffmpm_bin_ptrs": (C.c_int, [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                  C.POINTER(C.c_int64)]),

@@ -1,6 +1,7 @@
 // C ABI of the MPM substep library (see include/femflow_mpm.h).
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -34,6 +35,7 @@ static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * 
 struct FfMpmHandle {
   FfMpmConfig cfg;
   DevCfg dev;
+  Colliders colliders;
   int device;
   int sm_count;
   int64_t n_nodes;
@@ -130,7 +132,6 @@ int ffmpm_create(const FfMpmConfig* cfg, int32_t device, FfMpmHandle** out) {
   d.dim = cfg->dim; d.model = cfg->model;
   for (int i = 0; i < 3; ++i) {
     d.n[i] = cfg->n[i]; d.origin[i] = cfg->origin[i]; d.res[i] = cfg->res[i];
-    d.wall_lo[i] = cfg->wall_lo[i]; d.wall_hi[i] = cfg->wall_hi[i];
   }
   if (cfg->dim == 2) { d.n[2] = 1; d.origin[2] = 0; d.res[2] = 2; }
   d.inv_dx = cfg->inv_dx; d.dx = cfg->dx; d.dt = cfg->dt; d.volume = cfg->volume;
@@ -346,7 +347,7 @@ static int grid_op_t(FfMpmHandle* h, cudaStream_t s, const void* halo_lo = nullp
   unsigned blocks = (unsigned)((h->n_nodes + 255) / 256);
   if (h->cfg.dim == 3)
     grid_op3_kernel<T><<<blocks, 256, 0, s>>>(h->dev, (T*)h->grid, h->n_nodes, (const T*)halo_lo, nodes_lo,
-                                               (const T*)halo_hi, nodes_hi);
+                                               (const T*)halo_hi, nodes_hi, h->colliders);
   else
     grid_op2_kernel<T><<<blocks, 256, 0, s>>>(h->dev, (T*)h->grid, h->n_nodes);
   return check_launch(h, 1);
@@ -508,6 +509,36 @@ int ffmpm_substep(FfMpmHandle* h, int32_t n_substeps, void* stream) {
     if ((rc = ffmpm_gather(h, stream))) return rc;
   }
   return FFMPM_OK;
+}
+
+int ffmpm_set_colliders(FfMpmHandle* h, const double* points, const double* normals, int32_t count) {
+  if (!h) return set_err(FFMPM_E_INVALID, "null handle");
+  if (count < 0 || count > FFMPM_MAX_COLLIDERS || (count > 0 && (!points || !normals)))
+    return set_err(FFMPM_E_INVALID, "bad collider arguments");
+  if (count > 0 && h->cfg.dim != 3) return set_err(FFMPM_E_INVALID, "colliders are 3D only (three_d/grid_op.py:50-67)");
+  h->colliders.count = count;
+  for (int c = 0; c < count; ++c) {
+    const double* nrm = normals + 3 * c;
+    const double denom = sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
+    for (int d = 0; d < 3; ++d) {
+      h->colliders.point[c][d] = points[3 * c + d];
+      h->colliders.normal[c][d] = nrm[d] + (1.0 / denom);   // grid_op.py:59-60: scalar added to every component
+    }
+  }
+  return FFMPM_OK;
+}
+
+int ffmpm_collide(FfMpmHandle* h, void* stream) {
+  int rc = ready(h);
+  if (rc) return rc;
+  if (h->cfg.dim != 3) return set_err(FFMPM_E_INVALID, "colliders are 3D only (three_d/grid_op.py:50-67)");
+  if (h->colliders.count == 0) return FFMPM_OK;
+  unsigned blocks = (unsigned)((h->n_nodes + 255) / 256);
+  if (h->cfg.dtype == FFMPM_F64)
+    collide3_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>(h->dev, (double*)h->grid, h->n_nodes, h->colliders);
+  else
+    collide3_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(h->dev, (float*)h->grid, h->n_nodes, h->colliders);
+  return check_launch(h, 1);
 }
 
 int ffmpm_grid_ptr(FfMpmHandle* h, void** grid) {

@@ -10,10 +10,18 @@ namespace ffmpm {
 // Device copy of FfMpmConfig (passed by value as a kernel argument).
 struct DevCfg {
   int dim, model;
-  int n[3], origin[3], res[3], wall_lo[3], wall_hi[3];
+  int n[3], origin[3], res[3];
   double inv_dx, dx, dt, volume, gravity, hardening;
   double mass, mu0, lam0;
   int fp32_stress;   // fp32 build: evaluate the stress in perturbation form in fp32 when the strain allows
+};
+
+// Plane colliders of three_d/grid_op.py:50-67 (normals already shifted by 1/|normal|, the
+// reference's quirk of adding the scalar to every component).
+struct Colliders {
+  int count;
+  double point[8][3];
+  double normal[8][3];
 };
 
 template <typename T>

@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(128) p2g_scatter2_kernel(DevCfg cfg, StateView
 template <typename T>
 __global__ void __launch_bounds__(256) grid_op3_kernel(DevCfg cfg, T* __restrict__ grid, long long n_nodes,
                                                        const T* __restrict__ halo_lo, long long nodes_lo,
-                                                       const T* __restrict__ halo_hi, long long nodes_hi) {
+                                                       const T* __restrict__ halo_hi, long long nodes_hi, Colliders col) {
   long long node = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (node >= n_nodes) return;
   using V4 = typename Vec4<T>::type;
@@ -238,7 +238,29 @@ __global__ void __launch_bounds__(256) grid_op3_kernel(DevCfg cfg, T* __restrict
   if (I0 < boundary || I0 >= cfg.res[0] - boundary) g.x = (T)0;
   if (I1 < boundary || I1 >= cfg.res[1] - boundary) g.y = (T)0;
   if (I2 < boundary || I2 >= cfg.res[2] - boundary) g.z = (T)0;
+  // plane colliders (three_d/grid_op.py:50-67), predicate in fp64 like the reference
+  for (int c = 0; c < col.count; ++c) {
+    const double ox = I0 * cfg.dx - col.point[c][0], oy = I1 * cfg.dx - col.point[c][1], oz = I2 * cfg.dx - col.point[c][2];
+    if (ox * col.normal[c][0] + oy * col.normal[c][1] + oz * col.normal[c][2] < 0) { g.x = g.y = g.z = (T)0; }
+  }
   reinterpret_cast<V4*>(grid)[node] = g;
+}
+
+// Stand-alone plane colliders (three_d/grid_op.py:50-67) for the phase-level API; inside a
+// substep the same predicate runs fused at the end of grid_op3_kernel.
+template <typename T>
+__global__ void __launch_bounds__(256) collide3_kernel(DevCfg cfg, T* __restrict__ grid, long long n_nodes, Colliders col) {
+  long long node = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (node >= n_nodes) return;
+  const int k = (int)(node % cfg.n[2]);
+  const long long r = node / cfg.n[2];
+  const int I0 = (int)(r / cfg.n[1]) + cfg.origin[0], I1 = (int)(r % cfg.n[1]) + cfg.origin[1], I2 = k + cfg.origin[2];
+  bool hit = false;
+  for (int c = 0; c < col.count; ++c) {
+    const double ox = I0 * cfg.dx - col.point[c][0], oy = I1 * cfg.dx - col.point[c][1], oz = I2 * cfg.dx - col.point[c][2];
+    hit = hit || (ox * col.normal[c][0] + oy * col.normal[c][1] + oz * col.normal[c][2] < 0);
+  }
+  if (hit) { grid[node * 4 + 0] = (T)0; grid[node * 4 + 1] = (T)0; grid[node * 4 + 2] = (T)0; }
 }
 
 // 2D (two_d/grid_op.py:13-24): only nodes with mass > 0; walls are f64 predicates on

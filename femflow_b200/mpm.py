@@ -101,8 +101,6 @@ class MpmSolver:
             cfg.res[i] = self.res[i]
             cfg.n[i] = self.n[i]
             cfg.origin[i] = self.origin[i]
-            cfg.wall_lo[i] = 1
-            cfg.wall_hi[i] = 1
         r0 = self.res[0]
         cfg.dx = float(dx) if dx is not None else 1.0 / r0
         cfg.inv_dx = float(inv_dx) if inv_dx is not None else 1.0 / cfg.dx
@@ -252,6 +250,17 @@ class MpmSolver:
             self.substep(n_substeps)
         self.graph_launches = self.launch_count() - before
         return g
+
+    def set_colliders(self, points, normals) -> None:
+        """Plane colliders applied at the end of every grid update (three_d/grid_op.py:50-67)."""
+        pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+        nrm = np.ascontiguousarray(normals, dtype=np.float64).reshape(-1, 3)
+        assert len(pts) == len(nrm)
+        dp = C.POINTER(C.c_double)
+        N.check(self.lib.ffmpm_set_colliders(self._h, pts.ctypes.data_as(dp), nrm.ctypes.data_as(dp), len(pts)))
+
+    def collide(self, stream=None) -> None:
+        N.check(self.lib.ffmpm_collide(self._h, self._stream(stream)))
 
     def launch_count(self) -> int:
         return int(self.lib.ffmpm_launch_count(self._h))

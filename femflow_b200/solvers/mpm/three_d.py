@@ -48,6 +48,19 @@ def grid_op(grid_resolution, dx, dt, gravity, grid_velocity, grid_mass):
     grid_velocity[...] = gv
 
 
+def check_collision_points(points, normals, grid_resolution, dx, grid_velocity):
+    """three_d/grid_op.py:50-67: zero ``grid_velocity`` behind the planes (point, normal), in place."""
+    s = _solver(grid_resolution, 0, 1.0 / dx, dx, 1.0, 1.0, 0.0, 1.0, "neo_hookean")
+    s.set_colliders(points, normals)
+    try:
+        R.grid_to_device(s, grid_velocity, np.zeros(grid_velocity.shape[:-1] + (1,)))
+        s.collide()
+        gv, _ = R.grid_from_device(s)
+    finally:
+        s.set_colliders(np.zeros((0, 3)), np.zeros((0, 3)))
+    grid_velocity[...] = gv
+
+
 def g2p(inv_dx, dt, grid_velocity, particles, v, F, C, Jp, model: str = "neo_hookean"):
     """three_d/g2p.py:9-59: mutates ``particles[i].pos``, ``v``, ``F``, ``C`` in place."""
     soa = particles_to_soa(particles)

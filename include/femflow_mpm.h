@@ -16,6 +16,10 @@
  *   ffmpm_bin          (new) cell binning of base_coord, three_d/p2g.py:50
  *   ffmpm_poll_error   the RuntimeError of three_d/p2g.py:51-52,70-71, g2p.py:23-24,35-36
  *   ffmpm_snapshot     femflow/solvers/mpm/particle.py:30-33   map_particles_to_pos
+ *   ffmpm_set_colliders / ffmpm_collide
+ *                      femflow/solvers/mpm/three_d/grid_op.py:50-67  check_collision_points
+ *   ffmpm_scatter / ffmpm_gather / ffmpm_grid_op_halo
+ *                      (new) the halves of a substep around the grid update, for slab drivers
  *
  * Conventions
  *   - Plain C, no torch types.  All array arguments are DEVICE pointers owned by
@@ -70,9 +74,8 @@ typedef struct FfMpmConfig {
   int32_t model;          /* FFMPM_NEO_HOOKEAN / FFMPM_SNOW                      */
   int32_t res[3];         /* GLOBAL grid_resolution per axis (walls use it)      */
   int32_t n[3];           /* LOCAL node counts per axis (res+1 for one GPU)      */
-  int32_t origin[3];      /* global index of local node 0 per axis               */
-  int32_t wall_lo[3];     /* 1: this rank owns the low global face of the axis   */
-  int32_t wall_hi[3];     /* 1: this rank owns the high global face              */
+  int32_t origin[3];      /* global index of local node 0 per axis (walls act on GLOBAL
+                             indices, so only the ranks holding a global face see them) */
   double inv_dx, dx, dt, volume, gravity, hardening;
   /* 2D only (two_d/p2g.py:14-16 takes global material scalars); also used in
    * 3D when the per-particle arrays of FfMpmState are NULL. */
@@ -141,6 +144,15 @@ int ffmpm_scatter(FfMpmHandle* h, void* stream);
 int ffmpm_gather(FfMpmHandle* h, void* stream);
 /* n_substeps x (scatter, grid_op, gather). */
 int ffmpm_substep(FfMpmHandle* h, int32_t n_substeps, void* stream);
+
+/* Plane colliders (femflow/solvers/mpm/three_d/grid_op.py:50-67 check_collision_points, unused
+ * by the reference's driver): every node with dot(I*dx - point, normal + 1/|normal|) < 0 for
+ * some (point, normal) gets zero velocity at the end of the grid update.  `points`, `normals`:
+ * HOST arrays of count x 3 doubles (copied); count <= FFMPM_MAX_COLLIDERS, 0 clears them. */
+#define FFMPM_MAX_COLLIDERS 8
+int ffmpm_set_colliders(FfMpmHandle* h, const double* points, const double* normals, int32_t count);
+/* check_collision_points on its own (phase-level parity): applies the colliders to the grid. */
+int ffmpm_collide(FfMpmHandle* h, void* stream);
 
 /* Phase-level access for parity tests: device pointer of the node-major grid
  * (n[0]*n[1]*n[2]*4 scalars of cfg.dtype). */

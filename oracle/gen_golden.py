@@ -417,11 +417,25 @@ def gen_snow2d(ref):
     save("snow2d", x=x, v=v, F=F, C=C, Jp=Jp, **{k: np.float64(val) for k, val in p.items()}, **out)
 
 
+def gen_collide3d(ref):
+    """Plane colliders, three_d/grid_op.py:50-67 (check_collision_points), on a random velocity grid."""
+    three_d = ref[0]
+    from femflow.solvers.mpm.three_d.grid_op import check_collision_points
+    rng = np.random.default_rng(9)
+    res = 12; G = res + 1
+    gv = rng.normal(0, 1, size=(G, G, G, 3))
+    points = np.array([[0.2, 0.1, 0.3], [0.8, 0.5, 0.5], [0.5, 0.9, 0.1]])
+    normals = np.array([[0.0, 1.0, 0.0], [-1.0, 0.2, 0.1], [0.3, -2.0, 0.5]])
+    out = gv.copy()
+    check_collision_points(points, normals, res, 1.0 / res, out)
+    save("collide3d", grid_velocity=gv, points=points, normals=normals, res=np.float64(res), grid_velocity_out=out)
+
+
 def main(argv):
     ref = _import_reference()
     gens = dict(kat3d=gen_kat3d, block3d=gen_block3d, rest3d=gen_rest3d, walls3d=gen_walls3d,
                 c1=gen_c1, drift3d=gen_drift3d, test2d=gen_test2d, drift2d=gen_drift2d, block2d=gen_block2d,
-                quirk2d=gen_quirk2d, snow3d=gen_snow3d, snow2d=gen_snow2d)
+                quirk2d=gen_quirk2d, snow3d=gen_snow3d, snow2d=gen_snow2d, collide3d=gen_collide3d)
     which = argv[1:] or list(gens)
     for name in which:
         print(f"== {name}")

@@ -27,7 +27,7 @@ __all__ = [
     "Ev_to_mu", "Ev_to_lambda", "bspline_weights", "base_and_fx", "cell_keys",
     "polar_decomp_2d", "polar_decomp_3d",
     "fixed_corotated_stress_2d", "fixed_corotated_stress_3d",
-    "p2g_3d", "grid_op_3d", "g2p_3d", "solve_mls_mpm_3d",
+    "p2g_3d", "grid_op_3d", "check_collision_points", "g2p_3d", "solve_mls_mpm_3d",
     "p2g_2d", "grid_op_2d", "g2p_2d", "solve_mls_mpm_2d",
     "boundary_masks_2d",
 ]
@@ -197,6 +197,18 @@ def grid_op_3d(grid_resolution, dx, dt, gravity, grid_velocity, grid_mass):
     gv[wall, :, :, 0] = 0
     gv[:, wall, :, 1] = 0
     gv[:, :, wall, 2] = 0
+
+
+def check_collision_points(points, normals, grid_resolution, dx, grid_velocity):
+    """three_d/grid_op.py:50-67: zero the velocity of every node behind any of the planes
+    (point, normal); the reference adds the scalar 1/|normal| to every component of the
+    normal before the test (grid_op.py:59-60)."""
+    G = grid_resolution + 1
+    I = np.stack(np.meshgrid(*([np.arange(G)] * 3), indexing="ij"), -1).astype(np.float64)
+    for point, normal in zip(np.asarray(points, dtype=np.float64), np.asarray(normals, dtype=np.float64)):
+        normal = normal + (1.0 / np.sqrt(np.sum(np.square(normal))))
+        offset = I * dx - point
+        grid_velocity[offset @ normal < 0] = 0.0
 
 
 def g2p_3d(inv_dx, dt, grid_velocity, x, v, F, C, Jp, model="neo_hookean"):

@@ -334,3 +334,32 @@ def test_multi_substep_pipelines_vs_oracle(mode):
     assert rel_err(out["F"], F, 1.0) < 1e-5 * steps
     assert np.abs(out["C"] - C).max() / (4 * sc.res * V) < 1e-5 * steps
     s.close()
+
+
+def test_collision_planes(dtype):
+    """Plane colliders fused into the grid update vs the reference (three_d/grid_op.py:50-67)."""
+    from femflow_b200.solvers.mpm import three_d
+    from femflow_b200.mpm import MpmSolver
+    g = load_golden("collide3d")
+    res = int(g["res"])
+    gv = g["grid_velocity"].copy()
+    three_d.check_collision_points(g["points"], g["normals"], res, 1.0 / res, gv)
+    want = g["grid_velocity_out"]
+    assert np.array_equal(gv == 0, want == 0)
+    assert rel_err(gv, want) < (1e-6 if dtype == "float32" else 1e-15)
+    # and fused at the end of the grid update: same result as the stand-alone function applied afterwards
+    s = MpmSolver(3, 16, 1e-3, 1e-4, -9.8, 1.0, capacity=64, dtype=getattr(torch, dtype))
+    x = np.random.default_rng(0).uniform(0.3, 0.7, size=(40, 3))
+    s.set_particles(x, v=np.tile([0.3, -1.0, 0.2], (40, 1)), mass=1e-3, mu0=10.0, lam0=10.0)
+    planes = ([[0.5, 0.5, 0.5], [0.2, 0.9, 0.2]], [[0.0, 1.0, 0.0], [1.0, -3.0, 0.5]])
+    s.clear_grid(); s.p2g(); s.grid_op()
+    plain = s.grid().double().cpu().numpy()[..., :3].copy()
+    s.set_colliders(*planes)
+    s.clear_grid(); s.p2g(); s.grid_op()
+    fused = s.grid().double().cpu().numpy()[..., :3]
+    O.check_collision_points(planes[0], planes[1], 16, 1.0 / 16, plain)
+    assert np.array_equal(fused, plain)
+    assert np.any(plain != 0) and np.any((fused == 0).all(-1) & (s.grid().cpu().numpy()[..., 3] > 0))
+    with pytest.raises(Exception):
+        s.set_colliders(np.zeros((9, 3)), np.ones((9, 3)))      # more than FFMPM_MAX_COLLIDERS
+    s.close()

@@ -267,3 +267,13 @@ def test_snow2d_matches_reference():
         assert rel_err(got, g[key]) < 1e-11, key
     # the clamp really acts in this fixture
     assert np.abs(g["Jp_out"] - g["Jp"]).max() > 1e-3
+
+
+def test_collision_planes_match_reference():
+    """three_d/grid_op.py:50-67 check_collision_points (incl. the scalar-added-to-normal quirk)."""
+    g = load_golden("collide3d")
+    gv = g["grid_velocity"].copy()
+    O.check_collision_points(g["points"], g["normals"], int(g["res"]), 1.0 / int(g["res"]), gv)
+    assert np.array_equal(gv, g["grid_velocity_out"])
+    hit = np.all(g["grid_velocity_out"] == 0, axis=-1)
+    assert 0 < hit.sum() < hit.size
