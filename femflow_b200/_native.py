@@ -58,6 +58,8 @@ PROTOTYPES = {
     "ffmpm_substep": (C.c_int, [H, C.c_int32, C.c_void_p]),
     "ffmpm_set_colliders": (C.c_int, [H, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int32]),
     "ffmpm_collide": (C.c_int, [H, C.c_void_p]),
+    "ffmpm_set_owned_range": (C.c_int, [H, C.c_int32, C.c_int32]),
+    "ffmpm_leaver_count_ptr": (C.c_int, [H, C.POINTER(C.c_void_p)]),
     "ffmpm_grid_ptr": (C.c_int, [H, C.POINTER(C.c_void_p)]),
     "ffmpm_bin_ptrs": (C.c_int, [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                  C.POINTER(C.c_int64)]),

@@ -2,6 +2,8 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <climits>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -137,6 +139,8 @@ int ffmpm_create(const FfMpmConfig* cfg, int32_t device, FfMpmHandle** out) {
   d.inv_dx = cfg->inv_dx; d.dx = cfg->dx; d.dt = cfg->dt; d.volume = cfg->volume;
   d.gravity = cfg->gravity; d.hardening = cfg->hardening;
   d.mass = cfg->mass; d.mu0 = cfg->mu_0; d.lam0 = cfg->lambda_0;
+  d.own_lo = INT32_MIN;   // single domain: nobody leaves
+  d.own_hi = INT32_MAX;
   d.fp32_stress = 1;
   if (const char* e = getenv("FFMPM_FP32_STRESS")) d.fp32_stress = atoi(e) != 0;
   h->n_nodes = (int64_t)d.n[0] * d.n[1] * d.n[2];
@@ -525,6 +529,19 @@ int ffmpm_set_colliders(FfMpmHandle* h, const double* points, const double* norm
       h->colliders.normal[c][d] = nrm[d] + (1.0 / denom);   // grid_op.py:59-60: scalar added to every component
     }
   }
+  return FFMPM_OK;
+}
+
+int ffmpm_set_owned_range(FfMpmHandle* h, int32_t own_lo, int32_t own_hi) {
+  if (!h || own_lo > own_hi) return set_err(FFMPM_E_INVALID, "bad owned range");
+  h->dev.own_lo = own_lo;
+  h->dev.own_hi = own_hi;
+  return FFMPM_OK;
+}
+
+int ffmpm_leaver_count_ptr(FfMpmHandle* h, int32_t** count) {
+  if (!h || !h->ws || !count) return set_err(FFMPM_E_STATE, "workspace not set");
+  *count = &h->bin.counters[3];
   return FFMPM_OK;
 }
 

@@ -23,7 +23,8 @@ constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 struct BinBuffers {
-  int32_t* counters;     // [16]: 0 = n_active_tiles, 1 = p2g work counter, 2 = g2p work counter
+  int32_t* counters;     // [16]: 0 = n_active_tiles, 1 = p2g work counter, 2 = g2p work counter,
+                         //       3 = particles whose base cell left the rank's owned x range (slabs)
   int32_t* cell_count;   // [n_cells + 2] histogram, bin n_cells = out-of-grid
   int32_t* cell_off;     // [n_cells + 2] exclusive scan of cell_count
   int32_t* block_sums;   // [n_scan_blocks + 1]
@@ -97,7 +98,7 @@ __device__ __forceinline__ int bin_key2(int bx, int by, int ty) {
 // Bin key of a particle position: tile-major id of its LOCAL base cell, or n_cells
 // when the stencil would leave the grid (utils.py:138-150) / the position is NaN.
 template <typename T>
-__device__ __forceinline__ int bin_key_of(const DevCfg& cfg, const BinBuffers& B, T x0, T x1, T x2) {
+__device__ __forceinline__ int bin_key_of(const DevCfg& cfg, const BinBuffers& B, T x0, T x1, T x2, int* base_x = nullptr) {
   const T xs[3] = {x0, x1, x2};
   int b[3] = {0, 0, 0};
   bool ok = true;
@@ -108,6 +109,7 @@ __device__ __forceinline__ int bin_key_of(const DevCfg& cfg, const BinBuffers& B
       int g;
       base_fx(xs[d], cfg.inv_dx, g, fx);
       b[d] = g - cfg.origin[d];
+      if (d == 0 && base_x) *base_x = g;
       ok = ok && !isnan((double)xs[d]) && b[d] >= 0 && b[d] + 2 < cfg.n[d];
     }
   }

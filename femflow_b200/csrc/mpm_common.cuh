@@ -14,6 +14,7 @@ struct DevCfg {
   double inv_dx, dx, dt, volume, gravity, hardening;
   double mass, mu0, lam0;
   int fp32_stress;   // fp32 build: evaluate the stress in perturbation form in fp32 when the strain allows
+  int own_lo, own_hi;  // slabs: GLOBAL base cells [own_lo, own_hi) along x owned by this rank (G2P counts leavers)
 };
 
 // Plane colliders of three_d/grid_op.py:50-67 (normals already shifted by 1/|normal|, the

@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_tiled3_kernel(Dev
       const int slot = rbase + threadIdx.x;
       const bool mine = slot >= start && slot < end;
       int next_key = -1;
+      bool leaving = false;
       T o[24];
       T cm = 0, cmu = 0, cl = 0, cjp = 0;
       int cid = 0;
@@ -196,8 +197,15 @@ __global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_tiled3_kernel(Dev
         o[21] = m20 * f00 + m21 * f10 + m22 * f20;
         o[22] = m20 * f01 + m21 * f11 + m22 * f21;
         o[23] = m20 * f02 + m21 * f12 + m22 * f22;
-        next_key = bin_key_of<T>(cfg, B, o[0], o[1], o[2]);
+        int gbx = 0;
+        next_key = bin_key_of<T>(cfg, B, o[0], o[1], o[2], &gbx);
         B.keys[slot] = next_key;
+        leaving = gbx < cfg.own_lo || gbx >= cfg.own_hi;
+      }
+      {
+        // slabs: count the particles that now belong to a neighbour rank (read by the migration logic)
+        const unsigned lm = __ballot_sync(0xffffffffu, leaving);
+        if (lm && (threadIdx.x & 31) == 0) atomicAdd(&B.counters[3], __popc(lm));
       }
       {
         if (mine) {

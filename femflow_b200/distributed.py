@@ -266,6 +266,10 @@ class CudaSlab(LocalSlab):
                                 inv_dx=1.0 / dx, dtype=dtype, device=device,
                                 n_nodes=(plan.n_local_x, plan.res[1] + 1, plan.res[2] + 1),
                                 origin=(plan.g_lo, 0, 0), per_particle_material=True, p2g_mode=p2g_mode, reorder=True)
+        # the binned G2P counts the particles that left [own_lo, own_hi) while it advects them
+        self.solver.set_owned_range(plan.own_lo if plan.rank > 0 else -(2 ** 31),
+                                    plan.own_hi if plan.rank < plan.world - 1 else 2 ** 31 - 1)
+        self._g2p_counts = p2g_mode != "fused"
 
     @property
     def num_particles(self) -> int:
@@ -326,6 +330,8 @@ class CudaSlab(LocalSlab):
     def count_leavers_async(self, own_lo: int, own_hi: int):
         """Device-side count of the particles whose base cell left [own_lo, own_hi)."""
         s = self.solver
+        if self._g2p_counts and s.num_particles > 0:
+            return s.leaver_count().to(torch.int64)      # filled by the last G2P, no extra pass over x
         x0 = s.live.x[0, :s.num_particles]
         t_lo, t_hi = self._threshold(own_lo), self._threshold(own_hi)
         return torch.count_nonzero((x0 < t_lo) | (x0 >= t_hi)).to(torch.int64).reshape(1)

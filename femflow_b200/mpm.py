@@ -259,6 +259,16 @@ class MpmSolver:
         dp = C.POINTER(C.c_double)
         N.check(self.lib.ffmpm_set_colliders(self._h, pts.ctypes.data_as(dp), nrm.ctypes.data_as(dp), len(pts)))
 
+    def set_owned_range(self, own_lo: int, own_hi: int) -> None:
+        N.check(self.lib.ffmpm_set_owned_range(self._h, int(own_lo), int(own_hi)))
+
+    def leaver_count(self) -> torch.Tensor:
+        """(1,) int32 view of the device counter the binned G2P fills (see ffmpm_set_owned_range)."""
+        ptr = C.c_void_p()
+        N.check(self.lib.ffmpm_leaver_count_ptr(self._h, C.byref(ptr)))
+        off = ptr.value - self.workspace.data_ptr()
+        return self.workspace[off:off + 4].view(torch.int32)
+
     def collide(self, stream=None) -> None:
         N.check(self.lib.ffmpm_collide(self._h, self._stream(stream)))
 

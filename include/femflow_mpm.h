@@ -133,6 +133,12 @@ int ffmpm_g2p(FfMpmHandle* h, void* stream);
  * axis 0 is slowest).  With 0 planes it is ffmpm_grid_op. */
 int ffmpm_grid_op_halo(FfMpmHandle* h, const void* recv_lo, int32_t planes_lo, const void* recv_hi,
                        int32_t planes_hi, void* stream);
+/* Slabs: the GLOBAL base cells [own_lo, own_hi) along axis 0 owned by this rank.  The binned
+ * G2P then counts, per substep, the particles whose new base cell lies outside that range in a
+ * device counter (ffmpm_leaver_count_ptr; cleared by the next ffmpm_bin), so the migration logic
+ * needs no pass of its own over the positions. */
+int ffmpm_set_owned_range(FfMpmHandle* h, int32_t own_lo, int32_t own_hi);
+int ffmpm_leaver_count_ptr(FfMpmHandle* h, int32_t** count);
 /* The two halves of a substep either side of the grid update, as ffmpm_substep issues
  * them (slab drivers put the halo exchange in between):
  *   ffmpm_scatter  zeroed grid + cell binning + P2G   (mls_mpm.py:54-73).  The library keeps
