@@ -25,7 +25,8 @@ _P2G = {"auto": N.FFMPM_P2G_AUTO, "scatter": N.FFMPM_P2G_SCATTER, "tiled": N.FFM
 def _as_tensor(a, dtype, device):
     if isinstance(a, torch.Tensor):
         return a.to(device=device, dtype=dtype)
-    return torch.as_tensor(np.ascontiguousarray(a), device=device).to(dtype)
+    a = np.array(a, copy=True, order="C") if not getattr(a, "flags", None) or not a.flags.writeable else np.ascontiguousarray(a)
+    return torch.as_tensor(a, device=device).to(dtype)
 
 
 class _StateBuffer:

@@ -363,3 +363,43 @@ def test_collision_planes(dtype):
     with pytest.raises(Exception):
         s.set_colliders(np.zeros((9, 3)), np.ones((9, 3)))      # more than FFMPM_MAX_COLLIDERS
     s.close()
+
+
+def test_c_abi_error_codes():
+    """Error convention of the boundary: negative codes + ffmpm_last_error, never an exception or a crash."""
+    import ctypes as C
+    from femflow_b200 import _native as N
+    lib = N.lib()
+    cfg = N.FfMpmConfig()
+    cfg.dim = 3
+    for i in range(3):
+        cfg.res[i] = 16; cfg.n[i] = 17
+    cfg.dx, cfg.inv_dx, cfg.dt, cfg.volume, cfg.hardening = 1 / 16, 16.0, 1e-4, 1.0, 1.0
+    h = N.H()
+    assert lib.ffmpm_create(C.byref(cfg), 99, C.byref(h)) == N.FFMPM_E_INVALID          # no such device
+    assert lib.ffmpm_create(C.byref(cfg), 0, C.byref(h)) == 0
+    stream = C.c_void_p(0)
+    assert lib.ffmpm_substep(h, 1, stream) == N.FFMPM_E_STATE                            # no workspace yet
+    nbytes = lib.ffmpm_workspace_bytes(C.byref(cfg), 1000)
+    ws = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+    assert lib.ffmpm_set_workspace(h, ws.data_ptr() + 8, nbytes - 8) == N.FFMPM_E_INVALID   # misaligned
+    assert lib.ffmpm_set_workspace(h, ws.data_ptr(), 1024) == N.FFMPM_E_STATE            # too small for the grid
+    assert lib.ffmpm_set_workspace(h, ws.data_ptr(), nbytes) == 0
+    assert lib.ffmpm_substep(h, 1, stream) == N.FFMPM_E_STATE                            # state not bound
+    planes = {k: torch.zeros((m, 1024), device="cuda") for k, m in (("x", 3), ("v", 3), ("C", 9), ("F", 9))}
+    st = N.FfMpmState(planes["x"].data_ptr(), planes["v"].data_ptr(), planes["C"].data_ptr(), planes["F"].data_ptr(),
+                      None, planes["x"].data_ptr(), None, None, None, 1024)               # mass without mu0/lam0
+    assert lib.ffmpm_bind_state(h, C.byref(st), None, 10) == N.FFMPM_E_INVALID
+    st = N.FfMpmState(planes["x"].data_ptr(), planes["v"].data_ptr(), planes["C"].data_ptr(), planes["F"].data_ptr(),
+                      None, None, None, None, None, 1024)
+    assert lib.ffmpm_bind_state(h, C.byref(st), None, 2000) == N.FFMPM_E_INVALID         # n > stride
+    assert lib.ffmpm_bind_state(h, C.byref(st), None, 10) == 0
+    planes["F"][[0, 4, 8], :10] = 1.0
+    planes["x"][:, :10] = 0.5
+    planes["x"][2, 0] = 5.0                                                               # one particle far outside
+    assert lib.ffmpm_substep(h, 1, stream) == 0
+    code, n_oob = C.c_int32(), C.c_int64()
+    assert lib.ffmpm_poll_error(h, stream, C.byref(code), C.byref(n_oob)) == N.FFMPM_E_OOB and n_oob.value >= 1
+    assert lib.ffmpm_poll_error(h, stream, C.byref(code), C.byref(n_oob)) == 0           # sticky flag was cleared
+    assert b"" != lib.ffmpm_last_error()
+    lib.ffmpm_destroy(h)
