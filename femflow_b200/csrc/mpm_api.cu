@@ -214,6 +214,9 @@ int ffmpm_set_workspace(FfMpmHandle* h, void* workspace, int64_t bytes) {
 
 static bool state_ok(const FfMpmHandle* h, const FfMpmState* s) {
   if (!s->x || !s->v || !s->C || !s->F) return false;
+  // per-particle material: all three planes or none (then the config scalars apply)
+  const int mats = (s->mass != nullptr) + (s->mu0 != nullptr) + (s->lam0 != nullptr);
+  if (mats != 0 && mats != 3) return false;
   if (h->cfg.dim == 2 && !s->Jp) return false;
   if (h->cfg.model == FFMPM_SNOW && !s->Jp) return false;
   return true;
