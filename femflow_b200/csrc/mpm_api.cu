@@ -139,6 +139,12 @@ int ffmpm_create(const FfMpmConfig* cfg, int32_t device, FfMpmHandle** out) {
   d.inv_dx = cfg->inv_dx; d.dx = cfg->dx; d.dt = cfg->dt; d.volume = cfg->volume;
   d.gravity = cfg->gravity; d.hardening = cfg->hardening;
   d.mass = cfg->mass; d.mu0 = cfg->mu_0; d.lam0 = cfg->lambda_0;
+  {
+    int e = 0;
+    const double m = frexp(cfg->inv_dx, &e);
+    d.index_fp32 = (m == 0.5 && e > -100 && e < 100) ? 1 : 0;   // inv_dx == 2^(e-1) exactly
+    if (const char* ev = getenv("FFMPM_INDEX_FP32")) d.index_fp32 = d.index_fp32 && atoi(ev) != 0;
+  }
   d.own_lo = INT32_MIN;   // single domain: nobody leaves
   d.own_hi = INT32_MAX;
   d.fp32_stress = 1;

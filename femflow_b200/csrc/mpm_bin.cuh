@@ -107,7 +107,7 @@ __device__ __forceinline__ int bin_key_of(const DevCfg& cfg, const BinBuffers& B
     if (d < cfg.dim) {
       T fx;
       int g;
-      base_fx(xs[d], cfg.inv_dx, g, fx);
+      base_fx(xs[d], cfg, g, fx);
       b[d] = g - cfg.origin[d];
       if (d == 0 && base_x) *base_x = g;
       ok = ok && !isnan((double)xs[d]) && b[d] >= 0 && b[d] + 2 < cfg.n[d];

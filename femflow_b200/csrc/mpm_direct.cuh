@@ -30,9 +30,9 @@ __device__ __forceinline__ P2GParticle3<T> p2g_prepare3_from(const DevCfg& cfg, 
   P2GParticle3<T> q;
   T x0 = get(P2G_X), x1 = get(P2G_X + 1), x2 = get(P2G_X + 2);
   int gx, gy, gz;
-  base_fx(x0, cfg.inv_dx, gx, q.fx);
-  base_fx(x1, cfg.inv_dx, gy, q.fy);
-  base_fx(x2, cfg.inv_dx, gz, q.fz);
+  base_fx(x0, cfg, gx, q.fx);
+  base_fx(x1, cfg, gy, q.fy);
+  base_fx(x2, cfg, gz, q.fz);
   q.bx = gx - cfg.origin[0]; q.by = gy - cfg.origin[1]; q.bz = gz - cfg.origin[2];
   // utils.py:138-150 with res = G: base < 0 or base + 2 >= G  -> RuntimeError
   q.ok = !(isnan((double)x0) || isnan((double)x1) || isnan((double)x2)) &&
@@ -108,8 +108,8 @@ __device__ __forceinline__ P2GParticle2<T> p2g_prepare2(const DevCfg& cfg, const
   const long long st = s.stride;
   T x0 = s.x[p], x1 = s.x[st + p];
   int gx, gy;
-  base_fx(x0, cfg.inv_dx, gx, q.fx);
-  base_fx(x1, cfg.inv_dx, gy, q.fy);
+  base_fx(x0, cfg, gx, q.fx);
+  base_fx(x1, cfg, gy, q.fy);
   q.bx = gx - cfg.origin[0]; q.by = gy - cfg.origin[1];
   // The 2D reference has no bounds check (UB there); we flag and skip instead.
   q.ok = !(isnan((double)x0) || isnan((double)x1)) && q.bx >= 0 && q.by >= 0 && q.bx + 2 < cfg.n[0] && q.by + 2 < cfg.n[1];
@@ -340,9 +340,9 @@ __global__ void __launch_bounds__(128) g2p_gather3_kernel(DevCfg cfg, StateView<
   T x0 = s.x[p], x1 = s.x[st + p], x2 = s.x[2 * st + p];
   int gx, gy, gz;
   T fx, fy, fz;
-  base_fx(x0, cfg.inv_dx, gx, fx);
-  base_fx(x1, cfg.inv_dx, gy, fy);
-  base_fx(x2, cfg.inv_dx, gz, fz);
+  base_fx(x0, cfg, gx, fx);
+  base_fx(x1, cfg, gy, fy);
+  base_fx(x2, cfg, gz, fz);
   int bx = gx - cfg.origin[0], by = gy - cfg.origin[1], bz = gz - cfg.origin[2];
   bool ok = !(isnan((double)x0) || isnan((double)x1) || isnan((double)x2)) && bx >= 0 && by >= 0 && bz >= 0 &&
             bx + 2 < cfg.n[0] && by + 2 < cfg.n[1] && bz + 2 < cfg.n[2];
@@ -387,8 +387,8 @@ __global__ void __launch_bounds__(128) g2p_gather2_kernel(DevCfg cfg, StateView<
   T x0 = s.x[p], x1 = s.x[st + p];
   int gx, gy;
   T fx, fy;
-  base_fx(x0, cfg.inv_dx, gx, fx);
-  base_fx(x1, cfg.inv_dx, gy, fy);
+  base_fx(x0, cfg, gx, fx);
+  base_fx(x1, cfg, gy, fy);
   int bx = gx - cfg.origin[0], by = gy - cfg.origin[1];
   bool ok = !(isnan((double)x0) || isnan((double)x1)) && bx >= 0 && by >= 0 && bx + 2 < cfg.n[0] && by + 2 < cfg.n[1];
   if (!ok) { atomicAdd(&err->n_oob, 1ULL); return; }

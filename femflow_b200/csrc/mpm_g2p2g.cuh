@@ -99,9 +99,9 @@ g2p2g_tiled3_kernel(DevCfg cfg, StateView<T> src, StateView<T> dst, BinBuffers B
           const T f20 = src.F[6 * ss + p], f21 = src.F[7 * ss + p], f22 = src.F[8 * ss + p];
           int gx, gy, gz;
           T fx, fy, fz;
-          base_fx(x0, cfg.inv_dx, gx, fx);
-          base_fx(x1, cfg.inv_dx, gy, fy);
-          base_fx(x2, cfg.inv_dx, gz, fz);
+          base_fx(x0, cfg, gx, fx);
+          base_fx(x1, cfg, gy, fy);
+          base_fx(x2, cfg, gz, fz);
           const int cb = ((gx - cfg.origin[0] - ox) * TN3 + (gy - cfg.origin[1] - oy)) * TN3 + (gz - cfg.origin[2] - oz);
           T o[24];
           {

@@ -171,9 +171,9 @@ __global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_tiled3_kernel(Dev
         }
         int gx, gy, gz;
         T fx, fy, fz;
-        base_fx(x0, cfg.inv_dx, gx, fx);
-        base_fx(x1, cfg.inv_dx, gy, fy);
-        base_fx(x2, cfg.inv_dx, gz, fz);
+        base_fx(x0, cfg, gx, fx);
+        base_fx(x1, cfg, gy, fy);
+        base_fx(x2, cfg, gz, fz);
         const int cb = ((gx - cfg.origin[0] - ox) * TN3 + (gy - cfg.origin[1] - oy)) * TN3 + (gz - cfg.origin[2] - oz);
         T vx, vy, vz, c00, c01, c02, c10, c11, c12, c20, c21, c22;
         g2p_accumulate3<T>([&](int i, int j, int k) { return tile[cb + (i * TN3 + j) * TN3 + k]; }, fx, fy, fz,
