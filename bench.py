@@ -152,6 +152,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--p2g-mode", default="auto")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--material", default="auto", choices=["auto", "planes"],
+                    help="per-particle material layout (N=1): auto = table/rows when <= 256 distinct triples, planes = 3 scalar planes")
     ap.add_argument("--slab-timing", action="store_true", help="N>1: print per-phase CUDA-event times per rank to stderr")
     ap.add_argument("--margin", type=int, default=4, help="slab halo margin in cells = substeps between migrations")
     args = ap.parse_args()
@@ -195,7 +197,8 @@ def main():
     else:
         solver = MpmSolver(scene.dim, scene.res, scene.dt, scene.volume, scene.gravity, scene.hardening,
                            capacity=n, device=dev, mass=scene.mass, mu_0=scene.mu_0, lambda_0=scene.lambda_0,
-                           p2g_mode=args.p2g_mode)
+                           p2g_mode=args.p2g_mode,
+                           per_particle_material=(True if args.material == "planes" and scene.dim == 3 else None))
         solver.set_particles(scene.x, scene.v, scene.F, scene.C, None,
                              *( (scene.mass, scene.mu_0, scene.lambda_0) if scene.dim == 3 else (None, None, None)))
 
@@ -274,9 +277,9 @@ def main():
         b = core.buffers[0]
         host_in = {k: torch.empty_like(getattr(b, k)[..., :n], device="cpu").pin_memory()
                    for k in ("x", "v", "C", "F") }
-        for k in ("mass", "mu0", "lam0"):
+        for k in ("mass", "mu0", "lam0", "material"):
             if getattr(b, k) is not None:
-                host_in[k] = torch.empty(n, dtype=b.x.dtype).pin_memory()
+                host_in[k] = torch.empty(n, dtype=getattr(b, k).dtype).pin_memory()
         live = core.live
         for k in host_in:
             host_in[k].copy_(getattr(live, k)[..., :n])
@@ -331,12 +334,16 @@ def main():
     if phases:
         N_, A = n, scene.active_nodes
         if scene.dim == 3:
-            alg = {"p2g": 108 * N_ + 16 * A, "g2p": (48 + 96) * N_ + 12 * A, "grid_op": 28 * A, "clear": 16 * A}
+            core_ = solver if world == 1 else solver.local.solver
+            b0 = core_.buffers[0]
+            # per-particle material bytes P2G reads: 12 as planes, 1 as table rows, 0 for a one-row table
+            mat_b = 12 if b0.mass is not None else (1 if b0.material is not None else 0)
+            alg = {"p2g": (96 + mat_b) * N_ + 16 * A, "g2p": (48 + 96) * N_ + 12 * A, "grid_op": 28 * A, "clear": 16 * A}
         else:
             alg = {"p2g": 48 * N_ + 12 * A, "g2p": (28 + 52) * N_ + 8 * A, "grid_op": 20 * A, "clear": 12 * A}
         dom = max((k for k in phases if k in alg), key=lambda k: phases[k])
         achieved = alg[dom] / (phases[dom] * 1e-3) / 1e9
-        total_alg = (252 * N_ + 72 * A) if scene.dim == 3 else (128 * N_ + 52 * A)
+        total_alg = ((240 + mat_b) * N_ + 72 * A) if scene.dim == 3 else (128 * N_ + 52 * A)
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic.get(dom), "peak_source": peak_src,
                     "traffic_source": traffic.get("source") if traffic.get(dom) else None,
@@ -361,6 +368,7 @@ def main():
                    "l2": ("inputs larger than L2 (no flush)" if n * (112 if scene.dim == 3 else 52) > 2 * 126e6
                           else "particle state fits in the 126 MB L2 (flagged: HBM fraction is not meaningful)"),
                    "n_oob": n_oob,
+                   "material_layout": (solver if world == 1 else solver.local.solver).material_layout,
                    "parallelism": (f"{world} slabs along x, halo sum over NCCL p2p every substep, migration every "
                                    f"{args.margin} substeps") if world > 1 else "single GPU"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,

@@ -12,7 +12,7 @@ FFMPM_E_INVALID, FFMPM_E_CUDA, FFMPM_E_OOB, FFMPM_E_STATE = -1, -2, -3, -4
 FFMPM_F32, FFMPM_F64 = 0, 1
 FFMPM_NEO_HOOKEAN, FFMPM_SNOW = 0, 1
 FFMPM_P2G_AUTO, FFMPM_P2G_SCATTER, FFMPM_P2G_TILED, FFMPM_P2G_FUSED = 0, 1, 2, 3
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class FfMpmConfig(C.Structure):
@@ -30,7 +30,7 @@ class FfMpmState(C.Structure):
     _fields_ = [
         ("x", C.c_void_p), ("v", C.c_void_p), ("C", C.c_void_p), ("F", C.c_void_p), ("Jp", C.c_void_p),
         ("mass", C.c_void_p), ("mu0", C.c_void_p), ("lam0", C.c_void_p), ("id", C.c_void_p),
-        ("stride", C.c_int64),
+        ("material", C.c_void_p), ("stride", C.c_int64),
     ]
 
 
@@ -56,6 +56,7 @@ PROTOTYPES = {
     "ffmpm_scatter": (C.c_int, [H, C.c_void_p]),
     "ffmpm_gather": (C.c_int, [H, C.c_void_p]),
     "ffmpm_substep": (C.c_int, [H, C.c_int32, C.c_void_p]),
+    "ffmpm_set_materials": (C.c_int, [H, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int32]),
     "ffmpm_set_colliders": (C.c_int, [H, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int32]),
     "ffmpm_collide": (C.c_int, [H, C.c_void_p]),
     "ffmpm_set_owned_range": (C.c_int, [H, C.c_int32, C.c_int32]),

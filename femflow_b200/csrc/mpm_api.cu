@@ -68,6 +68,8 @@ struct FfMpmHandle {
   bool prebinned;     // keys/rank/histogram of the live buffer were emitted by the last reordering G2P
   int p2g_variant;    // see p2g_t (FFMPM_P2G_VARIANT)
   int p2g_blocks_per_sm, g2p_blocks_per_sm;   // persistent-grid sizing (tunable: FFMPM_P2G_BPS / FFMPM_G2P_BPS)
+  void* mat_table;    // device, [3][MAT_ROWS] of the storage type (ffmpm_set_materials)
+  int n_materials;
 };
 
 static size_t elem_size(const FfMpmConfig& c) { return c.dtype == FFMPM_F64 ? 8 : 4; }
@@ -185,6 +187,7 @@ void ffmpm_destroy(FfMpmHandle* h) {
   if (h->aux) { cudaStreamSynchronize(h->aux); cudaStreamDestroy(h->aux); }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->mat_table) cudaFree(h->mat_table);
   delete h;
 }
 
@@ -238,6 +241,7 @@ int ffmpm_bind_state(FfMpmHandle* h, const FfMpmState* cur, const FfMpmState* al
     if (!state_ok(h, alt) || alt->stride != cur->stride) return set_err(FFMPM_E_INVALID, "alt buffer layout mismatch");
     if ((cur->mass != nullptr) != (alt->mass != nullptr) || (cur->mu0 != nullptr) != (alt->mu0 != nullptr) ||
         (cur->lam0 != nullptr) != (alt->lam0 != nullptr) || (cur->id != nullptr) != (alt->id != nullptr) ||
+        (cur->material != nullptr) != (alt->material != nullptr) ||
         (cur->Jp != nullptr) != (alt->Jp != nullptr))
       return set_err(FFMPM_E_INVALID, "alt buffer must carry the same optional planes");
     h->st[1] = *alt;
@@ -249,6 +253,35 @@ int ffmpm_bind_state(FfMpmHandle* h, const FfMpmState* cur, const FfMpmState* al
   h->prebinned = false;
   h->scatter_ahead = false;
   h->grid_clean[0] = h->grid_clean[1] = false;
+  return FFMPM_OK;
+}
+
+int ffmpm_set_materials(FfMpmHandle* h, const double* mass, const double* mu0, const double* lam0, int32_t count) {
+  if (!h) return set_err(FFMPM_E_INVALID, "null handle");
+  if (count < 0 || count > FFMPM_MAX_MATERIALS) return set_err(FFMPM_E_INVALID, "material count must be in [0, 256]");
+  if (count > 0 && (!mass || !mu0 || !lam0)) return set_err(FFMPM_E_INVALID, "null material arrays");
+  static_assert(FFMPM_MAX_MATERIALS == MAT_ROWS, "table rows");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (count > 0) {
+    const size_t es = elem_size(h->cfg);
+    if (!h->mat_table) CUDA_TRY(cudaMalloc(&h->mat_table, 3 * MAT_ROWS * sizeof(double)));
+    alignas(8) unsigned char host[3 * MAT_ROWS * sizeof(double)] = {};
+    const double* rows[3] = {mass, mu0, lam0};
+    for (int r = 0; r < 3; ++r)
+      for (int i = 0; i < count; ++i) {
+        if (es == 8) ((double*)host)[r * MAT_ROWS + i] = rows[r][i];
+        else ((float*)host)[r * MAT_ROWS + i] = (float)rows[r][i];
+      }
+    CUDA_TRY(cudaDeviceSynchronize());   // nothing in flight may still read the old table
+    CUDA_TRY(cudaMemcpy(h->mat_table, host, 3 * MAT_ROWS * es, cudaMemcpyHostToDevice));
+  }
+  h->n_materials = count;
+  h->scatter_ahead = false;
+  // one material: the kernels take it from the config scalars, rounded to the storage type like a plane would be
+  const bool f64 = h->cfg.dtype == FFMPM_F64;
+  h->dev.mass = count == 1 ? (f64 ? mass[0] : (double)(float)mass[0]) : h->cfg.mass;
+  h->dev.mu0 = count == 1 ? (f64 ? mu0[0] : (double)(float)mu0[0]) : h->cfg.mu_0;
+  h->dev.lam0 = count == 1 ? (f64 ? lam0[0] : (double)(float)lam0[0]) : h->cfg.lambda_0;
   return FFMPM_OK;
 }
 
@@ -265,10 +298,15 @@ int ffmpm_set_num_particles(FfMpmHandle* h, int64_t n) {
 }
 
 template <typename T>
-static StateView<T> view(const FfMpmState& s) {
+static StateView<T> view(const FfMpmHandle* h, const FfMpmState& s) {
   StateView<T> v;
   v.x = (T*)s.x; v.v = (T*)s.v; v.C = (T*)s.C; v.F = (T*)s.F; v.Jp = (T*)s.Jp;
   v.mass = (T*)s.mass; v.mu0 = (T*)s.mu0; v.lam0 = (T*)s.lam0; v.id = s.id; v.stride = s.stride;
+  // The row plane is only meaningful with a table (ready() rejects the other combinations).  A one-row
+  // table is served through the config scalars (ffmpm_set_materials overrides them in h->dev): no
+  // per-particle material traffic or lookups at all.
+  v.mat_table = h->n_materials > 1 ? (const T*)h->mat_table : nullptr;
+  v.material = h->n_materials > 1 ? s.material : nullptr;
   return v;
 }
 
@@ -276,6 +314,8 @@ static int ready(FfMpmHandle* h) {
   if (!h) return set_err(FFMPM_E_INVALID, "null handle");
   if (!h->ws) return set_err(FFMPM_E_STATE, "workspace not set");
   if (!h->st[0].x) return set_err(FFMPM_E_STATE, "state not bound");
+  if (h->n_materials > 0 && h->st[0].mass) return set_err(FFMPM_E_STATE, "material table and mass/mu0/lam0 planes are exclusive");
+  if (h->n_materials == 0 && h->st[0].material) return set_err(FFMPM_E_STATE, "material rows bound but no table set (ffmpm_set_materials)");
   cudaError_t e = cudaSetDevice(h->device);  // callable from any host thread (simulation.py:117)
   if (e != cudaSuccess) return set_err(FFMPM_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
   return FFMPM_OK;
@@ -299,7 +339,7 @@ int ffmpm_clear_grid(FfMpmHandle* h, void* stream) {
 template <typename T>
 static int bin_t(FfMpmHandle* h, cudaStream_t s) {
   if (h->n > h->capacity) return set_err(FFMPM_E_STATE, "workspace too small for this particle count");
-  int nl = bin_particles<T>(h->dev, view<T>(h->st[h->live]), h->n, h->bin, h->err, h->prebinned, s);
+  int nl = bin_particles<T>(h->dev, view<T>(h, h->st[h->live]), h->n, h->bin, h->err, h->prebinned, s);
   h->binned = true;
   h->prebinned = false;
   return check_launch(h, nl);
@@ -314,7 +354,7 @@ int ffmpm_bin(FfMpmHandle* h, void* stream) {
 
 template <typename T>
 static int p2g_t(FfMpmHandle* h, cudaStream_t s) {
-  StateView<T> sv = view<T>(h->st[h->live]);
+  StateView<T> sv = view<T>(h, h->st[h->live]);
   int mode = h->cfg.p2g_mode;
   if (mode == FFMPM_P2G_FUSED) mode = FFMPM_P2G_AUTO;
   if (mode == FFMPM_P2G_AUTO) mode = (h->binned && h->cfg.dim == 3) ? FFMPM_P2G_TILED : FFMPM_P2G_SCATTER;
@@ -388,10 +428,10 @@ int ffmpm_grid_op_halo(FfMpmHandle* h, const void* recv_lo, int32_t planes_lo, c
 
 template <typename T>
 static int g2p_t(FfMpmHandle* h, cudaStream_t s) {
-  StateView<T> sv = view<T>(h->st[h->live]);
+  StateView<T> sv = view<T>(h, h->st[h->live]);
   if (h->binned && h->have_alt && h->cfg.dim == 3) {
     // binned: write the particles back in cell order into the other buffer
-    StateView<T> dst = view<T>(h->st[h->live ^ 1]);
+    StateView<T> dst = view<T>(h, h->st[h->live ^ 1]);
     bin_clear_histogram(h->bin, s);   // the kernel pre-bins the advected particles for the next substep
     int nl = g2p_tiled<T>(h->dev, sv, dst, h->n, h->bin, (const T*)h->grid, h->err, h->sm_count, h->g2p_blocks_per_sm, s);
     h->live ^= 1;
@@ -486,7 +526,7 @@ int ffmpm_scatter(FfMpmHandle* h, void* stream) {
 
 template <typename T>
 static int g2p2g_t(FfMpmHandle* h, cudaStream_t s) {
-  StateView<T> sv = view<T>(h->st[h->live]), dst = view<T>(h->st[h->live ^ 1]);
+  StateView<T> sv = view<T>(h, h->st[h->live]), dst = view<T>(h, h->st[h->live ^ 1]);
   bin_clear_histogram(h->bin, s);
   int nl = g2p2g_tiled<T>(h->dev, sv, dst, h->bin, (const T*)h->grid, (T*)h->grids[h->grid_cur ^ 1], h->err, h->sm_count,
                           h->gg_blocks_per_sm, s);
@@ -612,9 +652,9 @@ int ffmpm_snapshot(FfMpmHandle* h, double coeff, double* out, void* stream) {
   unsigned blocks = (unsigned)((h->n + 255) / 256);
   // particle.py:32 divides by coeff (x / coeff != x * (1/coeff) in general): divide on the device too
   if (h->cfg.dtype == FFMPM_F64)
-    snapshot_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>(view<double>(h->st[h->live]), h->n, h->cfg.dim, coeff, out);
+    snapshot_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>(view<double>(h, h->st[h->live]), h->n, h->cfg.dim, coeff, out);
   else
-    snapshot_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(view<float>(h->st[h->live]), h->n, h->cfg.dim, coeff, out);
+    snapshot_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(view<float>(h, h->st[h->live]), h->n, h->cfg.dim, coeff, out);
   return check_launch(h, 1);
 }
 

@@ -30,8 +30,19 @@ template <typename T>
 struct StateView {
   T* x; T* v; T* C; T* F; T* Jp; T* mass; T* mu0; T* lam0;
   int* id;
+  unsigned char* material;   // row of mat_table per particle (nullptr: row 0)
+  const T* mat_table;        // [3][MAT_ROWS]: mass, mu0, lam0 rows; nullptr: planes or config scalars
   long long stride;
 };
+constexpr int MAT_ROWS = 256;
+
+// Where a kernel takes a particle's (mass, mu_0, lambda_0) from (reference Particle, particle.py:7-13).
+enum MatMode { MAT_CFG = 0, MAT_PLANES = 1, MAT_TABLE = 2 };
+template <typename T>
+__host__ __device__ __forceinline__ int mat_mode_of(const StateView<T>& s) {
+  if (s.mat_table) return MAT_TABLE;
+  return (s.mass && s.mu0 && s.lam0) ? MAT_PLANES : MAT_CFG;
+}
 
 // Sticky error record in the workspace: [0] = code, [1] = number of out-of-grid particles.
 struct ErrRec {

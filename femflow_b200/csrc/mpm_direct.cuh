@@ -72,25 +72,32 @@ __device__ __forceinline__ P2GParticle3<T> p2g_prepare3_from(const DevCfg& cfg, 
     q.a20 = (T)A.a20; q.a21 = (T)A.a21; q.a22 = (T)A.a22;
   }
   q.m = (T)mass;
-  q.mvx = (T)(mass * (double)get(P2G_V)); q.mvy = (T)(mass * (double)get(P2G_V + 1)); q.mvz = (T)(mass * (double)get(P2G_V + 2));
+  if (sizeof(T) == 4 && has_mat) {
+    // the product of two floats is exact in fp64, so rounding it once is the fp32 product: same bits, no fp64 pipe
+    q.mvx = q.m * get(P2G_V); q.mvy = q.m * get(P2G_V + 1); q.mvz = q.m * get(P2G_V + 2);
+  } else {
+    q.mvx = (T)(mass * (double)get(P2G_V)); q.mvy = (T)(mass * (double)get(P2G_V + 1)); q.mvz = (T)(mass * (double)get(P2G_V + 2));
+  }
   return q;
 }
 
 template <typename T>
 __device__ __forceinline__ P2GParticle3<T> p2g_prepare3(const DevCfg& cfg, const StateView<T>& s, long long p) {
   const long long st = s.stride;
+  const int mode = mat_mode_of(s);
+  const int row = (mode == MAT_TABLE && s.material) ? (int)s.material[p] : 0;
   auto get = [&](int k) -> T {
     if (k < P2G_V) return s.x[k * st + p];
     if (k < P2G_C) return s.v[(k - P2G_V) * st + p];
     if (k < P2G_F) return s.C[(k - P2G_C) * st + p];
     if (k < P2G_MASS) return s.F[(k - P2G_F) * st + p];
+    if (mode == MAT_TABLE) return s.mat_table[(k - P2G_MASS) * MAT_ROWS + row];
     if (k == P2G_MASS) return s.mass[p];
     if (k == P2G_MU) return s.mu0[p];
     return s.lam0[p];
   };
-  const bool has_mat = s.mass != nullptr && s.mu0 != nullptr && s.lam0 != nullptr;
   const double jp = cfg.model == 1 ? (double)s.Jp[p] : 1.0;
-  return p2g_prepare3_from<T>(cfg, get, has_mat, jp);
+  return p2g_prepare3_from<T>(cfg, get, mode != MAT_CFG, jp);
 }
 
 template <typename T>
@@ -114,9 +121,14 @@ __device__ __forceinline__ P2GParticle2<T> p2g_prepare2(const DevCfg& cfg, const
   // The 2D reference has no bounds check (UB there); we flag and skip instead.
   q.ok = !(isnan((double)x0) || isnan((double)x1)) && q.bx >= 0 && q.by >= 0 && q.bx + 2 < cfg.n[0] && q.by + 2 < cfg.n[1];
   if (!q.ok) return q;
-  double mass = s.mass ? (double)s.mass[p] : cfg.mass;
-  double mu = (s.mu0 ? (double)s.mu0[p] : cfg.mu0);
-  double lam = (s.lam0 ? (double)s.lam0[p] : cfg.lam0);
+  double mass = cfg.mass, mu = cfg.mu0, lam = cfg.lam0;
+  const int mode = mat_mode_of(s);
+  if (mode == MAT_TABLE) {
+    const int row = s.material ? (int)s.material[p] : 0;
+    mass = (double)s.mat_table[row]; mu = (double)s.mat_table[MAT_ROWS + row]; lam = (double)s.mat_table[2 * MAT_ROWS + row];
+  } else if (mode == MAT_PLANES) {
+    mass = (double)s.mass[p]; mu = (double)s.mu0[p]; lam = (double)s.lam0[p];
+  }
   double e = cfg.hardening;
   if (cfg.model == 1) e = exp(cfg.hardening * (1.0 - (double)s.Jp[p]));
   mu *= e; lam *= e;

@@ -40,7 +40,8 @@ g2p2g_tiled3_kernel(DevCfg cfg, StateView<T> src, StateView<T> dst, BinBuffers B
   const long long ss = src.stride, ds = dst.stride;
   const int ny = cfg.n[1], nz = cfg.n[2];
   const T dxs = (T)cfg.dx;
-  const bool has_mat = src.mass != nullptr && src.mu0 != nullptr && src.lam0 != nullptr;
+  const int mat_mode = mat_mode_of(src);
+  const bool has_mat = mat_mode != MAT_CFG;
 
   for (;;) {
     __syncthreads();
@@ -93,6 +94,11 @@ g2p2g_tiled3_kernel(DevCfg cfg, StateView<T> src, StateView<T> dst, BinBuffers B
           if (src.lam0) cl = src.lam0[p];
           if (src.id) cid = src.id[p];
           if (src.Jp) cjp = src.Jp[p];
+          unsigned char row = 0;
+          if (src.material) row = src.material[p];
+          if (mat_mode == MAT_TABLE) {
+            cm = src.mat_table[row]; cmu = src.mat_table[MAT_ROWS + row]; cl = src.mat_table[2 * MAT_ROWS + row];
+          }
           const T x0 = src.x[p], x1 = src.x[ss + p], x2 = src.x[2 * ss + p];
           const T f00 = src.F[0 * ss + p], f01 = src.F[1 * ss + p], f02 = src.F[2 * ss + p];
           const T f10 = src.F[3 * ss + p], f11 = src.F[4 * ss + p], f12 = src.F[5 * ss + p];
@@ -137,6 +143,7 @@ g2p2g_tiled3_kernel(DevCfg cfg, StateView<T> src, StateView<T> dst, BinBuffers B
           if (src.lam0) dst.lam0[slot] = cl;
           if (src.id) dst.id[slot] = cid;
           if (src.Jp) dst.Jp[slot] = cjp;
+          if (src.material) dst.material[slot] = row;
           next_key = bin_key_of<T>(cfg, B, o[0], o[1], o[2]);
           B.keys[slot] = next_key;
           // ---- P2G of the next substep, phase 1, from registers ----

@@ -19,6 +19,7 @@ template <int NBUF>
 struct P2GBulkWarp {
   alignas(128) float raw[NBUF][P2G_NPLANES][P2G_WINDOW];
   P2GWarpSlab<float> slab;
+  alignas(16) unsigned char mat[NBUF][P2G_WINDOW];   // material rows of the window (table mode)
   alignas(8) unsigned long long bar[NBUF];
 };
 
@@ -56,7 +57,9 @@ __device__ __forceinline__ void bulk_load_s(void* sdst, const void* gsrc, unsign
 // instructions in profiles/r01_final before this).
 struct P2GPlanes {
   const float* p[P2G_NPLANES];
-  int n;
+  int n;                           // planes to prefetch: 27 with material planes, else 24
+  const unsigned char* material;   // table mode: row per particle (nullptr: row 0)
+  const float* table;              // table mode: [3][MAT_ROWS]
 };
 
 inline P2GPlanes p2g_planes_of(const StateView<float>& s) {
@@ -65,7 +68,10 @@ inline P2GPlanes p2g_planes_of(const StateView<float>& s) {
   for (int k = 0; k < 3; ++k) { P.p[P2G_X + k] = s.x + k * st; P.p[P2G_V + k] = s.v + k * st; }
   for (int k = 0; k < 9; ++k) { P.p[P2G_C + k] = s.C + k * st; P.p[P2G_F + k] = s.F + k * st; }
   P.p[P2G_MASS] = s.mass; P.p[P2G_MU] = s.mu0; P.p[P2G_LAM] = s.lam0;
-  P.n = (s.mass && s.mu0 && s.lam0) ? P2G_NPLANES : P2G_MASS;
+  const int mode = mat_mode_of(s);
+  P.n = mode == MAT_PLANES ? P2G_NPLANES : P2G_MASS;
+  P.material = mode == MAT_TABLE ? s.material : nullptr;
+  P.table = mode == MAT_TABLE ? s.mat_table : nullptr;
   return P;
 }
 
@@ -89,7 +95,7 @@ p2g_bulk3_kernel(DevCfg cfg, P2GPlanes planes, long long n, float* __restrict__ 
   const T dx = (T)cfg.dx;
   const int ny = cfg.n[1], nz = cfg.n[2];
   const int n_planes = planes.n;
-  const bool has_mat = n_planes == P2G_NPLANES;
+  const bool has_mat = n_planes == P2G_NPLANES || planes.table != nullptr;
   const int n_windows = (int)((n + P2G_WINDOW - 1) / P2G_WINDOW);
   // wpw > 0: every warp owns `wpw` consecutive windows and the CTA retires after them (a finite
   // grid lets the block scheduler interleave CTAs of kernels running on other streams);
@@ -116,13 +122,16 @@ p2g_bulk3_kernel(DevCfg cfg, P2GPlanes planes, long long n, float* __restrict__ 
         const int k = hi ? k1 : k0;
         if (k < n_planes) cp_async16(&W.raw[buf][k][(lane & 15) * 4], src + w0);
       }
+      if (planes.material && lane < P2G_WINDOW / 16)
+        cp_async16(&W.mat[buf][lane * 16], planes.material + (long long)win * P2G_WINDOW + lane * 16);
       asm volatile("cp.async.commit_group;" ::: "memory");
       return;
     }
     // one lane posts the whole window: n_planes x 256 B
     if (lane == 0) {
-      mbar_expect_tx(&W.bar[buf], (unsigned)n_planes * P2G_WINDOW * 4u);
+      mbar_expect_tx(&W.bar[buf], (unsigned)n_planes * P2G_WINDOW * 4u + (planes.material ? (unsigned)P2G_WINDOW : 0u));
       const long long w0 = (long long)win * P2G_WINDOW;
+      if (planes.material) bulk_load_s(&W.mat[buf][0], planes.material + w0, P2G_WINDOW, &W.bar[buf]);
 #pragma unroll
       for (int k = 0; k < P2G_NPLANES; ++k)
         if (k < n_planes) bulk_load_s(&W.raw[buf][k][0], planes.p[k] + w0, P2G_WINDOW * 4u, &W.bar[buf]);
@@ -151,7 +160,14 @@ p2g_bulk3_kernel(DevCfg cfg, P2GPlanes planes, long long n, float* __restrict__ 
       const int idx = h * 32 + lane;
       node[h] = -1;
       if (idx < cnt) {
-        P2GParticle3<T> q = p2g_prepare3_from<T>(cfg, [&](int k) -> T { return W.raw[buf][k][idx]; }, has_mat, 1.0);
+        const int row = planes.material ? (int)W.mat[buf][idx] : 0;
+        P2GParticle3<T> q = p2g_prepare3_from<T>(
+            cfg,
+            [&](int k) -> T {
+              if (k >= P2G_MASS && planes.table) return __ldg(planes.table + (k - P2G_MASS) * MAT_ROWS + row);
+              return W.raw[buf][k][idx];
+            },
+            has_mat, 1.0);
         node[h] = p2g_park(S, q, idx, dx, ny, nz);
       }
     }
@@ -192,7 +208,7 @@ static bool p2g_bulk_launch(const DevCfg& cfg, const StateView<float>& s, long l
 inline bool p2g_bulk_eligible(const DevCfg& cfg, const StateView<float>& s) {
   if (cfg.model != 0 || cfg.dim != 3) return false;
   if ((s.stride % P2G_WINDOW) != 0) return false;
-  const void* planes[] = {s.x, s.v, s.C, s.F, s.mass, s.mu0, s.lam0};
+  const void* planes[] = {s.x, s.v, s.C, s.F, s.mass, s.mu0, s.lam0, s.material};
   for (const void* q : planes)
     if (((uintptr_t)q & 15) != 0) return false;
   return true;

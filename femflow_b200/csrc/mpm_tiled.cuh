@@ -32,10 +32,11 @@ __device__ __forceinline__ void carry_planes(const StateView<T>& src, const Stat
   if (src.mu0) dst.mu0[slot] = src.mu0[p];
   if (src.lam0) dst.lam0[slot] = src.lam0[p];
   if (src.id) dst.id[slot] = src.id[p];
+  if (src.material) dst.material[slot] = src.material[p];
   if (with_jp && src.Jp) dst.Jp[slot] = src.Jp[p];
 }
 
-constexpr int G2P_PRE_PLANES = 17;   // x3 F9 mass mu0 lam0 id Jp
+constexpr int G2P_PRE_PLANES = 17;   // x3 F9 mass mu0 lam0 id Jp (+ the word holding the material row: ROWS)
 
 __device__ __forceinline__ void cp_async4(void* sdst, const void* gsrc) {
   unsigned d = (unsigned)__cvta_generic_to_shared(sdst);
@@ -46,14 +47,16 @@ __device__ __forceinline__ void cp_async4(void* sdst, const void* gsrc) {
 // into shared memory with 4-byte cp.async (the gather through `perm` rules out bulk copies)
 // while the current round computes; the permutation entry itself is fetched two rounds
 // ahead.  Each thread only ever reads what it copied itself, so no barrier is involved.
-template <typename T, int MIN_BLOCKS, bool PRE = false>
+// ROWS: the state carries 1-byte material rows (table mode); compiled out otherwise, the kernel sits
+// exactly at its 64-register budget.
+template <typename T, int MIN_BLOCKS, bool PRE = false, bool ROWS = false>
 __global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_tiled3_kernel(DevCfg cfg, StateView<T> src, StateView<T> dst,
                                                                  BinBuffers B, const T* __restrict__ grid, ErrRec* err) {
   using V4 = typename Vec4<T>::type;
   __shared__ V4 tile[TNODES3];
   __shared__ int s_work;
   static_assert(!PRE || sizeof(T) == 4, "the cp.async prefetch is for the fp32 build");
-  __shared__ __align__(16) float pre[PRE ? 2 : 1][PRE ? G2P_PRE_PLANES : 1][PRE ? G2P_THREADS : 1];
+  __shared__ __align__(16) float pre[PRE ? 2 : 1][PRE ? G2P_PRE_PLANES + (ROWS ? 1 : 0) : 1][PRE ? G2P_THREADS : 1];
   int pre_buf = 0;
   const int n_active = B.counters[0];
   const long long ss = src.stride, ds = dst.stride;
@@ -108,6 +111,8 @@ __global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_tiled3_kernel(Dev
           if (src.lam0) cp_async4(&pre[buf][14][tid], src.lam0 + q);
           if (src.id) cp_async4(&pre[buf][15][tid], src.id + q);
           if (src.Jp) cp_async4(&pre[buf][16][tid], src.Jp + q);
+          // a row is 1 byte, cp.async moves >= 4: fetch the aligned word around it
+          if constexpr (ROWS) cp_async4(&pre[buf][G2P_PRE_PLANES][tid], src.material + (q & ~3));
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
       }
@@ -131,6 +136,7 @@ __global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_tiled3_kernel(Dev
       T o[24];
       T cm = 0, cmu = 0, cl = 0, cjp = 0;
       int cid = 0;
+      unsigned row = 0;
       int q_nn = -1;
       if constexpr (PRE) {
         const bool more = rbase + G2P_THREADS < end;
@@ -156,6 +162,7 @@ __global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_tiled3_kernel(Dev
           if (src.lam0) cl = pb[14][tid];
           if (src.id) cid = __float_as_int(pb[15][tid]);
           if (src.Jp) cjp = pb[16][tid];
+          if constexpr (ROWS) row = (__float_as_uint(pb[G2P_PRE_PLANES][tid]) >> ((q_cur & 3) * 8)) & 0xffu;
         } else {
           const long long p = B.perm[slot];
           // carried planes first: their latency hides behind the gather
@@ -164,6 +171,7 @@ __global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_tiled3_kernel(Dev
           if (src.lam0) cl = src.lam0[p];
           if (src.id) cid = src.id[p];
           if (src.Jp) cjp = src.Jp[p];
+          if constexpr (ROWS) row = src.material[p];
           x0 = src.x[p]; x1 = src.x[ss + p]; x2 = src.x[2 * ss + p];
           f00 = src.F[0 * ss + p]; f01 = src.F[1 * ss + p]; f02 = src.F[2 * ss + p];
           f10 = src.F[3 * ss + p]; f11 = src.F[4 * ss + p]; f12 = src.F[5 * ss + p];
@@ -218,6 +226,7 @@ __global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_tiled3_kernel(Dev
           if (src.lam0) dst.lam0[slot] = cl;
           if (src.id) dst.id[slot] = cid;
           if (src.Jp) dst.Jp[slot] = cjp;
+          if constexpr (ROWS) dst.material[slot] = (unsigned char)row;
         }
       }
       // next substep's histogram + within-cell rank (same scheme as bin_count_kernel)
@@ -239,12 +248,19 @@ int g2p_tiled(const DevCfg& cfg, const StateView<T>& src, const StateView<T>& ds
   if constexpr (sizeof(T) == 4) {
     // FFMPM_G2P_PRE=0 disables the cp.async input prefetch (64 registers, 8 CTAs per SM either way)
     static int prefetch = [] { const char* e = getenv("FFMPM_G2P_PRE"); return e ? atoi(e) : 1; }();
-    if (prefetch)
-      g2p_tiled3_kernel<T, 8, true><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
+    const bool rows = src.material != nullptr;
+    if (prefetch && rows)
+      g2p_tiled3_kernel<T, 8, true, true><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
+    else if (prefetch)
+      g2p_tiled3_kernel<T, 8, true, false><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
+    else if (rows)
+      g2p_tiled3_kernel<T, 8, false, true><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
     else
-      g2p_tiled3_kernel<T, 8, false><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
+      g2p_tiled3_kernel<T, 8, false, false><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
+  } else if (src.material) {
+    g2p_tiled3_kernel<T, 4, false, true><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
   } else {
-    g2p_tiled3_kernel<T, 4, false><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
+    g2p_tiled3_kernel<T, 4, false, false><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
   }
   return 1;
 }

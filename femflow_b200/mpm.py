@@ -35,6 +35,8 @@ class _StateBuffer:
     def __init__(self, dim, cap, dtype, device, per_particle_material, with_id, with_jp):
         d = dim
         self.cap = cap
+        self.dtype, self.device = dtype, device
+        self.material = None      # uint8 rows of the material table (MpmSolver._set_material_layout)
         self.x = torch.zeros((d, cap), dtype=dtype, device=device)
         self.v = torch.zeros((d, cap), dtype=dtype, device=device)
         self.C = torch.zeros((d * d, cap), dtype=dtype, device=device)
@@ -52,11 +54,28 @@ class _StateBuffer:
         def p(t):
             return None if t is None else t.data_ptr()
         return N.FfMpmState(p(self.x), p(self.v), p(self.C), p(self.F), p(self.Jp), p(self.mass), p(self.mu0),
-                            p(self.lam0), p(self.id), self.cap)
+                            p(self.lam0), p(self.id), p(self.material), self.cap)
 
     def nbytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in
-                   (self.x, self.v, self.C, self.F, self.Jp, self.mass, self.mu0, self.lam0, self.id) if t is not None)
+                   (self.x, self.v, self.C, self.F, self.Jp, self.mass, self.mu0, self.lam0, self.id, self.material)
+                   if t is not None)
+
+    def set_material_storage(self, kind: str) -> None:
+        """``planes``: three scalar planes; ``rows``: one uint8 plane; ``none``: neither."""
+        if kind == "planes":
+            if self.mass is None:
+                self.mass = torch.zeros((self.cap,), dtype=self.dtype, device=self.device)
+                self.mu0 = torch.zeros((self.cap,), dtype=self.dtype, device=self.device)
+                self.lam0 = torch.zeros((self.cap,), dtype=self.dtype, device=self.device)
+            self.material = None
+        else:
+            self.mass = self.mu0 = self.lam0 = None
+            if kind == "rows":
+                if self.material is None:
+                    self.material = torch.zeros((self.cap,), dtype=torch.uint8, device=self.device)
+            else:
+                self.material = None
 
 
 class MpmSolver:
@@ -89,8 +108,15 @@ class MpmSolver:
         self.origin = [int(o) for o in origin] + [0] * (3 - len(origin))
         self.capacity = (int(capacity) + 63) // 64 * 64      # plane stride: 16-byte aligned plane segments
         self.model = model
+        # Per-particle material (reference Particle.mass / mu_0 / lambda_0): True = three scalar planes,
+        # False = the config scalars, None (3D default) = chosen from the data in set_particles: a
+        # <= 256-row table + 1-byte rows (no row plane at all for a single material), else planes.
+        self._material_auto = per_particle_material is None and self.dim == 3
+        self.material_layout = "config"
         if per_particle_material is None:
-            per_particle_material = self.dim == 3
+            per_particle_material = False
+        if per_particle_material:
+            self.material_layout = "planes"
         if reorder is None:
             reorder = self.dim == 3 and p2g_mode != "scatter"
         self.reorder = bool(reorder)
@@ -181,16 +207,55 @@ class MpmSolver:
         b.C[:, :n] = 0 if C_ is None else _as_tensor(C_, self.dtype, self.device).reshape(n, d * d).t()
         if b.Jp is not None:
             b.Jp[:n] = 1 if Jp is None else _as_tensor(Jp, self.dtype, self.device).reshape(n)
-        if b.mass is not None:
+        if self._material_auto or b.mass is not None:
+            given = {}
             for name, val in (("mass", mass), ("mu0", mu0), ("lam0", lam0)):
                 if val is None:
                     raise ValueError(f"per-particle {name} is required")
-                t = _as_tensor(np.broadcast_to(np.asarray(val, dtype=np.float64), (n,)) if not isinstance(val, torch.Tensor) else val,
-                               self.dtype, self.device).reshape(n)
-                getattr(b, name)[:n] = t
+                given[name] = _as_tensor(np.broadcast_to(np.asarray(val, dtype=np.float64), (n,))
+                                         if not isinstance(val, torch.Tensor) else val, self.dtype, self.device).reshape(n)
+            if self._material_auto:
+                self._choose_material_layout(given, n)
+            if b.mass is not None:
+                for name, t in given.items():
+                    getattr(b, name)[:n] = t
         if b.id is not None:
             b.id[:n] = torch.arange(n, dtype=torch.int32, device=self.device)
         self._bind(n)
+
+    def set_materials(self, mass, mu0, lam0) -> None:
+        """Material table (``ffmpm_set_materials``): row ``i`` = ``(mass[i], mu0[i], lam0[i])``."""
+        arrs = [np.ascontiguousarray(a, dtype=np.float64).reshape(-1) for a in (mass, mu0, lam0)]
+        dp = C.POINTER(C.c_double)
+        N.check(self.lib.ffmpm_set_materials(self._h, *(a.ctypes.data_as(dp) for a in arrs), len(arrs[0])))
+
+    def _choose_material_layout(self, given: Dict[str, torch.Tensor], n: int) -> None:
+        """Pick the cheapest exact representation of the per-particle (mass, mu0, lam0) triples."""
+        trip = torch.stack([given["mass"], given["mu0"], given["lam0"]], 1)
+        rows = inv = None
+        if n == 0:
+            rows = torch.tensor([[self.cfg.mass, self.cfg.mu_0, self.cfg.lambda_0]], dtype=self.dtype, device=self.device)
+        elif bool((trip == trip[0]).all()):
+            rows = trip[:1]
+        else:
+            u, i = torch.unique(trip, dim=0, return_inverse=True)
+            if u.shape[0] <= 256:
+                rows, inv = u, i
+        if rows is None:
+            kind = "planes"
+        else:
+            kind = "rows" if inv is not None else "none"
+        for b in self.buffers:
+            b.set_material_storage(kind)
+        if rows is None:
+            N.check(self.lib.ffmpm_set_materials(self._h, None, None, None, 0))
+            self.material_layout = "planes"
+        else:
+            r = rows.double().cpu().numpy()
+            self.set_materials(r[:, 0], r[:, 1], r[:, 2])
+            if inv is not None:
+                self.buffers[0].material[:n] = inv.to(torch.uint8)
+            self.material_layout = f"table[{rows.shape[0]}]"
 
     def get_particles(self) -> Dict[str, torch.Tensor]:
         """State in the ORIGINAL particle order, reference layouts, device tensors."""

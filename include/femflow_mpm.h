@@ -16,6 +16,8 @@
  *   ffmpm_bin          (new) cell binning of base_coord, three_d/p2g.py:50
  *   ffmpm_poll_error   the RuntimeError of three_d/p2g.py:51-52,70-71, g2p.py:23-24,35-36
  *   ffmpm_snapshot     femflow/solvers/mpm/particle.py:30-33   map_particles_to_pos
+ *   ffmpm_set_materials
+ *                      femflow/solvers/mpm/particle.py:7-13  Particle.mass / mu_0 / lambda_0
  *   ffmpm_set_colliders / ffmpm_collide
  *                      femflow/solvers/mpm/three_d/grid_op.py:50-67  check_collision_points
  *   ffmpm_scatter / ffmpm_gather / ffmpm_grid_op_halo
@@ -45,7 +47,7 @@
 extern "C" {
 #endif
 
-#define FFMPM_ABI_VERSION 1
+#define FFMPM_ABI_VERSION 2
 
 enum {
   FFMPM_OK = 0,
@@ -95,6 +97,8 @@ typedef struct FfMpmState {
   void* mu0;      /* 1 plane, or NULL -> cfg.mu_0     */
   void* lam0;     /* 1 plane, or NULL -> cfg.lambda_0 */
   int32_t* id;    /* original particle index (carried through reordering), or NULL */
+  uint8_t* material; /* 1 byte per particle: row of the ffmpm_set_materials table; NULL -> row 0.
+                      * Only read once a table is set, and then mass/mu0/lam0 must be NULL. */
   int64_t stride; /* elements between consecutive component planes (>= n)   */
 } FfMpmState;
 
@@ -150,6 +154,16 @@ int ffmpm_scatter(FfMpmHandle* h, void* stream);
 int ffmpm_gather(FfMpmHandle* h, void* stream);
 /* n_substeps x (scatter, grid_op, gather). */
 int ffmpm_substep(FfMpmHandle* h, int32_t n_substeps, void* stream);
+
+/* Material table (femflow/solvers/mpm/particle.py:7-13: every Particle carries mass, mu_0 and
+ * lambda_0, but a scene only ever holds a handful of distinct triples -- one per mesh in
+ * simulation.py:92-104).  With a table set, particles name their triple by a 1-byte row index
+ * (FfMpmState.material) instead of three scalar planes: 1 instead of 12 bytes read by P2G and
+ * 2 instead of 24 moved by the reordering G2P, bit-identical results.  `mass`, `mu0`, `lam0`:
+ * HOST arrays of `count` doubles (rounded to the storage type like the planes would be);
+ * 1 <= count <= FFMPM_MAX_MATERIALS, count == 0 removes the table.  Synchronous. */
+#define FFMPM_MAX_MATERIALS 256
+int ffmpm_set_materials(FfMpmHandle* h, const double* mass, const double* mu0, const double* lam0, int32_t count);
 
 /* Plane colliders (femflow/solvers/mpm/three_d/grid_op.py:50-67 check_collision_points, unused
  * by the reference's driver): every node with dot(I*dx - point, normal + 1/|normal|) < 0 for

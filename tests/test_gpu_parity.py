@@ -336,6 +336,58 @@ def test_multi_substep_pipelines_vs_oracle(mode):
     s.close()
 
 
+@pytest.mark.parametrize("n_materials", [1, 3, 300])
+@pytest.mark.parametrize("mode", ["auto", "fused", "scatter"])
+def test_material_layouts_agree(n_materials, mode):
+    """Particle.mass / mu_0 / lambda_0 (particle.py:7-13) as a material table + 1-byte rows (chosen
+    automatically for <= 256 distinct triples; no row plane at all for one) feeds the kernels the same
+    values as three scalar planes, through reordering, pre-binning and the prefetching kernels; more
+    than 256 triples fall back to planes.  Both layouts are pinned to the oracle (1e-5 per substep);
+    against each other they may only differ by the order of the fp32 grid atomics (1e-6 per substep)."""
+    from femflow_b200 import scenes
+    from femflow_b200.mpm import MpmSolver
+    from oracle import native as ON
+    sc = scenes.elastic_block(3, 64, 20, 2, seed=5)
+    n = sc.n
+    rng = np.random.default_rng(7)
+    row = rng.integers(0, n_materials, n)
+    scale = 1.0 + 0.5 * np.arange(n_materials) / max(n_materials, 1)
+    m = (sc.mass * scale[row]).astype(np.float32).astype(np.float64)
+    mu = (sc.mu_0 * scale[::-1][row]).astype(np.float32).astype(np.float64)
+    lam = (sc.lambda_0 * scale[row]).astype(np.float32).astype(np.float64)
+    outs = {}
+    for ppm in (None, True):
+        s = MpmSolver(3, sc.res, sc.dt, sc.volume, sc.gravity, sc.hardening, capacity=n, p2g_mode=mode,
+                      per_particle_material=ppm)
+        s.set_particles(sc.x, sc.v, sc.F, sc.C, None, m, mu, lam)
+        if ppm is None:
+            want = "planes" if n_materials > 256 else f"table[{n_materials}]"
+            assert s.material_layout == want
+            assert (s.buffers[0].material is not None) == (1 < n_materials <= 256)
+            assert (s.buffers[0].mass is not None) == (n_materials > 256)
+        else:
+            assert s.material_layout == "planes"
+        for chunk in (1, 2, 4):
+            s.substep(chunk)
+        s.check_errors()
+        outs[ppm] = {k: t.cpu().numpy() for k, t in s.get_particles().items()}
+        s.close()
+    x, v, F, C = (a.astype(np.float64) for a in (sc.x, sc.v, sc.F, sc.C))
+    for _ in range(7):
+        ON.solve_mls_mpm_3d(sc.res, float(sc.res), sc.hardening, 1 / sc.res, sc.dt, sc.volume, sc.gravity,
+                            x, m, mu, lam, v, F, C)
+    V = max(np.abs(v).max(), sc.dt * 9.8)
+    for o in outs.values():
+        assert rel_err(o["x"].astype(np.float64), x, 1.0) < 7e-5
+        assert np.abs(o["v"] - v).max() / V < 7e-5
+        assert rel_err(o["F"].astype(np.float64), F, 1.0) < 7e-5
+        assert np.abs(o["C"] - C).max() / (4 * sc.res * V) < 7e-5
+    a, b = outs[None], outs[True]
+    assert np.abs(a["x"] - b["x"]).max() < 7e-6
+    assert np.abs(a["v"] - b["v"]).max() / V < 7e-6
+    assert np.abs(a["F"] - b["F"]).max() < 7e-6
+
+
 def test_collision_planes(dtype):
     """Plane colliders fused into the grid update vs the reference (three_d/grid_op.py:50-67)."""
     from femflow_b200.solvers.mpm import three_d
@@ -388,11 +440,19 @@ def test_c_abi_error_codes():
     assert lib.ffmpm_substep(h, 1, stream) == N.FFMPM_E_STATE                            # state not bound
     planes = {k: torch.zeros((m, 1024), device="cuda") for k, m in (("x", 3), ("v", 3), ("C", 9), ("F", 9))}
     st = N.FfMpmState(planes["x"].data_ptr(), planes["v"].data_ptr(), planes["C"].data_ptr(), planes["F"].data_ptr(),
-                      None, planes["x"].data_ptr(), None, None, None, 1024)               # mass without mu0/lam0
+                      None, planes["x"].data_ptr(), None, None, None, None, 1024)         # mass without mu0/lam0
     assert lib.ffmpm_bind_state(h, C.byref(st), None, 10) == N.FFMPM_E_INVALID
     st = N.FfMpmState(planes["x"].data_ptr(), planes["v"].data_ptr(), planes["C"].data_ptr(), planes["F"].data_ptr(),
-                      None, None, None, None, None, 1024)
+                      None, None, None, None, None, None, 1024)
     assert lib.ffmpm_bind_state(h, C.byref(st), None, 2000) == N.FFMPM_E_INVALID         # n > stride
+    rows = torch.zeros(1024, dtype=torch.uint8, device="cuda")
+    st.material = rows.data_ptr()
+    assert lib.ffmpm_bind_state(h, C.byref(st), None, 10) == 0
+    assert lib.ffmpm_substep(h, 1, stream) == N.FFMPM_E_STATE                            # rows without a table
+    one = (C.c_double * 1)(1.0)
+    assert lib.ffmpm_set_materials(h, one, one, one, 257) == N.FFMPM_E_INVALID           # > FFMPM_MAX_MATERIALS
+    assert lib.ffmpm_set_materials(h, None, one, one, 1) == N.FFMPM_E_INVALID
+    st.material = None
     assert lib.ffmpm_bind_state(h, C.byref(st), None, 10) == 0
     planes["F"][[0, 4, 8], :10] = 1.0
     planes["x"][:, :10] = 0.5
