@@ -265,7 +265,7 @@ class CudaSlab(LocalSlab):
         self.solver = MpmSolver(3, list(plan.res), dt, volume, gravity, hardening, capacity=capacity, dx=dx,
                                 inv_dx=1.0 / dx, dtype=dtype, device=device,
                                 n_nodes=(plan.n_local_x, plan.res[1] + 1, plan.res[2] + 1),
-                                origin=(plan.g_lo, 0, 0), per_particle_material=True, p2g_mode=p2g_mode, reorder=True)
+                                origin=(plan.g_lo, 0, 0), per_particle_material=None, p2g_mode=p2g_mode, reorder=True)
         # the binned G2P counts the particles that left [own_lo, own_hi) while it advects them
         self.solver.set_owned_range(plan.own_lo if plan.rank > 0 else -(2 ** 31),
                                     plan.own_hi if plan.rank < plan.world - 1 else 2 ** 31 - 1)
@@ -276,8 +276,20 @@ class CudaSlab(LocalSlab):
         return self.solver.num_particles
 
     def set_particles(self, x, v, F, C_, mass, mu0, lam0, ids) -> None:
+        """Collective when torch.distributed is initialised: the ranks agree on ONE material table
+        (the union of their distinct (mass, mu0, lam0) triples), so a migrating particle's row index
+        means the same thing on the receiving rank."""
         s = self.solver
-        s.set_particles(x, v, F, C_, None, mass, mu0, lam0)
+        n = len(x)
+        trip = np.stack([np.broadcast_to(np.asarray(a, dtype=np.float64), (n,)) for a in (mass, mu0, lam0)], 1)
+        np_dt = np.float64 if self.dtype == torch.float64 else np.float32
+        mine = np.unique(trip.astype(np_dt), axis=0)[:257]
+        also = mine
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            parts = [None] * dist.get_world_size()
+            dist.all_gather_object(parts, mine)
+            also = np.unique(np.concatenate([p.reshape(-1, 3) for p in parts], 0), axis=0)
+        s.set_particles(x, v, F, C_, None, mass, mu0, lam0, also_materials=also)
         s.buffers[0].id[:s.num_particles] = torch.as_tensor(np.asarray(ids), device=self.device).to(torch.int32)
 
     def scatter(self) -> None:
@@ -299,7 +311,16 @@ class CudaSlab(LocalSlab):
         return 3 + 3 + 9 + 9 + 3
 
     def _pack(self, b, idx):
-        rows = [b.x[:, idx], b.v[:, idx], b.C[:, idx], b.F[:, idx], b.mass[idx][None], b.mu0[idx][None], b.lam0[idx][None]]
+        """27 payload rows: x v C F, then the material -- (mass, mu0, lam0) with planes; with a table
+        the row index (exact as a float, the table is the same on every rank) and two unused rows."""
+        rows = [b.x[:, idx], b.v[:, idx], b.C[:, idx], b.F[:, idx]]
+        if b.mass is not None:
+            rows += [b.mass[idx][None], b.mu0[idx][None], b.lam0[idx][None]]
+        else:
+            mat = torch.zeros((3, idx.numel()), dtype=b.x.dtype, device=b.x.device)
+            if b.material is not None:
+                mat[0] = b.material[idx].to(b.x.dtype)
+            rows.append(mat)
         return torch.cat(rows, 0), b.id[idx]
 
     def extract_leavers(self, own_lo: int, own_hi: int):
@@ -373,9 +394,12 @@ class CudaSlab(LocalSlab):
         b.v[:, at:at + k] = data[3:6]
         b.C[:, at:at + k] = data[6:15]
         b.F[:, at:at + k] = data[15:24]
-        b.mass[at:at + k] = data[24]
-        b.mu0[at:at + k] = data[25]
-        b.lam0[at:at + k] = data[26]
+        if b.mass is not None:
+            b.mass[at:at + k] = data[24]
+            b.mu0[at:at + k] = data[25]
+            b.lam0[at:at + k] = data[26]
+        elif b.material is not None:
+            b.material[at:at + k] = data[24].to(torch.uint8)
         b.id[at:at + k] = ids
 
     def append(self, payload) -> None:

@@ -113,6 +113,7 @@ class MpmSolver:
         # <= 256-row table + 1-byte rows (no row plane at all for a single material), else planes.
         self._material_auto = per_particle_material is None and self.dim == 3
         self.material_layout = "config"
+        self.material_table = None     # (R, 3) rows of the table in effect
         if per_particle_material is None:
             per_particle_material = False
         if per_particle_material:
@@ -189,9 +190,11 @@ class MpmSolver:
         return C.c_void_p(stream.cuda_stream)
 
     # ------------------------------------------------------------------ #
-    def set_particles(self, x, v=None, F=None, C_=None, Jp=None, mass=None, mu0=None, lam0=None) -> None:
+    def set_particles(self, x, v=None, F=None, C_=None, Jp=None, mass=None, mu0=None, lam0=None,
+                      also_materials=None) -> None:
         """Upload particle state given in the reference's layouts: ``x, v (N, d)``,
-        ``F, C (N, d, d)``, ``Jp (N, 1)``; per-particle ``mass, mu0, lam0 (N,)``."""
+        ``F, C (N, d, d)``, ``Jp (N, 1)``; per-particle ``mass, mu0, lam0 (N,)``.
+        ``also_materials``: see ``_choose_material_layout``."""
         d = self.dim
         x = _as_tensor(x, self.dtype, self.device).reshape(-1, d)
         n = x.shape[0]
@@ -215,7 +218,7 @@ class MpmSolver:
                 given[name] = _as_tensor(np.broadcast_to(np.asarray(val, dtype=np.float64), (n,))
                                          if not isinstance(val, torch.Tensor) else val, self.dtype, self.device).reshape(n)
             if self._material_auto:
-                self._choose_material_layout(given, n)
+                self._choose_material_layout(given, n, also_materials)
             if b.mass is not None:
                 for name, t in given.items():
                     getattr(b, name)[:n] = t
@@ -229,24 +232,32 @@ class MpmSolver:
         dp = C.POINTER(C.c_double)
         N.check(self.lib.ffmpm_set_materials(self._h, *(a.ctypes.data_as(dp) for a in arrs), len(arrs[0])))
 
-    def _choose_material_layout(self, given: Dict[str, torch.Tensor], n: int) -> None:
-        """Pick the cheapest exact representation of the per-particle (mass, mu0, lam0) triples."""
+    def _choose_material_layout(self, given: Dict[str, torch.Tensor], n: int, also=None) -> None:
+        """Pick the cheapest exact representation of the per-particle (mass, mu0, lam0) triples.
+        ``also``: (R, 3) triples that must be in the table too (slabs: the triples of the other
+        ranks, so that every rank derives the same table and a migrating row index stays valid)."""
         trip = torch.stack([given["mass"], given["mu0"], given["lam0"]], 1)
+        k = 0
+        if also is not None and len(also):
+            also = torch.as_tensor(np.asarray(also), device=self.device).to(self.dtype).reshape(-1, 3)
+            k = also.shape[0]
+            trip = torch.cat([also, trip], 0)
         rows = inv = None
-        if n == 0:
+        if trip.shape[0] == 0:
             rows = torch.tensor([[self.cfg.mass, self.cfg.mu_0, self.cfg.lambda_0]], dtype=self.dtype, device=self.device)
         elif bool((trip == trip[0]).all()):
             rows = trip[:1]
         else:
-            u, i = torch.unique(trip, dim=0, return_inverse=True)
+            u, i = torch.unique(trip, dim=0, return_inverse=True)     # lexicographically sorted rows
             if u.shape[0] <= 256:
-                rows, inv = u, i
+                rows, inv = u, i[k:]
         if rows is None:
             kind = "planes"
         else:
             kind = "rows" if inv is not None else "none"
         for b in self.buffers:
             b.set_material_storage(kind)
+        self.material_table = rows
         if rows is None:
             N.check(self.lib.ffmpm_set_materials(self._h, None, None, None, 0))
             self.material_layout = "planes"
