@@ -42,6 +42,10 @@ def make_scene(workload: str, seed: int = 0, cells_x=None, res_x=None):
         return scenes.config_2d_1m(seed)
     if workload == "3d16m":
         return scenes.config_3d_16m(seed)
+    if workload == "3d16m-rest":          # same block as the reference starts it: F = I, v = 0 (simulation.py:76-79)
+        sc = scenes.elastic_block(3, 256, 128, 2, seed, perturb=False)
+        sc.name += " (at rest)"
+        return sc
     if workload.startswith("3d:"):        # 3d:<res>:<cells>  (tests / quick runs)
         _, res, cells = workload.split(":")
         return scenes.elastic_block(3, int(res), int(cells), 2, seed)

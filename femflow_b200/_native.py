@@ -70,7 +70,9 @@ PROTOTYPES = {
 }
 
 
-def load_library(path: str = LIBPATH) -> C.CDLL:
+def load_library(path: str = "") -> C.CDLL:
+    # FEMFLOW_MPM_LIB: load another build of the same ABI (A/B runs of kernel variants on one box)
+    path = path or os.environ.get("FEMFLOW_MPM_LIB") or LIBPATH
     if not os.path.exists(path):
         raise ImportError(
             f"{path} is missing: the femflow_b200 CUDA library has not been built. "

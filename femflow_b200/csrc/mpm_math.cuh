@@ -130,7 +130,12 @@ __device__ __forceinline__ Sym3f sym3_mul(const Sym3f& a, const Sym3f& b) {
   return r;
 }
 
-constexpr float kPerturbationMaxG = 0.15f;
+// The series M = I - (I + G)^(-1/2) = sum_k c_k G^k is truncated at a degree picked from the
+// Frobenius norm r of G (an upper bound of its spectral radius): degree 3 for r < 0.005, 5 for
+// r < 0.04, 8 for r < 0.15 -- each keeps the truncation error of M below 1e-7 relative (checked
+// against an eigendecomposition over random and rank-one G, scripts/series_degree.py).  Small
+// strains, the common case for an elastic solid, take 2 instead of 7 matrix products.
+constexpr float kPerturbationMaxR = 0.15f;
 
 // Returns false when the strain is too large for the series (caller falls back to fp64).
 __device__ __forceinline__ bool fixed_corotated_affine3_f32(const Mat3<float>& F, const Mat3<float>& C, float mu,
@@ -144,19 +149,24 @@ __device__ __forceinline__ bool fixed_corotated_affine3_f32(const Mat3<float>& F
   G.xy = (E.a01 + E.a10) + (E.a00 * E.a01 + E.a10 * E.a11 + E.a20 * E.a21);
   G.xz = (E.a02 + E.a20) + (E.a00 * E.a02 + E.a10 * E.a12 + E.a20 * E.a22);
   G.yz = (E.a12 + E.a21) + (E.a01 * E.a02 + E.a11 * E.a12 + E.a21 * E.a22);
-  const float gmax = fmaxf(fmaxf(fmaxf(fabsf(G.xx), fabsf(G.yy)), fmaxf(fabsf(G.zz), fabsf(G.xy))),
-                           fmaxf(fabsf(G.xz), fabsf(G.yz)));
-  if (!(gmax < kPerturbationMaxG)) return false;
-  // q(G) = M / G, Horner from the highest coefficient
+  const float r2 = (G.xx * G.xx + G.yy * G.yy + G.zz * G.zz) + 2.0f * (G.xy * G.xy + G.xz * G.xz + G.yz * G.yz);
+  if (!(r2 < kPerturbationMaxR * kPerturbationMaxR)) return false;
+  // q(G) = M / G, Horner from the highest coefficient kept
   const float c[8] = {0.5f, -0.375f, 0.3125f, -0.2734375f, 0.24609375f, -0.2255859375f, 0.20947265625f,
                       -0.196380615234375f};
+  float ca = c[7], cb = c[6];
+  int top = 5;                                             // degree 8: Horner steps c[5] .. c[0]
+  if (r2 < 0.005f * 0.005f) { ca = c[2]; cb = c[1]; top = 0; }        // degree 3
+  else if (r2 < 0.04f * 0.04f) { ca = c[4]; cb = c[3]; top = 2; }     // degree 5
   Sym3f q;
-  q.xx = q.yy = q.zz = c[7];
-  q.xy = q.xz = q.yz = 0.0f;
+  q.xx = ca * G.xx + cb; q.yy = ca * G.yy + cb; q.zz = ca * G.zz + cb;
+  q.xy = ca * G.xy; q.xz = ca * G.xz; q.yz = ca * G.yz;
 #pragma unroll
-  for (int i = 6; i >= 0; --i) {
-    q = sym3_mul(G, q);
-    q.xx += c[i]; q.yy += c[i]; q.zz += c[i];
+  for (int i = 5; i >= 0; --i) {
+    if (i <= top) {                                        // a warp pays for its most strained particle
+      q = sym3_mul(G, q);
+      q.xx += c[i]; q.yy += c[i]; q.zz += c[i];
+    }
   }
   const Sym3f M = sym3_mul(G, q);
   // W = F M,  X = W F^T (symmetric)

@@ -144,6 +144,36 @@ def test_binning_is_bit_exact(dtype):
         s.close()
 
 
+@pytest.mark.parametrize("strain", [1e-4, 1.5e-3, 1e-2, 4e-2, 0.3])
+def test_stress_accuracy_across_series_tiers(strain):
+    """fp32 stress (three_d/p2g.py:57-65 via utils.py:75-92): the perturbation series switches degree
+    with the strain (3 / 5 / 8 terms, fp64 Newton fallback beyond); with v = C = 0 the grid momentum
+    IS the stress term, so its relative error measures the stress alone.  Same 1e-5 bar on every tier."""
+    from femflow_b200.mpm import MpmSolver
+    rng = np.random.default_rng(11)
+    res, n = 32, 40_000
+    f32 = lambda a: np.asarray(a, dtype=np.float32).astype(np.float64)
+    x = f32(rng.uniform(0.25, 0.75, size=(n, 3)))
+    v = np.zeros((n, 3)); C = np.zeros((n, 3, 3))
+    F = f32(np.eye(3) + strain * rng.uniform(-1, 1, size=(n, 3, 3)))
+    dx = 1.0 / res
+    vol = float(f32((dx / 2) ** 3))
+    mass = np.full(n, vol); mu0 = np.full(n, f32(4166.67)); lam0 = np.full(n, f32(2777.78))
+    gv = np.zeros((res + 1,) * 3 + (3,)); gm = np.zeros((res + 1,) * 3 + (1,))
+    O.p2g_3d(float(res), 1.0, dx, 1e-4, vol, gv, gm, x, mass, mu0, lam0, v, F, C, np.ones((n, 1)))
+    for mode in ("scatter", "tiled"):
+        s = MpmSolver(3, res, 1e-4, vol, 0.0, 1.0, capacity=n, p2g_mode=mode)
+        s.set_particles(x, v, F, C, None, mass, mu0, lam0)
+        s.clear_grid()
+        if mode == "tiled":
+            s.bin()
+        s.p2g()
+        assert s.poll_error() == 0
+        g = s.grid().double().cpu().numpy()
+        assert rel_err(g[..., :3], gv, np.abs(gv).max()) < TOL["float32"], (mode, strain)
+        s.close()
+
+
 @pytest.mark.parametrize("mode", ["scatter", "tiled"])
 def test_large_block_vs_oracle(mode, dtype):
     """200k-particle perturbed block, res 64: full substep vs the NumPy oracle, per phase."""
