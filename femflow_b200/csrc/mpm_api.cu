@@ -432,7 +432,8 @@ static int g2p_t(FfMpmHandle* h, cudaStream_t s) {
   if (h->binned && h->have_alt && h->cfg.dim == 3) {
     // binned: write the particles back in cell order into the other buffer
     StateView<T> dst = view<T>(h, h->st[h->live ^ 1]);
-    bin_clear_histogram(h->bin, s);   // the kernel pre-bins the advected particles for the next substep
+    // (the kernel pre-bins the advected particles for the next substep into the histogram that
+    // bin_particles left cleared)
     int nl = g2p_tiled<T>(h->dev, sv, dst, h->n, h->bin, (const T*)h->grid, h->err, h->sm_count, h->g2p_blocks_per_sm, s);
     h->live ^= 1;
     h->binned = false;  // positions moved: perm / cell offsets are stale ...
@@ -527,7 +528,6 @@ int ffmpm_scatter(FfMpmHandle* h, void* stream) {
 template <typename T>
 static int g2p2g_t(FfMpmHandle* h, cudaStream_t s) {
   StateView<T> sv = view<T>(h, h->st[h->live]), dst = view<T>(h, h->st[h->live ^ 1]);
-  bin_clear_histogram(h->bin, s);
   int nl = g2p2g_tiled<T>(h->dev, sv, dst, h->bin, (const T*)h->grid, (T*)h->grids[h->grid_cur ^ 1], h->err, h->sm_count,
                           h->gg_blocks_per_sm, s);
   h->live ^= 1;
