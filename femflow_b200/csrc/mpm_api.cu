@@ -68,6 +68,9 @@ struct FfMpmHandle {
   bool prebinned;     // keys/rank/histogram of the live buffer were emitted by the last reordering G2P
   int p2g_variant;    // see p2g_t (FFMPM_P2G_VARIANT)
   int p2g_blocks_per_sm, g2p_blocks_per_sm;   // persistent-grid sizing (tunable: FFMPM_P2G_BPS / FFMPM_G2P_BPS)
+  bool grid_in_blocks; // the current grid was zero before a P2G of exactly the binned particles: everything
+                       // non-zero lies inside the node blocks listed by the binning (bin.node_tiles)
+  int sparse_grid_op;  // FFMPM_SPARSE_GRID_OP=0: always update the whole grid
   void* mat_table;    // device, [3][MAT_ROWS] of the storage type (ffmpm_set_materials)
   int n_materials;
 };
@@ -171,6 +174,8 @@ int ffmpm_create(const FfMpmConfig* cfg, int32_t device, FfMpmHandle** out) {
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
     if (ce != cudaSuccess) { delete h; return set_err(FFMPM_E_CUDA, "stream/event creation: %s", cudaGetErrorString(ce)); }
   }
+  h->sparse_grid_op = 1;
+  if (const char* e = getenv("FFMPM_SPARSE_GRID_OP")) h->sparse_grid_op = atoi(e) != 0;
   h->p2g_blocks_per_sm = 5;
   h->g2p_blocks_per_sm = 8;
   h->p2g_variant = 5;   // physical-order P2G with cp.async-prefetched state when eligible (profiles/r01j)
@@ -252,6 +257,7 @@ int ffmpm_bind_state(FfMpmHandle* h, const FfMpmState* cur, const FfMpmState* al
   h->binned = false;
   h->prebinned = false;
   h->scatter_ahead = false;
+  h->grid_in_blocks = false;
   h->grid_clean[0] = h->grid_clean[1] = false;
   return FFMPM_OK;
 }
@@ -293,6 +299,7 @@ int ffmpm_set_num_particles(FfMpmHandle* h, int64_t n) {
   h->binned = false;
   h->prebinned = false;
   h->scatter_ahead = false;
+  h->grid_in_blocks = false;
   h->grid_clean[0] = h->grid_clean[1] = false;
   return FFMPM_OK;
 }
@@ -389,6 +396,8 @@ static int p2g_t(FfMpmHandle* h, cudaStream_t s) {
 int ffmpm_p2g(FfMpmHandle* h, void* stream) {
   int rc = ready(h);
   if (rc) return rc;
+  // a zero grid + the particles the bin buffers describe: what P2G writes stays inside bin.node_tiles
+  h->grid_in_blocks = h->grid_clean[h->grid_cur] && h->binned && h->cfg.dim == 3 && h->n > 0;
   h->grid_clean[h->grid_cur] = false;
   if (h->n == 0) return FFMPM_OK;
   return h->cfg.dtype == FFMPM_F64 ? p2g_t<double>(h, (cudaStream_t)stream) : p2g_t<float>(h, (cudaStream_t)stream);
@@ -398,7 +407,17 @@ template <typename T>
 static int grid_op_t(FfMpmHandle* h, cudaStream_t s, const void* halo_lo = nullptr, long long nodes_lo = 0,
                      const void* halo_hi = nullptr, long long nodes_hi = 0) {
   unsigned blocks = (unsigned)((h->n_nodes + 255) / 256);
-  if (h->cfg.dim == 3)
+  if (h->cfg.dim == 3 && h->grid_in_blocks && h->sparse_grid_op) {
+    // the node-block list comes from the binning, which may still be in flight on the internal stream
+    if (h->bin_pending) {
+      CUDA_TRY(cudaStreamWaitEvent(s, h->ev_join, 0));
+      h->bin_pending = false;
+    }
+    h->grid_in_blocks = false;   // velocities now: a second update would have to see every node again
+    grid_op3_blocks_kernel<T><<<h->sm_count * 8, 256, 0, s>>>(h->dev, (T*)h->grid, h->n_nodes, (const T*)halo_lo, nodes_lo,
+                                                             (const T*)halo_hi, nodes_hi, h->colliders, h->bin.node_tiles,
+                                                             h->bin.counters + 4, h->bin.ntile[1], h->bin.ntile[2]);
+  } else if (h->cfg.dim == 3)
     grid_op3_kernel<T><<<blocks, 256, 0, s>>>(h->dev, (T*)h->grid, h->n_nodes, (const T*)halo_lo, nodes_lo,
                                                (const T*)halo_hi, nodes_hi, h->colliders);
   else
@@ -534,6 +553,7 @@ static int g2p2g_t(FfMpmHandle* h, cudaStream_t s) {
   h->binned = false;
   h->prebinned = true;
   h->grid_clean[h->grid_cur ^ 1] = false;
+  h->grid_in_blocks = false;
   h->scatter_ahead = true;
   return check_launch(h, nl);
 }
@@ -611,6 +631,7 @@ int ffmpm_grid_ptr(FfMpmHandle* h, void** grid) {
   if (!h || !grid || !h->ws) return set_err(FFMPM_E_STATE, "workspace not set");
   *grid = h->grid;
   h->grid_clean[h->grid_cur] = false;   // the caller may write through this pointer
+  h->grid_in_blocks = false;
   return FFMPM_OK;
 }
 

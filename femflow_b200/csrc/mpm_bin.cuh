@@ -24,11 +24,16 @@ constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 struct BinBuffers {
   int32_t* counters;     // [16]: 0 = n_active_tiles, 1 = p2g work counter, 2 = g2p work counter,
-                         //       3 = particles whose base cell left the rank's owned x range (slabs)
+                         //       3 = particles whose base cell left the rank's owned x range (slabs),
+                         //       4 = number of entries of node_tiles
   int32_t* cell_count;   // [n_cells + 2] histogram, bin n_cells = out-of-grid
   int32_t* cell_off;     // [n_cells + 2] exclusive scan of cell_count
   int32_t* block_sums;   // [n_scan_blocks + 1]
   int32_t* active_tiles; // [n_tiles]
+  uint8_t* tile_flag;    // [n_tiles] 1 = the tile holds particles (rewritten by every binning)
+  int32_t* node_tiles;   // [n_node_tiles] 4x4x4 node blocks P2G may have written (see node_tiles_kernel)
+  int ntile[3];          // node-tile grid: ceil(n / 4) per axis
+  int n_node_tiles;
   int32_t* keys;         // [capacity]
   int32_t* rank;         // [capacity]
   int32_t* perm;         // [capacity]
@@ -54,6 +59,15 @@ inline void bin_geometry(int dim, const int* n, int* tiles, int& n_tiles, int& n
   n_cells = n_tiles * TILE_CELLS;
 }
 
+inline int bin_node_tiles(int dim, const int* n, int* ntile) {
+  int total = 1;
+  for (int d = 0; d < 3; ++d) {
+    ntile[d] = d < dim ? (n[d] + TILE3 - 1) / TILE3 : 1;
+    total *= ntile[d];
+  }
+  return total;
+}
+
 inline int64_t bin_a256(int64_t v) { return (v + 255) / 256 * 256; }
 
 inline int64_t bin_workspace_bytes(int dim, const int* n, int64_t capacity) {
@@ -65,6 +79,9 @@ inline int64_t bin_workspace_bytes(int dim, const int* n, int64_t capacity) {
   b += bin_a256((int64_t)(n_cells + 2) * 4) * 2;
   b += bin_a256((int64_t)(n_scan_blocks + 1) * 4);
   b += bin_a256((int64_t)n_tiles * 4);
+  int ntile[3];
+  b += bin_a256((int64_t)n_tiles);
+  b += bin_a256((int64_t)bin_node_tiles(dim, n, ntile) * 4);
   b += bin_a256(capacity * 4) * 3;
   return b;
 }
@@ -80,6 +97,9 @@ inline void bin_carve(BinBuffers& B, char* base, int dim, const int* n, int64_t 
   B.cell_off = (int32_t*)p; p += bin_a256((int64_t)(B.n_cells + 2) * 4);
   B.block_sums = (int32_t*)p; p += bin_a256((int64_t)(B.n_scan_blocks + 1) * 4);
   B.active_tiles = (int32_t*)p; p += bin_a256((int64_t)B.n_tiles * 4);
+  B.tile_flag = (uint8_t*)p; p += bin_a256((int64_t)B.n_tiles);
+  B.n_node_tiles = bin_node_tiles(dim, n, B.ntile);
+  B.node_tiles = (int32_t*)p; p += bin_a256((int64_t)B.n_node_tiles * 4);
   B.keys = (int32_t*)p; p += bin_a256(capacity * 4);
   B.rank = (int32_t*)p; p += bin_a256(capacity * 4);
   B.perm = (int32_t*)p; p += bin_a256(capacity * 4);
@@ -242,7 +262,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_downsweep_kernel(const int3
 __global__ void __launch_bounds__(256) active_tiles_kernel(BinBuffers B) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   bool act = false;
-  if (t < B.n_tiles) act = B.cell_off[(t + 1) * TILE_CELLS] > B.cell_off[t * TILE_CELLS];
+  if (t < B.n_tiles) {
+    act = B.cell_off[(t + 1) * TILE_CELLS] > B.cell_off[t * TILE_CELLS];
+    B.tile_flag[t] = act ? 1 : 0;
+  }
   unsigned m = __ballot_sync(0xffffffffu, act);
   if (m) {
     unsigned lane = threadIdx.x & 31;
@@ -251,6 +274,33 @@ __global__ void __launch_bounds__(256) active_tiles_kernel(BinBuffers B) {
     if ((int)lane == leader) base = atomicAdd(&B.counters[0], __popc(m));
     base = __shfl_sync(0xffffffffu, base, leader);
     if (act) B.active_tiles[base + __popc(m & ((1u << lane) - 1u))] = t;
+  }
+}
+
+// 3D: list of the 4x4x4 NODE blocks that the P2G of the binned particles can have written.  A tile of
+// base cells 4t .. 4t+3 scatters to nodes 4t .. 4t+5, i.e. into node blocks t and t+1 per axis, so node
+// block T is live iff one of the base-cell tiles T - {0,1}^3 holds particles.  The grid update then
+// visits these blocks only (the grid is 8x larger than the occupied part in the 16M-particle block).
+__global__ void __launch_bounds__(256) node_tiles_kernel(BinBuffers B) {
+  const int T = blockIdx.x * blockDim.x + threadIdx.x;
+  bool live = false;
+  if (T < B.n_node_tiles) {
+    const int c = T % B.ntile[2], b = (T / B.ntile[2]) % B.ntile[1], a = T / (B.ntile[2] * B.ntile[1]);
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      const int ta = a - (d >> 2), tb = b - ((d >> 1) & 1), tc = c - (d & 1);
+      if (ta >= 0 && tb >= 0 && tc >= 0 && ta < B.tiles[0] && tb < B.tiles[1] && tc < B.tiles[2])
+        live = live || B.tile_flag[(ta * B.tiles[1] + tb) * B.tiles[2] + tc] != 0;
+    }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, live);
+  if (m) {
+    const unsigned lane = threadIdx.x & 31;
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if ((int)lane == leader) base = atomicAdd(&B.counters[4], __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (live) B.node_tiles[base + __popc(m & ((1u << lane) - 1u))] = T;
   }
 }
 
@@ -290,6 +340,10 @@ int bin_particles(const DevCfg& cfg, const StateView<T>& s, long long n, BinBuff
   // pre-bins the next substep, instead of in front of that G2P on the main stream
   bin_clear_histogram(B, st);
   active_tiles_kernel<<<(B.n_tiles + 255) / 256, 256, 0, st>>>(B);
+  if (cfg.dim == 3) {
+    node_tiles_kernel<<<(B.n_node_tiles + 255) / 256, 256, 0, st>>>(B);
+    ++launches;
+  }
   bin_scatter_kernel<<<pb, 256, 0, st>>>(n, B, err);
   return launches;
 }

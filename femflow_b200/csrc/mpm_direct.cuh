@@ -213,11 +213,9 @@ __global__ void __launch_bounds__(128) p2g_scatter2_kernel(DevCfg cfg, StateView
 // 3D (three_d/grid_op.py:25-47): v = mom/mass, v.y += dt*g, clamp to +-0.9 dx/dt,
 // then zero component d on nodes with global index I[d] < 1 or I[d] >= R-1 (quirk 5).
 template <typename T>
-__global__ void __launch_bounds__(256) grid_op3_kernel(DevCfg cfg, T* __restrict__ grid, long long n_nodes,
-                                                       const T* __restrict__ halo_lo, long long nodes_lo,
-                                                       const T* __restrict__ halo_hi, long long nodes_hi, Colliders col) {
-  long long node = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (node >= n_nodes) return;
+__device__ __forceinline__ void grid_op3_node(const DevCfg& cfg, T* __restrict__ grid, long long n_nodes, long long node,
+                                              int i, int j, int k, const T* __restrict__ halo_lo, long long nodes_lo,
+                                              const T* __restrict__ halo_hi, long long nodes_hi, const Colliders& col) {
   using V4 = typename Vec4<T>::type;
   V4 g = reinterpret_cast<V4*>(grid)[node];
   // Halo SUM fused into the load: the neighbour slabs' partial {momentum, mass} of the
@@ -232,10 +230,6 @@ __global__ void __launch_bounds__(256) grid_op3_kernel(DevCfg cfg, T* __restrict
   }
   // empty node with zero momentum: velocity stays zero under the wall projection
   if (!(g.w > (T)0) && g.x == (T)0 && g.y == (T)0 && g.z == (T)0) return;
-  int k = (int)(node % cfg.n[2]);
-  long long r = node / cfg.n[2];
-  int j = (int)(r % cfg.n[1]);
-  int i = (int)(r / cfg.n[1]);
   if (g.w > (T)0) {
     const T va = (T)(cfg.dx * 0.9 / cfg.dt);
     const T dtg = (T)(cfg.dt * cfg.gravity);
@@ -256,6 +250,43 @@ __global__ void __launch_bounds__(256) grid_op3_kernel(DevCfg cfg, T* __restrict
     if (ox * col.normal[c][0] + oy * col.normal[c][1] + oz * col.normal[c][2] < 0) { g.x = g.y = g.z = (T)0; }
   }
   reinterpret_cast<V4*>(grid)[node] = g;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) grid_op3_kernel(DevCfg cfg, T* __restrict__ grid, long long n_nodes,
+                                                       const T* __restrict__ halo_lo, long long nodes_lo,
+                                                       const T* __restrict__ halo_hi, long long nodes_hi, Colliders col) {
+  long long node = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (node >= n_nodes) return;
+  int k = (int)(node % cfg.n[2]);
+  long long r = node / cfg.n[2];
+  int j = (int)(r % cfg.n[1]);
+  int i = (int)(r / cfg.n[1]);
+  grid_op3_node<T>(cfg, grid, n_nodes, node, i, j, k, halo_lo, nodes_lo, halo_hi, nodes_hi, col);
+}
+
+// The same update over a list of 4x4x4 node blocks (mpm_bin.cuh: node_tiles_kernel) instead of the
+// whole grid: every node outside the listed blocks is zero {momentum, mass} by construction (the grid
+// was cleared, P2G of the binned particles wrote only inside them), and the dense kernel leaves such
+// nodes untouched.  One node per thread, four blocks per CTA round, grid-stride over the list.
+template <typename T>
+__global__ void __launch_bounds__(256) grid_op3_blocks_kernel(DevCfg cfg, T* __restrict__ grid, long long n_nodes,
+                                                              const T* __restrict__ halo_lo, long long nodes_lo,
+                                                              const T* __restrict__ halo_hi, long long nodes_hi,
+                                                              Colliders col, const int* __restrict__ node_tiles,
+                                                              const int* __restrict__ n_listed, int nt1, int nt2) {
+  const int count = *n_listed;
+  const int local = threadIdx.x & 63;
+  const int di = local >> 4, dj = (local >> 2) & 3, dk = local & 3;
+  for (int idx = blockIdx.x * 4 + (threadIdx.x >> 6); idx < count; idx += gridDim.x * 4) {
+    const int t = node_tiles[idx];
+    const int c = t % nt2, b = (t / nt2) % nt1, a = t / (nt2 * nt1);
+    const int i = a * 4 + di, j = b * 4 + dj, k = c * 4 + dk;
+    if (i < cfg.n[0] && j < cfg.n[1] && k < cfg.n[2]) {
+      const long long node = ((long long)i * cfg.n[1] + j) * cfg.n[2] + k;
+      grid_op3_node<T>(cfg, grid, n_nodes, node, i, j, k, halo_lo, nodes_lo, halo_hi, nodes_hi, col);
+    }
+  }
 }
 
 // Stand-alone plane colliders (three_d/grid_op.py:50-67) for the phase-level API; inside a
