@@ -70,7 +70,9 @@ struct FfMpmHandle {
   int p2g_blocks_per_sm, g2p_blocks_per_sm;   // persistent-grid sizing (tunable: FFMPM_P2G_BPS / FFMPM_G2P_BPS)
   bool grid_in_blocks; // the current grid was zero before a P2G of exactly the binned particles: everything
                        // non-zero lies inside the node blocks listed by the binning (bin.node_tiles)
-  int sparse_grid_op;  // FFMPM_SPARSE_GRID_OP=0: always update the whole grid
+  int sparse_grid_op;  // FFMPM_SPARSE_GRID_OP=0: always update / clear the whole grid
+  int bin_slot;        // which of bin.node_tiles2[] the last binning filled (= grid_cur at that time)
+  bool grid_listed[2]; // everything non-zero in grids[g] lies inside the blocks of bin.node_tiles2[g]
   void* mat_table;    // device, [3][MAT_ROWS] of the storage type (ffmpm_set_materials)
   int n_materials;
 };
@@ -217,6 +219,8 @@ int ffmpm_set_workspace(FfMpmHandle* h, void* workspace, int64_t bytes) {
   h->grid_cur = 0;
   h->grid = h->grids[0];
   h->grid_clean[0] = h->grid_clean[1] = false;
+  h->grid_listed[0] = h->grid_listed[1] = false;
+  h->grid_in_blocks = false;
   h->bin_pending = false;
   h->scatter_ahead = false;
   bin_carve(h->bin, h->ws + L.bin_off, h->cfg.dim, h->dev.n, lo);
@@ -258,6 +262,7 @@ int ffmpm_bind_state(FfMpmHandle* h, const FfMpmState* cur, const FfMpmState* al
   h->prebinned = false;
   h->scatter_ahead = false;
   h->grid_in_blocks = false;
+  h->grid_listed[0] = h->grid_listed[1] = false;
   h->grid_clean[0] = h->grid_clean[1] = false;
   return FFMPM_OK;
 }
@@ -300,6 +305,7 @@ int ffmpm_set_num_particles(FfMpmHandle* h, int64_t n) {
   h->prebinned = false;
   h->scatter_ahead = false;
   h->grid_in_blocks = false;
+  h->grid_listed[0] = h->grid_listed[1] = false;
   h->grid_clean[0] = h->grid_clean[1] = false;
   return FFMPM_OK;
 }
@@ -346,6 +352,9 @@ int ffmpm_clear_grid(FfMpmHandle* h, void* stream) {
 template <typename T>
 static int bin_t(FfMpmHandle* h, cudaStream_t s) {
   if (h->n > h->capacity) return set_err(FFMPM_E_STATE, "workspace too small for this particle count");
+  h->bin_slot = h->grid_cur;   // the node-block list belongs to the grid this substep's P2G writes
+  h->bin.node_tiles = h->bin.node_tiles2[h->bin_slot];
+  h->bin.node_count = h->bin.node_counts + h->bin_slot;
   int nl = bin_particles<T>(h->dev, view<T>(h, h->st[h->live]), h->n, h->bin, h->err, h->prebinned, s);
   h->binned = true;
   h->prebinned = false;
@@ -397,7 +406,8 @@ int ffmpm_p2g(FfMpmHandle* h, void* stream) {
   int rc = ready(h);
   if (rc) return rc;
   // a zero grid + the particles the bin buffers describe: what P2G writes stays inside bin.node_tiles
-  h->grid_in_blocks = h->grid_clean[h->grid_cur] && h->binned && h->cfg.dim == 3 && h->n > 0;
+  h->grid_in_blocks = h->grid_clean[h->grid_cur] && h->binned && h->bin_slot == h->grid_cur && h->cfg.dim == 3 && h->n > 0;
+  h->grid_listed[h->grid_cur] = h->grid_in_blocks;
   h->grid_clean[h->grid_cur] = false;
   if (h->n == 0) return FFMPM_OK;
   return h->cfg.dtype == FFMPM_F64 ? p2g_t<double>(h, (cudaStream_t)stream) : p2g_t<float>(h, (cudaStream_t)stream);
@@ -415,8 +425,9 @@ static int grid_op_t(FfMpmHandle* h, cudaStream_t s, const void* halo_lo = nullp
     }
     h->grid_in_blocks = false;   // velocities now: a second update would have to see every node again
     grid_op3_blocks_kernel<T><<<h->sm_count * 8, 256, 0, s>>>(h->dev, (T*)h->grid, h->n_nodes, (const T*)halo_lo, nodes_lo,
-                                                             (const T*)halo_hi, nodes_hi, h->colliders, h->bin.node_tiles,
-                                                             h->bin.counters + 4, h->bin.ntile[1], h->bin.ntile[2]);
+                                                             (const T*)halo_hi, nodes_hi, h->colliders,
+                                                             h->bin.node_tiles2[h->grid_cur], h->bin.node_counts + h->grid_cur,
+                                                             h->bin.ntile[1], h->bin.ntile[2]);
   } else if (h->cfg.dim == 3)
     grid_op3_kernel<T><<<blocks, 256, 0, s>>>(h->dev, (T*)h->grid, h->n_nodes, (const T*)halo_lo, nodes_lo,
                                                (const T*)halo_hi, nodes_hi, h->colliders);
@@ -501,8 +512,21 @@ static int fork_bin(FfMpmHandle* h, cudaStream_t s, bool clear_idle) {
   }
   if ((rc = ffmpm_bin(h, (void*)w))) return rc;
   if (clear_idle) {
-    CUDA_TRY(cudaMemsetAsync(h->grids[h->grid_cur ^ 1], 0, (size_t)h->n_nodes * 4 * elem_size(h->cfg), w));
-    h->grid_clean[h->grid_cur ^ 1] = true;
+    const int idle = h->grid_cur ^ 1;
+    if (h->grid_listed[idle] && h->sparse_grid_op) {
+      // only the node blocks its last substep touched (listed by that substep's binning) are non-zero
+      if (h->cfg.dtype == FFMPM_F64)
+        grid_clear_blocks_kernel<double><<<h->sm_count * 8, 256, 0, w>>>(h->dev, (double*)h->grids[idle], h->bin.node_tiles2[idle],
+                                                                        h->bin.node_counts + idle, h->bin.ntile[1], h->bin.ntile[2]);
+      else
+        grid_clear_blocks_kernel<float><<<h->sm_count * 8, 256, 0, w>>>(h->dev, (float*)h->grids[idle], h->bin.node_tiles2[idle],
+                                                                       h->bin.node_counts + idle, h->bin.ntile[1], h->bin.ntile[2]);
+      if ((rc = check_launch(h, 1))) return rc;
+    } else {
+      CUDA_TRY(cudaMemsetAsync(h->grids[idle], 0, (size_t)h->n_nodes * 4 * elem_size(h->cfg), w));
+    }
+    h->grid_clean[idle] = true;
+    h->grid_listed[idle] = false;
   }
   if (h->overlap) {
     CUDA_TRY(cudaEventRecord(h->ev_join, h->aux));
@@ -553,6 +577,7 @@ static int g2p2g_t(FfMpmHandle* h, cudaStream_t s) {
   h->binned = false;
   h->prebinned = true;
   h->grid_clean[h->grid_cur ^ 1] = false;
+  h->grid_listed[h->grid_cur ^ 1] = false;
   h->grid_in_blocks = false;
   h->scatter_ahead = true;
   return check_launch(h, nl);
@@ -632,6 +657,7 @@ int ffmpm_grid_ptr(FfMpmHandle* h, void** grid) {
   *grid = h->grid;
   h->grid_clean[h->grid_cur] = false;   // the caller may write through this pointer
   h->grid_in_blocks = false;
+  h->grid_listed[h->grid_cur] = false;
   return FFMPM_OK;
 }
 

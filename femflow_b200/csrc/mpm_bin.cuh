@@ -24,14 +24,16 @@ constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 struct BinBuffers {
   int32_t* counters;     // [16]: 0 = n_active_tiles, 1 = p2g work counter, 2 = g2p work counter,
-                         //       3 = particles whose base cell left the rank's owned x range (slabs),
-                         //       4 = number of entries of node_tiles
+                         //       3 = particles whose base cell left the rank's owned x range (slabs)
   int32_t* cell_count;   // [n_cells + 2] histogram, bin n_cells = out-of-grid
   int32_t* cell_off;     // [n_cells + 2] exclusive scan of cell_count
   int32_t* block_sums;   // [n_scan_blocks + 1]
   int32_t* active_tiles; // [n_tiles]
   uint8_t* tile_flag;    // [n_tiles] 1 = the tile holds particles (rewritten by every binning)
-  int32_t* node_tiles;   // [n_node_tiles] 4x4x4 node blocks P2G may have written (see node_tiles_kernel)
+  int32_t* node_tiles;   // [n_node_tiles] 4x4x4 node blocks P2G may have written (see node_tiles_kernel):
+  int32_t* node_count;   //   the list + its length that the next binning fills (one of the two below)
+  int32_t* node_tiles2[2];   // one list per grid of the ping-pong pair: the list also tells which blocks of
+  int32_t* node_counts;      // that grid have to be cleared once the substep is over ([2] lengths)
   int ntile[3];          // node-tile grid: ceil(n / 4) per axis
   int n_node_tiles;
   int32_t* keys;         // [capacity]
@@ -81,7 +83,7 @@ inline int64_t bin_workspace_bytes(int dim, const int* n, int64_t capacity) {
   b += bin_a256((int64_t)n_tiles * 4);
   int ntile[3];
   b += bin_a256((int64_t)n_tiles);
-  b += bin_a256((int64_t)bin_node_tiles(dim, n, ntile) * 4);
+  b += bin_a256((int64_t)bin_node_tiles(dim, n, ntile) * 4) * 2 + 256;
   b += bin_a256(capacity * 4) * 3;
   return b;
 }
@@ -99,7 +101,11 @@ inline void bin_carve(BinBuffers& B, char* base, int dim, const int* n, int64_t 
   B.active_tiles = (int32_t*)p; p += bin_a256((int64_t)B.n_tiles * 4);
   B.tile_flag = (uint8_t*)p; p += bin_a256((int64_t)B.n_tiles);
   B.n_node_tiles = bin_node_tiles(dim, n, B.ntile);
-  B.node_tiles = (int32_t*)p; p += bin_a256((int64_t)B.n_node_tiles * 4);
+  B.node_tiles2[0] = (int32_t*)p; p += bin_a256((int64_t)B.n_node_tiles * 4);
+  B.node_tiles2[1] = (int32_t*)p; p += bin_a256((int64_t)B.n_node_tiles * 4);
+  B.node_counts = (int32_t*)p; p += 256;
+  B.node_tiles = B.node_tiles2[0];
+  B.node_count = B.node_counts;
   B.keys = (int32_t*)p; p += bin_a256(capacity * 4);
   B.rank = (int32_t*)p; p += bin_a256(capacity * 4);
   B.perm = (int32_t*)p; p += bin_a256(capacity * 4);
@@ -298,7 +304,7 @@ __global__ void __launch_bounds__(256) node_tiles_kernel(BinBuffers B) {
     const unsigned lane = threadIdx.x & 31;
     const int leader = __ffs(m) - 1;
     int base = 0;
-    if ((int)lane == leader) base = atomicAdd(&B.counters[4], __popc(m));
+    if ((int)lane == leader) base = atomicAdd(B.node_count, __popc(m));
     base = __shfl_sync(0xffffffffu, base, leader);
     if (live) B.node_tiles[base + __popc(m & ((1u << lane) - 1u))] = T;
   }
@@ -341,6 +347,7 @@ int bin_particles(const DevCfg& cfg, const StateView<T>& s, long long n, BinBuff
   bin_clear_histogram(B, st);
   active_tiles_kernel<<<(B.n_tiles + 255) / 256, 256, 0, st>>>(B);
   if (cfg.dim == 3) {
+    cudaMemsetAsync(B.node_count, 0, sizeof(int32_t), st);
     node_tiles_kernel<<<(B.n_node_tiles + 255) / 256, 256, 0, st>>>(B);
     ++launches;
   }

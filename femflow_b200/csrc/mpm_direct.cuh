@@ -289,6 +289,26 @@ __global__ void __launch_bounds__(256) grid_op3_blocks_kernel(DevCfg cfg, T* __r
   }
 }
 
+// Zeroes the listed node blocks: after a substep nothing else of that grid is non-zero.
+template <typename T>
+__global__ void __launch_bounds__(256) grid_clear_blocks_kernel(DevCfg cfg, T* __restrict__ grid,
+                                                                const int* __restrict__ node_tiles,
+                                                                const int* __restrict__ n_listed, int nt1, int nt2) {
+  using V4 = typename Vec4<T>::type;
+  const int count = *n_listed;
+  const int local = threadIdx.x & 63;
+  const int di = local >> 4, dj = (local >> 2) & 3, dk = local & 3;
+  V4 z;
+  z.x = z.y = z.z = z.w = (T)0;
+  for (int idx = blockIdx.x * 4 + (threadIdx.x >> 6); idx < count; idx += gridDim.x * 4) {
+    const int t = node_tiles[idx];
+    const int c = t % nt2, b = (t / nt2) % nt1, a = t / (nt2 * nt1);
+    const int i = a * 4 + di, j = b * 4 + dj, k = c * 4 + dk;
+    if (i < cfg.n[0] && j < cfg.n[1] && k < cfg.n[2])
+      reinterpret_cast<V4*>(grid)[((long long)i * cfg.n[1] + j) * cfg.n[2] + k] = z;
+  }
+}
+
 // Stand-alone plane colliders (three_d/grid_op.py:50-67) for the phase-level API; inside a
 // substep the same predicate runs fused at the end of grid_op3_kernel.
 template <typename T>
