@@ -62,6 +62,7 @@ PROTOTYPES = {
     "ffmpm_set_owned_range": (C.c_int, [H, C.c_int32, C.c_int32]),
     "ffmpm_leaver_count_ptr": (C.c_int, [H, C.POINTER(C.c_void_p)]),
     "ffmpm_grid_ptr": (C.c_int, [H, C.POINTER(C.c_void_p)]),
+    "ffmpm_grid_view": (C.c_int, [H, C.POINTER(C.c_void_p)]),
     "ffmpm_bin_ptrs": (C.c_int, [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                  C.POINTER(C.c_int64)]),
     "ffmpm_poll_error": (C.c_int, [H, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),

@@ -661,6 +661,12 @@ int ffmpm_grid_ptr(FfMpmHandle* h, void** grid) {
   return FFMPM_OK;
 }
 
+int ffmpm_grid_view(FfMpmHandle* h, const void** grid) {
+  if (!h || !grid || !h->ws) return set_err(FFMPM_E_STATE, "workspace not set");
+  *grid = h->grid;
+  return FFMPM_OK;
+}
+
 int ffmpm_bin_ptrs(FfMpmHandle* h, int32_t** keys, int32_t** perm, int32_t** cell_offsets, int64_t* n_cells) {
   if (!h || !h->ws) return set_err(FFMPM_E_STATE, "workspace not set");
   if (keys) *keys = h->bin.keys;

@@ -296,7 +296,7 @@ class CudaSlab(LocalSlab):
         self.solver.scatter()
 
     def grid_planes(self, a: int, b: int) -> torch.Tensor:
-        return self.solver.grid()[a:b]
+        return self.solver.grid(readonly=True)[a:b]
 
     def grid_update(self, recv_lo, planes_lo, recv_hi, planes_hi) -> None:
         from . import _native as N

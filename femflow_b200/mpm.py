@@ -352,10 +352,12 @@ class MpmSolver:
     def launch_count(self) -> int:
         return int(self.lib.ffmpm_launch_count(self._h))
 
-    def grid(self) -> torch.Tensor:
-        """Node-major grid ``(nx, ny, nz, 4)`` (view into the workspace)."""
+    def grid(self, readonly: bool = False) -> torch.Tensor:
+        """Node-major grid ``(nx, ny, nz, 4)`` (view into the workspace).  ``readonly=True`` promises
+        not to write through the view (``ffmpm_grid_view``): the library then keeps its knowledge of
+        which node blocks are non-zero."""
         ptr = C.c_void_p()
-        N.check(self.lib.ffmpm_grid_ptr(self._h, C.byref(ptr)))
+        N.check((self.lib.ffmpm_grid_view if readonly else self.lib.ffmpm_grid_ptr)(self._h, C.byref(ptr)))
         off = ptr.value - self.workspace.data_ptr()
         count = self.n[0] * self.n[1] * self.n[2] * 4
         es = 8 if self.dtype == torch.float64 else 4

@@ -177,6 +177,10 @@ int ffmpm_collide(FfMpmHandle* h, void* stream);
 /* Phase-level access for parity tests: device pointer of the node-major grid
  * (n[0]*n[1]*n[2]*4 scalars of cfg.dtype). */
 int ffmpm_grid_ptr(FfMpmHandle* h, void** grid);
+/* The same pointer for READING only (slab drivers send halo planes straight out of grid memory).
+ * ffmpm_grid_ptr must assume the caller writes, which turns off the block-list grid update and clear
+ * for that substep; this accessor keeps them. */
+int ffmpm_grid_view(FfMpmHandle* h, const void** grid);
 /* Binning results (device pointers into the workspace, valid after ffmpm_bin):
  *   keys[p]          bin key of particle p of the live buffer: tile-major cell id
  *                    (tile = 4x4x4 base cells in 3D, 8x8 in 2D);
