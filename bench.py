@@ -358,6 +358,11 @@ def main():
                     "traffic_source": traffic.get("source") if traffic.get(dom) else None,
                     "algorithmic_bytes_per_launch": alg[dom],
                     "phase_ms": {k: round(v, 4) for k, v in phases.items()},
+                    # every kernel of the step against the same peak (SURVEY 8d also asks for the nominal 8 TB/s)
+                    "kernels": {k: {"algorithmic_bytes": alg[k], "achieved": alg[k] / (phases[k] * 1e-3) / 1e9,
+                                    "frac": alg[k] / (phases[k] * 1e-3) / 1e9 / peak, "traffic": traffic.get(k)}
+                                for k in phases if k in alg and phases[k] > 0},
+                    "frac_of_nominal_8TBs": achieved / 8000.0,
                     "substep_frac_of_hbm_roofline": (total_alg / (ms * 1e-3 / args.steps) / 1e9) / peak}
 
     cpu = None
