@@ -160,6 +160,10 @@ def main():
                     help="per-particle material layout (N=1): auto = table/rows when <= 256 distinct triples, planes = 3 scalar planes")
     ap.add_argument("--slab-timing", action="store_true", help="N>1: print per-phase CUDA-event times per rank to stderr")
     ap.add_argument("--margin", type=int, default=4, help="slab halo margin in cells = substeps between migrations")
+    ap.add_argument("--rebalance", action="store_true",
+                    help="dam workloads, N>1: re-cut the slabs by particle count before the warm-up (SlabDriver.rebalance)")
+    ap.add_argument("--rebalance-every", type=int, default=0,
+                    help="with --rebalance: also offer a re-cut every K timed substeps (inside the timed region)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -199,6 +203,8 @@ def main():
                                            p2g_mode=args.p2g_mode)
         scene.name = solver.scene_name
         scene.dt = solver.local.solver.cfg.dt
+        if args.rebalance and world > 1:
+            solver.rebalance()
         n = solver.num_particles
     elif world > 1:
         from femflow_b200.distributed import SlabSolver
@@ -231,8 +237,10 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
-    for _ in range(args.steps):
+    for k in range(args.steps):
         solver.substep(1)
+        if dam and world > 1 and args.rebalance and args.rebalance_every and (k + 1) % args.rebalance_every == 0:
+            solver.rebalance()
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -241,9 +249,11 @@ def main():
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-        cnt = torch.tensor([solver.num_particles], device=dev, dtype=torch.float64)
-        dist.all_reduce(cnt)
-        n_total = int(cnt.item())
+        cnt = torch.tensor([solver.num_particles], device=dev, dtype=torch.int64)
+        per_rank = [torch.zeros_like(cnt) for _ in range(world)]
+        dist.all_gather(per_rank, cnt)
+        slab_counts = [int(t.item()) for t in per_rank]
+        n_total = sum(slab_counts)
     else:
         n_total = n
     clocks = sampler.stop() if rank == 0 else None
@@ -384,7 +394,9 @@ def main():
                    "n_oob": n_oob,
                    "material_layout": (solver if world == 1 else solver.local.solver).material_layout,
                    "parallelism": (f"{world} slabs along x, halo sum over NCCL p2p every substep, migration every "
-                                   f"{args.margin} substeps") if world > 1 else "single GPU"},
+                                   f"{args.margin} substeps") if world > 1 else "single GPU",
+                   **({"slab_particles": slab_counts, "slab_cells": [list(r) for r in solver.plan.all_ranges],
+                       "rebalanced": solver.driver.rebalanced} if world > 1 else {})},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
     }
     print(json.dumps(line))

@@ -45,6 +45,7 @@ class SlabPlan:
     g_hi: int
     planes_lo: int   # planes shared with rank-1 (the first planes of the local grid)
     planes_hi: int   # planes shared with rank+1 (the last planes of the local grid)
+    all_ranges: Tuple[Tuple[int, int], ...] = ()   # owned cell range of every rank (the cut this plan belongs to)
 
     @property
     def n_local_x(self) -> int:
@@ -62,22 +63,76 @@ class SlabPlan:
             lo = hi
         return out
 
+    @staticmethod
+    def min_cells(margin: int) -> int:
+        """Thinnest slab whose halo planes stay inside the neighbouring slab."""
+        return 2 * margin + 2
+
+    @staticmethod
+    def balanced_ranges(counts, world: int, min_cells: int, layer_cost: float = 0.0) -> List[Tuple[int, int]]:
+        """Cut the base-cell layers 0 .. len(counts)-1 into ``world`` contiguous ranges of about equal
+        cost, where a layer costs ``counts[layer] + layer_cost`` (its particles plus a constant for the
+        cells the binning scans whether or not they hold particles), each at least ``min_cells`` thick,
+        minimising the cost of the heaviest range.  Pure function of its arguments: every rank derives the same cut from the all-reduced counts."""
+        cost = np.asarray(counts, dtype=np.float64) + float(layer_cost)
+        cells = len(cost)
+        if cells < world * min_cells:
+            raise ValueError("slabs are thinner than 2*margin+2 cells: halos would reach past the neighbour")
+        prefix = np.concatenate([[0.0], np.cumsum(cost)])      # prefix[c] = cost of layers [0, c)
+
+        def cut(bound):
+            """Greedy cut with every slab as thick as ``bound`` allows (a thicker slab never hurts the
+            ones after it); None when some slab cannot stay under ``bound``."""
+            cuts = [0]
+            for r in range(world - 1):
+                lo = cuts[-1]
+                c = int(np.searchsorted(prefix, prefix[lo] + bound, side="right")) - 1
+                c = min(c, cells - (world - 1 - r) * min_cells)        # room for the slabs still to come
+                if c < lo + min_cells:
+                    c = lo + min_cells
+                    if prefix[c] - prefix[lo] > bound:
+                        return None
+                cuts.append(c)
+            if prefix[cells] - prefix[cuts[-1]] > bound:
+                return None
+            return cuts + [cells]
+
+        # smallest feasible bottleneck by bisection (the cost of the heaviest slab is what a substep waits for)
+        lo_b, hi_b = prefix[-1] / world, prefix[-1]
+        best = cut(lo_b)
+        if best is None:
+            best = cut(hi_b)
+            for _ in range(64):
+                mid = 0.5 * (lo_b + hi_b)
+                got = cut(mid)
+                if got is None:
+                    lo_b = mid
+                else:
+                    hi_b, best = mid, got
+        return [(best[r], best[r + 1]) for r in range(world)]
+
     @classmethod
-    def make(cls, res: Sequence[int], world: int, rank: int, margin: int = 2) -> "SlabPlan":
+    def make(cls, res: Sequence[int], world: int, rank: int, margin: int = 2,
+             ranges: Optional[Sequence[Tuple[int, int]]] = None) -> "SlabPlan":
+        """``ranges``: owned base-cell range of every rank (contiguous, covering 0 .. res_x-2);
+        default: the even split."""
         res = tuple(int(r) for r in res)
-        rng = cls.ranges(res[0], world)
+        rng = [(int(a), int(b)) for a, b in ranges] if ranges is not None else cls.ranges(res[0], world)
+        if len(rng) != world or rng[0][0] != 0 or rng[-1][1] != res[0] - 1 or \
+                any(a[1] != b[0] for a, b in zip(rng[:-1], rng[1:])):
+            raise ValueError(f"ranges {rng} do not tile the base cells 0 .. {res[0] - 2} over {world} ranks")
         G = res[0] + 1
 
         def nodes(r):
             lo, hi = rng[r]
             return max(0, lo - margin), min(G, hi + margin + 2)
         for lo, hi in rng:
-            if world > 1 and hi - lo < 2 * margin + 2:
+            if world > 1 and hi - lo < cls.min_cells(margin):
                 raise ValueError("slabs are thinner than 2*margin+2 cells: halos would reach past the neighbour")
         g_lo, g_hi = nodes(rank)
         planes_lo = nodes(rank - 1)[1] - g_lo if rank > 0 else 0
         planes_hi = g_hi - nodes(rank + 1)[0] if rank < world - 1 else 0
-        return cls(res, world, rank, margin, rng[rank][0], rng[rank][1], g_lo, g_hi, planes_lo, planes_hi)
+        return cls(res, world, rank, margin, rng[rank][0], rng[rank][1], g_lo, g_hi, planes_lo, planes_hi, tuple(rng))
 
 
 # --------------------------------------------------------------------------- #
@@ -109,6 +164,16 @@ class LocalSlab:
     def payload_rows(self) -> int:
         raise NotImplementedError
 
+    # -- slab rebalancing (optional: SlabDriver.rebalance) -----------------------
+    def layer_histogram(self, cells: int) -> torch.Tensor:   # (cells,) int64: local particles per global base-cell layer
+        raise NotImplementedError
+
+    def take_all(self):                                      # -> (payload, base_x int64 (n,)); leaves the slab empty
+        raise NotImplementedError
+
+    def rebuild(self, plan: "SlabPlan", n_particles: int) -> None:   # empty local grid for ``plan``, room for n_particles
+        raise NotImplementedError
+
 
 class SlabDriver:
     def __init__(self, plan: SlabPlan, local: LocalSlab, group=None, migrate_every: Optional[int] = None):
@@ -127,6 +192,7 @@ class SlabDriver:
         self.recv_hi = torch.zeros(shape_hi, dtype=probe.dtype, device=probe.device)
         self.halo_bytes = (self.recv_lo.numel() + self.recv_hi.numel()) * probe.element_size()
         self.migrated = 0
+        self.rebalanced = 0
         self._pending = None
         if hasattr(local, "count_leavers_async") and plan.world > 1:
             # the leaver count is acted upon one substep after it was taken
@@ -208,6 +274,81 @@ class SlabDriver:
         self._events = []
         return dict(self.timing)
 
+    # -- slab rebalancing (per-slab particle counts every k steps) -------
+    def imbalance(self, layer_cost_per_cell: float = 0.03):
+        """Collective.  (counts per base-cell layer summed over the ranks, cost of the most loaded
+        rank / mean cost) under the present cut."""
+        p = self.plan
+        cells = p.res[0] - 1
+        hist = self.local.layer_histogram(cells)
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=self.group)
+        counts = hist.cpu().numpy()
+        cost = counts + layer_cost_per_cell * p.res[1] * p.res[2]
+        loads = [cost[lo:hi].sum() for lo, hi in p.all_ranges]
+        return counts, float(max(loads) / max(np.mean(loads), 1e-300))
+
+    def rebalance(self, min_gain: float = 0.1, layer_cost_per_cell: float = 0.03) -> bool:
+        """Collective.  Re-cut the slabs so that every rank carries about the same cost -- particles
+        plus ``layer_cost_per_cell`` per base cell of its range (the binning scans every cell; 0.03 is
+        the measured scan time per cell over the substep time per particle) -- and move every particle
+        to the owner of its base cell under the new cut, any number of ranks away.  The cut is a pure
+        function of the all-reduced layer histogram, so the ranks agree without further talk.  Nothing
+        happens (False) unless the most loaded rank gets at least ``min_gain`` lighter.
+
+        Call it between substeps.  It subsumes a migration round (a particle that strayed into the halo
+        margin is delivered to its owner too) and voids a pending lagged leaver count."""
+        p, L = self.plan, self.local
+        if p.world == 1:
+            return False
+        counts, _ = self.imbalance(layer_cost_per_cell)
+        layer_cost = layer_cost_per_cell * p.res[1] * p.res[2]
+        new = SlabPlan.balanced_ranges(counts, p.world, SlabPlan.min_cells(p.margin), layer_cost)
+        cost = counts + layer_cost
+
+        def worst(ranges):
+            return max(cost[lo:hi].sum() for lo, hi in ranges)
+        if tuple(new) == tuple(p.all_ranges) or worst(new) > (1.0 - min_gain) * worst(p.all_ranges):
+            return False
+        new_plan = SlabPlan.make(p.res, p.world, p.rank, p.margin, ranges=new)
+        # split the local particles by destination (base cells outside 0 .. cells-1 are out-of-grid
+        # particles: they stay with the edge ranks, as in the kernels' trailing bin)
+        (data, ids), base_x = L.take_all()
+        cuts = torch.tensor([hi for _, hi in new[:-1]], dtype=torch.int64, device=base_x.device)
+        dest = torch.bucketize(base_x, cuts, right=True)
+        parts = []
+        for r in range(p.world):
+            sel = torch.nonzero(dest == r).flatten()
+            parts.append((data[:, sel].contiguous(), ids[sel].contiguous()))
+        del data, ids, dest
+        dev = L.device
+        n_out = torch.tensor([q[1].numel() for q in parts], dtype=torch.int64, device=dev)
+        table = [torch.zeros_like(n_out) for _ in range(p.world)]
+        dist.all_gather(table, n_out, group=self.group)
+        n_in = [int(t[p.rank]) for t in table]                 # n_in[r]: particles rank r holds for this rank
+        rows = L.payload_rows()
+        recv, ops = {}, []
+        for r in range(p.world):
+            if r == p.rank:
+                continue
+            if parts[r][1].numel():
+                ops += [dist.P2POp(dist.isend, parts[r][0], r, self.group), dist.P2POp(dist.isend, parts[r][1], r, self.group)]
+            if n_in[r]:
+                recv[r] = (torch.empty((rows, n_in[r]), dtype=L.dtype, device=dev),
+                           torch.empty((n_in[r],), dtype=torch.int32, device=dev))
+                ops += [dist.P2POp(dist.irecv, recv[r][0], r, self.group), dist.P2POp(dist.irecv, recv[r][1], r, self.group)]
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        L.rebuild(new_plan, sum(n_in))
+        L.append(parts[p.rank])
+        for r in sorted(recv):
+            L.append(recv[r])
+            self.migrated += n_in[r]
+        self.plan = new_plan
+        self._pending = None
+        self.rebalanced += 1
+        return True
+
     # -- particle migration to the +-1 neighbours -------------------------------
     def migrate(self) -> None:
         p, L = self.plan, self.local
@@ -257,19 +398,27 @@ class CudaSlab(LocalSlab):
 
     def __init__(self, plan: SlabPlan, dx: float, dt: float, volume: float, gravity: float, hardening: float, *,
                  capacity: int, device, dtype=torch.float32, p2g_mode: str = "auto"):
-        from .mpm import MpmSolver
-        self.plan = plan
         self.device = torch.device(device)
         self.dtype = dtype
-        self.inv_dx = 1.0 / dx
-        self.solver = MpmSolver(3, list(plan.res), dt, volume, gravity, hardening, capacity=capacity, dx=dx,
-                                inv_dx=1.0 / dx, dtype=dtype, device=device,
+        self.dx, self.inv_dx = dx, 1.0 / dx
+        self._scalars = (dt, volume, gravity, hardening)
+        self._p2g_mode = p2g_mode
+        self._g2p_counts = p2g_mode != "fused"
+        self.launches_carried = 0      # kernel launches of the solvers a rebalancing replaced
+        self._make_solver(plan, capacity)
+
+    def _make_solver(self, plan: SlabPlan, capacity: int) -> None:
+        from .mpm import MpmSolver
+        dt, volume, gravity, hardening = self._scalars
+        self.plan = plan
+        self.solver = MpmSolver(3, list(plan.res), dt, volume, gravity, hardening, capacity=capacity, dx=self.dx,
+                                inv_dx=self.inv_dx, dtype=self.dtype, device=self.device,
                                 n_nodes=(plan.n_local_x, plan.res[1] + 1, plan.res[2] + 1),
-                                origin=(plan.g_lo, 0, 0), per_particle_material=None, p2g_mode=p2g_mode, reorder=True)
+                                origin=(plan.g_lo, 0, 0), per_particle_material=None, p2g_mode=self._p2g_mode,
+                                reorder=True)
         # the binned G2P counts the particles that left [own_lo, own_hi) while it advects them
         self.solver.set_owned_range(plan.own_lo if plan.rank > 0 else -(2 ** 31),
                                     plan.own_hi if plan.rank < plan.world - 1 else 2 ** 31 - 1)
-        self._g2p_counts = p2g_mode != "fused"
 
     @property
     def num_particles(self) -> int:
@@ -409,6 +558,44 @@ class CudaSlab(LocalSlab):
         self._store(payload, n, live)
         s._bind(n + payload[0].shape[1], cur=live)
 
+    # -- slab rebalancing ---------------------------------------------------------
+    def _base_x(self, n: int) -> torch.Tensor:
+        """Global base-cell layer of the first n live particles, by the kernels' own expression
+        (trunc toward zero of x*inv_dx - 0.5 evaluated in fp64 from the stored position)."""
+        x0 = self.solver.live.x[0, :n]
+        return torch.trunc(x0.double() * self.inv_dx - 0.5).to(torch.int64)
+
+    def layer_histogram(self, cells: int) -> torch.Tensor:
+        n = self.solver.num_particles
+        if n == 0:
+            return torch.zeros(cells, dtype=torch.int64, device=self.device)
+        return torch.bincount(self._base_x(n).clamp_(0, cells - 1), minlength=cells)
+
+    def take_all(self):
+        s = self.solver
+        n = s.num_particles
+        idx = torch.arange(n, dtype=torch.int64, device=self.device)
+        payload, base_x = self._pack(s.live, idx), self._base_x(n)
+        s._bind(0, cur=s.live_index)
+        return payload, base_x
+
+    def rebuild(self, plan: SlabPlan, n_particles: int) -> None:
+        """New local grid (extent, origin, workspace) for ``plan``; the material representation the
+        ranks agreed on in ``set_particles`` is carried over, so payload rows keep their meaning."""
+        old = self.solver
+        b = old.live
+        kind = "planes" if b.mass is not None else ("rows" if b.material is not None else "none")
+        table = old.material_table
+        capacity = max(old.capacity, n_particles + n_particles // 4 + 1024)
+        torch.cuda.synchronize(self.device)
+        self.launches_carried += old.launch_count()
+        old.close()
+        old.buffers, old.workspace = [], None
+        self.solver = None
+        del old, b
+        self._make_solver(plan, capacity)
+        self.solver.adopt_material_layout(kind, table)
+
     def state_by_id(self):
         """(ids, x, v, F, C) of the local particles, for gathering / validation."""
         s = self.solver
@@ -446,8 +633,8 @@ class SlabSolver:
     def from_dam_break(cls, rank: int, world: int, device, res: int = 256, n_total: int = 33_554_432,
                        margin: int = 4, capacity: Optional[int] = None, p2g_mode: str = "auto"):
         """BASELINE configs[4]: soft column at one x-end of a (res*world) x res x res domain;
-        every rank generates the particles of its own x interval.  Slabs are static (no
-        rebalancing yet), so ranks away from the column start empty."""
+        every rank generates the particles of its own x interval.  The even cut leaves the ranks
+        away from the column empty; ``rebalance()`` re-cuts the slabs by particle count."""
         from . import scenes
         plan = SlabPlan.make((res * world, res, res), world, rank, margin)
         dx = 1.0 / res
@@ -458,8 +645,8 @@ class SlabSolver:
         local = CudaSlab(plan, dx, sc.dt, sc.volume, sc.gravity, sc.hardening, capacity=cap, device=device,
                          p2g_mode=p2g_mode)
         ids = (np.arange(sc.n, dtype=np.int64) + rank * (2 ** 27)) % (2 ** 31)
-        if sc.n:
-            local.set_particles(sc.x, sc.v, sc.F, sc.C, sc.mass, sc.mu_0, sc.lambda_0, ids.astype(np.int32))
+        # collective (the ranks agree on the material table): ranks that start empty take part too
+        local.set_particles(sc.x, sc.v, sc.F, sc.C, sc.mass, sc.mu_0, sc.lambda_0, ids.astype(np.int32))
         obj = cls(plan, local, SlabDriver(plan, local))
         obj.scene_name = sc.name
         return obj
@@ -471,8 +658,14 @@ class SlabSolver:
     def substep(self, n: int = 1) -> None:
         self.driver.substep(n)
 
+    def rebalance(self, **kw) -> bool:
+        """Collective: ``SlabDriver.rebalance``; the plan of this bundle follows the driver's."""
+        done = self.driver.rebalance(**kw)
+        self.plan = self.driver.plan
+        return done
+
     def poll_error(self) -> int:
         return self.local.solver.poll_error()
 
     def launch_count(self) -> int:
-        return self.local.solver.launch_count()
+        return self.local.solver.launch_count() + self.local.launches_carried

@@ -268,6 +268,26 @@ class MpmSolver:
                 self.buffers[0].material[:n] = inv.to(torch.uint8)
             self.material_layout = f"table[{rows.shape[0]}]"
 
+    def adopt_material_layout(self, kind: str, table: Optional[torch.Tensor]) -> None:
+        """Take over a material representation decided elsewhere (``kind``: ``planes`` / ``rows`` /
+        ``none`` as in ``_StateBuffer.set_material_storage``; ``table``: its (R, 3) rows or None) instead
+        of deriving one from the data of ``set_particles`` -- a slab re-created by a rebalancing keeps
+        the table all ranks agreed on.  Leaves the solver bound to zero particles."""
+        if (kind == "planes") != (table is None):
+            raise ValueError("material planes come without a table; rows / none need one")
+        for b in self.buffers:
+            b.set_material_storage(kind)
+        self._material_auto = False
+        self.material_table = table
+        if table is None:
+            N.check(self.lib.ffmpm_set_materials(self._h, None, None, None, 0))
+            self.material_layout = "planes"
+        else:
+            r = table.double().cpu().numpy()
+            self.set_materials(r[:, 0], r[:, 1], r[:, 2])
+            self.material_layout = f"table[{table.shape[0]}]"
+        self._bind(0)
+
     def get_particles(self) -> Dict[str, torch.Tensor]:
         """State in the ORIGINAL particle order, reference layouts, device tensors."""
         b = self.live

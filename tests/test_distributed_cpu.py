@@ -92,6 +92,22 @@ class OracleSlab(LocalSlab):
             setattr(self, name, getattr(self, name)[keep])
         return left, right
 
+    # slab rebalancing
+    def layer_histogram(self, cells):
+        base, _ = O.base_and_fx(self.x, self.p["inv_dx"])
+        return torch.from_numpy(np.bincount(np.clip(base[:, 0], 0, cells - 1), minlength=cells).astype(np.int64))
+
+    def take_all(self):
+        base, _ = O.base_and_fx(self.x, self.p["inv_dx"])
+        payload = self._pack(np.arange(len(self.x)))
+        for name in ("x", "v", "F", "C", "mass", "mu0", "lam0", "ids"):
+            setattr(self, name, getattr(self, name)[:0])
+        return payload, torch.from_numpy(base[:, 0].astype(np.int64))
+
+    def rebuild(self, plan, n_particles):
+        self.plan = plan          # the stand-in computes on the whole global grid; only the exchanged planes move
+        self.rebuilt_for = n_particles
+
     # optional asynchronous-count interface (exercises SlabDriver's lagged migration decision)
     lagged = False
 
@@ -179,5 +195,88 @@ def test_slabs_match_single_domain(tmp_path, world, margin, migrate_every, lagge
                            x, mass, mu0, lam0, v, F, C, Jp)
     assert np.array_equal(got["ids"], ids)                     # nobody lost, nobody duplicated
     assert got["migrated"] > 0                                 # the scene really exercises migration
+    for k, ref in (("x", x), ("v", v), ("F", F), ("C", C)):
+        assert np.abs(got[k] - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), k
+
+
+def test_balanced_ranges():
+    counts = np.zeros(63, dtype=np.int64)
+    counts[5:15] = 1000                                         # a column near the low end
+    r = SlabPlan.balanced_ranges(counts, 4, min_cells=6)
+    assert r[0][0] == 0 and r[-1][1] == 63 and all(a[1] == b[0] for a, b in zip(r[:-1], r[1:]))
+    assert all(hi - lo >= 6 for lo, hi in r)
+    loads = [counts[lo:hi].sum() for lo, hi in r]
+    assert max(loads) == 5000            # optimum under the width constraint (10 column layers, slabs >= 6); even cut: 10000
+    # uniform counts reproduce (about) the even split, and the layer cost spreads empty space
+    u = SlabPlan.balanced_ranges(np.full(63, 10), 3, 6)
+    assert [hi - lo for lo, hi in u] == [21, 21, 21]
+    e = SlabPlan.balanced_ranges(np.zeros(63), 3, 6, layer_cost=1.0)
+    assert [hi - lo for lo, hi in e] == [21, 21, 21]
+    with pytest.raises(ValueError):
+        SlabPlan.balanced_ranges(np.zeros(15), 3, 6)
+    # explicit ranges round-trip through make(); ranges that do not tile are refused
+    plan = SlabPlan.make((64, 64, 64), 4, 1, margin=2, ranges=r)
+    assert (plan.own_lo, plan.own_hi) == r[1] and plan.all_ranges == tuple(r)
+    assert plan.planes_lo == plan.planes_hi == 6
+    with pytest.raises(ValueError):
+        SlabPlan.make((64, 64, 64), 2, 0, margin=2, ranges=[(0, 30), (31, 63)])
+
+
+def make_lopsided_scene(res=32, n=1800, seed=5):
+    """All particles in the low-x third of the domain, drifting towards +x: the even cut leaves
+    the upper ranks idle."""
+    p, (x, v, F, C, mass, mu0, lam0, ids) = make_scene(res=res, n=n, seed=seed)
+    x[:, 0] = 0.12 + (x[:, 0] - 0.15) * (0.30 / 0.70)
+    v[:, 0] = np.abs(v[:, 0])
+    return p, (x, v, F, C, mass, mu0, lam0, ids)
+
+
+def _rebalance_worker(rank, world, port, margin, lagged, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        p, state = make_lopsided_scene()
+        plan = SlabPlan.make((p["res"],) * 3, world, rank, margin)
+        base, _ = O.base_and_fx(state[0], p["inv_dx"])
+        mine = np.flatnonzero((base[:, 0] >= plan.own_lo) & (base[:, 0] < plan.own_hi))
+        local = OracleSlab(plan, p, tuple(a[mine].copy() for a in state))
+        local.lagged = lagged
+        drv = SlabDriver(plan, local, migrate_every=1)
+        drv.substep(2)
+        _, before = drv.imbalance(0.0)
+        assert drv.rebalance(layer_cost_per_cell=0.0)
+        _, after = drv.imbalance(0.0)
+        assert not drv.rebalance(layer_cost_per_cell=0.0)         # a second call has nothing to gain
+        counts_after = local.num_particles
+        drv.substep(3)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (local.ids, local.x, local.v, local.F, local.C, counts_after,
+                                          (drv.plan.own_lo, drv.plan.own_hi)))
+        if rank == 0:
+            ids = np.concatenate([g[0] for g in gathered])
+            order = np.argsort(ids)
+            res = {k: np.concatenate([g[i] for g in gathered])[order] for i, k in ((1, "x"), (2, "v"), (3, "F"), (4, "C"))}
+            res.update(ids=ids[order], counts=[g[5] for g in gathered], ranges=[g[6] for g in gathered],
+                       before=before, after=after)
+            torch.save(res, out)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,margin,lagged", [(3, 2, False), (2, 3, True), (4, 1, False)])
+def test_rebalanced_slabs_match_single_domain(tmp_path, world, margin, lagged):
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_rebalance_worker, args=(world, _free_port(), margin, lagged, out), nprocs=world, join=True)
+    got = torch.load(out, weights_only=False)
+    p, (x, v, F, C, mass, mu0, lam0, ids) = make_lopsided_scene()
+    Jp = np.ones((len(x), 1))
+    for _ in range(5):
+        O.solve_mls_mpm_3d(p["res"], p["inv_dx"], p["hardening"], p["dx"], p["dt"], p["volume"], p["gravity"],
+                           x, mass, mu0, lam0, v, F, C, Jp)
+    assert np.array_equal(got["ids"], ids)
+    assert got["after"] < got["before"]                          # the most loaded rank got lighter ...
+    assert max(got["counts"]) < len(ids)                         # ... and no longer holds everything
+    r = got["ranges"]
+    assert r[0][0] == 0 and r[-1][1] == p["res"] - 1 and all(a[1] == b[0] for a, b in zip(r[:-1], r[1:]))
     for k, ref in (("x", x), ("v", v), ("F", F), ("C", C)):
         assert np.abs(got[k] - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), k

@@ -86,3 +86,131 @@ def test_two_gpu_slabs_match_oracle(tmp_path, nmat):
     assert np.abs(got["v"] - v).max() / V < tol
     assert np.abs(got["F"] - F).max() < tol
     assert np.abs(got["C"] - C).max() / (4 * p["inv_dx"] * V) < tol
+
+
+def _lopsided(nmat):
+    """_scene() squeezed into the low-x 40 % of the domain: the even cut leaves rank 1 idle."""
+    p, (x, v, F, C, mass, mu0, lam0, ids) = _scene(nmat)
+    x = x.copy()
+    x[:, 0] = 0.12 + (x[:, 0] - 0.15) * (0.28 / 0.70)
+    x = x.astype(np.float32).astype(np.float64)
+    return p, (x, v, F, C, mass, mu0, lam0, ids)
+
+
+def _oracle_run(p, state, steps):
+    from oracle import mpm_oracle as O
+    x, v, F, C, mass, mu0, lam0, ids = (a.copy() for a in state)
+    Jp = np.ones((len(x), 1))
+    for _ in range(steps):
+        O.solve_mls_mpm_3d(p["res"], p["inv_dx"], p["hardening"], p["dx"], p["dt"], p["volume"], p["gravity"],
+                           x, mass, mu0, lam0, v, F, C, Jp)
+    return x, v, F, C
+
+
+def _assert_close(p, got, ref, steps):
+    x, v, F, C = ref
+    V = max(np.abs(v).max(), p["dt"] * 9.8)
+    tol = 1e-5 * steps
+    assert np.abs(got["x"] - x).max() < tol
+    assert np.abs(got["v"] - v).max() / V < tol
+    assert np.abs(got["F"] - F).max() < tol
+    assert np.abs(got["C"] - C).max() / (4 * p["inv_dx"] * V) < tol
+
+
+@pytest.mark.parametrize("nmat", [1, 3])
+def test_cuda_slab_rebuild_one_gpu(nmat):
+    """CudaSlab.take_all / rebuild / append (the local half of SlabDriver.rebalance) on one GPU: rank 0
+    of a two-slab cut is moved from cells [0, 16) to [0, 21) between substeps.  All particles live on
+    rank 0 (the absent rank 1 would contribute zero to the shared planes), so no halo exchange is needed
+    and the single-domain oracle is the reference."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from femflow_b200.distributed import CudaSlab, SlabPlan
+    p, state = _lopsided(nmat)
+    x, v, F, C, mass, mu0, lam0, ids = state
+    assert x[:, 0].max() * p["inv_dx"] < 13.5           # base cell <= 12 now, <= 14 after 4 substeps: inside both local grids
+    res = (p["res"],) * 3
+    plan_a = SlabPlan.make(res, 2, 0, margin=2, ranges=[(0, 16), (16, 31)])
+    plan_b = SlabPlan.make(res, 2, 0, margin=2, ranges=[(0, 21), (21, 31)])
+    dev = torch.device("cuda", 0)
+    local = CudaSlab(plan_a, p["dx"], p["dt"], p["volume"], p["gravity"], p["hardening"], capacity=len(x), device=dev)
+    local.set_particles(x, v, F, C, mass, mu0, lam0, ids)
+    layout = local.solver.material_layout
+
+    def substeps(k):
+        for _ in range(k):
+            local.scatter()
+            local.grid_update(None, 0, None, 0)
+            local.gather()
+
+    substeps(2)
+    hist = local.layer_histogram(p["res"] - 1)
+    assert int(hist.sum()) == len(x) and int(hist[14:].sum()) == 0
+    launches = local.solver.launch_count()
+    payload, base_x = local.take_all()
+    assert local.num_particles == 0 and payload[0].shape == (27, len(x)) and int(base_x.max()) <= 13
+    local.rebuild(plan_b, len(x))
+    assert local.solver.n[0] == plan_b.n_local_x == 21 + 2 + 2 and local.solver.material_layout == layout
+    assert local.launches_carried == launches
+    local.append(payload)
+    assert local.num_particles == len(x)
+    substeps(2)
+    assert local.solver.poll_error() == 0
+    idv, gx, gv, gF, gC = (t.cpu().numpy() for t in local.state_by_id())
+    order = np.argsort(idv)
+    assert np.array_equal(idv[order], ids)
+    got = {"x": gx[order], "v": gv[order], "F": gF[order], "C": gC[order]}
+    _assert_close(p, got, _oracle_run(p, state, 4), 4)
+
+
+def _rebalance_worker(rank, world, port, out, nmat):
+    import torch.distributed as dist
+    from femflow_b200.distributed import CudaSlab, SlabDriver, SlabPlan
+    from oracle import mpm_oracle as O
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        p, state = _lopsided(nmat)
+        x, v, F, C, mass, mu0, lam0, ids = state
+        plan = SlabPlan.make((p["res"],) * 3, world, rank, margin=2)
+        base, _ = O.base_and_fx(x, p["inv_dx"])
+        mine = np.flatnonzero((base[:, 0] >= plan.own_lo) & (base[:, 0] < plan.own_hi))
+        local = CudaSlab(plan, p["dx"], p["dt"], p["volume"], p["gravity"], p["hardening"], capacity=len(x), device=dev)
+        local.set_particles(x[mine], v[mine], F[mine], C[mine], mass[mine], mu0[mine], lam0[mine], ids[mine])
+        drv = SlabDriver(plan, local, migrate_every=1)
+        drv.substep(2)
+        _, before = drv.imbalance(0.0)
+        assert drv.rebalance(layer_cost_per_cell=0.0)
+        _, after = drv.imbalance(0.0)
+        count = local.num_particles
+        drv.substep(4)
+        assert local.solver.poll_error() == 0
+        got = [t.cpu().numpy() for t in local.state_by_id()]
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (got, count, before, after))
+        if rank == 0:
+            idv = np.concatenate([g[0][0] for g in gathered])
+            order = np.argsort(idv)
+            res = {k: np.concatenate([g[0][i] for g in gathered])[order] for i, k in ((1, "x"), (2, "v"), (3, "F"), (4, "C"))}
+            res.update(ids=idv[order], counts=[g[1] for g in gathered], before=before, after=after)
+            torch.save(res, out)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_rebalance_matches_oracle(tmp_path):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_rebalance_worker, args=(2, port, out, 3), nprocs=2, join=True)
+    got = torch.load(out, weights_only=False)
+    p, state = _lopsided(3)
+    assert np.array_equal(got["ids"], state[7])
+    assert got["after"] < got["before"] and min(got["counts"]) > 0      # rank 1 started empty
+    _assert_close(p, got, _oracle_run(p, state, 6), 6)
