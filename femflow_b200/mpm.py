@@ -273,10 +273,13 @@ class MpmSolver:
         ``none`` as in ``_StateBuffer.set_material_storage``; ``table``: its (R, 3) rows or None) instead
         of deriving one from the data of ``set_particles`` -- a slab re-created by a rebalancing keeps
         the table all ranks agreed on.  Leaves the solver bound to zero particles."""
-        if (kind == "planes") != (table is None):
-            raise ValueError("material planes come without a table; rows / none need one")
+        if kind == "planes" and table is not None or kind == "rows" and table is None:
+            raise ValueError("material planes come without a table; rows need one")
         for b in self.buffers:
             b.set_material_storage(kind)
+        if kind == "none" and table is None:      # nothing was ever decided: the config scalars stay in effect
+            self._bind(0)
+            return
         self._material_auto = False
         self.material_table = table
         if table is None:
