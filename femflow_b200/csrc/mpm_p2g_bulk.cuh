@@ -15,9 +15,9 @@
 
 namespace ffmpm {
 
-template <int NBUF>
+template <int NBUF, int RAWP = P2G_NPLANES>
 struct P2GBulkWarp {
-  alignas(128) float raw[NBUF][P2G_NPLANES][P2G_WINDOW];
+  alignas(128) float raw[NBUF][RAWP][P2G_WINDOW];   // RAWP = 24: no room for material planes (table / config material)
   P2GWarpSlab<float> slab;
   alignas(16) unsigned char mat[NBUF][P2G_WINDOW];   // material rows of the window (table mode)
   alignas(8) unsigned long long bar[NBUF];
@@ -83,14 +83,18 @@ __device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
 // LDGSTS: 0 = bulk copies by the TMA engine (cp.async.bulk + mbarrier, one elected lane);
 //         1 = per-lane 16-byte cp.async (LDGSTS): two planes per warp instruction, 14
 //             instructions per window -- fewer issue slots than 27 elected UBLKCP sequences.
-template <int WARPS, int NBUF, int LDGSTS>
-__global__ void __launch_bounds__(WARPS * 32, 16 / WARPS)   // <= 128 registers: 16 warps per SM
+// RAWP / SMW: planes held per window and resident warps per SM the launch bounds ask for.  <27, 16> is the
+// measured default (128 registers); <24, 20> (no material planes: 11.1 KB of shared memory per warp, 5 CTAs
+// of 4 warps, <= 96 registers) is the occupancy experiment behind FFMPM_P2G_VARIANT=6.
+template <int WARPS, int NBUF, int LDGSTS, int RAWP = P2G_NPLANES, int SMW = 16>
+__global__ void __launch_bounds__(WARPS * 32, SMW / WARPS)
 p2g_bulk3_kernel(DevCfg cfg, P2GPlanes planes, long long n, float* __restrict__ grid, ErrRec* err, int wpw) {
   using T = float;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  P2GBulkWarp<NBUF>* warps = reinterpret_cast<P2GBulkWarp<NBUF>*>(smem_raw);
+  using WarpMem = P2GBulkWarp<NBUF, RAWP>;
+  WarpMem* warps = reinterpret_cast<WarpMem*>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  P2GBulkWarp<NBUF>& W = warps[warp];
+  WarpMem& W = warps[warp];
   P2GWarpSlab<T>& S = W.slab;
   const T dx = (T)cfg.dx;
   const int ny = cfg.n[1], nz = cfg.n[2];
@@ -120,7 +124,7 @@ p2g_bulk3_kernel(DevCfg cfg, P2GPlanes planes, long long n, float* __restrict__ 
         const int k0 = 2 * j, k1 = 2 * j + 1;
         const float* src = (hi && k1 < P2G_NPLANES) ? planes.p[k1 < P2G_NPLANES ? k1 : k0] : planes.p[k0];
         const int k = hi ? k1 : k0;
-        if (k < n_planes) cp_async16(&W.raw[buf][k][(lane & 15) * 4], src + w0);
+        if (k < n_planes && k < RAWP) cp_async16(&W.raw[buf][k][(lane & 15) * 4], src + w0);
       }
       if (planes.material && lane < P2G_WINDOW / 16)
         cp_async16(&W.mat[buf][lane * 16], planes.material + (long long)win * P2G_WINDOW + lane * 16);
@@ -134,7 +138,7 @@ p2g_bulk3_kernel(DevCfg cfg, P2GPlanes planes, long long n, float* __restrict__ 
       if (planes.material) bulk_load_s(&W.mat[buf][0], planes.material + w0, P2G_WINDOW, &W.bar[buf]);
 #pragma unroll
       for (int k = 0; k < P2G_NPLANES; ++k)
-        if (k < n_planes) bulk_load_s(&W.raw[buf][k][0], planes.p[k] + w0, P2G_WINDOW * 4u, &W.bar[buf]);
+        if (k < n_planes && k < RAWP) bulk_load_s(&W.raw[buf][k][0], planes.p[k] + w0, P2G_WINDOW * 4u, &W.bar[buf]);
     }
   };
 
@@ -165,6 +169,7 @@ p2g_bulk3_kernel(DevCfg cfg, P2GPlanes planes, long long n, float* __restrict__ 
             cfg,
             [&](int k) -> T {
               if (k >= P2G_MASS && planes.table) return __ldg(planes.table + (k - P2G_MASS) * MAT_ROWS + row);
+              if (k >= RAWP) return (T)0;          // RAWP = 24 is launched only without material planes
               return W.raw[buf][k][idx];
             },
             has_mat, 1.0);
@@ -179,13 +184,13 @@ p2g_bulk3_kernel(DevCfg cfg, P2GPlanes planes, long long n, float* __restrict__ 
   }
 }
 
-template <int WARPS, int NBUF, int LDGSTS>
+template <int WARPS, int NBUF, int LDGSTS, int RAWP = P2G_NPLANES, int SMW = 16>
 static bool p2g_bulk_launch(const DevCfg& cfg, const StateView<float>& s, long long n, float* grid, ErrRec* err,
                             int sm_count, int blocks_per_sm, cudaStream_t st) {
-  const size_t smem = sizeof(P2GBulkWarp<NBUF>) * WARPS;
+  const size_t smem = sizeof(P2GBulkWarp<NBUF, RAWP>) * WARPS;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(p2g_bulk3_kernel<WARPS, NBUF, LDGSTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(p2g_bulk3_kernel<WARPS, NBUF, LDGSTS, RAWP, SMW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return false;
     configured = true;
   }
@@ -200,7 +205,7 @@ static bool p2g_bulk_launch(const DevCfg& cfg, const StateView<float>& s, long l
     blocks = (int)(want < cap ? want : cap);
   }
   if (blocks < 1) blocks = 1;
-  p2g_bulk3_kernel<WARPS, NBUF, LDGSTS><<<blocks, WARPS * 32, smem, st>>>(cfg, p2g_planes_of(s), n, grid, err, wpw);
+  p2g_bulk3_kernel<WARPS, NBUF, LDGSTS, RAWP, SMW><<<blocks, WARPS * 32, smem, st>>>(cfg, p2g_planes_of(s), n, grid, err, wpw);
   return true;
 }
 
