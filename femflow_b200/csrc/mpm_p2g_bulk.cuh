@@ -188,11 +188,14 @@ template <int WARPS, int NBUF, int LDGSTS, int RAWP = P2G_NPLANES, int SMW = 16>
 static bool p2g_bulk_launch(const DevCfg& cfg, const StateView<float>& s, long long n, float* grid, ErrRec* err,
                             int sm_count, int blocks_per_sm, cudaStream_t st) {
   const size_t smem = sizeof(P2GBulkWarp<NBUF, RAWP>) * WARPS;
-  static bool configured = false;
-  if (!configured) {
+  // function attributes are per device: a process that drives several GPUs configures each once
+  static bool configured[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+  if (!configured[dev]) {
     if (cudaFuncSetAttribute(p2g_bulk3_kernel<WARPS, NBUF, LDGSTS, RAWP, SMW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return false;
-    configured = true;
+    configured[dev] = true;
   }
   long long windows = (n + P2G_WINDOW - 1) / P2G_WINDOW;
   static int wpw = [] { const char* e = getenv("FFMPM_P2G_WPW"); return e ? atoi(e) : 16; }();
