@@ -160,6 +160,9 @@ def main():
                     help="per-particle material layout (N=1): auto = table/rows when <= 256 distinct triples, planes = 3 scalar planes")
     ap.add_argument("--slab-timing", action="store_true", help="N>1: print per-phase CUDA-event times per rank to stderr")
     ap.add_argument("--margin", type=int, default=4, help="slab halo margin in cells = substeps between migrations")
+    ap.add_argument("--graph", action="store_true",
+                    help="N=1: replay the timed substeps as CUDA graphs of 10 substeps (MpmSolver.make_graph); "
+                         "measured -11 %% on 2d1m, -4 %% on a 2M-particle 3D block (profiles/r01q_graph_experiment.json)")
     ap.add_argument("--rebalance", action="store_true",
                     help="dam workloads, N>1: re-cut the slabs by particle count before the warm-up (SlabDriver.rebalance)")
     ap.add_argument("--rebalance-every", type=int, default=0,
@@ -233,18 +236,25 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    graph = None
+    if args.graph and world == 1 and not dam and args.steps % 10 == 0:
+        graph = solver.make_graph(10)         # captured from the warmed-up (pre-binned) state; does not execute
     l0 = solver.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
-    for k in range(args.steps):
-        solver.substep(1)
-        if dam and world > 1 and args.rebalance and args.rebalance_every and (k + 1) % args.rebalance_every == 0:
-            solver.rebalance()
+    if graph is not None:
+        for _ in range(args.steps // 10):
+            graph.replay()
+    else:
+        for k in range(args.steps):
+            solver.substep(1)
+            if dam and world > 1 and args.rebalance and args.rebalance_every and (k + 1) % args.rebalance_every == 0:
+                solver.rebalance()
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    launches = solver.launch_count() - l0
+    launches = solver.launch_count() - l0 if graph is None else solver.graph_launches * (args.steps // 10)
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -388,7 +398,7 @@ def main():
         "dtype": "f32 (cell indexing in f64; stress in f32 perturbation form, f64 fallback at large strain)",
         "data": "synthetic",
         "config": {"workload": scene.name, "particles_per_gpu": n, "particles_total": n_total,
-                   "grid": f"{scene.res}^{scene.dim}", "dt": scene.dt, "p2g_mode": args.p2g_mode,
+                   "grid": f"{scene.res}^{scene.dim}", "dt": scene.dt, "p2g_mode": args.p2g_mode, "cuda_graph": bool(args.graph and world == 1 and not dam and args.steps % 10 == 0),
                    "l2": ("inputs larger than L2 (no flush)" if n * (112 if scene.dim == 3 else 52) > 2 * 126e6
                           else "particle state fits in the 126 MB L2 (flagged: HBM fraction is not meaningful)"),
                    "n_oob": n_oob,

@@ -366,6 +366,37 @@ def test_multi_substep_pipelines_vs_oracle(mode):
     s.close()
 
 
+def test_graph_replay_matches_eager_substeps():
+    """MpmSolver.make_graph: 3 replays of a captured pair of substeps (internal binning stream and both
+    ping-pong halves inside the capture) against the same 6 substeps launched one by one, from the same
+    warmed-up state.  Only the order of the atomic sums may differ (scripts/graph_experiment.py,
+    profiles/r01q_graph_experiment.json: x 6e-8, v 8e-7, F 2.4e-7 absolute)."""
+    from femflow_b200 import scenes
+    from femflow_b200.mpm import MpmSolver
+    sc = scenes.elastic_block(3, 64, 24, 2, seed=1)
+
+    def make():
+        s = MpmSolver(3, sc.res, sc.dt, sc.volume, sc.gravity, sc.hardening, capacity=sc.n)
+        s.set_particles(sc.x, sc.v, sc.F, sc.C, None, sc.mass, sc.mu_0, sc.lambda_0)
+        return s
+    a, b = make(), make()
+    a.substep(8)
+    b.substep(2)                          # steady state: the live buffer is pre-binned by the last G2P
+    g = b.make_graph(2)
+    assert b.graph_substeps == 2 and b.graph_launches > 0
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    a.check_errors(); b.check_errors()
+    pa, pb = a.get_particles(), b.get_particles()
+    V = max(float(pa["v"].abs().max()), sc.dt * 9.8)
+    assert float((pa["x"] - pb["x"]).abs().max()) < 1e-5
+    assert float((pa["v"] - pb["v"]).abs().max()) / V < 1e-4
+    assert float((pa["F"] - pb["F"]).abs().max()) < 1e-5
+    assert float((pa["C"] - pb["C"]).abs().max()) / (4 * sc.res * V) < 1e-4
+    a.close(); b.close()
+
+
 @pytest.mark.parametrize("n_materials", [1, 3, 300])
 @pytest.mark.parametrize("mode", ["auto", "fused", "scatter"])
 def test_material_layouts_agree(n_materials, mode):
