@@ -160,6 +160,9 @@ def main():
                     help="per-particle material layout (N=1): auto = table/rows when <= 256 distinct triples, planes = 3 scalar planes")
     ap.add_argument("--slab-timing", action="store_true", help="N>1: print per-phase CUDA-event times per rank to stderr")
     ap.add_argument("--margin", type=int, default=4, help="slab halo margin in cells = substeps between migrations")
+    ap.add_argument("--halo", default="p2p", choices=["p2p", "symm"],
+                    help="N>1: halo planes by NCCL send/recv (p2p) or by one-sided puts into the neighbour's "
+                         "symmetric-memory inbox over NVLink (symm; SymmHalo, not yet measured)")
     ap.add_argument("--graph", action="store_true",
                     help="N=1: replay the timed substeps as CUDA graphs of 10 substeps (MpmSolver.make_graph); "
                          "measured -11 %% on 2d1m, -4 %% on a 2M-particle 3D block (profiles/r01q_graph_experiment.json)")
@@ -203,7 +206,7 @@ def main():
         if world == 1:
             import torch.distributed as dist_  # noqa: F401  (single rank: the driver never communicates)
         solver = SlabSolver.from_dam_break(rank, world, dev, n_total=n_total_req, margin=args.margin,
-                                           p2g_mode=args.p2g_mode)
+                                           p2g_mode=args.p2g_mode, halo=args.halo)
         scene.name = solver.scene_name
         scene.dt = solver.local.solver.cfg.dt
         if args.rebalance and world > 1:
@@ -211,7 +214,8 @@ def main():
         n = solver.num_particles
     elif world > 1:
         from femflow_b200.distributed import SlabSolver
-        solver = SlabSolver.from_scene(scene, rank, world, dev, p2g_mode=args.p2g_mode, margin=args.margin)
+        solver = SlabSolver.from_scene(scene, rank, world, dev, p2g_mode=args.p2g_mode, margin=args.margin,
+                                       halo=args.halo)
     else:
         solver = MpmSolver(scene.dim, scene.res, scene.dt, scene.volume, scene.gravity, scene.hardening,
                            capacity=n, device=dev, mass=scene.mass, mu_0=scene.mu_0, lambda_0=scene.lambda_0,
@@ -403,7 +407,8 @@ def main():
                           else "particle state fits in the 126 MB L2 (flagged: HBM fraction is not meaningful)"),
                    "n_oob": n_oob,
                    "material_layout": (solver if world == 1 else solver.local.solver).material_layout,
-                   "parallelism": (f"{world} slabs along x, halo sum over NCCL p2p every substep, migration every "
+                   "parallelism": (f"{world} slabs along x, halo sum over "
+                                   f"{'NCCL p2p' if args.halo == 'p2p' else 'symmetric-memory puts'} every substep, migration every "
                                    f"{args.margin} substeps") if world > 1 else "single GPU",
                    **({"slab_particles": slab_counts, "slab_cells": [list(r) for r in solver.plan.all_ranges],
                        "rebalanced": solver.driver.rebalanced} if world > 1 else {})},

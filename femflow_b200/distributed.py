@@ -175,9 +175,85 @@ class LocalSlab:
         raise NotImplementedError
 
 
+# --------------------------------------------------------------------------- #
+class SymmHalo:
+    """Halo planes pushed straight into the neighbour's memory over NVLink (one-sided put into a
+    symmetric-memory inbox + a signal), instead of a matched NCCL send/recv pair.
+
+    Every rank owns an inbox ``[parity][side][planes, ny, nz, 4]`` allocated from
+    ``torch.distributed._symmetric_memory`` (CUDA IPC / NVLink peer mapping).  Per substep ``k``
+    (parity ``q = k & 1``) a rank
+
+      * copies its last shared planes into ``inbox[q][LO]`` OF THE RIGHT NEIGHBOUR and its first
+        shared planes into ``inbox[q][HI]`` OF THE LEFT NEIGHBOUR (plain peer stores),
+      * raises one flag per neighbour (``put_signal``, release at system scope, stream-ordered
+        after the copy), then waits for the two flags raised for it (``wait_signal``),
+      * hands ``inbox[q]`` to the grid update, which sums it while loading (``ffmpm_grid_op_halo``).
+
+    Everything is enqueued on the current stream; the host never blocks.  Two parities make reuse
+    safe without a second handshake: a neighbour writes ``inbox[q]`` for substep k+2 only after it
+    has seen this rank's flag of substep k+1, which this rank raises after its scatter of k+1, i.e.
+    (same stream) after its grid update of k consumed ``inbox[q]``.
+
+    ``fabric`` abstracts the allocator / rendezvous so that the protocol is unit-tested on CPU with a
+    shared-memory stand-in (tests/test_distributed_cpu.py); on GPUs it is torch's symmetric memory.
+    """
+    LO, HI = 0, 1
+
+    def __init__(self, plan: SlabPlan, plane_shape: Sequence[int], dtype, device, group=None, fabric=None,
+                 timeout_ms: int = 20000):
+        self.rank, self.world = plan.rank, plan.world
+        self.left = plan.rank - 1 if plan.rank > 0 else None
+        self.right = plan.rank + 1 if plan.rank < plan.world - 1 else None
+        self.planes = SlabPlan.min_cells(plan.margin)          # 2*margin + 2 on every interior cut
+        self.timeout_ms = int(timeout_ms)
+        shape = (2, 2, self.planes) + tuple(int(v) for v in plane_shape)
+        fabric = fabric if fabric is not None else _TorchSymmFabric()
+        self.inbox = fabric.empty(shape, dtype, device)
+        self.inbox.zero_()
+        self.handle = fabric.rendezvous(self.inbox, group)
+        self.peer = {nb: self.handle.get_buffer(nb, shape, dtype, 0) for nb in (self.left, self.right) if nb is not None}
+        self.handle.barrier(0, self.timeout_ms)               # every inbox is zeroed and mapped before the first put
+        self.bytes_per_step = 0
+
+    def exchange(self, step: int, send_lo: Optional[torch.Tensor], send_hi: Optional[torch.Tensor]):
+        """``send_lo`` / ``send_hi``: this rank's first / last shared planes (None at a domain end).
+        Returns the planes received from the left / right neighbour (None at a domain end)."""
+        q, h, t = step & 1, self.handle, self.timeout_ms
+        if self.right is not None:
+            self.peer[self.right][q, self.LO].copy_(send_hi)
+            h.put_signal(self.right, 2 * q + self.LO, t)
+        if self.left is not None:
+            self.peer[self.left][q, self.HI].copy_(send_lo)
+            h.put_signal(self.left, 2 * q + self.HI, t)
+        if self.left is not None:
+            h.wait_signal(self.left, 2 * q + self.LO, t)
+        if self.right is not None:
+            h.wait_signal(self.right, 2 * q + self.HI, t)
+        return (self.inbox[q, self.LO] if self.left is not None else None,
+                self.inbox[q, self.HI] if self.right is not None else None)
+
+
+class _TorchSymmFabric:
+    """torch.distributed._symmetric_memory as the SymmHalo fabric (GPUs of one NVLink domain)."""
+
+    def empty(self, shape, dtype, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        return symm_mem.empty(*shape, dtype=dtype, device=device)
+
+    def rendezvous(self, tensor, group):
+        import torch.distributed._symmetric_memory as symm_mem
+        return symm_mem.rendezvous(tensor, group if group is not None else dist.group.WORLD)
+
+
 class SlabDriver:
-    def __init__(self, plan: SlabPlan, local: LocalSlab, group=None, migrate_every: Optional[int] = None):
+    def __init__(self, plan: SlabPlan, local: LocalSlab, group=None, migrate_every: Optional[int] = None,
+                 halo: str = "p2p", fabric=None):
+        """``halo``: ``"p2p"`` = grouped send/recv of the shared planes (NCCL on GPUs, gloo in the CPU
+        tests); ``"symm"`` = one-sided puts into the neighbour's symmetric-memory inbox (``SymmHalo``)."""
         self.plan, self.local, self.group = plan, local, group
+        if halo not in ("p2p", "symm"):
+            raise ValueError(f"unknown halo transport {halo!r}")
         self.migrate_every = migrate_every if migrate_every is not None else max(1, plan.margin)
         if self.migrate_every > max(1, plan.margin) and plan.world > 1:
             raise ValueError("migrate_every must not exceed the halo margin (particles move < 1 cell per substep)")
@@ -191,6 +267,9 @@ class SlabDriver:
         self.recv_lo = torch.zeros(shape_lo, dtype=probe.dtype, device=probe.device)
         self.recv_hi = torch.zeros(shape_hi, dtype=probe.dtype, device=probe.device)
         self.halo_bytes = (self.recv_lo.numel() + self.recv_hi.numel()) * probe.element_size()
+        self.symm = None
+        if halo == "symm" and plan.world > 1:
+            self.symm = SymmHalo(plan, tuple(probe.shape[1:]), probe.dtype, probe.device, group, fabric)
         self.migrated = 0
         self.rebalanced = 0
         self._pending = None
@@ -202,6 +281,15 @@ class SlabDriver:
     # -- halo planes: exchange partial sums with both neighbours ------------------
     def _exchange_halos(self) -> None:
         p, L = self.plan, self.local
+        if self.symm is not None:
+            lo, hi = self.symm.exchange(self.steps,
+                                        L.grid_planes(0, p.planes_lo) if self.left is not None else None,
+                                        L.grid_planes(p.n_local_x - p.planes_hi, p.n_local_x) if self.right is not None else None)
+            if lo is not None:
+                self.recv_lo = lo
+            if hi is not None:
+                self.recv_hi = hi
+            return
         ops = []
         if self.right is not None:
             ops.append(dist.P2POp(dist.isend, L.grid_planes(p.n_local_x - p.planes_hi, p.n_local_x), self.right, self.group))
@@ -614,7 +702,7 @@ class SlabSolver:
 
     @classmethod
     def from_scene(cls, scene, rank: int, world: int, device, p2g_mode: str = "auto", margin: int = 2,
-                   capacity_factor: float = 1.25):
+                   capacity_factor: float = 1.25, halo: str = "p2p"):
         """Weak scaling (BASELINE configs[3]): the scene's block is replicated once per
         rank along x; the global grid is (res*world) x res x res cells, dx = 1/res."""
         res = scene.res
@@ -627,11 +715,11 @@ class SlabSolver:
         ids = np.arange(scene.n, dtype=np.int64) + rank * scene.n
         local.set_particles(x, scene.v, scene.F, scene.C, scene.mass, scene.mu_0, scene.lambda_0,
                             (ids % (2 ** 31)).astype(np.int32))
-        return cls(plan, local, SlabDriver(plan, local))
+        return cls(plan, local, SlabDriver(plan, local, halo=halo))
 
     @classmethod
     def from_dam_break(cls, rank: int, world: int, device, res: int = 256, n_total: int = 33_554_432,
-                       margin: int = 4, capacity: Optional[int] = None, p2g_mode: str = "auto"):
+                       margin: int = 4, capacity: Optional[int] = None, p2g_mode: str = "auto", halo: str = "p2p"):
         """BASELINE configs[4]: soft column at one x-end of a (res*world) x res x res domain;
         every rank generates the particles of its own x interval.  The even cut leaves the ranks
         away from the column empty; ``rebalance()`` re-cuts the slabs by particle count."""
@@ -647,7 +735,7 @@ class SlabSolver:
         ids = (np.arange(sc.n, dtype=np.int64) + rank * (2 ** 27)) % (2 ** 31)
         # collective (the ranks agree on the material table): ranks that start empty take part too
         local.set_particles(sc.x, sc.v, sc.F, sc.C, sc.mass, sc.mu_0, sc.lambda_0, ids.astype(np.int32))
-        obj = cls(plan, local, SlabDriver(plan, local))
+        obj = cls(plan, local, SlabDriver(plan, local, halo=halo))
         obj.scene_name = sc.name
         return obj
 

@@ -150,7 +150,52 @@ def make_scene(res=24, n=1500, seed=3):
     return p, (x, v, F, C, mass, mu0, lam0, np.arange(n, dtype=np.int64))
 
 
-def _worker(rank, world, port, steps, margin, migrate_every, out, lagged=False):
+class SharedFabric:
+    """SymmHalo fabric on CPU: the inboxes and signal pads of all ranks are shared-memory tensors made
+    by the parent process, so a rank really writes into its neighbour's inbox and raises flags in its
+    neighbour's pad -- the semantics of torch's symmetric memory (put_signal: wait for 0, set 1;
+    wait_signal: wait for 1, set 0; one flag per (channel, source rank))."""
+
+    def __init__(self, rank, world, inboxes, pads):
+        self.rank, self.world, self.inboxes, self.pads = rank, world, inboxes, pads
+        self.puts = self.waits = 0
+
+    def empty(self, shape, dtype, device):
+        t = self.inboxes[self.rank]
+        assert tuple(t.shape) == tuple(shape) and t.dtype == dtype
+        return t
+
+    def rendezvous(self, tensor, group):
+        return self
+
+    def get_buffer(self, rank, sizes, dtype, storage_offset=0):
+        return self.inboxes[rank]
+
+    def barrier(self, channel=0, timeout_ms=0):
+        dist.barrier()
+
+    def _spin(self, flag, index, want, timeout_ms):
+        import time
+        t0 = time.time()
+        while int(flag[index]) != want:
+            if time.time() - t0 > timeout_ms / 1000:
+                raise TimeoutError(f"rank {self.rank}: flag {index} never became {want}")
+            time.sleep(0)
+
+    def put_signal(self, dst_rank, channel=0, timeout_ms=0):
+        i = channel * self.world + self.rank
+        self._spin(self.pads[dst_rank], i, 0, timeout_ms)
+        self.pads[dst_rank][i] = 1
+        self.puts += 1
+
+    def wait_signal(self, src_rank, channel=0, timeout_ms=0):
+        i = channel * self.world + src_rank
+        self._spin(self.pads[self.rank], i, 1, timeout_ms)
+        self.pads[self.rank][i] = 0
+        self.waits += 1
+
+
+def _worker(rank, world, port, steps, margin, migrate_every, out, lagged=False, shared=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -160,8 +205,12 @@ def _worker(rank, world, port, steps, margin, migrate_every, out, lagged=False):
         mine = np.flatnonzero((base[:, 0] >= plan.own_lo) & (base[:, 0] < plan.own_hi))
         local = OracleSlab(plan, p, tuple(a[mine].copy() for a in state))
         local.lagged = lagged
-        drv = SlabDriver(plan, local, migrate_every=migrate_every)
+        fabric = SharedFabric(rank, world, *shared) if shared is not None else None
+        drv = SlabDriver(plan, local, migrate_every=migrate_every, halo="symm" if fabric else "p2p", fabric=fabric)
         drv.substep(steps)
+        if fabric is not None:
+            n_nb = (rank > 0) + (rank < world - 1)
+            assert fabric.puts == fabric.waits == steps * n_nb      # one flag per neighbour per substep, all consumed
         gathered = [None] * world
         dist.all_gather_object(gathered, (local.ids, local.x, local.v, local.F, local.C, drv.migrated))
         if rank == 0:
@@ -195,6 +244,33 @@ def test_slabs_match_single_domain(tmp_path, world, margin, migrate_every, lagge
                            x, mass, mu0, lam0, v, F, C, Jp)
     assert np.array_equal(got["ids"], ids)                     # nobody lost, nobody duplicated
     assert got["migrated"] > 0                                 # the scene really exercises migration
+    for k, ref in (("x", x), ("v", v), ("F", F), ("C", C)):
+        assert np.abs(got[k] - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), k
+
+
+@pytest.mark.parametrize("world,margin,migrate_every", [(2, 2, 2), (3, 1, 1)])
+def test_symm_halo_protocol_matches_single_domain(tmp_path, world, margin, migrate_every):
+    """SlabDriver(halo="symm"): halo planes put into the neighbour's inbox + signal flags instead of
+    matched send/recv (SymmHalo), over a shared-memory stand-in for torch's symmetric memory.  Same
+    bar as the p2p transport: the single-domain oracle to 1e-12, after an odd number of substeps so
+    that both inbox parities are used an unequal number of times."""
+    steps = 7
+    p, _ = make_scene()
+    G = p["res"] + 1
+    planes = SlabPlan.min_cells(margin)
+    inboxes = [torch.zeros((2, 2, planes, G, G, 4), dtype=torch.float64).share_memory_() for _ in range(world)]
+    pads = [torch.zeros(4 * world, dtype=torch.int32).share_memory_() for _ in range(world)]
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_worker, args=(world, _free_port(), steps, margin, migrate_every, out, False, (inboxes, pads)),
+             nprocs=world, join=True)
+    assert all(int(pad.abs().sum()) == 0 for pad in pads)           # every raised flag was consumed
+    got = torch.load(out, weights_only=False)
+    p, (x, v, F, C, mass, mu0, lam0, ids) = make_scene()
+    Jp = np.ones((len(x), 1))
+    for _ in range(steps):
+        O.solve_mls_mpm_3d(p["res"], p["inv_dx"], p["hardening"], p["dx"], p["dt"], p["volume"], p["gravity"],
+                           x, mass, mu0, lam0, v, F, C, Jp)
+    assert np.array_equal(got["ids"], ids) and got["migrated"] > 0
     for k, ref in (("x", x), ("v", v), ("F", F), ("C", C)):
         assert np.abs(got[k] - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), k
 

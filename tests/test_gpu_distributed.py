@@ -26,7 +26,7 @@ def _scene(nmat):
     return p, tuple(np.asarray(a, dtype=np.float32).astype(np.float64) if a.dtype == np.float64 else a for a in state)
 
 
-def _worker(rank, world, port, steps, out, nmat):
+def _worker(rank, world, port, steps, out, nmat, halo="p2p"):
     import torch.distributed as dist
     from femflow_b200.distributed import CudaSlab, SlabDriver, SlabPlan
     from oracle import mpm_oracle as O
@@ -43,7 +43,7 @@ def _worker(rank, world, port, steps, out, nmat):
         local = CudaSlab(plan, p["dx"], p["dt"], p["volume"], p["gravity"], p["hardening"], capacity=len(x), device=dev)
         local.set_particles(x[mine], v[mine], F[mine], C[mine], mass[mine], mu0[mine], lam0[mine], ids[mine])
         assert local.solver.material_layout == f"table[{nmat}]"
-        drv = SlabDriver(plan, local, migrate_every=2)
+        drv = SlabDriver(plan, local, migrate_every=2, halo=halo)
         drv.substep(steps)
         assert local.solver.poll_error() == 0
         got = [t.cpu().numpy() for t in local.state_by_id()]
@@ -86,6 +86,25 @@ def test_two_gpu_slabs_match_oracle(tmp_path, nmat):
     assert np.abs(got["v"] - v).max() / V < tol
     assert np.abs(got["F"] - F).max() < tol
     assert np.abs(got["C"] - C).max() / (4 * p["inv_dx"] * V) < tol
+
+
+@pytest.mark.skipif(os.environ.get("FFMPM_TEST_SYMM") != "1",
+                    reason="SymmHalo over torch symmetric memory has not run on hardware yet (GPU budget): "
+                           "set FFMPM_TEST_SYMM=1 on a box with two NVLink-connected GPUs")
+def test_two_gpu_symm_halo_matches_oracle(tmp_path):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    steps = 7
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_worker, args=(2, port, steps, out, 3, "symm"), nprocs=2, join=True)
+    got = torch.load(out, weights_only=False)
+    p, state = _scene(3)
+    assert np.array_equal(got["ids"], state[7]) and got["migrated"] > 0
+    _assert_close(p, got, _oracle_run(p, state, steps), steps)
 
 
 def _lopsided(nmat):
