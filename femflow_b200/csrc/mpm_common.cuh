@@ -58,7 +58,7 @@ struct ErrRec {
 // inside the grid, so the fp32 path returns the same bits at a fraction of the issue slots
 // (6 fp64 conversion chains per particle in G2P, 3 in P2G).
 template <typename T>
-__device__ __forceinline__ void base_fx(T xs, const DevCfg& cfg, int& base, T& fx) {
+FFMPM_HD void base_fx(T xs, const DevCfg& cfg, int& base, T& fx) {
   if (sizeof(T) == 4 && cfg.index_fp32) {
     const float s = (float)xs * (float)cfg.inv_dx;
     float t = s - 0.5f;
@@ -78,7 +78,7 @@ __device__ __forceinline__ void base_fx(T xs, const DevCfg& cfg, int& base, T& f
 
 // Quadratic B-spline weights (three_d/p2g.py:55).
 template <typename T>
-__device__ __forceinline__ void bspline(T fx, T& w0, T& w1, T& w2) {
+FFMPM_HD void bspline(T fx, T& w0, T& w1, T& w2) {
   T a = (T)1.5 - fx, b = fx - (T)1.0, c = fx - (T)0.5;
   w0 = (T)0.5 * a * a;
   w1 = (T)0.75 - b * b;

@@ -26,7 +26,7 @@ enum { P2G_X = 0, P2G_V = 3, P2G_C = 6, P2G_F = 15, P2G_MASS = 24, P2G_MU = 25, 
 // `get(k)` returns plane k of the particle (k is a literal at every call site, so a
 // loader that switches on k folds away); has_mat: per-particle mass/mu0/lam0 planes exist.
 template <typename T, typename Get>
-__device__ __forceinline__ P2GParticle3<T> p2g_prepare3_from(const DevCfg& cfg, Get get, bool has_mat, double jp) {
+FFMPM_HD P2GParticle3<T> p2g_prepare3_from(const DevCfg& cfg, Get get, bool has_mat, double jp) {
   P2GParticle3<T> q;
   T x0 = get(P2G_X), x1 = get(P2G_X + 1), x2 = get(P2G_X + 2);
   int gx, gy, gz;
@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(256) grid_op2_kernel(DevCfg cfg, T* __restrict
 // node-by-node outer product, same sums up to round-off.
 // ----------------------------------------------------------------------------
 template <typename T, typename Fetch>
-__device__ __forceinline__ void g2p_accumulate3(Fetch fetch, T fx, T fy, T fz, T& vx, T& vy, T& vz, T& c00, T& c01,
+FFMPM_HD void g2p_accumulate3(Fetch fetch, T fx, T fy, T fz, T& vx, T& vy, T& vz, T& c00, T& c01,
                                                 T& c02, T& c10, T& c11, T& c12, T& c20, T& c21, T& c22) {
   T wx[3], wy[3], wz[3];
   bspline(fx, wx[0], wx[1], wx[2]);

@@ -4,6 +4,10 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+// The constitutive math is plain arithmetic: it also compiles for the host, where tests/native/
+// runs these very functions against LAPACK on CPU (tests/test_kernel_math_host.py).
+#define FFMPM_HD __host__ __device__ __forceinline__
+
 namespace ffmpm {
 
 template <typename T>
@@ -17,13 +21,13 @@ struct Mat2 {
 };
 
 template <typename T>
-__device__ __forceinline__ T det3(const Mat3<T>& m) {
+FFMPM_HD T det3(const Mat3<T>& m) {
   return m.a00 * (m.a11 * m.a22 - m.a12 * m.a21) - m.a01 * (m.a10 * m.a22 - m.a12 * m.a20) +
          m.a02 * (m.a10 * m.a21 - m.a11 * m.a20);
 }
 
 // Cofactor matrix cof(X) (so that X^{-T} = cof(X) / det X).
-__device__ __forceinline__ Mat3<double> cofactor3(const Mat3<double>& m) {
+FFMPM_HD Mat3<double> cofactor3(const Mat3<double>& m) {
   Mat3<double> c;
   c.a00 = m.a11 * m.a22 - m.a12 * m.a21;
   c.a01 = m.a12 * m.a20 - m.a10 * m.a22;
@@ -42,7 +46,7 @@ __device__ __forceinline__ Mat3<double> cofactor3(const Mat3<double>& m) {
 // X <- (g X + X^{-T} / g) / 2 with determinant scaling while far from orthogonal;
 // converges quadratically, det F < 0 converges to the det = -1 factor exactly as
 // U*Vh does.  F = I returns I exactly.
-__device__ __forceinline__ Mat3<double> polar_rotation3(const Mat3<double>& F, double& detF) {
+FFMPM_HD Mat3<double> polar_rotation3(const Mat3<double>& F, double& detF) {
   Mat3<double> X = F;
   Mat3<double> c = cofactor3(X);
   double det = X.a00 * c.a00 + X.a01 * c.a01 + X.a02 * c.a02;
@@ -75,7 +79,7 @@ __device__ __forceinline__ Mat3<double> polar_rotation3(const Mat3<double>& F, d
 
 // affine = -(dt*vol)*(4 inv_dx^2) * (2 mu (F-R) F^T + lam (J-1) J [on ALL entries]) + mass*C
 // (solvers/mpm/utils.py:120-135; the broadcast of the lambda term is quirk 2).
-__device__ __forceinline__ Mat3<double> fixed_corotated_affine3(const Mat3<double>& F, const Mat3<double>& C,
+FFMPM_HD Mat3<double> fixed_corotated_affine3(const Mat3<double>& F, const Mat3<double>& C,
                                                                 double mu, double lam, double mass,
                                                                 double dt_vol_dinv) {
   double J;
@@ -119,7 +123,7 @@ struct Sym3f {
 };
 
 // Product of two COMMUTING symmetric matrices (symmetric again).
-__device__ __forceinline__ Sym3f sym3_mul(const Sym3f& a, const Sym3f& b) {
+FFMPM_HD Sym3f sym3_mul(const Sym3f& a, const Sym3f& b) {
   Sym3f r;
   r.xx = a.xx * b.xx + a.xy * b.xy + a.xz * b.xz;
   r.xy = a.xx * b.xy + a.xy * b.yy + a.xz * b.yz;
@@ -138,7 +142,7 @@ __device__ __forceinline__ Sym3f sym3_mul(const Sym3f& a, const Sym3f& b) {
 constexpr float kPerturbationMaxR = 0.15f;
 
 // Returns false when the strain is too large for the series (caller falls back to fp64).
-__device__ __forceinline__ bool fixed_corotated_affine3_f32(const Mat3<float>& F, const Mat3<float>& C, float mu,
+FFMPM_HD bool fixed_corotated_affine3_f32(const Mat3<float>& F, const Mat3<float>& C, float mu,
                                                             float lam, float mass, float dt_vol_dinv, Mat3<float>& A) {
   Mat3<float> E = F;
   E.a00 -= 1.0f; E.a11 -= 1.0f; E.a22 -= 1.0f;
@@ -195,7 +199,7 @@ __device__ __forceinline__ bool fixed_corotated_affine3_f32(const Mat3<float>& F
 
 // 2D: closed-form rotation with the reference's +1e-10 in the norm
 // (numerics/linear_algebra.py:108-113; quirks 3 and 12), stress as utils.py:75-92.
-__device__ __forceinline__ Mat2<double> fixed_corotated_affine2(const Mat2<double>& F, const Mat2<double>& C,
+FFMPM_HD Mat2<double> fixed_corotated_affine2(const Mat2<double>& F, const Mat2<double>& C,
                                                                 double mu, double lam, double mass,
                                                                 double dt_vol_dinv) {
   double J = F.a00 * F.a11 - F.a01 * F.a10;
@@ -225,7 +229,7 @@ __device__ __forceinline__ Mat2<double> fixed_corotated_affine2(const Mat2<doubl
 // For `snow` the singular values are first clamped to [1-2.5e-2, 1+7.5e-3]:
 //     U S' Vh = F * (r0 v1 v1^T + r1 v2 v2^T),  r_i = clamp(s_i) / s_i.
 // Returns det of the result through `det_out` (sign follows det F).
-__device__ __forceinline__ Mat2<double> svd_roundtrip2(const Mat2<double>& F, bool snow, double& det_out) {
+FFMPM_HD Mat2<double> svd_roundtrip2(const Mat2<double>& F, bool snow, double& det_out) {
   double detF = F.a00 * F.a11 - F.a01 * F.a10;
   double m00 = F.a00 * F.a00 + F.a10 * F.a10;
   double m01 = F.a00 * F.a01 + F.a10 * F.a11;

@@ -1,0 +1,132 @@
+// Host harness around the kernels' own per-particle device functions (femflow_b200/csrc):
+// cell indexing, B-spline weights, the constitutive update in both precisions, the P2G payload and
+// the separable G2P stencil sums are `__host__ __device__`, so the CPU test suite runs THE SAME
+// SOURCE the GPU runs against LAPACK / the NumPy oracle (tests/test_kernel_math_host.py).  Test
+// infrastructure only: nothing in the product links this file.
+#include "../../femflow_b200/csrc/mpm_direct.cuh"
+
+using namespace ffmpm;
+
+namespace {
+
+DevCfg make_cfg(int res, int n_nodes, double inv_dx, double dx, double dt, double volume, double hardening, int model,
+                int fp32_stress, int index_fp32) {
+  DevCfg c{};
+  c.dim = 3;
+  c.model = model;
+  for (int d = 0; d < 3; ++d) { c.n[d] = n_nodes; c.origin[d] = 0; c.res[d] = res; }
+  c.inv_dx = inv_dx; c.dx = dx; c.dt = dt; c.volume = volume; c.gravity = 0.0; c.hardening = hardening;
+  c.mass = c.mu0 = c.lam0 = 0.0;
+  c.fp32_stress = fp32_stress;
+  c.index_fp32 = index_fp32;
+  c.own_lo = INT32_MIN; c.own_hi = INT32_MAX;
+  return c;
+}
+
+template <typename T>
+void prepare3(const DevCfg& cfg, long long n, const T* x, const T* v, const T* C, const T* F, const T* mass, const T* mu,
+              const T* lam, const double* jp, int* base, T* fx, T* aff, T* mv, T* m, int* ok) {
+  for (long long p = 0; p < n; ++p) {
+    auto get = [&](int k) -> T {
+      if (k < P2G_V) return x[3 * p + k];
+      if (k < P2G_C) return v[3 * p + (k - P2G_V)];
+      if (k < P2G_F) return C[9 * p + (k - P2G_C)];
+      if (k < P2G_MASS) return F[9 * p + (k - P2G_F)];
+      return k == P2G_MASS ? mass[p] : (k == P2G_MU ? mu[p] : lam[p]);
+    };
+    P2GParticle3<T> q = p2g_prepare3_from<T>(cfg, get, true, jp ? jp[p] : 1.0);
+    ok[p] = q.ok ? 1 : 0;
+    base[3 * p] = q.bx; base[3 * p + 1] = q.by; base[3 * p + 2] = q.bz;
+    fx[3 * p] = q.fx; fx[3 * p + 1] = q.fy; fx[3 * p + 2] = q.fz;
+    if (!q.ok) continue;
+    const T a[9] = {q.a00, q.a01, q.a02, q.a10, q.a11, q.a12, q.a20, q.a21, q.a22};
+    for (int e = 0; e < 9; ++e) aff[9 * p + e] = a[e];
+    mv[3 * p] = q.mvx; mv[3 * p + 1] = q.mvy; mv[3 * p + 2] = q.mvz;
+    m[p] = q.m;
+  }
+}
+
+template <typename T>
+struct V3 { T x, y, z; };
+
+template <typename T>
+void accumulate3(long long n, const T* f, const T* gv, T* v, T* c) {
+  for (long long p = 0; p < n; ++p) {
+    const T* g = gv + 81 * p;   // [3][3][3][3]
+    T o[12];
+    g2p_accumulate3<T>([&](int i, int j, int k) { const T* q = g + ((i * 3 + j) * 3 + k) * 3; return V3<T>{q[0], q[1], q[2]}; },
+                       f[3 * p], f[3 * p + 1], f[3 * p + 2], o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7], o[8], o[9],
+                       o[10], o[11]);
+    for (int e = 0; e < 3; ++e) v[3 * p + e] = o[e];
+    for (int e = 0; e < 9; ++e) c[9 * p + e] = o[3 + e];
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+void km_prepare3_f32(int res, int n_nodes, double inv_dx, double dx, double dt, double volume, double hardening, int model,
+                     int fp32_stress, int index_fp32, long long n, const float* x, const float* v, const float* C,
+                     const float* F, const float* mass, const float* mu, const float* lam, const double* jp, int* base,
+                     float* fx, float* aff, float* mv, float* m, int* ok) {
+  prepare3<float>(make_cfg(res, n_nodes, inv_dx, dx, dt, volume, hardening, model, fp32_stress, index_fp32), n, x, v, C, F,
+                  mass, mu, lam, jp, base, fx, aff, mv, m, ok);
+}
+
+void km_prepare3_f64(int res, int n_nodes, double inv_dx, double dx, double dt, double volume, double hardening, int model,
+                     int fp32_stress, int index_fp32, long long n, const double* x, const double* v, const double* C,
+                     const double* F, const double* mass, const double* mu, const double* lam, const double* jp, int* base,
+                     double* fx, double* aff, double* mv, double* m, int* ok) {
+  prepare3<double>(make_cfg(res, n_nodes, inv_dx, dx, dt, volume, hardening, model, fp32_stress, index_fp32), n, x, v, C,
+                   F, mass, mu, lam, jp, base, fx, aff, mv, m, ok);
+}
+
+void km_g2p_accumulate3_f32(long long n, const float* f, const float* gv, float* v, float* c) { accumulate3<float>(n, f, gv, v, c); }
+void km_g2p_accumulate3_f64(long long n, const double* f, const double* gv, double* v, double* c) { accumulate3<double>(n, f, gv, v, c); }
+
+// 1 when the fp32 perturbation series accepted the strain (else the caller's fp64 path would run)
+int km_affine3_f32(const float* F, const float* C, float mu, float lam, float mass, float k, float* A) {
+  Mat3<float> f{F[0], F[1], F[2], F[3], F[4], F[5], F[6], F[7], F[8]}, c{C[0], C[1], C[2], C[3], C[4], C[5], C[6], C[7], C[8]}, a;
+  const bool done = fixed_corotated_affine3_f32(f, c, mu, lam, mass, k, a);
+  if (done) { const float o[9] = {a.a00, a.a01, a.a02, a.a10, a.a11, a.a12, a.a20, a.a21, a.a22}; for (int e = 0; e < 9; ++e) A[e] = o[e]; }
+  return done ? 1 : 0;
+}
+
+void km_polar3(long long n, const double* F, double* R, double* det) {
+  for (long long p = 0; p < n; ++p) {
+    const double* f = F + 9 * p;
+    Mat3<double> m{f[0], f[1], f[2], f[3], f[4], f[5], f[6], f[7], f[8]};
+    Mat3<double> r = polar_rotation3(m, det[p]);
+    const double o[9] = {r.a00, r.a01, r.a02, r.a10, r.a11, r.a12, r.a20, r.a21, r.a22};
+    for (int e = 0; e < 9; ++e) R[9 * p + e] = o[e];
+  }
+}
+
+void km_affine2(long long n, const double* F, const double* C, double mu, double lam, double mass, double k, double* A) {
+  for (long long p = 0; p < n; ++p) {
+    Mat2<double> f{F[4 * p], F[4 * p + 1], F[4 * p + 2], F[4 * p + 3]}, c{C[4 * p], C[4 * p + 1], C[4 * p + 2], C[4 * p + 3]};
+    Mat2<double> a = fixed_corotated_affine2(f, c, mu, lam, mass, k);
+    A[4 * p] = a.a00; A[4 * p + 1] = a.a01; A[4 * p + 2] = a.a10; A[4 * p + 3] = a.a11;
+  }
+}
+
+void km_svd_roundtrip2(long long n, const double* F, int snow, double* G, double* det) {
+  for (long long p = 0; p < n; ++p) {
+    Mat2<double> f{F[4 * p], F[4 * p + 1], F[4 * p + 2], F[4 * p + 3]};
+    Mat2<double> g = svd_roundtrip2(f, snow != 0, det[p]);
+    G[4 * p] = g.a00; G[4 * p + 1] = g.a01; G[4 * p + 2] = g.a10; G[4 * p + 3] = g.a11;
+  }
+}
+
+void km_base_fx_f32(double inv_dx, int index_fp32, long long n, const float* x, int* base, float* fx) {
+  DevCfg c{}; c.inv_dx = inv_dx; c.index_fp32 = index_fp32;
+  for (long long p = 0; p < n; ++p) base_fx<float>(x[p], c, base[p], fx[p]);
+}
+
+void km_base_fx_f64(double inv_dx, long long n, const double* x, int* base, double* fx) {
+  DevCfg c{}; c.inv_dx = inv_dx; c.index_fp32 = 0;
+  for (long long p = 0; p < n; ++p) base_fx<double>(x[p], c, base[p], fx[p]);
+}
+
+}  // extern "C"

@@ -1,0 +1,240 @@
+"""The kernels' own per-particle math on the CPU.
+
+Cell indexing, B-spline weights, both constitutive evaluations (fp32 perturbation series and fp64
+Newton polar), the P2G payload and the separable G2P stencil sums are ``__host__ __device__``
+functions of femflow_b200/csrc; tests/native/kernel_math_host.cu compiles those very sources for the
+host and this file checks them against LAPACK / the NumPy oracle -- the same bars as the GPU parity
+tests, without a GPU.  (The warp-level scatter, the binning and the atomics only exist on the device:
+tests/test_gpu_parity.py.)"""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import mpm_oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "native", "kernel_math_host.cu")
+CSRC = os.path.join(os.path.dirname(HERE), "femflow_b200", "csrc")
+LIB = os.path.join(HERE, "native", "_build", "libkernel_math_host.so")
+
+
+def build_host_harness(force: bool = False) -> str:
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("mpm_math.cuh", "mpm_common.cuh", "mpm_direct.cuh")]
+    if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
+        return LIB
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    cmd = [nvcc, "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-diag-suppress", "20013,20011,20015",
+           "-Xcompiler", "-fPIC", "-shared", "-o", LIB, SRC]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr
+    return LIB
+
+
+@pytest.fixture(scope="module")
+def km():
+    return C.CDLL(build_host_harness())
+
+
+def ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def prepare3(km, dtype, res, x, v, Cm, F, mass, mu, lam, dt, volume, hardening=1.0, fp32_stress=1, index_fp32=None, jp=None,
+             model=0):
+    n = len(x)
+    np_dt = np.float32 if dtype == "f32" else np.float64
+    arrs = [np.ascontiguousarray(a, dtype=np_dt) for a in (x, v, Cm.reshape(n, 9), F.reshape(n, 9), mass, mu, lam)]
+    base = np.zeros((n, 3), np.int32); fx = np.zeros((n, 3), np_dt); aff = np.zeros((n, 9), np_dt)
+    mv = np.zeros((n, 3), np_dt); m = np.zeros(n, np_dt); ok = np.zeros(n, np.int32)
+    if index_fp32 is None:
+        index_fp32 = int(res & (res - 1) == 0)
+    jp_arr = None if jp is None else np.ascontiguousarray(jp, dtype=np.float64)
+    fn = getattr(km, f"km_prepare3_{dtype}")
+    fn(C.c_int(res), C.c_int(res + 1), C.c_double(float(res)), C.c_double(1.0 / res), C.c_double(dt), C.c_double(volume),
+       C.c_double(hardening), C.c_int(model), C.c_int(fp32_stress), C.c_int(index_fp32), C.c_longlong(n),
+       *(ptr(a) for a in arrs), ptr(jp_arr) if jp_arr is not None else None, ptr(base), ptr(fx), ptr(aff), ptr(mv), ptr(m),
+       ptr(ok))
+    return base, fx, aff.reshape(n, 3, 3), mv, m, ok.astype(bool)
+
+
+def f32(a):
+    return np.asarray(a, dtype=np.float32).astype(np.float64)
+
+
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("res", [37, 64, 80, 256, 1024])
+def test_cell_indexing_is_bit_exact(km, res):
+    """base = trunc(x*inv_dx - 0.5) (quirks 1, 11): positions one fp32 ulp either side of every cell
+    boundary, plus the (-1, 0) band that truncation sends to cell 0 -- fp64 evaluation for any R, and
+    the fp32 evaluation the kernels switch to when inv_dx is a power of two."""
+    k = np.arange(0, min(res, 300), dtype=np.float64)
+    edge = ((k + 0.5) / res).astype(np.float32)
+    xs = np.concatenate([edge, np.nextafter(edge, np.float32(-1)), np.nextafter(edge, np.float32(2)),
+                         np.float32([0.0, 1e-9, -1e-9, 0.2 / res, 0.49999 / res]),
+                         np.random.default_rng(res).uniform(0, 1, 4000).astype(np.float32)])
+    want_base, want_fx = O.base_and_fx(xs.astype(np.float64)[:, None], float(res))
+    pow2 = res & (res - 1) == 0
+    for index_fp32 in ([0, 1] if pow2 else [0]):
+        base = np.zeros(len(xs), np.int32); fx = np.zeros(len(xs), np.float32)
+        km.km_base_fx_f32(C.c_double(float(res)), C.c_int(index_fp32), C.c_longlong(len(xs)), ptr(xs), ptr(base), ptr(fx))
+        assert np.array_equal(base, want_base[:, 0]), (res, index_fp32)
+        assert np.array_equal(fx, want_fx[:, 0].astype(np.float32)), (res, index_fp32)   # fx is exact, then rounded once
+    xd = xs.astype(np.float64)
+    base = np.zeros(len(xs), np.int32); fxd = np.zeros(len(xs), np.float64)
+    km.km_base_fx_f64(C.c_double(float(res)), C.c_longlong(len(xs)), ptr(xd), ptr(base), ptr(fxd))
+    assert np.array_equal(base, want_base[:, 0]) and np.array_equal(fxd, want_fx[:, 0])
+
+
+@pytest.mark.parametrize("strain", [0.0, 1e-6, 1e-4, 1.5e-3, 1e-2, 4e-2, 0.3])
+def test_fp32_stress_tiers_against_lapack(km, strain):
+    """affine = stress + mass*C of three_d/p2g.py:57-65 (utils.py:120-135) from the fp32 kernel path: the
+    series tiers (3 / 5 / 8 terms by the Frobenius norm of G) and the fp64 Newton fallback beyond, each
+    to 1e-5 of the batch's largest STRESS entry (C = 0, so nothing hides the stress) -- the bar of
+    test_stress_accuracy_across_series_tiers on the GPU."""
+    rng = np.random.default_rng(11)
+    res, n = 32, 4000
+    dx = 1.0 / res
+    vol = float(f32((dx / 2) ** 3))
+    x = f32(rng.uniform(0.25, 0.75, size=(n, 3)))
+    F = f32(np.eye(3) + strain * rng.uniform(-1, 1, size=(n, 3, 3)))
+    Z = np.zeros((n, 3, 3))
+    mass = np.full(n, vol); mu = np.full(n, f32(4166.67)); lam = np.full(n, f32(2777.78))
+    want = O.fixed_corotated_stress_3d(F, float(res), mu, lam, 1e-4, vol, mass, Z)
+    base, fx, aff, mv, m, ok = prepare3(km, "f32", res, x, np.zeros((n, 3)), Z, F, mass, mu, lam, 1e-4, vol)
+    assert ok.all()
+    scale = np.abs(want).max()
+    if strain == 0.0:
+        assert np.all(aff == 0.0) and scale == 0.0            # F = I: exactly no stress (every reference scene starts so)
+    else:
+        assert np.abs(aff - want).max() / scale < 1e-5, strain
+    # the tier decision itself: the series declines beyond ||G||_F = 0.15 and the caller goes to fp64
+    A = np.zeros(9, np.float32)
+    Ff = np.ascontiguousarray(F[0].reshape(9), dtype=np.float32)
+    Cf = np.zeros(9, np.float32)
+    km.km_affine3_f32.restype = C.c_int
+    took = km.km_affine3_f32(ptr(Ff), ptr(Cf), C.c_float(1.0), C.c_float(1.0), C.c_float(1.0), C.c_float(1.0), ptr(A))
+    G = F[0].T @ F[0] - np.eye(3)
+    assert bool(took) == bool(np.linalg.norm(G) < 0.15 * (1 - 1e-4)) or abs(np.linalg.norm(G) - 0.15) < 1e-4
+
+
+def test_fp64_stress_and_polar_against_lapack(km):
+    """fp64 build / large-strain fallback: Newton polar factor == U @ Vh of the SVD (also for det F < 0,
+    where both give the det = -1 factor), stress to 1e-12; F = I returns R = I exactly."""
+    rng = np.random.default_rng(5)
+    n = 3000
+    F = np.eye(3) + rng.uniform(-1, 1, size=(n, 3, 3)) * rng.choice([1e-6, 1e-3, 0.1, 0.5, 1.5], size=(n, 1, 1))
+    F[0] = np.eye(3)
+    F[1] = np.diag([1.0, 1.0, -1.0]) @ F[1]                                   # a reflection
+    R = np.zeros((n, 9)); det = np.zeros(n)
+    km.km_polar3(C.c_longlong(n), ptr(np.ascontiguousarray(F.reshape(n, 9))), ptr(R), ptr(det))
+    R = R.reshape(n, 3, 3)
+    want = O.polar_decomp_3d(F)
+    cond = np.linalg.cond(F)
+    sel = cond < 1e3                                                          # R is ill-defined near singular F
+    assert sel.sum() > 0.9 * n and (np.linalg.det(F) < 0).sum() > 10
+    assert np.abs(R[sel] - want[sel]).max() < 1e-11
+    assert np.array_equal(R[0], np.eye(3))
+    assert np.allclose(det, np.linalg.det(F), rtol=1e-12, atol=1e-14)
+    res = 16
+    x = np.full((n, 3), 0.5)
+    Cm = rng.normal(0, 0.3, size=(n, 3, 3))
+    mass = rng.uniform(0.5, 2, n); mu = rng.uniform(10, 50, n); lam = rng.uniform(10, 50, n)
+    want_aff = O.fixed_corotated_stress_3d(F, float(res), 0.7 * mu, 0.7 * lam, 1e-3, 0.5, mass, Cm)
+    base, fx, aff, mv, m, ok = prepare3(km, "f64", res, x, rng.normal(size=(n, 3)), Cm, F, mass, mu, lam, 1e-3, 0.5,
+                                        hardening=0.7)
+    assert ok.all()
+    assert np.abs(aff[sel] - want_aff[sel]).max() / np.abs(want_aff[sel]).max() < 1e-12
+
+
+def test_p2g_payload_and_oob_flag(km):
+    """mass*v, mass, base, fx as the scatter consumes them; particles whose stencil leaves [0, R] are
+    flagged instead of written (three_d/p2g.py:51-52, utils.py:138-150); snow hardening multiplier."""
+    rng = np.random.default_rng(2)
+    res, n = 16, 500
+    x = f32(rng.uniform(0.1, 0.9, size=(n, 3)))
+    x[0] = [0.99, 0.5, 0.5]          # base 15 -> stencil reaches node 17 > R
+    x[1] = [0.5, -0.2, 0.5]          # base -3
+    x[2] = [np.nan, 0.5, 0.5]
+    x[3] = [0.0, 0.5, 0.5]           # x*inv_dx - 0.5 in (-1, 0): truncates to cell 0, legal (quirk 1)
+    v = f32(rng.normal(size=(n, 3)))
+    F = f32(np.eye(3) + 0.01 * rng.normal(size=(n, 3, 3)))
+    Cm = f32(rng.normal(0, 0.2, size=(n, 3, 3)))
+    mass = f32(rng.uniform(0.5, 2, n)); mu = f32(rng.uniform(10, 50, n)); lam = f32(rng.uniform(10, 50, n))
+    base, fx, aff, mv, m, ok = prepare3(km, "f32", res, x, v, Cm, F, mass, mu, lam, 1e-3, 0.5)
+    assert not ok[0] and not ok[1] and not ok[2] and ok[3] and ok[4:].all()
+    wb, wfx = O.base_and_fx(x[3:], float(res))
+    assert np.array_equal(base[3:], wb) and base[3, 0] == 0
+    assert np.array_equal(fx[3:], wfx.astype(np.float32))
+    assert np.array_equal(m[3:], mass[3:].astype(np.float32))
+    assert np.array_equal(mv[3:], (mass[3:, None].astype(np.float32) * v[3:].astype(np.float32)))
+    want = O.fixed_corotated_stress_3d(F[3:], float(res), mu[3:], lam[3:], 1e-3, 0.5, mass[3:], Cm[3:])
+    assert np.abs(aff[3:] - want).max() / np.abs(want).max() < 1e-5
+    # snow (three_d/p2g.py:59-61): mu, lam scaled by exp(h (1 - Jp))
+    jp = rng.uniform(0.8, 1.2, n)
+    h = 3.0
+    _, _, aff_s, _, _, ok_s = prepare3(km, "f64", res, x, v, Cm, F, mass, mu, lam, 1e-3, 0.5, hardening=h, jp=jp, model=1)
+    e = np.exp(h * (1 - jp[3:]))
+    want_s = O.fixed_corotated_stress_3d(F[3:], float(res), mu[3:] * e, lam[3:] * e, 1e-3, 0.5, mass[3:], Cm[3:])
+    assert np.abs(aff_s[3:] - want_s).max() / np.abs(want_s).max() < 1e-12
+
+
+@pytest.mark.parametrize("dtype,tol", [("f32", 2e-6), ("f64", 1e-14)])
+def test_separable_g2p_stencil_sums(km, dtype, tol):
+    """v = sum w gv, C = sum (w gv) (x) dpos (three_d/g2p.py:31-43) folded z -> y -> x against the
+    node-by-node sums of the reference."""
+    rng = np.random.default_rng(8)
+    n = 2000
+    np_dt = np.float32 if dtype == "f32" else np.float64
+    f = rng.uniform(0.5, 1.5, size=(n, 3)).astype(np_dt)
+    gv = rng.normal(size=(n, 3, 3, 3, 3)).astype(np_dt)
+    v = np.zeros((n, 3), np_dt); c = np.zeros((n, 9), np_dt)
+    getattr(km, f"km_g2p_accumulate3_{dtype}")(C.c_longlong(n), ptr(f), ptr(np.ascontiguousarray(gv)), ptr(v), ptr(c))
+    fd = f.astype(np.float64)
+    w = O.bspline_weights(fd)                                     # (3, n, 3): [offset, particle, axis]
+    want_v = np.zeros((n, 3)); want_c = np.zeros((n, 3, 3))
+    for i in range(3):
+        for j in range(3):
+            for k in range(3):
+                wt = w[i, :, 0] * w[j, :, 1] * w[k, :, 2]
+                wgv = wt[:, None] * gv[:, i, j, k].astype(np.float64)
+                dpos = np.array((i, j, k)) - fd
+                want_v += wgv
+                want_c += wgv[:, :, None] * dpos[:, None, :]
+    assert np.abs(v - want_v).max() / np.abs(want_v).max() < tol
+    assert np.abs(c.reshape(n, 3, 3) - want_c).max() / np.abs(want_c).max() < tol
+
+
+def test_2d_stress_and_svd_roundtrip(km):
+    """2D constitutive update with the reference's +1e-10 (quirks 3, 12) and the U diag(s) Vh^T round trip
+    of two_d/g2p.py:37-43 including det F < 0 (where the wrong transpose matters) and the snow clamp."""
+    rng = np.random.default_rng(4)
+    n = 4000
+    F = np.eye(2) + rng.uniform(-1, 1, size=(n, 2, 2)) * rng.choice([1e-8, 1e-3, 0.2, 1.2], size=(n, 1, 1))
+    F[0] = np.eye(2)
+    Cm = rng.normal(0, 0.3, size=(n, 2, 2))
+    mu, lam, mass, dt, vol, inv_dx = 4166.67, 2777.78, 1.0, 1e-4, 1.0, 80.0
+    k = dt * vol * 4 * inv_dx * inv_dx
+    A = np.zeros((n, 4))
+    km.km_affine2(C.c_longlong(n), ptr(np.ascontiguousarray(F.reshape(n, 4))), ptr(np.ascontiguousarray(Cm.reshape(n, 4))),
+                  C.c_double(mu), C.c_double(lam), C.c_double(mass), C.c_double(k), ptr(A))
+    want = O.fixed_corotated_stress_2d(F, inv_dx, np.full(n, mu), np.full(n, lam), dt, vol, np.full(n, mass), Cm)
+    assert np.abs(A.reshape(n, 2, 2) - want).max() / np.abs(want).max() < 1e-13
+    assert abs(A[0, 0] - want[0, 0, 0]) < 1e-12 * abs(want[0, 0, 0]) and want[0, 0, 0] != 0     # the 1e-10 stress at F = I
+    sel = np.linalg.cond(F) < 1e4
+    assert (np.linalg.det(F[sel]) < 0).sum() > 20
+    for snow in (0, 1):
+        G = np.zeros((n, 4)); det = np.zeros(n)
+        km.km_svd_roundtrip2(C.c_longlong(n), ptr(np.ascontiguousarray(F.reshape(n, 4))), C.c_int(snow), ptr(G), ptr(det))
+        U, sig, Vh = np.linalg.svd(F)
+        if snow:
+            sig = np.clip(sig, 1.0 - 2.5e-2, 1.0 + 7.5e-3)
+        wantG = (U * sig[:, None, :]) @ np.swapaxes(Vh, 1, 2)
+        assert np.abs(G.reshape(n, 2, 2)[sel] - wantG[sel]).max() < 1e-9, snow
+        assert np.abs(det[sel] - np.linalg.det(wantG[sel])).max() < 1e-9, snow
