@@ -1,0 +1,34 @@
+#!/bin/bash
+# First GPU calls of the next round (everything here was written after this round's GPU budget ran out).
+#   gpurun --gpus 2 --timeout 600 -- 'bash scripts/next_round_measure.sh 2'
+#   gpurun --gpus 8 --timeout 900 -- 'bash scripts/next_round_measure.sh 8'
+set -u
+N=${1:-2}
+out=gpurun_out/next_n$N
+mkdir -p $out
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+if [ "$N" = "2" ]; then
+  # SymmHalo on hardware: parity first (signals time out after 20 s instead of hanging), then p2p vs symm
+  FFMPM_TEST_SYMM=1 timeout 180 python -m pytest tests/test_gpu_distributed.py -x -q -k "symm" > $out/pytest_symm.txt 2>&1
+  tail -3 $out/pytest_symm.txt
+fi
+for halo in p2p symm; do
+  timeout 300 $TR --master-port 2952$N bench.py --gpus $N --steps 100 --warmup 10 --no-cpu-baseline --halo $halo --slab-timing \
+      > $out/bench_${halo}.json 2> $out/bench_${halo}.err
+done
+if [ "$N" = "8" ]; then
+  for mode in "" "--rebalance"; do
+    tag=$([ -z "$mode" ] && echo static || echo rebalanced)
+    timeout 300 $TR --master-port 2953$N bench.py --gpus $N --steps 100 --warmup 10 --workload dam32m --no-cpu-baseline $mode \
+        > $out/dam32m_${tag}.json 2> $out/dam32m_${tag}.err
+  done
+fi
+python - <<PY
+import glob, json
+for f in sorted(glob.glob("$out/*.json")):
+    try:
+        d = json.load(open(f))
+        print(f, d["ms_per_step"], d["value"], d["config"].get("slab_particles"))
+    except Exception as e:
+        print(f, "failed:", e)
+PY
