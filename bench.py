@@ -168,6 +168,9 @@ def main():
                          "measured -11 %% on 2d1m, -4 %% on a 2M-particle 3D block (profiles/r01q_graph_experiment.json)")
     ap.add_argument("--rebalance", action="store_true",
                     help="dam workloads, N>1: re-cut the slabs by particle count before the warm-up (SlabDriver.rebalance)")
+    ap.add_argument("--presteps", type=int, default=0,
+                    help="dam workloads: substeps run before the warm-up (untimed) so that a later window of the collapse "
+                         "is measured (SURVEY 8d C5: tall column vs pancake); re-cut every --rebalance-every of them")
     ap.add_argument("--rebalance-every", type=int, default=0,
                     help="with --rebalance: also offer a re-cut every K timed substeps (inside the timed region)")
     args = ap.parse_args()
@@ -228,6 +231,14 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
+
+    if dam and args.presteps > 0:
+        for k in range(args.presteps):
+            solver.substep(1)
+            if world > 1 and args.rebalance and args.rebalance_every and (k + 1) % args.rebalance_every == 0:
+                solver.rebalance()
+        if solver.poll_error():
+            raise SystemExit("pre-steps left particles outside the grid")
 
     # ---- warm-up ----
     for _ in range(args.warmup):
@@ -403,6 +414,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": scene.name, "particles_per_gpu": n, "particles_total": n_total,
                    "grid": f"{scene.res}^{scene.dim}", "dt": scene.dt, "p2g_mode": args.p2g_mode, "cuda_graph": bool(args.graph and world == 1 and not dam and args.steps % 10 == 0),
+                   **({"presteps": args.presteps} if dam else {}),
                    "l2": ("inputs larger than L2 (no flush)" if n * (112 if scene.dim == 3 else 52) > 2 * 126e6
                           else "particle state fits in the 126 MB L2 (flagged: HBM fraction is not meaningful)"),
                    "n_oob": n_oob,
