@@ -385,6 +385,8 @@ static int p2g_t(FfMpmHandle* h, cudaStream_t s) {
         bool ok;
         const int bps = h->p2g_blocks_per_sm;
         if (h->p2g_variant == 3) ok = p2g_bulk_launch<3, 1, 0>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
+        else if (h->p2g_variant == 7)   // packed-fp32 phase 2 (two particles per FFMA2), 12 warps/SM for the 72 accumulator registers
+          ok = p2g_bulk_launch<4, 1, 1, P2G_NPLANES, 12, true>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
         else if (h->p2g_variant == 6 && mat_mode_of(sv) != MAT_PLANES)   // occupancy experiment: 20 warps/SM
           ok = p2g_bulk_launch<4, 1, 1, P2G_MASS, 20>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
         else ok = p2g_bulk_launch<4, 1, 1>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);

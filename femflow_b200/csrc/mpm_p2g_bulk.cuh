@@ -11,14 +11,17 @@
 // a window is a contiguous, 256-byte aligned segment of every plane (no permutation
 // gather); the reordering G2P keeps that order cell-sorted up to one substep of motion.
 #pragma once
+#include <type_traits>
+
+#include "mpm_p2g_pair.cuh"
 #include "mpm_p2g_runs.cuh"
 
 namespace ffmpm {
 
-template <int NBUF, int RAWP = P2G_NPLANES>
+template <int NBUF, int RAWP = P2G_NPLANES, bool PAIR = false>
 struct P2GBulkWarp {
   alignas(128) float raw[NBUF][RAWP][P2G_WINDOW];   // RAWP = 24: no room for material planes (table / config material)
-  P2GWarpSlab<float> slab;
+  std::conditional_t<PAIR, P2GPairSlab, P2GWarpSlab<float>> slab;   // PAIR: pair-major payload (mpm_p2g_pair.cuh)
   alignas(16) unsigned char mat[NBUF][P2G_WINDOW];   // material rows of the window (table mode)
   alignas(8) unsigned long long bar[NBUF];
 };
@@ -86,16 +89,18 @@ __device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
 // RAWP / SMW: planes held per window and resident warps per SM the launch bounds ask for.  <27, 16> is the
 // measured default (128 registers); <24, 20> (no material planes: 11.1 KB of shared memory per warp, 5 CTAs
 // of 4 warps, <= 96 registers) is the occupancy experiment behind FFMPM_P2G_VARIANT=6.
-template <int WARPS, int NBUF, int LDGSTS, int RAWP = P2G_NPLANES, int SMW = 16>
+// PAIR: phase 2 walks the runs two particles per instruction with packed fp32 (FFMA2; mpm_p2g_pair.cuh) --
+// FFMPM_P2G_VARIANT=7, written after this round's GPU budget was spent: not yet measured.
+template <int WARPS, int NBUF, int LDGSTS, int RAWP = P2G_NPLANES, int SMW = 16, bool PAIR = false>
 __global__ void __launch_bounds__(WARPS * 32, SMW / WARPS)
 p2g_bulk3_kernel(DevCfg cfg, P2GPlanes planes, long long n, float* __restrict__ grid, ErrRec* err, int wpw) {
   using T = float;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  using WarpMem = P2GBulkWarp<NBUF, RAWP>;
+  using WarpMem = P2GBulkWarp<NBUF, RAWP, PAIR>;
   WarpMem* warps = reinterpret_cast<WarpMem*>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   WarpMem& W = warps[warp];
-  P2GWarpSlab<T>& S = W.slab;
+  auto& S = W.slab;
   const T dx = (T)cfg.dx;
   const int ny = cfg.n[1], nz = cfg.n[2];
   const int n_planes = planes.n;
@@ -124,7 +129,7 @@ p2g_bulk3_kernel(DevCfg cfg, P2GPlanes planes, long long n, float* __restrict__ 
         const int k0 = 2 * j, k1 = 2 * j + 1;
         const float* src = (hi && k1 < P2G_NPLANES) ? planes.p[k1 < P2G_NPLANES ? k1 : k0] : planes.p[k0];
         const int k = hi ? k1 : k0;
-        if (k < n_planes && k < RAWP) cp_async16(&W.raw[buf][k][(lane & 15) * 4], src + w0);
+        if (k < n_planes && (RAWP == P2G_NPLANES || k < RAWP)) cp_async16(&W.raw[buf][k][(lane & 15) * 4], src + w0);
       }
       if (planes.material && lane < P2G_WINDOW / 16)
         cp_async16(&W.mat[buf][lane * 16], planes.material + (long long)win * P2G_WINDOW + lane * 16);
@@ -138,7 +143,7 @@ p2g_bulk3_kernel(DevCfg cfg, P2GPlanes planes, long long n, float* __restrict__ 
       if (planes.material) bulk_load_s(&W.mat[buf][0], planes.material + w0, P2G_WINDOW, &W.bar[buf]);
 #pragma unroll
       for (int k = 0; k < P2G_NPLANES; ++k)
-        if (k < n_planes && k < RAWP) bulk_load_s(&W.raw[buf][k][0], planes.p[k] + w0, P2G_WINDOW * 4u, &W.bar[buf]);
+        if (k < n_planes && (RAWP == P2G_NPLANES || k < RAWP)) bulk_load_s(&W.raw[buf][k][0], planes.p[k] + w0, P2G_WINDOW * 4u, &W.bar[buf]);
     }
   };
 
@@ -169,31 +174,35 @@ p2g_bulk3_kernel(DevCfg cfg, P2GPlanes planes, long long n, float* __restrict__ 
             cfg,
             [&](int k) -> T {
               if (k >= P2G_MASS && planes.table) return __ldg(planes.table + (k - P2G_MASS) * MAT_ROWS + row);
-              if (k >= RAWP) return (T)0;          // RAWP = 24 is launched only without material planes
+              if constexpr (RAWP < P2G_NPLANES) { if (k >= RAWP) return (T)0; }   // RAWP = 24 is launched only without material planes
               return W.raw[buf][k][idx];
             },
             has_mat, 1.0);
-        node[h] = p2g_park(S, q, idx, dx, ny, nz);
+        if constexpr (PAIR) node[h] = p2g_park_pair(S.pay, S.node0, q, idx, dx, ny, nz);
+        else node[h] = p2g_park(S, q, idx, dx, ny, nz);
+      } else if constexpr (PAIR) {
+        p2g_park_pair_zero(S.pay, idx);   // the last window's tail: a masked partner must read finite values
       }
     }
     __syncwarp();
     // single buffer: the raw slab is free again -> prefetch the next window behind phase 2
     if (NBUF == 1 && win + total_warps < last_excl) issue(win + total_warps, 0);
-    p2g_runs_phase2<T>(S, node, cnt, lane, ny, nz, grid);
+    if constexpr (PAIR) p2g_runs_phase2_pair(S, node, cnt, lane, ny, nz, grid);
+    else p2g_runs_phase2<T>(S, node, cnt, lane, ny, nz, grid);
     __syncwarp();   // the payload slab is rewritten by the next window
   }
 }
 
-template <int WARPS, int NBUF, int LDGSTS, int RAWP = P2G_NPLANES, int SMW = 16>
+template <int WARPS, int NBUF, int LDGSTS, int RAWP = P2G_NPLANES, int SMW = 16, bool PAIR = false>
 static bool p2g_bulk_launch(const DevCfg& cfg, const StateView<float>& s, long long n, float* grid, ErrRec* err,
                             int sm_count, int blocks_per_sm, cudaStream_t st) {
-  const size_t smem = sizeof(P2GBulkWarp<NBUF, RAWP>) * WARPS;
+  const size_t smem = sizeof(P2GBulkWarp<NBUF, RAWP, PAIR>) * WARPS;
   // function attributes are per device: a process that drives several GPUs configures each once
   static bool configured[64] = {};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
   if (!configured[dev]) {
-    if (cudaFuncSetAttribute(p2g_bulk3_kernel<WARPS, NBUF, LDGSTS, RAWP, SMW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(p2g_bulk3_kernel<WARPS, NBUF, LDGSTS, RAWP, SMW, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return false;
     configured[dev] = true;
   }
@@ -208,7 +217,7 @@ static bool p2g_bulk_launch(const DevCfg& cfg, const StateView<float>& s, long l
     blocks = (int)(want < cap ? want : cap);
   }
   if (blocks < 1) blocks = 1;
-  p2g_bulk3_kernel<WARPS, NBUF, LDGSTS, RAWP, SMW><<<blocks, WARPS * 32, smem, st>>>(cfg, p2g_planes_of(s), n, grid, err, wpw);
+  p2g_bulk3_kernel<WARPS, NBUF, LDGSTS, RAWP, SMW, PAIR><<<blocks, WARPS * 32, smem, st>>>(cfg, p2g_planes_of(s), n, grid, err, wpw);
   return true;
 }
 

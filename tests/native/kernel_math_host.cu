@@ -4,6 +4,7 @@
 // SOURCE the GPU runs against LAPACK / the NumPy oracle (tests/test_kernel_math_host.py).  Test
 // infrastructure only: nothing in the product links this file.
 #include "../../femflow_b200/csrc/mpm_direct.cuh"
+#include "../../femflow_b200/csrc/mpm_p2g_pair.cuh"
 
 using namespace ffmpm;
 
@@ -127,6 +128,44 @@ void km_base_fx_f32(double inv_dx, int index_fp32, long long n, const float* x, 
 void km_base_fx_f64(double inv_dx, long long n, const double* x, int* base, double* fx) {
   DevCfg c{}; c.inv_dx = inv_dx; c.index_fp32 = 0;
   for (long long p = 0; p < n; ++p) base_fx<double>(x[p], c, base[p], fx[p]);
+}
+
+// Packed-fp32 P2G phase 2 (mpm_p2g_pair.cuh): park `n_slots` payloads (16 floats each, PP_* order) in the
+// pair-major shared-memory image exactly as phase 1 does, then accumulate x-slab `li` of the run [r0, r1).
+// Slots >= n_slots are parked as the kernel parks the tail of the last window.  Returns 0, or -1 when two
+// slots alias in the layout.
+int km_pair_accumulate(int n_slots, const float* payload, int r0, int r1, int li, float* out) {
+  static float4 pay[P2G_PAIR_PLANES][P2G_PAIR_PADDED];
+  for (int c = 0; c < P2G_PAIR_PLANES; ++c)
+    for (int s = 0; s < P2G_PAIR_PADDED; ++s) pay[c][s] = make_float4(NAN, NAN, NAN, NAN);   // unwritten smem is garbage
+  static int node0[P2G_WINDOW];
+  for (int q = 0; q < P2G_WINDOW; ++q) {
+    if (q < n_slots) {
+      for (int c = 0; c < 16; ++c)
+        if (!(*p2g_pair_slot(pay, q, c) != *p2g_pair_slot(pay, q, c))) return -1;   // already written: layout not injective
+      const float* v = payload + 16 * q;
+      P2GParticle3<float> pq{};
+      pq.ok = true; pq.bx = q; pq.by = 0; pq.bz = 0;
+      pq.mvx = v[PP_MVX]; pq.mvy = v[PP_MVY]; pq.mvz = v[PP_MVZ]; pq.m = v[PP_M];
+      pq.a00 = v[PP_A00]; pq.a01 = v[PP_A01]; pq.a02 = v[PP_A02]; pq.fx = v[PP_FX];
+      pq.a10 = v[PP_A10]; pq.a11 = v[PP_A11]; pq.a12 = v[PP_A12]; pq.fy = v[PP_FY];
+      pq.a20 = v[PP_A20]; pq.a21 = v[PP_A21]; pq.a22 = v[PP_A22]; pq.fz = v[PP_FZ];
+      if (p2g_park_pair(pay, node0, pq, q, 1.0f, 1, 1) != q) return -2;          // phase 1's own parking (dx = 1)
+    } else {
+      p2g_park_pair_zero(pay, q);
+    }
+  }
+  float o[9][4];
+  p2g_pair_accumulate(pay, r0, r1, li, o);
+  for (int e = 0; e < 9; ++e)
+    for (int d = 0; d < 4; ++d) out[4 * e + d] = o[e][d];
+  return 0;
+}
+
+// Bank of the first word each of `n_lanes` lanes touches when lane l reads slot pair start[l] of a plane
+// (LDS.128: 4 consecutive banks from there); the test asserts that aligned runs do not collide.
+void km_pair_banks(int n_lanes, const int* start, int* bank) {
+  for (int l = 0; l < n_lanes; ++l) bank[l] = (p2g_pair_pad(start[l]) * 4) % 32;
 }
 
 }  // extern "C"

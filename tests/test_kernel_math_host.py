@@ -23,7 +23,7 @@ LIB = os.path.join(HERE, "native", "_build", "libkernel_math_host.so")
 
 
 def build_host_harness(force: bool = False) -> str:
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("mpm_math.cuh", "mpm_common.cuh", "mpm_direct.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
@@ -241,3 +241,49 @@ def test_2d_stress_and_svd_roundtrip(km):
         wantG = (U * sig[:, None, :]) @ np.swapaxes(Vh, 1, 2)
         assert np.abs(G.reshape(n, 2, 2)[sel] - wantG[sel]).max() < 1e-9, snow
         assert np.abs(det[sel] - np.linalg.det(wantG[sel])).max() < 1e-9, snow
+
+
+def test_packed_fp32_p2g_phase2(km):
+    """mpm_p2g_pair.cuh (FFMPM_P2G_VARIANT=7): runs walked two particles per packed-fp32 instruction.  The
+    pair-major shared-memory layout, the masking of a partner that belongs to the neighbouring run (odd
+    run start / odd run end, also against the zero-parked tail of the last window) and the node sums of
+    three_d/p2g.py:67-80 -- against the plain per-particle sums in fp64."""
+    rng = np.random.default_rng(21)
+    n = 64
+    pay = np.zeros((n, 16), np.float32)
+    pay[:, 0:3] = rng.normal(size=(n, 3))                       # m v
+    pay[:, 3] = rng.uniform(0.5, 2, n)                          # m
+    A = rng.normal(size=(n, 3, 3)).astype(np.float32)           # affine * dx
+    f = rng.uniform(0.5, 1.5, size=(n, 3)).astype(np.float32)
+    for r in range(3):
+        pay[:, 4 + 4 * r:7 + 4 * r] = A[:, r]
+        pay[:, 7 + 4 * r] = f[:, r]
+    km.km_pair_accumulate.restype = C.c_int
+
+    def want(r0, r1, li):
+        out = np.zeros((9, 4))
+        fd = f[r0:r1].astype(np.float64)
+        w = O.bspline_weights(fd)
+        for j in range(3):
+            for k in range(3):
+                wt = w[li, :, 0] * w[j, :, 1] * w[k, :, 2]
+                dpos = np.array((li, j, k)) - fd
+                mom = pay[r0:r1, 0:3].astype(np.float64) + np.einsum("pab,pb->pa", A[r0:r1].astype(np.float64), dpos)
+                out[j * 3 + k, :3] = (wt[:, None] * mom).sum(0)
+                out[j * 3 + k, 3] = (wt * pay[r0:r1, 3]).sum()
+        return out
+
+    cases = [(0, 8), (8, 16), (3, 4), (5, 12), (4, 13), (7, 8), (0, 64), (1, 63), (56, 61)]
+    for n_slots, (r0, r1) in [(64, c) for c in cases] + [(61, (56, 61)), (1, (0, 1))]:
+        for li in range(3):
+            out = np.zeros((9, 4), np.float32)
+            rc = km.km_pair_accumulate(C.c_int(n_slots), ptr(pay), C.c_int(r0), C.c_int(r1), C.c_int(li), ptr(out))
+            assert rc == 0
+            ref = want(r0, r1, li)
+            assert np.isfinite(out).all()
+            assert np.abs(out - ref).max() <= 3e-6 * np.abs(ref).max(), (n_slots, r0, r1, li)
+    # eight aligned runs of eight particles (the 8-ppc benchmark block): 24 lanes, 8 distinct addresses, all 32 banks
+    start = np.repeat(np.arange(8, dtype=np.int32) * 4, 3)
+    bank = np.zeros(len(start), np.int32)
+    km.km_pair_banks(C.c_int(len(start)), ptr(start), ptr(bank))
+    assert sorted(set(bank.tolist())) == list(range(0, 32, 4))
