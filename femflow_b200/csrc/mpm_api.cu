@@ -386,7 +386,11 @@ static int p2g_t(FfMpmHandle* h, cudaStream_t s) {
         const int bps = h->p2g_blocks_per_sm;
         if (h->p2g_variant == 3) ok = p2g_bulk_launch<3, 1, 0>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
         else if (h->p2g_variant == 7)   // packed-fp32 phase 2 (two particles per FFMA2), 12 warps/SM for the 72 accumulator registers
-          ok = p2g_bulk_launch<4, 1, 1, P2G_NPLANES, 12, true>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
+          ok = p2g_bulk_launch<4, 1, 1, P2G_NPLANES, 12, 1>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
+        else if (h->p2g_variant == 8)   // ... and the stress of a lane's two particles in packed fp32 as well
+          ok = p2g_bulk_launch<4, 1, 1, P2G_NPLANES, 12, 2>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
+        else if (h->p2g_variant == 9)   // same at 8 warps/SM: 255 registers, no spills (variant 8 spills 364 B at 168)
+          ok = p2g_bulk_launch<4, 1, 1, P2G_NPLANES, 8, 2>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
         else if (h->p2g_variant == 6 && mat_mode_of(sv) != MAT_PLANES)   // occupancy experiment: 20 warps/SM
           ok = p2g_bulk_launch<4, 1, 1, P2G_MASS, 20>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
         else ok = p2g_bulk_launch<4, 1, 1>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);

@@ -18,10 +18,10 @@
 
 namespace ffmpm {
 
-template <int NBUF, int RAWP = P2G_NPLANES, bool PAIR = false>
+template <int NBUF, int RAWP = P2G_NPLANES, int PAIR = 0>
 struct P2GBulkWarp {
   alignas(128) float raw[NBUF][RAWP][P2G_WINDOW];   // RAWP = 24: no room for material planes (table / config material)
-  std::conditional_t<PAIR, P2GPairSlab, P2GWarpSlab<float>> slab;   // PAIR: pair-major payload (mpm_p2g_pair.cuh)
+  std::conditional_t<(PAIR > 0), P2GPairSlab, P2GWarpSlab<float>> slab;   // PAIR: pair-major payload (mpm_p2g_pair.cuh)
   alignas(16) unsigned char mat[NBUF][P2G_WINDOW];   // material rows of the window (table mode)
   alignas(8) unsigned long long bar[NBUF];
 };
@@ -89,9 +89,10 @@ __device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
 // RAWP / SMW: planes held per window and resident warps per SM the launch bounds ask for.  <27, 16> is the
 // measured default (128 registers); <24, 20> (no material planes: 11.1 KB of shared memory per warp, 5 CTAs
 // of 4 warps, <= 96 registers) is the occupancy experiment behind FFMPM_P2G_VARIANT=6.
-// PAIR: phase 2 walks the runs two particles per instruction with packed fp32 (FFMA2; mpm_p2g_pair.cuh) --
-// FFMPM_P2G_VARIANT=7, written after this round's GPU budget was spent: not yet measured.
-template <int WARPS, int NBUF, int LDGSTS, int RAWP = P2G_NPLANES, int SMW = 16, bool PAIR = false>
+// PAIR >= 1: phase 2 walks the runs two particles per instruction with packed fp32 (FFMA2; mpm_p2g_pair.cuh);
+// PAIR == 2: phase 1 too -- the stress of the two particles a lane owns in a window is evaluated in packed
+// fp32.  FFMPM_P2G_VARIANT=7 / 8, written after this round's GPU budget was spent: not yet measured.
+template <int WARPS, int NBUF, int LDGSTS, int RAWP = P2G_NPLANES, int SMW = 16, int PAIR = 0>
 __global__ void __launch_bounds__(WARPS * 32, SMW / WARPS)
 p2g_bulk3_kernel(DevCfg cfg, P2GPlanes planes, long long n, float* __restrict__ grid, ErrRec* err, int wpw) {
   using T = float;
@@ -164,6 +165,26 @@ p2g_bulk3_kernel(DevCfg cfg, P2GPlanes planes, long long n, float* __restrict__ 
     }
     // ---- phase 1: lane per particle, state from the prefetched slab ----
     int node[2];
+    if constexpr (PAIR == 2) {
+      // both particles of the lane (slots lane and lane + 32) in one packed evaluation
+      const bool live_a = lane < cnt, live_b = 32 + lane < cnt;
+      auto getter = [&](int idx) {
+        return [&, idx](int k) -> T {
+          const int row = planes.material ? (int)W.mat[buf][idx] : 0;
+          if (k >= P2G_MASS && planes.table) return __ldg(planes.table + (k - P2G_MASS) * MAT_ROWS + row);
+          if constexpr (RAWP < P2G_NPLANES) { if (k >= RAWP) return (T)0; }
+          return W.raw[buf][k][idx];
+        };
+      };
+      P2GParticle3<T> qa, qb;
+      qa.ok = qb.ok = false;
+      p2g_prepare3_pair(cfg, getter(lane), getter(32 + lane), has_mat, live_a, live_b, qa, qb);
+      node[0] = node[1] = -1;
+      if (live_a) node[0] = p2g_park_pair(S.pay, S.node0, qa, lane, dx, ny, nz);
+      else p2g_park_pair_zero(S.pay, lane);
+      if (live_b) node[1] = p2g_park_pair(S.pay, S.node0, qb, 32 + lane, dx, ny, nz);
+      else p2g_park_pair_zero(S.pay, 32 + lane);
+    } else {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int idx = h * 32 + lane;
@@ -178,22 +199,23 @@ p2g_bulk3_kernel(DevCfg cfg, P2GPlanes planes, long long n, float* __restrict__ 
               return W.raw[buf][k][idx];
             },
             has_mat, 1.0);
-        if constexpr (PAIR) node[h] = p2g_park_pair(S.pay, S.node0, q, idx, dx, ny, nz);
+        if constexpr (PAIR > 0) node[h] = p2g_park_pair(S.pay, S.node0, q, idx, dx, ny, nz);
         else node[h] = p2g_park(S, q, idx, dx, ny, nz);
-      } else if constexpr (PAIR) {
+      } else if constexpr (PAIR > 0) {
         p2g_park_pair_zero(S.pay, idx);   // the last window's tail: a masked partner must read finite values
       }
+    }
     }
     __syncwarp();
     // single buffer: the raw slab is free again -> prefetch the next window behind phase 2
     if (NBUF == 1 && win + total_warps < last_excl) issue(win + total_warps, 0);
-    if constexpr (PAIR) p2g_runs_phase2_pair(S, node, cnt, lane, ny, nz, grid);
+    if constexpr (PAIR > 0) p2g_runs_phase2_pair(S, node, cnt, lane, ny, nz, grid);
     else p2g_runs_phase2<T>(S, node, cnt, lane, ny, nz, grid);
     __syncwarp();   // the payload slab is rewritten by the next window
   }
 }
 
-template <int WARPS, int NBUF, int LDGSTS, int RAWP = P2G_NPLANES, int SMW = 16, bool PAIR = false>
+template <int WARPS, int NBUF, int LDGSTS, int RAWP = P2G_NPLANES, int SMW = 16, int PAIR = 0>
 static bool p2g_bulk_launch(const DevCfg& cfg, const StateView<float>& s, long long n, float* grid, ErrRec* err,
                             int sm_count, int blocks_per_sm, cudaStream_t st) {
   const size_t smem = sizeof(P2GBulkWarp<NBUF, RAWP, PAIR>) * WARPS;

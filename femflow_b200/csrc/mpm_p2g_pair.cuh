@@ -51,6 +51,165 @@ FFMPM_HD F2 f2_add(F2 a, F2 b) {
 #endif
 }
 
+FFMPM_HD F2 f2_sub(F2 a, F2 b) { return f2_fma(b, f2(-1.0f), a); }   // a - b: one FFMA2 (operand negation folds in SASS)
+
+// ----------------------------------------------------------------------------
+// The fp32 perturbation-form stress of mpm_math.cuh (fixed_corotated_affine3_f32) for TWO particles at
+// once: every quantity is a register pair, every operation one packed instruction.  Same formulae, same
+// series tiers; the degree is picked from the more strained of the two, and the function declines (the
+// caller then evaluates both particles one by one, fp64 path included) when either is beyond the series.
+// ----------------------------------------------------------------------------
+struct Sym3x2 {
+  F2 xx, xy, xz, yy, yz, zz;
+};
+
+FFMPM_HD Sym3x2 sym3_mul2(const Sym3x2& a, const Sym3x2& b) {
+  Sym3x2 r;
+  r.xx = f2_fma(a.xz, b.xz, f2_fma(a.xy, b.xy, f2_mul(a.xx, b.xx)));
+  r.xy = f2_fma(a.xz, b.yz, f2_fma(a.xy, b.yy, f2_mul(a.xx, b.xy)));
+  r.xz = f2_fma(a.xz, b.zz, f2_fma(a.xy, b.yz, f2_mul(a.xx, b.xz)));
+  r.yy = f2_fma(a.yz, b.yz, f2_fma(a.yy, b.yy, f2_mul(a.xy, b.xy)));
+  r.yz = f2_fma(a.yz, b.zz, f2_fma(a.yy, b.yz, f2_mul(a.xy, b.xz)));
+  r.zz = f2_fma(a.zz, b.zz, f2_fma(a.yz, b.yz, f2_mul(a.xz, b.xz)));
+  return r;
+}
+
+struct Mat3x2 {
+  F2 a00, a01, a02, a10, a11, a12, a20, a21, a22;
+};
+
+FFMPM_HD bool fixed_corotated_affine3_f32x2(const Mat3x2& F, const Mat3x2& C, F2 mu, F2 lam, F2 mass, float dt_vol_dinv,
+                                            Mat3x2& A) {
+  const F2 neg1 = f2(-1.0f), two = f2(2.0f);
+  Mat3x2 E = F;
+  E.a00 = f2_add(F.a00, neg1); E.a11 = f2_add(F.a11, neg1); E.a22 = f2_add(F.a22, neg1);
+  Sym3x2 G;
+  G.xx = f2_fma(two, E.a00, f2_fma(E.a20, E.a20, f2_fma(E.a10, E.a10, f2_mul(E.a00, E.a00))));
+  G.yy = f2_fma(two, E.a11, f2_fma(E.a21, E.a21, f2_fma(E.a11, E.a11, f2_mul(E.a01, E.a01))));
+  G.zz = f2_fma(two, E.a22, f2_fma(E.a22, E.a22, f2_fma(E.a12, E.a12, f2_mul(E.a02, E.a02))));
+  G.xy = f2_add(f2_add(E.a01, E.a10), f2_fma(E.a20, E.a21, f2_fma(E.a10, E.a11, f2_mul(E.a00, E.a01))));
+  G.xz = f2_add(f2_add(E.a02, E.a20), f2_fma(E.a20, E.a22, f2_fma(E.a10, E.a12, f2_mul(E.a00, E.a02))));
+  G.yz = f2_add(f2_add(E.a12, E.a21), f2_fma(E.a21, E.a22, f2_fma(E.a11, E.a12, f2_mul(E.a01, E.a02))));
+  const F2 d2 = f2_fma(G.zz, G.zz, f2_fma(G.yy, G.yy, f2_mul(G.xx, G.xx)));
+  const F2 o2 = f2_fma(G.yz, G.yz, f2_fma(G.xz, G.xz, f2_mul(G.xy, G.xy)));
+  const F2 r2p = f2_fma(two, o2, d2);
+  const float r2 = fmaxf(r2p.v.x, r2p.v.y);
+  if (!(r2 < kPerturbationMaxR * kPerturbationMaxR)) return false;      // also catches NaN in either half
+  const float c[8] = {0.5f, -0.375f, 0.3125f, -0.2734375f, 0.24609375f, -0.2255859375f, 0.20947265625f,
+                      -0.196380615234375f};
+  float ca = c[7], cb = c[6];
+  int top = 5;
+  if (r2 < 0.005f * 0.005f) { ca = c[2]; cb = c[1]; top = 0; }
+  else if (r2 < 0.04f * 0.04f) { ca = c[4]; cb = c[3]; top = 2; }
+  const F2 ca2 = f2(ca), cb2 = f2(cb);
+  Sym3x2 q;
+  q.xx = f2_fma(ca2, G.xx, cb2); q.yy = f2_fma(ca2, G.yy, cb2); q.zz = f2_fma(ca2, G.zz, cb2);
+  q.xy = f2_mul(ca2, G.xy); q.xz = f2_mul(ca2, G.xz); q.yz = f2_mul(ca2, G.yz);
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    if (i <= top) {
+      q = sym3_mul2(G, q);
+      const F2 ci = f2(c[i]);
+      q.xx = f2_add(q.xx, ci); q.yy = f2_add(q.yy, ci); q.zz = f2_add(q.zz, ci);
+    }
+  }
+  const Sym3x2 M = sym3_mul2(G, q);
+  // W = F M,  X = W F^T (symmetric)
+  const F2 w00 = f2_fma(F.a02, M.xz, f2_fma(F.a01, M.xy, f2_mul(F.a00, M.xx)));
+  const F2 w01 = f2_fma(F.a02, M.yz, f2_fma(F.a01, M.yy, f2_mul(F.a00, M.xy)));
+  const F2 w02 = f2_fma(F.a02, M.zz, f2_fma(F.a01, M.yz, f2_mul(F.a00, M.xz)));
+  const F2 w10 = f2_fma(F.a12, M.xz, f2_fma(F.a11, M.xy, f2_mul(F.a10, M.xx)));
+  const F2 w11 = f2_fma(F.a12, M.yz, f2_fma(F.a11, M.yy, f2_mul(F.a10, M.xy)));
+  const F2 w12 = f2_fma(F.a12, M.zz, f2_fma(F.a11, M.yz, f2_mul(F.a10, M.xz)));
+  const F2 w20 = f2_fma(F.a22, M.xz, f2_fma(F.a21, M.xy, f2_mul(F.a20, M.xx)));
+  const F2 w21 = f2_fma(F.a22, M.yz, f2_fma(F.a21, M.yy, f2_mul(F.a20, M.xy)));
+  const F2 w22 = f2_fma(F.a22, M.zz, f2_fma(F.a21, M.yz, f2_mul(F.a20, M.xz)));
+  const F2 x00 = f2_fma(w02, F.a02, f2_fma(w01, F.a01, f2_mul(w00, F.a00)));
+  const F2 x01 = f2_fma(w02, F.a12, f2_fma(w01, F.a11, f2_mul(w00, F.a10)));
+  const F2 x02 = f2_fma(w02, F.a22, f2_fma(w01, F.a21, f2_mul(w00, F.a20)));
+  const F2 x11 = f2_fma(w12, F.a12, f2_fma(w11, F.a11, f2_mul(w10, F.a10)));
+  const F2 x12 = f2_fma(w12, F.a22, f2_fma(w11, F.a21, f2_mul(w10, F.a20)));
+  const F2 x22 = f2_fma(w22, F.a22, f2_fma(w21, F.a21, f2_mul(w20, F.a20)));
+  // J - 1 = tr E + principal 2x2 minors + det E, without cancellation
+  const F2 trE = f2_add(f2_add(E.a00, E.a11), E.a22);
+  const F2 m01 = f2_sub(f2_mul(E.a00, E.a11), f2_mul(E.a01, E.a10));
+  const F2 m02 = f2_sub(f2_mul(E.a00, E.a22), f2_mul(E.a02, E.a20));
+  const F2 m12 = f2_sub(f2_mul(E.a11, E.a22), f2_mul(E.a12, E.a21));
+  const F2 c2 = f2_add(f2_add(m01, m02), m12);
+  const F2 k0 = f2_sub(f2_mul(E.a11, E.a22), f2_mul(E.a12, E.a21));
+  const F2 k1 = f2_sub(f2_mul(E.a10, E.a22), f2_mul(E.a12, E.a20));
+  const F2 k2m = f2_sub(f2_mul(E.a10, E.a21), f2_mul(E.a11, E.a20));
+  const F2 dE = f2_fma(E.a02, k2m, f2_sub(f2_mul(E.a00, k0), f2_mul(E.a01, k1)));
+  const F2 jm1 = f2_add(f2_add(trE, c2), dE);
+  const F2 l = f2_mul(f2_mul(lam, jm1), f2_add(jm1, f2(1.0f)));       // lam (J-1) J, broadcast onto ALL entries (quirk 2)
+  const F2 nk = f2(-dt_vol_dinv);
+  const F2 k2 = f2_mul(f2_mul(nk, two), mu), kl = f2_mul(nk, l);
+  A.a00 = f2_fma(mass, C.a00, f2_fma(k2, x00, kl)); A.a01 = f2_fma(mass, C.a01, f2_fma(k2, x01, kl));
+  A.a02 = f2_fma(mass, C.a02, f2_fma(k2, x02, kl)); A.a10 = f2_fma(mass, C.a10, f2_fma(k2, x01, kl));
+  A.a11 = f2_fma(mass, C.a11, f2_fma(k2, x11, kl)); A.a12 = f2_fma(mass, C.a12, f2_fma(k2, x12, kl));
+  A.a20 = f2_fma(mass, C.a20, f2_fma(k2, x02, kl)); A.a21 = f2_fma(mass, C.a21, f2_fma(k2, x12, kl));
+  A.a22 = f2_fma(mass, C.a22, f2_fma(k2, x22, kl));
+  return true;
+}
+
+// Phase 1 for the two particles a lane owns in a window (slots `lane` and `lane + 32`): cell index, weights
+// offset and material one by one (integer / fp64 work), the stress of both in packed fp32.  Falls back to
+// the one-particle routine (p2g_prepare3_from, fp64 stress included) unless both are inside the grid and
+// inside the series' strain range.  `live_b` false: the window holds no second particle for this lane.
+template <typename GetA, typename GetB>
+FFMPM_HD void p2g_prepare3_pair(const DevCfg& cfg, GetA ga, GetB gb, bool has_mat, bool live_a, bool live_b,
+                                P2GParticle3<float>& qa, P2GParticle3<float>& qb) {
+  bool packed = live_a && live_b && cfg.fp32_stress && cfg.model == 0;
+  if (packed) {
+    float mass_a, mu_a, lam_a, mass_b, mu_b, lam_b;
+    auto index_part = [&](auto get, P2GParticle3<float>& q, float& mass_f, float& mu_f, float& lam_f) {
+      const float x0 = get(P2G_X), x1 = get(P2G_X + 1), x2 = get(P2G_X + 2);
+      int gx, gy, gz;
+      base_fx(x0, cfg, gx, q.fx);
+      base_fx(x1, cfg, gy, q.fy);
+      base_fx(x2, cfg, gz, q.fz);
+      q.bx = gx - cfg.origin[0]; q.by = gy - cfg.origin[1]; q.bz = gz - cfg.origin[2];
+      q.ok = !(isnan((double)x0) || isnan((double)x1) || isnan((double)x2)) &&
+             q.bx >= 0 && q.by >= 0 && q.bz >= 0 && q.bx + 2 < cfg.n[0] && q.by + 2 < cfg.n[1] && q.bz + 2 < cfg.n[2];
+      const double mass = has_mat ? (double)get(P2G_MASS) : cfg.mass;
+      const double mu = (has_mat ? (double)get(P2G_MU) : cfg.mu0) * cfg.hardening;     // constant hardening: a multiplier (quirk 8)
+      const double lam = (has_mat ? (double)get(P2G_LAM) : cfg.lam0) * cfg.hardening;
+      mass_f = (float)mass; mu_f = (float)mu; lam_f = (float)lam;
+      q.m = (float)mass;
+      if (has_mat) {
+        q.mvx = q.m * get(P2G_V); q.mvy = q.m * get(P2G_V + 1); q.mvz = q.m * get(P2G_V + 2);
+      } else {
+        q.mvx = (float)(mass * (double)get(P2G_V)); q.mvy = (float)(mass * (double)get(P2G_V + 1));
+        q.mvz = (float)(mass * (double)get(P2G_V + 2));
+      }
+    };
+    index_part(ga, qa, mass_a, mu_a, lam_a);
+    index_part(gb, qb, mass_b, mu_b, lam_b);
+    packed = qa.ok && qb.ok;
+    if (packed) {
+      Mat3x2 F, C, A;
+      F.a00 = f2(ga(P2G_F + 0), gb(P2G_F + 0)); F.a01 = f2(ga(P2G_F + 1), gb(P2G_F + 1)); F.a02 = f2(ga(P2G_F + 2), gb(P2G_F + 2));
+      F.a10 = f2(ga(P2G_F + 3), gb(P2G_F + 3)); F.a11 = f2(ga(P2G_F + 4), gb(P2G_F + 4)); F.a12 = f2(ga(P2G_F + 5), gb(P2G_F + 5));
+      F.a20 = f2(ga(P2G_F + 6), gb(P2G_F + 6)); F.a21 = f2(ga(P2G_F + 7), gb(P2G_F + 7)); F.a22 = f2(ga(P2G_F + 8), gb(P2G_F + 8));
+      C.a00 = f2(ga(P2G_C + 0), gb(P2G_C + 0)); C.a01 = f2(ga(P2G_C + 1), gb(P2G_C + 1)); C.a02 = f2(ga(P2G_C + 2), gb(P2G_C + 2));
+      C.a10 = f2(ga(P2G_C + 3), gb(P2G_C + 3)); C.a11 = f2(ga(P2G_C + 4), gb(P2G_C + 4)); C.a12 = f2(ga(P2G_C + 5), gb(P2G_C + 5));
+      C.a20 = f2(ga(P2G_C + 6), gb(P2G_C + 6)); C.a21 = f2(ga(P2G_C + 7), gb(P2G_C + 7)); C.a22 = f2(ga(P2G_C + 8), gb(P2G_C + 8));
+      const double k = (cfg.dt * cfg.volume) * (4.0 * cfg.inv_dx * cfg.inv_dx);
+      packed = fixed_corotated_affine3_f32x2(F, C, f2(mu_a, mu_b), f2(lam_a, lam_b), f2(mass_a, mass_b),
+                                             (float)k, A);
+      if (packed) {
+        qa.a00 = A.a00.v.x; qa.a01 = A.a01.v.x; qa.a02 = A.a02.v.x; qa.a10 = A.a10.v.x; qa.a11 = A.a11.v.x; qa.a12 = A.a12.v.x;
+        qa.a20 = A.a20.v.x; qa.a21 = A.a21.v.x; qa.a22 = A.a22.v.x;
+        qb.a00 = A.a00.v.y; qb.a01 = A.a01.v.y; qb.a02 = A.a02.v.y; qb.a10 = A.a10.v.y; qb.a11 = A.a11.v.y; qb.a12 = A.a12.v.y;
+        qb.a20 = A.a20.v.y; qb.a21 = A.a21.v.y; qb.a22 = A.a22.v.y;
+        return;
+      }
+    }
+  }
+  if (live_a) qa = p2g_prepare3_from<float>(cfg, ga, has_mat, 1.0);
+  if (live_b) qb = p2g_prepare3_from<float>(cfg, gb, has_mat, 1.0);
+}
+
 constexpr int P2G_NPAIR = P2G_WINDOW / 2;
 constexpr int P2G_PAIR_PADDED = P2G_NPAIR + P2G_NPAIR / 4;
 constexpr int P2G_PAIR_PLANES = 8;   // 16 payload components, two per plane

@@ -2,11 +2,30 @@
 # First GPU calls of the next round (everything here was written after this round's GPU budget ran out).
 #   gpurun --gpus 2 --timeout 600 -- 'bash scripts/next_round_measure.sh 2'
 #   gpurun --gpus 8 --timeout 900 -- 'bash scripts/next_round_measure.sh 8'
+#   gpurun --timeout 600 -- 'bash scripts/next_round_measure.sh 1'     (packed-fp32 P2G variants: parity, then A/B)
 set -u
 N=${1:-2}
 out=gpurun_out/next_n$N
 mkdir -p $out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+if [ "$N" = "1" ]; then
+  FFMPM_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -k "packed_fp32" > $out/pytest_packed.txt 2>&1
+  tail -3 $out/pytest_packed.txt
+  for v in 5 7 8 9; do
+    FFMPM_P2G_VARIANT=$v timeout 120 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --e2e-steps 1 \
+        > $out/bench_v$v.json 2> $out/bench_v$v.err
+  done
+  python - <<PY
+import json
+for v in (5, 7, 8, 9):
+    try:
+        d = json.load(open("$out/bench_v%d.json" % v))
+        print("variant", v, d["ms_per_step"], d["roofline"]["phase_ms"])
+    except Exception as e:
+        print("variant", v, "failed:", e)
+PY
+  exit 0
+fi
 if [ "$N" = "2" ]; then
   # SymmHalo on hardware: parity first (signals time out after 20 s instead of hanging), then p2p vs symm
   FFMPM_TEST_SYMM=1 timeout 180 python -m pytest tests/test_gpu_distributed.py -x -q -k "symm" > $out/pytest_symm.txt 2>&1

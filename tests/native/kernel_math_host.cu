@@ -130,6 +130,43 @@ void km_base_fx_f64(double inv_dx, long long n, const double* x, int* base, doub
   for (long long p = 0; p < n; ++p) base_fx<double>(x[p], c, base[p], fx[p]);
 }
 
+// Packed-fp32 phase 1 (mpm_p2g_pair.cuh: p2g_prepare3_pair): particle p is paired with particle p + n/2,
+// as a lane pairs the slots `lane` and `lane + 32` of a window; an odd last particle is evaluated alone.
+void km_prepare3_pair_f32(int res, int n_nodes, double inv_dx, double dx, double dt, double volume, double hardening,
+                          int fp32_stress, int index_fp32, long long n, const float* x, const float* v, const float* C,
+                          const float* F, const float* mass, const float* mu, const float* lam, int* base, float* fx,
+                          float* aff, float* mv, float* m, int* ok) {
+  const DevCfg cfg = make_cfg(res, n_nodes, inv_dx, dx, dt, volume, hardening, 0, fp32_stress, index_fp32);
+  const long long half = (n + 1) / 2;
+  auto getter = [&](long long p) {
+    return [=](int k) -> float {
+      if (k < P2G_V) return x[3 * p + k];
+      if (k < P2G_C) return v[3 * p + (k - P2G_V)];
+      if (k < P2G_F) return C[9 * p + (k - P2G_C)];
+      if (k < P2G_MASS) return F[9 * p + (k - P2G_F)];
+      return k == P2G_MASS ? mass[p] : (k == P2G_MU ? mu[p] : lam[p]);
+    };
+  };
+  auto store = [&](long long p, const P2GParticle3<float>& q) {
+    ok[p] = q.ok ? 1 : 0;
+    base[3 * p] = q.bx; base[3 * p + 1] = q.by; base[3 * p + 2] = q.bz;
+    fx[3 * p] = q.fx; fx[3 * p + 1] = q.fy; fx[3 * p + 2] = q.fz;
+    if (!q.ok) return;
+    const float a[9] = {q.a00, q.a01, q.a02, q.a10, q.a11, q.a12, q.a20, q.a21, q.a22};
+    for (int e = 0; e < 9; ++e) aff[9 * p + e] = a[e];
+    mv[3 * p] = q.mvx; mv[3 * p + 1] = q.mvy; mv[3 * p + 2] = q.mvz;
+    m[p] = q.m;
+  };
+  for (long long p = 0; p < half; ++p) {
+    const long long pb = p + half;
+    const bool live_b = pb < n;
+    P2GParticle3<float> qa{}, qb{};
+    p2g_prepare3_pair(cfg, getter(p), getter(live_b ? pb : p), true, true, live_b, qa, qb);
+    store(p, qa);
+    if (live_b) store(pb, qb);
+  }
+}
+
 // Packed-fp32 P2G phase 2 (mpm_p2g_pair.cuh): park `n_slots` payloads (16 floats each, PP_* order) in the
 // pair-major shared-memory image exactly as phase 1 does, then accumulate x-slab `li` of the run [r0, r1).
 // Slots >= n_slots are parked as the kernel parks the tail of the last window.  Returns 0, or -1 when two

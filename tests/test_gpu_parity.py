@@ -5,6 +5,8 @@ velocity and particle x, v, C, F within 1e-5 max-norm-relative per substep for t
 fp32 build (absolute floors from the reference's own neighbouring fields, SURVEY
 8d), 1e-11 for the fp64 build (only summation order differs).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -359,6 +361,52 @@ def test_multi_substep_pipelines_vs_oracle(mode):
     out = {k: t.double().cpu().numpy() for k, t in s.get_particles().items()}
     V = max(np.abs(v).max(), sc.dt * 9.8)
     steps = 20
+    assert rel_err(out["x"], x, 1.0) < 1e-5 * steps
+    assert np.abs(out["v"] - v).max() / V < 1e-5 * steps
+    assert rel_err(out["F"], F, 1.0) < 1e-5 * steps
+    assert np.abs(out["C"] - C).max() / (4 * sc.res * V) < 1e-5 * steps
+    s.close()
+
+
+@pytest.mark.skipif(os.environ.get("FFMPM_TEST_EXPERIMENTAL") != "1",
+                    reason="packed-fp32 P2G (FFMPM_P2G_VARIANT 7/8/9) was written after the round's GPU budget ran out: "
+                           "its arithmetic is checked on the host (tests/test_kernel_math_host.py); set "
+                           "FFMPM_TEST_EXPERIMENTAL=1 to run it on a GPU")
+@pytest.mark.parametrize("variant", [7, 8, 9])
+@pytest.mark.parametrize("n_materials", [1, 3, 300])
+def test_packed_fp32_p2g_variants(variant, n_materials, monkeypatch):
+    """P2G with two particles per FFMA2 (mpm_p2g_pair.cuh): the grid after P2G and 12 chained substeps against
+    the oracle, with one material, a material table and material planes; a particle count that leaves the
+    last window ragged (n % 64 != 0, odd)."""
+    from femflow_b200 import scenes
+    from femflow_b200.mpm import MpmSolver
+    from oracle import native as ON
+    monkeypatch.setenv("FFMPM_P2G_VARIANT", str(variant))
+    sc = scenes.elastic_block(3, 64, 20, 2, seed=4)
+    n = sc.n - 37
+    rng = np.random.default_rng(0)
+    k = rng.integers(0, n_materials, n).astype(np.float64)
+    f32 = lambda a: np.asarray(a, dtype=np.float32).astype(np.float64)
+    m = f32(sc.mass * (1 + 0.25 * k / n_materials)); mu = f32(sc.mu_0 * (1 + 0.5 * k / n_materials))
+    lam = f32(sc.lambda_0 * (1 - 0.125 * k / n_materials))
+    x, v, F, C = (a[:n].astype(np.float64) for a in (sc.x, sc.v, sc.F, sc.C))
+    s = MpmSolver(3, sc.res, sc.dt, sc.volume, sc.gravity, sc.hardening, capacity=n)
+    s.set_particles(x, v, F, C, None, m, mu, lam)
+    s.clear_grid(); s.bin(); s.p2g()
+    G = sc.res + 1
+    gv = np.zeros((G, G, G, 3)); gm = np.zeros((G, G, G, 1))
+    O.p2g_3d(float(sc.res), sc.hardening, 1 / sc.res, sc.dt, sc.volume, gv, gm, x, m, mu, lam, v, F, C, np.ones((n, 1)))
+    g = s.grid().double().cpu().numpy()
+    assert s.poll_error() == 0
+    assert rel_err(g[..., 3:], gm) < 1e-5 and rel_err(g[..., :3], gv) < 1e-5
+    s.set_particles(x, v, F, C, None, m, mu, lam)
+    steps = 12
+    s.substep(steps)
+    s.check_errors()
+    for _ in range(steps):
+        ON.solve_mls_mpm_3d(sc.res, float(sc.res), sc.hardening, 1 / sc.res, sc.dt, sc.volume, sc.gravity, x, m, mu, lam, v, F, C)
+    out = {k_: t.double().cpu().numpy() for k_, t in s.get_particles().items()}
+    V = max(np.abs(v).max(), sc.dt * 9.8)
     assert rel_err(out["x"], x, 1.0) < 1e-5 * steps
     assert np.abs(out["v"] - v).max() / V < 1e-5 * steps
     assert rel_err(out["F"], F, 1.0) < 1e-5 * steps

@@ -287,3 +287,51 @@ def test_packed_fp32_p2g_phase2(km):
     bank = np.zeros(len(start), np.int32)
     km.km_pair_banks(C.c_int(len(start)), ptr(start), ptr(bank))
     assert sorted(set(bank.tolist())) == list(range(0, 32, 4))
+
+
+def prepare3_pair(km, res, x, v, Cm, F, mass, mu, lam, dt, volume, hardening=1.0, fp32_stress=1):
+    n = len(x)
+    arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (x, v, Cm.reshape(n, 9), F.reshape(n, 9), mass, mu, lam)]
+    base = np.zeros((n, 3), np.int32); fx = np.zeros((n, 3), np.float32); aff = np.zeros((n, 9), np.float32)
+    mv = np.zeros((n, 3), np.float32); m = np.zeros(n, np.float32); ok = np.zeros(n, np.int32)
+    km.km_prepare3_pair_f32(C.c_int(res), C.c_int(res + 1), C.c_double(float(res)), C.c_double(1.0 / res), C.c_double(dt),
+                            C.c_double(volume), C.c_double(hardening), C.c_int(fp32_stress), C.c_int(int(res & (res - 1) == 0)),
+                            C.c_longlong(n), *(ptr(a) for a in arrs), ptr(base), ptr(fx), ptr(aff), ptr(mv), ptr(m), ptr(ok))
+    return base, fx, aff.reshape(n, 3, 3), mv, m, ok.astype(bool)
+
+
+@pytest.mark.parametrize("strain", [0.0, 1e-6, 1e-4, 1.5e-3, 1e-2, 4e-2, 0.3, "mixed"])
+def test_packed_fp32_stress_pairs(km, strain):
+    """p2g_prepare3_pair (FFMPM_P2G_VARIANT=8/9): the stress of two particles per packed instruction.  Same
+    1e-5 bar against LAPACK as the one-particle path on every series tier; a pair with one particle beyond
+    the series, outside the grid or NaN falls back to the one-particle routine for both; index, weights
+    offset and mass*v are the one-particle routine's bits."""
+    rng = np.random.default_rng(13)
+    res, n = 32, 4001                                            # odd: the last particle has no partner
+    dx = 1.0 / res
+    vol = float(f32((dx / 2) ** 3))
+    x = f32(rng.uniform(0.25, 0.75, size=(n, 3)))
+    if strain == "mixed":
+        amp = rng.choice([1e-5, 1e-3, 2e-2, 6e-2, 0.3], size=(n, 1, 1))
+        x[5] = [0.99, 0.5, 0.5]; x[n // 2 + 7, 1] = np.nan; x[11] = [0.0, 0.5, 0.5]
+    else:
+        amp = strain
+    F = f32(np.eye(3) + amp * rng.uniform(-1, 1, size=(n, 3, 3)))
+    v = f32(rng.normal(size=(n, 3)))
+    Cm = f32(rng.normal(0, 0.05, size=(n, 3, 3))) if strain == "mixed" else np.zeros((n, 3, 3))
+    mass = f32(rng.uniform(0.5, 1.5, n) * vol); mu = f32(rng.uniform(3000, 5000, n)); lam = f32(rng.uniform(2000, 3000, n))
+    ref = prepare3(km, "f32", res, x, v, Cm, F, mass, mu, lam, 1e-4, vol)
+    got = prepare3_pair(km, res, x, v, Cm, F, mass, mu, lam, 1e-4, vol)
+    ok = ref[5]
+    assert np.array_equal(got[5], ok)
+    if strain == "mixed":
+        assert not ok[5] and not ok[n // 2 + 7] and ok[11] and ok.sum() == n - 2
+    assert np.array_equal(got[0][ok], ref[0][ok]) and np.array_equal(got[1][ok], ref[1][ok])   # base, fx: same bits
+    assert np.array_equal(got[3][ok], ref[3][ok]) and np.array_equal(got[4][ok], ref[4][ok])  # m v, m: same bits
+    want = O.fixed_corotated_stress_3d(F[ok], float(res), mu[ok], lam[ok], 1e-4, vol, mass[ok], Cm[ok])
+    scale = np.abs(want).max()
+    if strain == 0.0:
+        assert np.all(got[2] == 0.0)
+    else:
+        assert np.abs(got[2][ok] - want).max() / scale < 1e-5
+        assert np.abs(got[2][ok] - ref[2][ok]).max() / scale < 2e-6      # and next to the one-particle evaluation
