@@ -24,34 +24,6 @@
 
 namespace ffmpm {
 
-struct F2 {
-  float2 v;
-};
-FFMPM_HD F2 f2(float a, float b) { F2 r; r.v.x = a; r.v.y = b; return r; }
-FFMPM_HD F2 f2(float a) { return f2(a, a); }
-FFMPM_HD F2 f2_fma(F2 a, F2 b, F2 c) {
-#ifdef __CUDA_ARCH__
-  F2 r; r.v = __ffma2_rn(a.v, b.v, c.v); return r;
-#else
-  return f2(fmaf(a.v.x, b.v.x, c.v.x), fmaf(a.v.y, b.v.y, c.v.y));
-#endif
-}
-FFMPM_HD F2 f2_mul(F2 a, F2 b) {
-#ifdef __CUDA_ARCH__
-  F2 r; r.v = __fmul2_rn(a.v, b.v); return r;
-#else
-  return f2(a.v.x * b.v.x, a.v.y * b.v.y);
-#endif
-}
-FFMPM_HD F2 f2_add(F2 a, F2 b) {
-#ifdef __CUDA_ARCH__
-  F2 r; r.v = __fadd2_rn(a.v, b.v); return r;
-#else
-  return f2(a.v.x + b.v.x, a.v.y + b.v.y);
-#endif
-}
-
-FFMPM_HD F2 f2_sub(F2 a, F2 b) { return f2_fma(b, f2(-1.0f), a); }   // a - b: one FFMA2 (operand negation folds in SASS)
 
 // ----------------------------------------------------------------------------
 // The fp32 perturbation-form stress of mpm_math.cuh (fixed_corotated_affine3_f32) for TWO particles at

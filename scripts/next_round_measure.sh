@@ -15,11 +15,13 @@ if [ "$N" = "1" ]; then
     FFMPM_P2G_VARIANT=$v timeout 120 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --e2e-steps 1 \
         > $out/bench_v$v.json 2> $out/bench_v$v.err
   done
+  FFMPM_G2P_PACKED=1 timeout 120 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --e2e-steps 1 \
+      > $out/bench_vg2p.json 2> $out/bench_vg2p.err
   python - <<PY
 import json
-for v in (5, 7, 8, 9):
+for v in (5, 7, 8, 9, "g2p"):
     try:
-        d = json.load(open("$out/bench_v%d.json" % v))
+        d = json.load(open("$out/bench_v%s.json" % v))
         print("variant", v, d["ms_per_step"], d["roofline"]["phase_ms"])
     except Exception as e:
         print("variant", v, "failed:", e)
