@@ -15,6 +15,8 @@ if [ "$N" = "1" ]; then
     FFMPM_P2G_VARIANT=$v timeout 120 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --e2e-steps 1 \
         > $out/bench_v$v.json 2> $out/bench_v$v.err
   done
+  timeout 180 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --e2e-streamed > $out/bench_e2e_streamed.json 2> $out/bench_e2e_streamed.err
+  timeout 120 python bench.py --steps 100 --warmup 6 --no-cpu-baseline --e2e-steps 1 --graph > $out/bench_graph.json 2> $out/bench_graph.err
   FFMPM_G2P_PACKED=1 timeout 120 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --e2e-steps 1 \
       > $out/bench_vg2p.json 2> $out/bench_vg2p.err
   python - <<PY
