@@ -248,10 +248,12 @@ class _TorchSymmFabric:
 
 class SlabDriver:
     def __init__(self, plan: SlabPlan, local: LocalSlab, group=None, migrate_every: Optional[int] = None,
-                 halo: str = "p2p", fabric=None):
+                 halo: str = "p2p", fabric=None, rebalance_every: int = 0):
         """``halo``: ``"p2p"`` = grouped send/recv of the shared planes (NCCL on GPUs, gloo in the CPU
-        tests); ``"symm"`` = one-sided puts into the neighbour's symmetric-memory inbox (``SymmHalo``)."""
+        tests); ``"symm"`` = one-sided puts into the neighbour's symmetric-memory inbox (``SymmHalo``).
+        ``rebalance_every``: offer a re-cut of the slabs (``rebalance``) every that many substeps; 0 = never."""
         self.plan, self.local, self.group = plan, local, group
+        self.rebalance_every = int(rebalance_every)
         if halo not in ("p2p", "symm"):
             raise ValueError(f"unknown halo transport {halo!r}")
         self.migrate_every = migrate_every if migrate_every is not None else max(1, plan.margin)
@@ -314,7 +316,9 @@ class SlabDriver:
             self._mark("gather")
             self.steps += 1
             if self.plan.world > 1:
-                self._maybe_migrate()
+                # a re-cut delivers strays too and stands in for this step's migration round; a declined one does not
+                if not (self.rebalance_every and self.steps % self.rebalance_every == 0 and self.rebalance()):
+                    self._maybe_migrate()
                 self._mark("migrate")
 
     def _maybe_migrate(self) -> None:

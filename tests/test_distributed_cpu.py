@@ -307,7 +307,7 @@ def make_lopsided_scene(res=32, n=1800, seed=5):
     return p, (x, v, F, C, mass, mu0, lam0, ids)
 
 
-def _rebalance_worker(rank, world, port, margin, lagged, out):
+def _rebalance_worker(rank, world, port, margin, lagged, out, migrate_every=1, pre_steps=2):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -317,14 +317,19 @@ def _rebalance_worker(rank, world, port, margin, lagged, out):
         mine = np.flatnonzero((base[:, 0] >= plan.own_lo) & (base[:, 0] < plan.own_hi))
         local = OracleSlab(plan, p, tuple(a[mine].copy() for a in state))
         local.lagged = lagged
-        drv = SlabDriver(plan, local, migrate_every=1)
-        drv.substep(2)
+        auto = pre_steps == 0                                     # the driver re-cuts by itself every 2 substeps
+        drv = SlabDriver(plan, local, migrate_every=migrate_every, rebalance_every=2 if auto else 0)
         _, before = drv.imbalance(0.0)
-        assert drv.rebalance(layer_cost_per_cell=0.0)
+        drv.substep(pre_steps if not auto else 2)
+        if auto:
+            assert drv.rebalanced == 1
+            pre_steps = 2
+        else:
+            assert drv.rebalance(layer_cost_per_cell=0.0)
         _, after = drv.imbalance(0.0)
         assert not drv.rebalance(layer_cost_per_cell=0.0)         # a second call has nothing to gain
         counts_after = local.num_particles
-        drv.substep(3)
+        drv.substep(5 - pre_steps)
         gathered = [None] * world
         dist.all_gather_object(gathered, (local.ids, local.x, local.v, local.F, local.C, counts_after,
                                           (drv.plan.own_lo, drv.plan.own_hi)))
@@ -339,10 +344,15 @@ def _rebalance_worker(rank, world, port, margin, lagged, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,margin,lagged", [(3, 2, False), (2, 3, True), (4, 1, False)])
-def test_rebalanced_slabs_match_single_domain(tmp_path, world, margin, lagged):
+@pytest.mark.parametrize("world,margin,lagged,migrate_every,pre_steps",
+                         [(3, 2, False, 1, 2), (2, 3, True, 1, 2), (4, 1, False, 1, 2),
+                          (2, 3, False, 3, 2),      # re-cut between migrations: particles that strayed into the margin go along
+                          (3, 2, False, 2, 3),
+                          (3, 2, True, 1, 0)])      # SlabDriver(rebalance_every=2)
+def test_rebalanced_slabs_match_single_domain(tmp_path, world, margin, lagged, migrate_every, pre_steps):
     out = str(tmp_path / "res.pt")
-    mp.spawn(_rebalance_worker, args=(world, _free_port(), margin, lagged, out), nprocs=world, join=True)
+    mp.spawn(_rebalance_worker, args=(world, _free_port(), margin, lagged, out, migrate_every, pre_steps), nprocs=world,
+             join=True)
     got = torch.load(out, weights_only=False)
     p, (x, v, F, C, mass, mu0, lam0, ids) = make_lopsided_scene()
     Jp = np.ones((len(x), 1))
