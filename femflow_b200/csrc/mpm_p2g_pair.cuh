@@ -50,7 +50,10 @@ struct Mat3x2 {
   F2 a00, a01, a02, a10, a11, a12, a20, a21, a22;
 };
 
-FFMPM_HD bool fixed_corotated_affine3_f32x2(const Mat3x2& F, const Mat3x2& C, F2 mu, F2 lam, F2 mass, float dt_vol_dinv,
+// `load_C()` fetches the two APIC matrices only when the series is done: they are needed for the last nine
+// FFMA2s, and holding 18 more registers through the series is what makes the packed phase 1 spill.
+template <typename LoadC>
+FFMPM_HD bool fixed_corotated_affine3_f32x2(const Mat3x2& F, LoadC load_C, F2 mu, F2 lam, F2 mass, float dt_vol_dinv,
                                             Mat3x2& A) {
   const F2 neg1 = f2(-1.0f), two = f2(2.0f);
   Mat3x2 E = F;
@@ -116,6 +119,10 @@ FFMPM_HD bool fixed_corotated_affine3_f32x2(const Mat3x2& F, const Mat3x2& C, F2
   const F2 l = f2_mul(f2_mul(lam, jm1), f2_add(jm1, f2(1.0f)));       // lam (J-1) J, broadcast onto ALL entries (quirk 2)
   const F2 nk = f2(-dt_vol_dinv);
   const F2 k2 = f2_mul(f2_mul(nk, two), mu), kl = f2_mul(nk, l);
+#ifdef __CUDA_ARCH__
+  asm volatile("" ::: "memory");   // keep the loads of C below the series (scheduling barrier only)
+#endif
+  const Mat3x2 C = load_C();
   A.a00 = f2_fma(mass, C.a00, f2_fma(k2, x00, kl)); A.a01 = f2_fma(mass, C.a01, f2_fma(k2, x01, kl));
   A.a02 = f2_fma(mass, C.a02, f2_fma(k2, x02, kl)); A.a10 = f2_fma(mass, C.a10, f2_fma(k2, x01, kl));
   A.a11 = f2_fma(mass, C.a11, f2_fma(k2, x11, kl)); A.a12 = f2_fma(mass, C.a12, f2_fma(k2, x12, kl));
@@ -159,15 +166,19 @@ FFMPM_HD void p2g_prepare3_pair(const DevCfg& cfg, GetA ga, GetB gb, bool has_ma
     index_part(gb, qb, mass_b, mu_b, lam_b);
     packed = qa.ok && qb.ok;
     if (packed) {
-      Mat3x2 F, C, A;
+      Mat3x2 F, A;
       F.a00 = f2(ga(P2G_F + 0), gb(P2G_F + 0)); F.a01 = f2(ga(P2G_F + 1), gb(P2G_F + 1)); F.a02 = f2(ga(P2G_F + 2), gb(P2G_F + 2));
       F.a10 = f2(ga(P2G_F + 3), gb(P2G_F + 3)); F.a11 = f2(ga(P2G_F + 4), gb(P2G_F + 4)); F.a12 = f2(ga(P2G_F + 5), gb(P2G_F + 5));
       F.a20 = f2(ga(P2G_F + 6), gb(P2G_F + 6)); F.a21 = f2(ga(P2G_F + 7), gb(P2G_F + 7)); F.a22 = f2(ga(P2G_F + 8), gb(P2G_F + 8));
-      C.a00 = f2(ga(P2G_C + 0), gb(P2G_C + 0)); C.a01 = f2(ga(P2G_C + 1), gb(P2G_C + 1)); C.a02 = f2(ga(P2G_C + 2), gb(P2G_C + 2));
-      C.a10 = f2(ga(P2G_C + 3), gb(P2G_C + 3)); C.a11 = f2(ga(P2G_C + 4), gb(P2G_C + 4)); C.a12 = f2(ga(P2G_C + 5), gb(P2G_C + 5));
-      C.a20 = f2(ga(P2G_C + 6), gb(P2G_C + 6)); C.a21 = f2(ga(P2G_C + 7), gb(P2G_C + 7)); C.a22 = f2(ga(P2G_C + 8), gb(P2G_C + 8));
+      auto load_C = [&]() {
+        Mat3x2 C;
+        C.a00 = f2(ga(P2G_C + 0), gb(P2G_C + 0)); C.a01 = f2(ga(P2G_C + 1), gb(P2G_C + 1)); C.a02 = f2(ga(P2G_C + 2), gb(P2G_C + 2));
+        C.a10 = f2(ga(P2G_C + 3), gb(P2G_C + 3)); C.a11 = f2(ga(P2G_C + 4), gb(P2G_C + 4)); C.a12 = f2(ga(P2G_C + 5), gb(P2G_C + 5));
+        C.a20 = f2(ga(P2G_C + 6), gb(P2G_C + 6)); C.a21 = f2(ga(P2G_C + 7), gb(P2G_C + 7)); C.a22 = f2(ga(P2G_C + 8), gb(P2G_C + 8));
+        return C;
+      };
       const double k = (cfg.dt * cfg.volume) * (4.0 * cfg.inv_dx * cfg.inv_dx);
-      packed = fixed_corotated_affine3_f32x2(F, C, f2(mu_a, mu_b), f2(lam_a, lam_b), f2(mass_a, mass_b),
+      packed = fixed_corotated_affine3_f32x2(F, load_C, f2(mu_a, mu_b), f2(lam_a, lam_b), f2(mass_a, mass_b),
                                              (float)k, A);
       if (packed) {
         qa.a00 = A.a00.v.x; qa.a01 = A.a01.v.x; qa.a02 = A.a02.v.x; qa.a10 = A.a10.v.x; qa.a11 = A.a11.v.x; qa.a12 = A.a12.v.x;
