@@ -214,7 +214,6 @@ class SymmHalo:
         self.handle = fabric.rendezvous(self.inbox, group)
         self.peer = {nb: self.handle.get_buffer(nb, shape, dtype, 0) for nb in (self.left, self.right) if nb is not None}
         self.handle.barrier(0, self.timeout_ms)               # every inbox is zeroed and mapped before the first put
-        self.bytes_per_step = 0
 
     def exchange(self, step: int, send_lo: Optional[torch.Tensor], send_hi: Optional[torch.Tensor]):
         """``send_lo`` / ``send_hi``: this rank's first / last shared planes (None at a domain end).
