@@ -67,7 +67,7 @@ struct FfMpmHandle {
   int64_t launches;
   bool prebinned;     // keys/rank/histogram of the live buffer were emitted by the last reordering G2P
   int p2g_variant;    // see p2g_t (FFMPM_P2G_VARIANT)
-  int g2p_packed;     // FFMPM_G2P_PACKED=1: stencil sums in packed fp32 (g2p_accumulate3_packed; not yet measured)
+  int g2p_packed;     // FFMPM_G2P_PACKED=1/2: stencil sums in packed fp32 (g2p_accumulate3_packed; not yet measured)
   int p2g_blocks_per_sm, g2p_blocks_per_sm;   // persistent-grid sizing (tunable: FFMPM_P2G_BPS / FFMPM_G2P_BPS)
   bool grid_in_blocks; // the current grid was zero before a P2G of exactly the binned particles: everything
                        // non-zero lies inside the node blocks listed by the binning (bin.node_tiles)
@@ -183,7 +183,7 @@ int ffmpm_create(const FfMpmConfig* cfg, int32_t device, FfMpmHandle** out) {
   h->g2p_blocks_per_sm = 8;
   h->p2g_variant = 5;   // physical-order P2G with cp.async-prefetched state when eligible (profiles/r01j)
   if (const char* e = getenv("FFMPM_P2G_VARIANT")) h->p2g_variant = atoi(e);
-  if (const char* e = getenv("FFMPM_G2P_PACKED")) h->g2p_packed = atoi(e) != 0;
+  if (const char* e = getenv("FFMPM_G2P_PACKED")) h->g2p_packed = atoi(e);   // 1: packed sums, 2: at 6 CTAs/SM
   if (const char* e = getenv("FFMPM_P2G_BPS")) { int v = atoi(e); if (v > 0 && v <= 32) h->p2g_blocks_per_sm = v; }
   if (const char* e = getenv("FFMPM_G2P_BPS")) { int v = atoi(e); if (v > 0 && v <= 32) h->g2p_blocks_per_sm = v; }
   *out = h;
@@ -475,7 +475,7 @@ static int g2p_t(FfMpmHandle* h, cudaStream_t s) {
     // (the kernel pre-bins the advected particles for the next substep into the histogram that
     // bin_particles left cleared)
     int nl = g2p_tiled<T>(h->dev, sv, dst, h->n, h->bin, (const T*)h->grid, h->err, h->sm_count, h->g2p_blocks_per_sm, s,
-                          h->g2p_packed != 0);
+                          h->g2p_packed);
     h->live ^= 1;
     h->binned = false;  // positions moved: perm / cell offsets are stale ...
     h->prebinned = true;  // ... but keys, ranks and the histogram of the new live buffer are ready

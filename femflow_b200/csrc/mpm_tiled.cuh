@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_tiled3_kernel(Dev
 
 template <typename T>
 int g2p_tiled(const DevCfg& cfg, const StateView<T>& src, const StateView<T>& dst, long long n, BinBuffers& B,
-              const T* grid, ErrRec* err, int sm_count, int blocks_per_sm, cudaStream_t st, bool packed = false) {
+              const T* grid, ErrRec* err, int sm_count, int blocks_per_sm, cudaStream_t st, int packed = 0) {
   (void)n;
   cudaMemsetAsync(&B.counters[2], 0, sizeof(int32_t), st);
   int blocks = min(B.n_tiles + 1, sm_count * blocks_per_sm);
@@ -255,7 +255,12 @@ int g2p_tiled(const DevCfg& cfg, const StateView<T>& src, const StateView<T>& ds
     // FFMPM_G2P_PRE=0 disables the cp.async input prefetch (64 registers, 8 CTAs per SM either way)
     static int prefetch = [] { const char* e = getenv("FFMPM_G2P_PRE"); return e ? atoi(e) : 1; }();
     const bool rows = src.material != nullptr;
-    if (packed && prefetch && rows)
+    // packed == 2: the packed sums at 6 CTAs per SM (85 registers: no spills) instead of 8 (64 registers)
+    if (packed == 2 && prefetch && rows)
+      g2p_tiled3_kernel<T, 6, true, true, true><<<min(blocks, sm_count * 6), G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
+    else if (packed == 2 && prefetch)
+      g2p_tiled3_kernel<T, 6, true, false, true><<<min(blocks, sm_count * 6), G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
+    else if (packed && prefetch && rows)
       g2p_tiled3_kernel<T, 8, true, true, true><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
     else if (packed && prefetch)
       g2p_tiled3_kernel<T, 8, true, false, true><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);

@@ -19,9 +19,11 @@ if [ "$N" = "1" ]; then
   timeout 120 python bench.py --steps 100 --warmup 6 --no-cpu-baseline --e2e-steps 1 --graph > $out/bench_graph.json 2> $out/bench_graph.err
   FFMPM_G2P_PACKED=1 timeout 120 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --e2e-steps 1 \
       > $out/bench_vg2p.json 2> $out/bench_vg2p.err
+  FFMPM_G2P_PACKED=2 timeout 120 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --e2e-steps 1 \
+      > $out/bench_vg2p6.json 2> $out/bench_vg2p6.err
   python - <<PY
 import json
-for v in (5, 7, 8, 9, "g2p"):
+for v in (5, 7, 8, 9, "g2p", "g2p6"):
     try:
         d = json.load(open("$out/bench_v%s.json" % v))
         print("variant", v, d["ms_per_step"], d["roofline"]["phase_ms"])
