@@ -72,3 +72,40 @@ def test_mpm_simulation_matches_reference_trajectory(tmp_path):
     # reset == load (simulation.py:119-120)
     sim.reset(meshes=meshes, params=[(1.0, 140, 0.2), (10.0, 1000, 0.4)])
     assert len(sim.displacements) == 1
+
+
+def test_headless_paper_scenes_reproduce_the_reference_setup():
+    """femflow_b200.simulation.mpm.headless.multi_drop_scene == paper_1.multi_drop_experiment (paper_1.py:17-144):
+    the scene of experiment 0 point for point (golden: every 8th vertex of the reference's meshes) and the
+    constructor arguments the reference passes."""
+    from femflow_b200.simulation.mpm.headless import PointMesh, multi_drop_scene
+    g = load_golden("c1_scene")
+    meshes, params, ctor = multi_drop_scene(0)
+    gy, co = (m.vertices.reshape(-1, 3) for m in meshes)
+    assert gy.dtype == np.float32 and len(gy) == 8321 and len(co) == 27000
+    assert np.array_equal(gy[::8], g["gyroid_vertices"]) and np.array_equal(co[::8], g["collider_vertices"])
+    assert params == [(1.0, 140, 0.2), (10.0, 1000, 0.4)]
+    assert (ctor["steps"], ctor["dt"], ctor["grid_res"], ctor["tightening_coeff"]) == (3500, float(g["dt"]), int(g["res"]),
+                                                                                      float(g["tightening_coeff"]))
+    assert (ctor["volume"], ctor["force"], ctor["hardening"]) == (float(g["volume"]), float(g["gravity"]), float(g["hardening"]))
+    meshes1, _, ctor1 = multi_drop_scene(1)
+    assert ctor1["steps"] == 1000 and ctor1["tightening_coeff"] == 0.10 and len(meshes1[1].vertices) == 3 * 40 ** 3
+    with pytest.raises(ValueError):
+        multi_drop_scene(2)
+    m = PointMesh(np.arange(6.0).reshape(2, 3))
+    m.translate_y(0.5); m.translate_x(-1); m.translate_z(2)
+    assert np.array_equal(m.vertices, np.float32([-1, 1.5, 4, 2, 4.5, 7]))
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("FFMPM_TEST_EXPERIMENTAL") != "1",
+                    reason="composed of tested parts but not yet run on hardware as a whole (GPU budget); FFMPM_TEST_EXPERIMENTAL=1")
+def test_headless_runner_runs_experiment_0(tmp_path):
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from femflow_b200.simulation.mpm.headless import run
+    sim, seconds = run(0, steps=6, outdir=str(tmp_path / "out"))
+    assert sim.error is None and not sim.running and len(sim.displacements) == 7
+    assert sim.displacements[-1].shape == (3 * 35321,) and np.isfinite(sim.displacements[-1]).all()
+    assert sorted(os.listdir(sim.outdir), key=lambda f: int(f.split(".")[0])) == [f"{i}.npy" for i in range(7)]
