@@ -389,6 +389,8 @@ static int p2g_t(FfMpmHandle* h, cudaStream_t s) {
         if (h->p2g_variant == 3) ok = p2g_bulk_launch<3, 1, 0>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
         else if (h->p2g_variant == 7)   // packed-fp32 phase 2 (two particles per FFMA2), 12 warps/SM for the 72 accumulator registers
           ok = p2g_bulk_launch<4, 1, 1, P2G_NPLANES, 12, 1>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
+        else if (h->p2g_variant == 10)  // variant 7 squeezed into 128 registers: 16 warps/SM
+          ok = p2g_bulk_launch<4, 1, 1, P2G_NPLANES, 16, 1>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
         else if (h->p2g_variant == 8)   // ... and the stress of a lane's two particles in packed fp32 as well
           ok = p2g_bulk_launch<4, 1, 1, P2G_NPLANES, 12, 2>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
         else if (h->p2g_variant == 9)   // same at 8 warps/SM: 255 registers, no spills (variant 8 spills 364 B at 168)
