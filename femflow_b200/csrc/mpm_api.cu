@@ -67,6 +67,7 @@ struct FfMpmHandle {
   int64_t launches;
   bool prebinned;     // keys/rank/histogram of the live buffer were emitted by the last reordering G2P
   int p2g_variant;    // see p2g_t (FFMPM_P2G_VARIANT)
+  int p2g_run_cap;    // FFMPM_P2G_RUN_CAP (packed P2G variants only): cut runs every 2^k slots (dense cells)
   int g2p_packed;     // FFMPM_G2P_PACKED=1/2: stencil sums in packed fp32 (g2p_accumulate3_packed; not yet measured)
   int p2g_blocks_per_sm, g2p_blocks_per_sm;   // persistent-grid sizing (tunable: FFMPM_P2G_BPS / FFMPM_G2P_BPS)
   bool grid_in_blocks; // the current grid was zero before a P2G of exactly the binned particles: everything
@@ -183,6 +184,10 @@ int ffmpm_create(const FfMpmConfig* cfg, int32_t device, FfMpmHandle** out) {
   h->g2p_blocks_per_sm = 8;
   h->p2g_variant = 5;   // physical-order P2G with cp.async-prefetched state when eligible (profiles/r01j)
   if (const char* e = getenv("FFMPM_P2G_VARIANT")) h->p2g_variant = atoi(e);
+  if (const char* e = getenv("FFMPM_P2G_RUN_CAP")) {
+    const int v = atoi(e);
+    if (v == 2 || v == 4 || v == 8 || v == 16 || v == 32) h->p2g_run_cap = v;
+  }
   if (const char* e = getenv("FFMPM_G2P_PACKED")) h->g2p_packed = atoi(e);   // 1: packed sums, 2: at 6 CTAs/SM
   if (const char* e = getenv("FFMPM_P2G_BPS")) { int v = atoi(e); if (v > 0 && v <= 32) h->p2g_blocks_per_sm = v; }
   if (const char* e = getenv("FFMPM_G2P_BPS")) { int v = atoi(e); if (v > 0 && v <= 32) h->g2p_blocks_per_sm = v; }
@@ -388,13 +393,13 @@ static int p2g_t(FfMpmHandle* h, cudaStream_t s) {
         const int bps = h->p2g_blocks_per_sm;
         if (h->p2g_variant == 3) ok = p2g_bulk_launch<3, 1, 0>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
         else if (h->p2g_variant == 7)   // packed-fp32 phase 2 (two particles per FFMA2), 12 warps/SM for the 72 accumulator registers
-          ok = p2g_bulk_launch<4, 1, 1, P2G_NPLANES, 12, 1>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
+          ok = p2g_bulk_launch<4, 1, 1, P2G_NPLANES, 12, 1>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s, h->p2g_run_cap);
         else if (h->p2g_variant == 10)  // variant 7 squeezed into 128 registers: 16 warps/SM
-          ok = p2g_bulk_launch<4, 1, 1, P2G_NPLANES, 16, 1>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
+          ok = p2g_bulk_launch<4, 1, 1, P2G_NPLANES, 16, 1>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s, h->p2g_run_cap);
         else if (h->p2g_variant == 8)   // ... and the stress of a lane's two particles in packed fp32 as well
-          ok = p2g_bulk_launch<4, 1, 1, P2G_NPLANES, 12, 2>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
+          ok = p2g_bulk_launch<4, 1, 1, P2G_NPLANES, 12, 2>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s, h->p2g_run_cap);
         else if (h->p2g_variant == 9)   // same at 8 warps/SM: 255 registers, no spills (variant 8 spills 364 B at 168)
-          ok = p2g_bulk_launch<4, 1, 1, P2G_NPLANES, 8, 2>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
+          ok = p2g_bulk_launch<4, 1, 1, P2G_NPLANES, 8, 2>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s, h->p2g_run_cap);
         else if (h->p2g_variant == 6 && mat_mode_of(sv) != MAT_PLANES)   // occupancy experiment: 20 warps/SM
           ok = p2g_bulk_launch<4, 1, 1, P2G_MASS, 20>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
         else ok = p2g_bulk_launch<4, 1, 1>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);

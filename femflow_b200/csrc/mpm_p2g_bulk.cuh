@@ -106,6 +106,8 @@ p2g_bulk3_kernel(DevCfg cfg, P2GPlanes planes, long long n, float* __restrict__ 
   const int ny = cfg.n[1], nz = cfg.n[2];
   const int n_planes = planes.n;
   const bool has_mat = n_planes == P2G_NPLANES || planes.table != nullptr;
+  int run_cap = 0;
+  if constexpr (PAIR > 0) { run_cap = wpw >> 16; wpw &= 0xffff; }   // experimental kernels: run cap rides in the high half
   const int n_windows = (int)((n + P2G_WINDOW - 1) / P2G_WINDOW);
   // wpw > 0: every warp owns `wpw` consecutive windows and the CTA retires after them (a finite
   // grid lets the block scheduler interleave CTAs of kernels running on other streams);
@@ -209,7 +211,7 @@ p2g_bulk3_kernel(DevCfg cfg, P2GPlanes planes, long long n, float* __restrict__ 
     __syncwarp();
     // single buffer: the raw slab is free again -> prefetch the next window behind phase 2
     if (NBUF == 1 && win + total_warps < last_excl) issue(win + total_warps, 0);
-    if constexpr (PAIR > 0) p2g_runs_phase2_pair(S, node, cnt, lane, ny, nz, grid);
+    if constexpr (PAIR > 0) p2g_runs_phase2_pair(S, node, cnt, lane, ny, nz, grid, run_cap);
     else p2g_runs_phase2<T>(S, node, cnt, lane, ny, nz, grid);
     __syncwarp();   // the payload slab is rewritten by the next window
   }
@@ -217,7 +219,7 @@ p2g_bulk3_kernel(DevCfg cfg, P2GPlanes planes, long long n, float* __restrict__ 
 
 template <int WARPS, int NBUF, int LDGSTS, int RAWP = P2G_NPLANES, int SMW = 16, int PAIR = 0>
 static bool p2g_bulk_launch(const DevCfg& cfg, const StateView<float>& s, long long n, float* grid, ErrRec* err,
-                            int sm_count, int blocks_per_sm, cudaStream_t st) {
+                            int sm_count, int blocks_per_sm, cudaStream_t st, int run_cap = 0) {
   const size_t smem = sizeof(P2GBulkWarp<NBUF, RAWP, PAIR>) * WARPS;
   // function attributes are per device: a process that drives several GPUs configures each once
   static bool configured[64] = {};
@@ -239,7 +241,8 @@ static bool p2g_bulk_launch(const DevCfg& cfg, const StateView<float>& s, long l
     blocks = (int)(want < cap ? want : cap);
   }
   if (blocks < 1) blocks = 1;
-  p2g_bulk3_kernel<WARPS, NBUF, LDGSTS, RAWP, SMW, PAIR><<<blocks, WARPS * 32, smem, st>>>(cfg, p2g_planes_of(s), n, grid, err, wpw);
+  const int wpw_arg = PAIR > 0 ? ((wpw & 0xffff) | (run_cap << 16)) : wpw;
+  p2g_bulk3_kernel<WARPS, NBUF, LDGSTS, RAWP, SMW, PAIR><<<blocks, WARPS * 32, smem, st>>>(cfg, p2g_planes_of(s), n, grid, err, wpw_arg);
   return true;
 }
 

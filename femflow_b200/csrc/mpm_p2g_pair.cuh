@@ -300,14 +300,18 @@ FFMPM_HD void p2g_pair_accumulate(const float4 (*pay)[P2G_PAIR_PADDED], int r0, 
 }
 
 // Runs + phase 2 over a window parked in the pair-major layout (twin of p2g_runs_phase2).
+// `run_cap` (0 or a power of two): additionally cut a run at every run_cap-th slot of the window.  Where many
+// particles share a cell (a column settling on the floor) a window holds one or two runs and most lanes
+// of phase 2 idle; capped runs keep >= 64 / run_cap * 3 (run, slab) items per window at the price of one
+// more set of REDs per cut.
 __device__ __forceinline__ void p2g_runs_phase2_pair(P2GPairSlab& S, const int (&node)[2], int cnt, int lane, int ny, int nz,
-                                                     float* __restrict__ grid) {
+                                                     float* __restrict__ grid, int run_cap) {
   unsigned heads[2];
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int idx = h * 32 + lane;
     const int prev = idx > 0 ? S.node0[idx - 1] : -2;
-    heads[h] = __ballot_sync(0xffffffffu, idx < cnt && node[h] != prev);
+    heads[h] = __ballot_sync(0xffffffffu, idx < cnt && (node[h] != prev || (run_cap > 0 && (idx & (run_cap - 1)) == 0)));
   }
   const int n0 = __popc(heads[0]);
   const int n_runs = n0 + __popc(heads[1]);

@@ -30,6 +30,13 @@ for v in (5, 7, 10, 8, 9, "g2p", "g2p6"):
     except Exception as e:
         print("variant", v, "failed:", e)
 PY
+  # dense cells (column settling): long runs leave phase-2 lanes idle; run cap on the packed kernel
+  for cfgs in "5:0" "7:0" "7:8" "7:16"; do
+    v=${cfgs%%:*}; cap=${cfgs##*:}
+    FFMPM_P2G_VARIANT=$v FFMPM_P2G_RUN_CAP=$cap timeout 200 python bench.py --workload dam:8388608 --steps 50 --warmup 5 \
+        --presteps 2000 --no-cpu-baseline > $out/dam8m_v${v}_cap${cap}.json 2> $out/dam8m_v${v}_cap${cap}.err
+    python -c "import json;d=json.load(open('$out/dam8m_v${v}_cap${cap}.json'));print('dam8m variant $v cap $cap', d['ms_per_step'])" || true
+  done
   exit 0
 fi
 if [ "$N" = "2" ]; then
