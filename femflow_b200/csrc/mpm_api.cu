@@ -731,3 +731,17 @@ int ffmpm_snapshot(FfMpmHandle* h, double coeff, double* out, void* stream) {
 
 int64_t ffmpm_launch_count(const FfMpmHandle* h) { return h ? h->launches : 0; }
 
+__global__ void debug_red_add4_kernel(float* __restrict__ dst, float a, float b, float c, float d, long long count) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) red_add4(dst + 4 * i, a, b, c, d);
+}
+
+int ffmpm_debug_red_add4(float* dst, const float* v, int64_t count, void* stream) {
+  if (!dst || !v || count < 0 || ((uintptr_t)dst & 15) != 0) return set_err(FFMPM_E_INVALID, "bad red probe arguments");
+  if (count == 0) return FFMPM_OK;
+  debug_red_add4_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dst, v[0], v[1], v[2], v[3], count);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_err(FFMPM_E_CUDA, "kernel launch: %s", cudaGetErrorString(e));
+  return FFMPM_OK;
+}
+

@@ -201,6 +201,12 @@ int ffmpm_snapshot(FfMpmHandle* h, double coeff, double* out, void* stream);
 /* Number of kernel launches issued by this handle so far. */
 int64_t ffmpm_launch_count(const FfMpmHandle* h);
 
+/* Diagnostic (no reference counterpart): dst[4*i .. 4*i+3] += value[0..3] for i < count with the one
+ * 16-byte vector reduction P2G issues per node (red.global.add.v4.f32).  `dst` may be PEER memory mapped
+ * over NVLink: scripts/peer_red_probe.py uses it to find out whether P2G could scatter its halo planes
+ * straight into a neighbour GPU's inbox.  fp32 only; asynchronous on `stream`. */
+int ffmpm_debug_red_add4(float* dst, const float* value4_host, int64_t count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
