@@ -112,11 +112,11 @@ inline void bin_carve(BinBuffers& B, char* base, int dim, const int* n, int64_t 
 }
 
 // Tile-major key of a LOCAL base cell.
-__device__ __forceinline__ int bin_key3(int bx, int by, int bz, int ty, int tz) {
+FFMPM_HD int bin_key3(int bx, int by, int bz, int ty, int tz) {
   int tile = ((bx >> 2) * ty + (by >> 2)) * tz + (bz >> 2);
   return tile * TILE_CELLS + ((bx & 3) << 4) + ((by & 3) << 2) + (bz & 3);
 }
-__device__ __forceinline__ int bin_key2(int bx, int by, int ty) {
+FFMPM_HD int bin_key2(int bx, int by, int ty) {
   int tile = (bx >> 3) * ty + (by >> 3);
   return tile * TILE_CELLS + ((bx & 7) << 3) + (by & 7);
 }
@@ -124,7 +124,7 @@ __device__ __forceinline__ int bin_key2(int bx, int by, int ty) {
 // Bin key of a particle position: tile-major id of its LOCAL base cell, or n_cells
 // when the stencil would leave the grid (utils.py:138-150) / the position is NaN.
 template <typename T>
-__device__ __forceinline__ int bin_key_of(const DevCfg& cfg, const BinBuffers& B, T x0, T x1, T x2, int* base_x = nullptr) {
+FFMPM_HD int bin_key_of(const DevCfg& cfg, const BinBuffers& B, T x0, T x1, T x2, int* base_x = nullptr) {
   const T xs[3] = {x0, x1, x2};
   int b[3] = {0, 0, 0};
   bool ok = true;

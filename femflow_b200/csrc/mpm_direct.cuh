@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(128) p2g_scatter2_kernel(DevCfg cfg, StateView
 // 3D (three_d/grid_op.py:25-47): v = mom/mass, v.y += dt*g, clamp to +-0.9 dx/dt,
 // then zero component d on nodes with global index I[d] < 1 or I[d] >= R-1 (quirk 5).
 template <typename T>
-__device__ __forceinline__ void grid_op3_node(const DevCfg& cfg, T* __restrict__ grid, long long n_nodes, long long node,
+FFMPM_HD void grid_op3_node(const DevCfg& cfg, T* __restrict__ grid, long long n_nodes, long long node,
                                               int i, int j, int k, const T* __restrict__ halo_lo, long long nodes_lo,
                                               const T* __restrict__ halo_hi, long long nodes_hi, const Colliders& col) {
   using V4 = typename Vec4<T>::type;

@@ -65,6 +65,32 @@ void accumulate3(long long n, const T* f, const T* gv, T* v, T* c) {
 
 }  // namespace
 
+// Grid update of every node (three_d/grid_op.py:5-67 through the kernels' grid_op3_node): a slab of `n0`
+// node planes at global x origin `origin0` of a (res0, res1, res2) grid, halo partial sums of the first
+// `planes_lo` / last `planes_hi` planes added while loading, `n_col` plane colliders (normals as
+// ffmpm_set_colliders stores them).  In place on grid[n0*n1*n2][4].
+template <typename T>
+static void grid_op3_host(const int* res, const int* n, int origin0, double dx, double dt, double gravity, T* grid, const T* halo_lo,
+                          int planes_lo, const T* halo_hi, int planes_hi, int n_col, const double* col_point, const double* col_normal) {
+  DevCfg c{};
+  c.dim = 3;
+  for (int d = 0; d < 3; ++d) { c.res[d] = res[d]; c.n[d] = n[d]; c.origin[d] = 0; }
+  c.origin[0] = origin0;
+  c.dx = dx; c.inv_dx = 1.0 / dx; c.dt = dt; c.gravity = gravity;
+  Colliders col{};
+  col.count = n_col;
+  for (int k = 0; k < n_col; ++k)
+    for (int d = 0; d < 3; ++d) { col.point[k][d] = col_point[3 * k + d]; col.normal[k][d] = col_normal[3 * k + d]; }
+  const long long plane = (long long)n[1] * n[2], nodes = plane * n[0];
+  for (long long node = 0; node < nodes; ++node) {
+    const int k = (int)(node % n[2]);
+    const long long r = node / n[2];
+    grid_op3_node<T>(c, grid, nodes, node, (int)(r / n[1]), (int)(r % n[1]), k, halo_lo, planes_lo * plane, halo_hi,
+                     planes_hi * plane, col);
+  }
+}
+
+
 extern "C" {
 
 void km_prepare3_f32(int res, int n_nodes, double inv_dx, double dx, double dt, double volume, double hardening, int model,
@@ -214,6 +240,31 @@ int km_pair_accumulate(int n_slots, const float* payload, int r0, int r1, int li
 // (LDS.128: 4 consecutive banks from there); the test asserts that aligned runs do not collide.
 void km_pair_banks(int n_lanes, const int* start, int* bank) {
   for (int l = 0; l < n_lanes; ++l) bank[l] = (p2g_pair_pad(start[l]) * 4) % 32;
+}
+
+void km_grid_op3_f32(const int* res, const int* n, int origin0, double dx, double dt, double gravity, float* grid, const float* halo_lo,
+                     int planes_lo, const float* halo_hi, int planes_hi, int n_col, const double* cp, const double* cn) {
+  grid_op3_host<float>(res, n, origin0, dx, dt, gravity, grid, halo_lo, planes_lo, halo_hi, planes_hi, n_col, cp, cn);
+}
+void km_grid_op3_f64(const int* res, const int* n, int origin0, double dx, double dt, double gravity, double* grid, const double* halo_lo,
+                     int planes_lo, const double* halo_hi, int planes_hi, int n_col, const double* cp, const double* cn) {
+  grid_op3_host<double>(res, n, origin0, dx, dt, gravity, grid, halo_lo, planes_lo, halo_hi, planes_hi, n_col, cp, cn);
+}
+
+// Tile-major bin keys (mpm_bin.cuh: bin_key_of) of fp32 positions on an n-node grid at x origin `origin0`;
+// also the global base cell along x that the slab migration logic reads.
+int km_bin_keys_f32(int dim, const int* n, int origin0, double inv_dx, int index_fp32, long long count, const float* x, int* keys,
+                    int* base_x) {
+  DevCfg c{};
+  c.dim = dim;
+  for (int d = 0; d < 3; ++d) { c.n[d] = n[d]; c.origin[d] = 0; }
+  c.origin[0] = origin0;
+  c.inv_dx = inv_dx; c.index_fp32 = index_fp32;
+  BinBuffers B{};
+  bin_geometry(dim, n, B.tiles, B.n_tiles, B.n_cells);
+  for (long long p = 0; p < count; ++p)
+    keys[p] = bin_key_of<float>(c, B, x[3 * p], x[3 * p + 1], x[3 * p + 2], base_x + p);
+  return B.n_cells;
 }
 
 }  // extern "C"

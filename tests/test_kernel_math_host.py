@@ -335,3 +335,77 @@ def test_packed_fp32_stress_pairs(km, strain):
     else:
         assert np.abs(got[2][ok] - want).max() / scale < 1e-5
         assert np.abs(got[2][ok] - ref[2][ok]).max() / scale < 2e-6      # and next to the one-particle evaluation
+
+
+@pytest.mark.parametrize("dtype,tol", [("f32", 2e-6), ("f64", 1e-14)])
+def test_grid_update_walls_clamp_colliders_and_halo_sum(km, dtype, tol):
+    """grid_op3_node, the body of every 3D grid-update kernel (three_d/grid_op.py:25-67): momentum -> velocity,
+    gravity on y, the +-0.9 dx/dt clamp, per-axis sticky walls on GLOBAL faces only (quirk 5), plane colliders
+    with the reference's scalar-added normal -- on the whole grid, and on a two-slab cut whose shared planes are
+    summed while loading (ffmpm_grid_op_halo)."""
+    rng = np.random.default_rng(17)
+    res, G = 12, 13
+    np_dt = np.float32 if dtype == "f32" else np.float64
+    dx, dt, g = 1.0 / res, 2e-3, -9.8
+    mass = np.where(rng.random((G, G, G, 1)) < 0.6, rng.uniform(0.1, 2.0, (G, G, G, 1)), 0.0)
+    mom = rng.normal(0, 30.0, (G, G, G, 3)) * (mass > 0)            # large enough to hit the clamp (0.9 dx/dt = 37.5)
+    mass, mom = mass.astype(np_dt).astype(np.float64), mom.astype(np_dt).astype(np.float64)
+    pts = np.array([[0.5, 0.3, 0.5], [0.2, 0.5, 0.5]]); nrm = np.array([[0.0, 1.0, 0.0], [1.0, 0.2, 0.0]])
+    want_v, want_m = mom.copy(), mass.copy()
+    O.grid_op_3d(res, dx, dt, g, want_v, want_m)
+    O.check_collision_points(pts, nrm, res, dx, want_v)
+    stored_n = nrm + 1.0 / np.linalg.norm(nrm, axis=1, keepdims=True)        # ffmpm_set_colliders (grid_op.py:59-60)
+    ia = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+
+    def run(i0, i1, grid, halo_lo=None, planes_lo=0, halo_hi=None, planes_hi=0):
+        grid = np.array(grid, dtype=np_dt, order="C", copy=True)          # updated in place: never the caller's array
+        getattr(km, f"km_grid_op3_{dtype}")(ptr(ia([res] * 3)), ptr(ia([i1 - i0, G, G])), C.c_int(i0), C.c_double(dx),
+                                            C.c_double(dt), C.c_double(g), ptr(grid),
+                                            ptr(halo_lo) if halo_lo is not None else None, C.c_int(planes_lo),
+                                            ptr(halo_hi) if halo_hi is not None else None, C.c_int(planes_hi),
+                                            C.c_int(len(pts)), ptr(np.ascontiguousarray(pts)), ptr(np.ascontiguousarray(stored_n)))
+        return grid
+
+    whole = run(0, G, np.concatenate([mom, mass], -1))
+    scale = np.abs(want_v).max()
+    assert np.abs(whole[..., :3] - want_v).max() / scale < tol and np.array_equal(whole[..., 3:], mass.astype(np_dt))
+    assert (np.abs(want_v) == 0.9 * dx / dt).any()                     # the clamp was exercised
+    # two slabs sharing planes 5..8: each holds a random split of the shared planes' {momentum, mass}
+    full = np.concatenate([mom, mass], -1)
+    share = rng.uniform(0.2, 0.8, (4, G, G, 1)) * (rng.random((4, G, G, 1)) < 0.7)
+    lo_part = full[:9].copy(); lo_part[5:9] *= share
+    hi_part = full[5:].copy(); hi_part[0:4] *= (1 - share)
+    to = lambda a: np.ascontiguousarray(a, dtype=np_dt)
+    lo = run(0, 9, lo_part, halo_hi=to(hi_part[0:4]), planes_hi=4)
+    hi = run(5, G, hi_part, halo_lo=to(lo_part[5:9]), planes_lo=4)
+    assert np.abs(lo[..., :3] - want_v[:9]).max() / scale < max(tol, 5e-7 if dtype == "f32" else 0)
+    assert np.abs(hi[..., :3] - want_v[5:]).max() / scale < max(tol, 5e-7 if dtype == "f32" else 0)
+    assert np.array_equal(lo[5:9], hi[0:4])                            # shared planes: a + b == b + a, bit for bit
+
+
+@pytest.mark.parametrize("res", [16, 37, 64])
+def test_tile_major_bin_keys(km, res):
+    """bin_key_of: tile-major id of the base cell (4x4x4 cells per tile), n_cells for a stencil that leaves the
+    grid or a NaN position; on a slab the key is local to the slab while base_x stays global."""
+    rng = np.random.default_rng(res)
+    n = 20000
+    x = rng.uniform(-0.05, 1.05, size=(n, 3)).astype(np.float32)
+    x[0] = [np.nan, 0.5, 0.5]; x[1] = [0.0, 0.0, 0.0]; x[2] = [(res - 1.5) / res] * 3
+    with np.errstate(invalid="ignore"):                     # the NaN row: its base is never compared
+        base, _ = O.base_and_fx(x.astype(np.float64), float(res))
+    km.km_bin_keys_f32.restype = C.c_int
+    for origin, n0 in ((0, res + 1), (5, 9)):
+        nn = np.array([n0, res + 1, res + 1], np.int32)
+        keys = np.zeros(n, np.int32); bx = np.zeros(n, np.int32)
+        n_cells = km.km_bin_keys_f32(C.c_int(3), ptr(nn), C.c_int(origin), C.c_double(float(res)), C.c_int(int(res & (res - 1) == 0)),
+                                     C.c_longlong(n), ptr(x), ptr(keys), ptr(bx))
+        tiles = [(int(v) - 2 + 3) // 4 for v in nn]
+        assert n_cells == tiles[0] * tiles[1] * tiles[2] * 64
+        b = base - np.array([origin, 0, 0])
+        ok = ~np.isnan(x).any(1) & (b >= 0).all(1) & (b + 2 < nn).all(1)
+        t = ((b[:, 0] >> 2) * tiles[1] + (b[:, 1] >> 2)) * tiles[2] + (b[:, 2] >> 2)
+        want = np.where(ok, t * 64 + ((b[:, 0] & 3) << 4) + ((b[:, 1] & 3) << 2) + (b[:, 2] & 3), n_cells)
+        assert np.array_equal(keys, want.astype(np.int32))
+        fin = ~np.isnan(x[:, 0])
+        assert np.array_equal(bx[fin], base[fin, 0].astype(np.int32))
+        assert not ok[0] and (origin > 0 or (ok[1] and ok[2]))
