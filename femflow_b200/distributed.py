@@ -201,7 +201,14 @@ class SymmHalo:
     LO, HI = 0, 1
 
     def __init__(self, plan: SlabPlan, plane_shape: Sequence[int], dtype, device, group=None, fabric=None,
-                 timeout_ms: int = 20000):
+                 timeout_ms: int = 20000, sync: Optional[str] = None):
+        """``sync``: ``"signal"`` (default) = one flag per neighbour and substep; ``"barrier"`` = the fabric's
+        stream-ordered barrier over all ranks instead (coarser, but the primitive torch's own symmetric-memory
+        collectives rely on) -- selectable with FFMPM_SYMM_SYNC for bring-up on new hardware."""
+        import os
+        self.sync = sync or os.environ.get("FFMPM_SYMM_SYNC", "signal")
+        if self.sync not in ("signal", "barrier"):
+            raise ValueError(f"unknown SymmHalo sync {self.sync!r}")
         self.rank, self.world = plan.rank, plan.world
         self.left = plan.rank - 1 if plan.rank > 0 else None
         self.right = plan.rank + 1 if plan.rank < plan.world - 1 else None
@@ -219,15 +226,20 @@ class SymmHalo:
         """``send_lo`` / ``send_hi``: this rank's first / last shared planes (None at a domain end).
         Returns the planes received from the left / right neighbour (None at a domain end)."""
         q, h, t = step & 1, self.handle, self.timeout_ms
+        flags = self.sync == "signal"
         if self.right is not None:
             self.peer[self.right][q, self.LO].copy_(send_hi)
-            h.put_signal(self.right, 2 * q + self.LO, t)
+            if flags:
+                h.put_signal(self.right, 2 * q + self.LO, t)
         if self.left is not None:
             self.peer[self.left][q, self.HI].copy_(send_lo)
-            h.put_signal(self.left, 2 * q + self.HI, t)
-        if self.left is not None:
+            if flags:
+                h.put_signal(self.left, 2 * q + self.HI, t)
+        if not flags:
+            h.barrier(q, t)                      # every rank's puts of this substep have landed
+        if flags and self.left is not None:
             h.wait_signal(self.left, 2 * q + self.LO, t)
-        if self.right is not None:
+        if flags and self.right is not None:
             h.wait_signal(self.right, 2 * q + self.HI, t)
         return (self.inbox[q, self.LO] if self.left is not None else None,
                 self.inbox[q, self.HI] if self.right is not None else None)

@@ -43,6 +43,9 @@ if [ "$N" = "2" ]; then
   # SymmHalo on hardware: parity first (signals time out after 20 s instead of hanging), then p2p vs symm
   FFMPM_TEST_SYMM=1 timeout 180 python -m pytest tests/test_gpu_distributed.py -x -q -k "symm" > $out/pytest_symm.txt 2>&1
   tail -3 $out/pytest_symm.txt
+  # if the flag protocol misbehaves on this torch build, the coarser barrier protocol isolates the copy path
+  FFMPM_TEST_SYMM=1 FFMPM_SYMM_SYNC=barrier timeout 180 python -m pytest tests/test_gpu_distributed.py -x -q -k "symm" > $out/pytest_symm_barrier.txt 2>&1
+  tail -3 $out/pytest_symm_barrier.txt
   # vector REDs at peer memory over NVLink: the precondition for P2G scattering halo planes into the neighbour's inbox
   timeout 120 $TR --master-port 29541 scripts/peer_red_probe.py > $out/peer_red_probe.json 2> $out/peer_red_probe.err
   tail -c 600 $out/peer_red_probe.json

@@ -195,8 +195,8 @@ class SharedFabric:
         self.waits += 1
 
 
-def _worker(rank, world, port, steps, margin, migrate_every, out, lagged=False, shared=None):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+def _worker(rank, world, port, steps, margin, migrate_every, out, lagged=False, shared=None, symm_sync="signal"):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), FFMPM_SYMM_SYNC=symm_sync)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         p, state = make_scene()
@@ -210,7 +210,8 @@ def _worker(rank, world, port, steps, margin, migrate_every, out, lagged=False, 
         drv.substep(steps)
         if fabric is not None:
             n_nb = (rank > 0) + (rank < world - 1)
-            assert fabric.puts == fabric.waits == steps * n_nb      # one flag per neighbour per substep, all consumed
+            # one flag per neighbour per substep, all consumed (none at all under the barrier protocol)
+            assert fabric.puts == fabric.waits == (steps * n_nb if symm_sync == "signal" else 0)
         gathered = [None] * world
         dist.all_gather_object(gathered, (local.ids, local.x, local.v, local.F, local.C, drv.migrated))
         if rank == 0:
@@ -248,8 +249,8 @@ def test_slabs_match_single_domain(tmp_path, world, margin, migrate_every, lagge
         assert np.abs(got[k] - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), k
 
 
-@pytest.mark.parametrize("world,margin,migrate_every", [(2, 2, 2), (3, 1, 1)])
-def test_symm_halo_protocol_matches_single_domain(tmp_path, world, margin, migrate_every):
+@pytest.mark.parametrize("world,margin,migrate_every,sync", [(2, 2, 2, "signal"), (3, 1, 1, "signal"), (3, 2, 2, "barrier")])
+def test_symm_halo_protocol_matches_single_domain(tmp_path, world, margin, migrate_every, sync):
     """SlabDriver(halo="symm"): halo planes put into the neighbour's inbox + signal flags instead of
     matched send/recv (SymmHalo), over a shared-memory stand-in for torch's symmetric memory.  Same
     bar as the p2p transport: the single-domain oracle to 1e-12, after an odd number of substeps so
@@ -261,7 +262,7 @@ def test_symm_halo_protocol_matches_single_domain(tmp_path, world, margin, migra
     inboxes = [torch.zeros((2, 2, planes, G, G, 4), dtype=torch.float64).share_memory_() for _ in range(world)]
     pads = [torch.zeros(4 * world, dtype=torch.int32).share_memory_() for _ in range(world)]
     out = str(tmp_path / "res.pt")
-    mp.spawn(_worker, args=(world, _free_port(), steps, margin, migrate_every, out, False, (inboxes, pads)),
+    mp.spawn(_worker, args=(world, _free_port(), steps, margin, migrate_every, out, False, (inboxes, pads), sync),
              nprocs=world, join=True)
     assert all(int(pad.abs().sum()) == 0 for pad in pads)           # every raised flag was consumed
     got = torch.load(out, weights_only=False)
