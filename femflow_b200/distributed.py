@@ -79,36 +79,24 @@ class SlabPlan:
         if cells < world * min_cells:
             raise ValueError("slabs are thinner than 2*margin+2 cells: halos would reach past the neighbour")
         prefix = np.concatenate([[0.0], np.cumsum(cost)])      # prefix[c] = cost of layers [0, c)
-
-        def cut(bound):
-            """Greedy cut with every slab as thick as ``bound`` allows (a thicker slab never hurts the
-            ones after it); None when some slab cannot stay under ``bound``."""
-            cuts = [0]
-            for r in range(world - 1):
-                lo = cuts[-1]
-                c = int(np.searchsorted(prefix, prefix[lo] + bound, side="right")) - 1
-                c = min(c, cells - (world - 1 - r) * min_cells)        # room for the slabs still to come
-                if c < lo + min_cells:
-                    c = lo + min_cells
-                    if prefix[c] - prefix[lo] > bound:
-                        return None
-                cuts.append(c)
-            if prefix[cells] - prefix[cuts[-1]] > bound:
-                return None
-            return cuts + [cells]
-
-        # smallest feasible bottleneck by bisection (the cost of the heaviest slab is what a substep waits for)
-        lo_b, hi_b = prefix[-1] / world, prefix[-1]
-        best = cut(lo_b)
-        if best is None:
-            best = cut(hi_b)
-            for _ in range(64):
-                mid = 0.5 * (lo_b + hi_b)
-                got = cut(mid)
-                if got is None:
-                    lo_b = mid
-                else:
-                    hi_b, best = mid, got
+        # Dynamic programme over (slabs used, layers covered): heaviest[r][c] = the lightest possible heaviest
+        # slab when the first r+1 slabs cover layers [0, c).  (A greedy "fill each slab up to a bound" is NOT
+        # optimal here: with a minimum thickness a fuller slab can force a later one across two heavy layers.)
+        inf = np.inf
+        heaviest = np.full((world, cells + 1), inf)
+        prev_cut = np.zeros((world, cells + 1), dtype=np.int64)
+        heaviest[0, min_cells:] = prefix[min_cells:]
+        for r in range(1, world):
+            for c in range((r + 1) * min_cells, cells + 1):
+                starts = np.arange(r * min_cells, c - min_cells + 1)          # where slab r may begin
+                worst = np.maximum(heaviest[r - 1, starts], prefix[c] - prefix[starts])
+                k = int(np.argmin(worst))
+                heaviest[r, c], prev_cut[r, c] = worst[k], starts[k]
+        best = [cells]
+        for r in range(world - 1, 0, -1):
+            best.append(int(prev_cut[r, best[-1]]))
+        best.append(0)
+        best.reverse()
         return [(best[r], best[r + 1]) for r in range(world)]
 
     @classmethod

@@ -367,3 +367,28 @@ def test_rebalanced_slabs_match_single_domain(tmp_path, world, margin, lagged, m
     assert r[0][0] == 0 and r[-1][1] == p["res"] - 1 and all(a[1] == b[0] for a, b in zip(r[:-1], r[1:]))
     for k, ref in (("x", x), ("v", v), ("F", F), ("C", C)):
         assert np.abs(got[k] - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), k
+
+
+def test_balanced_ranges_is_optimal_on_small_cases():
+    """SlabPlan.balanced_ranges against brute force: over all cuts that respect the minimum slab thickness,
+    none has a lighter heaviest slab."""
+    import itertools
+    rng = np.random.default_rng(0)
+    for trial in range(200):
+        world = int(rng.integers(2, 5))
+        min_cells = int(rng.integers(1, 4))
+        cells = int(rng.integers(world * min_cells, world * min_cells + 9))
+        counts = rng.integers(0, 50, cells) * (rng.random(cells) < 0.7)
+        layer_cost = float(rng.choice([0.0, 0.5, 3.0]))
+        got = SlabPlan.balanced_ranges(counts, world, min_cells, layer_cost)
+        assert got[0][0] == 0 and got[-1][1] == cells and all(a[1] == b[0] for a, b in zip(got[:-1], got[1:]))
+        assert all(hi - lo >= min_cells for lo, hi in got)
+        cost = counts + layer_cost
+
+        def worst(cuts):
+            edges = (0,) + cuts + (cells,)
+            return max(cost[a:b].sum() for a, b in zip(edges[:-1], edges[1:]))
+        best = min(worst(c) for c in itertools.combinations(range(1, cells), world - 1)
+                   if all(b - a >= min_cells for a, b in zip((0,) + c, c + (cells,))))
+        mine = max(cost[lo:hi].sum() for lo, hi in got)
+        assert mine <= best + 1e-9 * max(1.0, best), (trial, got, mine, best)
