@@ -392,3 +392,25 @@ def test_balanced_ranges_is_optimal_on_small_cases():
                    if all(b - a >= min_cells for a, b in zip((0,) + c, c + (cells,))))
         mine = max(cost[lo:hi].sum() for lo, hi in got)
         assert mine <= best + 1e-9 * max(1.0, best), (trial, got, mine, best)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_leaver_threshold_is_the_exact_cell_boundary(dtype):
+    """CudaSlab._threshold(cell): the smallest storage-precision position whose base cell is >= cell, so that
+    `x < t` / `x >= t` reproduce `base < cell` / `base >= cell` of the kernels' fp64 indexing exactly (any
+    resolution; base 0 also owns the (-1, 0) band that truncation sends there, quirk 1)."""
+    from femflow_b200.distributed import CudaSlab
+    np_dt = np.float32 if dtype == torch.float32 else np.float64
+    for res in (37, 64, 80, 256, 1000):
+        slab = CudaSlab.__new__(CudaSlab)             # the threshold needs no device: only dtype and inv_dx
+        slab.dtype, slab.inv_dx = dtype, float(res)
+        assert slab._threshold(0) == float("-inf")
+        for cell in (1, 2, 7, res // 3, res // 2, res - 2):
+            t = np_dt(slab._threshold(cell))
+            below = np.nextafter(t, np_dt(-np.inf))
+            base = lambda v: int(np.float64(v) * float(res) - 0.5)
+            assert base(t) >= cell and base(below) < cell, (res, cell)
+            # and agrees with the oracle's indexing on a cloud of positions around the boundary
+            x = (t + np.arange(-50, 50) * np.spacing(t)).astype(np_dt)
+            b, _ = O.base_and_fx(x.astype(np.float64)[:, None], float(res))
+            assert np.array_equal(x >= t, b[:, 0] >= cell)
