@@ -178,14 +178,12 @@ p2g_bulk3_kernel(DevCfg cfg, P2GPlanes planes, long long n, float* __restrict__ 
           return W.raw[buf][k][idx];
         };
       };
-      P2GParticle3<T> qa, qb;
-      qa.ok = qb.ok = false;
-      p2g_prepare3_pair(cfg, getter(lane), getter(32 + lane), has_mat, live_a, live_b, qa, qb);
-      node[0] = node[1] = -1;
-      if (live_a) node[0] = p2g_park_pair(S.pay, S.node0, qa, lane, dx, ny, nz);
-      else p2g_park_pair_zero(S.pay, lane);
-      if (live_b) node[1] = p2g_park_pair(S.pay, S.node0, qb, 32 + lane, dx, ny, nz);
-      else p2g_park_pair_zero(S.pay, 32 + lane);
+      P2GPairParker park{S.pay, S.node0, lane, ny, nz, dx, {-1, -1}};
+      p2g_prepare3_pair_sink(cfg, getter(lane), getter(32 + lane), has_mat, live_a, live_b, park);
+      node[0] = park.node[0];
+      node[1] = park.node[1];
+      if (!live_a) p2g_park_pair_zero(S.pay, lane);
+      if (!live_b) p2g_park_pair_zero(S.pay, 32 + lane);
     } else {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {

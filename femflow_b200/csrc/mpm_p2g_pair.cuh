@@ -135,12 +135,18 @@ FFMPM_HD bool fixed_corotated_affine3_f32x2(const Mat3x2& F, LoadC load_C, F2 mu
 // offset and material one by one (integer / fp64 work), the stress of both in packed fp32.  Falls back to
 // the one-particle routine (p2g_prepare3_from, fp64 stress included) unless both are inside the grid and
 // inside the series' strain range.  `live_b` false: the window holds no second particle for this lane.
-template <typename GetA, typename GetB>
-FFMPM_HD void p2g_prepare3_pair(const DevCfg& cfg, GetA ga, GetB gb, bool has_mat, bool live_a, bool live_b,
-                                P2GParticle3<float>& qa, P2GParticle3<float>& qb) {
+// `sink` receives the results as they become final, so that a kernel can park them in shared memory at once
+// instead of carrying two whole particles in registers through the stress evaluation (what made the first
+// packed phase 1 spill):
+//   sink.head(h, q)   particle h (0 / 1): base cell, weights offset, mass, mass*v are final (q.ok is true);
+//   sink.affine(A)    the nine affine entries of both particles (pairs: .x = particle 0, .y = particle 1);
+//   sink.full(h, q)   particle h evaluated by the one-particle routine (everything final, q.ok may be false).
+template <typename GetA, typename GetB, typename Sink>
+FFMPM_HD void p2g_prepare3_pair_sink(const DevCfg& cfg, GetA ga, GetB gb, bool has_mat, bool live_a, bool live_b, Sink& sink) {
   bool packed = live_a && live_b && cfg.fp32_stress && cfg.model == 0;
   if (packed) {
     float mass_a, mu_a, lam_a, mass_b, mu_b, lam_b;
+    P2GParticle3<float> qa, qb;
     auto index_part = [&](auto get, P2GParticle3<float>& q, float& mass_f, float& mu_f, float& lam_f) {
       const float x0 = get(P2G_X), x1 = get(P2G_X + 1), x2 = get(P2G_X + 2);
       int gx, gy, gz;
@@ -178,19 +184,41 @@ FFMPM_HD void p2g_prepare3_pair(const DevCfg& cfg, GetA ga, GetB gb, bool has_ma
         return C;
       };
       const double k = (cfg.dt * cfg.volume) * (4.0 * cfg.inv_dx * cfg.inv_dx);
-      packed = fixed_corotated_affine3_f32x2(F, load_C, f2(mu_a, mu_b), f2(lam_a, lam_b), f2(mass_a, mass_b),
-                                             (float)k, A);
+      // whether the series accepts the pair is known from F alone, but only at the end of its first stage; the
+      // heads are parked first (a declined pair parks everything again through the one-particle routine)
+      sink.head(0, qa);
+      sink.head(1, qb);
+      packed = fixed_corotated_affine3_f32x2(F, load_C, f2(mu_a, mu_b), f2(lam_a, lam_b), f2(mass_a, mass_b), (float)k, A);
       if (packed) {
-        qa.a00 = A.a00.v.x; qa.a01 = A.a01.v.x; qa.a02 = A.a02.v.x; qa.a10 = A.a10.v.x; qa.a11 = A.a11.v.x; qa.a12 = A.a12.v.x;
-        qa.a20 = A.a20.v.x; qa.a21 = A.a21.v.x; qa.a22 = A.a22.v.x;
-        qb.a00 = A.a00.v.y; qb.a01 = A.a01.v.y; qb.a02 = A.a02.v.y; qb.a10 = A.a10.v.y; qb.a11 = A.a11.v.y; qb.a12 = A.a12.v.y;
-        qb.a20 = A.a20.v.y; qb.a21 = A.a21.v.y; qb.a22 = A.a22.v.y;
+        sink.affine(A);
         return;
       }
     }
   }
-  if (live_a) qa = p2g_prepare3_from<float>(cfg, ga, has_mat, 1.0);
-  if (live_b) qb = p2g_prepare3_from<float>(cfg, gb, has_mat, 1.0);
+  if (live_a) { P2GParticle3<float> q = p2g_prepare3_from<float>(cfg, ga, has_mat, 1.0); sink.full(0, q); }
+  if (live_b) { P2GParticle3<float> q = p2g_prepare3_from<float>(cfg, gb, has_mat, 1.0); sink.full(1, q); }
+}
+
+// The same with the two particles returned whole (host tests, and callers that keep them in registers).
+struct P2GPairRegisters {
+  P2GParticle3<float>* q[2];
+  FFMPM_HD void head(int h, const P2GParticle3<float>& v) { *q[h] = v; }
+  FFMPM_HD void affine(const Mat3x2& A) {
+    P2GParticle3<float>& a = *q[0];
+    P2GParticle3<float>& b = *q[1];
+    a.a00 = A.a00.v.x; a.a01 = A.a01.v.x; a.a02 = A.a02.v.x; a.a10 = A.a10.v.x; a.a11 = A.a11.v.x; a.a12 = A.a12.v.x;
+    a.a20 = A.a20.v.x; a.a21 = A.a21.v.x; a.a22 = A.a22.v.x;
+    b.a00 = A.a00.v.y; b.a01 = A.a01.v.y; b.a02 = A.a02.v.y; b.a10 = A.a10.v.y; b.a11 = A.a11.v.y; b.a12 = A.a12.v.y;
+    b.a20 = A.a20.v.y; b.a21 = A.a21.v.y; b.a22 = A.a22.v.y;
+  }
+  FFMPM_HD void full(int h, const P2GParticle3<float>& v) { *q[h] = v; }
+};
+
+template <typename GetA, typename GetB>
+FFMPM_HD void p2g_prepare3_pair(const DevCfg& cfg, GetA ga, GetB gb, bool has_mat, bool live_a, bool live_b,
+                                P2GParticle3<float>& qa, P2GParticle3<float>& qb) {
+  P2GPairRegisters sink{{&qa, &qb}};
+  p2g_prepare3_pair_sink(cfg, ga, gb, has_mat, live_a, live_b, sink);
 }
 
 constexpr int P2G_NPAIR = P2G_WINDOW / 2;
@@ -234,6 +262,39 @@ FFMPM_HD void p2g_park_pair_zero(float4 (*pay)[P2G_PAIR_PADDED], int idx) {
 #pragma unroll
   for (int c = 0; c < 16; ++c) *p2g_pair_slot(pay, idx, c) = c == PP_FX || c == PP_FY || c == PP_FZ ? 0.5f : 0.0f;
 }
+
+// Sink of p2g_prepare3_pair_sink that parks straight into the pair-major payload: slots `slot0` (particle 0)
+// and `slot0 + 32` (particle 1) of the warp's window.
+struct P2GPairParker {
+  float4 (*pay)[P2G_PAIR_PADDED];
+  int* node0;
+  int slot0, ny, nz;
+  float dx;
+  int node[2];
+  FFMPM_HD void head(int h, const P2GParticle3<float>& q) {
+    const int idx = slot0 + 32 * h;
+    *p2g_pair_slot(pay, idx, PP_MVX) = q.mvx; *p2g_pair_slot(pay, idx, PP_MVY) = q.mvy; *p2g_pair_slot(pay, idx, PP_MVZ) = q.mvz;
+    *p2g_pair_slot(pay, idx, PP_M) = q.m;
+    *p2g_pair_slot(pay, idx, PP_FX) = q.fx; *p2g_pair_slot(pay, idx, PP_FY) = q.fy; *p2g_pair_slot(pay, idx, PP_FZ) = q.fz;
+    node[h] = (q.bx * ny + q.by) * nz + q.bz;
+    node0[idx] = node[h];
+  }
+  FFMPM_HD void affine(const Mat3x2& A) {
+    const F2 d = f2(dx);
+    const F2 v[9] = {f2_mul(A.a00, d), f2_mul(A.a01, d), f2_mul(A.a02, d), f2_mul(A.a10, d), f2_mul(A.a11, d),
+                     f2_mul(A.a12, d), f2_mul(A.a20, d), f2_mul(A.a21, d), f2_mul(A.a22, d)};
+    const int comp[9] = {PP_A00, PP_A01, PP_A02, PP_A10, PP_A11, PP_A12, PP_A20, PP_A21, PP_A22};
+#pragma unroll
+    for (int e = 0; e < 9; ++e) {
+      *p2g_pair_slot(pay, slot0, comp[e]) = v[e].v.x;
+      *p2g_pair_slot(pay, slot0 + 32, comp[e]) = v[e].v.y;
+    }
+  }
+  FFMPM_HD void full(int h, const P2GParticle3<float>& q) {
+    P2GParticle3<float> c = q;
+    node[h] = p2g_park_pair(pay, node0, c, slot0 + 32 * h, dx, ny, nz);
+  }
+};
 
 // Packed quadratic B-spline pieces (three_d/p2g.py:55) of both particles, and the node offsets k - f.
 FFMPM_HD void f2_bspline(F2 f, F2 (&w)[3], F2 (&d)[3]) {

@@ -204,6 +204,40 @@ void km_prepare3_pair_f32(int res, int n_nodes, double inv_dx, double dx, double
   }
 }
 
+// Phase 1 of the packed kernels exactly as a warp runs it (FFMPM_P2G_VARIANT=8/9/11): lane l prepares slots l and
+// l + 32 of a window of `cnt` <= 64 particles through p2g_prepare3_pair_sink and parks them with P2GPairParker;
+// slots >= cnt are parked as zeros.  Returns the parked window as payload[64][16] (PP_* order) and node0[64].
+void km_pair_phase1_window(int res, int n_nodes, double inv_dx, double dx, double dt, double volume, double hardening,
+                           int index_fp32, int cnt, const float* x, const float* v, const float* C, const float* F,
+                           const float* mass, const float* mu, const float* lam, float* payload, int* node0_out) {
+  const DevCfg cfg = make_cfg(res, n_nodes, inv_dx, dx, dt, volume, hardening, 0, 1, index_fp32);
+  static float4 pay[P2G_PAIR_PLANES][P2G_PAIR_PADDED];
+  static int node0[P2G_WINDOW];
+  for (int c = 0; c < P2G_PAIR_PLANES; ++c)
+    for (int s = 0; s < P2G_PAIR_PADDED; ++s) pay[c][s] = make_float4(NAN, NAN, NAN, NAN);
+  for (int q = 0; q < P2G_WINDOW; ++q) node0[q] = -7;
+  auto getter = [&](long long p) {
+    return [=](int k) -> float {
+      if (k < P2G_V) return x[3 * p + k];
+      if (k < P2G_C) return v[3 * p + (k - P2G_V)];
+      if (k < P2G_F) return C[9 * p + (k - P2G_C)];
+      if (k < P2G_MASS) return F[9 * p + (k - P2G_F)];
+      return k == P2G_MASS ? mass[p] : (k == P2G_MU ? mu[p] : lam[p]);
+    };
+  };
+  for (int lane = 0; lane < 32; ++lane) {
+    const bool live_a = lane < cnt, live_b = 32 + lane < cnt;
+    P2GPairParker park{pay, node0, lane, n_nodes, n_nodes, (float)dx, {-1, -1}};
+    p2g_prepare3_pair_sink(cfg, getter(live_a ? lane : 0), getter(live_b ? 32 + lane : 0), true, live_a, live_b, park);
+    if (!live_a) p2g_park_pair_zero(pay, lane);
+    if (!live_b) p2g_park_pair_zero(pay, 32 + lane);
+  }
+  for (int q = 0; q < P2G_WINDOW; ++q) {
+    for (int c = 0; c < 16; ++c) payload[16 * q + c] = *p2g_pair_slot(pay, q, c);
+    node0_out[q] = node0[q];
+  }
+}
+
 // Packed-fp32 P2G phase 2 (mpm_p2g_pair.cuh): park `n_slots` payloads (16 floats each, PP_* order) in the
 // pair-major shared-memory image exactly as phase 1 does, then accumulate x-slab `li` of the run [r0, r1).
 // Slots >= n_slots are parked as the kernel parks the tail of the last window.  Returns 0, or -1 when two

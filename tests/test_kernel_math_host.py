@@ -409,3 +409,82 @@ def test_tile_major_bin_keys(km, res):
         fin = ~np.isnan(x[:, 0])
         assert np.array_equal(bx[fin], base[fin, 0].astype(np.int32))
         assert not ok[0] and (origin > 0 or (ok[1] and ok[2]))
+
+
+@pytest.mark.parametrize("cnt", [64, 63, 33, 32, 5])
+def test_packed_phase1_parks_the_window_like_the_scalar_path(km, cnt):
+    """The warp-level phase 1 of FFMPM_P2G_VARIANT=8/9/11 replayed lane by lane on the host: heads parked before
+    the stress, affine entries after it (P2GPairParker), one-particle fallback for out-of-grid / over-strained
+    partners, zero-parked tail -- the parked window must equal what the scalar routine would have parked
+    (index, m v, m, f bit for bit; affine * dx to fp32 round-off of the stress)."""
+    rng = np.random.default_rng(cnt)
+    res, n = 32, 64
+    dx = 1.0 / res
+    vol = float(f32((dx / 2) ** 3))
+    x = f32(rng.uniform(0.2, 0.8, size=(n, 3)))
+    x[3] = [0.995, 0.5, 0.5]                                     # out of grid: its partner (slot 35) takes the fallback too
+    amp = rng.choice([1e-4, 2e-2, 6e-2], size=(n, 1, 1)); amp[40] = 0.4      # slot 40: beyond the series -> pair (8, 40) falls back
+    F = f32(np.eye(3) + amp * rng.uniform(-1, 1, size=(n, 3, 3)))
+    v = f32(rng.normal(size=(n, 3))); Cm = f32(rng.normal(0, 0.05, size=(n, 3, 3)))
+    mass = f32(rng.uniform(0.5, 1.5, n) * vol); mu = f32(rng.uniform(3000, 5000, n)); lam = f32(rng.uniform(2000, 3000, n))
+    base, fx, aff, mv, m, ok = prepare3(km, "f32", res, x, v, Cm, F, mass, mu, lam, 1e-4, vol)
+    arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (x, v, Cm.reshape(n, 9), F.reshape(n, 9), mass, mu, lam)]
+    pay = np.zeros((64, 16), np.float32); node0 = np.zeros(64, np.int32)
+    km.km_pair_phase1_window(C.c_int(res), C.c_int(res + 1), C.c_double(float(res)), C.c_double(dx), C.c_double(1e-4), C.c_double(vol),
+                             C.c_double(1.0), C.c_int(1), C.c_int(cnt), *(ptr(a) for a in arrs), ptr(pay), ptr(node0))
+    G = res + 1
+    scale = np.abs(aff[ok]).max() * dx
+    for q in range(64):
+        if q >= cnt:
+            assert np.array_equal(pay[q, [0, 1, 2, 3, 4, 5, 6, 8, 9, 10, 12, 13, 14]], np.zeros(13, np.float32))
+            assert np.array_equal(pay[q, [7, 11, 15]], np.float32([0.5, 0.5, 0.5]))
+            continue
+        if not ok[q]:
+            assert node0[q] == -1 and not pay[q, :7].any() and pay[q, 7] == 0.5
+            continue
+        assert node0[q] == (base[q, 0] * G + base[q, 1]) * G + base[q, 2]
+        assert np.array_equal(pay[q, 0:3], mv[q]) and pay[q, 3] == m[q]
+        assert np.array_equal(pay[q, [7, 11, 15]], fx[q])
+        got_a = pay[q, [4, 5, 6, 8, 9, 10, 12, 13, 14]].reshape(3, 3)
+        assert np.abs(got_a - aff[q] * np.float32(dx)).max() <= 2e-6 * scale, q
+
+
+def test_packed_p2g_window_end_to_end_against_the_oracle(km):
+    """One window of the packed-fp32 P2G on the host, arithmetic end to end: phase 1 as the warp runs it
+    (km_pair_phase1_window), runs of equal base cell, the packed accumulation of every (run, x-slab), and the
+    scatter of the nine node sums per item -- against the oracle's P2G (three_d/p2g.py:14-80) of the same 64
+    cell-sorted particles.  Only the device-side plumbing (ballots, REDs, prefetch) is left to the GPU test."""
+    rng = np.random.default_rng(3)
+    res, n = 16, 64
+    G, dx = res + 1, 1.0 / res
+    vol = float(f32((dx / 2) ** 3))
+    cells = rng.integers(4, 7, size=(9, 3))                       # nine occupied cells, ~7 particles each, some repeated
+    cell = cells[np.sort(rng.integers(0, 9, n))]
+    x = f32((cell + 0.5 + rng.uniform(0.02, 0.98, size=(n, 3))) * dx)
+    base, _ = O.base_and_fx(x, float(res))
+    order = np.lexsort((base[:, 2], base[:, 1], base[:, 0]))      # cell-sorted, as the reordering G2P leaves the buffer
+    x = x[order]
+    F = f32(np.eye(3) + 0.03 * rng.uniform(-1, 1, size=(n, 3, 3)))
+    v = f32(rng.normal(size=(n, 3))); Cm = f32(rng.normal(0, 0.5, size=(n, 3, 3)))
+    mass = f32(rng.uniform(0.5, 1.5, n) * vol); mu = f32(rng.uniform(3000, 5000, n)); lam = f32(rng.uniform(2000, 3000, n))
+    arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (x, v, Cm.reshape(n, 9), F.reshape(n, 9), mass, mu, lam)]
+    pay = np.zeros((64, 16), np.float32); node0 = np.zeros(64, np.int32)
+    km.km_pair_phase1_window(C.c_int(res), C.c_int(G), C.c_double(float(res)), C.c_double(dx), C.c_double(1e-4), C.c_double(vol),
+                             C.c_double(1.0), C.c_int(1), C.c_int(n), *(ptr(a) for a in arrs), ptr(pay), ptr(node0))
+    assert (node0 >= 0).all()
+    heads = [0] + [q for q in range(1, n) if node0[q] != node0[q - 1]] + [n]
+    assert len(heads) - 1 >= 5
+    grid = np.zeros((G * G * G, 4))
+    km.km_pair_accumulate.restype = C.c_int
+    for r0, r1 in zip(heads[:-1], heads[1:]):
+        for li in range(3):
+            out = np.zeros((9, 4), np.float32)
+            assert km.km_pair_accumulate(C.c_int(n), ptr(pay), C.c_int(r0), C.c_int(r1), C.c_int(li), ptr(out)) == 0
+            for j in range(3):
+                for k in range(3):
+                    grid[node0[r0] + (li * G + j) * G + k] += out[j * 3 + k]
+    gv = np.zeros((G, G, G, 3)); gm = np.zeros((G, G, G, 1))
+    O.p2g_3d(float(res), 1.0, dx, 1e-4, vol, gv, gm, x, mass, mu, lam, v, F, Cm, np.ones((n, 1)))
+    grid = grid.reshape(G, G, G, 4)
+    assert np.abs(grid[..., 3:] - gm).max() <= 1e-5 * np.abs(gm).max()
+    assert np.abs(grid[..., :3] - gv).max() <= 1e-5 * np.abs(gv).max()
