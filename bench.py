@@ -330,13 +330,25 @@ def main():
         for _ in range(args.steps // 10):
             graph.replay()
     else:
+        # SURVEY 8d asks for the spread as well: an event every fifth of the region (recording one costs nothing
+        # on the stream) gives five per-substep samples next to the total
+        marks, chunk = [], max(1, args.steps // 5)
         for k in range(args.steps):
             solver.substep(1)
             if dam and world > 1 and args.rebalance and args.rebalance_every and (k + 1) % args.rebalance_every == 0:
                 solver.rebalance()
+            if (k + 1) % chunk == 0 and k + 1 < args.steps:
+                marks.append((k + 1, torch.cuda.Event(enable_timing=True)))
+                marks[-1][1].record()
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
+    samples = []
+    if graph is None:
+        prev_k, prev_ev = 0, ev0
+        for k_done, ev in marks + [(args.steps, ev1)]:
+            samples.append(prev_ev.elapsed_time(ev) / (k_done - prev_k))
+            prev_k, prev_ev = k_done, ev
     launches = solver.launch_count() - l0 if graph is None else solver.graph_launches * (args.steps // 10)
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -483,7 +495,7 @@ def main():
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "ms_per_step_samples": [round(v, 5) for v in samples], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (cell indexing in f64; stress in f32 perturbation form, f64 fallback at large strain)",
         "data": "synthetic",
         "config": {"workload": scene.name, "particles_per_gpu": n, "particles_total": n_total,
