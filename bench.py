@@ -345,10 +345,13 @@ def main():
     ms = ev0.elapsed_time(ev1)
     samples = []
     if graph is None:
-        prev_k, prev_ev = 0, ev0
-        for k_done, ev in marks + [(args.steps, ev1)]:
-            samples.append(prev_ev.elapsed_time(ev) / (k_done - prev_k))
-            prev_k, prev_ev = k_done, ev
+        try:
+            prev_k, prev_ev = 0, ev0
+            for k_done, ev in marks + [(args.steps, ev1)]:
+                samples.append(prev_ev.elapsed_time(ev) / (k_done - prev_k))
+                prev_k, prev_ev = k_done, ev
+        except Exception:  # an extra: never at the expense of the line itself
+            samples = []
     launches = solver.launch_count() - l0 if graph is None else solver.graph_launches * (args.steps // 10)
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
