@@ -1,0 +1,176 @@
+"""bench.py's control flow and JSON assembly, dry: the solver, CUDA events / streams and pinned memory are
+stand-ins, everything else (argument handling, timed loop, sample spread, phase table, e2e bookkeeping, roofline,
+the one JSON line) is the real code.  No number printed here means anything; the point is that a typo in the
+script the round's measurement depends on fails HERE, on CPU, not on the GPU box."""
+import contextlib
+import json
+import os
+import sys
+
+import pytest
+
+torch = pytest.importorskip("torch")
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+class FakeEvent:
+    clock = [0.0]
+
+    def __init__(self, enable_timing=False):
+        self.t = None
+
+    def record(self, stream=None):
+        FakeEvent.clock[0] += 1.0
+        self.t = FakeEvent.clock[0]
+
+    def elapsed_time(self, other):
+        return other.t - self.t
+
+    def synchronize(self):
+        pass
+
+
+class FakeStream:
+    cuda_stream = 0
+
+    def __init__(self, device=None):
+        pass
+
+    def wait_event(self, ev):
+        assert ev.t is not None, "waited on an event that was never recorded"
+
+    def wait_stream(self, s):
+        pass
+
+    def synchronize(self):
+        pass
+
+
+class FakeBuf:
+    def __init__(self, cap):
+        self.x = torch.zeros((3, cap)); self.v = torch.zeros((3, cap))
+        self.C = torch.zeros((9, cap)); self.F = torch.zeros((9, cap))
+        self.Jp = self.mass = self.mu0 = self.lam0 = self.material = None
+        self.id = torch.arange(cap, dtype=torch.int32)
+
+
+class FakeGraph:
+    def __init__(self, solver, n):
+        self.solver, self.n = solver, n
+
+    def replay(self):
+        self.solver.steps_run += self.n
+
+
+class FakeSolver:
+    """The surface of femflow_b200.mpm.MpmSolver that bench.py touches."""
+    instances = []
+
+    def __init__(self, dim, res, dt, volume, gravity, hardening, *, capacity, device=None, **kw):
+        self.dim, self.capacity, self.device, self.dtype = dim, (capacity + 63) // 64 * 64, torch.device("cpu"), torch.float32
+        self.reorder = dim == 3
+        self.buffers = [FakeBuf(self.capacity), FakeBuf(self.capacity)]
+        self.material_layout = "table[1]"
+        self.num_particles = 0
+        self.steps_run = self.launches = self.binds = 0
+        self._live = 0
+        FakeSolver.instances.append(self)
+
+    live = property(lambda self: self.buffers[self._live])
+
+    def set_particles(self, x, *a, **k):
+        self.num_particles = len(x)
+
+    def _bind(self, n, cur=0):
+        self.num_particles, self._live, self.binds = n, 0, self.binds + 1
+
+    def substep(self, n=1):
+        self.steps_run += n
+        self.launches += 10 * n
+        if self.reorder:
+            self._live ^= n & 1
+
+    def make_graph(self, n):
+        self.graph_substeps, self.graph_launches = n, 10 * n
+        return FakeGraph(self, n)
+
+    def poll_error(self):
+        return 0
+
+    def launch_count(self):
+        return self.launches
+
+    def clear_grid(self): pass
+    def bin(self): pass
+    def p2g(self): pass
+    def grid_op(self): pass
+    def g2p(self): pass
+
+
+@pytest.fixture
+def dry(monkeypatch):
+    import femflow_b200.mpm as mpm
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda i: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(torch.cuda, "Stream", FakeStream)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: FakeStream())
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    monkeypatch.setattr(mpm, "MpmSolver", FakeSolver)
+    monkeypatch.delenv("RANK", raising=False); monkeypatch.delenv("WORLD_SIZE", raising=False)
+    FakeSolver.instances.clear()
+    return monkeypatch
+
+
+def run_bench(monkeypatch, capsys, *flags):
+    import bench
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--workload", "3d:32:8", "--no-cpu-baseline", *flags])
+    bench.main()
+    out = [ln for ln in capsys.readouterr().out.splitlines() if ln.strip()]
+    assert len(out) == 1, out                                   # exactly ONE line on stdout
+    return json.loads(out[0])
+
+
+CONTRACT = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+            "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline")
+
+
+def test_default_line_carries_the_contract(dry, capsys):
+    d = run_bench(dry, capsys, "--steps", "10", "--warmup", "1", "--e2e-steps", "2")
+    for k in CONTRACT:
+        assert k in d, k
+    s = FakeSolver.instances[0]
+    assert d["warmup"] == 3 and d["steps"] == 10 and d["n_gpus"] == 1          # warm-up is raised to the required 3
+    assert d["gpu_launches"] == 100 and d["config"]["cuda_graph"] is False
+    assert len(d["ms_per_step_samples"]) == 5
+    assert d["config"]["workload"].startswith("3D elastic block") and d["config"]["parallelism"] == "single GPU"
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] == e["d2h_bytes_per_step"] == 24 * 4 * s.num_particles and "streamed" not in e
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and set(r["phase_ms"]) == {"clear", "bin", "p2g", "grid_op", "g2p"}
+    assert r["algorithmic_bytes_per_launch"] > 0 and 0 < r["frac"]
+    assert s.steps_run == 3 + 10 + 1 + 2                                       # warm-up, timed region, e2e warm step + e2e steps
+
+
+def test_graph_and_streamed_options(dry, capsys):
+    d = run_bench(dry, capsys, "--steps", "20", "--warmup", "4", "--e2e-steps", "1", "--graph", "--e2e-streamed")
+    assert d["config"]["cuda_graph"] is True and d["gpu_launches"] == 200 and d["ms_per_step_samples"] == []
+    st = d["e2e"]["streamed"]
+    assert st.get("error") is None and st["steps"] == 4 and st["value"] > 0
+    s = FakeSolver.instances[0]
+    assert len(s.buffers) == 2 and s.buffers[0].x.shape[1] == s.capacity       # the solver got its own buffers back
+    # steps not a multiple of 10: the graph request is declined, not an error
+    d = run_bench(dry, capsys, "--steps", "7", "--graph")
+    assert d["config"]["cuda_graph"] is False and d["gpu_launches"] == 70 and len(d["ms_per_step_samples"]) == 7
+
+
+def test_2d_workload_line(dry, capsys, monkeypatch):
+    import bench
+    from femflow_b200 import scenes
+    monkeypatch.setattr(bench, "make_scene", lambda w, seed=0, **k: scenes.elastic_block(2, 64, 16, 2, seed))
+    d = run_bench(dry, capsys, "--steps", "5")
+    assert set(d["roofline"]["phase_ms"]) == {"clear", "p2g", "grid_op", "g2p"} and d["e2e"]["value"] > 0
