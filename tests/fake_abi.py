@@ -1,0 +1,362 @@
+"""A CPU stand-in for libfemflow_mpm.so, for TESTS of the Python host code above the C ABI.
+
+``FakeLib`` implements the entry points of include/femflow_mpm.h in Python over the same raw pointers (ctypes
+structs, data_ptr() of torch tensors -- here CPU tensors), with the NumPy oracle as the arithmetic.  It lets the
+real ``MpmSolver`` / ``CudaSlab`` / ``SlabDriver`` code -- buffer binding, material tables, the reordering
+ping-pong, id carrying, leaver extraction, migration payloads, slab rebuilds -- run on CPU under gloo, where the
+round's single-GPU test box can never run the multi-GPU plumbing.  Test infrastructure only: it lives in tests/,
+nothing in femflow_b200/ can import it, and it is not a fallback (the product path raises without CUDA).
+
+3D, cubic global grids (the oracle's assumption); slabs are cut along x (cfg.origin[0], cfg.n[0]).
+"""
+import contextlib
+import ctypes as C
+
+import numpy as np
+
+from femflow_b200 import _native as N
+from oracle import mpm_oracle as O
+
+_CT = {4: C.c_float, 8: C.c_double}
+
+
+def _view(ptr, count, ctype):
+    if not ptr or count == 0:
+        return None
+    return np.ctypeslib.as_array(C.cast(int(ptr), C.POINTER(ctype)), (int(count),))
+
+
+def _val(a):
+    """Python value of a ctypes scalar / plain int / None."""
+    return getattr(a, "value", a)
+
+
+class _Handle:
+    pass
+
+
+class FakeLib:
+    def __init__(self):
+        self.handles, self.next_id, self.err = {}, 1, b""
+
+    # -- bookkeeping ------------------------------------------------------------------------------
+    def ffmpm_abi_version(self):
+        return N.ABI_VERSION
+
+    def ffmpm_last_error(self):
+        return self.err
+
+    def _fail(self, code, msg):
+        self.err = msg.encode()
+        return code
+
+    @staticmethod
+    def _layout(cfg, capacity):
+        es = 8 if cfg.dtype == N.FFMPM_F64 else 4
+        nodes = cfg.n[0] * cfg.n[1] * cfg.n[2]
+        grid_off = 256
+        bin_off = grid_off + ((nodes * 4 * es + 255) // 256) * 256
+        return es, nodes, grid_off, bin_off, bin_off + 3 * 4 * max(int(capacity), 1) + 4096
+
+    def ffmpm_workspace_bytes(self, cfg_ref, capacity):
+        cfg = cfg_ref._obj
+        if cfg.dim not in (2, 3) or not cfg.dt > 0:
+            return self._fail(N.FFMPM_E_INVALID, "bad config")
+        return self._layout(cfg, _val(capacity))[4]
+
+    def ffmpm_create(self, cfg_ref, device, out_ref):
+        cfg = cfg_ref._obj
+        if cfg.dim != 3:
+            return self._fail(N.FFMPM_E_INVALID, "the CPU stand-in is 3D only")
+        h = _Handle()
+        h.cfg = N.FfMpmConfig.from_buffer_copy(cfg)
+        h.ws = None
+        h.st = [None, None]
+        h.live, h.n, h.launches, h.n_oob = 0, 0, 0, 0
+        h.table = None
+        h.colliders = None
+        h.own = (-2 ** 31, 2 ** 31 - 1)
+        self.handles[self.next_id] = h
+        out_ref._obj.value = self.next_id
+        self.next_id += 1
+        return N.FFMPM_OK
+
+    def _h(self, h):
+        return self.handles[_val(h)]
+
+    def ffmpm_destroy(self, h):
+        self.handles.pop(_val(h), None)
+
+    def ffmpm_set_workspace(self, h, ptr, nbytes):
+        h = self._h(h)
+        h.ws, h.ws_bytes = int(_val(ptr)), int(_val(nbytes))
+        h.es, h.nodes, h.grid_off, h.bin_off, _ = self._layout(h.cfg, 0)
+        return N.FFMPM_OK
+
+    def ffmpm_bind_state(self, h, cur_ref, alt_ref, n):
+        h = self._h(h)
+        h.st[0] = N.FfMpmState.from_buffer_copy(cur_ref._obj)
+        h.st[1] = N.FfMpmState.from_buffer_copy(alt_ref._obj) if alt_ref is not None else None
+        n = int(_val(n))
+        if n < 0 or n > h.st[0].stride:
+            return self._fail(N.FFMPM_E_INVALID, "n must be in [0, stride]")
+        mats = sum(bool(getattr(h.st[0], k)) for k in ("mass", "mu0", "lam0"))
+        if mats not in (0, 3):
+            return self._fail(N.FFMPM_E_INVALID, "state is missing a required plane")
+        h.live, h.n = 0, n
+        return N.FFMPM_OK
+
+    def ffmpm_live_buffer(self, h):
+        return self._h(h).live
+
+    def ffmpm_num_particles(self, h):
+        return self._h(h).n
+
+    def ffmpm_set_num_particles(self, h, n):
+        self._h(h).n = int(_val(n))
+        return N.FFMPM_OK
+
+    def ffmpm_set_materials(self, h, mass, mu0, lam0, count):
+        h = self._h(h)
+        count = int(_val(count))
+        if count == 0:
+            h.table = None
+            return N.FFMPM_OK
+        dt = np.float64 if h.cfg.dtype == N.FFMPM_F64 else np.float32
+        h.table = np.stack([np.ctypeslib.as_array(p, (count,)).astype(dt).astype(np.float64) for p in (mass, mu0, lam0)])
+        return N.FFMPM_OK
+
+    def ffmpm_set_colliders(self, h, points, normals, count):
+        self._h(h).colliders = None if not _val(count) else (np.ctypeslib.as_array(points, (_val(count) * 3,)).reshape(-1, 3).copy(),
+                                                            np.ctypeslib.as_array(normals, (_val(count) * 3,)).reshape(-1, 3).copy())
+        return N.FFMPM_OK
+
+    def ffmpm_set_owned_range(self, h, lo, hi):
+        self._h(h).own = (int(_val(lo)), int(_val(hi)))
+        return N.FFMPM_OK
+
+    def ffmpm_leaver_count_ptr(self, h, out_ref):
+        out_ref._obj.value = self._h(h).ws + 64
+        return N.FFMPM_OK
+
+    def ffmpm_grid_ptr(self, h, out_ref):
+        h = self._h(h)
+        out_ref._obj.value = h.ws + h.grid_off
+        return N.FFMPM_OK
+
+    ffmpm_grid_view = ffmpm_grid_ptr
+
+    def ffmpm_bin_ptrs(self, h, keys, perm, off, n_cells):
+        return self._fail(N.FFMPM_E_STATE, "the CPU stand-in keeps no binning")
+
+    def ffmpm_launch_count(self, h):
+        return self._h(h).launches
+
+    def ffmpm_poll_error(self, h, stream, code_ref, n_ref):
+        h = self._h(h)
+        n, h.n_oob = h.n_oob, 0
+        code_ref._obj.value, n_ref._obj.value = 0, n
+        return self._fail(N.FFMPM_E_OOB, "particle stencil left the grid") if n else N.FFMPM_OK
+
+    # -- state access -----------------------------------------------------------------------------
+    def _planes(self, h, which):
+        """SoA planes of buffer `which` as NumPy views onto the caller's memory."""
+        s, ct, st = h.st[which], _CT[h.es], h.st[which].stride
+        out = {k: _view(getattr(s, k), rows * st, ct).reshape(rows, st) for k, rows in (("x", 3), ("v", 3), ("C", 9), ("F", 9))}
+        for k in ("mass", "mu0", "lam0", "Jp"):
+            out[k] = _view(getattr(s, k), st, ct)
+        out["id"] = _view(s.id, st, C.c_int32)
+        out["material"] = _view(s.material, st, C.c_uint8)
+        return out
+
+    def _materials(self, h, p, n):
+        if p["mass"] is not None:
+            return tuple(p[k][:n].astype(np.float64) for k in ("mass", "mu0", "lam0"))
+        if h.table is not None:
+            row = p["material"][:n].astype(np.int64) if (p["material"] is not None and h.table.shape[1] > 1) else np.zeros(n, np.int64)
+            return tuple(h.table[i][row] for i in range(3))
+        c = h.cfg
+        return tuple(np.full(n, v) for v in (c.mass, c.mu_0, c.lambda_0))
+
+    def _grid(self, h):
+        return _view(h.ws + h.grid_off, h.nodes * 4, _CT[h.es]).reshape(h.cfg.n[0], h.cfg.n[1], h.cfg.n[2], 4)
+
+    def _embed(self, h):
+        """Local grid planes inside zeroed global oracle arrays."""
+        G = h.cfg.res[0] + 1
+        assert h.cfg.res[1] + 1 == G == h.cfg.res[2] + 1 and h.cfg.n[1] == G == h.cfg.n[2], "cubic global grids only"
+        g, o = self._grid(h), h.cfg.origin[0]
+        gv, gm = np.zeros((G, G, G, 3)), np.zeros((G, G, G, 1))
+        gv[o:o + h.cfg.n[0]] = g[..., :3]
+        gm[o:o + h.cfg.n[0]] = g[..., 3:]
+        return gv, gm, slice(o, o + h.cfg.n[0])
+
+    def _inside(self, h, x):
+        """Particles whose stencil stays inside the LOCAL grid (the kernels flag and skip the others)."""
+        base, _ = O.base_and_fx(x, h.cfg.inv_dx)
+        b = base - np.array([h.cfg.origin[0], 0, 0])
+        with np.errstate(invalid="ignore"):
+            return ~np.isnan(x).any(1) & (b >= 0).all(1) & (b + 2 < np.array(list(h.cfg.n))).all(1), base
+
+    # -- phases -----------------------------------------------------------------------------------
+    def ffmpm_clear_grid(self, h, stream):
+        self._grid(self._h(h))[...] = 0
+        return N.FFMPM_OK
+
+    def ffmpm_bin(self, h, stream):
+        return N.FFMPM_OK
+
+    def ffmpm_p2g(self, h, stream):
+        h = self._h(h)
+        h.launches += 1
+        if h.n == 0:
+            return N.FFMPM_OK
+        p, n = self._planes(h, h.live), h.n
+        x = p["x"][:, :n].T.astype(np.float64)
+        ok, _ = self._inside(h, x)
+        h.n_oob += int((~ok).sum())
+        mass, mu, lam = (a[ok] for a in self._materials(h, p, n))
+        gv, gm, sl = self._embed(h)
+        c = h.cfg
+        O.p2g_3d(c.inv_dx, c.hardening, c.dx, c.dt, c.volume, gv, gm, x[ok], mass, mu, lam, p["v"][:, :n].T.astype(np.float64)[ok],
+                 p["F"][:, :n].T.reshape(n, 3, 3).astype(np.float64)[ok], p["C"][:, :n].T.reshape(n, 3, 3).astype(np.float64)[ok],
+                 np.ones((int(ok.sum()), 1)))
+        g = self._grid(h)
+        g[..., :3], g[..., 3:] = gv[sl], gm[sl]
+        return N.FFMPM_OK
+
+    def ffmpm_grid_op_halo(self, h, lo, planes_lo, hi, planes_hi, stream):
+        h = self._h(h)
+        h.launches += 1
+        g = self._grid(h)
+        plane = h.cfg.n[1] * h.cfg.n[2] * 4
+        planes_lo, planes_hi = int(_val(planes_lo) or 0), int(_val(planes_hi) or 0)
+        if planes_lo:
+            g[:planes_lo] += _view(_val(lo), planes_lo * plane, _CT[h.es]).reshape(planes_lo, *g.shape[1:])
+        if planes_hi:
+            g[g.shape[0] - planes_hi:] += _view(_val(hi), planes_hi * plane, _CT[h.es]).reshape(planes_hi, *g.shape[1:])
+        gv, gm, sl = self._embed(h)
+        c = h.cfg
+        O.grid_op_3d(c.res[0], c.dx, c.dt, c.gravity, gv, gm)
+        if h.colliders is not None:
+            O.check_collision_points(h.colliders[0], h.colliders[1], c.res[0], c.dx, gv)
+        g[..., :3] = gv[sl]
+        return N.FFMPM_OK
+
+    def ffmpm_grid_op(self, h, stream):
+        return self.ffmpm_grid_op_halo(h, None, 0, None, 0, stream)
+
+    def ffmpm_collide(self, h, stream):
+        return N.FFMPM_OK
+
+    def ffmpm_g2p(self, h, stream):
+        h = self._h(h)
+        h.launches += 1
+        if h.n == 0:
+            return N.FFMPM_OK
+        p, n = self._planes(h, h.live), h.n
+        x = p["x"][:, :n].T.astype(np.float64)
+        v = p["v"][:, :n].T.astype(np.float64)
+        F = p["F"][:, :n].T.reshape(n, 3, 3).astype(np.float64)
+        Cm = p["C"][:, :n].T.reshape(n, 3, 3).astype(np.float64)
+        ok, base = self._inside(h, x)
+        h.n_oob += int((~ok).sum())
+        gv, _, _ = self._embed(h)
+        xo, vo, Fo, Co = x[ok], v[ok], F[ok], Cm[ok]
+        O.g2p_3d(h.cfg.inv_dx, h.cfg.dt, gv, xo, vo, Fo, Co, np.ones((len(xo), 1)))
+        x[ok], v[ok], F[ok], Cm[ok] = xo, vo, Fo, Co
+        if h.st[1] is not None:
+            # the reordering G2P: cell-sorted into the other buffer, out-of-grid particles last, planes carried along
+            G = h.cfg.res[0] + 1
+            key = np.where(ok, O.cell_keys(np.where(ok[:, None], base, 0), G), np.iinfo(np.int64).max)
+            order = np.argsort(key, kind="stable")
+            q = self._planes(h, h.live ^ 1)
+            for k in ("mass", "mu0", "lam0", "Jp", "id", "material"):
+                if p[k] is not None:
+                    q[k][:n] = p[k][:n][order]
+            h.live ^= 1
+        else:
+            order, q = np.arange(n), p
+        q["x"][:, :n] = x[order].T
+        q["v"][:, :n] = v[order].T
+        q["F"][:, :n] = F[order].reshape(n, 9).T
+        q["C"][:, :n] = Cm[order].reshape(n, 9).T
+        nb, _ = O.base_and_fx(x[ok], h.cfg.inv_dx)
+        leavers = int(((nb[:, 0] < h.own[0]) | (nb[:, 0] >= h.own[1])).sum())
+        _view(h.ws + 64, 1, C.c_int32)[0] = leavers
+        return N.FFMPM_OK
+
+    def ffmpm_scatter(self, h, stream):
+        self.ffmpm_clear_grid(h, stream)
+        return self.ffmpm_p2g(h, stream)
+
+    def ffmpm_gather(self, h, stream):
+        return self.ffmpm_g2p(h, stream)
+
+    def ffmpm_substep(self, h, n, stream):
+        for _ in range(int(_val(n))):
+            self.ffmpm_scatter(h, stream)
+            self.ffmpm_grid_op(h, stream)
+            self.ffmpm_gather(h, stream)
+        return N.FFMPM_OK
+
+    def ffmpm_snapshot(self, h, coeff, out, stream):
+        h = self._h(h)
+        p, n = self._planes(h, h.live), h.n
+        dst = _view(_val(out), 3 * n, C.c_double).reshape(n, 3)
+        ids = p["id"][:n] if p["id"] is not None else np.arange(n)
+        dst[ids] = p["x"][:, :n].T.astype(np.float64) / _val(coeff)
+        return N.FFMPM_OK
+
+    def ffmpm_debug_red_add4(self, dst, v, count, stream):
+        return N.FFMPM_OK
+
+
+class _Stream:
+    cuda_stream = 0
+
+    def __init__(self, *a, **k):
+        pass
+
+    def synchronize(self):
+        pass
+
+    def wait_event(self, ev):
+        pass
+
+
+class _Event:
+    def __init__(self, *a, **k):
+        pass
+
+    def record(self, *a):
+        pass
+
+    def synchronize(self):
+        pass
+
+
+def install(monkeypatch=None):
+    """Route femflow_b200 through FakeLib and make torch.cuda's stream / event / pinning calls no-ops.
+    With a pytest ``monkeypatch`` everything is undone at the end of the test; without one (spawned worker
+    processes) the patches last for the life of the process."""
+    import torch
+
+    def put(obj, name, value):
+        if monkeypatch is not None:
+            monkeypatch.setattr(obj, name, value, raising=False)
+        else:
+            setattr(obj, name, value)
+    fake = FakeLib()
+    put(N, "_lib", fake)
+    put(torch.cuda, "is_available", lambda: True)
+    put(torch.cuda, "current_device", lambda: 0)
+    put(torch.cuda, "set_device", lambda *a: None)
+    put(torch.cuda, "synchronize", lambda *a, **k: None)
+    put(torch.cuda, "current_stream", lambda *a, **k: _Stream())
+    put(torch.cuda, "Stream", _Stream)
+    put(torch.cuda, "Event", _Event)
+    put(torch.cuda, "device", lambda *a, **k: contextlib.nullcontext())
+    put(torch.cuda, "stream", lambda *a, **k: contextlib.nullcontext())
+    put(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    return fake
