@@ -7,7 +7,9 @@ ping-pong, id carrying, leaver extraction, migration payloads, slab rebuilds -- 
 round's single-GPU test box can never run the multi-GPU plumbing.  Test infrastructure only: it lives in tests/,
 nothing in femflow_b200/ can import it, and it is not a fallback (the product path raises without CUDA).
 
-3D, cubic global grids (the oracle's assumption); slabs are cut along x (cfg.origin[0], cfg.n[0]).
+3D; slabs are cut along x (cfg.origin[0], cfg.n[0]).  The oracle works on cubic grids, so a (res_x, res_y, res_z)
+domain is embedded in a cube of the largest extent for the particle phases, and the grid update -- whose walls sit at
+different indices per axis then -- is restated here for a box (identical to the oracle's on a cube: asserted in the test).
 """
 import contextlib
 import ctypes as C
@@ -182,14 +184,30 @@ class FakeLib:
         return _view(h.ws + h.grid_off, h.nodes * 4, _CT[h.es]).reshape(h.cfg.n[0], h.cfg.n[1], h.cfg.n[2], 4)
 
     def _embed(self, h):
-        """Local grid planes inside zeroed global oracle arrays."""
-        G = h.cfg.res[0] + 1
-        assert h.cfg.res[1] + 1 == G == h.cfg.res[2] + 1 and h.cfg.n[1] == G == h.cfg.n[2], "cubic global grids only"
-        g, o = self._grid(h), h.cfg.origin[0]
+        """Local grid planes inside zeroed cubic oracle arrays (side = the largest global extent + 1)."""
+        c = h.cfg
+        G = max(c.res[0], c.res[1], c.res[2]) + 1
+        g, o = self._grid(h), c.origin[0]
         gv, gm = np.zeros((G, G, G, 3)), np.zeros((G, G, G, 1))
-        gv[o:o + h.cfg.n[0]] = g[..., :3]
-        gm[o:o + h.cfg.n[0]] = g[..., 3:]
-        return gv, gm, slice(o, o + h.cfg.n[0])
+        gv[o:o + c.n[0], :c.n[1], :c.n[2]] = g[..., :3]
+        gm[o:o + c.n[0], :c.n[1], :c.n[2]] = g[..., 3:]
+        return gv, gm, (slice(o, o + c.n[0]), slice(0, c.n[1]), slice(0, c.n[2]))
+
+    @staticmethod
+    def box_grid_op(res, dx, dt, gravity, gv, gm):
+        """three_d/grid_op.py:5-47 on a (res_x, res_y, res_z) box: as oracle.grid_op_3d, walls per axis."""
+        m = gm[..., 0]
+        act = m > 0
+        gv[act] /= m[act][:, None]
+        gv[act, 1] += dt * gravity
+        va = dx * 0.9 / dt
+        gv[act] = np.clip(gv[act], -va, va)
+        for d in range(3):
+            idx = np.arange(gv.shape[d])
+            wall = (idx < 1) | (idx >= res[d] - 1)
+            sel = [slice(None)] * 3
+            sel[d] = wall
+            gv[tuple(sel) + (d,)] = 0
 
     def _inside(self, h, x):
         """Particles whose stencil stays inside the LOCAL grid (the kernels flag and skip the others)."""
@@ -237,9 +255,9 @@ class FakeLib:
             g[g.shape[0] - planes_hi:] += _view(_val(hi), planes_hi * plane, _CT[h.es]).reshape(planes_hi, *g.shape[1:])
         gv, gm, sl = self._embed(h)
         c = h.cfg
-        O.grid_op_3d(c.res[0], c.dx, c.dt, c.gravity, gv, gm)
+        self.box_grid_op(list(c.res), c.dx, c.dt, c.gravity, gv, gm)
         if h.colliders is not None:
-            O.check_collision_points(h.colliders[0], h.colliders[1], c.res[0], c.dx, gv)
+            O.check_collision_points(h.colliders[0], h.colliders[1], gv.shape[0] - 1, c.dx, gv)
         g[..., :3] = gv[sl]
         return N.FFMPM_OK
 
@@ -267,7 +285,7 @@ class FakeLib:
         x[ok], v[ok], F[ok], Cm[ok] = xo, vo, Fo, Co
         if h.st[1] is not None:
             # the reordering G2P: cell-sorted into the other buffer, out-of-grid particles last, planes carried along
-            G = h.cfg.res[0] + 1
+            G = gv.shape[0]
             key = np.where(ok, O.cell_keys(np.where(ok[:, None], base, 0), G), np.iinfo(np.int64).max)
             order = np.argsort(key, kind="stable")
             q = self._planes(h, h.live ^ 1)

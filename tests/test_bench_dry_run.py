@@ -174,3 +174,57 @@ def test_2d_workload_line(dry, capsys, monkeypatch):
     monkeypatch.setattr(bench, "make_scene", lambda w, seed=0, **k: scenes.elastic_block(2, 64, 16, 2, seed))
     d = run_bench(dry, capsys, "--steps", "5")
     assert set(d["roofline"]["phase_ms"]) == {"clear", "p2g", "grid_op", "g2p"} and d["e2e"]["value"] > 0
+
+
+def _two_rank_worker(rank, world, port, outdir):
+    """bench.main() as rank `rank` of `world`: gloo instead of NCCL, CPU tensors instead of CUDA ones, the stand-in
+    library (tests/fake_abi.py) instead of the .so -- the real bench.py, SlabSolver, CudaSlab and SlabDriver code."""
+    import io
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    import fake_abi
+    fake_abi.install()
+    torch.cuda.Event = FakeEvent
+    real_device, real_init = torch.device, dist.init_process_group
+
+    class CpuDevice:                                            # torch.device("cuda", i) -> the CPU
+        def __new__(cls, *a, **k):
+            return real_device("cpu")
+    torch.device = CpuDevice
+    dist.init_process_group = lambda backend=None, **k: real_init("gloo", rank=rank, world_size=world)
+    import femflow_b200.mpm as mpm
+    real_solver = mpm.MpmSolver
+    mpm.MpmSolver = lambda *a, **k: real_solver(*a, **{**k, "dtype": torch.float64})      # the stand-in's oracle arithmetic is fp64
+    import femflow_b200.distributed as D
+    real_slab_init = D.CudaSlab.__init__
+    D.CudaSlab.__init__ = lambda self, *a, **k: real_slab_init(self, *a, **{**k, "dtype": torch.float64})
+    import bench
+    sys.argv = ["bench.py", "--gpus", str(world), "--workload", "3d:32:8", "--steps", "5", "--warmup", "3", "--no-cpu-baseline",
+                "--e2e-steps", "1", "--margin", "2"]
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        bench.main()
+    with open(os.path.join(outdir, f"rank{rank}.txt"), "w") as f:
+        f.write(buf.getvalue())
+
+
+def test_two_rank_line(tmp_path):
+    """N = 2 as the driver launches it (one process per rank): rank 0 prints the one line, rank 1 nothing; the line
+    carries the whole-job aggregate and the slab bookkeeping."""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_two_rank_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    lines = [ln for ln in open(tmp_path / "rank0.txt").read().splitlines() if ln.strip()]
+    assert len(lines) == 1 and open(tmp_path / "rank1.txt").read().strip() == ""
+    d = json.loads(lines[0])
+    for k in CONTRACT:
+        assert k in d, k
+    n = d["config"]["particles_per_gpu"]
+    assert d["n_gpus"] == 2 and d["config"]["particles_total"] == 2 * n == sum(d["config"]["slab_particles"])
+    assert d["config"]["slab_cells"] == [[0, 32], [32, 63]] and d["config"]["rebalanced"] == 0
+    assert "2 slabs along x" in d["config"]["parallelism"] and d["scaling"] == "weak"
+    assert d["e2e"]["h2d_bytes_per_step"] == 2 * 24 * 8 * n and d["roofline"] is None and d["config"]["n_oob"] == 0

@@ -134,3 +134,14 @@ def test_headless_runner_on_the_stand_in(monkeypatch, tmp_path):
     assert np.isfinite(sim.displacements[-1]).all()
     y0, y3 = sim.displacements[0][1::3], sim.displacements[3][1::3]
     assert (y3 < y0).mean() > 0.99                                  # everything is falling
+
+
+def test_stand_in_grid_update_equals_the_oracle_on_a_cube():
+    rng = np.random.default_rng(2)
+    res, G = 10, 11
+    gm = np.where(rng.random((G, G, G, 1)) < 0.5, rng.uniform(0.1, 2, (G, G, G, 1)), 0.0)
+    gv = rng.normal(0, 20, (G, G, G, 3)) * (gm > 0)
+    a, b = gv.copy(), gv.copy()
+    O.grid_op_3d(res, 0.1, 2e-3, -9.8, a, gm.copy())
+    fake_abi.FakeLib.box_grid_op([res] * 3, 0.1, 2e-3, -9.8, b, gm.copy())
+    assert np.array_equal(a, b)
