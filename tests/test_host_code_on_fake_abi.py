@@ -145,3 +145,29 @@ def test_stand_in_grid_update_equals_the_oracle_on_a_cube():
     O.grid_op_3d(res, 0.1, 2e-3, -9.8, a, gm.copy())
     fake_abi.FakeLib.box_grid_op([res] * 3, 0.1, 2e-3, -9.8, b, gm.copy())
     assert np.array_equal(a, b)
+
+
+@pytest.fixture
+def gpu_test_bodies(monkeypatch):
+    """The bodies of GPU parity tests, run on the stand-in library in fp64: what they exercise here is the
+    reference-signature wrappers' marshalling (typed lists / SoA, caller-owned grids in the reference's two-array
+    layout, in-place updates, the error convention) against the goldens of the real reference."""
+    fake_abi.install(monkeypatch)
+    import test_gpu_parity as TP
+    from femflow_b200.solvers.mpm import _runtime
+    import femflow_b200.mpm as mpm
+    monkeypatch.setattr(_runtime, "_default_dtype", torch.float64)
+    monkeypatch.setattr(_runtime, "MpmSolver", lambda *a, **k: mpm.MpmSolver(*a, device="cpu", **k))
+    _runtime.clear_cache()
+    yield TP
+    _runtime.clear_cache()
+
+
+@pytest.mark.parametrize("name", ["kat3d", "block3d", "rest3d", "walls3d"])
+def test_phase_wrappers_against_reference_goldens(gpu_test_bodies, name):
+    gpu_test_bodies.test_3d_phase_functions_match_reference(name, "float64")
+
+
+def test_solve_wrapper_on_the_paper_scene_and_error_convention(gpu_test_bodies):
+    gpu_test_bodies.test_solve_mls_mpm_3d_c1_scene("auto", "float64")
+    gpu_test_bodies.test_oob_raises_runtime_error("float64")
