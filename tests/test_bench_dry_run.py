@@ -228,3 +228,23 @@ def test_two_rank_line(tmp_path):
     assert d["config"]["slab_cells"] == [[0, 32], [32, 63]] and d["config"]["rebalanced"] == 0
     assert "2 slabs along x" in d["config"]["parallelism"] and d["scaling"] == "weak"
     assert d["e2e"]["h2d_bytes_per_step"] == 2 * 24 * 8 * n and d["roofline"] is None and d["config"]["n_oob"] == 0
+
+
+def test_cpu_baseline_leg_and_reference_arm(dry, capsys, monkeypatch):
+    """The two places bench.py may execute oracle/: the cpu_baseline leg of the default run (real C port, tiny
+    budget here) and `--impl reference`."""
+    import bench
+    from oracle import native as onative
+    real = onative.time_sample
+    monkeypatch.setattr(onative, "time_sample", lambda scene, budget_s=15.0, threads=None: real(scene, budget_s=0.2, threads=threads))
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--workload", "3d:32:8", "--steps", "5", "--e2e-steps", "1"])
+    bench.main()
+    d = json.loads([ln for ln in capsys.readouterr().out.splitlines() if ln.strip()][0])
+    c = d["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and "particles of the workload" in c["sample"]
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--workload", "3d:32:8", "--impl", "reference", "--steps", "2", "--warmup", "1"])
+    bench.main()
+    r = json.loads([ln for ln in capsys.readouterr().out.splitlines() if ln.strip()][0])
+    assert r["impl"] == "reference" and r["gpu_launches"] == 0 and r["value"] > 0 and r["metric"] == d["metric"]
+    assert r["e2e"] == {"value": r["value"], "unit": r["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert r["cpu_baseline"]["kind"] == "port" and r["config"]["workload"] == d["config"]["workload"]
