@@ -171,3 +171,15 @@ def test_phase_wrappers_against_reference_goldens(gpu_test_bodies, name):
 def test_solve_wrapper_on_the_paper_scene_and_error_convention(gpu_test_bodies):
     gpu_test_bodies.test_solve_mls_mpm_3d_c1_scene("auto", "float64")
     gpu_test_bodies.test_oob_raises_runtime_error("float64")
+
+
+def test_graft_entry_smoke_body(monkeypatch, capsys):
+    """__graft_entry__.smoke() -- the call the driver makes on the GPU box before the bench -- on the stand-in
+    library (fp32 storage): its own code path, comparison and tolerance."""
+    fake_abi.install(monkeypatch)
+    import femflow_b200.mpm as mpm
+    real = mpm.MpmSolver
+    monkeypatch.setattr(mpm, "MpmSolver", lambda *a, **k: real(*a, **{**k, "device": "cpu"}))
+    import __graft_entry__ as entry
+    entry.smoke()
+    assert "max-norm relative errors vs oracle" in capsys.readouterr().out
