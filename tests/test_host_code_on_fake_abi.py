@@ -183,3 +183,48 @@ def test_graft_entry_smoke_body(monkeypatch, capsys):
     import __graft_entry__ as entry
     entry.smoke()
     assert "max-norm relative errors vs oracle" in capsys.readouterr().out
+
+
+def test_solver_reuse_across_particle_counts_and_material_layouts(monkeypatch):
+    """One MpmSolver / one cached wrapper solver fed, in turn, three materials, one material, 300 materials, fewer and
+    then more particles than before, and none at all: every re-upload rebinds cleanly (no stale rows, planes or ids)."""
+    fake_abi.install(monkeypatch)
+    from femflow_b200.mpm import MpmSolver
+    p, _ = scene()
+    s = MpmSolver(3, p["res"], p["dt"], p["volume"], p["gravity"], p["hardening"], capacity=900, dtype=torch.float64, device="cpu")
+    for n, nmat, layout in ((600, 3, "table[3]"), (250, 1, "table[1]"), (900, 300, "planes"), (400, 2, "table[2]"), (0, 1, "table[1]")):
+        _, (x, v, F, C, mass, mu0, lam0) = scene(n=n, seed=n + nmat, nmat=nmat)
+        s.set_particles(x, v, F, C, None, mass, mu0, lam0)
+        assert s.material_layout == layout and s.num_particles == n
+        s.substep(2)
+        s.check_errors()
+        out = s.get_particles()
+        Jp = np.ones((n, 1))
+        for _ in range(2):
+            O.solve_mls_mpm_3d(p["res"], p["inv_dx"], p["hardening"], p["dx"], p["dt"], p["volume"], p["gravity"],
+                               x, mass, mu0, lam0, v, F, C, Jp)
+        assert out["x"].shape == (n, 3) and out["F"].shape == (n, 3, 3)
+        if n:
+            assert np.abs(out["x"].numpy() - x).max() < 1e-12 and np.abs(out["C"].numpy() - C).max() < 1e-9, (n, nmat)
+    s.close()
+    # the wrapper's solver cache: capacity grows, then is reused for a smaller call
+    from femflow_b200.solvers.mpm import _runtime
+    from femflow_b200.solvers.mpm.mls_mpm import make_mls_mpm_coefficients, solve_mls_mpm_3d
+    from femflow_b200.solvers.mpm.particle import ParticleArray
+    import femflow_b200.mpm as mpm
+    monkeypatch.setattr(_runtime, "_default_dtype", torch.float64)
+    monkeypatch.setattr(_runtime, "MpmSolver", lambda *a, **k: mpm.MpmSolver(*a, device="cpu", **k))
+    _runtime.clear_cache()
+    made = []
+    for n in (100, 3000, 50):
+        _, (x, v0, F0, C0, mass, mu0, lam0) = scene(n=n, seed=n)
+        particles = ParticleArray(x.copy(), mass, lam0, mu0)
+        v, F, C, Jp = make_mls_mpm_coefficients(n, 3)
+        v[:] = v0; F[:] = F0; C[:] = C0
+        solve_mls_mpm_3d(p["res"], p["inv_dx"], p["hardening"], p["dx"], p["dt"], p["volume"], p["gravity"], particles, v, F, C, Jp)
+        O.solve_mls_mpm_3d(p["res"], p["inv_dx"], p["hardening"], p["dx"], p["dt"], p["volume"], p["gravity"],
+                           x, mass, mu0, lam0, v0, F0, C0, np.ones((n, 1)))
+        assert np.abs(particles.pos - x).max() < 1e-12 and np.abs(v - v0).max() < 1e-11
+        made.append(id(next(iter(_runtime._cache.values()))))
+    assert len(_runtime._cache) == 1 and made[0] != made[1] and made[1] == made[2]
+    _runtime.clear_cache()
