@@ -68,8 +68,6 @@ class FakeLib:
 
     def ffmpm_create(self, cfg_ref, device, out_ref):
         cfg = cfg_ref._obj
-        if cfg.dim != 3:
-            return self._fail(N.FFMPM_E_INVALID, "the CPU stand-in is 3D only")
         h = _Handle()
         h.cfg = N.FfMpmConfig.from_buffer_copy(cfg)
         h.ws = None
@@ -163,8 +161,8 @@ class FakeLib:
     # -- state access -----------------------------------------------------------------------------
     def _planes(self, h, which):
         """SoA planes of buffer `which` as NumPy views onto the caller's memory."""
-        s, ct, st = h.st[which], _CT[h.es], h.st[which].stride
-        out = {k: _view(getattr(s, k), rows * st, ct).reshape(rows, st) for k, rows in (("x", 3), ("v", 3), ("C", 9), ("F", 9))}
+        s, ct, st, d = h.st[which], _CT[h.es], h.st[which].stride, h.cfg.dim
+        out = {k: _view(getattr(s, k), rows * st, ct).reshape(rows, st) for k, rows in (("x", d), ("v", d), ("C", d * d), ("F", d * d))}
         for k in ("mass", "mu0", "lam0", "Jp"):
             out[k] = _view(getattr(s, k), st, ct)
         out["id"] = _view(s.id, st, C.c_int32)
@@ -229,6 +227,8 @@ class FakeLib:
         h.launches += 1
         if h.n == 0:
             return N.FFMPM_OK
+        if h.cfg.dim == 2:
+            return self._p2g_2d(h)
         p, n = self._planes(h, h.live), h.n
         x = p["x"][:, :n].T.astype(np.float64)
         ok, _ = self._inside(h, x)
@@ -236,16 +236,54 @@ class FakeLib:
         mass, mu, lam = (a[ok] for a in self._materials(h, p, n))
         gv, gm, sl = self._embed(h)
         c = h.cfg
+        jp = p["Jp"][:n].astype(np.float64)[ok].reshape(-1, 1) if p["Jp"] is not None else np.ones((int(ok.sum()), 1))
         O.p2g_3d(c.inv_dx, c.hardening, c.dx, c.dt, c.volume, gv, gm, x[ok], mass, mu, lam, p["v"][:, :n].T.astype(np.float64)[ok],
                  p["F"][:, :n].T.reshape(n, 3, 3).astype(np.float64)[ok], p["C"][:, :n].T.reshape(n, 3, 3).astype(np.float64)[ok],
-                 np.ones((int(ok.sum()), 1)))
+                 jp, "snow" if c.model == N.FFMPM_SNOW else "neo_hookean")
         g = self._grid(h)
         g[..., :3], g[..., 3:] = gv[sl], gm[sl]
+        return N.FFMPM_OK
+
+    # -- 2D (two_d/{p2g,grid_op,g2p}.py): grid nodes are {mom_x, mom_y, mass, -}, no slabs, no reordering ---------
+    def _state_2d(self, h):
+        p, n = self._planes(h, h.live), h.n
+        return (p, n, p["x"][:, :n].T.astype(np.float64), p["v"][:, :n].T.astype(np.float64),
+                p["F"][:, :n].T.reshape(n, 2, 2).astype(np.float64), p["C"][:, :n].T.reshape(n, 2, 2).astype(np.float64),
+                p["Jp"][:n].astype(np.float64).reshape(n, 1))
+
+    def _p2g_2d(self, h):
+        c, g = h.cfg, self._grid(h)
+        p, n, x, v, F, Cm, Jp = self._state_2d(h)
+        base, _ = O.base_and_fx(x, c.inv_dx)
+        ok = (base >= 0).all(1) & (base + 2 < np.array([c.n[0], c.n[1]])).all(1)
+        h.n_oob += int((~ok).sum())
+        gv, gm = g[:, :, 0, :2].astype(np.float64), g[:, :, 0, 2:3].astype(np.float64)
+        O.p2g_2d(c.inv_dx, c.hardening, c.mu_0, c.lambda_0, c.mass, c.dx, c.dt, c.volume, gv, gm, x[ok], v[ok], F[ok], Cm[ok], Jp[ok],
+                 "snow" if c.model == N.FFMPM_SNOW else "neo_hookean")
+        g[:, :, 0, :2], g[:, :, 0, 2:3] = gv, gm
+        return N.FFMPM_OK
+
+    def _grid_op_2d(self, h):
+        c, g = h.cfg, self._grid(h)
+        gv, gm = g[:, :, 0, :2].astype(np.float64), g[:, :, 0, 2:3].astype(np.float64)
+        O.grid_op_2d(c.res[0], c.dt, c.gravity, gv, gm)
+        g[:, :, 0, :2] = gv
+        return N.FFMPM_OK
+
+    def _g2p_2d(self, h):
+        c, g = h.cfg, self._grid(h)
+        p, n, x, v, F, Cm, Jp = self._state_2d(h)
+        O.g2p_2d(c.inv_dx, c.dt, g[:, :, 0, :2].astype(np.float64), x, v, F, Cm, Jp, "snow" if c.model == N.FFMPM_SNOW else "neo_hookean")
+        p["x"][:, :n], p["v"][:, :n] = x.T, v.T
+        p["F"][:, :n], p["C"][:, :n] = F.reshape(n, 4).T, Cm.reshape(n, 4).T
+        p["Jp"][:n] = Jp[:, 0]
         return N.FFMPM_OK
 
     def ffmpm_grid_op_halo(self, h, lo, planes_lo, hi, planes_hi, stream):
         h = self._h(h)
         h.launches += 1
+        if h.cfg.dim == 2:
+            return self._grid_op_2d(h)
         g = self._grid(h)
         plane = h.cfg.n[1] * h.cfg.n[2] * 4
         planes_lo, planes_hi = int(_val(planes_lo) or 0), int(_val(planes_hi) or 0)
@@ -272,6 +310,10 @@ class FakeLib:
         h.launches += 1
         if h.n == 0:
             return N.FFMPM_OK
+        if h.cfg.dim == 2:
+            return self._g2p_2d(h)
+        if h.cfg.model == N.FFMPM_SNOW:
+            return self._fail(N.FFMPM_E_INVALID, "3D snow G2P is not reproducible")
         p, n = self._planes(h, h.live), h.n
         x = p["x"][:, :n].T.astype(np.float64)
         v = p["v"][:, :n].T.astype(np.float64)

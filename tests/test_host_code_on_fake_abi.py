@@ -228,3 +228,14 @@ def test_solver_reuse_across_particle_counts_and_material_layouts(monkeypatch):
         made.append(id(next(iter(_runtime._cache.values()))))
     assert len(_runtime._cache) == 1 and made[0] != made[1] and made[1] == made[2]
     _runtime.clear_cache()
+
+
+@pytest.mark.parametrize("name", ["test2d", "block2d"])
+def test_2d_wrappers_against_reference_goldens(gpu_test_bodies, name):
+    gpu_test_bodies.test_2d_phase_functions_match_reference(name, "float64")
+
+
+def test_2d_snow_quirk_and_3d_snow_wrappers(gpu_test_bodies):
+    gpu_test_bodies.test_2d_snow_matches_reference("float64")
+    gpu_test_bodies.test_2d_svd_roundtrip_quirk("float64")
+    gpu_test_bodies.test_snow_p2g_3d("float64")
