@@ -52,9 +52,15 @@ struct Mat3x2 {
 
 // `load_C()` fetches the two APIC matrices only when the series is done: they are needed for the last nine
 // FFMA2s, and holding 18 more registers through the series is what makes the packed phase 1 spill.
+//
+// `economised` (cfg.fp32_stress == 2, FFMPM_FP32_STRESS=2): q = M / G is not the truncated Taylor series but its
+// Chebyshev interpolant on the tier's interval [-r_t, r_t] (scripts/series_economized.py prints the table below):
+// the same 1e-7 bar with q of degree 2 / 3 / 4 / 5 / 6 for ||G||_F < 0.007 / 0.025 / 0.069 / 0.109 / 0.15 instead of
+// 2 / 4 / 7 for 0.005 / 0.04 / 0.15 -- at the headline workload's strain (warp maximum ~ 0.08) five matrix
+// products instead of seven.  Evaluated in fp32 both forms sit at ~2e-7 (rounding, not truncation).
 template <typename LoadC>
 FFMPM_HD bool fixed_corotated_affine3_f32x2(const Mat3x2& F, LoadC load_C, F2 mu, F2 lam, F2 mass, float dt_vol_dinv,
-                                            Mat3x2& A) {
+                                            Mat3x2& A, bool economised = false) {
   const F2 neg1 = f2(-1.0f), two = f2(2.0f);
   Mat3x2 E = F;
   E.a00 = f2_add(F.a00, neg1); E.a11 = f2_add(F.a11, neg1); E.a22 = f2_add(F.a22, neg1);
@@ -70,12 +76,27 @@ FFMPM_HD bool fixed_corotated_affine3_f32x2(const Mat3x2& F, LoadC load_C, F2 mu
   const F2 r2p = f2_fma(two, o2, d2);
   const float r2 = fmaxf(r2p.v.x, r2p.v.y);
   if (!(r2 < kPerturbationMaxR * kPerturbationMaxR)) return false;      // also catches NaN in either half
-  const float c[8] = {0.5f, -0.375f, 0.3125f, -0.2734375f, 0.24609375f, -0.2255859375f, 0.20947265625f,
-                      -0.196380615234375f};
-  float ca = c[7], cb = c[6];
+  // c[0 .. top]: the coefficients the Horner steps add, ca / cb: the two highest (q starts as ca G + cb)
+  float c[6] = {0.5f, -0.375f, 0.3125f, -0.2734375f, 0.24609375f, -0.2255859375f};
+  float ca = -0.196380615234375f, cb = 0.20947265625f;
   int top = 5;
-  if (r2 < 0.005f * 0.005f) { ca = c[2]; cb = c[1]; top = 0; }
-  else if (r2 < 0.04f * 0.04f) { ca = c[4]; cb = c[3]; top = 2; }
+  if (!economised) {
+    if (r2 < 0.005f * 0.005f) { ca = c[2]; cb = c[1]; top = 0; }
+    else if (r2 < 0.04f * 0.04f) { ca = c[4]; cb = c[3]; top = 2; }
+  } else if (r2 < 0.007f * 0.007f) {        // kEcon tier 0: q of degree 2
+    c[0] = 0.5f; cb = -0.37501004338264465f; ca = 0.31250903010368347f; top = 0;
+  } else if (r2 < 0.025f * 0.025f) {        // tier 1: degree 3
+    c[0] = 0.5f; c[1] = -0.375f; cb = 0.31265386939048767f; ca = -0.27357855439186096f; top = 1;
+  } else if (r2 < 0.069f * 0.069f) {        // tier 2: degree 4
+    c[0] = 0.5f; c[1] = -0.37499839067459106f; c[2] = 0.3124985098838806f; cb = -0.2747856080532074f; ca = 0.24734565615653992f;
+    top = 2;
+  } else if (r2 < 0.109f * 0.109f) {        // tier 3: degree 5
+    c[0] = 0.5f; c[1] = -0.375f; c[2] = 0.3124831020832062f; c[3] = -0.27342167496681213f; cb = 0.24987153708934784f;
+    ca = -0.2291281670331955f; top = 3;
+  } else {                                  // tier 4: degree 6, up to kPerturbationMaxR
+    c[0] = 0.5f; c[1] = -0.3750002682209015f; c[2] = 0.3125002384185791f; c[3] = -0.2733475863933563f;
+    c[4] = 0.24600879848003387f; cb = -0.2335180640220642f; ca = 0.2169661521911621f; top = 4;
+  }
   const F2 ca2 = f2(ca), cb2 = f2(cb);
   Sym3x2 q;
   q.xx = f2_fma(ca2, G.xx, cb2); q.yy = f2_fma(ca2, G.yy, cb2); q.zz = f2_fma(ca2, G.zz, cb2);
@@ -188,7 +209,8 @@ FFMPM_HD void p2g_prepare3_pair_sink(const DevCfg& cfg, GetA ga, GetB gb, bool h
       // heads are parked first (a declined pair parks everything again through the one-particle routine)
       sink.head(0, qa);
       sink.head(1, qb);
-      packed = fixed_corotated_affine3_f32x2(F, load_C, f2(mu_a, mu_b), f2(lam_a, lam_b), f2(mass_a, mass_b), (float)k, A);
+      packed = fixed_corotated_affine3_f32x2(F, load_C, f2(mu_a, mu_b), f2(lam_a, lam_b), f2(mass_a, mass_b), (float)k, A,
+                                             cfg.fp32_stress == 2);
       if (packed) {
         sink.affine(A);
         return;

@@ -1,0 +1,67 @@
+"""Economised series for the fp32 stress: M = I - (I+G)^(-1/2) = G q(G), with q fitted on [-r_t, r_t] by Chebyshev
+interpolation (near-minimax) instead of truncating its Taylor series.  For the same 1e-7 bar the degree drops from
+7 to 5 at the strain of the headline workload (warp maximum ||G||_F ~ 0.08) and to 4 below 0.069: two / three
+matrix products fewer out of seven.  Prints the tier table that mpm_p2g_pair.cuh embeds (kEcon*); the CPU suite
+regenerates it and compares (tests/test_kernel_math_host.py).
+
+Tiers are chosen so that the uniform error of q on the tier's interval, WITH the coefficients rounded to fp32,
+stays below 5e-8 (relative 1e-7 on M, whose leading coefficient is 1/2)."""
+import numpy as np
+from numpy.polynomial import chebyshev as Ch, polynomial as P
+
+# (upper bound of ||G||_F for the tier, degree of q)
+TIERS = ((0.007, 2), (0.025, 3), (0.069, 4), (0.109, 5), (0.15, 6))
+
+
+def q_exact(x):
+    x = np.asarray(x, dtype=np.float64)
+    out = np.full_like(x, 0.5)
+    nz = np.abs(x) > 1e-9
+    out[nz] = (1 - (1 + x[nz]) ** -0.5) / x[nz]
+    return out
+
+
+def coefficients(r, deg):
+    """Power-basis coefficients (c_0 .. c_deg, as float32) of the Chebyshev interpolant of q on [-r, r]."""
+    c = Ch.chebinterpolate(lambda t: q_exact(t * r), deg)
+    return (Ch.cheb2poly(c) / r ** np.arange(deg + 1)).astype(np.float32)
+
+
+def table():
+    return [(r, deg, coefficients(r, deg)) for r, deg in TIERS]
+
+
+def uniform_error(r, coeffs):
+    xs = np.linspace(-r, r, 20001)
+    return float(np.max(np.abs(P.polyval(xs, coeffs.astype(np.float64)) - q_exact(xs))) / 0.5)
+
+
+def worst_matrix_error(r, coeffs, n=1500, seed=0):
+    """As scripts/series_degree.py: symmetric G of Frobenius norm r (every third one rank one: spectral radius = r),
+    Horner in float32 as the kernel evaluates it, against an eigendecomposition."""
+    rng = np.random.default_rng(seed)
+    worst = 0.0
+    for t in range(n):
+        a = rng.uniform(-1, 1, (3, 3))
+        g = (a + a.T) / 2
+        if t % 3 == 0:
+            v = rng.normal(size=3)
+            v /= np.linalg.norm(v)
+            g = np.outer(v, v) * rng.choice([-1, 1])
+        g = g / np.linalg.norm(g) * r
+        w, q = np.linalg.eigh(g)
+        exact = q @ np.diag(1 - 1 / np.sqrt(1 + w)) @ q.T
+        g32 = g.astype(np.float32)
+        acc = coeffs[-1] * g32 + coeffs[-2] * np.eye(3, dtype=np.float32)
+        for c in coeffs[-3::-1]:
+            acc = (g32 @ acc).astype(np.float32) + c * np.eye(3, dtype=np.float32)
+        series = (g32 @ acc).astype(np.float64)
+        worst = max(worst, np.abs(series - exact).max() / np.abs(exact).max())
+    return worst
+
+
+if __name__ == "__main__":
+    for r, deg, c in table():
+        print(f"// ||G||_F < {r}: q of degree {deg}; uniform error {uniform_error(r, c):.1e}, "
+              f"worst matrix error in fp32 {worst_matrix_error(r, c, 600):.1e}")
+        print("  {" + ", ".join(f"{float(v)!r}f" for v in c) + "},")

@@ -300,12 +300,14 @@ def prepare3_pair(km, res, x, v, Cm, F, mass, mu, lam, dt, volume, hardening=1.0
     return base, fx, aff.reshape(n, 3, 3), mv, m, ok.astype(bool)
 
 
-@pytest.mark.parametrize("strain", [0.0, 1e-6, 1e-4, 1.5e-3, 1e-2, 4e-2, 0.3, "mixed"])
-def test_packed_fp32_stress_pairs(km, strain):
+@pytest.mark.parametrize("series", [1, 2])
+@pytest.mark.parametrize("strain", [0.0, 1e-6, 1e-4, 1.5e-3, 4e-3, 1e-2, 2.5e-2, 4e-2, 6e-2, 0.3, "mixed"])
+def test_packed_fp32_stress_pairs(km, strain, series):
     """p2g_prepare3_pair (FFMPM_P2G_VARIANT=8/9): the stress of two particles per packed instruction.  Same
     1e-5 bar against LAPACK as the one-particle path on every series tier; a pair with one particle beyond
     the series, outside the grid or NaN falls back to the one-particle routine for both; index, weights
-    offset and mass*v are the one-particle routine's bits."""
+    offset and mass*v are the one-particle routine's bits.  series = 2: the economised coefficient tiers
+    (FFMPM_FP32_STRESS=2; strains chosen to land in each of its five tiers)."""
     rng = np.random.default_rng(13)
     res, n = 32, 4001                                            # odd: the last particle has no partner
     dx = 1.0 / res
@@ -321,7 +323,7 @@ def test_packed_fp32_stress_pairs(km, strain):
     Cm = f32(rng.normal(0, 0.05, size=(n, 3, 3))) if strain == "mixed" else np.zeros((n, 3, 3))
     mass = f32(rng.uniform(0.5, 1.5, n) * vol); mu = f32(rng.uniform(3000, 5000, n)); lam = f32(rng.uniform(2000, 3000, n))
     ref = prepare3(km, "f32", res, x, v, Cm, F, mass, mu, lam, 1e-4, vol)
-    got = prepare3_pair(km, res, x, v, Cm, F, mass, mu, lam, 1e-4, vol)
+    got = prepare3_pair(km, res, x, v, Cm, F, mass, mu, lam, 1e-4, vol, fp32_stress=series)
     ok = ref[5]
     assert np.array_equal(got[5], ok)
     if strain == "mixed":
@@ -488,3 +490,27 @@ def test_packed_p2g_window_end_to_end_against_the_oracle(km):
     grid = grid.reshape(G, G, G, 4)
     assert np.abs(grid[..., 3:] - gm).max() <= 1e-5 * np.abs(gm).max()
     assert np.abs(grid[..., :3] - gv).max() <= 1e-5 * np.abs(gv).max()
+
+
+def test_economised_series_table_is_the_generated_one():
+    """The coefficient tiers embedded in mpm_p2g_pair.cuh are what scripts/series_economized.py generates, each tier
+    keeps q within 5e-8 of (1 - (1+x)^(-1/2)) / x on its interval with fp32 coefficients, and evaluated in fp32 on
+    matrices at the tier's upper bound it is no worse than the Taylor tiers the scalar path uses (~2e-7, rounding)."""
+    import re
+    import sys
+    root = os.path.dirname(HERE)
+    sys.path.insert(0, os.path.join(root, "scripts"))
+    import series_economized as E
+    src = open(os.path.join(CSRC, "mpm_p2g_pair.cuh")).read()
+    body = src[src.index("} else if (r2 < 0.007f * 0.007f)"):src.index("const F2 ca2 = f2(ca), cb2 = f2(cb);")]
+    bounds = [float(v) for v in re.findall(r"r2 < ([0-9.]+)f \* [0-9.]+f", body)] + [0.15]
+    assert bounds == [r for r, _ in E.TIERS]
+    blocks = re.split(r"\} else", body)
+    assert len(blocks) == len(E.TIERS) + 1
+    for (r, deg, coef), block in zip(E.table(), blocks[1:]):
+        vals = {k: float(v) for k, v in re.findall(r"(c\[\d\]|ca|cb) = (-?[0-9.e-]+)f;", block)}
+        mine = [vals[f"c[{i}]"] for i in range(deg - 1)] + [vals["cb"], vals["ca"]]
+        assert np.array_equal(np.float32(mine), coef), r
+        assert int(re.search(r"top = (\d);", block).group(1)) == deg - 2
+        assert E.uniform_error(r, coef) < 5.05e-8
+        assert E.worst_matrix_error(r, coef, n=300) < 3e-7
