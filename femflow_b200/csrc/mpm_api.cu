@@ -157,8 +157,9 @@ int ffmpm_create(const FfMpmConfig* cfg, int32_t device, FfMpmHandle** out) {
   d.own_lo = INT32_MIN;   // single domain: nobody leaves
   d.own_hi = INT32_MAX;
   d.fp32_stress = 1;
-  // 0: fp64 stress always; 1: fp32 perturbation series; 2: ... with economised coefficients in the packed variants
-  if (const char* e = getenv("FFMPM_FP32_STRESS")) { const int v = atoi(e); d.fp32_stress = v == 2 ? 2 : (v != 0); }
+  // 0: fp64 stress always; 1: fp32 perturbation series; packed variants only: 2 = economised coefficients,
+  // 3 = the left form h(F F^T - I) with economised coefficients (no products with F)
+  if (const char* e = getenv("FFMPM_FP32_STRESS")) { const int v = atoi(e); d.fp32_stress = (v == 2 || v == 3) ? v : (v != 0); }
   h->n_nodes = (int64_t)d.n[0] * d.n[1] * d.n[2];
   h->overlap = 1;
   if (const char* e = getenv("FFMPM_OVERLAP")) h->overlap = atoi(e) != 0;

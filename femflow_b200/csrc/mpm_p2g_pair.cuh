@@ -58,19 +58,35 @@ struct Mat3x2 {
 // the same 1e-7 bar with q of degree 2 / 3 / 4 / 5 / 6 for ||G||_F < 0.007 / 0.025 / 0.069 / 0.109 / 0.15 instead of
 // 2 / 4 / 7 for 0.005 / 0.04 / 0.15 -- at the headline workload's strain (warp maximum ~ 0.08) five matrix
 // products instead of seven.  Evaluated in fp32 both forms sit at ~2e-7 (rounding, not truncation).
+//
+// `form` 3 (FFMPM_FP32_STRESS=3), the LEFT form: with F = V R (V = (F F^T)^(1/2)), (F - R) F^T = F F^T - V, i.e. the
+// stress term is the matrix function  h(G_B) = (I + G_B) - (I + G_B)^(1/2) = G_B p(G_B)  of the left Cauchy-Green
+// strain G_B = F F^T - I = E + E^T + E E^T alone: no product with F afterwards (45 multiply-adds saved), and
+// p(x) = (1 + x - sqrt(1 + x)) / x converges faster than q: degree 2 / 3 / 4 / 5 below 0.0136 / 0.0436 / 0.112 / 0.15
+// -- four symmetric matrix products in all at the headline strain, against seven plus the two products with F.
 template <typename LoadC>
 FFMPM_HD bool fixed_corotated_affine3_f32x2(const Mat3x2& F, LoadC load_C, F2 mu, F2 lam, F2 mass, float dt_vol_dinv,
-                                            Mat3x2& A, bool economised = false) {
+                                            Mat3x2& A, int form = 1) {
+  const bool economised = form == 2, left = form == 3;
   const F2 neg1 = f2(-1.0f), two = f2(2.0f);
   Mat3x2 E = F;
   E.a00 = f2_add(F.a00, neg1); E.a11 = f2_add(F.a11, neg1); E.a22 = f2_add(F.a22, neg1);
   Sym3x2 G;
-  G.xx = f2_fma(two, E.a00, f2_fma(E.a20, E.a20, f2_fma(E.a10, E.a10, f2_mul(E.a00, E.a00))));
-  G.yy = f2_fma(two, E.a11, f2_fma(E.a21, E.a21, f2_fma(E.a11, E.a11, f2_mul(E.a01, E.a01))));
-  G.zz = f2_fma(two, E.a22, f2_fma(E.a22, E.a22, f2_fma(E.a12, E.a12, f2_mul(E.a02, E.a02))));
-  G.xy = f2_add(f2_add(E.a01, E.a10), f2_fma(E.a20, E.a21, f2_fma(E.a10, E.a11, f2_mul(E.a00, E.a01))));
-  G.xz = f2_add(f2_add(E.a02, E.a20), f2_fma(E.a20, E.a22, f2_fma(E.a10, E.a12, f2_mul(E.a00, E.a02))));
-  G.yz = f2_add(f2_add(E.a12, E.a21), f2_fma(E.a21, E.a22, f2_fma(E.a11, E.a12, f2_mul(E.a01, E.a02))));
+  if (!left) {     // G = F^T F - I = E + E^T + E^T E
+    G.xx = f2_fma(two, E.a00, f2_fma(E.a20, E.a20, f2_fma(E.a10, E.a10, f2_mul(E.a00, E.a00))));
+    G.yy = f2_fma(two, E.a11, f2_fma(E.a21, E.a21, f2_fma(E.a11, E.a11, f2_mul(E.a01, E.a01))));
+    G.zz = f2_fma(two, E.a22, f2_fma(E.a22, E.a22, f2_fma(E.a12, E.a12, f2_mul(E.a02, E.a02))));
+    G.xy = f2_add(f2_add(E.a01, E.a10), f2_fma(E.a20, E.a21, f2_fma(E.a10, E.a11, f2_mul(E.a00, E.a01))));
+    G.xz = f2_add(f2_add(E.a02, E.a20), f2_fma(E.a20, E.a22, f2_fma(E.a10, E.a12, f2_mul(E.a00, E.a02))));
+    G.yz = f2_add(f2_add(E.a12, E.a21), f2_fma(E.a21, E.a22, f2_fma(E.a11, E.a12, f2_mul(E.a01, E.a02))));
+  } else {         // G_B = F F^T - I = E + E^T + E E^T
+    G.xx = f2_fma(two, E.a00, f2_fma(E.a02, E.a02, f2_fma(E.a01, E.a01, f2_mul(E.a00, E.a00))));
+    G.yy = f2_fma(two, E.a11, f2_fma(E.a12, E.a12, f2_fma(E.a11, E.a11, f2_mul(E.a10, E.a10))));
+    G.zz = f2_fma(two, E.a22, f2_fma(E.a22, E.a22, f2_fma(E.a21, E.a21, f2_mul(E.a20, E.a20))));
+    G.xy = f2_add(f2_add(E.a01, E.a10), f2_fma(E.a02, E.a12, f2_fma(E.a01, E.a11, f2_mul(E.a00, E.a10))));
+    G.xz = f2_add(f2_add(E.a02, E.a20), f2_fma(E.a02, E.a22, f2_fma(E.a01, E.a21, f2_mul(E.a00, E.a20))));
+    G.yz = f2_add(f2_add(E.a12, E.a21), f2_fma(E.a12, E.a22, f2_fma(E.a11, E.a21, f2_mul(E.a10, E.a20))));
+  }
   const F2 d2 = f2_fma(G.zz, G.zz, f2_fma(G.yy, G.yy, f2_mul(G.xx, G.xx)));
   const F2 o2 = f2_fma(G.yz, G.yz, f2_fma(G.xz, G.xz, f2_mul(G.xy, G.xy)));
   const F2 r2p = f2_fma(two, o2, d2);
@@ -80,7 +96,19 @@ FFMPM_HD bool fixed_corotated_affine3_f32x2(const Mat3x2& F, LoadC load_C, F2 mu
   float c[6] = {0.5f, -0.375f, 0.3125f, -0.2734375f, 0.24609375f, -0.2255859375f};
   float ca = -0.196380615234375f, cb = 0.20947265625f;
   int top = 5;
-  if (!economised) {
+  if (left) {                               // p(x) = (1 + x - sqrt(1 + x)) / x, economised per tier
+    if (r2 < 0.0136f * 0.0136f) {
+      c[0] = 0.5f; cb = 0.12500542402267456f; ca = -0.06250379234552383f; top = 0;
+    } else if (r2 < 0.0436f * 0.0436f) {
+      c[0] = 0.5f; c[1] = 0.1249999925494194f; cb = -0.06255202740430832f; ca = 0.03910152614116669f; top = 1;
+    } else if (r2 < 0.112f * 0.112f) {
+      c[0] = 0.5f; c[1] = 0.12499897927045822f; c[2] = -0.06249919906258583f; cb = 0.03938665986061096f; ca = -0.02759857103228569f;
+      top = 2;
+    } else {
+      c[0] = 0.5f; c[1] = 0.125f; c[2] = -0.062495309859514236f; c[3] = 0.039058685302734375f; cb = -0.027897052466869354f;
+      ca = 0.02095773071050644f; top = 3;
+    }
+  } else if (!economised) {
     if (r2 < 0.005f * 0.005f) { ca = c[2]; cb = c[1]; top = 0; }
     else if (r2 < 0.04f * 0.04f) { ca = c[4]; cb = c[3]; top = 2; }
   } else if (r2 < 0.007f * 0.007f) {        // kEcon tier 0: q of degree 2
@@ -110,22 +138,26 @@ FFMPM_HD bool fixed_corotated_affine3_f32x2(const Mat3x2& F, LoadC load_C, F2 mu
     }
   }
   const Sym3x2 M = sym3_mul2(G, q);
-  // W = F M,  X = W F^T (symmetric)
-  const F2 w00 = f2_fma(F.a02, M.xz, f2_fma(F.a01, M.xy, f2_mul(F.a00, M.xx)));
-  const F2 w01 = f2_fma(F.a02, M.yz, f2_fma(F.a01, M.yy, f2_mul(F.a00, M.xy)));
-  const F2 w02 = f2_fma(F.a02, M.zz, f2_fma(F.a01, M.yz, f2_mul(F.a00, M.xz)));
-  const F2 w10 = f2_fma(F.a12, M.xz, f2_fma(F.a11, M.xy, f2_mul(F.a10, M.xx)));
-  const F2 w11 = f2_fma(F.a12, M.yz, f2_fma(F.a11, M.yy, f2_mul(F.a10, M.xy)));
-  const F2 w12 = f2_fma(F.a12, M.zz, f2_fma(F.a11, M.yz, f2_mul(F.a10, M.xz)));
-  const F2 w20 = f2_fma(F.a22, M.xz, f2_fma(F.a21, M.xy, f2_mul(F.a20, M.xx)));
-  const F2 w21 = f2_fma(F.a22, M.yz, f2_fma(F.a21, M.yy, f2_mul(F.a20, M.xy)));
-  const F2 w22 = f2_fma(F.a22, M.zz, f2_fma(F.a21, M.yz, f2_mul(F.a20, M.xz)));
-  const F2 x00 = f2_fma(w02, F.a02, f2_fma(w01, F.a01, f2_mul(w00, F.a00)));
-  const F2 x01 = f2_fma(w02, F.a12, f2_fma(w01, F.a11, f2_mul(w00, F.a10)));
-  const F2 x02 = f2_fma(w02, F.a22, f2_fma(w01, F.a21, f2_mul(w00, F.a20)));
-  const F2 x11 = f2_fma(w12, F.a12, f2_fma(w11, F.a11, f2_mul(w10, F.a10)));
-  const F2 x12 = f2_fma(w12, F.a22, f2_fma(w11, F.a21, f2_mul(w10, F.a20)));
-  const F2 x22 = f2_fma(w22, F.a22, f2_fma(w21, F.a21, f2_mul(w20, F.a20)));
+  F2 x00, x01, x02, x11, x12, x22;
+  if (left) {      // M is h(G_B) = (F - R) F^T itself
+    x00 = M.xx; x01 = M.xy; x02 = M.xz; x11 = M.yy; x12 = M.yz; x22 = M.zz;
+  } else {         // W = F M,  X = W F^T (symmetric)
+    const F2 w00 = f2_fma(F.a02, M.xz, f2_fma(F.a01, M.xy, f2_mul(F.a00, M.xx)));
+    const F2 w01 = f2_fma(F.a02, M.yz, f2_fma(F.a01, M.yy, f2_mul(F.a00, M.xy)));
+    const F2 w02 = f2_fma(F.a02, M.zz, f2_fma(F.a01, M.yz, f2_mul(F.a00, M.xz)));
+    const F2 w10 = f2_fma(F.a12, M.xz, f2_fma(F.a11, M.xy, f2_mul(F.a10, M.xx)));
+    const F2 w11 = f2_fma(F.a12, M.yz, f2_fma(F.a11, M.yy, f2_mul(F.a10, M.xy)));
+    const F2 w12 = f2_fma(F.a12, M.zz, f2_fma(F.a11, M.yz, f2_mul(F.a10, M.xz)));
+    const F2 w20 = f2_fma(F.a22, M.xz, f2_fma(F.a21, M.xy, f2_mul(F.a20, M.xx)));
+    const F2 w21 = f2_fma(F.a22, M.yz, f2_fma(F.a21, M.yy, f2_mul(F.a20, M.xy)));
+    const F2 w22 = f2_fma(F.a22, M.zz, f2_fma(F.a21, M.yz, f2_mul(F.a20, M.xz)));
+    x00 = f2_fma(w02, F.a02, f2_fma(w01, F.a01, f2_mul(w00, F.a00)));
+    x01 = f2_fma(w02, F.a12, f2_fma(w01, F.a11, f2_mul(w00, F.a10)));
+    x02 = f2_fma(w02, F.a22, f2_fma(w01, F.a21, f2_mul(w00, F.a20)));
+    x11 = f2_fma(w12, F.a12, f2_fma(w11, F.a11, f2_mul(w10, F.a10)));
+    x12 = f2_fma(w12, F.a22, f2_fma(w11, F.a21, f2_mul(w10, F.a20)));
+    x22 = f2_fma(w22, F.a22, f2_fma(w21, F.a21, f2_mul(w20, F.a20)));
+  }
   // J - 1 = tr E + principal 2x2 minors + det E, without cancellation
   const F2 trE = f2_add(f2_add(E.a00, E.a11), E.a22);
   const F2 m01 = f2_sub(f2_mul(E.a00, E.a11), f2_mul(E.a01, E.a10));
@@ -210,7 +242,7 @@ FFMPM_HD void p2g_prepare3_pair_sink(const DevCfg& cfg, GetA ga, GetB gb, bool h
       sink.head(0, qa);
       sink.head(1, qb);
       packed = fixed_corotated_affine3_f32x2(F, load_C, f2(mu_a, mu_b), f2(lam_a, lam_b), f2(mass_a, mass_b), (float)k, A,
-                                             cfg.fp32_stress == 2);
+                                             cfg.fp32_stress);
       if (packed) {
         sink.affine(A);
         return;

@@ -17,9 +17,11 @@ if [ "$N" = "1" ]; then
   done
   timeout 180 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --e2e-streamed > $out/bench_e2e_streamed.json 2> $out/bench_e2e_streamed.err
   timeout 120 python bench.py --steps 100 --warmup 6 --no-cpu-baseline --e2e-steps 1 --graph > $out/bench_graph.json 2> $out/bench_graph.err
-  for v in 8 11; do   # economised series coefficients in the packed stress: 5 matrix products instead of 7 at this strain
+  for v in 8 11; do   # packed stress: economised coefficients (5 products instead of 7 here), and the left form (4, none with F)
     FFMPM_P2G_VARIANT=$v FFMPM_FP32_STRESS=2 timeout 120 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --e2e-steps 1 \
         > $out/bench_v${v}econ.json 2> $out/bench_v${v}econ.err
+    FFMPM_P2G_VARIANT=$v FFMPM_FP32_STRESS=3 timeout 120 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --e2e-steps 1 \
+        > $out/bench_v${v}left.json 2> $out/bench_v${v}left.err
   done
   FFMPM_G2P_PACKED=1 timeout 120 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --e2e-steps 1 \
       > $out/bench_vg2p.json 2> $out/bench_vg2p.err
@@ -27,7 +29,7 @@ if [ "$N" = "1" ]; then
       > $out/bench_vg2p6.json 2> $out/bench_vg2p6.err
   python - <<PY
 import json
-for v in (5, 7, 10, 8, 11, 9, "8econ", "11econ", "g2p", "g2p6"):
+for v in (5, 7, 10, 8, 11, 9, "8econ", "11econ", "8left", "11left", "g2p", "g2p6"):
     try:
         d = json.load(open("$out/bench_v%s.json" % v))
         print("variant", v, d["ms_per_step"], d["roofline"]["phase_ms"])

@@ -300,14 +300,15 @@ def prepare3_pair(km, res, x, v, Cm, F, mass, mu, lam, dt, volume, hardening=1.0
     return base, fx, aff.reshape(n, 3, 3), mv, m, ok.astype(bool)
 
 
-@pytest.mark.parametrize("series", [1, 2])
+@pytest.mark.parametrize("series", [1, 2, 3])
 @pytest.mark.parametrize("strain", [0.0, 1e-6, 1e-4, 1.5e-3, 4e-3, 1e-2, 2.5e-2, 4e-2, 6e-2, 0.3, "mixed"])
 def test_packed_fp32_stress_pairs(km, strain, series):
     """p2g_prepare3_pair (FFMPM_P2G_VARIANT=8/9): the stress of two particles per packed instruction.  Same
     1e-5 bar against LAPACK as the one-particle path on every series tier; a pair with one particle beyond
     the series, outside the grid or NaN falls back to the one-particle routine for both; index, weights
     offset and mass*v are the one-particle routine's bits.  series = 2: the economised coefficient tiers
-    (FFMPM_FP32_STRESS=2; strains chosen to land in each of its five tiers)."""
+    (FFMPM_FP32_STRESS=2; strains chosen to land in each of its five tiers); series = 3: the left form
+    (F - R) F^T = B - B^(1/2) as a series in F F^T - I, no products with F (FFMPM_FP32_STRESS=3)."""
     rng = np.random.default_rng(13)
     res, n = 32, 4001                                            # odd: the last particle has no partner
     dx = 1.0 / res
@@ -502,15 +503,19 @@ def test_economised_series_table_is_the_generated_one():
     sys.path.insert(0, os.path.join(root, "scripts"))
     import series_economized as E
     src = open(os.path.join(CSRC, "mpm_p2g_pair.cuh")).read()
-    body = src[src.index("} else if (r2 < 0.007f * 0.007f)"):src.index("const F2 ca2 = f2(ca), cb2 = f2(cb);")]
-    bounds = [float(v) for v in re.findall(r"r2 < ([0-9.]+)f \* [0-9.]+f", body)] + [0.15]
-    assert bounds == [r for r, _ in E.TIERS]
-    blocks = re.split(r"\} else", body)
-    assert len(blocks) == len(E.TIERS) + 1
-    for (r, deg, coef), block in zip(E.table(), blocks[1:]):
-        vals = {k: float(v) for k, v in re.findall(r"(c\[\d\]|ca|cb) = (-?[0-9.e-]+)f;", block)}
-        mine = [vals[f"c[{i}]"] for i in range(deg - 1)] + [vals["cb"], vals["ca"]]
-        assert np.array_equal(np.float32(mine), coef), r
-        assert int(re.search(r"top = (\d);", block).group(1)) == deg - 2
-        assert E.uniform_error(r, coef) < 5.05e-8
-        assert E.worst_matrix_error(r, coef, n=300) < 3e-7
+    def check(body, tiers, left):
+        bounds = [float(v) for v in re.findall(r"r2 < ([0-9.]+)f \* [0-9.]+f", body)] + [0.15]
+        assert bounds == [r for r, _ in tiers]
+        blocks = re.split(r"\} else", body)
+        assert len(blocks) == len(tiers) + 1
+        fn = E.p_exact if left else E.q_exact
+        for (r, deg, coef), block in zip(E.table(left), blocks[1:]):
+            vals = {k: float(v) for k, v in re.findall(r"(c\[\d\]|ca|cb) = (-?[0-9.e-]+)f;", block)}
+            mine = [vals[f"c[{i}]"] for i in range(deg - 1)] + [vals["cb"], vals["ca"]]
+            assert np.array_equal(np.float32(mine), coef), (left, r)
+            assert int(re.search(r"top = (\d);", block).group(1)) == deg - 2
+            assert E.uniform_error(r, coef, fn) < 5.1e-8
+            assert E.worst_matrix_error(r, coef, n=300, left=left) < 3e-7
+
+    check(src[src.index("} else if (r2 < 0.007f * 0.007f)"):src.index("const F2 ca2 = f2(ca), cb2 = f2(cb);")], E.TIERS, False)
+    check("} else " + src[src.index("if (r2 < 0.0136f * 0.0136f)"):src.index("} else if (!economised) {")], E.TIERS_LEFT, True)
