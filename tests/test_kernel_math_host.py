@@ -519,3 +519,33 @@ def test_economised_series_table_is_the_generated_one():
 
     check(src[src.index("} else if (r2 < 0.007f * 0.007f)"):src.index("const F2 ca2 = f2(ca), cb2 = f2(cb);")], E.TIERS, False)
     check("} else " + src[src.index("if (r2 < 0.0136f * 0.0136f)"):src.index("} else if (!economised) {")], E.TIERS_LEFT, True)
+
+
+@pytest.mark.parametrize("angle,strain", [(0.02, 1e-3), (0.1, 1e-3), (0.1, 3e-2), (0.3, 1e-3), (0.3, 3e-2)])
+def test_stress_forms_under_rotation(km, angle, strain):
+    """F = R(angle) (I + strain): E = F - I is then O(angle), and G = E + E^T + E^T E (or E E^T) cancels in fp32.
+    Every form of the fp32 stress -- scalar, packed Taylor, economised, left -- must stay inside the 1e-5 bar and
+    next to each other (the left form shares the right form's conditioning)."""
+    rng = np.random.default_rng(int(angle * 1000 + strain * 1e6))
+    n, res = 2000, 32
+    dx = 1.0 / res
+    vol = float(f32((dx / 2) ** 3))
+
+    def rot(a, ax):
+        c, s = np.cos(a), np.sin(a)
+        R = np.eye(3)
+        i, j = [(1, 2), (0, 2), (0, 1)][ax]
+        R[i, i] = c; R[j, j] = c; R[i, j] = -s; R[j, i] = s
+        return R
+    Rm = np.stack([rot(rng.uniform(-angle, angle), int(rng.integers(3))) for _ in range(n)])
+    F = f32(Rm @ (np.eye(3) + strain * rng.uniform(-1, 1, (n, 3, 3))))
+    x = f32(rng.uniform(0.25, 0.75, (n, 3)))
+    Z = np.zeros((n, 3, 3)); mass = np.full(n, vol); mu = np.full(n, f32(4166.67)); lam = np.full(n, f32(2777.78))
+    want = O.fixed_corotated_stress_3d(F, float(res), mu, lam, 1e-4, vol, mass, Z)
+    scale = np.abs(want).max()
+    errs = [np.abs(prepare3(km, "f32", res, x, np.zeros((n, 3)), Z, F, mass, mu, lam, 1e-4, vol)[2] - want).max() / scale]
+    for form in (1, 2, 3):
+        got = prepare3_pair(km, res, x, np.zeros((n, 3)), Z, F, mass, mu, lam, 1e-4, vol, fp32_stress=form)
+        errs.append(np.abs(got[2] - want).max() / scale)
+    assert max(errs) < 1e-5, errs
+    assert max(errs) < 2.0 * min(errs) + 2e-7, errs
