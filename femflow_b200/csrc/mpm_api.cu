@@ -400,6 +400,8 @@ static int p2g_t(FfMpmHandle* h, cudaStream_t s) {
           ok = p2g_bulk_launch<4, 1, 1, P2G_NPLANES, 16, 1>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s, h->p2g_run_cap);
         else if (h->p2g_variant == 8)   // ... and the stress of a lane's two particles in packed fp32 as well
           ok = p2g_bulk_launch<4, 1, 1, P2G_NPLANES, 12, 2>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s, h->p2g_run_cap);
+        else if (h->p2g_variant == 12)  // both phases packed, left-form stress compiled in, 16 warps/SM
+          ok = p2g_bulk_launch<4, 1, 1, P2G_NPLANES, 16, 3>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s, h->p2g_run_cap);
         else if (h->p2g_variant == 11)  // variant 8 squeezed into 128 registers: 16 warps/SM
           ok = p2g_bulk_launch<4, 1, 1, P2G_NPLANES, 16, 2>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s, h->p2g_run_cap);
         else if (h->p2g_variant == 9)   // same at 8 warps/SM (210 registers)

@@ -91,7 +91,7 @@ __device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
 // of 4 warps, <= 96 registers) is the occupancy experiment behind FFMPM_P2G_VARIANT=6.
 // PAIR >= 1: phase 2 walks the runs two particles per instruction with packed fp32 (FFMA2; mpm_p2g_pair.cuh);
 // PAIR == 2: phase 1 too -- the stress of the two particles a lane owns in a window is evaluated in packed
-// fp32.  FFMPM_P2G_VARIANT=7 / 8, written after this round's GPU budget was spent: not yet measured.
+// fp32; PAIR == 3: ... in the left form only, chosen at compile time.  FFMPM_P2G_VARIANT=7 / 8, written after this round's GPU budget was spent: not yet measured.
 template <int WARPS, int NBUF, int LDGSTS, int RAWP = P2G_NPLANES, int SMW = 16, int PAIR = 0>
 __global__ void __launch_bounds__(WARPS * 32, SMW / WARPS)
 p2g_bulk3_kernel(DevCfg cfg, P2GPlanes planes, long long n, float* __restrict__ grid, ErrRec* err, int wpw) {
@@ -167,7 +167,7 @@ p2g_bulk3_kernel(DevCfg cfg, P2GPlanes planes, long long n, float* __restrict__ 
     }
     // ---- phase 1: lane per particle, state from the prefetched slab ----
     int node[2];
-    if constexpr (PAIR == 2) {
+    if constexpr (PAIR >= 2) {
       // both particles of the lane (slots lane and lane + 32) in one packed evaluation
       const bool live_a = lane < cnt, live_b = 32 + lane < cnt;
       auto getter = [&](int idx) {
@@ -179,7 +179,7 @@ p2g_bulk3_kernel(DevCfg cfg, P2GPlanes planes, long long n, float* __restrict__ 
         };
       };
       P2GPairParker park{S.pay, S.node0, lane, ny, nz, dx, {-1, -1}};
-      p2g_prepare3_pair_sink(cfg, getter(lane), getter(32 + lane), has_mat, live_a, live_b, park);
+      p2g_prepare3_pair_sink<(PAIR == 3 ? 3 : 0)>(cfg, getter(lane), getter(32 + lane), has_mat, live_a, live_b, park);
       node[0] = park.node[0];
       node[1] = park.node[1];
       if (!live_a) p2g_park_pair_zero(S.pay, lane);

@@ -194,7 +194,9 @@ FFMPM_HD bool fixed_corotated_affine3_f32x2(const Mat3x2& F, LoadC load_C, F2 mu
 //   sink.head(h, q)   particle h (0 / 1): base cell, weights offset, mass, mass*v are final (q.ok is true);
 //   sink.affine(A)    the nine affine entries of both particles (pairs: .x = particle 0, .y = particle 1);
 //   sink.full(h, q)   particle h evaluated by the one-particle routine (everything final, q.ok may be false).
-template <typename GetA, typename GetB, typename Sink>
+// FORM: 0 = the stress form is cfg.fp32_stress at run time (1 Taylor, 2 economised, 3 left); 3 = the left form at
+// compile time (F is dead once F F^T - I is formed, and the code of the other forms is not generated at all).
+template <int FORM = 0, typename GetA, typename GetB, typename Sink>
 FFMPM_HD void p2g_prepare3_pair_sink(const DevCfg& cfg, GetA ga, GetB gb, bool has_mat, bool live_a, bool live_b, Sink& sink) {
   bool packed = live_a && live_b && cfg.fp32_stress && cfg.model == 0;
   if (packed) {
@@ -242,7 +244,7 @@ FFMPM_HD void p2g_prepare3_pair_sink(const DevCfg& cfg, GetA ga, GetB gb, bool h
       sink.head(0, qa);
       sink.head(1, qb);
       packed = fixed_corotated_affine3_f32x2(F, load_C, f2(mu_a, mu_b), f2(lam_a, lam_b), f2(mass_a, mass_b), (float)k, A,
-                                             cfg.fp32_stress);
+                                             FORM != 0 ? FORM : cfg.fp32_stress);
       if (packed) {
         sink.affine(A);
         return;
@@ -272,7 +274,7 @@ template <typename GetA, typename GetB>
 FFMPM_HD void p2g_prepare3_pair(const DevCfg& cfg, GetA ga, GetB gb, bool has_mat, bool live_a, bool live_b,
                                 P2GParticle3<float>& qa, P2GParticle3<float>& qb) {
   P2GPairRegisters sink{{&qa, &qb}};
-  p2g_prepare3_pair_sink(cfg, ga, gb, has_mat, live_a, live_b, sink);
+  p2g_prepare3_pair_sink<0>(cfg, ga, gb, has_mat, live_a, live_b, sink);
 }
 
 constexpr int P2G_NPAIR = P2G_WINDOW / 2;

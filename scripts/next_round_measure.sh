@@ -11,7 +11,7 @@ TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr
 if [ "$N" = "1" ]; then
   FFMPM_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -k "packed_fp32" > $out/pytest_packed.txt 2>&1
   tail -3 $out/pytest_packed.txt
-  for v in 5 7 10 8 11 9; do
+  for v in 5 7 10 8 11 12 9; do
     FFMPM_P2G_VARIANT=$v timeout 120 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --e2e-steps 1 \
         > $out/bench_v$v.json 2> $out/bench_v$v.err
   done
@@ -29,7 +29,7 @@ if [ "$N" = "1" ]; then
       > $out/bench_vg2p6.json 2> $out/bench_vg2p6.err
   python - <<PY
 import json
-for v in (5, 7, 10, 8, 11, 9, "8econ", "11econ", "8left", "11left", "g2p", "g2p6"):
+for v in (5, 7, 10, 8, 11, 12, 9, "8econ", "11econ", "8left", "11left", "g2p", "g2p6"):
     try:
         d = json.load(open("$out/bench_v%s.json" % v))
         print("variant", v, d["ms_per_step"], d["roofline"]["phase_ms"])

@@ -372,7 +372,7 @@ def test_multi_substep_pipelines_vs_oracle(mode):
                     reason="packed-fp32 P2G (FFMPM_P2G_VARIANT 7/8/9) was written after the round's GPU budget ran out: "
                            "its arithmetic is checked on the host (tests/test_kernel_math_host.py); set "
                            "FFMPM_TEST_EXPERIMENTAL=1 to run it on a GPU")
-@pytest.mark.parametrize("variant", [7, 8, 9, 10, 11, "7cap4", "11econ", "11left", "g2p", "g2p6"])
+@pytest.mark.parametrize("variant", [7, 8, 9, 10, 11, 12, "7cap4", "11econ", "11left", "g2p", "g2p6"])
 @pytest.mark.parametrize("n_materials", [1, 3, 300])
 def test_packed_fp32_p2g_variants(variant, n_materials, monkeypatch):
     """P2G with two particles per FFMA2 (mpm_p2g_pair.cuh) and the G2P stencil sums in packed fp32 ("g2p":
