@@ -60,6 +60,12 @@ for halo in p2p symm; do
   timeout 300 $TR --master-port 2952$N bench.py --gpus $N --steps 100 --warmup 10 --no-cpu-baseline --halo $halo --slab-timing \
       > $out/bench_${halo}.json 2> $out/bench_${halo}.err
 done
+# the p2p exchange moves 2 x (2*margin+2) planes of 1.06 MB per neighbour: 21 MB in ~0.18 ms looks bandwidth- as much as
+# latency-bound for NCCL send/recv, so a thinner margin (more frequent, still asynchronous, migration checks) may pay
+for m in 2 3; do
+  timeout 300 $TR --master-port 2954$N bench.py --gpus $N --steps 100 --warmup 10 --no-cpu-baseline --margin $m \
+      > $out/bench_p2p_margin$m.json 2> $out/bench_p2p_margin$m.err
+done
 if [ "$N" = "8" ]; then
   for mode in "" "--rebalance"; do
     tag=$([ -z "$mode" ] && echo static || echo rebalanced)
