@@ -67,8 +67,6 @@ struct FfMpmHandle {
   int64_t launches;
   bool prebinned;     // keys/rank/histogram of the live buffer were emitted by the last reordering G2P
   int p2g_variant;    // see p2g_t (FFMPM_P2G_VARIANT)
-  int p2g_run_cap;    // FFMPM_P2G_RUN_CAP (packed P2G variants only): cut runs every 2^k slots (dense cells)
-  int g2p_packed;     // FFMPM_G2P_PACKED=1/2: stencil sums in packed fp32 (g2p_accumulate3_packed; not yet measured)
   int p2g_blocks_per_sm, g2p_blocks_per_sm;   // persistent-grid sizing (tunable: FFMPM_P2G_BPS / FFMPM_G2P_BPS)
   bool grid_in_blocks; // the current grid was zero before a P2G of exactly the binned particles: everything
                        // non-zero lies inside the node blocks listed by the binning (bin.node_tiles)
@@ -156,10 +154,8 @@ int ffmpm_create(const FfMpmConfig* cfg, int32_t device, FfMpmHandle** out) {
   }
   d.own_lo = INT32_MIN;   // single domain: nobody leaves
   d.own_hi = INT32_MAX;
-  d.fp32_stress = 1;
-  // 0: fp64 stress always; 1: fp32 perturbation series; packed variants only: 2 = economised coefficients,
-  // 3 = the left form h(F F^T - I) with economised coefficients (no products with F)
-  if (const char* e = getenv("FFMPM_FP32_STRESS")) { const int v = atoi(e); d.fp32_stress = (v == 2 || v == 3) ? v : (v != 0); }
+  d.fp32_stress = 1;   // fp32 build: left-form perturbation series (mpm_math.cuh); FFMPM_FP32_STRESS=0: fp64 stress always
+  if (const char* e = getenv("FFMPM_FP32_STRESS")) d.fp32_stress = atoi(e) != 0;
   h->n_nodes = (int64_t)d.n[0] * d.n[1] * d.n[2];
   h->overlap = 1;
   if (const char* e = getenv("FFMPM_OVERLAP")) h->overlap = atoi(e) != 0;
@@ -184,13 +180,8 @@ int ffmpm_create(const FfMpmConfig* cfg, int32_t device, FfMpmHandle** out) {
   if (const char* e = getenv("FFMPM_SPARSE_GRID_OP")) h->sparse_grid_op = atoi(e) != 0;
   h->p2g_blocks_per_sm = 5;
   h->g2p_blocks_per_sm = 8;
-  h->p2g_variant = 5;   // physical-order P2G with cp.async-prefetched state when eligible (profiles/r01j)
+  h->p2g_variant = 5;   // physical-order P2G with cp.async-prefetched state when eligible (profiles/r01j, r02a)
   if (const char* e = getenv("FFMPM_P2G_VARIANT")) h->p2g_variant = atoi(e);
-  if (const char* e = getenv("FFMPM_P2G_RUN_CAP")) {
-    const int v = atoi(e);
-    if (v == 2 || v == 4 || v == 8 || v == 16 || v == 32) h->p2g_run_cap = v;
-  }
-  if (const char* e = getenv("FFMPM_G2P_PACKED")) h->g2p_packed = atoi(e);   // 1: packed sums, 2: at 6 CTAs/SM
   if (const char* e = getenv("FFMPM_P2G_BPS")) { int v = atoi(e); if (v > 0 && v <= 32) h->p2g_blocks_per_sm = v; }
   if (const char* e = getenv("FFMPM_G2P_BPS")) { int v = atoi(e); if (v > 0 && v <= 32) h->g2p_blocks_per_sm = v; }
   *out = h;
@@ -386,30 +377,12 @@ static int p2g_t(FfMpmHandle* h, cudaStream_t s) {
   if (mode == FFMPM_P2G_TILED) {
     if (h->cfg.dim != 3) return set_err(FFMPM_E_INVALID, "tiled P2G is 3D only (2D uses the scatter kernel)");
     if (!h->binned) return set_err(FFMPM_E_STATE, "tiled P2G needs ffmpm_bin first");
-    // P2G variant: 0 = through the permutation, 1 = physical order (kept sorted by G2P),
-    // 3 = physical order, state prefetched by TMA bulk copies (fp32), 5 = by per-lane 16-byte cp.async
-    // (fp32, default: fewer issue slots than 27 elected UBLKCP sequences per window)
+    // P2G variant (FFMPM_P2G_VARIANT): 0 = through the permutation, 1 = physical order (kept sorted by G2P),
+    // 5 (default) = physical order with the window state prefetched by per-lane cp.async (fp32, mpm_p2g_bulk.cuh)
     if constexpr (sizeof(T) == 4) {
       if (h->p2g_variant >= 3 && p2g_bulk_eligible(h->dev, sv)) {
-        bool ok;
-        const int bps = h->p2g_blocks_per_sm;
-        if (h->p2g_variant == 3) ok = p2g_bulk_launch<3, 1, 0>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
-        else if (h->p2g_variant == 7)   // packed-fp32 phase 2 (two particles per FFMA2), 12 warps/SM for the 72 accumulator registers
-          ok = p2g_bulk_launch<4, 1, 1, P2G_NPLANES, 12, 1>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s, h->p2g_run_cap);
-        else if (h->p2g_variant == 10)  // variant 7 squeezed into 128 registers: 16 warps/SM
-          ok = p2g_bulk_launch<4, 1, 1, P2G_NPLANES, 16, 1>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s, h->p2g_run_cap);
-        else if (h->p2g_variant == 8)   // ... and the stress of a lane's two particles in packed fp32 as well
-          ok = p2g_bulk_launch<4, 1, 1, P2G_NPLANES, 12, 2>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s, h->p2g_run_cap);
-        else if (h->p2g_variant == 12)  // both phases packed, left-form stress compiled in, 16 warps/SM
-          ok = p2g_bulk_launch<4, 1, 1, P2G_NPLANES, 16, 3>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s, h->p2g_run_cap);
-        else if (h->p2g_variant == 11)  // variant 8 squeezed into 128 registers: 16 warps/SM
-          ok = p2g_bulk_launch<4, 1, 1, P2G_NPLANES, 16, 2>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s, h->p2g_run_cap);
-        else if (h->p2g_variant == 9)   // same at 8 warps/SM (210 registers)
-          ok = p2g_bulk_launch<4, 1, 1, P2G_NPLANES, 8, 2>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s, h->p2g_run_cap);
-        else if (h->p2g_variant == 6 && mat_mode_of(sv) != MAT_PLANES)   // occupancy experiment: 20 warps/SM
-          ok = p2g_bulk_launch<4, 1, 1, P2G_MASS, 20>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
-        else ok = p2g_bulk_launch<4, 1, 1>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, bps, s);
-        if (!ok) return set_err(FFMPM_E_CUDA, "could not configure the bulk P2G kernel");
+        if (!p2g_bulk_launch<4, 1>(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, h->p2g_blocks_per_sm, s))
+          return set_err(FFMPM_E_CUDA, "could not configure the bulk P2G kernel");
         return check_launch(h, 1);
       }
     }
@@ -487,8 +460,7 @@ static int g2p_t(FfMpmHandle* h, cudaStream_t s) {
     StateView<T> dst = view<T>(h, h->st[h->live ^ 1]);
     // (the kernel pre-bins the advected particles for the next substep into the histogram that
     // bin_particles left cleared)
-    int nl = g2p_tiled<T>(h->dev, sv, dst, h->n, h->bin, (const T*)h->grid, h->err, h->sm_count, h->g2p_blocks_per_sm, s,
-                          h->g2p_packed);
+    int nl = g2p_tiled<T>(h->dev, sv, dst, h->n, h->bin, (const T*)h->grid, h->err, h->sm_count, h->g2p_blocks_per_sm, s);
     h->live ^= 1;
     h->binned = false;  // positions moved: perm / cell offsets are stale ...
     h->prebinned = true;  // ... but keys, ranks and the histogram of the new live buffer are ready

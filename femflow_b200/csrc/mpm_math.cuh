@@ -108,15 +108,21 @@ FFMPM_HD Mat3<double> fixed_corotated_affine3(const Mat3<double>& F, const Mat3<
 // fp32 evaluation of the same affine matrix in PERTURBATION FORM (used by the fp32
 // build when the strain is moderate).  The cancellation that rules out a naive fp32
 // stress -- F - R and J - 1 for F close to I -- is removed
-// algebraically instead of being bought with fp64:
+// algebraically instead of being bought with fp64.  LEFT form: with F = V R
+// (V = (F F^T)^(1/2) the left stretch),
+//   (F - R) F^T = F F^T - V = B - B^(1/2),           B = F F^T = I + G,
 //   E = F - I                      (exact in fp32 for entries near 1 / 0)
-//   G = F^T F - I = E + E^T + E^T E
-//   S = (I + G)^(1/2),  R = F S^-1  =>  (F - R) F^T = F (I - S^-1) F^T = F M F^T,
-//   M = I - (I + G)^(-1/2) = G/2 - 3G^2/8 + 5G^3/16 - ...   (binomial series, Horner)
+//   G = F F^T - I = E + E^T + E E^T                  (left Cauchy-Green strain)
+//   h(G) = (I + G) - (I + G)^(1/2) = G p(G),         p(x) = (1 + x - sqrt(1 + x)) / x = 1/2 + x/8 - x^2/16 + ...
 //   J - 1 = det(I + E) - 1 = tr E + (principal 2x2 minors of E) + det E
-// Every quantity is O(strain), so fp32 keeps ~1e-7 RELATIVE accuracy on the stress
-// (prototype vs LAPACK: 1.5e-7 for strains 1e-6 .. 1e-2).  The degree-8 series is used
-// for max|G| < 0.15 (truncation < 1e-7 there); larger strains take the fp64 path.
+// so the stress term is a matrix function of the symmetric G alone (no product with F, no SVD, no
+// iteration) and every quantity is O(strain): fp32 keeps ~2e-7 RELATIVE accuracy on the stress.
+// p is not the truncated Taylor series but its Chebyshev interpolant on the tier's interval
+// (scripts/series_economized.py prints the table below and the CPU suite regenerates and compares it):
+// degree 2 / 3 / 4 / 5 for ||G||_F < 0.0136 / 0.0436 / 0.112 / 0.15 keeps the error of p below 5e-8 with
+// fp32 coefficients; larger strains take the fp64 path.  Measured on B200 against the right form
+// F (I - (I + F^T F - I)^(-1/2)) F^T with its 8-term Taylor series that round 1 shipped: four symmetric
+// products instead of seven plus two products with F at the headline strain (profiles/r02a).
 // ----------------------------------------------------------------------------
 struct Sym3f {
   float xx, xy, xz, yy, yz, zz;
@@ -134,66 +140,104 @@ FFMPM_HD Sym3f sym3_mul(const Sym3f& a, const Sym3f& b) {
   return r;
 }
 
-// The series M = I - (I + G)^(-1/2) = sum_k c_k G^k is truncated at a degree picked from the
-// Frobenius norm r of G (an upper bound of its spectral radius): degree 3 for r < 0.005, 5 for
-// r < 0.04, 8 for r < 0.15 -- each keeps the truncation error of M below 1e-7 relative (checked
-// against an eigendecomposition over random and rank-one G, scripts/series_degree.py).  Small
-// strains, the common case for an elastic solid, take 2 instead of 7 matrix products.
 constexpr float kPerturbationMaxR = 0.15f;
+constexpr int kStressTiers = 4;
+// upper bound of ||G||_F per tier (tier t uses p of degree t + 2) and the power-basis coefficients c_0 .. c_deg
+// of p per tier (scripts/series_economized.py, TIERS_LEFT).  Functions of literals rather than tables: with the
+// tier a template argument and the Horner loop unrolled they fold to immediates in host and device code alike.
+FFMPM_HD constexpr float stress_tier_r(int tier) {
+  return tier == 0 ? 0.0136f : tier == 1 ? 0.0436f : tier == 2 ? 0.112f : 0.15f;
+}
+FFMPM_HD constexpr float stress_coef(int tier, int i) {
+  switch (tier * 8 + i) {
+    // ||G||_F < 0.0136: degree 2
+    case 0: return 0.5f; case 1: return 0.12500542402267456f; case 2: return -0.06250379234552383f;
+    // ||G||_F < 0.0436: degree 3
+    case 8: return 0.5f; case 9: return 0.1249999925494194f; case 10: return -0.06255202740430832f; case 11: return 0.03910152614116669f;
+    // ||G||_F < 0.112: degree 4
+    case 16: return 0.5f; case 17: return 0.12499897927045822f; case 18: return -0.06249919906258583f; case 19: return 0.03938665986061096f;
+    case 20: return -0.02759857103228569f;
+    // ||G||_F < 0.15: degree 5
+    case 24: return 0.5f; case 25: return 0.125f; case 26: return -0.062495309859514236f; case 27: return 0.039058685302734375f;
+    case 28: return -0.027897052466869354f; case 29: return 0.02095773071050644f;
+    default: return 0.0f;
+  }
+}
 
-// Returns false when the strain is too large for the series (caller falls back to fp64).
-FFMPM_HD bool fixed_corotated_affine3_f32(const Mat3<float>& F, const Mat3<float>& C, float mu,
-                                                            float lam, float mass, float dt_vol_dinv, Mat3<float>& A) {
-  Mat3<float> E = F;
+// E = F - I, G = E + E^T + E E^T and the squared Frobenius norm of G (an upper bound of its spectral radius^2).
+FFMPM_HD void left_strain3(const Mat3<float>& F, Mat3<float>& E, Sym3f& G, float& r2) {
+  E = F;
   E.a00 -= 1.0f; E.a11 -= 1.0f; E.a22 -= 1.0f;
-  Sym3f G;
-  G.xx = 2.0f * E.a00 + (E.a00 * E.a00 + E.a10 * E.a10 + E.a20 * E.a20);
-  G.yy = 2.0f * E.a11 + (E.a01 * E.a01 + E.a11 * E.a11 + E.a21 * E.a21);
-  G.zz = 2.0f * E.a22 + (E.a02 * E.a02 + E.a12 * E.a12 + E.a22 * E.a22);
-  G.xy = (E.a01 + E.a10) + (E.a00 * E.a01 + E.a10 * E.a11 + E.a20 * E.a21);
-  G.xz = (E.a02 + E.a20) + (E.a00 * E.a02 + E.a10 * E.a12 + E.a20 * E.a22);
-  G.yz = (E.a12 + E.a21) + (E.a01 * E.a02 + E.a11 * E.a12 + E.a21 * E.a22);
-  const float r2 = (G.xx * G.xx + G.yy * G.yy + G.zz * G.zz) + 2.0f * (G.xy * G.xy + G.xz * G.xz + G.yz * G.yz);
-  if (!(r2 < kPerturbationMaxR * kPerturbationMaxR)) return false;
-  // q(G) = M / G, Horner from the highest coefficient kept
-  const float c[8] = {0.5f, -0.375f, 0.3125f, -0.2734375f, 0.24609375f, -0.2255859375f, 0.20947265625f,
-                      -0.196380615234375f};
-  float ca = c[7], cb = c[6];
-  int top = 5;                                             // degree 8: Horner steps c[5] .. c[0]
-  if (r2 < 0.005f * 0.005f) { ca = c[2]; cb = c[1]; top = 0; }        // degree 3
-  else if (r2 < 0.04f * 0.04f) { ca = c[4]; cb = c[3]; top = 2; }     // degree 5
+  G.xx = 2.0f * E.a00 + (E.a00 * E.a00 + E.a01 * E.a01 + E.a02 * E.a02);
+  G.yy = 2.0f * E.a11 + (E.a10 * E.a10 + E.a11 * E.a11 + E.a12 * E.a12);
+  G.zz = 2.0f * E.a22 + (E.a20 * E.a20 + E.a21 * E.a21 + E.a22 * E.a22);
+  G.xy = (E.a01 + E.a10) + (E.a00 * E.a10 + E.a01 * E.a11 + E.a02 * E.a12);
+  G.xz = (E.a02 + E.a20) + (E.a00 * E.a20 + E.a01 * E.a21 + E.a02 * E.a22);
+  G.yz = (E.a12 + E.a21) + (E.a10 * E.a20 + E.a11 * E.a21 + E.a12 * E.a22);
+  r2 = (G.xx * G.xx + G.yy * G.yy + G.zz * G.zz) + 2.0f * (G.xy * G.xy + G.xz * G.xz + G.yz * G.yz);
+}
+
+// Tier of the series for a squared norm r2: 0 .. kStressTiers-1, or kStressTiers when the strain is beyond
+// the series (also for NaN).
+FFMPM_HD int stress_tier_of(float r2) {
+  int t = kStressTiers;
+#pragma unroll
+  for (int i = kStressTiers - 1; i >= 0; --i)
+    if (r2 < stress_tier_r(i) * stress_tier_r(i)) t = i;
+  return t;
+}
+
+// h(G) = G p(G) by Horner, p of degree TIER + 2: TIER + 2 symmetric products, straight-line code with the
+// coefficients as immediates (the kernels pick TIER per warp, so no per-lane branching).
+template <int TIER>
+FFMPM_HD Sym3f left_stress_h(const Sym3f& G) {
+  constexpr int deg = TIER + 2;
+  const float ca = stress_coef(TIER, deg), cb = stress_coef(TIER, deg - 1);
   Sym3f q;
   q.xx = ca * G.xx + cb; q.yy = ca * G.yy + cb; q.zz = ca * G.zz + cb;
   q.xy = ca * G.xy; q.xz = ca * G.xz; q.yz = ca * G.yz;
 #pragma unroll
-  for (int i = 5; i >= 0; --i) {
-    if (i <= top) {                                        // a warp pays for its most strained particle
-      q = sym3_mul(G, q);
-      q.xx += c[i]; q.yy += c[i]; q.zz += c[i];
-    }
+  for (int i = deg - 2; i >= 0; --i) {
+    q = sym3_mul(G, q);
+    q.xx += stress_coef(TIER, i); q.yy += stress_coef(TIER, i); q.zz += stress_coef(TIER, i);
   }
-  const Sym3f M = sym3_mul(G, q);
-  // W = F M,  X = W F^T (symmetric)
-  const float w00 = F.a00 * M.xx + F.a01 * M.xy + F.a02 * M.xz, w01 = F.a00 * M.xy + F.a01 * M.yy + F.a02 * M.yz,
-              w02 = F.a00 * M.xz + F.a01 * M.yz + F.a02 * M.zz;
-  const float w10 = F.a10 * M.xx + F.a11 * M.xy + F.a12 * M.xz, w11 = F.a10 * M.xy + F.a11 * M.yy + F.a12 * M.yz,
-              w12 = F.a10 * M.xz + F.a11 * M.yz + F.a12 * M.zz;
-  const float w20 = F.a20 * M.xx + F.a21 * M.xy + F.a22 * M.xz, w21 = F.a20 * M.xy + F.a21 * M.yy + F.a22 * M.yz,
-              w22 = F.a20 * M.xz + F.a21 * M.yz + F.a22 * M.zz;
-  const float x00 = w00 * F.a00 + w01 * F.a01 + w02 * F.a02, x01 = w00 * F.a10 + w01 * F.a11 + w02 * F.a12,
-              x02 = w00 * F.a20 + w01 * F.a21 + w02 * F.a22;
-  const float x11 = w10 * F.a10 + w11 * F.a11 + w12 * F.a12, x12 = w10 * F.a20 + w11 * F.a21 + w12 * F.a22;
-  const float x22 = w20 * F.a20 + w21 * F.a21 + w22 * F.a22;
-  // J - 1 without cancellation
+  return sym3_mul(G, q);
+}
+
+// J - 1 = tr E + principal 2x2 minors + det E, without cancellation.
+FFMPM_HD float jm1_of(const Mat3<float>& E) {
   const float trE = E.a00 + E.a11 + E.a22;
   const float c2 = (E.a00 * E.a11 - E.a01 * E.a10) + (E.a00 * E.a22 - E.a02 * E.a20) + (E.a11 * E.a22 - E.a12 * E.a21);
-  const float dE = det3(E);
-  const float jm1 = trE + c2 + dE;
+  return trE + c2 + det3(E);
+}
+
+// A = k2 * h(G) + kl [on ALL entries, quirk 2] + mc * C with
+//   k2 = -(dt vol 4 inv_dx^2) 2 mu * s,  kl = -(dt vol 4 inv_dx^2) lam (J-1) J * s,  mc = mass * s
+// (s: a common scale the caller folds in -- the P2G kernels park affine * dx).
+FFMPM_HD void affine3_assemble(const Sym3f& H, const Mat3<float>& C, float k2, float kl, float mc, Mat3<float>& A) {
+  A.a00 = k2 * H.xx + kl + mc * C.a00; A.a01 = k2 * H.xy + kl + mc * C.a01; A.a02 = k2 * H.xz + kl + mc * C.a02;
+  A.a10 = k2 * H.xy + kl + mc * C.a10; A.a11 = k2 * H.yy + kl + mc * C.a11; A.a12 = k2 * H.yz + kl + mc * C.a12;
+  A.a20 = k2 * H.xz + kl + mc * C.a20; A.a21 = k2 * H.yz + kl + mc * C.a21; A.a22 = k2 * H.zz + kl + mc * C.a22;
+}
+
+// One particle, tier picked from its own strain.  Returns false when the strain is too large for the series
+// (caller falls back to fp64).  Used by the thread-per-particle kernels; the warp-autonomous P2G picks the tier
+// per warp and calls the pieces above directly.
+FFMPM_HD bool fixed_corotated_affine3_f32(const Mat3<float>& F, const Mat3<float>& C, float mu,
+                                                            float lam, float mass, float dt_vol_dinv, Mat3<float>& A) {
+  Mat3<float> E;
+  Sym3f G, H;
+  float r2;
+  left_strain3(F, E, G, r2);
+  const int tier = stress_tier_of(r2);
+  if (tier >= kStressTiers) return false;
+  if (tier == 0) H = left_stress_h<0>(G);
+  else if (tier == 1) H = left_stress_h<1>(G);
+  else if (tier == 2) H = left_stress_h<2>(G);
+  else H = left_stress_h<3>(G);
+  const float jm1 = jm1_of(E);
   const float l = lam * jm1 * (1.0f + jm1);   // lam (J-1) J, broadcast onto ALL entries (quirk 2)
-  const float k2 = -dt_vol_dinv * 2.0f * mu, kl = -dt_vol_dinv * l;
-  A.a00 = k2 * x00 + kl + mass * C.a00; A.a01 = k2 * x01 + kl + mass * C.a01; A.a02 = k2 * x02 + kl + mass * C.a02;
-  A.a10 = k2 * x01 + kl + mass * C.a10; A.a11 = k2 * x11 + kl + mass * C.a11; A.a12 = k2 * x12 + kl + mass * C.a12;
-  A.a20 = k2 * x02 + kl + mass * C.a20; A.a21 = k2 * x12 + kl + mass * C.a21; A.a22 = k2 * x22 + kl + mass * C.a22;
+  affine3_assemble(H, C, -dt_vol_dinv * 2.0f * mu, -dt_vol_dinv * l, mass, A);
   return true;
 }
 
@@ -261,40 +305,5 @@ FFMPM_HD Mat2<double> svd_roundtrip2(const Mat2<double>& F, bool snow, double& d
   }
   return G;
 }
-
-// ----------------------------------------------------------------------------
-// Packed fp32: sm_100 executes fma / mul / add on two fp32 values held in an aligned register pair
-// (PTX fma.rn.f32x2 -> SASS FFMA2, FMUL2, FADD2; operands may be a broadcast scalar, an immediate, negated).
-// Two results per issue slot for the same FMA-pipe time: what an issue-bound kernel wants.  The host
-// instantiation is two plain floats (tests/test_kernel_math_host.py runs the packed code paths on CPU).
-// ----------------------------------------------------------------------------
-struct F2 {
-  float2 v;
-};
-FFMPM_HD F2 f2(float a, float b) { F2 r; r.v.x = a; r.v.y = b; return r; }
-FFMPM_HD F2 f2(float a) { return f2(a, a); }
-FFMPM_HD F2 f2_fma(F2 a, F2 b, F2 c) {
-#ifdef __CUDA_ARCH__
-  F2 r; r.v = __ffma2_rn(a.v, b.v, c.v); return r;
-#else
-  return f2(fmaf(a.v.x, b.v.x, c.v.x), fmaf(a.v.y, b.v.y, c.v.y));
-#endif
-}
-FFMPM_HD F2 f2_mul(F2 a, F2 b) {
-#ifdef __CUDA_ARCH__
-  F2 r; r.v = __fmul2_rn(a.v, b.v); return r;
-#else
-  return f2(a.v.x * b.v.x, a.v.y * b.v.y);
-#endif
-}
-FFMPM_HD F2 f2_add(F2 a, F2 b) {
-#ifdef __CUDA_ARCH__
-  F2 r; r.v = __fadd2_rn(a.v, b.v); return r;
-#else
-  return f2(a.v.x + b.v.x, a.v.y + b.v.y);
-#endif
-}
-
-FFMPM_HD F2 f2_sub(F2 a, F2 b) { return f2_fma(b, f2(-1.0f), a); }   // a - b: one FFMA2 (operand negation folds in SASS)
 
 }  // namespace ffmpm

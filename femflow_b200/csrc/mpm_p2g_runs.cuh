@@ -64,28 +64,10 @@ __device__ __forceinline__ int p2g_park(P2GWarpSlab<T>& S, P2GParticle3<T>& q, i
   return node;
 }
 
-// Runs + phase 2 over a parked window (call after a __syncwarp() that follows phase 1).
+// Phase 2 proper: lane per (run, x-slab) over the run table S.run_start[0 .. n_runs] of a parked window.
 template <typename T>
-__device__ __forceinline__ void p2g_runs_phase2(P2GWarpSlab<T>& S, const int (&node)[2], int cnt, int lane, int ny,
-                                                int nz, T* __restrict__ grid) {
-  // run heads: first slot of the window, or base cell differs from the predecessor's
-  unsigned heads[2];
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int idx = h * 32 + lane;
-    const int prev = idx > 0 ? S.node0[idx - 1] : -2;
-    heads[h] = __ballot_sync(0xffffffffu, idx < cnt && node[h] != prev);
-  }
-  const int n0 = __popc(heads[0]);
-  const int n_runs = n0 + __popc(heads[1]);
-  {
-    const unsigned below = (1u << lane) - 1u;
-    if (heads[0] & (1u << lane)) S.run_start[__popc(heads[0] & below)] = lane;
-    if (heads[1] & (1u << lane)) S.run_start[n0 + __popc(heads[1] & below)] = 32 + lane;
-    if (lane == 0) S.run_start[n_runs] = cnt;
-  }
-  __syncwarp();
-  // lane per (run, x-slab)
+__device__ __forceinline__ void p2g_accumulate_runs(P2GWarpSlab<T>& S, int n_runs, int lane, int ny, int nz,
+                                                    T* __restrict__ grid) {
   const int n_items = n_runs * 3;
   for (int item = lane; item < n_items; item += 32) {
     const int r = item / 3, li = item - r * 3;
@@ -131,6 +113,31 @@ __device__ __forceinline__ void p2g_runs_phase2(P2GWarpSlab<T>& S, const int (&n
       for (int k = 0; k < 3; ++k)
         red_add4(g + ((long long)j * nz + k) * 4, ax[j * 3 + k], ay[j * 3 + k], az[j * 3 + k], am[j * 3 + k]);
   }
+}
+
+// Runs + phase 2 over a parked window (call after a __syncwarp() that follows phase 1); lane l owns the
+// slots l and 32 + l.
+template <typename T>
+__device__ __forceinline__ void p2g_runs_phase2(P2GWarpSlab<T>& S, const int (&node)[2], int cnt, int lane, int ny,
+                                                int nz, T* __restrict__ grid) {
+  // run heads: first slot of the window, or base cell differs from the predecessor's
+  unsigned heads[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int idx = h * 32 + lane;
+    const int prev = idx > 0 ? S.node0[idx - 1] : -2;
+    heads[h] = __ballot_sync(0xffffffffu, idx < cnt && node[h] != prev);
+  }
+  const int n0 = __popc(heads[0]);
+  const int n_runs = n0 + __popc(heads[1]);
+  {
+    const unsigned below = (1u << lane) - 1u;
+    if (heads[0] & (1u << lane)) S.run_start[__popc(heads[0] & below)] = lane;
+    if (heads[1] & (1u << lane)) S.run_start[n0 + __popc(heads[1] & below)] = 32 + lane;
+    if (lane == 0) S.run_start[n_runs] = cnt;
+  }
+  __syncwarp();
+  p2g_accumulate_runs<T>(S, n_runs, lane, ny, nz, grid);
 }
 
 // USE_PERM: walk the particles through the counting-sort permutation (exactly cell-sorted);

@@ -49,9 +49,7 @@ __device__ __forceinline__ void cp_async4(void* sdst, const void* gsrc) {
 // ahead.  Each thread only ever reads what it copied itself, so no barrier is involved.
 // ROWS: the state carries 1-byte material rows (table mode); compiled out otherwise, the kernel sits
 // exactly at its 64-register budget.
-// PACKED (fp32): the stencil sums in packed fp32 (g2p_accumulate3_packed, FFMA2) -- FFMPM_G2P_PACKED=1, written
-// after this round's GPU budget was spent: host-verified arithmetic, not yet measured.
-template <typename T, int MIN_BLOCKS, bool PRE = false, bool ROWS = false, bool PACKED = false>
+template <typename T, int MIN_BLOCKS, bool PRE = false, bool ROWS = false>
 __global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_tiled3_kernel(DevCfg cfg, StateView<T> src, StateView<T> dst,
                                                                  BinBuffers B, const T* __restrict__ grid, ErrRec* err) {
   using V4 = typename Vec4<T>::type;
@@ -186,10 +184,6 @@ __global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_tiled3_kernel(Dev
         base_fx(x2, cfg, gz, fz);
         const int cb = ((gx - cfg.origin[0] - ox) * TN3 + (gy - cfg.origin[1] - oy)) * TN3 + (gz - cfg.origin[2] - oz);
         T vx, vy, vz, c00, c01, c02, c10, c11, c12, c20, c21, c22;
-        if constexpr (PACKED)
-          g2p_accumulate3_packed([&](int i, int j, int k) { return tile[cb + (i * TN3 + j) * TN3 + k]; }, fx, fy, fz,
-                                 vx, vy, vz, c00, c01, c02, c10, c11, c12, c20, c21, c22);
-        else
         g2p_accumulate3<T>([&](int i, int j, int k) { return tile[cb + (i * TN3 + j) * TN3 + k]; }, fx, fy, fz,
                            vx, vy, vz, c00, c01, c02, c10, c11, c12, c20, c21, c22);
         const T s4 = (T)(4.0 * cfg.inv_dx);
@@ -247,7 +241,7 @@ __global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_tiled3_kernel(Dev
 
 template <typename T>
 int g2p_tiled(const DevCfg& cfg, const StateView<T>& src, const StateView<T>& dst, long long n, BinBuffers& B,
-              const T* grid, ErrRec* err, int sm_count, int blocks_per_sm, cudaStream_t st, int packed = 0) {
+              const T* grid, ErrRec* err, int sm_count, int blocks_per_sm, cudaStream_t st) {
   (void)n;
   cudaMemsetAsync(&B.counters[2], 0, sizeof(int32_t), st);
   int blocks = min(B.n_tiles + 1, sm_count * blocks_per_sm);
@@ -255,16 +249,7 @@ int g2p_tiled(const DevCfg& cfg, const StateView<T>& src, const StateView<T>& ds
     // FFMPM_G2P_PRE=0 disables the cp.async input prefetch (64 registers, 8 CTAs per SM either way)
     static int prefetch = [] { const char* e = getenv("FFMPM_G2P_PRE"); return e ? atoi(e) : 1; }();
     const bool rows = src.material != nullptr;
-    // packed == 2: the packed sums at 6 CTAs per SM (85 registers: no spills) instead of 8 (64 registers)
-    if (packed == 2 && prefetch && rows)
-      g2p_tiled3_kernel<T, 6, true, true, true><<<min(blocks, sm_count * 6), G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
-    else if (packed == 2 && prefetch)
-      g2p_tiled3_kernel<T, 6, true, false, true><<<min(blocks, sm_count * 6), G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
-    else if (packed && prefetch && rows)
-      g2p_tiled3_kernel<T, 8, true, true, true><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
-    else if (packed && prefetch)
-      g2p_tiled3_kernel<T, 8, true, false, true><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
-    else if (prefetch && rows)
+    if (prefetch && rows)
       g2p_tiled3_kernel<T, 8, true, true><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
     else if (prefetch)
       g2p_tiled3_kernel<T, 8, true, false><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);

@@ -13,10 +13,26 @@ from . import _runtime as R
 from .particle import particles_to_soa, write_back_positions
 
 
+# Which kernels the phase functions run: "direct" = one thread per particle on the caller's particle order
+# (no binning); "production" = what ffmpm_substep runs -- cell binning, the warp-autonomous bulk P2G over
+# cell runs, the tiled reordering G2P (results are returned in the caller's order through the id plane).
+_KERNELS = "direct"
+
+
+def set_kernels(kind: str) -> str:
+    """Select "direct" or "production" kernels for the 3D phase functions; returns the previous setting."""
+    global _KERNELS
+    if kind not in ("direct", "production"):
+        raise ValueError(f"unknown kernel path {kind!r}")
+    prev, _KERNELS = _KERNELS, kind
+    return prev
+
+
 def _solver(res, n, inv_dx, dx, dt, volume, gravity, hardening, model):
+    prod = _KERNELS == "production"
     return R.solver_for(3, res, n, inv_dx=float(inv_dx), dx=float(dx), dt=float(dt), volume=float(volume),
                         gravity=float(gravity), hardening=float(hardening), model=model,
-                        p2g_mode="scatter", reorder=False)
+                        p2g_mode="tiled" if prod else "scatter", reorder=prod)
 
 
 def _upload(s, soa, v, F, C, Jp):
@@ -32,6 +48,8 @@ def p2g(inv_dx, hardening, dx, dt, volume, grid_velocity, grid_mass, particles, 
     s = _solver(G - 1, len(soa), inv_dx, dx, dt, volume, 0.0, hardening, model)
     _upload(s, soa, v, F, C, Jp)
     s.clear_grid()
+    if s.reorder:
+        s.bin()
     s.p2g()
     s.check_errors()
     gv, gm = R.grid_from_device(s)
@@ -68,6 +86,8 @@ def g2p(inv_dx, dt, grid_velocity, particles, v, F, C, Jp, model: str = "neo_hoo
     s = _solver(G - 1, len(soa), inv_dx, 1.0 / inv_dx, dt, 1.0, 0.0, 1.0, model)
     _upload(s, soa, v, F, C, Jp)
     R.grid_to_device(s, grid_velocity, np.zeros(grid_velocity.shape[:-1] + (1,)))
+    if s.reorder:
+        s.bin()
     s.g2p()
     s.check_errors()
     out = s.get_particles()

@@ -52,6 +52,16 @@ def _c(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
+def host_threads() -> int:
+    """Threads the CPU baseline runs on: every core this process may be scheduled on.  NOT
+    omp_get_max_threads(): torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, which would
+    silently turn the baseline of an N > 1 launch into a single-threaded one."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 # ---- reference-shaped helpers (same argument order as oracle/mpm_oracle.py) ----
 def p2g_3d(inv_dx, hardening, dx, dt, volume, grid_velocity, grid_mass, x, mass, mu0, lam0, v, F, C_, Jp, model="neo_hookean"):
     n = len(x)
@@ -100,7 +110,7 @@ def time_sample(scene, budget_s: float = 15.0, threads=None, substeps=None):
     sub-block of the same density on the same grid resolution), m chosen so that a
     few substeps take about `budget_s` seconds."""
     L = lib()
-    cores = threads or L.oracle_max_threads()
+    cores = threads or host_threads()
     L.oracle_set_threads(cores)
     d, res = scene.dim, scene.res
     G = res + 1
@@ -141,7 +151,7 @@ class SampleRunner:
 
     def __init__(self, scene, m: int, threads=None):
         self.L = lib()
-        self.cores = threads or self.L.oracle_max_threads()
+        self.cores = threads or host_threads()
         self.L.oracle_set_threads(self.cores)
         self.scene, self.m = scene, int(min(m, scene.n))
         d, res = scene.dim, scene.res

@@ -4,7 +4,7 @@
 // SOURCE the GPU runs against LAPACK / the NumPy oracle (tests/test_kernel_math_host.py).  Test
 // infrastructure only: nothing in the product links this file.
 #include "../../femflow_b200/csrc/mpm_direct.cuh"
-#include "../../femflow_b200/csrc/mpm_p2g_pair.cuh"
+#include "../../femflow_b200/csrc/mpm_bin.cuh"
 
 using namespace ffmpm;
 
@@ -110,17 +110,6 @@ void km_prepare3_f64(int res, int n_nodes, double inv_dx, double dx, double dt, 
 }
 
 void km_g2p_accumulate3_f32(long long n, const float* f, const float* gv, float* v, float* c) { accumulate3<float>(n, f, gv, v, c); }
-void km_g2p_accumulate3_packed(long long n, const float* f, const float* gv, float* v, float* c) {
-  for (long long p = 0; p < n; ++p) {
-    const float* g = gv + 81 * p;
-    float o[12];
-    g2p_accumulate3_packed([&](int i, int j, int k) { const float* q = g + ((i * 3 + j) * 3 + k) * 3; return make_float4(q[0], q[1], q[2], 7.0f); },
-                           f[3 * p], f[3 * p + 1], f[3 * p + 2], o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7], o[8], o[9], o[10],
-                           o[11]);
-    for (int e = 0; e < 3; ++e) v[3 * p + e] = o[e];
-    for (int e = 0; e < 9; ++e) c[9 * p + e] = o[3 + e];
-  }
-}
 void km_g2p_accumulate3_f64(long long n, const double* f, const double* gv, double* v, double* c) { accumulate3<double>(n, f, gv, v, c); }
 
 // 1 when the fp32 perturbation series accepted the strain (else the caller's fp64 path would run)
@@ -167,114 +156,34 @@ void km_base_fx_f64(double inv_dx, long long n, const double* x, int* base, doub
   for (long long p = 0; p < n; ++p) base_fx<double>(x[p], c, base[p], fx[p]);
 }
 
-// Packed-fp32 phase 1 (mpm_p2g_pair.cuh: p2g_prepare3_pair): particle p is paired with particle p + n/2,
-// as a lane pairs the slots `lane` and `lane + 32` of a window; an odd last particle is evaluated alone.
-void km_prepare3_pair_f32(int res, int n_nodes, double inv_dx, double dx, double dt, double volume, double hardening,
-                          int fp32_stress, int index_fp32, long long n, const float* x, const float* v, const float* C,
-                          const float* F, const float* mass, const float* mu, const float* lam, int* base, float* fx,
-                          float* aff, float* mv, float* m, int* ok) {
-  const DevCfg cfg = make_cfg(res, n_nodes, inv_dx, dx, dt, volume, hardening, 0, fp32_stress, index_fp32);
-  const long long half = (n + 1) / 2;
-  auto getter = [&](long long p) {
-    return [=](int k) -> float {
-      if (k < P2G_V) return x[3 * p + k];
-      if (k < P2G_C) return v[3 * p + (k - P2G_V)];
-      if (k < P2G_F) return C[9 * p + (k - P2G_C)];
-      if (k < P2G_MASS) return F[9 * p + (k - P2G_F)];
-      return k == P2G_MASS ? mass[p] : (k == P2G_MU ? mu[p] : lam[p]);
-    };
-  };
-  auto store = [&](long long p, const P2GParticle3<float>& q) {
-    ok[p] = q.ok ? 1 : 0;
-    base[3 * p] = q.bx; base[3 * p + 1] = q.by; base[3 * p + 2] = q.bz;
-    fx[3 * p] = q.fx; fx[3 * p + 1] = q.fy; fx[3 * p + 2] = q.fz;
-    if (!q.ok) return;
-    const float a[9] = {q.a00, q.a01, q.a02, q.a10, q.a11, q.a12, q.a20, q.a21, q.a22};
-    for (int e = 0; e < 9; ++e) aff[9 * p + e] = a[e];
-    mv[3 * p] = q.mvx; mv[3 * p + 1] = q.mvy; mv[3 * p + 2] = q.mvz;
-    m[p] = q.m;
-  };
-  for (long long p = 0; p < half; ++p) {
-    const long long pb = p + half;
-    const bool live_b = pb < n;
-    P2GParticle3<float> qa{}, qb{};
-    p2g_prepare3_pair(cfg, getter(p), getter(live_b ? pb : p), true, true, live_b, qa, qb);
-    store(p, qa);
-    if (live_b) store(pb, qb);
+// The left-form series h(G) = G p(G) of mpm_math.cuh at a GIVEN tier (the warp-autonomous P2G evaluates every
+// particle of a warp at the tier of its most strained one): G as (xx, xy, xz, yy, yz, zz).
+void km_left_stress_h(int tier, long long n, const float* G, float* H) {
+  for (long long p = 0; p < n; ++p) {
+    const float* g = G + 6 * p;
+    const Sym3f s{g[0], g[1], g[2], g[3], g[4], g[5]};
+    const Sym3f h = tier == 0 ? left_stress_h<0>(s) : tier == 1 ? left_stress_h<1>(s) : tier == 2 ? left_stress_h<2>(s) : left_stress_h<3>(s);
+    float* o = H + 6 * p;
+    o[0] = h.xx; o[1] = h.xy; o[2] = h.xz; o[3] = h.yy; o[4] = h.yz; o[5] = h.zz;
   }
 }
 
-// Phase 1 of the packed kernels exactly as a warp runs it (FFMPM_P2G_VARIANT=8/9/11): lane l prepares slots l and
-// l + 32 of a window of `cnt` <= 64 particles through p2g_prepare3_pair_sink and parks them with P2GPairParker;
-// slots >= cnt are parked as zeros.  Returns the parked window as payload[64][16] (PP_* order) and node0[64].
-void km_pair_phase1_window(int res, int n_nodes, double inv_dx, double dx, double dt, double volume, double hardening,
-                           int index_fp32, int cnt, const float* x, const float* v, const float* C, const float* F,
-                           const float* mass, const float* mu, const float* lam, float* payload, int* node0_out) {
-  const DevCfg cfg = make_cfg(res, n_nodes, inv_dx, dx, dt, volume, hardening, 0, 1, index_fp32);
-  static float4 pay[P2G_PAIR_PLANES][P2G_PAIR_PADDED];
-  static int node0[P2G_WINDOW];
-  for (int c = 0; c < P2G_PAIR_PLANES; ++c)
-    for (int s = 0; s < P2G_PAIR_PADDED; ++s) pay[c][s] = make_float4(NAN, NAN, NAN, NAN);
-  for (int q = 0; q < P2G_WINDOW; ++q) node0[q] = -7;
-  auto getter = [&](long long p) {
-    return [=](int k) -> float {
-      if (k < P2G_V) return x[3 * p + k];
-      if (k < P2G_C) return v[3 * p + (k - P2G_V)];
-      if (k < P2G_F) return C[9 * p + (k - P2G_C)];
-      if (k < P2G_MASS) return F[9 * p + (k - P2G_F)];
-      return k == P2G_MASS ? mass[p] : (k == P2G_MU ? mu[p] : lam[p]);
-    };
-  };
-  for (int lane = 0; lane < 32; ++lane) {
-    const bool live_a = lane < cnt, live_b = 32 + lane < cnt;
-    P2GPairParker park{pay, node0, lane, n_nodes, n_nodes, (float)dx, {-1, -1}};
-    p2g_prepare3_pair_sink(cfg, getter(live_a ? lane : 0), getter(live_b ? 32 + lane : 0), true, live_a, live_b, park);
-    if (!live_a) p2g_park_pair_zero(pay, lane);
-    if (!live_b) p2g_park_pair_zero(pay, 32 + lane);
-  }
-  for (int q = 0; q < P2G_WINDOW; ++q) {
-    for (int c = 0; c < 16; ++c) payload[16 * q + c] = *p2g_pair_slot(pay, q, c);
-    node0_out[q] = node0[q];
+// E = F - I, G = F F^T - I and ||G||_F^2 as the kernels form them, and the tier the norm selects.
+void km_left_strain(long long n, const float* F, float* G, float* r2, int* tier, float* jm1) {
+  for (long long p = 0; p < n; ++p) {
+    const float* f = F + 9 * p;
+    Mat3<float> E;
+    Sym3f g;
+    left_strain3(Mat3<float>{f[0], f[1], f[2], f[3], f[4], f[5], f[6], f[7], f[8]}, E, g, r2[p]);
+    float* o = G + 6 * p;
+    o[0] = g.xx; o[1] = g.xy; o[2] = g.xz; o[3] = g.yy; o[4] = g.yz; o[5] = g.zz;
+    tier[p] = stress_tier_of(r2[p]);
+    jm1[p] = jm1_of(E);
   }
 }
 
-// Packed-fp32 P2G phase 2 (mpm_p2g_pair.cuh): park `n_slots` payloads (16 floats each, PP_* order) in the
-// pair-major shared-memory image exactly as phase 1 does, then accumulate x-slab `li` of the run [r0, r1).
-// Slots >= n_slots are parked as the kernel parks the tail of the last window.  Returns 0, or -1 when two
-// slots alias in the layout.
-int km_pair_accumulate(int n_slots, const float* payload, int r0, int r1, int li, float* out) {
-  static float4 pay[P2G_PAIR_PLANES][P2G_PAIR_PADDED];
-  for (int c = 0; c < P2G_PAIR_PLANES; ++c)
-    for (int s = 0; s < P2G_PAIR_PADDED; ++s) pay[c][s] = make_float4(NAN, NAN, NAN, NAN);   // unwritten smem is garbage
-  static int node0[P2G_WINDOW];
-  for (int q = 0; q < P2G_WINDOW; ++q) {
-    if (q < n_slots) {
-      for (int c = 0; c < 16; ++c)
-        if (!(*p2g_pair_slot(pay, q, c) != *p2g_pair_slot(pay, q, c))) return -1;   // already written: layout not injective
-      const float* v = payload + 16 * q;
-      P2GParticle3<float> pq{};
-      pq.ok = true; pq.bx = q; pq.by = 0; pq.bz = 0;
-      pq.mvx = v[PP_MVX]; pq.mvy = v[PP_MVY]; pq.mvz = v[PP_MVZ]; pq.m = v[PP_M];
-      pq.a00 = v[PP_A00]; pq.a01 = v[PP_A01]; pq.a02 = v[PP_A02]; pq.fx = v[PP_FX];
-      pq.a10 = v[PP_A10]; pq.a11 = v[PP_A11]; pq.a12 = v[PP_A12]; pq.fy = v[PP_FY];
-      pq.a20 = v[PP_A20]; pq.a21 = v[PP_A21]; pq.a22 = v[PP_A22]; pq.fz = v[PP_FZ];
-      if (p2g_park_pair(pay, node0, pq, q, 1.0f, 1, 1) != q) return -2;          // phase 1's own parking (dx = 1)
-    } else {
-      p2g_park_pair_zero(pay, q);
-    }
-  }
-  float o[9][4];
-  p2g_pair_accumulate(pay, r0, r1, li, o);
-  for (int e = 0; e < 9; ++e)
-    for (int d = 0; d < 4; ++d) out[4 * e + d] = o[e][d];
-  return 0;
-}
-
-// Bank of the first word each of `n_lanes` lanes touches when lane l reads slot pair start[l] of a plane
-// (LDS.128: 4 consecutive banks from there); the test asserts that aligned runs do not collide.
-void km_pair_banks(int n_lanes, const int* start, int* bank) {
-  for (int l = 0; l < n_lanes; ++l) bank[l] = (p2g_pair_pad(start[l]) * 4) % 32;
-}
+float km_stress_coef(int tier, int i) { return stress_coef(tier, i); }
+float km_stress_tier_r(int tier) { return stress_tier_r(tier); }
 
 void km_grid_op3_f32(const int* res, const int* n, int origin0, double dx, double dt, double gravity, float* grid, const float* halo_lo,
                      int planes_lo, const float* halo_hi, int planes_hi, int n_col, const double* cp, const double* cn) {

@@ -53,9 +53,20 @@ def _floors(p, mass, grid_velocity_ref):
 
 
 # --------------------------------------------------------------------------- #
+@pytest.fixture(params=["direct", "production"])
+def kernels(request):
+    """Kernel path of the reference-signature 3D phase functions (three_d.set_kernels): the thread-per-particle
+    kernels on the caller's order, or what ffmpm_substep runs (binning, bulk P2G over cell runs, tiled G2P)."""
+    from femflow_b200.solvers.mpm import three_d
+    prev = three_d.set_kernels(request.param)
+    yield request.param
+    three_d.set_kernels(prev)
+
+
 @pytest.mark.parametrize("name", ["kat3d", "block3d", "rest3d", "walls3d"])
-def test_3d_phase_functions_match_reference(name, dtype):
-    """three_d.p2g / grid_op / g2p with the reference's signatures vs the reference's outputs."""
+def test_3d_phase_functions_match_reference(name, dtype, kernels):
+    """three_d.p2g / grid_op / g2p with the reference's signatures vs the reference's outputs
+    (three_d/p2g.py:14-80, grid_op.py:5-47, g2p.py:9-59), through both kernel paths."""
     from femflow_b200.solvers.mpm import three_d
     from femflow_b200.solvers.mpm.particle import ParticleArray
     g = load_golden(name)
@@ -80,6 +91,34 @@ def test_3d_phase_functions_match_reference(name, dtype):
     assert rel_err(v, g["v_out"], fl["vel"]) < tol
     assert rel_err(F, g["F_out"], 1.0) < tol
     assert rel_err(C, g["C_out"], fl["C"]) < tol
+
+
+@pytest.mark.parametrize("name", ["kat3d", "block3d", "rest3d", "walls3d"])
+def test_3d_production_chain_matches_reference(name, dtype):
+    """The phases chained on the device exactly as ffmpm_substep issues them -- binning, bulk P2G, the grid
+    update over the node blocks listed by the binning (grid_op3_blocks_kernel only runs when nothing touches
+    the grid in between), tiled reordering G2P -- against the reference's grid velocity and particle outputs."""
+    from femflow_b200.mpm import MpmSolver
+    g = load_golden(name)
+    p = _p3(g)
+    n = len(g["x"])
+    fl = _floors(p, g["mass"], _grid(g, "grid_velocity"))
+    s = MpmSolver(3, p["res"], p["dt"], p["volume"], p["gravity"], p["hardening"], capacity=max(n, 1), dx=p["dx"],
+                  inv_dx=p["inv_dx"], dtype=getattr(torch, dtype), p2g_mode="tiled")
+    s.set_particles(g["x"], g["v"], g["F"], g["C"], None, g["mass"], g["mu0"], g["lam0"])
+    s.clear_grid(); s.bin(); s.p2g(); s.grid_op()
+    vel = s.grid(readonly=True).double().cpu().numpy()
+    # the chain is one substep; its error budget is the sum of the phases'
+    assert rel_err(vel[..., :3], _grid(g, "grid_velocity"), fl["vel"]) < 2 * TOL[dtype]
+    assert rel_err(vel[..., 3:4], _grid(g, "grid_mass")) < TOL[dtype]
+    s.g2p()
+    s.check_errors()
+    out = {k: t.double().cpu().numpy() for k, t in s.get_particles().items()}
+    assert rel_err(out["x"], g["x_out"], 1.0) < 2 * TOL[dtype]
+    assert rel_err(out["v"], g["v_out"], fl["vel"]) < 2 * TOL[dtype]
+    assert rel_err(out["F"], g["F_out"], 1.0) < 2 * TOL[dtype]
+    assert rel_err(out["C"], g["C_out"], fl["C"]) < 2 * TOL[dtype]
+    s.close()
 
 
 @pytest.mark.parametrize("mode", ["scatter", "auto"])
@@ -368,29 +407,18 @@ def test_multi_substep_pipelines_vs_oracle(mode):
     s.close()
 
 
-@pytest.mark.skipif(os.environ.get("FFMPM_TEST_EXPERIMENTAL") != "1",
-                    reason="packed-fp32 P2G (FFMPM_P2G_VARIANT 7/8/9) was written after the round's GPU budget ran out: "
-                           "its arithmetic is checked on the host (tests/test_kernel_math_host.py); set "
-                           "FFMPM_TEST_EXPERIMENTAL=1 to run it on a GPU")
-@pytest.mark.parametrize("variant", [7, 8, 9, 10, 11, 12, "7cap4", "11econ", "11left", "g2p", "g2p6"])
+@pytest.mark.parametrize("variant", [0, 1, 5])
 @pytest.mark.parametrize("n_materials", [1, 3, 300])
-def test_packed_fp32_p2g_variants(variant, n_materials, monkeypatch):
-    """P2G with two particles per FFMA2 (mpm_p2g_pair.cuh) and the G2P stencil sums in packed fp32 ("g2p":
-    FFMPM_G2P_PACKED=1): the grid after P2G and 12 chained substeps against the oracle, with one material, a
-    material table and material planes; a particle count that leaves the last window ragged (n % 64 != 0, odd)."""
+def test_p2g_kernel_variants(variant, n_materials, monkeypatch):
+    """The binned P2G kernels selectable with FFMPM_P2G_VARIANT -- 0: through the counting-sort permutation,
+    1: physical order without prefetch (p2g_runs3_kernel), 5: the production kernel (p2g_bulk3_kernel: cp.async window
+    prefetch, adjacent slot pairs, warp-uniform series degree) -- with one material, a material table and material
+    planes: the grid after P2G and 12 chained substeps against the oracle; a particle count that leaves the last
+    window ragged (n % 64 != 0, odd)."""
     from femflow_b200 import scenes
     from femflow_b200.mpm import MpmSolver
     from oracle import native as ON
-    if str(variant).startswith("g2p"):
-        monkeypatch.setenv("FFMPM_G2P_PACKED", "2" if variant == "g2p6" else "1")
-    elif variant in ("11econ", "11left"):
-        monkeypatch.setenv("FFMPM_P2G_VARIANT", "11")
-        monkeypatch.setenv("FFMPM_FP32_STRESS", "2" if variant == "11econ" else "3")   # economised coefficients / left form
-    elif variant == "7cap4":
-        monkeypatch.setenv("FFMPM_P2G_VARIANT", "7")
-        monkeypatch.setenv("FFMPM_P2G_RUN_CAP", "4")          # runs cut every 4 slots: twice the (run, slab) items
-    else:
-        monkeypatch.setenv("FFMPM_P2G_VARIANT", str(variant))
+    monkeypatch.setenv("FFMPM_P2G_VARIANT", str(variant))
     sc = scenes.elastic_block(3, 64, 20, 2, seed=4)
     n = sc.n - 37
     rng = np.random.default_rng(0)
@@ -399,6 +427,11 @@ def test_packed_fp32_p2g_variants(variant, n_materials, monkeypatch):
     m = f32(sc.mass * (1 + 0.25 * k / n_materials)); mu = f32(sc.mu_0 * (1 + 0.5 * k / n_materials))
     lam = f32(sc.lambda_0 * (1 - 0.125 * k / n_materials))
     x, v, F, C = (a[:n].astype(np.float64) for a in (sc.x, sc.v, sc.F, sc.C))
+    # a few particles far beyond the series (fp64 Newton path inside a window of series particles) and at every tier
+    F = F.copy()
+    F[5] = f32(np.eye(3) + 0.3 * rng.uniform(-1, 1, (3, 3)))
+    F[1000:1064] = f32(np.eye(3) + 1e-4 * rng.uniform(-1, 1, (64, 3, 3)))
+    F[2000:2064] = f32(np.eye(3) + 4e-3 * rng.uniform(-1, 1, (64, 3, 3)))
     s = MpmSolver(3, sc.res, sc.dt, sc.volume, sc.gravity, sc.hardening, capacity=n)
     s.set_particles(x, v, F, C, None, m, mu, lam)
     s.clear_grid(); s.bin(); s.p2g()
@@ -408,6 +441,7 @@ def test_packed_fp32_p2g_variants(variant, n_materials, monkeypatch):
     g = s.grid().double().cpu().numpy()
     assert s.poll_error() == 0
     assert rel_err(g[..., 3:], gm) < 1e-5 and rel_err(g[..., :3], gv) < 1e-5
+    F[5] = np.eye(3)              # the chained run without the violently strained particle (its P2G is checked above)
     s.set_particles(x, v, F, C, None, m, mu, lam)
     steps = 12
     s.substep(steps)

@@ -98,7 +98,7 @@ def test_cell_indexing_is_bit_exact(km, res):
 @pytest.mark.parametrize("strain", [0.0, 1e-6, 1e-4, 1.5e-3, 1e-2, 4e-2, 0.3])
 def test_fp32_stress_tiers_against_lapack(km, strain):
     """affine = stress + mass*C of three_d/p2g.py:57-65 (utils.py:120-135) from the fp32 kernel path: the
-    series tiers (3 / 5 / 8 terms by the Frobenius norm of G) and the fp64 Newton fallback beyond, each
+    left-form series tiers (degree 2 .. 5 by the Frobenius norm of G = F F^T - I) and the fp64 Newton fallback beyond, each
     to 1e-5 of the batch's largest STRESS entry (C = 0, so nothing hides the stress) -- the bar of
     test_stress_accuracy_across_series_tiers on the GPU."""
     rng = np.random.default_rng(11)
@@ -123,7 +123,7 @@ def test_fp32_stress_tiers_against_lapack(km, strain):
     Cf = np.zeros(9, np.float32)
     km.km_affine3_f32.restype = C.c_int
     took = km.km_affine3_f32(ptr(Ff), ptr(Cf), C.c_float(1.0), C.c_float(1.0), C.c_float(1.0), C.c_float(1.0), ptr(A))
-    G = F[0].T @ F[0] - np.eye(3)
+    G = F[0] @ F[0].T - np.eye(3)
     assert bool(took) == bool(np.linalg.norm(G) < 0.15 * (1 - 1e-4)) or abs(np.linalg.norm(G) - 0.15) < 1e-4
 
 
@@ -188,10 +188,10 @@ def test_p2g_payload_and_oob_flag(km):
     assert np.abs(aff_s[3:] - want_s).max() / np.abs(want_s).max() < 1e-12
 
 
-@pytest.mark.parametrize("dtype,tol", [("f32", 2e-6), ("f64", 1e-14), ("packed", 2e-6)])
+@pytest.mark.parametrize("dtype,tol", [("f32", 2e-6), ("f64", 1e-14)])
 def test_separable_g2p_stencil_sums(km, dtype, tol):
     """v = sum w gv, C = sum (w gv) (x) dpos (three_d/g2p.py:31-43) folded z -> y -> x against the
-    node-by-node sums of the reference; "packed" is the FFMA2 form (g2p_accumulate3_packed, FFMPM_G2P_PACKED=1)."""
+    node-by-node sums of the reference."""
     rng = np.random.default_rng(8)
     n = 2000
     np_dt = np.float64 if dtype == "f64" else np.float32
@@ -241,103 +241,6 @@ def test_2d_stress_and_svd_roundtrip(km):
         wantG = (U * sig[:, None, :]) @ np.swapaxes(Vh, 1, 2)
         assert np.abs(G.reshape(n, 2, 2)[sel] - wantG[sel]).max() < 1e-9, snow
         assert np.abs(det[sel] - np.linalg.det(wantG[sel])).max() < 1e-9, snow
-
-
-def test_packed_fp32_p2g_phase2(km):
-    """mpm_p2g_pair.cuh (FFMPM_P2G_VARIANT=7): runs walked two particles per packed-fp32 instruction.  The
-    pair-major shared-memory layout, the masking of a partner that belongs to the neighbouring run (odd
-    run start / odd run end, also against the zero-parked tail of the last window) and the node sums of
-    three_d/p2g.py:67-80 -- against the plain per-particle sums in fp64."""
-    rng = np.random.default_rng(21)
-    n = 64
-    pay = np.zeros((n, 16), np.float32)
-    pay[:, 0:3] = rng.normal(size=(n, 3))                       # m v
-    pay[:, 3] = rng.uniform(0.5, 2, n)                          # m
-    A = rng.normal(size=(n, 3, 3)).astype(np.float32)           # affine * dx
-    f = rng.uniform(0.5, 1.5, size=(n, 3)).astype(np.float32)
-    for r in range(3):
-        pay[:, 4 + 4 * r:7 + 4 * r] = A[:, r]
-        pay[:, 7 + 4 * r] = f[:, r]
-    km.km_pair_accumulate.restype = C.c_int
-
-    def want(r0, r1, li):
-        out = np.zeros((9, 4))
-        fd = f[r0:r1].astype(np.float64)
-        w = O.bspline_weights(fd)
-        for j in range(3):
-            for k in range(3):
-                wt = w[li, :, 0] * w[j, :, 1] * w[k, :, 2]
-                dpos = np.array((li, j, k)) - fd
-                mom = pay[r0:r1, 0:3].astype(np.float64) + np.einsum("pab,pb->pa", A[r0:r1].astype(np.float64), dpos)
-                out[j * 3 + k, :3] = (wt[:, None] * mom).sum(0)
-                out[j * 3 + k, 3] = (wt * pay[r0:r1, 3]).sum()
-        return out
-
-    cases = [(0, 8), (8, 16), (3, 4), (5, 12), (4, 13), (7, 8), (0, 64), (1, 63), (56, 61)]
-    for n_slots, (r0, r1) in [(64, c) for c in cases] + [(61, (56, 61)), (1, (0, 1))]:
-        for li in range(3):
-            out = np.zeros((9, 4), np.float32)
-            rc = km.km_pair_accumulate(C.c_int(n_slots), ptr(pay), C.c_int(r0), C.c_int(r1), C.c_int(li), ptr(out))
-            assert rc == 0
-            ref = want(r0, r1, li)
-            assert np.isfinite(out).all()
-            assert np.abs(out - ref).max() <= 3e-6 * np.abs(ref).max(), (n_slots, r0, r1, li)
-    # eight aligned runs of eight particles (the 8-ppc benchmark block): 24 lanes, 8 distinct addresses, all 32 banks
-    start = np.repeat(np.arange(8, dtype=np.int32) * 4, 3)
-    bank = np.zeros(len(start), np.int32)
-    km.km_pair_banks(C.c_int(len(start)), ptr(start), ptr(bank))
-    assert sorted(set(bank.tolist())) == list(range(0, 32, 4))
-
-
-def prepare3_pair(km, res, x, v, Cm, F, mass, mu, lam, dt, volume, hardening=1.0, fp32_stress=1):
-    n = len(x)
-    arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (x, v, Cm.reshape(n, 9), F.reshape(n, 9), mass, mu, lam)]
-    base = np.zeros((n, 3), np.int32); fx = np.zeros((n, 3), np.float32); aff = np.zeros((n, 9), np.float32)
-    mv = np.zeros((n, 3), np.float32); m = np.zeros(n, np.float32); ok = np.zeros(n, np.int32)
-    km.km_prepare3_pair_f32(C.c_int(res), C.c_int(res + 1), C.c_double(float(res)), C.c_double(1.0 / res), C.c_double(dt),
-                            C.c_double(volume), C.c_double(hardening), C.c_int(fp32_stress), C.c_int(int(res & (res - 1) == 0)),
-                            C.c_longlong(n), *(ptr(a) for a in arrs), ptr(base), ptr(fx), ptr(aff), ptr(mv), ptr(m), ptr(ok))
-    return base, fx, aff.reshape(n, 3, 3), mv, m, ok.astype(bool)
-
-
-@pytest.mark.parametrize("series", [1, 2, 3])
-@pytest.mark.parametrize("strain", [0.0, 1e-6, 1e-4, 1.5e-3, 4e-3, 1e-2, 2.5e-2, 4e-2, 6e-2, 0.3, "mixed"])
-def test_packed_fp32_stress_pairs(km, strain, series):
-    """p2g_prepare3_pair (FFMPM_P2G_VARIANT=8/9): the stress of two particles per packed instruction.  Same
-    1e-5 bar against LAPACK as the one-particle path on every series tier; a pair with one particle beyond
-    the series, outside the grid or NaN falls back to the one-particle routine for both; index, weights
-    offset and mass*v are the one-particle routine's bits.  series = 2: the economised coefficient tiers
-    (FFMPM_FP32_STRESS=2; strains chosen to land in each of its five tiers); series = 3: the left form
-    (F - R) F^T = B - B^(1/2) as a series in F F^T - I, no products with F (FFMPM_FP32_STRESS=3)."""
-    rng = np.random.default_rng(13)
-    res, n = 32, 4001                                            # odd: the last particle has no partner
-    dx = 1.0 / res
-    vol = float(f32((dx / 2) ** 3))
-    x = f32(rng.uniform(0.25, 0.75, size=(n, 3)))
-    if strain == "mixed":
-        amp = rng.choice([1e-5, 1e-3, 2e-2, 6e-2, 0.3], size=(n, 1, 1))
-        x[5] = [0.99, 0.5, 0.5]; x[n // 2 + 7, 1] = np.nan; x[11] = [0.0, 0.5, 0.5]
-    else:
-        amp = strain
-    F = f32(np.eye(3) + amp * rng.uniform(-1, 1, size=(n, 3, 3)))
-    v = f32(rng.normal(size=(n, 3)))
-    Cm = f32(rng.normal(0, 0.05, size=(n, 3, 3))) if strain == "mixed" else np.zeros((n, 3, 3))
-    mass = f32(rng.uniform(0.5, 1.5, n) * vol); mu = f32(rng.uniform(3000, 5000, n)); lam = f32(rng.uniform(2000, 3000, n))
-    ref = prepare3(km, "f32", res, x, v, Cm, F, mass, mu, lam, 1e-4, vol)
-    got = prepare3_pair(km, res, x, v, Cm, F, mass, mu, lam, 1e-4, vol, fp32_stress=series)
-    ok = ref[5]
-    assert np.array_equal(got[5], ok)
-    if strain == "mixed":
-        assert not ok[5] and not ok[n // 2 + 7] and ok[11] and ok.sum() == n - 2
-    assert np.array_equal(got[0][ok], ref[0][ok]) and np.array_equal(got[1][ok], ref[1][ok])   # base, fx: same bits
-    assert np.array_equal(got[3][ok], ref[3][ok]) and np.array_equal(got[4][ok], ref[4][ok])  # m v, m: same bits
-    want = O.fixed_corotated_stress_3d(F[ok], float(res), mu[ok], lam[ok], 1e-4, vol, mass[ok], Cm[ok])
-    scale = np.abs(want).max()
-    if strain == 0.0:
-        assert np.all(got[2] == 0.0)
-    else:
-        assert np.abs(got[2][ok] - want).max() / scale < 1e-5
-        assert np.abs(got[2][ok] - ref[2][ok]).max() / scale < 2e-6      # and next to the one-particle evaluation
 
 
 @pytest.mark.parametrize("dtype,tol", [("f32", 2e-6), ("f64", 1e-14)])
@@ -414,118 +317,89 @@ def test_tile_major_bin_keys(km, res):
         assert not ok[0] and (origin > 0 or (ok[1] and ok[2]))
 
 
-@pytest.mark.parametrize("cnt", [64, 63, 33, 32, 5])
-def test_packed_phase1_parks_the_window_like_the_scalar_path(km, cnt):
-    """The warp-level phase 1 of FFMPM_P2G_VARIANT=8/9/11 replayed lane by lane on the host: heads parked before
-    the stress, affine entries after it (P2GPairParker), one-particle fallback for out-of-grid / over-strained
-    partners, zero-parked tail -- the parked window must equal what the scalar routine would have parked
-    (index, m v, m, f bit for bit; affine * dx to fp32 round-off of the stress)."""
-    rng = np.random.default_rng(cnt)
-    res, n = 32, 64
-    dx = 1.0 / res
-    vol = float(f32((dx / 2) ** 3))
-    x = f32(rng.uniform(0.2, 0.8, size=(n, 3)))
-    x[3] = [0.995, 0.5, 0.5]                                     # out of grid: its partner (slot 35) takes the fallback too
-    amp = rng.choice([1e-4, 2e-2, 6e-2], size=(n, 1, 1)); amp[40] = 0.4      # slot 40: beyond the series -> pair (8, 40) falls back
-    F = f32(np.eye(3) + amp * rng.uniform(-1, 1, size=(n, 3, 3)))
-    v = f32(rng.normal(size=(n, 3))); Cm = f32(rng.normal(0, 0.05, size=(n, 3, 3)))
-    mass = f32(rng.uniform(0.5, 1.5, n) * vol); mu = f32(rng.uniform(3000, 5000, n)); lam = f32(rng.uniform(2000, 3000, n))
-    base, fx, aff, mv, m, ok = prepare3(km, "f32", res, x, v, Cm, F, mass, mu, lam, 1e-4, vol)
-    arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (x, v, Cm.reshape(n, 9), F.reshape(n, 9), mass, mu, lam)]
-    pay = np.zeros((64, 16), np.float32); node0 = np.zeros(64, np.int32)
-    km.km_pair_phase1_window(C.c_int(res), C.c_int(res + 1), C.c_double(float(res)), C.c_double(dx), C.c_double(1e-4), C.c_double(vol),
-                             C.c_double(1.0), C.c_int(1), C.c_int(cnt), *(ptr(a) for a in arrs), ptr(pay), ptr(node0))
-    G = res + 1
-    scale = np.abs(aff[ok]).max() * dx
-    for q in range(64):
-        if q >= cnt:
-            assert np.array_equal(pay[q, [0, 1, 2, 3, 4, 5, 6, 8, 9, 10, 12, 13, 14]], np.zeros(13, np.float32))
-            assert np.array_equal(pay[q, [7, 11, 15]], np.float32([0.5, 0.5, 0.5]))
-            continue
-        if not ok[q]:
-            assert node0[q] == -1 and not pay[q, :7].any() and pay[q, 7] == 0.5
-            continue
-        assert node0[q] == (base[q, 0] * G + base[q, 1]) * G + base[q, 2]
-        assert np.array_equal(pay[q, 0:3], mv[q]) and pay[q, 3] == m[q]
-        assert np.array_equal(pay[q, [7, 11, 15]], fx[q])
-        got_a = pay[q, [4, 5, 6, 8, 9, 10, 12, 13, 14]].reshape(3, 3)
-        assert np.abs(got_a - aff[q] * np.float32(dx)).max() <= 2e-6 * scale, q
-
-
-def test_packed_p2g_window_end_to_end_against_the_oracle(km):
-    """One window of the packed-fp32 P2G on the host, arithmetic end to end: phase 1 as the warp runs it
-    (km_pair_phase1_window), runs of equal base cell, the packed accumulation of every (run, x-slab), and the
-    scatter of the nine node sums per item -- against the oracle's P2G (three_d/p2g.py:14-80) of the same 64
-    cell-sorted particles.  Only the device-side plumbing (ballots, REDs, prefetch) is left to the GPU test."""
-    rng = np.random.default_rng(3)
-    res, n = 16, 64
-    G, dx = res + 1, 1.0 / res
-    vol = float(f32((dx / 2) ** 3))
-    cells = rng.integers(4, 7, size=(9, 3))                       # nine occupied cells, ~7 particles each, some repeated
-    cell = cells[np.sort(rng.integers(0, 9, n))]
-    x = f32((cell + 0.5 + rng.uniform(0.02, 0.98, size=(n, 3))) * dx)
-    base, _ = O.base_and_fx(x, float(res))
-    order = np.lexsort((base[:, 2], base[:, 1], base[:, 0]))      # cell-sorted, as the reordering G2P leaves the buffer
-    x = x[order]
-    F = f32(np.eye(3) + 0.03 * rng.uniform(-1, 1, size=(n, 3, 3)))
-    v = f32(rng.normal(size=(n, 3))); Cm = f32(rng.normal(0, 0.5, size=(n, 3, 3)))
-    mass = f32(rng.uniform(0.5, 1.5, n) * vol); mu = f32(rng.uniform(3000, 5000, n)); lam = f32(rng.uniform(2000, 3000, n))
-    arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (x, v, Cm.reshape(n, 9), F.reshape(n, 9), mass, mu, lam)]
-    pay = np.zeros((64, 16), np.float32); node0 = np.zeros(64, np.int32)
-    km.km_pair_phase1_window(C.c_int(res), C.c_int(G), C.c_double(float(res)), C.c_double(dx), C.c_double(1e-4), C.c_double(vol),
-                             C.c_double(1.0), C.c_int(1), C.c_int(n), *(ptr(a) for a in arrs), ptr(pay), ptr(node0))
-    assert (node0 >= 0).all()
-    heads = [0] + [q for q in range(1, n) if node0[q] != node0[q - 1]] + [n]
-    assert len(heads) - 1 >= 5
-    grid = np.zeros((G * G * G, 4))
-    km.km_pair_accumulate.restype = C.c_int
-    for r0, r1 in zip(heads[:-1], heads[1:]):
-        for li in range(3):
-            out = np.zeros((9, 4), np.float32)
-            assert km.km_pair_accumulate(C.c_int(n), ptr(pay), C.c_int(r0), C.c_int(r1), C.c_int(li), ptr(out)) == 0
-            for j in range(3):
-                for k in range(3):
-                    grid[node0[r0] + (li * G + j) * G + k] += out[j * 3 + k]
-    gv = np.zeros((G, G, G, 3)); gm = np.zeros((G, G, G, 1))
-    O.p2g_3d(float(res), 1.0, dx, 1e-4, vol, gv, gm, x, mass, mu, lam, v, F, Cm, np.ones((n, 1)))
-    grid = grid.reshape(G, G, G, 4)
-    assert np.abs(grid[..., 3:] - gm).max() <= 1e-5 * np.abs(gm).max()
-    assert np.abs(grid[..., :3] - gv).max() <= 1e-5 * np.abs(gv).max()
-
-
-def test_economised_series_table_is_the_generated_one():
-    """The coefficient tiers embedded in mpm_p2g_pair.cuh are what scripts/series_economized.py generates, each tier
-    keeps q within 5e-8 of (1 - (1+x)^(-1/2)) / x on its interval with fp32 coefficients, and evaluated in fp32 on
-    matrices at the tier's upper bound it is no worse than the Taylor tiers the scalar path uses (~2e-7, rounding)."""
-    import re
+def test_economised_series_table_is_the_generated_one(km):
+    """The coefficient tiers embedded in mpm_math.cuh (stress_coef / stress_tier_r) are what
+    scripts/series_economized.py generates for the left form, each tier keeps p within 5e-8 of
+    (1 + x - sqrt(1 + x)) / x on its interval with fp32 coefficients, and evaluated in fp32 on matrices at the
+    tier's upper bound the series sits at rounding level (~2e-7)."""
     import sys
     root = os.path.dirname(HERE)
     sys.path.insert(0, os.path.join(root, "scripts"))
     import series_economized as E
-    src = open(os.path.join(CSRC, "mpm_p2g_pair.cuh")).read()
-    def check(body, tiers, left):
-        bounds = [float(v) for v in re.findall(r"r2 < ([0-9.]+)f \* [0-9.]+f", body)] + [0.15]
-        assert bounds == [r for r, _ in tiers]
-        blocks = re.split(r"\} else", body)
-        assert len(blocks) == len(tiers) + 1
-        fn = E.p_exact if left else E.q_exact
-        for (r, deg, coef), block in zip(E.table(left), blocks[1:]):
-            vals = {k: float(v) for k, v in re.findall(r"(c\[\d\]|ca|cb) = (-?[0-9.e-]+)f;", block)}
-            mine = [vals[f"c[{i}]"] for i in range(deg - 1)] + [vals["cb"], vals["ca"]]
-            assert np.array_equal(np.float32(mine), coef), (left, r)
-            assert int(re.search(r"top = (\d);", block).group(1)) == deg - 2
-            assert E.uniform_error(r, coef, fn) < 5.1e-8
-            assert E.worst_matrix_error(r, coef, n=300, left=left) < 3e-7
+    km.km_stress_coef.restype = C.c_float
+    km.km_stress_tier_r.restype = C.c_float
+    tab = E.table(left=True)
+    assert len(tab) == 4
+    for tier, (r, deg, coef) in enumerate(tab):
+        assert deg == tier + 2
+        assert np.float32(km.km_stress_tier_r(C.c_int(tier))) == np.float32(r)
+        mine = np.float32([km.km_stress_coef(C.c_int(tier), C.c_int(i)) for i in range(deg + 1)])
+        assert np.array_equal(mine, coef), (tier, mine, coef)
+        assert km.km_stress_coef(C.c_int(tier), C.c_int(deg + 1)) == 0.0
+        assert E.uniform_error(r, coef, E.p_exact) < 5.1e-8
+        assert E.worst_matrix_error(r, coef, n=300, left=True) < 3e-7
 
-    check(src[src.index("} else if (r2 < 0.007f * 0.007f)"):src.index("const F2 ca2 = f2(ca), cb2 = f2(cb);")], E.TIERS, False)
-    check("} else " + src[src.index("if (r2 < 0.0136f * 0.0136f)"):src.index("} else if (!economised) {")], E.TIERS_LEFT, True)
+
+@pytest.mark.parametrize("tier", [0, 1, 2, 3])
+def test_series_at_a_higher_tier_than_needed(km, tier):
+    """The warp-autonomous P2G evaluates all 64 particles of a window at the tier of the most strained one:
+    h(G) = G p(G) with the tier-t polynomial must hold the bar for EVERY smaller strain as well (a higher-degree
+    interpolant on a wider interval, used well inside it), against the eigendecomposition."""
+    rng = np.random.default_rng(tier)
+    n = 3000
+    r_hi = [0.0136, 0.0436, 0.112, 0.15][tier]
+    a = rng.uniform(-1, 1, (n, 3, 3))
+    g = (a + np.swapaxes(a, 1, 2)) / 2
+    g[::3] = np.einsum("ni,nj->nij", *(2 * [rng.normal(size=(n, 3))[::3]]))            # rank one: spectral radius = norm
+    norm = np.linalg.norm(g, axis=(1, 2))
+    target = r_hi * 10.0 ** rng.uniform(-4, 0, n) * 0.999
+    g = (g / norm[:, None, None] * target[:, None, None]).astype(np.float32)
+    G6 = np.ascontiguousarray(np.stack([g[:, 0, 0], g[:, 0, 1], g[:, 0, 2], g[:, 1, 1], g[:, 1, 2], g[:, 2, 2]], 1))
+    H6 = np.zeros_like(G6)
+    km.km_left_stress_h(C.c_int(tier), C.c_longlong(n), ptr(G6), ptr(H6))
+    gs = np.zeros((n, 3, 3))
+    for (i, j), col in zip(((0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2)), range(6)):
+        gs[:, i, j] = gs[:, j, i] = G6[:, col].astype(np.float64)
+    w, q = np.linalg.eigh(gs)
+    exact = np.einsum("nij,nj,nkj->nik", q, 1 + w - np.sqrt(1 + w), q)
+    got = np.zeros((n, 3, 3))
+    for (i, j), col in zip(((0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2)), range(6)):
+        got[:, i, j] = got[:, j, i] = H6[:, col]
+    rel = np.abs(got - exact).max(axis=(1, 2)) / np.abs(exact).max(axis=(1, 2))
+    assert rel.max() < 5e-7, (tier, rel.max())
+
+
+def test_left_strain_and_tier_selection(km):
+    """G = F F^T - I = E + E^T + E E^T formed from E = F - I (no cancellation), its Frobenius norm, the tier it
+    selects (beyond 0.15 and NaN: the fp64 path) and J - 1 without cancellation, against fp64."""
+    rng = np.random.default_rng(3)
+    n = 6000
+    amp = 10.0 ** rng.uniform(-6, -0.5, (n, 1, 1))
+    F = f32(np.eye(3) + amp * rng.uniform(-1, 1, (n, 3, 3)))
+    F[7] = np.nan
+    Ff = np.ascontiguousarray(F.reshape(n, 9), dtype=np.float32)
+    G6 = np.zeros((n, 6), np.float32); r2 = np.zeros(n, np.float32); tier = np.zeros(n, np.int32); jm1 = np.zeros(n, np.float32)
+    km.km_left_strain(C.c_longlong(n), ptr(Ff), ptr(G6), ptr(r2), ptr(tier), ptr(jm1))
+    Gd = F @ np.swapaxes(F, 1, 2) - np.eye(3)
+    want6 = np.stack([Gd[:, 0, 0], Gd[:, 0, 1], Gd[:, 0, 2], Gd[:, 1, 1], Gd[:, 1, 2], Gd[:, 2, 2]], 1)
+    ok = np.arange(n) != 7
+    scale = np.abs(want6[ok]).max(axis=1)
+    assert (np.abs(G6[ok] - want6[ok]).max(axis=1) / scale).max() < 5e-7
+    norm = np.linalg.norm(Gd[ok], axis=(1, 2))
+    bounds = np.array([0.0136, 0.0436, 0.112, 0.15])
+    want_tier = np.searchsorted(bounds, norm, side="right")
+    near = np.min(np.abs(norm[:, None] - bounds[None, :]) / bounds[None, :], axis=1) < 1e-5
+    assert np.array_equal(tier[ok][~near], want_tier[~near])
+    assert tier[7] == 4                                            # NaN: beyond every tier
+    J = np.linalg.det(F[ok])
+    strain = np.abs(F[ok] - np.eye(3)).max(axis=(1, 2))            # J - 1 = tr E + O(E^2): the scale of its terms
+    assert (np.abs(jm1[ok] - (J - 1)) / strain).max() < 1e-6
 
 
 @pytest.mark.parametrize("angle,strain", [(0.02, 1e-3), (0.1, 1e-3), (0.1, 3e-2), (0.3, 1e-3), (0.3, 3e-2)])
-def test_stress_forms_under_rotation(km, angle, strain):
-    """F = R(angle) (I + strain): E = F - I is then O(angle), and G = E + E^T + E^T E (or E E^T) cancels in fp32.
-    Every form of the fp32 stress -- scalar, packed Taylor, economised, left -- must stay inside the 1e-5 bar and
-    next to each other (the left form shares the right form's conditioning)."""
+def test_stress_under_rotation(km, angle, strain):
+    """F = R(angle) (I + strain): E = F - I is then O(angle), and G = E + E^T + E E^T cancels in fp32; the series
+    declines once ||G||_F >= 0.15 and the fp64 path takes over -- either way inside the 1e-5 bar."""
     rng = np.random.default_rng(int(angle * 1000 + strain * 1e6))
     n, res = 2000, 32
     dx = 1.0 / res
@@ -543,9 +417,5 @@ def test_stress_forms_under_rotation(km, angle, strain):
     Z = np.zeros((n, 3, 3)); mass = np.full(n, vol); mu = np.full(n, f32(4166.67)); lam = np.full(n, f32(2777.78))
     want = O.fixed_corotated_stress_3d(F, float(res), mu, lam, 1e-4, vol, mass, Z)
     scale = np.abs(want).max()
-    errs = [np.abs(prepare3(km, "f32", res, x, np.zeros((n, 3)), Z, F, mass, mu, lam, 1e-4, vol)[2] - want).max() / scale]
-    for form in (1, 2, 3):
-        got = prepare3_pair(km, res, x, np.zeros((n, 3)), Z, F, mass, mu, lam, 1e-4, vol, fp32_stress=form)
-        errs.append(np.abs(got[2] - want).max() / scale)
-    assert max(errs) < 1e-5, errs
-    assert max(errs) < 2.0 * min(errs) + 2e-7, errs
+    got = prepare3(km, "f32", res, x, np.zeros((n, 3)), Z, F, mass, mu, lam, 1e-4, vol)[2]
+    assert np.abs(got - want).max() / scale < 1e-5

@@ -98,14 +98,43 @@ def test_headless_paper_scenes_reproduce_the_reference_setup():
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("FFMPM_TEST_EXPERIMENTAL") != "1",
-                    reason="composed of tested parts but not yet run on hardware as a whole (GPU budget); FFMPM_TEST_EXPERIMENTAL=1")
 def test_headless_runner_runs_experiment_0(tmp_path):
+    """paper_1.multi_drop_experiment(0) (paper_1.py:75-114): the FULL 35 321-particle scene, 100 substeps through
+    the headless runner (MPMSimulation thread, snapshot ring, .npy dump) against the C port of the reference loops
+    started from the same float32-vertex positions (simulation.py:81-83)."""
     torch = pytest.importorskip("torch")
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
-    from femflow_b200.simulation.mpm.headless import run
-    sim, seconds = run(0, steps=6, outdir=str(tmp_path / "out"))
-    assert sim.error is None and not sim.running and len(sim.displacements) == 7
-    assert sim.displacements[-1].shape == (3 * 35321,) and np.isfinite(sim.displacements[-1]).all()
-    assert sorted(os.listdir(sim.outdir), key=lambda f: int(f.split(".")[0])) == [f"{i}.npy" for i in range(7)]
+    from femflow_b200.simulation.mpm.headless import multi_drop_scene, run
+    from femflow_b200.solvers.mpm.utils import Ev_to_lambda, Ev_to_mu
+    from oracle import native as ON
+    steps = 100
+    sim, seconds = run(0, steps=steps, outdir=str(tmp_path / "out"))
+    n = 35321
+    assert sim.error is None and not sim.running and len(sim.displacements) == steps + 1
+    assert sim.displacements[-1].shape == (3 * n,) and np.isfinite(sim.displacements[-1]).all()
+    assert sorted(os.listdir(sim.outdir), key=lambda f: int(f.split(".")[0])) == [f"{i}.npy" for i in range(steps + 1)]
+    # the port on the same scene
+    meshes, params, ctor = multi_drop_scene(0)
+    coeff = ctor["tightening_coeff"]
+    x = np.concatenate([(m.vertices.reshape(-1, 3) * coeff).astype(np.float64) for m in meshes])
+    counts = [len(m.vertices) // 3 for m in meshes]
+    mass = np.concatenate([np.full(c, float(p[0])) for c, p in zip(counts, params)])
+    mu = np.concatenate([np.full(c, Ev_to_mu(*p[1:])) for c, p in zip(counts, params)])
+    lam = np.concatenate([np.full(c, Ev_to_lambda(*p[1:])) for c, p in zip(counts, params)])
+    assert len(x) == n
+    v = np.zeros((n, 3)); F = np.tile(np.eye(3), (n, 1, 1)); C = np.zeros((n, 3, 3))
+    res = ctor["grid_res"]
+    mid = None
+    for k in range(steps):
+        ON.solve_mls_mpm_3d(res, float(res), ctor["hardening"], 1.0 / res, ctor["dt"], ctor["volume"], ctor["force"],
+                            x, mass, mu, lam, v, F, C)
+        if k == 9:
+            mid = (x / coeff).reshape(-1)
+    V = max(np.abs(v).max(), ctor["dt"] * 9.8)
+    assert rel_err(sim.displacements[10], mid) < 1e-5 * 10
+    assert rel_err(sim.displacements[steps], (x / coeff).reshape(-1)) < 1e-5 * steps
+    assert rel_err(sim.particles.pos, x, 1.0) < 1e-5 * steps
+    assert rel_err(sim.v, v, V) < 1e-5 * steps
+    assert rel_err(sim.F, F, 1.0) < 1e-5 * steps
+    assert rel_err(sim.C, C, 4 * res * V) < 1e-5 * steps
