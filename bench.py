@@ -110,6 +110,61 @@ def cpu_baseline(scene, budget_s: float = 15.0, threads=None):
     return onative.time_sample(scene, budget_s=budget_s, threads=threads)
 
 
+def parity_block(solver, scene):
+    """One more substep of the TIMED workload, from the state the timed region left behind, on the GPU and by the
+    C port of the reference loops (oracle/mpm_oracle.c) started from the same downloaded state: max-norm errors
+    relative to the floors of SURVEY 8d.  The checker, never the thing measured."""
+    from oracle import native as onative
+    import torch
+    d, res, n = scene.dim, scene.res, solver.num_particles
+    st = solver.get_particles()
+    x, v, F, C = (st[k].double().cpu().numpy() for k in ("x", "v", "F", "C"))
+    Jp = st["Jp"].double().cpu().numpy() if "Jp" in st else np.ones((n, 1))
+    del st
+    solver.substep(1)
+    n_oob = solver.poll_error()
+    onative.lib().oracle_set_threads(onative.host_threads())
+    t0 = time.perf_counter()
+    if d == 3:
+        mass = np.full(n, scene.mass); mu = np.full(n, scene.mu_0); lam = np.full(n, scene.lambda_0)
+        gv, _ = onative.solve_mls_mpm_3d(res, float(res), scene.hardening, 1.0 / res, scene.dt, scene.volume, scene.gravity,
+                                         x, mass, mu, lam, v, F, C)
+    else:
+        gv, _ = onative.solve_mls_mpm_2d(res, float(res), scene.hardening, scene.mu_0, scene.lambda_0, scene.mass, 1.0 / res,
+                                         scene.dt, scene.volume, scene.gravity, x, v, F, C, Jp)
+    cpu_s = time.perf_counter() - t0
+    V = max(float(np.abs(gv).max()), scene.dt * abs(scene.gravity))
+    del gv
+    out = solver.get_particles()
+
+    def err(name, ref, floor):
+        worst, chunk = 0.0, 1 << 22
+        flat = ref.reshape(n, -1)
+        for a in range(0, n, chunk):
+            got = out[name][a:a + chunk].double().cpu().numpy().reshape(-1, flat.shape[1])
+            worst = max(worst, float(np.abs(got - flat[a:a + chunk]).max()))
+        return worst / floor
+    e = {"x": err("x", x, 1.0), "v": err("v", v, V), "F": err("F", F, 1.0), "C": err("C", C, 4 * res * V)}
+    if d == 2:
+        e["Jp"] = err("Jp", Jp, 1.0)
+    return {"against": "C port of the reference loops (oracle/mpm_oracle.c, fp64), one substep from the downloaded state of the "
+                       "timed workload, all particles", "particles": int(n), "max_norm_rel_err": e, "tolerance": 1e-5,
+            "within_tolerance": bool(max(e.values()) < 1e-5), "n_oob": int(n_oob), "port_seconds": round(cpu_s, 2),
+            "floors": "x, F: 1; v: V = max(|v_grid,ref|, dt |g|); C: 4 inv_dx V (SURVEY 8d)"}
+
+
+def numba_baseline(timeout_s: float = 240.0):
+    """The UNMODIFIED reference's numba substep timed on this box (oracle/time_numba_reference.py, a subprocess: numba's
+    JIT stays out of this process).  None when baseline/_ref or numba is not there."""
+    try:
+        proc = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "time_numba_reference.py")], capture_output=True,
+                              text=True, timeout=timeout_s, env={**os.environ, "CUDA_VISIBLE_DEVICES": ""})
+        line = [ln for ln in proc.stdout.splitlines() if ln.startswith("{")][-1]
+        return json.loads(line)
+    except Exception as e:
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm on all host threads.  The reference is
     pure Python/numba and cannot travel to the GPU box, so this is the C port of its loops
@@ -218,6 +273,8 @@ def main():
     ap.add_argument("--workload", default="3d16m")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity block (one substep of the timed workload against the C port)")
+    ap.add_argument("--no-numba", action="store_true", help="skip timing the reference's own numba path (baseline/_ref, ~60 s)")
     ap.add_argument("--p2g-mode", default="auto")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--material", default="auto", choices=["auto", "planes"],
@@ -395,6 +452,14 @@ def main():
                 acc[nm] += evs[i + 1].elapsed_time(evs[i + 2])
         phases = {k: v / reps for k, v in acc.items()}
 
+    # ---- parity of the timed workload (N = 1): one more substep against the C port ----
+    parity = None
+    if world == 1 and not dam and not args.no_parity:
+        try:
+            parity = parity_block(solver, scene)
+        except Exception as ex:  # the checker never takes the measurement down with it
+            parity = {"error": repr(ex)}
+
     # ---- end to end through host buffers (pinned), every step: H2D state, substep, D2H result ----
     e2e = None
     if not dam:
@@ -495,6 +560,8 @@ def main():
             cpu = cpu_baseline(scene)
         except Exception as e:  # the baseline is reported, never the product path
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+        if not args.no_numba:
+            cpu["numba"] = numba_baseline()
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -507,13 +574,14 @@ def main():
                    "l2": ("inputs larger than L2 (no flush)" if n * (112 if scene.dim == 3 else 52) > 2 * 126e6
                           else "particle state fits in the 126 MB L2 (flagged: HBM fraction is not meaningful)"),
                    "n_oob": n_oob,
-                   "material_layout": (solver if world == 1 else solver.local.solver).material_layout,
+                   "material_layout": (solver.local.solver if hasattr(solver, "local") else solver).material_layout,
                    "parallelism": (f"{world} slabs along x, halo sum over "
                                    f"{'NCCL p2p' if args.halo == 'p2p' else 'symmetric-memory puts'} every substep, migration every "
                                    f"{args.margin} substeps") if world > 1 else "single GPU",
                    **({"slab_particles": slab_counts, "slab_cells": [list(r) for r in solver.plan.all_ranges],
                        "rebalanced": solver.driver.rebalanced} if world > 1 else {})},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        "parity": parity,
     }
     print(json.dumps(line))
     if world > 1:

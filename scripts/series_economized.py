@@ -1,8 +1,10 @@
-"""Economised series for the fp32 stress: M = I - (I+G)^(-1/2) = G q(G), with q fitted on [-r_t, r_t] by Chebyshev
-interpolation (near-minimax) instead of truncating its Taylor series.  For the same 1e-7 bar the degree drops from
-7 to 5 at the strain of the headline workload (warp maximum ||G||_F ~ 0.08) and to 4 below 0.069: two / three
-matrix products fewer out of seven.  Prints the tier table that mpm_p2g_pair.cuh embeds (kEcon*); the CPU suite
-regenerates it and compares (tests/test_kernel_math_host.py).
+"""Economised series for the fp32 stress (femflow_b200/csrc/mpm_math.cuh).  LEFT form (the one the kernels use):
+(F - R) F^T = h(G) = G p(G) with G = F F^T - I and p(x) = (1 + x - sqrt(1 + x)) / x fitted on [-r_t, r_t] by Chebyshev
+interpolation (near-minimax) instead of truncating its Taylor series.  Prints the tier table that mpm_math.cuh embeds
+(stress_coef / stress_tier_r, TIERS_LEFT below); the CPU suite regenerates it and compares
+(tests/test_kernel_math_host.py::test_economised_series_table_is_the_generated_one).  The right form
+M = I - (I+G)^(-1/2) = G q(G) with G = F^T F - I, which round 1 shipped as a truncated Taylor series and needs two
+more products with F, is kept here for the comparison only.
 
 Tiers are chosen so that the uniform error of q on the tier's interval, WITH the coefficients rounded to fp32,
 stays below 5e-8 (relative 1e-7 on M, whose leading coefficient is 1/2)."""
@@ -11,7 +13,7 @@ from numpy.polynomial import chebyshev as Ch, polynomial as P
 
 # (upper bound of ||G||_F for the tier, degree of q)
 TIERS = ((0.007, 2), (0.025, 3), (0.069, 4), (0.109, 5), (0.15, 6))
-# The same for the LEFT form (FFMPM_FP32_STRESS=3): (F - R) F^T = B - B^(1/2) with B = F F^T = I + G_B, i.e. the stress
+# The LEFT form: (F - R) F^T = B - B^(1/2) with B = F F^T = I + G_B, i.e. the stress
 # term is the matrix function h(G_B) = G_B p(G_B), p(x) = (1 + x - sqrt(1 + x)) / x = 1 - 1 / (sqrt(1 + x) + 1), of the
 # left Cauchy-Green strain -- no product with F at all, and the square-root series converges faster than the
 # inverse square root's: degree 4 up to ||G||_F = 0.112.

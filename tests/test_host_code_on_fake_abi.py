@@ -163,9 +163,15 @@ def gpu_test_bodies(monkeypatch):
     _runtime.clear_cache()
 
 
+@pytest.mark.parametrize("kernels", ["direct", "production"])
 @pytest.mark.parametrize("name", ["kat3d", "block3d", "rest3d", "walls3d"])
-def test_phase_wrappers_against_reference_goldens(gpu_test_bodies, name):
-    gpu_test_bodies.test_3d_phase_functions_match_reference(name, "float64")
+def test_phase_wrappers_against_reference_goldens(gpu_test_bodies, name, kernels):
+    from femflow_b200.solvers.mpm import three_d
+    prev = three_d.set_kernels(kernels)       # "production": the wrappers' bin + reorder marshalling (ids, ping-pong)
+    try:
+        gpu_test_bodies.test_3d_phase_functions_match_reference(name, "float64", kernels)
+    finally:
+        three_d.set_kernels(prev)
 
 
 def test_solve_wrapper_on_the_paper_scene_and_error_convention(gpu_test_bodies):
