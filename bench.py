@@ -40,7 +40,7 @@ def make_scene(workload: str, seed: int = 0, cells_x=None, res_x=None):
     from femflow_b200 import scenes
     if workload == "2d1m":
         return scenes.config_2d_1m(seed)
-    if workload == "3d16m":
+    if workload in ("3d16m", "3d16m-blocks"):
         return scenes.config_3d_16m(seed)
     if workload == "3d16m-rest":          # same block as the reference starts it: F = I, v = 0 (simulation.py:76-79)
         sc = scenes.elastic_block(3, 256, 128, 2, seed, perturb=False)
@@ -281,6 +281,7 @@ def main():
                     help="per-particle material layout (N=1): auto = table/rows when <= 256 distinct triples, planes = 3 scalar planes")
     ap.add_argument("--slab-timing", action="store_true", help="N>1: print per-phase CUDA-event times per rank to stderr")
     ap.add_argument("--margin", type=int, default=4, help="slab halo margin in cells = substeps between migrations")
+    ap.add_argument("--drift", type=float, default=0.1, help="N>1 coupled bar: drift along x in cells per substep")
     ap.add_argument("--e2e-streamed", action="store_true",
                     help="N=1, 3D: also measure the host-buffer path as a stream of independent steps (double-buffered: the "
                          "upload of step k+1 overlaps the download of step k on the full-duplex link); reported as "
@@ -342,8 +343,19 @@ def main():
         n = solver.num_particles
     elif world > 1:
         from femflow_b200.distributed import SlabSolver
-        solver = SlabSolver.from_scene(scene, rank, world, dev, p2g_mode=args.p2g_mode, margin=args.margin,
-                                       halo=args.halo)
+        if args.workload == "3d16m-blocks":
+            # round-1 weak scaling: one independent block in the middle of every slab (empty halos, no migration)
+            solver = SlabSolver.from_scene(scene, rank, world, dev, p2g_mode=args.p2g_mode, margin=args.margin,
+                                           halo=args.halo)
+            coupling = "independent block per slab (halo planes carry zeros, nothing migrates)"
+        else:
+            # BASELINE configs[3]: ONE bar through all slabs, drifting along x: non-zero halos, migration every period
+            solver = SlabSolver.from_bar(scene, rank, world, dev, p2g_mode=args.p2g_mode, margin=args.margin,
+                                         halo=args.halo, drift_cells_per_substep=args.drift)
+            scene.name = solver.scene_name
+            coupling = (f"coupled: one bar through all slabs drifting {args.drift} cells/substep "
+                        "(halo planes carry mass and momentum, a particle layer migrates every period)")
+        n = solver.num_particles
     else:
         solver = MpmSolver(scene.dim, scene.res, scene.dt, scene.volume, scene.gravity, scene.hardening,
                            capacity=n, device=dev, mass=scene.mass, mu_0=scene.mu_0, lambda_0=scene.lambda_0,
@@ -414,11 +426,16 @@ def main():
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-        cnt = torch.tensor([solver.num_particles], device=dev, dtype=torch.int64)
+        drv = solver.driver
+        cnt = torch.tensor([solver.num_particles, drv.migrated, getattr(drv, "migrate_rounds", 0),
+                            getattr(drv, "migrate_overflow", 0)], device=dev, dtype=torch.int64)
         per_rank = [torch.zeros_like(cnt) for _ in range(world)]
         dist.all_gather(per_rank, cnt)
-        slab_counts = [int(t.item()) for t in per_rank]
+        slab_counts = [int(t[0].item()) for t in per_rank]
         n_total = sum(slab_counts)
+        mig_stats = {"particles_received": sum(int(t[1].item()) for t in per_rank),       # whole job, timed region + warm-up
+                     "rounds": max(int(t[2].item()) for t in per_rank),
+                     "overflow": sum(int(t[3].item()) for t in per_rank)}
     else:
         n_total = n
     clocks = sampler.stop() if rank == 0 else None
@@ -489,7 +506,7 @@ def main():
             core._bind(n)
             solver.substep(1)
             lv = core.live
-            m = core.num_particles
+            m = min(core.num_particles, n)       # N > 1: a migration round inside the step may have changed the count
             for k, t in host_out.items():
                 t[..., :m].copy_(getattr(lv, k)[..., :m], non_blocking=True)
 
@@ -506,8 +523,12 @@ def main():
             t = torch.tensor([e_ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e_ms = float(t.item())
-        e2e = {"value": n_total * args.e2e_steps / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
-               "d2h_bytes_per_step": d2h * world, "ms_per_step": e_ms / args.e2e_steps,
+        if world > 1:       # bytes of the whole job: the ranks' particle counts differ
+            t = torch.tensor([h2d, d2h], device=dev, dtype=torch.int64)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            h2d, d2h = int(t[0].item()), int(t[1].item())
+        e2e = {"value": n_total * args.e2e_steps / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": e_ms / args.e2e_steps,
                "api": "ffmpm C ABI via MpmSolver (host SoA pinned buffers in, x/v/C/F out, every step)"}
 
     if e2e is not None and args.e2e_streamed and world == 1 and scene.dim == 3 and core.reorder:
@@ -576,8 +597,10 @@ def main():
                    "n_oob": n_oob,
                    "material_layout": (solver.local.solver if hasattr(solver, "local") else solver).material_layout,
                    "parallelism": (f"{world} slabs along x, halo sum over "
-                                   f"{'NCCL p2p' if args.halo == 'p2p' else 'symmetric-memory puts'} every substep, migration every "
-                                   f"{args.margin} substeps") if world > 1 else "single GPU",
+                                   f"{'NCCL p2p' if args.halo == 'p2p' else 'symmetric-memory puts'} every substep, device-side "
+                                   f"migration (pack/unpack kernels) every {solver.driver.migrate_every} substeps; "
+                                   + ("dam break" if dam else coupling)) if hasattr(solver, "driver") else "single GPU",
+                   **({"migration": mig_stats} if world > 1 else {}),
                    **({"slab_particles": slab_counts, "slab_cells": [list(r) for r in solver.plan.all_ranges],
                        "rebalanced": solver.driver.rebalanced} if world > 1 else {})},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,

@@ -12,7 +12,7 @@ FFMPM_E_INVALID, FFMPM_E_CUDA, FFMPM_E_OOB, FFMPM_E_STATE = -1, -2, -3, -4
 FFMPM_F32, FFMPM_F64 = 0, 1
 FFMPM_NEO_HOOKEAN, FFMPM_SNOW = 0, 1
 FFMPM_P2G_AUTO, FFMPM_P2G_SCATTER, FFMPM_P2G_TILED, FFMPM_P2G_FUSED = 0, 1, 2, 3
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class FfMpmConfig(C.Structure):
@@ -61,6 +61,9 @@ PROTOTYPES = {
     "ffmpm_collide": (C.c_int, [H, C.c_void_p]),
     "ffmpm_set_owned_range": (C.c_int, [H, C.c_int32, C.c_int32]),
     "ffmpm_leaver_count_ptr": (C.c_int, [H, C.POINTER(C.c_void_p)]),
+    "ffmpm_migrate_rows": (C.c_int32, [H]),
+    "ffmpm_migrate_pack": (C.c_int, [H, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "ffmpm_migrate_unpack": (C.c_int, [H, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "ffmpm_grid_ptr": (C.c_int, [H, C.POINTER(C.c_void_p)]),
     "ffmpm_grid_view": (C.c_int, [H, C.POINTER(C.c_void_p)]),
     "ffmpm_bin_ptrs": (C.c_int, [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),

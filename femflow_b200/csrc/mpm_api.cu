@@ -16,6 +16,7 @@
 #include "mpm_p2g_bulk.cuh"
 #include "mpm_tiled.cuh"
 #include "mpm_g2p2g.cuh"
+#include "mpm_migrate.cuh"
 
 using namespace ffmpm;
 
@@ -632,6 +633,67 @@ int ffmpm_set_owned_range(FfMpmHandle* h, int32_t own_lo, int32_t own_hi) {
 int ffmpm_leaver_count_ptr(FfMpmHandle* h, int32_t** count) {
   if (!h || !h->ws || !count) return set_err(FFMPM_E_STATE, "workspace not set");
   *count = &h->bin.counters[3];
+  return FFMPM_OK;
+}
+
+// ---- slab migration (mpm_migrate.cuh) ----
+static int mig_rows(const FfMpmHandle* h) { return MIG_ROWS + (h->st[0].Jp ? 1 : 0); }
+
+int32_t ffmpm_migrate_rows(const FfMpmHandle* h) { return h ? mig_rows(h) : FFMPM_E_INVALID; }
+
+static MigRec* mig_rec(FfMpmHandle* h) { return reinterpret_cast<MigRec*>(h->bin.counters + 32); }
+
+template <typename T>
+static int migrate_pack_t(FfMpmHandle* h, void* out_lo, void* out_hi, int cap, cudaStream_t s) {
+  StateView<T> sv = view<T>(h, h->st[h->live]);
+  sv.material = h->st[h->live].material;   // rows travel with their particle whatever the table size
+  MigRec* rec = mig_rec(h);
+  CUDA_TRY(cudaMemsetAsync(rec, 0, sizeof(MigRec), s));
+  const int rows = mig_rows(h);
+  if (h->n > 0) {
+    mig_pack_kernel<T><<<(unsigned)((h->n + 255) / 256), 256, 0, s>>>(h->dev, sv, h->n, (T*)out_lo, (T*)out_hi, cap, rows, rec, h->bin.keys);
+    const unsigned blocks = (unsigned)((2 * (long long)cap + 255) / 256);
+    mig_match_kernel<T><<<blocks, 256, 0, s>>>(sv, h->n, cap, rec, h->bin.keys, h->bin.rank, h->bin.perm);
+    mig_fill_kernel<T><<<blocks, 256, 0, s>>>(sv, rows, rec, h->bin.rank, h->bin.perm);
+  }
+  mig_headers_kernel<T><<<1, 32, 0, s>>>((T*)out_lo, (T*)out_hi, cap, rec);
+  return check_launch(h, h->n > 0 ? 4 : 1);
+}
+
+int ffmpm_migrate_pack(FfMpmHandle* h, void* out_lo, void* out_hi, int32_t cap, void* stream) {
+  int rc = ready(h);
+  if (rc) return rc;
+  if (h->cfg.dim != 3) return set_err(FFMPM_E_INVALID, "slab migration is 3D only");
+  if (!h->st[h->live].id) return set_err(FFMPM_E_STATE, "slab migration needs the id plane (it marks the vacated slots)");
+  if (cap < 1 || cap > (1 << 22) || 2 * (int64_t)cap > h->capacity) return set_err(FFMPM_E_INVALID, "outbox capacity must be in [1, min(2^22, capacity / 2)]");
+  // the binning of the live buffer dies with the round: its key / rank / perm arrays are the scratch lists
+  if (h->bin_pending) {
+    CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, h->ev_join, 0));
+    h->bin_pending = false;
+  }
+  h->binned = false;
+  h->prebinned = false;
+  h->scatter_ahead = false;
+  return h->cfg.dtype == FFMPM_F64 ? migrate_pack_t<double>(h, out_lo, out_hi, cap, (cudaStream_t)stream)
+                                   : migrate_pack_t<float>(h, out_lo, out_hi, cap, (cudaStream_t)stream);
+}
+
+template <typename T>
+static int migrate_unpack_t(FfMpmHandle* h, const void* in_lo, const void* in_hi, int cap, cudaStream_t s) {
+  StateView<T> sv = view<T>(h, h->st[h->live]);
+  sv.material = h->st[h->live].material;
+  mig_unpack_kernel<T><<<(unsigned)((2 * (long long)cap + 255) / 256), 256, 0, s>>>(sv, (const T*)in_lo, (const T*)in_hi, cap, mig_rows(h), mig_rec(h));
+  return check_launch(h, 1);
+}
+
+int ffmpm_migrate_unpack(FfMpmHandle* h, const void* in_lo, const void* in_hi, int32_t cap, int32_t* record, void* stream) {
+  int rc = ready(h);
+  if (rc) return rc;
+  if (cap < 1 || !record) return set_err(FFMPM_E_INVALID, "bad migration arguments");
+  rc = h->cfg.dtype == FFMPM_F64 ? migrate_unpack_t<double>(h, in_lo, in_hi, cap, (cudaStream_t)stream)
+                                 : migrate_unpack_t<float>(h, in_lo, in_hi, cap, (cudaStream_t)stream);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(record, mig_rec(h), 6 * sizeof(int32_t), cudaMemcpyDefault, (cudaStream_t)stream));
   return FFMPM_OK;
 }
 

@@ -57,14 +57,21 @@ struct ErrRec {
 // the subtraction of 0.5, the truncation and fx are all EXACT in fp32 for every position
 // inside the grid, so the fp32 path returns the same bits at a fraction of the issue slots
 // (6 fp64 conversion chains per particle in G2P, 3 in P2G).
+// The exact-fp32 form (inv_dx a power of two): x*inv_dx, the subtraction of 0.5, the truncation and fx are exact.
+FFMPM_HD void base_fx_f32(float xs, float inv_dx, int& base, float& fx) {
+  const float s = xs * inv_dx;
+  float t = s - 0.5f;
+  t = fminf(fmaxf(t, -1.0e9f), 1.0e9f);   // keeps the int conversion defined; such values are out of grid anyway
+  base = (int)t;
+  fx = s - (float)base;
+}
+
 template <typename T>
 FFMPM_HD void base_fx(T xs, const DevCfg& cfg, int& base, T& fx) {
   if (sizeof(T) == 4 && cfg.index_fp32) {
-    const float s = (float)xs * (float)cfg.inv_dx;
-    float t = s - 0.5f;
-    t = fminf(fmaxf(t, -1.0e9f), 1.0e9f);   // keeps the int conversion defined; such values are out of grid anyway
-    base = (int)t;
-    fx = (T)(s - (float)base);
+    float f;
+    base_fx_f32((float)xs, (float)cfg.inv_dx, base, f);
+    fx = (T)f;
     return;
   }
   double s = (double)xs * cfg.inv_dx;

@@ -37,7 +37,15 @@ struct P2GPlanes {
   int n;                           // planes to prefetch: 27 with material planes, else 24
   const unsigned char* material;   // table mode: row per particle (nullptr: row 0)
   const float* table;              // table mode: [3][MAT_ROWS]
+  long long stride;                // contiguous(): plane k of x, v, C, F starts at p[0] + k * stride
 };
+
+// The 24 planes x3 v3 C9 F9 sit back to back at one stride (MpmSolver carves them from one allocation): the
+// prefetch then needs ONE per-lane source pointer and twelve constant steps instead of a pointer per plane.
+inline bool p2g_planes_contiguous(const StateView<float>& s) {
+  const long long st = s.stride;
+  return s.v == s.x + 3 * st && s.C == s.v + 3 * st && s.F == s.C + 9 * st;
+}
 
 inline P2GPlanes p2g_planes_of(const StateView<float>& s) {
   P2GPlanes P;
@@ -49,6 +57,7 @@ inline P2GPlanes p2g_planes_of(const StateView<float>& s) {
   P.n = mode == MAT_PLANES ? P2G_NPLANES : P2G_MASS;
   P.material = mode == MAT_TABLE ? s.material : nullptr;
   P.table = mode == MAT_TABLE ? s.mat_table : nullptr;
+  P.stride = s.stride;
   return P;
 }
 
@@ -90,7 +99,10 @@ __device__ __forceinline__ void p2g_runs_phase2_adjacent(P2GWarpSlab<float>& S, 
   p2g_accumulate_runs<float>(S, n_runs, lane, ny, nz, grid);
 }
 
-template <int WARPS, int NBUF>
+// CONTIG: the 24 state planes are one strided block (p2g_planes_contiguous) and there are no material planes;
+// IDX32: cfg.index_fp32 (power-of-two inv_dx: exact fp32 cell indexing), resolved at compile time so that the
+// fp64 indexing code is not even fetched.
+template <int WARPS, int NBUF, bool CONTIG, bool IDX32>
 __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS)
 p2g_bulk3_kernel(DevCfg cfg, P2GPlanes planes, long long n, float* __restrict__ grid, ErrRec* err, int wpw) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -117,7 +129,20 @@ p2g_bulk3_kernel(DevCfg cfg, P2GPlanes planes, long long n, float* __restrict__ 
   const float nkdx = -(float)kd * dxf;                                                 // -(dt vol 4/dx^2) dx
   const float m_u = (float)cfg.mass, mu_u = (float)(cfg.mu0 * cfg.hardening), lam_u = (float)(cfg.lam0 * cfg.hardening);
 
+  // CONTIG: lane l copies the 16-byte chunk (l & 15) of planes 2j + (l >> 4), j = 0 .. 11
+  const float* const lane_src = planes.p[0] + (long long)(lane >> 4) * planes.stride + (lane & 15) * 4;
   auto issue = [&](int win, int buf) {
+    if constexpr (CONTIG) {
+      const float* src = lane_src + (long long)win * P2G_WINDOW;
+      float* dst = &W.raw[buf][lane >> 4][(lane & 15) * 4];
+      const long long step = 2 * planes.stride;
+#pragma unroll
+      for (int j = 0; j < P2G_MASS / 2; ++j) cp_async16(dst + j * 2 * P2G_WINDOW, src + j * step);
+      if (planes.material && lane < P2G_WINDOW / 16)
+        cp_async16(&W.mat[buf][lane * 16], planes.material + (long long)win * P2G_WINDOW + lane * 16);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      return;
+    }
     const long long w0 = (long long)win * P2G_WINDOW + (lane & 15) * 4;
     const int hi = lane >> 4;
 #pragma unroll
@@ -159,9 +184,15 @@ p2g_bulk3_kernel(DevCfg cfg, P2GPlanes planes, long long n, float* __restrict__ 
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         int gx, gy, gz;
-        base_fx(xs[h][0], cfg, gx, fx[h]);
-        base_fx(xs[h][1], cfg, gy, fy[h]);
-        base_fx(xs[h][2], cfg, gz, fz[h]);
+        if constexpr (IDX32) {
+          base_fx_f32(xs[h][0], (float)cfg.inv_dx, gx, fx[h]);
+          base_fx_f32(xs[h][1], (float)cfg.inv_dx, gy, fy[h]);
+          base_fx_f32(xs[h][2], (float)cfg.inv_dx, gz, fz[h]);
+        } else {
+          base_fx(xs[h][0], cfg, gx, fx[h]);
+          base_fx(xs[h][1], cfg, gy, fy[h]);
+          base_fx(xs[h][2], cfg, gz, fz[h]);
+        }
         const int bx = gx - cfg.origin[0], by = gy - cfg.origin[1], bz = gz - cfg.origin[2];
         // utils.py:138-150 with res = G: base < 0 or base + 2 >= G -> RuntimeError (flagged by the binning / G2P)
         ok[h] = i0 + h < cnt && xs[h][0] == xs[h][0] && xs[h][1] == xs[h][1] && xs[h][2] == xs[h][2] &&
@@ -238,8 +269,8 @@ p2g_bulk3_kernel(DevCfg cfg, P2GPlanes planes, long long n, float* __restrict__ 
   }
 }
 
-template <int WARPS, int NBUF>
-static bool p2g_bulk_launch(const DevCfg& cfg, const StateView<float>& s, long long n, float* grid, ErrRec* err,
+template <int WARPS, int NBUF, bool CONTIG, bool IDX32>
+static bool p2g_bulk_launch_t(const DevCfg& cfg, const StateView<float>& s, long long n, float* grid, ErrRec* err,
                             int sm_count, int blocks_per_sm, cudaStream_t st) {
   const size_t smem = sizeof(P2GBulkWarp<NBUF>) * WARPS;
   // function attributes are per device: a process that drives several GPUs configures each once
@@ -247,7 +278,7 @@ static bool p2g_bulk_launch(const DevCfg& cfg, const StateView<float>& s, long l
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
   if (!configured[dev]) {
-    if (cudaFuncSetAttribute(p2g_bulk3_kernel<WARPS, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(p2g_bulk3_kernel<WARPS, NBUF, CONTIG, IDX32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return false;
     configured[dev] = true;
   }
@@ -262,8 +293,18 @@ static bool p2g_bulk_launch(const DevCfg& cfg, const StateView<float>& s, long l
     blocks = (int)(want < cap ? want : cap);
   }
   if (blocks < 1) blocks = 1;
-  p2g_bulk3_kernel<WARPS, NBUF><<<blocks, WARPS * 32, smem, st>>>(cfg, p2g_planes_of(s), n, grid, err, wpw);
+  p2g_bulk3_kernel<WARPS, NBUF, CONTIG, IDX32><<<blocks, WARPS * 32, smem, st>>>(cfg, p2g_planes_of(s), n, grid, err, wpw);
   return true;
+}
+
+template <int WARPS, int NBUF>
+static bool p2g_bulk_launch(const DevCfg& cfg, const StateView<float>& s, long long n, float* grid, ErrRec* err,
+                            int sm_count, int blocks_per_sm, cudaStream_t st) {
+  const bool contig = p2g_planes_contiguous(s) && mat_mode_of(s) != MAT_PLANES;
+  if (contig && cfg.index_fp32) return p2g_bulk_launch_t<WARPS, NBUF, true, true>(cfg, s, n, grid, err, sm_count, blocks_per_sm, st);
+  if (contig) return p2g_bulk_launch_t<WARPS, NBUF, true, false>(cfg, s, n, grid, err, sm_count, blocks_per_sm, st);
+  if (cfg.index_fp32) return p2g_bulk_launch_t<WARPS, NBUF, false, true>(cfg, s, n, grid, err, sm_count, blocks_per_sm, st);
+  return p2g_bulk_launch_t<WARPS, NBUF, false, false>(cfg, s, n, grid, err, sm_count, blocks_per_sm, st);
 }
 
 // True when the state layout allows 16-byte window copies: 16-byte aligned planes, stride multiple of the window.

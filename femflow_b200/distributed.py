@@ -275,7 +275,10 @@ class SlabDriver:
         self.rebalanced = 0
         self._pending = None
         if hasattr(local, "count_leavers_async") and plan.world > 1:
-            # the leaver count is acted upon one substep after it was taken
+            # the leaver count is acted upon one substep after it was taken: a particle may be margin-1 substeps
+            # past its slab when it is finally handed over, so one margin layer is not enough
+            if plan.margin < 2:
+                raise ValueError("lagged migration (count_leavers_async) needs a halo margin of at least 2 cells")
             if self.migrate_every + 1 > max(2, plan.margin):
                 self.migrate_every = max(1, plan.margin - 1)
 
@@ -331,13 +334,18 @@ class SlabDriver:
             if due:
                 self.migrate()
             return
+        migrated_now = False
         if self._pending is not None:
             k, handle = self._pending
             if self.steps > k:                      # one substep of GPU work is queued behind the count
                 self._pending = None
-                if L.read_leaver_count(handle) > 0:     # already the max over all ranks
-                    self.migrate()
-        if due and self._pending is None:
+                count = L.read_leaver_count(handle)     # already the max over all ranks
+                if count > 0:
+                    self.migrate(hint=count)
+                    migrated_now = True
+        # the device counter was filled by this substep's G2P, i.e. BEFORE a migration that has just run: it would
+        # still count the particles that were handed over.  Take the next count one period later instead.
+        if due and self._pending is None and not migrated_now:
             cnt = L.count_leavers_async(self.plan.own_lo, self.plan.own_hi)      # (1,) int64 on the device
             dist.all_reduce(cnt, op=dist.ReduceOp.MAX, group=self.group)         # every rank takes the same decision
             self._pending = (self.steps, L.stage_leaver_count(cnt))
@@ -437,13 +445,52 @@ class SlabDriver:
             self.migrated += n_in[r]
         self.plan = new_plan
         self._pending = None
+        self._cap_limit = None
         self.rebalanced += 1
         return True
 
     # -- particle migration to the +-1 neighbours -------------------------------
-    def migrate(self) -> None:
+    def _migrate_cap(self, hint) -> int:
+        """Outbox capacity per side, the same on every rank (``hint`` is the max-reduced lagged leaver count, taken
+        one substep ago: room for another substep of motion and then some; leavers that do not fit stay one round)."""
+        want = 4096 if hint is None else 3 * int(hint) + 4096
+        cap = 1 << max(12, (want - 1).bit_length())
+        if getattr(self, "_cap_limit", None) is None:
+            # the smallest local limit (scratch lists of the pack kernel live in the binning workspace), agreed once
+            # per cut: every rank must post the same message size
+            lim = torch.tensor([self.local.migrate_cap_limit()], dtype=torch.int64, device=self.local.device)
+            dist.all_reduce(lim, op=dist.ReduceOp.MIN, group=self.group)
+            self._cap_limit = int(lim.item())
+        return int(min(cap, 1 << 22, self._cap_limit))
+
+    def _migrate_device(self, hint) -> None:
+        """One round with the local solver's pack / unpack kernels (``ffmpm_migrate_pack`` / ``_unpack``): fixed-size
+        messages whose headers carry the counts, so nothing between the pack and the unpack needs the host; the
+        round's record is read once at the end."""
+        L = self.local
+        cap = self._migrate_cap(hint)
+        out_lo, out_hi, in_lo, in_hi = L.migrate_pack(cap, self.left is not None, self.right is not None)
+        ops = []
+        if self.right is not None:
+            ops += [dist.P2POp(dist.isend, out_hi, self.right, self.group), dist.P2POp(dist.irecv, in_hi, self.right, self.group)]
+        if self.left is not None:
+            ops += [dist.P2POp(dist.isend, out_lo, self.left, self.group), dist.P2POp(dist.irecv, in_lo, self.left, self.group)]
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        rec = L.migrate_unpack(cap, in_lo, in_hi)
+        self.migrated += rec["in_lo"] + rec["in_hi"]
+        self.migrate_rounds = getattr(self, "migrate_rounds", 0) + 1
+        self.migrate_overflow = getattr(self, "migrate_overflow", 0) + rec["overflow"]
+
+    def migrate(self, hint=None) -> None:
         p, L = self.plan, self.local
-        left, right = L.extract_leavers(p.own_lo, p.own_hi)
+        if hasattr(L, "migrate_pack"):
+            return self._migrate_device(hint)
+        # a domain-end rank has no neighbour on that side: nothing leaves there (a particle outside the global grid
+        # stays local and is flagged by the solver, as the reference raises for it)
+        left, right = L.extract_leavers(p.own_lo if self.left is not None else -(1 << 62),
+                                        p.own_hi if self.right is not None else (1 << 62))
         dev = L.device
         rows = L.payload_rows()
         n_out = torch.tensor([left[0].shape[1] if self.left is not None else 0,
@@ -494,7 +541,9 @@ class CudaSlab(LocalSlab):
         self.dx, self.inv_dx = dx, 1.0 / dx
         self._scalars = (dt, volume, gravity, hardening)
         self._p2g_mode = p2g_mode
-        self._g2p_counts = p2g_mode != "fused"
+        import os
+        # only the binned, non-fused reordering G2P (g2p_tiled3_kernel) fills the device leaver counter
+        self._g2p_counts = p2g_mode in ("auto", "tiled") and os.environ.get("FFMPM_FUSE", "0") in ("", "0")
         self.launches_carried = 0      # kernel launches of the solvers a rebalancing replaced
         self._make_solver(plan, capacity)
 
@@ -563,30 +612,49 @@ class CudaSlab(LocalSlab):
             rows.append(mat)
         return torch.cat(rows, 0), b.id[idx]
 
-    def extract_leavers(self, own_lo: int, own_hi: int):
-        """Host-synchronising stream compaction (round-1 plumbing in torch ops): split
-        the live buffer into (left leavers, right leavers, keepers) by the global base
-        cell of each particle, computed in f64 exactly as the kernels do."""
+    # -- migration on the device (csrc/mpm_migrate.cuh) ----------------------------------------
+    def migrate_cap_limit(self) -> int:
+        return max(1, self.solver.capacity // 2)
+
+    def _mig_buffers(self, cap: int):
+        key = (cap, id(self.solver))
+        if getattr(self, "_mig_key", None) != key:
+            from . import _native as N
+            rows = int(self.solver.lib.ffmpm_migrate_rows(self.solver._h))
+            mk = lambda: torch.zeros((rows + 1, cap), dtype=self.dtype, device=self.device)
+            self._mig = [mk(), mk(), mk(), mk()]                     # out_lo, out_hi, in_lo, in_hi
+            self._mig_rec = torch.zeros(8, dtype=torch.int32).pin_memory()
+            self._mig_key = key
+        return self._mig
+
+    def migrate_pack(self, cap: int, has_left: bool, has_right: bool):
+        """Leavers into the two outboxes (``None`` side = domain end: nothing leaves there), holes back-filled from the
+        tail; returns (out_lo, out_hi, in_lo, in_hi) message tensors of shape (rows + 1, cap)."""
+        from . import _native as N
         s = self.solver
-        b = s.live
-        n = s.num_particles
-        x0 = b.x[0, :n]
-        # base = trunc(x*inv_dx - 0.5) is monotone in x, so "base < own_lo" / "base >= own_hi" are plain
-        # comparisons against the smallest storage-precision x of the boundary cell (found on the
-        # host with the kernels' own fp64 expression): one pass over x, one scalar readback.
-        t_lo, t_hi = self._threshold(own_lo), self._threshold(own_hi)
-        out = (x0 < t_lo) | (x0 >= t_hi)
-        if int(torch.count_nonzero(out)) == 0:
-            empty = torch.empty(0, dtype=torch.int64, device=self.device)
-            return self._pack(b, empty), self._pack(b, empty)
-        left_idx = torch.nonzero(x0 < t_lo).flatten()
-        right_idx = torch.nonzero(x0 >= t_hi).flatten()
-        left, right = self._pack(b, left_idx), self._pack(b, right_idx)
-        keep = torch.nonzero(~out).flatten()
-        other = 1 - s.live_index
-        self._store(self._pack(b, keep), 0, other)     # compact the keepers into the idle buffer
-        s._bind(keep.numel(), cur=other)
-        return left, right
+        out_lo, out_hi, in_lo, in_hi = self._mig_buffers(cap)
+        N.check(s.lib.ffmpm_migrate_pack(s._h, out_lo.data_ptr() if has_left else None, out_hi.data_ptr() if has_right else None,
+                                         cap, s._stream()))
+        self._mig_sides = (has_left, has_right)
+        return out_lo, out_hi, in_lo, in_hi
+
+    def migrate_unpack(self, cap: int, in_lo, in_hi) -> dict:
+        """Append the received particles, read the round's record (the one host synchronisation of a round) and
+        take over the new particle count."""
+        from . import _native as N
+        s = self.solver
+        has_left, has_right = self._mig_sides
+        N.check(s.lib.ffmpm_migrate_unpack(s._h, in_lo.data_ptr() if has_left else None, in_hi.data_ptr() if has_right else None,
+                                           cap, self._mig_rec.data_ptr(), s._stream()))
+        ev = torch.cuda.Event()
+        ev.record()
+        ev.synchronize()
+        out_l, out_h, got_l, got_h, n_new, overflow = (int(v) for v in self._mig_rec[:6])
+        if overflow >= (1 << 24):
+            raise RuntimeError(f"slab capacity {s.capacity} exceeded by migration")
+        N.check(s.lib.ffmpm_set_num_particles(s._h, n_new))
+        s.num_particles = n_new
+        return {"out_lo": out_l, "out_hi": out_h, "in_lo": got_l, "in_hi": got_h, "n": n_new, "overflow": overflow}
 
     def count_leavers_async(self, own_lo: int, own_hi: int):
         """Device-side count of the particles whose base cell left [own_lo, own_hi)."""
@@ -594,7 +662,11 @@ class CudaSlab(LocalSlab):
         if self._g2p_counts and s.num_particles > 0:
             return s.leaver_count().to(torch.int64)      # filled by the last G2P, no extra pass over x
         x0 = s.live.x[0, :s.num_particles]
-        t_lo, t_hi = self._threshold(own_lo), self._threshold(own_hi)
+        # domain-end ranks have no neighbour on that side: nothing "leaves" there (a particle outside the global
+        # grid is reported by the binning, as the reference raises for it) -- the thresholds of _make_solver
+        p = self.plan
+        t_lo = self._threshold(own_lo) if p.rank > 0 else float("-inf")
+        t_hi = self._threshold(own_hi) if p.rank < p.world - 1 else float("inf")
         return torch.count_nonzero((x0 < t_lo) | (x0 >= t_hi)).to(torch.int64).reshape(1)
 
     def stage_leaver_count(self, cnt):
@@ -719,6 +791,42 @@ class SlabSolver:
         local.set_particles(x, scene.v, scene.F, scene.C, scene.mass, scene.mu_0, scene.lambda_0,
                             (ids % (2 ** 31)).astype(np.int32))
         return cls(plan, local, SlabDriver(plan, local, halo=halo))
+
+    @classmethod
+    def from_bar(cls, scene, rank: int, world: int, device, p2g_mode: str = "auto", margin: int = 4,
+                 capacity_factor: float = 1.3, halo: str = "p2p", drift_cells_per_substep: float = 0.1,
+                 yz_cells=None, end_clearance=None):
+        """COUPLED weak scaling (BASELINE configs[3] "with halo exchange + particle migration"): ONE elastic bar that
+        runs through every slab of the (res*world) x res x res domain -- res x yz_cells cells of 8 particles per GPU,
+        i.e. the 16.8 M particles per GPU of the headline block at res 256 -- drifting along +x at
+        ``drift_cells_per_substep``, so that every halo plane carries mass and momentum and every migration period
+        hands a layer of particles to the next rank.  Each rank generates the particles whose base cell it owns
+        (the material, dt and perturbation of ``scene``, the per-GPU block of the same resolution)."""
+        from . import scenes
+        res = scene.res
+        yz_cells = yz_cells or (res // 2, res // 4)                        # res 256: 256 x 128 x 64 cells per GPU
+        end_clearance = end_clearance or (max(2, res // 32), max(4, 3 * res // 32))
+        plan = SlabPlan.make((res * world, res, res), world, rank, margin)
+        dx = 1.0 / res
+        gx0, gx1 = end_clearance[0], res * world - end_clearance[1]
+        lo, hi = max(gx0, plan.own_lo), min(gx1, plan.own_hi + 1)          # cell c feeds base cells c-1 and c
+        cy, cz = yz_cells
+        sc = scenes.elastic_block(3, res, 0, 2, seed=1000 + rank, shape=(max(hi - lo, 0), cy, cz),
+                                  origin_cell=(lo, (res - cy) // 2, (res - cz) // 2))
+        base = np.trunc(sc.x[:, 0].astype(np.float64) * res - 0.5).astype(np.int64)
+        keep = (base >= (plan.own_lo if rank > 0 else -1)) & (base < (plan.own_hi if rank < world - 1 else 1 << 40))
+        x, v, F, C_ = sc.x[keep], sc.v[keep].copy(), sc.F[keep], sc.C[keep]
+        v[:, 0] += np.float32(drift_cells_per_substep * dx / sc.dt)
+        n = len(x)
+        local = CudaSlab(plan, dx, sc.dt, sc.volume, sc.gravity, sc.hardening,
+                         capacity=int(res * cy * cz * 8 * capacity_factor), device=device, p2g_mode=p2g_mode)
+        ids = (np.arange(n, dtype=np.int64) + rank * (1 << 27)) % (2 ** 31)
+        local.set_particles(x, v, F, C_, sc.mass, sc.mu_0, sc.lambda_0, ids.astype(np.int32))
+        obj = cls(plan, local, SlabDriver(plan, local, halo=halo))
+        obj.scene_name = (f"3D elastic bar {gx1 - gx0}x{cy}x{cz} cells x 8 ppc through {world} slabs of {res}^3, "
+                          f"drifting {drift_cells_per_substep} cells/substep along x")
+        obj.scene_dt = sc.dt
+        return obj
 
     @classmethod
     def from_dam_break(cls, rank: int, world: int, device, res: int = 256, n_total: int = 33_554_432,

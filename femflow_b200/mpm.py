@@ -37,10 +37,11 @@ class _StateBuffer:
         self.cap = cap
         self.dtype, self.device = dtype, device
         self.material = None      # uint8 rows of the material table (MpmSolver._set_material_layout)
-        self.x = torch.zeros((d, cap), dtype=dtype, device=device)
-        self.v = torch.zeros((d, cap), dtype=dtype, device=device)
-        self.C = torch.zeros((d * d, cap), dtype=dtype, device=device)
-        self.F = torch.zeros((d * d, cap), dtype=dtype, device=device)
+        # x, v, C, F are views into ONE allocation of 2d + 2d^2 planes at one stride: the P2G prefetch then walks the
+        # 24 planes of a window from a single per-lane pointer (csrc/mpm_p2g_bulk.cuh: p2g_planes_contiguous)
+        self.planes = torch.zeros((2 * d + 2 * d * d, cap), dtype=dtype, device=device)
+        self.x, self.v = self.planes[0:d], self.planes[d:2 * d]
+        self.C, self.F = self.planes[2 * d:2 * d + d * d], self.planes[2 * d + d * d:]
         self.Jp = torch.ones((cap,), dtype=dtype, device=device) if with_jp else None
         if per_particle_material:
             self.mass = torch.zeros((cap,), dtype=dtype, device=device)
@@ -58,7 +59,7 @@ class _StateBuffer:
 
     def nbytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in
-                   (self.x, self.v, self.C, self.F, self.Jp, self.mass, self.mu0, self.lam0, self.id, self.material)
+                   (self.planes, self.Jp, self.mass, self.mu0, self.lam0, self.id, self.material)
                    if t is not None)
 
     def set_material_storage(self, kind: str) -> None:

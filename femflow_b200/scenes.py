@@ -40,14 +40,14 @@ def _lame(E, nu):
 
 def elastic_block(dim: int, res: int, cells: int, ppc_side: int = 2, seed: int = 0, E: float = 1e4,
                   nu: float = 0.2, rho: float = 1.0, perturb: bool = True, origin_cell=None,
-                  cells_x=None) -> Scene:
+                  cells_x=None, shape=None) -> Scene:
     """Block of ``cells**dim`` grid cells centred in the unit domain (``cells_x`` cells
-    along axis 0 when given), ``ppc_side**dim`` jittered particles per cell
+    along axis 0 when given, or an explicit per-axis ``shape``), ``ppc_side**dim`` jittered particles per cell
     (jitter U(-0.25, 0.25) * dx / ppc_side).  ``perturb`` adds v0 ~ N(0, 0.05) and
     F = I + N(0, 0.01) so the constitutive path does real work."""
     rng = np.random.default_rng(seed)
     dx = 1.0 / res
-    shape = [cells_x or cells] + [cells] * (dim - 1)
+    shape = list(shape) if shape is not None else [cells_x or cells] + [cells] * (dim - 1)
     if origin_cell is None:
         origin_cell = [(res - c) // 2 for c in shape]
     sub = (np.arange(ppc_side) + 0.5) / ppc_side

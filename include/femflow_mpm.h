@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define FFMPM_ABI_VERSION 2
+#define FFMPM_ABI_VERSION 3
 
 enum {
   FFMPM_OK = 0,
@@ -143,6 +143,23 @@ int ffmpm_grid_op_halo(FfMpmHandle* h, const void* recv_lo, int32_t planes_lo, c
  * needs no pass of its own over the positions. */
 int ffmpm_set_owned_range(FfMpmHandle* h, int32_t own_lo, int32_t own_hi);
 int ffmpm_leaver_count_ptr(FfMpmHandle* h, int32_t** count);
+/* Slab migration on the device (new).  One round, all on `stream`, no host involvement:
+ *   ffmpm_migrate_pack    every live particle whose GLOBAL base cell along axis 0 (three_d/p2g.py:50) left the owned
+ *                         range of ffmpm_set_owned_range is copied into `out_lo` (cell < own_lo) or `out_hi`
+ *                         (cell >= own_hi) and its slot is back-filled from the tail of the live buffer: only the
+ *                         leavers and as many keepers move.  At most `cap` particles per side; the rest stays one
+ *                         more round.  A NULL outbox = no neighbour on that side: those particles stay (a particle
+ *                         outside the GLOBAL grid is then reported by the binning as in the reference).
+ *   (caller: exchange out_lo / out_hi with the neighbour ranks -- fixed-size messages)
+ *   ffmpm_migrate_unpack  appends the particles of `in_lo` / `in_hi` (NULL = none) behind the keepers and copies the
+ *                         round's record {out_lo, out_hi, in_lo, in_hi, n_new, overflow} (6 x int32) to `record`
+ *                         (device or pinned host memory).  The caller reads it ONCE, then ffmpm_set_num_particles(n_new).
+ * Message = (1 + ffmpm_migrate_rows) x cap scalars of cfg.dtype: row 0 = header (element 0: particle count), then one
+ * row per component: x3 v3 C9 F9, material (mass mu0 lam0 planes, or the table row and two unused rows), id bits, [Jp].
+ * Needs the id plane; invalidates the binning of the live buffer (its key/rank/perm arrays are the scratch lists). */
+int32_t ffmpm_migrate_rows(const FfMpmHandle* h);
+int ffmpm_migrate_pack(FfMpmHandle* h, void* out_lo, void* out_hi, int32_t cap, void* stream);
+int ffmpm_migrate_unpack(FfMpmHandle* h, const void* in_lo, const void* in_hi, int32_t cap, int32_t* record, void* stream);
 /* The two halves of a substep either side of the grid update, as ffmpm_substep issues
  * them (slab drivers put the halo exchange in between):
  *   ffmpm_scatter  zeroed grid + cell binning + P2G   (mls_mpm.py:54-73).  The library keeps

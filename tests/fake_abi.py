@@ -360,6 +360,101 @@ class FakeLib:
             self.ffmpm_gather(h, stream)
         return N.FFMPM_OK
 
+    # -- slab migration (csrc/mpm_migrate.cuh): same message layout, same back-fill rule -----------
+    def ffmpm_migrate_rows(self, h):
+        h = self._h(h)
+        return 28 + (1 if h.st[0].Jp else 0)
+
+    def _mig_row(self, h, p, r):
+        """(array, row index or None) behind payload row r of buffer planes p."""
+        if r < 3: return p["x"], r
+        if r < 6: return p["v"], r - 3
+        if r < 15: return p["C"], r - 6
+        if r < 24: return p["F"], r - 15
+        if r == 24: return (p["mass"] if p["mass"] is not None else p["material"]), None
+        if r == 25: return p["mu0"], None
+        if r == 26: return p["lam0"], None
+        if r == 27: return p["id"], None
+        return p["Jp"], None
+
+    def _mig_get(self, h, p, r, idx):
+        a, row = self._mig_row(h, p, r)
+        dt = np.float64 if h.es == 8 else np.float32
+        if a is None:
+            return np.zeros(len(idx), dt)
+        v = a[row][idx] if row is not None else a[idx]
+        if r == 27:
+            return v.astype(np.int32).view(np.float32) if h.es == 4 else v.astype(np.float64)
+        return v.astype(dt)
+
+    def _mig_put(self, h, p, r, idx, vals):
+        a, row = self._mig_row(h, p, r)
+        if a is None:
+            return
+        if r == 27:
+            vals = np.ascontiguousarray(vals, np.float32).view(np.int32) if h.es == 4 else vals.astype(np.int32)
+        if row is not None:
+            a[row][idx] = vals
+        else:
+            a[idx] = vals.astype(a.dtype)
+
+    def ffmpm_migrate_pack(self, h, out_lo, out_hi, cap, stream):
+        h = self._h(h)
+        cap, rows = int(_val(cap)), 28 + (1 if h.st[0].Jp else 0)
+        if h.st[h.live].id in (None, 0):
+            return self._fail(N.FFMPM_E_STATE, "slab migration needs the id plane")
+        p, n = self._planes(h, h.live), h.n
+        x0 = p["x"][0, :n].astype(np.float64)
+        gbx = (x0 * h.cfg.inv_dx - 0.5).astype(np.int64)
+        ct = _CT[h.es]
+        sides = []
+        for ptr, sel in ((_val(out_lo), gbx < h.own[0]), (_val(out_hi), gbx >= h.own[1])):
+            idx = np.nonzero(sel)[0] if ptr else np.zeros(0, np.int64)
+            over = max(0, len(idx) - cap)
+            idx = idx[:cap]
+            if ptr:
+                box = _view(ptr, (rows + 1) * cap, ct).reshape(rows + 1, cap)
+                box[0, 0] = len(idx)
+                for r in range(rows):
+                    box[1 + r, :len(idx)] = self._mig_get(h, p, r, idx)
+            sides.append((idx, over))
+        gone = np.concatenate([sides[0][0], sides[1][0]])
+        keep = n - len(gone)
+        hole = np.zeros(n, bool)
+        hole[gone] = True
+        lo_holes = np.nonzero(hole[:keep])[0]
+        movers = keep + np.nonzero(~hole[keep:n])[0]
+        assert len(lo_holes) == len(movers)
+        for r in range(rows):
+            self._mig_put(h, p, r, lo_holes, self._mig_get(h, p, r, movers))
+        h.mig = dict(out_lo=len(sides[0][0]), out_hi=len(sides[1][0]), keep=keep, overflow=sides[0][1] + sides[1][1])
+        h.launches += 4
+        return N.FFMPM_OK
+
+    def ffmpm_migrate_unpack(self, h, in_lo, in_hi, cap, record, stream):
+        h = self._h(h)
+        cap, rows = int(_val(cap)), 28 + (1 if h.st[0].Jp else 0)
+        p = self._planes(h, h.live)
+        ct = _CT[h.es]
+        at, counts = h.mig["keep"], []
+        for ptr in (_val(in_lo), _val(in_hi)):
+            k = 0
+            if ptr:
+                box = _view(ptr, (rows + 1) * cap, ct).reshape(rows + 1, cap)
+                k = min(int(box[0, 0]), cap)
+                if at + k > h.st[h.live].stride:
+                    h.mig["overflow"] += (1 << 24)
+                    k = 0
+                idx = np.arange(at, at + k)
+                for r in range(rows):
+                    self._mig_put(h, p, r, idx, box[1 + r, :k])
+                at += k
+            counts.append(k)
+        rec = _view(_val(record), 6, C.c_int32)
+        rec[:] = [h.mig["out_lo"], h.mig["out_hi"], counts[0], counts[1], at, h.mig["overflow"]]
+        h.launches += 1
+        return N.FFMPM_OK
+
     def ffmpm_snapshot(self, h, coeff, out, stream):
         h = self._h(h)
         p, n = self._planes(h, h.live), h.n

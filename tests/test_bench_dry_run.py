@@ -201,7 +201,7 @@ def _two_rank_worker(rank, world, port, outdir):
     D.CudaSlab.__init__ = lambda self, *a, **k: real_slab_init(self, *a, **{**k, "dtype": torch.float64})
     import bench
     sys.argv = ["bench.py", "--gpus", str(world), "--workload", "3d:32:8", "--steps", "5", "--warmup", "3", "--no-cpu-baseline",
-                "--e2e-steps", "1", "--margin", "2"]
+                "--e2e-steps", "1", "--margin", "2", "--drift", "0.4"]
     buf = io.StringIO()
     with contextlib.redirect_stdout(buf):
         bench.main()
@@ -223,11 +223,14 @@ def test_two_rank_line(tmp_path):
     d = json.loads(lines[0])
     for k in CONTRACT:
         assert k in d, k
-    n = d["config"]["particles_per_gpu"]
-    assert d["n_gpus"] == 2 and d["config"]["particles_total"] == 2 * n == sum(d["config"]["slab_particles"])
+    total = d["config"]["particles_total"]
+    assert d["n_gpus"] == 2 and total == sum(d["config"]["slab_particles"]) and min(d["config"]["slab_particles"]) > 0
     assert d["config"]["slab_cells"] == [[0, 32], [32, 63]] and d["config"]["rebalanced"] == 0
     assert "2 slabs along x" in d["config"]["parallelism"] and d["scaling"] == "weak"
-    assert d["e2e"]["h2d_bytes_per_step"] == 2 * 24 * 8 * n and d["roofline"] is None and d["config"]["n_oob"] == 0
+    # the default N > 1 workload is the COUPLED bar: it says so, and particles did cross the cut
+    assert "coupled" in d["config"]["parallelism"] and "bar" in d["config"]["workload"]
+    assert d["config"]["migration"]["particles_received"] > 0 and d["config"]["migration"]["rounds"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 24 * 8 * total and d["roofline"] is None and d["config"]["n_oob"] == 0
 
 
 def test_cpu_baseline_leg_and_reference_arm(dry, capsys, monkeypatch):

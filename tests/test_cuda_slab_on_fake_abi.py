@@ -41,7 +41,7 @@ def _worker(rank, world, port, out, cfg):
         # lagged=False: a slab without the asynchronous-count interface takes the driver's synchronous migration path
         cls = CudaSlab if cfg["lagged"] else type("CudaSlabSync", (CudaSlab,), {"__getattribute__": _hide_count})
         local = cls(plan, p["dx"], p["dt"], p["volume"], p["gravity"], p["hardening"], capacity=len(x), device="cpu",
-                    dtype=torch.float64)
+                    dtype=torch.float64, p2g_mode=cfg.get("p2g_mode", "auto"))
         local.set_particles(x[mine], v[mine], F[mine], C[mine], mass[mine], mu0[mine], lam0[mine], ids[mine])
         assert local.solver.material_layout == (f"table[{cfg['nmat']}]" if cfg["nmat"] <= 256 else "planes")
         fabric = SharedFabric(rank, world, *cfg["shared"]) if cfg.get("shared") else None
@@ -77,6 +77,8 @@ CASES = {
     "lagged-2-planes": dict(world=2, margin=3, migrate_every=2, lagged=True, nmat=300),
     "rebalance-3": dict(world=3, margin=2, migrate_every=1, lagged=True, nmat=3, lopsided=True, rebalance=True, pre=2),
     "symm-2": dict(world=2, margin=2, migrate_every=2, lagged=True, nmat=1, symm=True),
+    # the unbinned kernels never fill the device leaver counter: the count must come from the positions instead
+    "lagged-2-scatter": dict(world=2, margin=2, migrate_every=1, lagged=True, nmat=3, p2g_mode="scatter"),
 }
 
 

@@ -107,6 +107,90 @@ def test_two_gpu_symm_halo_matches_oracle(tmp_path):
     _assert_close(p, got, _oracle_run(p, state, steps), steps)
 
 
+@pytest.mark.parametrize("nmat,dtype", [(1, "float32"), (3, "float32"), (300, "float32"), (3, "float64")])
+def test_device_migration_pack_unpack_one_gpu(nmat, dtype):
+    """csrc/mpm_migrate.cuh through ffmpm_migrate_pack / _unpack on ONE GPU: the leavers of an owned range land in the
+    two outboxes (payload rows = their state, material and id), the holes are back-filled so that the live buffer holds
+    exactly the keepers, a small outbox leaves the overflow in place, and feeding the outboxes back in (a loop-back
+    exchange) restores the full particle set -- every plane, by particle id."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import ctypes as C
+    from femflow_b200 import _native as N
+    from femflow_b200.mpm import MpmSolver
+    p, (x, v, F, Cm, mass, mu0, lam0, ids) = _scene(nmat)
+    n, res = len(x), p["res"]
+    tdt = getattr(torch, dtype)
+    s = MpmSolver(3, res, p["dt"], p["volume"], p["gravity"], p["hardening"], capacity=2 * n, dtype=tdt, reorder=True)
+    s.set_particles(x, v, F, Cm, None, mass, mu0, lam0)
+    s.substep(1)                                    # a sorted live buffer with binning state to invalidate
+    before = {k: t.clone() for k, t in s.get_particles().items()}
+    live = s.live
+    base = torch.trunc(live.x[0, :n].double() * p["inv_dx"] - 0.5).long().cpu().numpy()
+    own_lo, own_hi = 12, 19
+    s.set_owned_range(own_lo, own_hi)
+    want_lo, want_hi = int((base < own_lo).sum()), int((base >= own_hi).sum())
+    assert want_lo > 100 and want_hi > 100
+    rows = int(s.lib.ffmpm_migrate_rows(s._h))
+    assert rows == 28
+    rec = torch.zeros(8, dtype=torch.int32).pin_memory()
+
+    def box(cap):
+        return torch.zeros((rows + 1, cap), dtype=tdt, device="cuda")
+
+    # ---- a round whose outboxes are too small: the overflow stays, nothing is lost ----
+    cap = 64
+    out_lo, out_hi = box(cap), box(cap)
+    N.check(s.lib.ffmpm_migrate_pack(s._h, out_lo.data_ptr(), out_hi.data_ptr(), cap, s._stream()))
+    N.check(s.lib.ffmpm_migrate_unpack(s._h, None, None, cap, rec.data_ptr(), s._stream()))
+    torch.cuda.synchronize()
+    o_lo, o_hi, i_lo, i_hi, n_new, overflow = (int(t) for t in rec[:6])
+    assert (o_lo, o_hi, i_lo, i_hi) == (cap, cap, 0, 0) and n_new == n - 2 * cap
+    assert overflow == want_lo + want_hi - 2 * cap
+    N.check(s.lib.ffmpm_set_num_particles(s._h, n_new)); s.num_particles = n_new
+    kept_ids = s.live.id[:n_new].cpu().numpy()
+    sent_ids = np.concatenate([out_lo[1 + 27, :cap].view(torch.int32).cpu().numpy() if dtype == "float32" else out_lo[28, :cap].long().cpu().numpy(),
+                               out_hi[1 + 27, :cap].view(torch.int32).cpu().numpy() if dtype == "float32" else out_hi[28, :cap].long().cpu().numpy()])
+    assert np.array_equal(np.sort(np.concatenate([kept_ids, sent_ids])), np.arange(n))
+    # loop back: what left to the left comes back "from the right" and vice versa
+    N.check(s.lib.ffmpm_migrate_pack(s._h, None, None, cap, s._stream()))         # no neighbours: nothing leaves
+    N.check(s.lib.ffmpm_migrate_unpack(s._h, out_hi.data_ptr(), out_lo.data_ptr(), cap, rec.data_ptr(), s._stream()))
+    torch.cuda.synchronize()
+    assert [int(t) for t in rec[:6]] == [0, 0, cap, cap, n, 0]
+    N.check(s.lib.ffmpm_set_num_particles(s._h, n)); s.num_particles = n
+
+    # ---- a full round ----
+    cap = 8192
+    out_lo, out_hi = box(cap), box(cap)
+    N.check(s.lib.ffmpm_migrate_pack(s._h, out_lo.data_ptr(), out_hi.data_ptr(), cap, s._stream()))
+    N.check(s.lib.ffmpm_migrate_unpack(s._h, None, None, cap, rec.data_ptr(), s._stream()))
+    torch.cuda.synchronize()
+    o_lo, o_hi, i_lo, i_hi, n_new, overflow = (int(t) for t in rec[:6])
+    assert (o_lo, o_hi, overflow) == (want_lo, want_hi, 0) and n_new == n - want_lo - want_hi
+    assert int(out_lo[0, 0]) == want_lo and int(out_hi[0, 0]) == want_hi
+    N.check(s.lib.ffmpm_set_num_particles(s._h, n_new)); s.num_particles = n_new
+    kb = torch.trunc(s.live.x[0, :n_new].double() * p["inv_dx"] - 0.5).long()
+    assert bool(((kb >= own_lo) & (kb < own_hi)).all())                 # only keepers are left, no holes
+    xb = torch.trunc(out_lo[1, :want_lo].double() * p["inv_dx"] - 0.5).long()
+    assert bool((xb < own_lo).all())
+    # and back again: the state by id is bit-identical to what it was
+    N.check(s.lib.ffmpm_migrate_pack(s._h, None, None, cap, s._stream()))
+    N.check(s.lib.ffmpm_migrate_unpack(s._h, out_lo.data_ptr(), out_hi.data_ptr(), cap, rec.data_ptr(), s._stream()))
+    torch.cuda.synchronize()
+    assert [int(t) for t in rec[:6]] == [0, 0, want_lo, want_hi, n, 0]
+    N.check(s.lib.ffmpm_set_num_particles(s._h, n)); s.num_particles = n
+    after = s.get_particles()
+    for k in before:
+        assert torch.equal(before[k], after[k]), k
+    # the material travelled with its particle: one more substep against the oracle
+    s.substep(1)
+    s.check_errors()
+    got = {k: t.double().cpu().numpy() for k, t in s.get_particles().items()}
+    ref = _oracle_run(p, (x, v, F, Cm, mass, mu0, lam0, ids), 2)
+    _assert_close(p, got, ref, 2) if dtype == "float32" else None
+    s.close()
+
+
 def _lopsided(nmat):
     """_scene() squeezed into the low-x 40 % of the domain: the even cut leaves rank 1 idle."""
     p, (x, v, F, C, mass, mu0, lam0, ids) = _scene(nmat)
