@@ -200,68 +200,32 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def e2e_streamed(torch, core, host_in, host_out, n, steps):
-    """The host-buffer path as a THROUGHPUT pipeline over independent steps (a parameter sweep, the reference's
-    paper_1.multi_drop_experiment): two upload targets and two result buffers, so that on the full-duplex link
-    the upload of step k+1 runs under the download of step k; every step still uploads its whole state from
-    pinned memory, runs one substep and downloads x, v, C, F.  Stream-ordered with events, timed on the device."""
-    from femflow_b200.mpm import _StateBuffer
-    dev = core.device
-    b0 = core.buffers[0]
-    kind = "planes" if b0.mass is not None else ("rows" if b0.material is not None else "none")
-
-    def make():
-        sb = _StateBuffer(core.dim, core.capacity, core.dtype, dev, False, True, b0.Jp is not None)
-        sb.set_material_storage(kind)
-        return sb
-    ins, outs = [make(), make()], [make(), make()]
-    houts = [host_out, {k: torch.empty_like(t).pin_memory() for k, t in host_out.items()}]
-    s_in, s_out, s_run = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.current_stream(dev)
-    uploaded = [torch.cuda.Event() for _ in range(2)]
-    computed = [torch.cuda.Event() for _ in range(2)]     # step done: its upload target is free, its result is ready
-    drained = [torch.cuda.Event() for _ in range(2)]      # result copied out: the result buffer is free
-    saved = list(core.buffers)
-
-    def step(k, first_use):
-        j = k & 1
-        with torch.cuda.stream(s_in):
-            if not first_use:
-                s_in.wait_event(computed[j])
-            for name, t in host_in.items():
-                getattr(ins[j], name)[..., :n].copy_(t, non_blocking=True)
-            uploaded[j].record(s_in)
-        s_run.wait_event(uploaded[j])
-        if not first_use:
-            s_run.wait_event(drained[j])
-        core.buffers[0], core.buffers[1] = ins[j], outs[j]
-        core._bind(n)
-        core.substep(1)
-        computed[j].record(s_run)
-        with torch.cuda.stream(s_out):
-            s_out.wait_event(computed[j])
-            lv = core.live                       # outs[j] after one reordering substep
-            for name, t in houts[j].items():
-                t[..., :n].copy_(getattr(lv, name)[..., :n], non_blocking=True)
-            drained[j].record(s_out)
-
+def e2e_pipelined(torch, core, host_in, host_out, n, steps, depth=3, step=None):
+    """The host-buffer path as a THROUGHPUT pipeline over independent calls (femflow_b200.host_pipeline: a parameter
+    sweep, the scenes of paper_1.multi_drop_experiment): `depth` device slots in flight, the upload of call k+1 under the
+    download of call k on the full-duplex link.  Every call still uploads its whole state from pinned memory, runs
+    one substep and downloads x, v, C, F -- in the caller's particle order.  Timed on the device."""
+    from femflow_b200.host_pipeline import HostSubstepPipeline
+    pipe = HostSubstepPipeline(core, depth=depth, step=step)
+    outs = [host_out] + [{k: torch.empty_like(t).pin_memory() for k, t in host_out.items()} for _ in range(depth - 1)]
+    run = torch.cuda.current_stream(core.device)
     try:
-        for k in range(2):
-            step(k, True)                         # warm both buffer pairs
-        torch.cuda.synchronize(dev)
+        for k in range(depth):
+            pipe.submit(host_in, outs[k % depth])          # warm every slot
+        pipe.drain()
+        torch.cuda.synchronize(core.device)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(s_run)
+        e0.record(run)
         for k in range(steps):
-            step(k, False)
-        s_run.wait_event(drained[0])
-        s_run.wait_event(drained[1])
-        e1.record(s_run)
-        torch.cuda.synchronize(dev)
+            pipe.submit(host_in, outs[k % depth])
+        for ev in pipe.drained:
+            run.wait_event(ev)
+        e1.record(run)
+        torch.cuda.synchronize(core.device)
         ms = e0.elapsed_time(e1)
     finally:
-        core.buffers[0], core.buffers[1] = saved
-        core._bind(n)
-    return {"value": n * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
-            "what": "independent steps, double-buffered: H2D of step k+1 under D2H of step k; same bytes per step"}
+        pipe.drain()
+    return ms, steps
 
 
 # ----------------------------------------------------------------------------- #
@@ -282,10 +246,8 @@ def main():
     ap.add_argument("--slab-timing", action="store_true", help="N>1: print per-phase CUDA-event times per rank to stderr")
     ap.add_argument("--margin", type=int, default=4, help="slab halo margin in cells = substeps between migrations")
     ap.add_argument("--drift", type=float, default=0.1, help="N>1 coupled bar: drift along x in cells per substep")
-    ap.add_argument("--e2e-streamed", action="store_true",
-                    help="N=1, 3D: also measure the host-buffer path as a stream of independent steps (double-buffered: the "
-                         "upload of step k+1 overlaps the download of step k on the full-duplex link); reported as "
-                         "e2e.streamed next to the synchronous e2e.value, not instead of it")
+    ap.add_argument("--e2e-serial-only", action="store_true",
+                    help="report the blocking host-buffer call as e2e.value instead of the pipelined one (round-1 behaviour)")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "symm"],
                     help="N>1: halo planes by NCCL send/recv (p2p) or by one-sided puts into the neighbour's "
                          "symmetric-memory inbox over NVLink (symm; SymmHalo, not yet measured)")
@@ -510,6 +472,18 @@ def main():
             for k, t in host_out.items():
                 t[..., :m].copy_(getattr(lv, k)[..., :m], non_blocking=True)
 
+        def reduce_ms(ms_):
+            if world > 1:
+                t_ = torch.tensor([ms_], device=dev, dtype=torch.float64)
+                dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+                return float(t_.item())
+            return ms_
+
+        if world > 1:
+            # every call is one independent substep from the uploaded state: nothing strays further than the halo
+            # margin, so the migration cadence of the resident run is held off while the host-buffer path is timed
+            hold = (solver.driver.migrate_every, solver.driver._pending)
+            solver.driver.migrate_every, solver.driver._pending = 1 << 60, None
         e2e_step()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -518,24 +492,36 @@ def main():
             e2e_step()
         e1.record()
         barrier()
-        e_ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([e_ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e_ms = float(t.item())
+        serial_ms = reduce_ms(e0.elapsed_time(e1))
         if world > 1:       # bytes of the whole job: the ranks' particle counts differ
             t = torch.tensor([h2d, d2h], device=dev, dtype=torch.int64)
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
             h2d, d2h = int(t[0].item()), int(t[1].item())
-        e2e = {"value": n_total * args.e2e_steps / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": e_ms / args.e2e_steps,
+        serial = {"value": n_total * args.e2e_steps / (serial_ms * 1e-3), "unit": UNIT, "ms_per_step": serial_ms / args.e2e_steps,
+                  "steps": args.e2e_steps,
+                  "what": "one blocking call at a time: H2D of the state, one substep, D2H of x, v, C, F (storage order)"}
+        e2e = {**serial, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "api": "ffmpm C ABI via MpmSolver (host SoA pinned buffers in, x/v/C/F out, every step)"}
-
-    if e2e is not None and args.e2e_streamed and world == 1 and scene.dim == 3 and core.reorder:
-        try:
-            e2e["streamed"] = e2e_streamed(torch, core, host_in, host_out, n, max(4, args.e2e_steps * 2))
-        except Exception as ex:  # an extra, never the headline
-            e2e["streamed"] = {"value": None, "error": repr(ex)}
+        if not args.e2e_serial_only and scene.dim == 3:
+            try:
+                p_steps = max(12, 4 * args.e2e_steps)
+                step_fn = (lambda: solver.driver.substep(1)) if world > 1 else None
+                from femflow_b200.host_pipeline import HostSubstepPipeline
+                barrier()
+                ms_p, p_steps = e2e_pipelined(torch, core, host_in, host_out, n, p_steps, step=step_fn)
+                barrier()
+                ms_p = reduce_ms(ms_p)
+                e2e = {"value": n_total * p_steps / (ms_p * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "ms_per_step": ms_p / p_steps, "steps": p_steps,
+                       "api": "femflow_b200.host_pipeline.HostSubstepPipeline over the ffmpm C ABI: every call uploads its whole "
+                              "state from pinned host SoA buffers, runs one substep and downloads x, v, C, F in the caller's "
+                              "particle order; 3 device slots in flight, so the upload of call k+1 runs under the download of "
+                              "call k (independent calls; a dependent chain is the `serial` figure)",
+                       "serial": serial}
+            except Exception as ex:  # the blocking figure stands
+                e2e["pipelined_error"] = repr(ex)
+        if world > 1:
+            solver.driver.migrate_every, solver.driver._pending = hold[0], None
 
     if rank != 0:
         if world > 1:

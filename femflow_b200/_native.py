@@ -70,6 +70,7 @@ PROTOTYPES = {
                                  C.POINTER(C.c_int64)]),
     "ffmpm_poll_error": (C.c_int, [H, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "ffmpm_snapshot": (C.c_int, [H, C.c_double, C.c_void_p, C.c_void_p]),
+    "ffmpm_export_state": (C.c_int, [H, C.POINTER(FfMpmState), C.c_void_p]),
     "ffmpm_launch_count": (C.c_int64, [H]),
     "ffmpm_debug_red_add4": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int64, C.c_void_p]),
 }

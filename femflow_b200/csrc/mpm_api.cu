@@ -769,6 +769,32 @@ int ffmpm_snapshot(FfMpmHandle* h, double coeff, double* out, void* stream) {
   return check_launch(h, 1);
 }
 
+// Live state -> caller buffers in ORIGINAL particle order (the id plane undoes the cell-sorted storage order).
+template <typename T>
+__global__ void __launch_bounds__(256) export_by_id_kernel(StateView<T> s, StateView<T> d, long long n, int dim) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const long long q = s.id ? (long long)s.id[p] : p;
+  const long long ss = s.stride, ds = d.stride;
+  const int dd = dim * dim;
+  for (int c = 0; c < dim; ++c) { d.x[c * ds + q] = s.x[c * ss + p]; d.v[c * ds + q] = s.v[c * ss + p]; }
+  for (int c = 0; c < dd; ++c) { d.C[c * ds + q] = s.C[c * ss + p]; d.F[c * ds + q] = s.F[c * ss + p]; }
+  if (s.Jp && d.Jp) d.Jp[q] = s.Jp[p];
+}
+
+int ffmpm_export_state(FfMpmHandle* h, const FfMpmState* dst, void* stream) {
+  int rc = ready(h);
+  if (rc) return rc;
+  if (!dst || !dst->x || !dst->v || !dst->C || !dst->F || dst->stride < h->n) return set_err(FFMPM_E_INVALID, "bad export target");
+  if (h->n == 0) return FFMPM_OK;
+  const unsigned blocks = (unsigned)((h->n + 255) / 256);
+  if (h->cfg.dtype == FFMPM_F64)
+    export_by_id_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>(view<double>(h, h->st[h->live]), view<double>(h, *dst), h->n, h->cfg.dim);
+  else
+    export_by_id_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(view<float>(h, h->st[h->live]), view<float>(h, *dst), h->n, h->cfg.dim);
+  return check_launch(h, 1);
+}
+
 int64_t ffmpm_launch_count(const FfMpmHandle* h) { return h ? h->launches : 0; }
 
 __global__ void debug_red_add4_kernel(float* __restrict__ dst, float a, float b, float c, float d, long long count) {

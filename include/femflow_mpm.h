@@ -215,6 +215,13 @@ int ffmpm_poll_error(FfMpmHandle* h, void* stream, int32_t* code, int64_t* n_oob
  * `out` a device or pinned-host-mapped pointer of n*dim doubles. */
 int ffmpm_snapshot(FfMpmHandle* h, double coeff, double* out, void* stream);
 
+/* The live state written into `dst` (same SoA layout, any stride >= n; only x, v, C, F and Jp are touched) in the
+ * caller's ORIGINAL particle order: dst.field[c * dst.stride + id[p]] = live.field[c * stride + p].  The reference
+ * updates the caller's arrays in place, particle i staying particle i (three_d/g2p.py:43-59); the CUDA path stores
+ * particles cell-sorted and carries their index in the id plane -- this is the way back for callers that hold
+ * their state outside the library (HostSubstepPipeline).  Without an id plane it is a plain copy. */
+int ffmpm_export_state(FfMpmHandle* h, const FfMpmState* dst, void* stream);
+
 /* Number of kernel launches issued by this handle so far. */
 int64_t ffmpm_launch_count(const FfMpmHandle* h);
 

@@ -463,6 +463,23 @@ class FakeLib:
         dst[ids] = p["x"][:, :n].T.astype(np.float64) / _val(coeff)
         return N.FFMPM_OK
 
+    def ffmpm_export_state(self, h, dst_ref, stream):
+        h = self._h(h)
+        p, n, d = self._planes(h, h.live), h.n, h.cfg.dim
+        saved = h.st[1]
+        h.st[1] = N.FfMpmState.from_buffer_copy(dst_ref._obj)
+        try:
+            q = self._planes(h, 1)
+        finally:
+            h.st[1] = saved
+        ids = p["id"][:n] if p["id"] is not None else np.arange(n)
+        for k in ("x", "v", "C", "F"):
+            q[k][:, ids] = p[k][:, :n]
+        if p["Jp"] is not None and q["Jp"] is not None:
+            q["Jp"][ids] = p["Jp"][:n]
+        h.launches += 1
+        return N.FFMPM_OK
+
     def ffmpm_debug_red_add4(self, dst, v, count, stream):
         return N.FFMPM_OK
 

@@ -64,9 +64,20 @@ class FakeGraph:
         self.solver.steps_run += self.n
 
 
+class FakeLibrary:
+    def ffmpm_export_state(self, h, dst, stream):
+        FakeSolver.exports += 1
+        return 0
+
+
 class FakeSolver:
-    """The surface of femflow_b200.mpm.MpmSolver that bench.py touches."""
+    """The surface of femflow_b200.mpm.MpmSolver that bench.py (and the host pipeline it drives) touches."""
     instances = []
+    exports = 0
+    lib, _h = FakeLibrary(), None
+
+    def _stream(self, stream=None):
+        return None
 
     def __init__(self, dim, res, dt, volume, gravity, hardening, *, capacity, device=None, **kw):
         self.dim, self.capacity, self.device, self.dtype = dim, (capacity + 63) // 64 * 64, torch.device("cpu"), torch.float32
@@ -123,6 +134,7 @@ def dry(monkeypatch):
     monkeypatch.setattr(mpm, "MpmSolver", FakeSolver)
     monkeypatch.delenv("RANK", raising=False); monkeypatch.delenv("WORLD_SIZE", raising=False)
     FakeSolver.instances.clear()
+    FakeSolver.exports = 0
     return monkeypatch
 
 
@@ -149,20 +161,20 @@ def test_default_line_carries_the_contract(dry, capsys):
     assert len(d["ms_per_step_samples"]) == 5
     assert d["config"]["workload"].startswith("3D elastic block") and d["config"]["parallelism"] == "single GPU"
     e = d["e2e"]
-    assert e["h2d_bytes_per_step"] == e["d2h_bytes_per_step"] == 24 * 4 * s.num_particles and "streamed" not in e
+    assert e["h2d_bytes_per_step"] == e["d2h_bytes_per_step"] == 24 * 4 * s.num_particles
+    # the headline e2e is the pipelined host-buffer path (12 calls, 3 slots); the blocking call is reported beside it
+    assert "pipelined_error" not in e and e["steps"] == 12 and e["serial"]["steps"] == 2 and "HostSubstepPipeline" in e["api"]
+    assert FakeSolver.exports == 3 + 12 and len(s.buffers) == 2 and s.buffers[0].x.shape[1] == s.capacity
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and set(r["phase_ms"]) == {"clear", "bin", "p2g", "grid_op", "g2p"}
     assert r["algorithmic_bytes_per_launch"] > 0 and 0 < r["frac"]
-    assert s.steps_run == 3 + 10 + 1 + 2                                       # warm-up, timed region, e2e warm step + e2e steps
+    assert s.steps_run == 3 + 10 + 1 + 2 + 3 + 12      # warm-up, timed region, e2e warm step + e2e steps, pipeline warm + timed
 
 
-def test_graph_and_streamed_options(dry, capsys):
-    d = run_bench(dry, capsys, "--steps", "20", "--warmup", "4", "--e2e-steps", "1", "--graph", "--e2e-streamed")
+def test_graph_and_serial_only_options(dry, capsys):
+    d = run_bench(dry, capsys, "--steps", "20", "--warmup", "4", "--e2e-steps", "1", "--graph", "--e2e-serial-only")
     assert d["config"]["cuda_graph"] is True and d["gpu_launches"] == 200 and d["ms_per_step_samples"] == []
-    st = d["e2e"]["streamed"]
-    assert st.get("error") is None and st["steps"] == 4 and st["value"] > 0
-    s = FakeSolver.instances[0]
-    assert len(s.buffers) == 2 and s.buffers[0].x.shape[1] == s.capacity       # the solver got its own buffers back
+    assert "serial" not in d["e2e"] and d["e2e"]["steps"] == 1 and d["e2e"]["value"] > 0
     # steps not a multiple of 10: the graph request is declined, not an error
     d = run_bench(dry, capsys, "--steps", "7", "--graph")
     assert d["config"]["cuda_graph"] is False and d["gpu_launches"] == 70 and len(d["ms_per_step_samples"]) == 7
@@ -231,6 +243,7 @@ def test_two_rank_line(tmp_path):
     assert "coupled" in d["config"]["parallelism"] and "bar" in d["config"]["workload"]
     assert d["config"]["migration"]["particles_received"] > 0 and d["config"]["migration"]["rounds"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 24 * 8 * total and d["roofline"] is None and d["config"]["n_oob"] == 0
+    assert "pipelined_error" not in d["e2e"] and d["e2e"]["steps"] == 12 and d["e2e"]["serial"]["steps"] == 1
 
 
 def test_cpu_baseline_leg_and_reference_arm(dry, capsys, monkeypatch):
