@@ -46,6 +46,12 @@ def make_scene(workload: str, seed: int = 0, cells_x=None, res_x=None):
         sc = scenes.elastic_block(3, 256, 128, 2, seed, perturb=False)
         sc.name += " (at rest)"
         return sc
+    if workload.startswith("3d16m-drift:"):   # the headline block moving along +x at <c> cells per substep: every substep a
+        c = float(workload.split(":")[1])      # fraction ~c of the particles changes cell (P2G run fragmentation, re-binning)
+        sc = scenes.config_3d_16m(seed)
+        sc.v[:, 0] += np.float32(c / sc.res / sc.dt)
+        sc.name += f" drifting {c} cells/substep"
+        return sc
     if workload.startswith("3d:"):        # 3d:<res>:<cells>  (tests / quick runs)
         _, res, cells = workload.split(":")
         return scenes.elastic_block(3, int(res), int(cells), 2, seed)
@@ -245,12 +251,14 @@ def main():
                     help="per-particle material layout (N=1): auto = table/rows when <= 256 distinct triples, planes = 3 scalar planes")
     ap.add_argument("--slab-timing", action="store_true", help="N>1: print per-phase CUDA-event times per rank to stderr")
     ap.add_argument("--margin", type=int, default=4, help="slab halo margin in cells = substeps between migrations")
-    ap.add_argument("--drift", type=float, default=0.1, help="N>1 coupled bar: drift along x in cells per substep")
+    ap.add_argument("--drift", type=float, default=0.02,
+                    help="N>1 coupled bar: drift along x in cells per substep (0.02 = 26 m/s, a quarter of the material's wave speed "
+                         "at the CFL-scaled dt of the block; 0.1 is the stress case kept in profiles/)")
     ap.add_argument("--e2e-serial-only", action="store_true",
                     help="report the blocking host-buffer call as e2e.value instead of the pipelined one (round-1 behaviour)")
-    ap.add_argument("--halo", default="p2p", choices=["p2p", "symm"],
-                    help="N>1: halo planes by NCCL send/recv (p2p) or by one-sided puts into the neighbour's "
-                         "symmetric-memory inbox over NVLink (symm; SymmHalo, not yet measured)")
+    ap.add_argument("--halo", default="symm", choices=["p2p", "symm"],
+                    help="N>1: halo planes by one-sided puts into the neighbour's symmetric-memory inbox over NVLink (symm, "
+                         "default; falls back to p2p when torch's symmetric memory is unavailable) or by NCCL send/recv (p2p)")
     ap.add_argument("--graph", action="store_true",
                     help="N=1: replay the timed substeps as CUDA graphs of 10 substeps (MpmSolver.make_graph); "
                          "measured -11 %% on 2d1m, -4 %% on a 2M-particle 3D block (profiles/r01q_graph_experiment.json)")
@@ -286,6 +294,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     from femflow_b200.mpm import MpmSolver
+    from femflow_b200._numa import bind_to_gpu
+    # pinned host buffers (e2e) are allocated from the CPUs next to this rank's GPU; the CPU-baseline leg gets every core back
+    affinity0 = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    numa_note = bind_to_gpu(local_rank)
 
     dam = args.workload.startswith("dam")
     scene = make_scene("3d:256:8" if dam else args.workload, seed=rank)
@@ -561,6 +573,11 @@ def main():
                     "frac_of_nominal_8TBs": achieved / 8000.0,
                     "substep_frac_of_hbm_roofline": (total_alg / (ms * 1e-3 / args.steps) / 1e9) / peak}
 
+    if affinity0 is not None:
+        try:
+            os.sched_setaffinity(0, affinity0)
+        except Exception:
+            pass
     cpu = None
     if not args.no_cpu_baseline:
         try:
@@ -580,10 +597,10 @@ def main():
                    **({"presteps": args.presteps} if dam else {}),
                    "l2": ("inputs larger than L2 (no flush)" if n * (112 if scene.dim == 3 else 52) > 2 * 126e6
                           else "particle state fits in the 126 MB L2 (flagged: HBM fraction is not meaningful)"),
-                   "n_oob": n_oob,
+                   "n_oob": n_oob, "host_numa": numa_note,
                    "material_layout": (solver.local.solver if hasattr(solver, "local") else solver).material_layout,
                    "parallelism": (f"{world} slabs along x, halo sum over "
-                                   f"{'NCCL p2p' if args.halo == 'p2p' else 'symmetric-memory puts'} every substep, device-side "
+                                   f"{'NCCL p2p' if solver.driver.halo == 'p2p' else 'symmetric-memory puts over NVLink'} every substep, device-side "
                                    f"migration (pack/unpack kernels) every {solver.driver.migrate_every} substeps; "
                                    + ("dam break" if dam else coupling)) if hasattr(solver, "driver") else "single GPU",
                    **({"migration": mig_stats} if world > 1 else {}),

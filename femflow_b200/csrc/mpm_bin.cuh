@@ -123,7 +123,9 @@ FFMPM_HD int bin_key2(int bx, int by, int ty) {
 
 // Bin key of a particle position: tile-major id of its LOCAL base cell, or n_cells
 // when the stencil would leave the grid (utils.py:138-150) / the position is NaN.
-template <typename T>
+// IDX32: cfg.index_fp32 is known to hold (fp32 build, power-of-two inv_dx): the exact-fp32 indexing without the
+// run-time choice (the fp64 code is then not generated at all).
+template <typename T, bool IDX32 = false>
 FFMPM_HD int bin_key_of(const DevCfg& cfg, const BinBuffers& B, T x0, T x1, T x2, int* base_x = nullptr) {
   const T xs[3] = {x0, x1, x2};
   int b[3] = {0, 0, 0};
@@ -133,10 +135,16 @@ FFMPM_HD int bin_key_of(const DevCfg& cfg, const BinBuffers& B, T x0, T x1, T x2
     if (d < cfg.dim) {
       T fx;
       int g;
-      base_fx(xs[d], cfg, g, fx);
+      if constexpr (IDX32 && sizeof(T) == 4) {
+        float f;
+        base_fx_f32((float)xs[d], (float)cfg.inv_dx, g, f);
+        fx = (T)f;
+      } else {
+        base_fx(xs[d], cfg, g, fx);
+      }
       b[d] = g - cfg.origin[d];
       if (d == 0 && base_x) *base_x = g;
-      ok = ok && !isnan((double)xs[d]) && b[d] >= 0 && b[d] + 2 < cfg.n[d];
+      ok = ok && xs[d] == xs[d] && b[d] >= 0 && b[d] + 2 < cfg.n[d];
     }
   }
   if (!ok) return B.n_cells;
@@ -145,6 +153,26 @@ FFMPM_HD int bin_key_of(const DevCfg& cfg, const BinBuffers& B, T x0, T x1, T x2
 
 // Warp-aggregated histogram: one atomic per distinct key per warp; the lanes of a group
 // take consecutive ranks in lane order.  Must be called by all 32 lanes; key < 0 = idle.
+// The same in two halves, so that the caller can put work between the atomic and the use of its return value
+// (the round trip to L2 is several hundred cycles): bin_rank_issue posts the atomic, bin_rank_finish writes the rank.
+struct BinRankTicket {
+  unsigned peers;
+  int base;      // valid in the group's leader lane
+};
+__device__ __forceinline__ BinRankTicket bin_rank_issue(const BinBuffers& B, int key) {
+  BinRankTicket t;
+  const unsigned lane = threadIdx.x & 31;
+  t.peers = __match_any_sync(0xffffffffu, key);
+  t.base = 0;
+  if (key >= 0 && (int)lane == __ffs(t.peers) - 1) t.base = atomicAdd(&B.cell_count[key], __popc(t.peers));
+  return t;
+}
+__device__ __forceinline__ void bin_rank_finish(const BinBuffers& B, const BinRankTicket& t, int key, long long slot) {
+  const unsigned lane = threadIdx.x & 31;
+  const int base = __shfl_sync(0xffffffffu, t.base, __ffs(t.peers) - 1);
+  if (key >= 0) B.rank[slot] = base + __popc(t.peers & ((1u << lane) - 1u));
+}
+
 __device__ __forceinline__ void bin_rank_warp(const BinBuffers& B, int key, long long slot) {
   const unsigned lane = threadIdx.x & 31;
   const unsigned peers = __match_any_sync(0xffffffffu, key);

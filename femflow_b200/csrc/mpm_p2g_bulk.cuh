@@ -91,9 +91,18 @@ __device__ __forceinline__ void p2g_runs_phase2_adjacent(P2GWarpSlab<float>& S, 
   const unsigned below = (1u << lane) - 1u;
   const int r_lo = __popc(h0 & below) + __popc(h1 & below);
   const unsigned mine0 = (h0 >> lane) & 1u, mine1 = (h1 >> lane) & 1u;
+  const int n_runs = __popc(h0) + __popc(h1);
+  if (n_runs * 3 > 32) {
+    // fragmented window (particles that changed cell since the G2P that placed them): merge the fragments
+    const int merged = p2g_sort_window(S, node, cnt, lane);
+    if (merged >= 0) {
+      __syncwarp();
+      p2g_accumulate_runs<float, true>(S, merged, lane, ny, nz, grid);
+      return;
+    }
+  }
   if (mine0) S.run_start[r_lo] = 2 * lane;
   if (mine1) S.run_start[r_lo + mine0] = 2 * lane + 1;
-  const int n_runs = __popc(h0) + __popc(h1);
   if (lane == 0) S.run_start[n_runs] = cnt;
   __syncwarp();
   p2g_accumulate_runs<float>(S, n_runs, lane, ny, nz, grid);

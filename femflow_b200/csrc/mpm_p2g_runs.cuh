@@ -44,6 +44,7 @@ struct P2GWarpSlab {
   P2GVec4<T> pay[4][P2G_PADDED];  // {mvx,mvy,mvz,m} {a00,a01,a02,fx} {a10,a11,a12,fy} {a20,a21,a22,fz}, a = affine*dx
   int node0[P2G_WINDOW];          // linear LOCAL node id of the particle's base cell (-1: outside the grid)
   int run_start[P2G_WINDOW + 1];  // window-relative first slot of each run (+ sentinel)
+  unsigned char order[P2G_WINDOW];   // INDIRECT phase 2: position in cell-sorted order -> slot of the window
 };
 
 // Phase 1 tail: park one particle's payload.
@@ -65,14 +66,17 @@ __device__ __forceinline__ int p2g_park(P2GWarpSlab<T>& S, P2GParticle3<T>& q, i
 }
 
 // Phase 2 proper: lane per (run, x-slab) over the run table S.run_start[0 .. n_runs] of a parked window.
-template <typename T>
+// INDIRECT: the runs are runs of the window's particles in CELL-SORTED order (S.order maps a sorted position to its
+// slot) instead of runs of consecutive slots -- see p2g_sort_window.
+template <typename T, bool INDIRECT = false>
 __device__ __forceinline__ void p2g_accumulate_runs(P2GWarpSlab<T>& S, int n_runs, int lane, int ny, int nz,
                                                     T* __restrict__ grid) {
   const int n_items = n_runs * 3;
   for (int item = lane; item < n_items; item += 32) {
     const int r = item / 3, li = item - r * 3;
     const int r0 = S.run_start[r], r1 = S.run_start[r + 1];
-    if (S.node0[r0] < 0) continue;   // a run of out-of-grid particles
+    const int node_r = S.node0[INDIRECT ? (int)S.order[r0] : r0];
+    if (node_r < 0) continue;   // a run of out-of-grid particles
     const T ci = (T)li;
     // B-spline piece of this slab along x: w = s * (f - c)^2 + o  (three_d/p2g.py:55)
     const T sx = li == 1 ? (T)-1 : (T)0.5, cx_ = (T)1.5 - (T)0.5 * ci, ox_ = li == 1 ? (T)0.75 : (T)0;
@@ -80,7 +84,7 @@ __device__ __forceinline__ void p2g_accumulate_runs(P2GWarpSlab<T>& S, int n_run
 #pragma unroll
     for (int e = 0; e < 9; ++e) ax[e] = ay[e] = az[e] = am[e] = (T)0;
     for (int qi = r0; qi < r1; ++qi) {
-      const int ph = p2g_pad(qi);
+      const int ph = p2g_pad(INDIRECT ? (int)S.order[qi] : qi);
       const P2GVec4<T> p0 = S.pay[0][ph], p1 = S.pay[1][ph], p2 = S.pay[2][ph], p3 = S.pay[3][ph];
       const T fx = p1.w, fy = p2.w, fz = p3.w;
       T wy[3], wz[3];
@@ -106,13 +110,80 @@ __device__ __forceinline__ void p2g_accumulate_runs(P2GWarpSlab<T>& S, int n_run
         }
       }
     }
-    T* g = grid + ((long long)S.node0[r0] + (long long)li * ny * nz) * 4;
+    T* g = grid + ((long long)node_r + (long long)li * ny * nz) * 4;
 #pragma unroll
     for (int j = 0; j < 3; ++j)
 #pragma unroll
       for (int k = 0; k < 3; ++k)
         red_add4(g + ((long long)j * nz + k) * 4, ax[j * 3 + k], ay[j * 3 + k], az[j * 3 + k], am[j * 3 + k]);
   }
+}
+
+// Cell-sort of one window inside the warp.  The reordering G2P stores a particle at the slot of the cell it was in
+// BEFORE it was advected, so with particles moving c cells per substep a fraction ~c of a window sits in a
+// neighbouring cell's run: every such particle is a run of its own and cuts another run in two, the (run, slab)
+// items overflow the 32 lanes and phase 2 takes two or three passes of short, ragged runs.  Sorting the window's
+// 64 (base node, slot) pairs -- a bitonic network over two keys per lane, shuffles only -- merges all particles of
+// a cell within the window into ONE run again.  lane l holds the elements 2l and 2l+1; key = node << 6 | slot
+// (nodes are compared relative to the window's smallest: 26 bits), out-of-grid particles sort last.
+// Returns the number of runs and fills S.order / S.run_start, or -1 when the window's nodes span more than 2^26 ids
+// (the caller then keeps the unsorted run table).  ~150 instructions: only called when the unsorted run table would
+// need more than one pass.
+__device__ __forceinline__ int p2g_sort_window(P2GWarpSlab<float>& S, const int (&node)[2], int cnt, int lane) {
+  const unsigned big = 0x03ffffffu;                                    // out of grid / past the end: sorts last
+  unsigned lo = 0xffffffffu, hi = 0u;
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+    if (2 * lane + h < cnt && node[h] >= 0) { lo = min(lo, (unsigned)node[h]); hi = max(hi, (unsigned)node[h]); }
+  lo = __reduce_min_sync(0xffffffffu, lo);
+  hi = __reduce_max_sync(0xffffffffu, hi);
+  if (lo != 0xffffffffu && hi - lo >= big) return -1;
+  unsigned key[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const bool live = 2 * lane + h < cnt && node[h] >= 0;
+    const unsigned rel = live ? (unsigned)node[h] - lo : big;
+    key[h] = (rel << 6) | (unsigned)(2 * lane + h);
+  }
+#pragma unroll
+  for (int k = 2; k <= P2G_WINDOW; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j >= 1; j >>= 1) {
+      if (j == 1) {
+        // partner = the lane's other element; ascending iff bit k of the element index is clear
+        const bool up = ((2 * lane) & k) == 0;
+        const unsigned a = min(key[0], key[1]), b = max(key[0], key[1]);
+        key[0] = up ? a : b;
+        key[1] = up ? b : a;
+      } else {
+        const int lj = j >> 1;                                         // partner lane distance
+        const bool lower = (lane & lj) == 0;                           // this lane holds the lower element index
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const unsigned other = __shfl_xor_sync(0xffffffffu, key[h], lj);
+          const bool up = ((2 * lane + h) & k) == 0;
+          key[h] = (lower == up) ? min(key[h], other) : max(key[h], other);
+        }
+      }
+    }
+  }
+  // sorted position 2l + h holds key[h]
+  S.order[2 * lane] = (unsigned char)(key[0] & 63u);
+  S.order[2 * lane + 1] = (unsigned char)(key[1] & 63u);
+  const unsigned c0 = key[0] >> 6, c1 = key[1] >> 6;
+  unsigned prev = __shfl_up_sync(0xffffffffu, c1, 1);
+  if (lane == 0) prev = 0xffffffffu;
+  // elements past `cnt` carry the `big` key and sort behind everything: position < cnt <=> a real particle
+  const unsigned h0 = __ballot_sync(0xffffffffu, 2 * lane < cnt && c0 != prev);
+  const unsigned h1 = __ballot_sync(0xffffffffu, 2 * lane + 1 < cnt && c1 != c0);
+  const unsigned below = (1u << lane) - 1u;
+  const int r_lo = __popc(h0 & below) + __popc(h1 & below);
+  const unsigned mine0 = (h0 >> lane) & 1u, mine1 = (h1 >> lane) & 1u;
+  if (mine0) S.run_start[r_lo] = 2 * lane;
+  if (mine1) S.run_start[r_lo + mine0] = 2 * lane + 1;
+  const int n_runs = __popc(h0) + __popc(h1);
+  if (lane == 0) S.run_start[n_runs] = cnt;
+  return n_runs;
 }
 
 // Runs + phase 2 over a parked window (call after a __syncwarp() that follows phase 1); lane l owns the

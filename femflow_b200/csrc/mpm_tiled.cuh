@@ -49,7 +49,8 @@ __device__ __forceinline__ void cp_async4(void* sdst, const void* gsrc) {
 // ahead.  Each thread only ever reads what it copied itself, so no barrier is involved.
 // ROWS: the state carries 1-byte material rows (table mode); compiled out otherwise, the kernel sits
 // exactly at its 64-register budget.
-template <typename T, int MIN_BLOCKS, bool PRE = false, bool ROWS = false>
+// IDX32: exact fp32 cell indexing known at compile time (cfg.index_fp32; see base_fx).
+template <typename T, int MIN_BLOCKS, bool PRE = false, bool ROWS = false, bool IDX32 = false>
 __global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_tiled3_kernel(DevCfg cfg, StateView<T> src, StateView<T> dst,
                                                                  BinBuffers B, const T* __restrict__ grid, ErrRec* err) {
   using V4 = typename Vec4<T>::type;
@@ -179,9 +180,15 @@ __global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_tiled3_kernel(Dev
         }
         int gx, gy, gz;
         T fx, fy, fz;
-        base_fx(x0, cfg, gx, fx);
-        base_fx(x1, cfg, gy, fy);
-        base_fx(x2, cfg, gz, fz);
+        if constexpr (IDX32 && sizeof(T) == 4) {
+          base_fx_f32(x0, (float)cfg.inv_dx, gx, fx);
+          base_fx_f32(x1, (float)cfg.inv_dx, gy, fy);
+          base_fx_f32(x2, (float)cfg.inv_dx, gz, fz);
+        } else {
+          base_fx(x0, cfg, gx, fx);
+          base_fx(x1, cfg, gy, fy);
+          base_fx(x2, cfg, gz, fz);
+        }
         const int cb = ((gx - cfg.origin[0] - ox) * TN3 + (gy - cfg.origin[1] - oy)) * TN3 + (gz - cfg.origin[2] - oz);
         T vx, vy, vz, c00, c01, c02, c10, c11, c12, c20, c21, c22;
         g2p_accumulate3<T>([&](int i, int j, int k) { return tile[cb + (i * TN3 + j) * TN3 + k]; }, fx, fy, fz,
@@ -206,10 +213,13 @@ __global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_tiled3_kernel(Dev
         o[22] = m20 * f01 + m21 * f11 + m22 * f21;
         o[23] = m20 * f02 + m21 * f12 + m22 * f22;
         int gbx = 0;
-        next_key = bin_key_of<T>(cfg, B, o[0], o[1], o[2], &gbx);
+        next_key = bin_key_of<T, IDX32>(cfg, B, o[0], o[1], o[2], &gbx);
         B.keys[slot] = next_key;
         leaving = gbx < cfg.own_lo || gbx >= cfg.own_hi;
       }
+      // next substep's histogram + within-cell rank (same scheme as bin_count_kernel): the atomic is posted here and
+      // its return value is used after the 24 stores below, which cover its round trip to L2
+      const BinRankTicket ticket = bin_rank_issue(B, next_key);
       {
         // slabs: count the particles that now belong to a neighbour rank (read by the migration logic)
         const unsigned lm = __ballot_sync(0xffffffffu, leaving);
@@ -229,8 +239,7 @@ __global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_tiled3_kernel(Dev
           if constexpr (ROWS) dst.material[slot] = (unsigned char)row;
         }
       }
-      // next substep's histogram + within-cell rank (same scheme as bin_count_kernel)
-      bin_rank_warp(B, next_key, slot);
+      bin_rank_finish(B, ticket, next_key, slot);
       if constexpr (PRE) {
         q_cur = q_nxt; q_nxt = q_nn;
         pre_buf ^= 1;
@@ -249,14 +258,17 @@ int g2p_tiled(const DevCfg& cfg, const StateView<T>& src, const StateView<T>& ds
     // FFMPM_G2P_PRE=0 disables the cp.async input prefetch (64 registers, 8 CTAs per SM either way)
     static int prefetch = [] { const char* e = getenv("FFMPM_G2P_PRE"); return e ? atoi(e) : 1; }();
     const bool rows = src.material != nullptr;
-    if (prefetch && rows)
-      g2p_tiled3_kernel<T, 8, true, true><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
-    else if (prefetch)
-      g2p_tiled3_kernel<T, 8, true, false><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
-    else if (rows)
-      g2p_tiled3_kernel<T, 8, false, true><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
-    else
-      g2p_tiled3_kernel<T, 8, false, false><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
+    const bool i32 = cfg.index_fp32 != 0;
+#define FFMPM_G2P(PRE_, ROWS_)                                                                                          \
+  do {                                                                                                                  \
+    if (i32) g2p_tiled3_kernel<T, 8, PRE_, ROWS_, true><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);   \
+    else g2p_tiled3_kernel<T, 8, PRE_, ROWS_, false><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);      \
+  } while (0)
+    if (prefetch && rows) FFMPM_G2P(true, true);
+    else if (prefetch) FFMPM_G2P(true, false);
+    else if (rows) FFMPM_G2P(false, true);
+    else FFMPM_G2P(false, false);
+#undef FFMPM_G2P
   } else if (src.material) {
     g2p_tiled3_kernel<T, 4, false, true><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
   } else {

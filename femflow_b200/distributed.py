@@ -269,8 +269,19 @@ class SlabDriver:
         self.recv_hi = torch.zeros(shape_hi, dtype=probe.dtype, device=probe.device)
         self.halo_bytes = (self.recv_lo.numel() + self.recv_hi.numel()) * probe.element_size()
         self.symm = None
+        self.halo = halo if plan.world > 1 else "none"
         if halo == "symm" and plan.world > 1:
-            self.symm = SymmHalo(plan, tuple(probe.shape[1:]), probe.dtype, probe.device, group, fabric)
+            try:
+                self.symm = SymmHalo(plan, tuple(probe.shape[1:]), probe.dtype, probe.device, group, fabric)
+            except Exception as e:      # no symmetric memory on this torch build / topology: the NCCL exchange does the same job
+                import warnings
+                warnings.warn(f"symmetric-memory halo unavailable ({type(e).__name__}: {e}); using NCCL send/recv")
+                self.halo = "p2p"
+            # every rank must take the same transport: one that could not map its peers sends everybody back to NCCL
+            ok = torch.tensor([1 if self.symm is not None else 0], dtype=torch.int32, device=probe.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0:
+                self.symm, self.halo = None, "p2p"
         self.migrated = 0
         self.rebalanced = 0
         self._pending = None

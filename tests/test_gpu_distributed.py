@@ -88,10 +88,9 @@ def test_two_gpu_slabs_match_oracle(tmp_path, nmat):
     assert np.abs(got["C"] - C).max() / (4 * p["inv_dx"] * V) < tol
 
 
-@pytest.mark.skipif(os.environ.get("FFMPM_TEST_SYMM") != "1",
-                    reason="SymmHalo over torch symmetric memory has not run on hardware yet (GPU budget): "
-                           "set FFMPM_TEST_SYMM=1 on a box with two NVLink-connected GPUs")
 def test_two_gpu_symm_halo_matches_oracle(tmp_path):
+    """One-sided halo puts over NVLink peer memory (SymmHalo on torch symmetric memory; green on 2 B200s:
+    profiles/r02c_pytest_gpu_2gpus.txt)."""
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     import torch.multiprocessing as mp

@@ -457,6 +457,40 @@ def test_p2g_kernel_variants(variant, n_materials, monkeypatch):
     s.close()
 
 
+@pytest.mark.parametrize("cells_per_substep", [0.1, 0.45])
+def test_fast_moving_particles_vs_oracle(cells_per_substep):
+    """Particles that change cell every few substeps (a block moving at 0.1 / 0.45 cells per substep in every
+    direction, dt such that the CFL clamp of three_d/grid_op.py:25,34-36 is not reached): the reordering G2P places a
+    particle by the cell it was in BEFORE advection, so the physical order P2G walks is fragmented -- the in-warp
+    window sort of mpm_p2g_runs.cuh (p2g_sort_window) and the multi-pass run table both run here.  16 substeps
+    against the C port."""
+    from femflow_b200 import scenes
+    from femflow_b200.mpm import MpmSolver
+    from oracle import native as ON
+    sc = scenes.elastic_block(3, 64, 24, 2, seed=8)
+    n = sc.n
+    rng = np.random.default_rng(8)
+    x, v, F, C = (a.astype(np.float64) for a in (sc.x, sc.v, sc.F, sc.C))
+    speed = cells_per_substep / sc.res / sc.dt
+    v = np.float32(v + speed * np.array([1.0, -0.6, 0.8]) + rng.normal(0, 0.02 * speed, v.shape)).astype(np.float64)
+    m = np.full(n, sc.mass); mu = np.full(n, sc.mu_0); lam = np.full(n, sc.lambda_0)
+    s = MpmSolver(3, sc.res, sc.dt, sc.volume, 0.0, sc.hardening, capacity=n)
+    s.set_particles(x, v, F, C, None, m, mu, lam)
+    steps = 16
+    for chunk in (1, 5, 10):
+        s.substep(chunk)
+        for _ in range(chunk):
+            ON.solve_mls_mpm_3d(sc.res, float(sc.res), sc.hardening, 1 / sc.res, sc.dt, sc.volume, 0.0, x, m, mu, lam, v, F, C)
+    s.check_errors()
+    out = {k: t.double().cpu().numpy() for k, t in s.get_particles().items()}
+    V = np.abs(v).max()
+    assert rel_err(out["x"], x, 1.0) < 1e-5 * steps
+    assert np.abs(out["v"] - v).max() / V < 1e-5 * steps
+    assert rel_err(out["F"], F, 1.0) < 1e-5 * steps
+    assert np.abs(out["C"] - C).max() / (4 * sc.res * V) < 1e-5 * steps
+    s.close()
+
+
 def test_graph_replay_matches_eager_substeps():
     """MpmSolver.make_graph: 3 replays of a captured pair of substeps (internal binning stream and both
     ping-pong halves inside the capture) against the same 6 substeps launched one by one, from the same
