@@ -363,6 +363,8 @@ def main():
     if rank == 0:
         sampler.start()
     graph = None
+    if scene.dim == 2 and world == 1 and args.steps % 10 == 0:
+        args.graph = True      # a 2D substep is a few tens of microseconds of kernels: replayed as CUDA graphs by default
     if args.graph and world == 1 and not dam and args.steps % 10 == 0:
         graph = solver.make_graph(10)         # captured from the warmed-up (pre-binned) state; does not execute
     l0 = solver.launch_count()
@@ -426,7 +428,7 @@ def main():
     # ---- per-phase timing (same stream, CUDA events) for the roofline of the dominant kernel ----
     phases = {}
     if world == 1 and not dam:
-        names = (["bin"] if (scene.dim == 3 and solver.reorder) else []) + ["p2g", "grid_op", "g2p"]
+        names = (["bin"] if solver.reorder else []) + ["p2g", "grid_op", "g2p"]
         acc = {k: 0.0 for k in ["clear"] + names}
         reps = max(3, min(args.steps, 10))
         for _ in range(reps):

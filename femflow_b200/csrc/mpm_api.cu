@@ -17,6 +17,7 @@
 #include "mpm_tiled.cuh"
 #include "mpm_g2p2g.cuh"
 #include "mpm_migrate.cuh"
+#include "mpm_2d.cuh"
 
 using namespace ffmpm;
 
@@ -374,10 +375,17 @@ static int p2g_t(FfMpmHandle* h, cudaStream_t s) {
   StateView<T> sv = view<T>(h, h->st[h->live]);
   int mode = h->cfg.p2g_mode;
   if (mode == FFMPM_P2G_FUSED) mode = FFMPM_P2G_AUTO;
-  if (mode == FFMPM_P2G_AUTO) mode = (h->binned && h->cfg.dim == 3) ? FFMPM_P2G_TILED : FFMPM_P2G_SCATTER;
+  if (mode == FFMPM_P2G_AUTO) mode = h->binned ? FFMPM_P2G_TILED : FFMPM_P2G_SCATTER;
   if (mode == FFMPM_P2G_TILED) {
-    if (h->cfg.dim != 3) return set_err(FFMPM_E_INVALID, "tiled P2G is 3D only (2D uses the scatter kernel)");
     if (!h->binned) return set_err(FFMPM_E_STATE, "tiled P2G needs ffmpm_bin first");
+    if (h->cfg.dim == 2) {
+      // 2D: warp-autonomous cell runs in physical order (mpm_2d.cuh); correct for any order, fast for a sorted one
+      const long long windows = (h->n + P2G_WINDOW - 1) / P2G_WINDOW;
+      long long want = (windows + P2G_RUN_WARPS - 1) / P2G_RUN_WARPS, cap = (long long)h->sm_count * 8;
+      const int blocks = (int)(want < cap ? want : cap);
+      p2g_runs2_kernel<T><<<blocks < 1 ? 1 : blocks, P2G_RUN_WARPS * 32, 0, s>>>(h->dev, sv, h->n, (T*)h->grid, h->err);
+      return check_launch(h, 1);
+    }
     // P2G variant (FFMPM_P2G_VARIANT): 0 = through the permutation, 1 = physical order (kept sorted by G2P),
     // 5 (default) = physical order with the window state prefetched by per-lane cp.async (fp32, mpm_p2g_bulk.cuh)
     if constexpr (sizeof(T) == 4) {
@@ -403,7 +411,7 @@ int ffmpm_p2g(FfMpmHandle* h, void* stream) {
   int rc = ready(h);
   if (rc) return rc;
   // a zero grid + the particles the bin buffers describe: what P2G writes stays inside bin.node_tiles
-  h->grid_in_blocks = h->grid_clean[h->grid_cur] && h->binned && h->bin_slot == h->grid_cur && h->cfg.dim == 3 && h->n > 0;
+  h->grid_in_blocks = h->grid_clean[h->grid_cur] && h->binned && h->bin_slot == h->grid_cur && h->n > 0;
   h->grid_listed[h->grid_cur] = h->grid_in_blocks;
   h->grid_clean[h->grid_cur] = false;
   if (h->n == 0) return FFMPM_OK;
@@ -414,13 +422,17 @@ template <typename T>
 static int grid_op_t(FfMpmHandle* h, cudaStream_t s, const void* halo_lo = nullptr, long long nodes_lo = 0,
                      const void* halo_hi = nullptr, long long nodes_hi = 0) {
   unsigned blocks = (unsigned)((h->n_nodes + 255) / 256);
-  if (h->cfg.dim == 3 && h->grid_in_blocks && h->sparse_grid_op) {
+  if (h->grid_in_blocks && h->sparse_grid_op) {
     // the node-block list comes from the binning, which may still be in flight on the internal stream
     if (h->bin_pending) {
       CUDA_TRY(cudaStreamWaitEvent(s, h->ev_join, 0));
       h->bin_pending = false;
     }
     h->grid_in_blocks = false;   // velocities now: a second update would have to see every node again
+    if (h->cfg.dim == 2)
+      grid_op2_blocks_kernel<T><<<h->sm_count * 4, 256, 0, s>>>(h->dev, (T*)h->grid, h->bin.node_tiles2[h->grid_cur],
+                                                               h->bin.node_counts + h->grid_cur, h->bin.ntile[1]);
+    else
     grid_op3_blocks_kernel<T><<<h->sm_count * 8, 256, 0, s>>>(h->dev, (T*)h->grid, h->n_nodes, (const T*)halo_lo, nodes_lo,
                                                              (const T*)halo_hi, nodes_hi, h->colliders,
                                                              h->bin.node_tiles2[h->grid_cur], h->bin.node_counts + h->grid_cur,
@@ -456,6 +468,15 @@ int ffmpm_grid_op_halo(FfMpmHandle* h, const void* recv_lo, int32_t planes_lo, c
 template <typename T>
 static int g2p_t(FfMpmHandle* h, cudaStream_t s) {
   StateView<T> sv = view<T>(h, h->st[h->live]);
+  if (h->binned && h->have_alt && h->cfg.dim == 2) {
+    // 2D, binned: thread per binned slot, new state in cell order into the other buffer, next substep pre-binned
+    StateView<T> dst = view<T>(h, h->st[h->live ^ 1]);
+    g2p_reorder2_kernel<T><<<(unsigned)((h->n + 255) / 256), 256, 0, s>>>(h->dev, sv, dst, h->n, h->bin, (const T*)h->grid, h->err);
+    h->live ^= 1;
+    h->binned = false;
+    h->prebinned = true;
+    return check_launch(h, 1);
+  }
   if (h->binned && h->have_alt && h->cfg.dim == 3) {
     // binned: write the particles back in cell order into the other buffer
     StateView<T> dst = view<T>(h, h->st[h->live ^ 1]);
@@ -495,7 +516,7 @@ static bool p2g_independent_of_bin(const FfMpmHandle* h) {
 }
 
 static bool binned_pipeline(const FfMpmHandle* h) {
-  return h->cfg.dim == 3 && h->have_alt && h->cfg.p2g_mode != FFMPM_P2G_SCATTER;
+  return h->have_alt && h->cfg.p2g_mode != FFMPM_P2G_SCATTER;
 }
 
 // Binning of the live buffer (+ a cleared idle grid for the fused G2P2G) on the auxiliary
@@ -512,7 +533,13 @@ static int fork_bin(FfMpmHandle* h, cudaStream_t s, bool clear_idle) {
     const int idle = h->grid_cur ^ 1;
     if (h->grid_listed[idle] && h->sparse_grid_op) {
       // only the node blocks its last substep touched (listed by that substep's binning) are non-zero
-      if (h->cfg.dtype == FFMPM_F64)
+      if (h->cfg.dim == 2 && h->cfg.dtype == FFMPM_F64)
+        grid_clear_blocks2_kernel<double><<<h->sm_count * 4, 256, 0, w>>>(h->dev, (double*)h->grids[idle], h->bin.node_tiles2[idle],
+                                                                         h->bin.node_counts + idle, h->bin.ntile[1]);
+      else if (h->cfg.dim == 2)
+        grid_clear_blocks2_kernel<float><<<h->sm_count * 4, 256, 0, w>>>(h->dev, (float*)h->grids[idle], h->bin.node_tiles2[idle],
+                                                                        h->bin.node_counts + idle, h->bin.ntile[1]);
+      else if (h->cfg.dtype == FFMPM_F64)
         grid_clear_blocks_kernel<double><<<h->sm_count * 8, 256, 0, w>>>(h->dev, (double*)h->grids[idle], h->bin.node_tiles2[idle],
                                                                         h->bin.node_counts + idle, h->bin.ntile[1], h->bin.ntile[2]);
       else
@@ -537,7 +564,7 @@ int ffmpm_scatter(FfMpmHandle* h, void* stream) {
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   const bool binned = binned_pipeline(h) && h->n > 0;
-  const bool fuse = binned && h->fuse;
+  const bool fuse = binned && h->fuse && h->cfg.dim == 3;
   if (h->scatter_ahead) {
     // the previous fused gather already scattered the live state into the idle grid
     h->scatter_ahead = false;
@@ -588,7 +615,7 @@ int ffmpm_gather(FfMpmHandle* h, void* stream) {
     CUDA_TRY(cudaStreamWaitEvent(s, h->ev_join, 0));
     h->bin_pending = false;
   }
-  const bool can_fuse = h->fuse && binned_pipeline(h) && h->n > 0 && h->binned &&
+  const bool can_fuse = h->fuse && h->cfg.dim == 3 && binned_pipeline(h) && h->n > 0 && h->binned &&
                         h->grid_clean[h->grid_cur ^ 1] && !(h->cfg.dim == 3 && h->cfg.model == FFMPM_SNOW);
   if (can_fuse)
     return h->cfg.dtype == FFMPM_F64 ? g2p2g_t<double>(h, s) : g2p2g_t<float>(h, s);

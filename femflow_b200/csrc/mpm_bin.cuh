@@ -61,10 +61,13 @@ inline void bin_geometry(int dim, const int* n, int* tiles, int& n_tiles, int& n
   n_cells = n_tiles * TILE_CELLS;
 }
 
+// Node blocks: 4x4x4 nodes in 3D, 8x8 in 2D -- the edge of the base-cell tiles, so that a tile scatters into the
+// blocks t and t+1 per axis.
 inline int bin_node_tiles(int dim, const int* n, int* ntile) {
+  const int edge = dim == 3 ? TILE3 : TILE2;
   int total = 1;
   for (int d = 0; d < 3; ++d) {
-    ntile[d] = d < dim ? (n[d] + TILE3 - 1) / TILE3 : 1;
+    ntile[d] = d < dim ? (n[d] + edge - 1) / edge : 1;
     total *= ntile[d];
   }
   return total;
@@ -338,6 +341,8 @@ __global__ void __launch_bounds__(256) node_tiles_kernel(BinBuffers B) {
   }
 }
 
+__global__ void node_tiles2_kernel(BinBuffers B);   // mpm_2d.cuh
+
 __global__ void __launch_bounds__(256) bin_scatter_kernel(long long n, BinBuffers B, ErrRec* err) {
   long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
@@ -374,11 +379,10 @@ int bin_particles(const DevCfg& cfg, const StateView<T>& s, long long n, BinBuff
   // pre-bins the next substep, instead of in front of that G2P on the main stream
   bin_clear_histogram(B, st);
   active_tiles_kernel<<<(B.n_tiles + 255) / 256, 256, 0, st>>>(B);
-  if (cfg.dim == 3) {
-    cudaMemsetAsync(B.node_count, 0, sizeof(int32_t), st);
-    node_tiles_kernel<<<(B.n_node_tiles + 255) / 256, 256, 0, st>>>(B);
-    ++launches;
-  }
+  cudaMemsetAsync(B.node_count, 0, sizeof(int32_t), st);
+  if (cfg.dim == 3) node_tiles_kernel<<<(B.n_node_tiles + 255) / 256, 256, 0, st>>>(B);
+  else node_tiles2_kernel<<<(B.n_node_tiles + 255) / 256, 256, 0, st>>>(B);
+  ++launches;
   bin_scatter_kernel<<<pb, 256, 0, st>>>(n, B, err);
   return launches;
 }

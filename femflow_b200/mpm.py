@@ -120,7 +120,7 @@ class MpmSolver:
         if per_particle_material:
             self.material_layout = "planes"
         if reorder is None:
-            reorder = self.dim == 3 and p2g_mode != "scatter"
+            reorder = p2g_mode != "scatter"          # 2D and 3D: binned pipeline, G2P writes the state back cell-sorted
         self.reorder = bool(reorder)
         cfg = N.FfMpmConfig()
         cfg.dim = self.dim

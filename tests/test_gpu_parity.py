@@ -407,6 +407,50 @@ def test_multi_substep_pipelines_vs_oracle(mode):
     s.close()
 
 
+@pytest.mark.parametrize("mode", ["auto", "scatter"])
+@pytest.mark.parametrize("model", ["neo_hookean", "snow"])
+def test_2d_multi_substep_pipelines_vs_oracle(mode, model, dtype):
+    """The binned 2D pipeline (csrc/mpm_2d.cuh: cell-run P2G, reordering G2P that pre-bins the next substep, node-block
+    grid update and clear, binning on the internal stream) and the thread-per-particle one, 15 substeps in odd and even
+    chunks against the C port of two_d/{p2g,grid_op,g2p}.py; particles moving ~0.2 cells per substep, some inside the
+    wall bands of two_d/grid_op.py:18-23."""
+    from femflow_b200 import scenes
+    from femflow_b200.mpm import MpmSolver
+    from oracle import native as ON
+    sc = scenes.elastic_block(2, 128, 100, 2, seed=6)         # 100 of 128 cells: reaches into the 5 % wall bands
+    n = sc.n
+    rng = np.random.default_rng(6)
+    x, v, F, C = (a.astype(np.float64) for a in (sc.x, sc.v, sc.F, sc.C))
+    speed = 0.2 / sc.res / sc.dt
+    v = np.float32(v + speed * np.array([0.7, -1.0]) + rng.normal(0, 0.02 * speed, v.shape)).astype(np.float64)
+    Jp = np.ones((n, 1))
+    hard = 1.0 if model == "neo_hookean" else 3.0
+    s = MpmSolver(2, sc.res, sc.dt, sc.volume, sc.gravity, hard, capacity=n, mass=sc.mass, mu_0=sc.mu_0, lambda_0=sc.lambda_0,
+                  model=model, dtype=getattr(torch, dtype), p2g_mode=mode)
+    assert s.reorder == (mode == "auto")
+    s.set_particles(x, v, F, C, Jp)
+    steps = 15
+    for chunk in (1, 2, 5, 7):
+        s.substep(chunk)
+        for _ in range(chunk):
+            if model == "snow":
+                O.solve_mls_mpm_2d(sc.res, float(sc.res), hard, sc.mu_0, sc.lambda_0, sc.mass, 1 / sc.res, sc.dt, sc.volume,
+                                   sc.gravity, x, v, F, C, Jp, "snow")
+            else:
+                ON.solve_mls_mpm_2d(sc.res, float(sc.res), hard, sc.mu_0, sc.lambda_0, sc.mass, 1 / sc.res, sc.dt, sc.volume,
+                                    sc.gravity, x, v, F, C, Jp)
+    s.check_errors()
+    out = {k: t.double().cpu().numpy() for k, t in s.get_particles().items()}
+    V = max(np.abs(v).max(), sc.dt * 9.8)
+    tol = TOL[dtype] * steps
+    assert rel_err(out["x"], x, 1.0) < tol
+    assert np.abs(out["v"] - v).max() / V < tol
+    assert rel_err(out["F"], F, 1.0) < tol
+    assert np.abs(out["C"] - C).max() / (4 * sc.res * V) < tol
+    assert rel_err(out["Jp"], Jp, 1.0) < tol
+    s.close()
+
+
 @pytest.mark.parametrize("variant", [0, 1, 5])
 @pytest.mark.parametrize("n_materials", [1, 3, 300])
 def test_p2g_kernel_variants(variant, n_materials, monkeypatch):
