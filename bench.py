@@ -416,6 +416,7 @@ def main():
         n_total = n
     clocks = sampler.stop() if rank == 0 else None
     if world > 1 and args.slab_timing:
+        barrier()                        # all ranks enter the instrumented loop together (rank 0 stopped the clock sampler first)
         solver.driver.enable_timing()
         for _ in range(20):
             solver.substep(1)

@@ -391,58 +391,6 @@ FFMPM_HD void g2p_accumulate3(Fetch fetch, T fx, T fy, T fz, T& vx, T& vy, T& vz
   }
 }
 
-// The same separable sums with packed fp32 (FFMA2): a node arrives as one 16-byte vector {vx, vy, vz, m}, so
-// (vx, vy) is already an aligned register pair; the z component rides with a (weight, weight * offset) pair.
-// 147 floating-point instructions per particle instead of 279, same sums up to round-off.  `fetch` returns
-// the node as float4 (the mass lane is ignored).
-template <typename Fetch>
-FFMPM_HD void g2p_accumulate3_packed(Fetch fetch, float fx, float fy, float fz, float& vx, float& vy, float& vz, float& c00,
-                                     float& c01, float& c02, float& c10, float& c11, float& c12, float& c20, float& c21,
-                                     float& c22) {
-  float wx[3], wy[3], wz[3];
-  bspline(fx, wx[0], wx[1], wx[2]);
-  bspline(fy, wy[0], wy[1], wy[2]);
-  bspline(fz, wz[0], wz[1], wz[2]);
-  const float dz[3] = {wz[0] * (0.0f - fz), wz[1] * (1.0f - fz), wz[2] * (2.0f - fz)};
-  const float dy[3] = {wy[0] * (0.0f - fy), wy[1] * (1.0f - fy), wy[2] * (2.0f - fy)};
-  const float dxw[3] = {wx[0] * (0.0f - fx), wx[1] * (1.0f - fx), wx[2] * (2.0f - fx)};
-  const F2 wdz[3] = {f2(wz[0], dz[0]), f2(wz[1], dz[1]), f2(wz[2], dz[2])};
-  F2 vxy = f2(0.0f), ca = f2(0.0f), cb = f2(0.0f), cc = f2(0.0f), vzc = f2(0.0f);   // (c00,c10) (c01,c11) (c02,c12) (vz,c22)
-  float s20 = 0.0f, s21 = 0.0f;
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    F2 pxy = f2(0.0f), qxy = f2(0.0f), rxy = f2(0.0f), pzrz = f2(0.0f);
-    float qz = 0.0f;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      F2 txy = f2(0.0f), uxy = f2(0.0f), tuz = f2(0.0f);      // (tx,ty) (ux,uy) (tz,uz)
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const float4 g = fetch(i, j, k);
-        const F2 gxy = f2(g.x, g.y);
-        txy = f2_fma(f2(wz[k]), gxy, txy);
-        uxy = f2_fma(f2(dz[k]), gxy, uxy);
-        tuz = f2_fma(wdz[k], f2(g.z), tuz);
-      }
-      pxy = f2_fma(f2(wy[j]), txy, pxy);
-      qxy = f2_fma(f2(dy[j]), txy, qxy);
-      rxy = f2_fma(f2(wy[j]), uxy, rxy);
-      pzrz = f2_fma(f2(wy[j]), tuz, pzrz);
-      qz = fmaf(dy[j], tuz.v.x, qz);
-    }
-    vxy = f2_fma(f2(wx[i]), pxy, vxy);
-    ca = f2_fma(f2(dxw[i]), pxy, ca);
-    cb = f2_fma(f2(wx[i]), qxy, cb);
-    cc = f2_fma(f2(wx[i]), rxy, cc);
-    vzc = f2_fma(f2(wx[i]), pzrz, vzc);
-    s20 = fmaf(dxw[i], pzrz.v.x, s20);
-    s21 = fmaf(wx[i], qz, s21);
-  }
-  vx = vxy.v.x; vy = vxy.v.y; vz = vzc.v.x;
-  c00 = ca.v.x; c10 = ca.v.y; c01 = cb.v.x; c11 = cb.v.y; c02 = cc.v.x; c12 = cc.v.y;
-  c20 = s20; c21 = s21; c22 = vzc.v.y;
-}
-
 // ----------------------------------------------------------------------------
 // G2P, gather form (in place)
 // ----------------------------------------------------------------------------

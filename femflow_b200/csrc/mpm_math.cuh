@@ -306,37 +306,4 @@ FFMPM_HD Mat2<double> svd_roundtrip2(const Mat2<double>& F, bool snow, double& d
   return G;
 }
 
-// ----------------------------------------------------------------------------
-// Packed fp32: sm_100 executes fma / mul / add on two fp32 values held in an aligned register pair
-// (PTX fma.rn.f32x2 -> SASS FFMA2, FMUL2, FADD2; operands may be a broadcast scalar, an immediate, negated).
-// Two results per issue slot for the same FMA-pipe time.  Used by the G2P stencil sums (mpm_direct.cuh).  The host
-// instantiation is two plain floats (tests/test_kernel_math_host.py runs the packed code paths on CPU).
-// ----------------------------------------------------------------------------
-struct F2 {
-  float2 v;
-};
-FFMPM_HD F2 f2(float a, float b) { F2 r; r.v.x = a; r.v.y = b; return r; }
-FFMPM_HD F2 f2(float a) { return f2(a, a); }
-FFMPM_HD F2 f2_fma(F2 a, F2 b, F2 c) {
-#ifdef __CUDA_ARCH__
-  F2 r; r.v = __ffma2_rn(a.v, b.v, c.v); return r;
-#else
-  return f2(fmaf(a.v.x, b.v.x, c.v.x), fmaf(a.v.y, b.v.y, c.v.y));
-#endif
-}
-FFMPM_HD F2 f2_mul(F2 a, F2 b) {
-#ifdef __CUDA_ARCH__
-  F2 r; r.v = __fmul2_rn(a.v, b.v); return r;
-#else
-  return f2(a.v.x * b.v.x, a.v.y * b.v.y);
-#endif
-}
-FFMPM_HD F2 f2_add(F2 a, F2 b) {
-#ifdef __CUDA_ARCH__
-  F2 r; r.v = __fadd2_rn(a.v, b.v); return r;
-#else
-  return f2(a.v.x + b.v.x, a.v.y + b.v.y);
-#endif
-}
-
 }  // namespace ffmpm

@@ -50,12 +50,7 @@ __device__ __forceinline__ void cp_async4(void* sdst, const void* gsrc) {
 // ROWS: the state carries 1-byte material rows (table mode); compiled out otherwise, the kernel sits
 // exactly at its 64-register budget.
 // IDX32: exact fp32 cell indexing known at compile time (cfg.index_fp32; see base_fx).
-// CONTIG (fp32, PRE): x, v, C, F of BOTH buffers are 24 planes at one stride (MpmSolver carves them from one
-// allocation): the prefetch and the 24 stores then walk one pointer with a constant step instead of fetching a base
-// pointer per plane from the parameter bank (the source-level profile of round 2 had 35 % of the executed instructions
-// in address arithmetic and predicates around the 13 cp.async and the 24 stores); the stencil sums use packed fp32
-// (g2p_accumulate3_packed: FFMA2, ~130 fewer floating-point instructions per particle).
-template <typename T, int MIN_BLOCKS, bool PRE = false, bool ROWS = false, bool IDX32 = false, bool CONTIG = false>
+template <typename T, int MIN_BLOCKS, bool PRE = false, bool ROWS = false, bool IDX32 = false>
 __global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_tiled3_kernel(DevCfg cfg, StateView<T> src, StateView<T> dst,
                                                                  BinBuffers B, const T* __restrict__ grid, ErrRec* err) {
   using V4 = typename Vec4<T>::type;
@@ -108,19 +103,10 @@ __global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_tiled3_kernel(Dev
       if constexpr (PRE) {
         if (q >= 0) {
           const int tid = threadIdx.x;
-          if constexpr (CONTIG) {
-            const T* sp = src.x + q;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) { cp_async4(&pre[buf][c][tid], sp); sp += ss; }
-            sp += 12 * ss;                                   // over v (3 planes) and C (9 planes) to F
-#pragma unroll
-            for (int c = 0; c < 9; ++c) { cp_async4(&pre[buf][3 + c][tid], sp); sp += ss; }
-          } else {
 #pragma unroll
           for (int c = 0; c < 3; ++c) cp_async4(&pre[buf][c][tid], src.x + c * ss + q);
 #pragma unroll
           for (int c = 0; c < 9; ++c) cp_async4(&pre[buf][3 + c][tid], src.F + c * ss + q);
-          }
           if (src.mass) cp_async4(&pre[buf][12][tid], src.mass + q);
           if (src.mu0) cp_async4(&pre[buf][13][tid], src.mu0 + q);
           if (src.lam0) cp_async4(&pre[buf][14][tid], src.lam0 + q);
@@ -205,12 +191,8 @@ __global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_tiled3_kernel(Dev
         }
         const int cb = ((gx - cfg.origin[0] - ox) * TN3 + (gy - cfg.origin[1] - oy)) * TN3 + (gz - cfg.origin[2] - oz);
         T vx, vy, vz, c00, c01, c02, c10, c11, c12, c20, c21, c22;
-        if constexpr (CONTIG && sizeof(T) == 4)
-          g2p_accumulate3_packed([&](int i, int j, int k) { return tile[cb + (i * TN3 + j) * TN3 + k]; }, fx, fy, fz,
-                                 vx, vy, vz, c00, c01, c02, c10, c11, c12, c20, c21, c22);
-        else
-          g2p_accumulate3<T>([&](int i, int j, int k) { return tile[cb + (i * TN3 + j) * TN3 + k]; }, fx, fy, fz,
-                             vx, vy, vz, c00, c01, c02, c10, c11, c12, c20, c21, c22);
+        g2p_accumulate3<T>([&](int i, int j, int k) { return tile[cb + (i * TN3 + j) * TN3 + k]; }, fx, fy, fz,
+                           vx, vy, vz, c00, c01, c02, c10, c11, c12, c20, c21, c22);
         const T s4 = (T)(4.0 * cfg.inv_dx);
         c00 *= s4; c01 *= s4; c02 *= s4; c10 *= s4; c11 *= s4; c12 *= s4; c20 *= s4; c21 *= s4; c22 *= s4;
         const T dt = (T)cfg.dt;
@@ -245,16 +227,10 @@ __global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_tiled3_kernel(Dev
       }
       {
         if (mine) {
-          if constexpr (CONTIG) {
-            T* dp = dst.x + slot;                       // planes x3 v3 C9 F9 back to back: o[] is in that order
-#pragma unroll
-            for (int k = 0; k < 24; ++k) { *dp = o[k]; dp += ds; }
-          } else {
 #pragma unroll
           for (int k = 0; k < 3; ++k) { dst.x[k * ds + slot] = o[k]; dst.v[k * ds + slot] = o[3 + k]; }
 #pragma unroll
           for (int k = 0; k < 9; ++k) { dst.C[k * ds + slot] = o[6 + k]; dst.F[k * ds + slot] = o[15 + k]; }
-          }
           if (src.mass) dst.mass[slot] = cm;
           if (src.mu0) dst.mu0[slot] = cmu;
           if (src.lam0) dst.lam0[slot] = cl;
@@ -283,16 +259,10 @@ int g2p_tiled(const DevCfg& cfg, const StateView<T>& src, const StateView<T>& ds
     static int prefetch = [] { const char* e = getenv("FFMPM_G2P_PRE"); return e ? atoi(e) : 1; }();
     const bool rows = src.material != nullptr;
     const bool i32 = cfg.index_fp32 != 0;
-    // FFMPM_G2P_MINB=7: the contiguous / packed kernel at 7 CTAs per SM (73 registers, no spills) instead of 8 (64, 60 B spilled)
-    static int minb = [] { const char* e = getenv("FFMPM_G2P_MINB"); return e ? atoi(e) : 8; }();
-    auto contiguous = [](const StateView<T>& v) { const long long st = v.stride; return v.v == v.x + 3 * st && v.C == v.v + 3 * st && v.F == v.C + 9 * st; };
-    const bool contig = contiguous(src) && contiguous(dst) && prefetch;
-#define FFMPM_G2P(PRE_, ROWS_)                                                                                               \
-  do {                                                                                                                       \
-    if (i32 && contig && minb == 7) g2p_tiled3_kernel<T, 7, PRE_, ROWS_, true, PRE_><<<min(blocks, sm_count * 7), G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err); \
-    else if (i32 && contig) g2p_tiled3_kernel<T, 8, PRE_, ROWS_, true, PRE_><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err); \
-    else if (i32) g2p_tiled3_kernel<T, 8, PRE_, ROWS_, true, false><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);    \
-    else g2p_tiled3_kernel<T, 8, PRE_, ROWS_, false, false><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);            \
+#define FFMPM_G2P(PRE_, ROWS_)                                                                                          \
+  do {                                                                                                                  \
+    if (i32) g2p_tiled3_kernel<T, 8, PRE_, ROWS_, true><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);   \
+    else g2p_tiled3_kernel<T, 8, PRE_, ROWS_, false><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);      \
   } while (0)
     if (prefetch && rows) FFMPM_G2P(true, true);
     else if (prefetch) FFMPM_G2P(true, false);

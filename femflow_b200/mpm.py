@@ -120,7 +120,10 @@ class MpmSolver:
         if per_particle_material:
             self.material_layout = "planes"
         if reorder is None:
-            reorder = p2g_mode != "scatter"          # 2D and 3D: binned pipeline, G2P writes the state back cell-sorted
+            # 3D: binned pipeline, G2P writes the state back cell-sorted.  2D (1 M particles, state resident in L2) is
+            # fastest unbinned (measured: profiles/r02e_g2p_packed_and_binned_2d_ab.json); the binned 2D pipeline stays
+            # selectable with reorder=True
+            reorder = self.dim == 3 and p2g_mode != "scatter"
         self.reorder = bool(reorder)
         cfg = N.FfMpmConfig()
         cfg.dim = self.dim

@@ -110,17 +110,6 @@ void km_prepare3_f64(int res, int n_nodes, double inv_dx, double dx, double dt, 
 }
 
 void km_g2p_accumulate3_f32(long long n, const float* f, const float* gv, float* v, float* c) { accumulate3<float>(n, f, gv, v, c); }
-void km_g2p_accumulate3_packed(long long n, const float* f, const float* gv, float* v, float* c) {
-  for (long long p = 0; p < n; ++p) {
-    const float* g = gv + 81 * p;
-    float o[12];
-    g2p_accumulate3_packed([&](int i, int j, int k) { const float* q = g + ((i * 3 + j) * 3 + k) * 3; return make_float4(q[0], q[1], q[2], 7.0f); },
-                           f[3 * p], f[3 * p + 1], f[3 * p + 2], o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7], o[8], o[9], o[10],
-                           o[11]);
-    for (int e = 0; e < 3; ++e) v[3 * p + e] = o[e];
-    for (int e = 0; e < 9; ++e) c[9 * p + e] = o[3 + e];
-  }
-}
 void km_g2p_accumulate3_f64(long long n, const double* f, const double* gv, double* v, double* c) { accumulate3<double>(n, f, gv, v, c); }
 
 // 1 when the fp32 perturbation series accepted the strain (else the caller's fp64 path would run)

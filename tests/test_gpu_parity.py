@@ -407,9 +407,9 @@ def test_multi_substep_pipelines_vs_oracle(mode):
     s.close()
 
 
-@pytest.mark.parametrize("mode", ["auto", "scatter"])
+@pytest.mark.parametrize("pipeline", ["binned", "direct"])
 @pytest.mark.parametrize("model", ["neo_hookean", "snow"])
-def test_2d_multi_substep_pipelines_vs_oracle(mode, model, dtype):
+def test_2d_multi_substep_pipelines_vs_oracle(pipeline, model, dtype):
     """The binned 2D pipeline (csrc/mpm_2d.cuh: cell-run P2G, reordering G2P that pre-bins the next substep, node-block
     grid update and clear, binning on the internal stream) and the thread-per-particle one, 15 substeps in odd and even
     chunks against the C port of two_d/{p2g,grid_op,g2p}.py; particles moving ~0.2 cells per substep, some inside the
@@ -426,8 +426,8 @@ def test_2d_multi_substep_pipelines_vs_oracle(mode, model, dtype):
     Jp = np.ones((n, 1))
     hard = 1.0 if model == "neo_hookean" else 3.0
     s = MpmSolver(2, sc.res, sc.dt, sc.volume, sc.gravity, hard, capacity=n, mass=sc.mass, mu_0=sc.mu_0, lambda_0=sc.lambda_0,
-                  model=model, dtype=getattr(torch, dtype), p2g_mode=mode)
-    assert s.reorder == (mode == "auto")
+                  model=model, dtype=getattr(torch, dtype), reorder=(pipeline == "binned"))
+    assert s.reorder == (pipeline == "binned")
     s.set_particles(x, v, F, C, Jp)
     steps = 15
     for chunk in (1, 2, 5, 7):

@@ -140,7 +140,7 @@ def test_c2_1m_substep_matches_port():
     Jp = np.ones((n, 1))
     dx = 1.0 / res
     s = MpmSolver(2, res, sc.dt, sc.volume, sc.gravity, sc.hardening, capacity=n, mass=sc.mass, mu_0=sc.mu_0,
-                  lambda_0=sc.lambda_0)
+                  lambda_0=sc.lambda_0)                       # the 2D default: thread-per-particle kernels (what bench.py times)
     s.set_particles(sc.x, sc.v, sc.F, sc.C)
 
     s.clear_grid(); s.bin()

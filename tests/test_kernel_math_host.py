@@ -188,10 +188,10 @@ def test_p2g_payload_and_oob_flag(km):
     assert np.abs(aff_s[3:] - want_s).max() / np.abs(want_s).max() < 1e-12
 
 
-@pytest.mark.parametrize("dtype,tol", [("f32", 2e-6), ("f64", 1e-14), ("packed", 2e-6)])
+@pytest.mark.parametrize("dtype,tol", [("f32", 2e-6), ("f64", 1e-14)])
 def test_separable_g2p_stencil_sums(km, dtype, tol):
     """v = sum w gv, C = sum (w gv) (x) dpos (three_d/g2p.py:31-43) folded z -> y -> x against the
-    node-by-node sums of the reference; "packed" is the FFMA2 form the production G2P uses (g2p_accumulate3_packed)."""
+    node-by-node sums of the reference."""
     rng = np.random.default_rng(8)
     n = 2000
     np_dt = np.float64 if dtype == "f64" else np.float32
