@@ -363,8 +363,9 @@ def main():
     if rank == 0:
         sampler.start()
     graph = None
-    if scene.dim == 2 and world == 1 and args.steps % 10 == 0:
-        args.graph = True      # a 2D substep is a few tens of microseconds of kernels: replayed as CUDA graphs by default
+    # 2D: ffmpm_substep(n) runs n substeps as ONE persistent cooperative kernel (csrc/mpm_2d.cuh); the timed loop hands it
+    # 10 substeps per call (FFMPM_FUSE2D=0 restores the separate kernels, --graph replays those as CUDA graphs)
+    fused2d = scene.dim == 2 and world == 1 and os.environ.get("FFMPM_FUSE2D", "1") != "0" and not args.graph and args.steps % 10 == 0
     if args.graph and world == 1 and not dam and args.steps % 10 == 0:
         graph = solver.make_graph(10)         # captured from the warmed-up (pre-binned) state; does not execute
     l0 = solver.launch_count()
@@ -374,6 +375,10 @@ def main():
     if graph is not None:
         for _ in range(args.steps // 10):
             graph.replay()
+    elif fused2d:
+        for _ in range(args.steps // 10):
+            solver.substep(10)
+        marks = []
     else:
         # SURVEY 8d asks for the spread as well: an event every fifth of the region (recording one costs nothing
         # on the stream) gives five per-substep samples next to the total
@@ -389,7 +394,7 @@ def main():
     barrier()
     ms = ev0.elapsed_time(ev1)
     samples = []
-    if graph is None:
+    if graph is None and not fused2d:
         try:
             prev_k, prev_ev = 0, ev0
             for k_done, ev in marks + [(args.steps, ev1)]:
@@ -597,6 +602,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": scene.name, "particles_per_gpu": n, "particles_total": n_total,
                    "grid": f"{scene.res}^{scene.dim}", "dt": scene.dt, "p2g_mode": args.p2g_mode, "cuda_graph": bool(args.graph and world == 1 and not dam and args.steps % 10 == 0),
+                   **({"substeps_per_launch": 10 if fused2d else 1} if scene.dim == 2 else {}),
                    **({"presteps": args.presteps} if dam else {}),
                    "l2": ("inputs larger than L2 (no flush)" if n * (112 if scene.dim == 3 else 52) > 2 * 126e6
                           else "particle state fits in the 126 MB L2 (flagged: HBM fraction is not meaningful)"),

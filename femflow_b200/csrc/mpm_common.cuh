@@ -115,4 +115,13 @@ __device__ __forceinline__ double4 ld_node(const double* g) {
   return make_double4(a.x, a.y, b.x, b.y);
 }
 
+// The same loads through L2 only (ld.global.cg): for grids that were written earlier IN THE SAME KERNEL by other
+// SMs (the persistent 2D substep loop) -- the read-only / L1 paths may serve lines cached before those writes.
+__device__ __forceinline__ float4 ld_node_cg(const float* g) { return __ldcg(reinterpret_cast<const float4*>(g)); }
+__device__ __forceinline__ double4 ld_node_cg(const double* g) {
+  double2 a = __ldcg(reinterpret_cast<const double2*>(g));
+  double2 b = __ldcg(reinterpret_cast<const double2*>(g) + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
+}
+
 }  // namespace ffmpm
