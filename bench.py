@@ -349,6 +349,12 @@ def main():
             if world > 1 and args.rebalance and args.rebalance_every and (k + 1) % args.rebalance_every == 0:
                 solver.rebalance()
         if solver.poll_error():
+            core_ = solver.local.solver
+            xs = core_.live.x[:, :core_.num_particles]
+            print(f"[rank {rank}] pre-steps left particles outside the LOCAL grid: n = {core_.num_particles}, x range "
+                  f"{[(float(xs[c].min()), float(xs[c].max())) for c in range(3)]}, local node planes "
+                  f"[{solver.plan.g_lo}, {solver.plan.g_hi}), owned cells [{solver.plan.own_lo}, {solver.plan.own_hi}), "
+                  f"non-finite: {int((~torch.isfinite(xs)).sum())}", file=sys.stderr, flush=True)
             raise SystemExit("pre-steps left particles outside the grid")
 
     # ---- warm-up ----

@@ -146,7 +146,7 @@ __device__ __forceinline__ void g2p_particle2(const DevCfg& cfg, const T* __rest
     for (int j = 0; j < 3; ++j) {
       const T dpy = (T)j - fy;
       const T w = wx[i] * wy[j];
-      const auto g = CG ? ld_node_cg(row + 4 * j) : ld_node(row + 4 * j);
+      const auto g = CG ? ld_node_coherent(row + 4 * j) : ld_node(row + 4 * j);
       const T ux = w * g.x, uy = w * g.y;
       vx += ux; vy += uy;
       c00 += ux * dpx; c01 += ux * dpy; c10 += uy * dpx; c11 += uy * dpy;
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(256) node_tiles2_kernel(BinBuffers B) {
 template <typename T, bool CG = false>
 __device__ __forceinline__ void grid_op2_node(const DevCfg& cfg, T* __restrict__ grid, long long node, int i, int j) {
   using V4 = typename Vec4<T>::type;
-  V4 g = CG ? ld_node_cg(grid + 4 * node) : reinterpret_cast<V4*>(grid)[node];
+  V4 g = CG ? ld_node_coherent(grid + 4 * node) : reinterpret_cast<V4*>(grid)[node];
   if (!(g.z > (T)0)) return;
   T vx = g.x / g.z, vy = g.y / g.z;
   vy += (T)(cfg.dt * cfg.gravity);
