@@ -305,11 +305,13 @@ def main():
     if dam:
         # BASELINE configs[4] (report only): --workload dam32m, or dam:<n_total> for smaller runs
         from femflow_b200.distributed import SlabSolver
-        n_total_req = 33_554_432 if args.workload == "dam32m" else int(args.workload.split(":")[1])
+        late = args.workload.endswith("-late")           # dam32m-late / dam:<n>-late: the settled state as initial condition
+        wl = args.workload[:-5] if late else args.workload
+        n_total_req = 33_554_432 if wl == "dam32m" else int(wl.split(":")[1])
         if world == 1:
             import torch.distributed as dist_  # noqa: F401  (single rank: the driver never communicates)
         solver = SlabSolver.from_dam_break(rank, world, dev, n_total=n_total_req, margin=args.margin,
-                                           p2g_mode=args.p2g_mode, halo=args.halo)
+                                           p2g_mode=args.p2g_mode, halo=args.halo, late=late)
         scene.name = solver.scene_name
         scene.dt = solver.local.solver.cfg.dt
         if args.rebalance and world > 1:
@@ -369,9 +371,8 @@ def main():
     if rank == 0:
         sampler.start()
     graph = None
-    # 2D: ffmpm_substep(n) runs n substeps as ONE persistent cooperative kernel (csrc/mpm_2d.cuh); the timed loop hands it
-    # 10 substeps per call (FFMPM_FUSE2D=0 restores the separate kernels, --graph replays those as CUDA graphs)
-    fused2d = scene.dim == 2 and world == 1 and os.environ.get("FFMPM_FUSE2D", "1") != "0" and not args.graph and args.steps % 10 == 0
+    if scene.dim == 2 and world == 1 and args.steps % 10 == 0:
+        args.graph = True      # a 2D substep is four kernels of ~15 us: replayed as CUDA graphs by default (-11 %)
     if args.graph and world == 1 and not dam and args.steps % 10 == 0:
         graph = solver.make_graph(10)         # captured from the warmed-up (pre-binned) state; does not execute
     l0 = solver.launch_count()
@@ -381,10 +382,6 @@ def main():
     if graph is not None:
         for _ in range(args.steps // 10):
             graph.replay()
-    elif fused2d:
-        for _ in range(args.steps // 10):
-            solver.substep(10)
-        marks = []
     else:
         # SURVEY 8d asks for the spread as well: an event every fifth of the region (recording one costs nothing
         # on the stream) gives five per-substep samples next to the total
@@ -400,7 +397,7 @@ def main():
     barrier()
     ms = ev0.elapsed_time(ev1)
     samples = []
-    if graph is None and not fused2d:
+    if graph is None:
         try:
             prev_k, prev_ev = 0, ev0
             for k_done, ev in marks + [(args.steps, ev1)]:
@@ -608,7 +605,6 @@ def main():
         "data": "synthetic",
         "config": {"workload": scene.name, "particles_per_gpu": n, "particles_total": n_total,
                    "grid": f"{scene.res}^{scene.dim}", "dt": scene.dt, "p2g_mode": args.p2g_mode, "cuda_graph": bool(args.graph and world == 1 and not dam and args.steps % 10 == 0),
-                   **({"substeps_per_launch": 10 if fused2d else 1} if scene.dim == 2 else {}),
                    **({"presteps": args.presteps} if dam else {}),
                    "l2": ("inputs larger than L2 (no flush)" if n * (112 if scene.dim == 3 else 52) > 2 * 126e6
                           else "particle state fits in the 126 MB L2 (flagged: HBM fraction is not meaningful)"),

@@ -1,21 +1,19 @@
-// 2D kernels beyond the thread-per-particle ones of mpm_direct.cuh (BASELINE configs[1]: 1 M particles on 1024^2, a
-// state that lives in L2 and a substep of a few tens of microseconds):
-//   * substep2_fused_kernel (bottom of this file): the whole substep loop as ONE persistent cooperative kernel --
-//     the 2D default (ffmpm_substep, unbinned state);
-//   * a binned pipeline with the architecture of the 3D one, selectable with reorder=True (measured SLOWER than the
-//     direct kernels at 1 M particles -- profiles/r02e_g2p_packed_and_binned_2d_ab.json -- and kept for scenes whose
-//     state does not fit L2):
-//       p2g_runs2_kernel     warp-autonomous P2G in physical order (two_d/p2g.py:49-76): lane per particle -> runs of
-//                            equal base cell -> lane per (run, x-slab) accumulating the slab's three nodes in registers
-//                            -> ONE vector RED per node and run;
-//       g2p_reorder2_kernel  thread per binned slot (two_d/g2p.py:17-47 incl. the SVD round trip and Jp): gathers its
-//                            particle through `perm`, reads the 9 nodes straight from the grid, writes the new state in
-//                            cell order into the other buffer and emits the next substep's key, rank and histogram;
-//       node_tiles2 / grid_op2_blocks / grid_clear_blocks2   grid update and clear over the 8x8-node blocks the binned
-//                            particles can have written.
+// The binned 2D pipeline: the architecture of the 3D one for two_d/{p2g,grid_op,g2p}.py, selectable with
+// MpmSolver(reorder=True).  At BASELINE configs[1] (1 M particles on 1024^2: 54 MB of state, resident in L2) it is SLOWER
+// than the thread-per-particle kernels of mpm_direct.cuh (88.7 us against 62.6 us per substep under CUDA-graph replay,
+// profiles/r02e_g2p_packed_and_binned_2d_ab.json), so those stay the 2D default; this path is for scenes whose state
+// does not fit L2.
+//   p2g_runs2_kernel     warp-autonomous P2G in physical order (two_d/p2g.py:49-76): lane per particle -> runs of equal
+//                        base cell -> lane per (run, x-slab) accumulating the slab's three nodes in registers -> ONE
+//                        vector RED per node and run;
+//   g2p_reorder2_kernel  thread per binned slot (two_d/g2p.py:17-47 incl. the SVD round trip and Jp): gathers its
+//                        particle through `perm`, reads the 9 nodes straight from the grid, writes the new state in cell
+//                        order into the other buffer and emits the next substep's key, rank and histogram;
+//   node_tiles2 / grid_op2_blocks / grid_clear_blocks2   grid update and clear over the 8x8-node blocks the binned
+//                        particles can have written.
+// (Also measured and removed, profiles/r02g / r02h: the whole 2D substep loop as ONE persistent cooperative kernel with
+// three grid-wide barriers per substep -- 79-81 us per substep, slower than the four separate kernels.)
 #pragma once
-#include <cooperative_groups.h>
-
 #include "mpm_bin.cuh"
 #include "mpm_common.cuh"
 #include "mpm_direct.cuh"
@@ -130,7 +128,7 @@ struct G2POut2 {
   T x0, x1, v0, v1, c00, c01, c10, c11, f00, f01, f10, f11, jp;
 };
 
-template <typename T, bool CG = false>
+template <typename T>
 __device__ __forceinline__ void g2p_particle2(const DevCfg& cfg, const T* __restrict__ grid, int bx, int by, T fx, T fy, T x0, T x1,
                                               T f00, T f01, T f10, T f11, T jp_in, bool has_jp, G2POut2<T>& o) {
   T wx[3], wy[3];
@@ -146,7 +144,7 @@ __device__ __forceinline__ void g2p_particle2(const DevCfg& cfg, const T* __rest
     for (int j = 0; j < 3; ++j) {
       const T dpy = (T)j - fy;
       const T w = wx[i] * wy[j];
-      const auto g = CG ? ld_node_coherent(row + 4 * j) : ld_node(row + 4 * j);
+      const auto g = ld_node(row + 4 * j);
       const T ux = w * g.x, uy = w * g.y;
       vx += ux; vy += uy;
       c00 += ux * dpx; c01 += ux * dpy; c10 += uy * dpx; c11 += uy * dpy;
@@ -247,10 +245,10 @@ __global__ void __launch_bounds__(256) node_tiles2_kernel(BinBuffers B) {
 }
 
 // two_d/grid_op.py:13-24 on one node; the walls are f64 predicates on i/R (quirk 6).
-template <typename T, bool CG = false>
+template <typename T>
 __device__ __forceinline__ void grid_op2_node(const DevCfg& cfg, T* __restrict__ grid, long long node, int i, int j) {
   using V4 = typename Vec4<T>::type;
-  V4 g = CG ? ld_node_coherent(grid + 4 * node) : reinterpret_cast<V4*>(grid)[node];
+  V4 g = reinterpret_cast<V4*>(grid)[node];
   if (!(g.z > (T)0)) return;
   T vx = g.x / g.z, vy = g.y / g.z;
   vy += (T)(cfg.dt * cfg.gravity);
@@ -290,105 +288,6 @@ __global__ void __launch_bounds__(256) grid_clear_blocks2_kernel(DevCfg cfg, T* 
     const int i = (t / nt1) * NODE_TILE2 + di, j = (t % nt1) * NODE_TILE2 + dj;
     if (i < cfg.n[0] && j < cfg.n[1]) reinterpret_cast<V4*>(grid)[(long long)i * cfg.n[1] + j] = z;
   }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// The whole 2D substep loop as ONE persistent cooperative kernel.
-//
-// At 1 M particles a 2D substep is ~25 us of work spread over four launches: what the separate kernels leave on the
-// table is launch gaps and ramp-up / tail of every kernel (70 us per substep eager, 63 us replayed as a CUDA graph).
-// Here one co-resident grid of CTAs runs  P2G -> grid update -> G2P (+ clear of the other grid)  for `n_substeps`
-// substeps with three grid-wide barriers per substep and no launch in between; the particle state (54 MB) and both
-// grids stay in L2 throughout.  Same per-particle / per-node device functions as the stand-alone kernels
-// (p2g_prepare2, grid_op2_node, g2p_particle2), so the results differ only by the order of the atomic sums.
-// Two grids ping-pong: substep k scatters into G[cur], and clears G[cur ^ 1] (substep k-1's) while it gathers.
-// ---------------------------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(256) substep2_fused_kernel(DevCfg cfg, StateView<T> s, long long n, T* __restrict__ grid_a,
-                                                             T* __restrict__ grid_b, long long n_nodes, ErrRec* err, int n_substeps) {
-  namespace cg = cooperative_groups;
-  cg::grid_group gg = cg::this_grid();
-  using V4 = typename Vec4<T>::type;
-  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long nthreads = (long long)gridDim.x * blockDim.x;
-  const long long st = s.stride;
-  const T dx = (T)cfg.dx;
-  const long long ny = cfg.n[1];
-  T* cur = grid_a;
-  T* other = grid_b;
-  for (int it = 0; it < n_substeps; ++it) {
-    // ---- P2G (two_d/p2g.py:49-76) into `cur`, which is all zero ----
-    for (long long p = tid; p < n; p += nthreads) {
-      const P2GParticle2<T> q = p2g_prepare2(cfg, s, p);
-      if (!q.ok) { atomicAdd(&err->n_oob, 1ULL); continue; }
-      T wx[3], wy[3];
-      bspline(q.fx, wx[0], wx[1], wx[2]);
-      bspline(q.fy, wy[0], wy[1], wy[2]);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const T dpx = ((T)i - q.fx) * dx;
-        T* row = cur + ((long long)(q.bx + i) * ny + q.by) * 4;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const T dpy = ((T)j - q.fy) * dx;
-          const T w = wx[i] * wy[j];
-          red_add4(row + 4 * j, w * (q.mvx + (q.a00 * dpx + q.a01 * dpy)), w * (q.mvy + (q.a10 * dpx + q.a11 * dpy)), w * q.m, (T)0);
-        }
-      }
-    }
-    gg.sync();
-    // ---- grid update (two_d/grid_op.py:13-24) ----
-    for (long long node = tid; node < n_nodes; node += nthreads) grid_op2_node<T, true>(cfg, cur, node, (int)(node / ny), (int)(node % ny));
-    gg.sync();
-    // ---- G2P (two_d/g2p.py:17-47), in place; and the other grid is cleared for the next substep ----
-    for (long long p = tid; p < n; p += nthreads) {
-      const T x0 = s.x[p], x1 = s.x[st + p];
-      int gx, gy;
-      T fx, fy;
-      base_fx(x0, cfg, gx, fx);
-      base_fx(x1, cfg, gy, fy);
-      const int bx = gx - cfg.origin[0], by = gy - cfg.origin[1];
-      const bool ok = x0 == x0 && x1 == x1 && bx >= 0 && by >= 0 && bx + 2 < cfg.n[0] && by + 2 < cfg.n[1];
-      if (!ok) { atomicAdd(&err->n_oob, 1ULL); continue; }
-      G2POut2<T> o;
-      g2p_particle2<T, true>(cfg, cur, bx, by, fx, fy, x0, x1, s.F[p], s.F[st + p], s.F[2 * st + p], s.F[3 * st + p],
-                             s.Jp ? s.Jp[p] : (T)1, s.Jp != nullptr, o);
-      s.x[p] = o.x0; s.x[st + p] = o.x1;
-      s.v[p] = o.v0; s.v[st + p] = o.v1;
-      s.C[p] = o.c00; s.C[st + p] = o.c01; s.C[2 * st + p] = o.c10; s.C[3 * st + p] = o.c11;
-      s.F[p] = o.f00; s.F[st + p] = o.f01; s.F[2 * st + p] = o.f10; s.F[3 * st + p] = o.f11;
-      if (s.Jp) s.Jp[p] = o.jp;
-    }
-    {
-      V4 z;
-      z.x = z.y = z.z = z.w = (T)0;
-      for (long long node = tid; node < n_nodes; node += nthreads) reinterpret_cast<V4*>(other)[node] = z;
-    }
-    gg.sync();
-    T* t = cur; cur = other; other = t;
-  }
-}
-
-// Launches the fused loop; returns false when the device cannot co-schedule it (the caller falls back to the
-// separate kernels).  `blocks_per_sm` is filled once per device from the occupancy calculator.
-template <typename T>
-static bool substep2_fused_launch(const DevCfg& cfg, const StateView<T>& s, long long n, T* grid_cur, T* grid_other, long long n_nodes,
-                                  ErrRec* err, int n_substeps, int sm_count, cudaStream_t st) {
-  static int bps[64] = {};
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
-  if (bps[dev] == 0) {
-    int coop = 0, occ = 0;
-    if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !coop) { bps[dev] = -1; return false; }
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, substep2_fused_kernel<T>, 256, 0) != cudaSuccess || occ < 1) { bps[dev] = -1; return false; }
-    bps[dev] = occ > 4 ? 4 : occ;      // 4 x 256 threads per SM already cover the latency; more CTAs only make the barriers dearer
-    if (const char* e = getenv("FFMPM_FUSE2D_BPS")) { const int v = atoi(e); if (v >= 1 && v <= occ) bps[dev] = v; }
-  }
-  if (bps[dev] < 0) return false;
-  DevCfg c = cfg;
-  StateView<T> sv = s;
-  void* args[] = {&c, &sv, &n, &grid_cur, &grid_other, &n_nodes, &err, &n_substeps};
-  return cudaLaunchCooperativeKernel((const void*)substep2_fused_kernel<T>, dim3(sm_count * bps[dev]), dim3(256), args, 0, st) == cudaSuccess;
 }
 
 }  // namespace ffmpm

@@ -52,7 +52,6 @@ struct FfMpmHandle {
   int grid_cur;
   bool grid_clean[2];  // known to be all-zero
   bool scatter_ahead;  // grids[grid_cur ^ 1] already holds P2G of the live state (fused G2P2G)
-  int fuse2d;          // 2D: the whole substep loop as one cooperative kernel (FFMPM_FUSE2D=0: separate kernels)
   int fuse;            // FFMPM_FUSE=0 disables the fused G2P2G kernel
   int gg_blocks_per_sm;
   bool bin_pending;    // the binning of this substep is in flight on `aux` (ev_join)
@@ -167,8 +166,6 @@ int ffmpm_create(const FfMpmConfig* cfg, int32_t device, FfMpmHandle** out) {
   // separate kernels whose binning/clear additionally hide under P2G, so it is not the default.
   h->fuse = cfg->p2g_mode == FFMPM_P2G_FUSED ? 1 : 0;
   if (const char* e = getenv("FFMPM_FUSE")) h->fuse = atoi(e) != 0;
-  h->fuse2d = 1;
-  if (const char* e = getenv("FFMPM_FUSE2D")) h->fuse2d = atoi(e) != 0;
   h->gg_blocks_per_sm = 4;
   if (const char* e = getenv("FFMPM_GG_BPS")) { int v = atoi(e); if (v > 0 && v <= 32) h->gg_blocks_per_sm = v; }
   {
@@ -625,41 +622,9 @@ int ffmpm_gather(FfMpmHandle* h, void* stream) {
   return ffmpm_g2p(h, stream);
 }
 
-// 2D, unbinned state: all n_substeps in ONE cooperative launch (mpm_2d.cuh: substep2_fused_kernel).
-template <typename T>
-static int substep2_fused_t(FfMpmHandle* h, int n_substeps, cudaStream_t s) {
-  if (!h->grid_clean[h->grid_cur] && h->grid_clean[h->grid_cur ^ 1]) {
-    h->grid_cur ^= 1;
-    h->grid = h->grids[h->grid_cur];
-  }
-  int rc;
-  if (!h->grid_clean[h->grid_cur] && (rc = ffmpm_clear_grid(h, (void*)s))) return rc;
-  StateView<T> sv = view<T>(h, h->st[h->live]);
-  if (!substep2_fused_launch<T>(h->dev, sv, h->n, (T*)h->grids[h->grid_cur], (T*)h->grids[h->grid_cur ^ 1], h->n_nodes, h->err,
-                                n_substeps, h->sm_count, s))
-    return FFMPM_E_STATE;      // not co-schedulable here: the caller runs the separate kernels
-  // the loop ends with velocities in the grid of its last substep and the other one cleared
-  const int last = (h->grid_cur + n_substeps - 1) & 1;
-  h->grid_cur = last;
-  h->grid = h->grids[last];
-  h->grid_clean[last] = false;
-  h->grid_clean[last ^ 1] = true;
-  h->grid_listed[0] = h->grid_listed[1] = false;
-  h->grid_in_blocks = false;
-  h->binned = false;
-  h->prebinned = false;
-  return check_launch(h, 1);
-}
-
 int ffmpm_substep(FfMpmHandle* h, int32_t n_substeps, void* stream) {
   int rc = ready(h);
   if (rc) return rc;
-  if (h->cfg.dim == 2 && h->fuse2d && !binned_pipeline(h) && h->n > 0 && n_substeps > 0) {
-    rc = h->cfg.dtype == FFMPM_F64 ? substep2_fused_t<double>(h, n_substeps, (cudaStream_t)stream)
-                                   : substep2_fused_t<float>(h, n_substeps, (cudaStream_t)stream);
-    if (rc != FFMPM_E_STATE) return rc;
-    h->fuse2d = 0;             // cooperative launch unavailable: separate kernels from now on
-  }
   for (int32_t it = 0; it < n_substeps; ++it) {
     if ((rc = ffmpm_scatter(h, stream))) return rc;
     if ((rc = ffmpm_grid_op(h, stream))) return rc;

@@ -115,16 +115,4 @@ __device__ __forceinline__ double4 ld_node(const double* g) {
   return make_double4(a.x, a.y, b.x, b.y);
 }
 
-// The same loads on the coherent path (ld.global.ca, never the read-only ld.global.nc that __ldg selects): for grids
-// that were written earlier IN THE SAME KERNEL by other SMs (the persistent 2D substep loop).  The grid-wide barrier
-// between the phases is an acquire fence, after which L1 holds no stale lines for these loads -- the non-coherent
-// path gives no such guarantee.  (A first version went through L2 only, ld.global.cg: correct, but it gives up the
-// L1 hits neighbouring particles get on their shared nodes -- 80 us per substep against 63 us for the separate kernels.)
-__device__ __forceinline__ float4 ld_node_coherent(const float* g) { return __ldca(reinterpret_cast<const float4*>(g)); }
-__device__ __forceinline__ double4 ld_node_coherent(const double* g) {
-  double2 a = __ldca(reinterpret_cast<const double2*>(g));
-  double2 b = __ldca(reinterpret_cast<const double2*>(g) + 1);
-  return make_double4(a.x, a.y, b.x, b.y);
-}
-
 }  // namespace ffmpm

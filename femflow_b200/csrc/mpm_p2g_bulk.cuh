@@ -86,12 +86,20 @@ __device__ __forceinline__ void p2g_runs_phase2_adjacent(P2GWarpSlab<float>& S, 
                                                          int ny, int nz, float* __restrict__ grid) {
   int prev0 = __shfl_up_sync(0xffffffffu, node[1], 1);
   if (lane == 0) prev0 = -2;
-  const unsigned h0 = __ballot_sync(0xffffffffu, 2 * lane < cnt && node[0] != prev0);
-  const unsigned h1 = __ballot_sync(0xffffffffu, 2 * lane + 1 < cnt && node[1] != node[0]);
+  unsigned h0 = __ballot_sync(0xffffffffu, 2 * lane < cnt && node[0] != prev0);
+  unsigned h1 = __ballot_sync(0xffffffffu, 2 * lane + 1 < cnt && node[1] != node[0]);
+  int n_runs = __popc(h0) + __popc(h1);
+  // dense cells (a settled column: tens of particles per cell): a window holds two or three long runs and most lanes
+  // of phase 2 would idle.  Cut the runs every 8 / 16 slots as well: up to 10 (run, slab) triples, at the price of one
+  // more set of REDs per cut.
+  const int cut = n_runs <= 2 ? 8 : (n_runs <= 5 ? 16 : 0);
+  if (cut) {
+    h0 = __ballot_sync(0xffffffffu, 2 * lane < cnt && (node[0] != prev0 || ((2 * lane) & (cut - 1)) == 0));
+    n_runs = __popc(h0) + __popc(h1);
+  }
   const unsigned below = (1u << lane) - 1u;
   const int r_lo = __popc(h0 & below) + __popc(h1 & below);
   const unsigned mine0 = (h0 >> lane) & 1u, mine1 = (h1 >> lane) & 1u;
-  const int n_runs = __popc(h0) + __popc(h1);
   if (n_runs * 3 > 32) {
     // fragmented window (particles that changed cell since the G2P that placed them): merge the fragments
     const int merged = p2g_sort_window(S, node, cnt, lane);

@@ -841,7 +841,8 @@ class SlabSolver:
 
     @classmethod
     def from_dam_break(cls, rank: int, world: int, device, res: int = 256, n_total: int = 33_554_432,
-                       margin: int = 4, capacity: Optional[int] = None, p2g_mode: str = "auto", halo: str = "p2p"):
+                       margin: int = 4, capacity: Optional[int] = None, p2g_mode: str = "auto", halo: str = "p2p",
+                       late: bool = False):
         """BASELINE configs[4]: soft column at one x-end of a (res*world) x res x res domain;
         every rank generates the particles of its own x interval.  The even cut leaves the ranks
         away from the column empty; ``rebalance()`` re-cuts the slabs by particle count."""
@@ -850,7 +851,7 @@ class SlabSolver:
         dx = 1.0 / res
         lo = (plan.own_lo + 0.5) * dx if rank > 0 else -1.0
         hi = (plan.own_hi + 0.5) * dx if rank < world - 1 else float(world) + 1.0
-        sc = scenes.dam_break_slab(world, rank, res, n_total, x_range=(lo, hi))
+        sc = scenes.dam_break_slab(world, rank, res, n_total, x_range=(lo, hi), late=late)
         cap = capacity or max(int(n_total * 0.6), sc.n + 1024)
         local = CudaSlab(plan, dx, sc.dt, sc.volume, sc.gravity, sc.hardening, capacity=cap, device=device,
                          p2g_mode=p2g_mode)

@@ -87,7 +87,7 @@ def config_3d_16m(seed: int = 0) -> Scene:
 
 
 def dam_break_slab(world: int, rank: int, res: int = 256, n_total: int = 33_554_432, seed: int = 0,
-                   x_range=None) -> Scene:
+                   x_range=None, late: bool = False) -> Scene:
     """BASELINE configs[4]: a tall soft column at one x-end of a (res*world) x res x res
     domain, ~8.9 particles per cell, that collapses onto the floor (high atomic contention
     near the floor, strong load imbalance between slabs).  Returns only the particles whose
@@ -97,6 +97,13 @@ def dam_break_slab(world: int, rank: int, res: int = 256, n_total: int = 33_554_
     L = float(world)
     x0, x1 = 0.05 * L, 0.20 * L
     y0, y1, z0, z1 = 0.02, 0.92, 0.40, 0.60
+    if late:
+        # the LATE window of the same scene, as an initial condition: the same particles spread over the floor
+        # (~27 per cell: the dense, contended cells of a settled column; every slab loaded).  Running the column until it
+        # has spread is not an option: under the reference's own stress formula (lambda (J-1) J added to ALL entries,
+        # utils.py:129) the soft column goes unstable after a few thousand substeps -- on one GPU as on eight.
+        x0, x1 = 0.05 * L, 0.95 * L
+        y0, y1 = 0.02, 0.07
     cx0, cx1 = int(round(x0 * res)), int(round(x1 * res))
     cy0, cy1 = int(round(y0 * res)), int(round(y1 * res))
     cz0, cz1 = int(round(z0 * res)), int(round(z1 * res))
@@ -127,4 +134,5 @@ def dam_break_slab(world: int, rank: int, res: int = 256, n_total: int = 33_554_
     return Scene(3, res, dt, volume, -9.8, 1.0, pos, np.zeros((n, 3), np.float32),
                  np.tile(np.eye(3, dtype=np.float32), (n, 1, 1)), np.zeros((n, 3, 3), np.float32),
                  float(np.float32(rho * volume)), float(np.float32(mu)), float(np.float32(lam)), 0,
-                 f"3D dam break, {ppc} ppc column {cx1 - cx0}x{cy1 - cy0}x{cz1 - cz0} cells on {res * world}x{res}x{res}")
+                 f"3D dam break{' (late: spread over the floor)' if late else ''}, {ppc} ppc "
+                 f"{'layer' if late else 'column'} {cx1 - cx0}x{cy1 - cy0}x{cz1 - cz0} cells on {res * world}x{res}x{res}")

@@ -34,5 +34,5 @@ DAM=dam32m
 [ "$N" = "2" ] && DAM=dam:8388608
 run $N dam_static_early --steps 100 --warmup 10 --workload $DAM
 run $N dam_recut_early --steps 100 --warmup 10 --workload $DAM --rebalance
-run $N dam_static_late --steps 100 --warmup 10 --workload $DAM --presteps 1500
-run $N dam_recut_late --steps 100 --warmup 10 --workload $DAM --presteps 1500 --rebalance --rebalance-every 250
+run $N dam_static_late --steps 100 --warmup 10 --workload $DAM-late
+run $N dam_recut_late --steps 100 --warmup 10 --workload $DAM-late --rebalance

@@ -535,6 +535,42 @@ def test_fast_moving_particles_vs_oracle(cells_per_substep):
     s.close()
 
 
+@pytest.mark.parametrize("ppc_side", [3, 4])
+def test_dense_cells_vs_oracle(ppc_side):
+    """27 / 64 particles per cell (a settled column, BASELINE configs[4]): a 64-slot P2G window then holds one to three
+    long runs, which the production kernel cuts every 8 / 16 slots to keep its (run, slab) lanes busy.  8 substeps
+    against the C port, grid after the first P2G included."""
+    from femflow_b200 import scenes
+    from femflow_b200.mpm import MpmSolver
+    from oracle import native as ON
+    sc = scenes.elastic_block(3, 32, 10, ppc_side, seed=12)
+    n = sc.n
+    x, v, F, C = (a.astype(np.float64) for a in (sc.x, sc.v, sc.F, sc.C))
+    m = np.full(n, sc.mass); mu = np.full(n, sc.mu_0); lam = np.full(n, sc.lambda_0)
+    s = MpmSolver(3, sc.res, sc.dt, sc.volume, sc.gravity, sc.hardening, capacity=n)
+    s.set_particles(x, v, F, C, None, m, mu, lam)
+    s.substep(1)                                   # the state is cell-sorted from here on: long runs
+    ON.solve_mls_mpm_3d(sc.res, float(sc.res), sc.hardening, 1 / sc.res, sc.dt, sc.volume, sc.gravity, x, m, mu, lam, v, F, C)
+    s.clear_grid(); s.bin(); s.p2g()
+    G = sc.res + 1
+    gv = np.zeros((G, G, G, 3)); gm = np.zeros((G, G, G, 1))
+    O.p2g_3d(float(sc.res), sc.hardening, 1 / sc.res, sc.dt, sc.volume, gv, gm, x, m, mu, lam, v, F, C, np.ones((n, 1)))
+    g = s.grid().double().cpu().numpy()
+    assert rel_err(g[..., 3:], gm) < 1e-5 and rel_err(g[..., :3], gv) < 1e-5
+    steps = 7
+    s.substep(steps)
+    s.check_errors()
+    for _ in range(steps):
+        ON.solve_mls_mpm_3d(sc.res, float(sc.res), sc.hardening, 1 / sc.res, sc.dt, sc.volume, sc.gravity, x, m, mu, lam, v, F, C)
+    out = {k_: t.double().cpu().numpy() for k_, t in s.get_particles().items()}
+    V = max(np.abs(v).max(), sc.dt * 9.8)
+    assert rel_err(out["x"], x, 1.0) < 1e-5 * (steps + 1)
+    assert np.abs(out["v"] - v).max() / V < 1e-5 * (steps + 1)
+    assert rel_err(out["F"], F, 1.0) < 1e-5 * (steps + 1)
+    assert np.abs(out["C"] - C).max() / (4 * sc.res * V) < 1e-5 * (steps + 1)
+    s.close()
+
+
 def test_graph_replay_matches_eager_substeps():
     """MpmSolver.make_graph: 3 replays of a captured pair of substeps (internal binning stream and both
     ping-pong halves inside the capture) against the same 6 substeps launched one by one, from the same
