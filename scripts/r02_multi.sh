@@ -27,7 +27,7 @@ run $N bar_p2p --steps 100 --warmup 10 --halo p2p --slab-timing --e2e-serial-onl
 run $N blocks_symm --steps 100 --warmup 10 --workload 3d16m-blocks --slab-timing --e2e-serial-only --e2e-steps 1
 if [ "$N" = "8" ]; then
   run 4 bar_symm_n4 --steps 100 --warmup 10 --e2e-steps 2
-  run 2 bar_symm_n2 --steps 100 --warmup 10 --e2e-steps 2
+
   run 8 bar_symm_drift0.1 --steps 100 --warmup 10 --drift 0.1 --slab-timing --e2e-serial-only --e2e-steps 1
 fi
 DAM=dam32m
