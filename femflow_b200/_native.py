@@ -12,7 +12,7 @@ FFMPM_E_INVALID, FFMPM_E_CUDA, FFMPM_E_OOB, FFMPM_E_STATE = -1, -2, -3, -4
 FFMPM_F32, FFMPM_F64 = 0, 1
 FFMPM_NEO_HOOKEAN, FFMPM_SNOW = 0, 1
 FFMPM_P2G_AUTO, FFMPM_P2G_SCATTER, FFMPM_P2G_TILED, FFMPM_P2G_FUSED = 0, 1, 2, 3
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class FfMpmConfig(C.Structure):
@@ -71,6 +71,9 @@ PROTOTYPES = {
     "ffmpm_poll_error": (C.c_int, [H, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "ffmpm_snapshot": (C.c_int, [H, C.c_double, C.c_void_p, C.c_void_p]),
     "ffmpm_export_state": (C.c_int, [H, C.POINTER(FfMpmState), C.c_void_p]),
+    "ffmpm_scene_scratch_bytes": (C.c_int64, [C.c_int32]),
+    "ffmpm_gen_implicit_points": (C.c_int, [C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "ffmpm_gen_cube_points": (C.c_int, [C.POINTER(C.c_double), C.c_int32, C.c_void_p, C.c_void_p]),
     "ffmpm_launch_count": (C.c_int64, [H]),
     "ffmpm_debug_red_add4": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int64, C.c_void_p]),
 }

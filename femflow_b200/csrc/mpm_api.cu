@@ -18,6 +18,7 @@
 #include "mpm_g2p2g.cuh"
 #include "mpm_migrate.cuh"
 #include "mpm_2d.cuh"
+#include "mpm_scene.cuh"
 
 using namespace ffmpm;
 
@@ -820,6 +821,44 @@ int ffmpm_export_state(FfMpmHandle* h, const FfMpmState* dst, void* stream) {
   else
     export_by_id_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(view<float>(h, h->st[h->live]), view<float>(h, *dst), h->n, h->cfg.dim);
   return check_launch(h, 1);
+}
+
+// ---- scene point generators (mpm_scene.cuh) ----
+int64_t ffmpm_scene_scratch_bytes(int32_t res) {
+  if (res < 1 || res > 2048) return set_err(FFMPM_E_INVALID, "lattice resolution must be in [1, 2048]");
+  const long long total = (long long)res * res * res;
+  const long long blocks = (total + SCENE_THREADS - 1) / SCENE_THREADS;
+  return 256 + ((blocks * 4 + 255) / 256) * 256 + blocks * 8;
+}
+
+int ffmpm_gen_implicit_points(int32_t kind, double k, double t, int32_t res, void* scratch, double* out, int64_t capacity,
+                              void* stream) {
+  if (kind < 0 || kind > 2) return set_err(FFMPM_E_INVALID, "Invalid implicit function specified");   // primitives.py:57
+  if (res < 1 || res > 2048 || !scratch || capacity < 0 || (capacity > 0 && !out) || !(k != 0.0))
+    return set_err(FFMPM_E_INVALID, "bad scene generator arguments");
+  const long long total = (long long)res * res * res;
+  const int blocks = (int)((total + SCENE_THREADS - 1) / SCENE_THREADS);
+  long long* count = (long long*)scratch;
+  int* counts = (int*)((char*)scratch + 256);
+  long long* offsets = (long long*)((char*)scratch + 256 + (((long long)blocks * 4 + 255) / 256) * 256);
+  cudaStream_t s = (cudaStream_t)stream;
+  implicit_count_kernel<<<blocks, SCENE_THREADS, 0, s>>>(kind, k, t, res, total, counts);
+  scene_scan_kernel<<<1, 1024, 0, s>>>(counts, offsets, blocks, count);
+  if (capacity > 0) implicit_write_kernel<<<blocks, SCENE_THREADS, 0, s>>>(kind, k, t, res, total, offsets, out, capacity);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_err(FFMPM_E_CUDA, "kernel launch: %s", cudaGetErrorString(e));
+  return FFMPM_OK;
+}
+
+int ffmpm_gen_cube_points(const double* bounds6_host, int32_t res, double* out, void* stream) {
+  if (!bounds6_host || !out || res < 1 || res > 2048) return set_err(FFMPM_E_INVALID, "bad scene generator arguments");
+  const long long total = (long long)res * res * res;
+  const double* b = bounds6_host;
+  cube_points_kernel<<<(unsigned)((total + SCENE_THREADS - 1) / SCENE_THREADS), SCENE_THREADS, 0, (cudaStream_t)stream>>>(
+      b[0], b[1], b[2], b[3], b[4], b[5], res, out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_err(FFMPM_E_CUDA, "kernel launch: %s", cudaGetErrorString(e));
+  return FFMPM_OK;
 }
 
 int64_t ffmpm_launch_count(const FfMpmHandle* h) { return h ? h->launches : 0; }

@@ -45,17 +45,24 @@ SHARED = dict(outdir="tmp", dt=1e-4, gyroid_mass=1.0, k=0.2, t=0.3, volume=1.0, 
               hardening=0.7, grid_res=64, mesh_type="gyroid")
 
 
-def multi_drop_scene(experiment: int) -> Tuple[List[PointMesh], List[Tuple[float, float, float]], dict]:
+def multi_drop_scene(experiment: int, device=None) -> Tuple[List[PointMesh], List[Tuple[float, float, float]], dict]:
     """Meshes, per-mesh ``(mass, E, nu)`` and the ``MPMSimulation`` constructor arguments of
-    ``multi_drop_experiment(experiment)`` (paper_1.py:17-73 ``prepare_sim``)."""
+    ``multi_drop_experiment(experiment)`` (paper_1.py:17-73 ``prepare_sim``).  ``device``: generate the two point
+    sets with the CUDA scene kernels (``primitives.generate_*_gpu``) instead of on the host."""
     if experiment not in EXPERIMENTS:
         raise ValueError(f"Experiment {experiment} is not valid")            # paper_1.py:144
     e, s = EXPERIMENTS[experiment], SHARED
-    gyroid = PointMesh(P.generate_implicit_points(s["mesh_type"], s["k"], s["t"], e["mesh_res"]))
+    if device is not None:
+        gyroid = PointMesh(P.generate_implicit_points_gpu(s["mesh_type"], s["k"], s["t"], e["mesh_res"], device).cpu().numpy())
+    else:
+        gyroid = PointMesh(P.generate_implicit_points(s["mesh_type"], s["k"], s["t"], e["mesh_res"]))
     gyroid.translate_y(0.1)
     v = gyroid.vertices.reshape(-1, 3)
     lo, hi = v.min(0), v.max(0)
-    collider = PointMesh(P.generate_cube_points((lo[0], hi[0]), (lo[1], hi[1]), (lo[2], hi[2]), e["mesh_res"]))
+    if device is not None:
+        collider = PointMesh(P.generate_cube_points_gpu((lo[0], hi[0]), (lo[1], hi[1]), (lo[2], hi[2]), e["mesh_res"], device).cpu().numpy())
+    else:
+        collider = PointMesh(P.generate_cube_points((lo[0], hi[0]), (lo[1], hi[1]), (lo[2], hi[2]), e["mesh_res"]))
     collider.translate_y(3)
     params = [(s["gyroid_mass"], e["gyroid_E"], s["gyroid_v"]), (e["collider_mass"], e["collider_E"], s["collider_v"])]
     ctor = dict(outdir=s["outdir"], steps=e["steps"], dt=s["dt"], gyroid_mass=s["gyroid_mass"], collider_mass=e["collider_mass"],
@@ -69,7 +76,7 @@ def run(experiment: int = 0, steps: int = None, outdir: str = None, save: bool =
         progress: bool = False):
     """Build the scene, run it on the GPU, return the finished ``MPMSimulation`` and the wall time of the run."""
     from .simulation import MPMSimulation
-    meshes, params, ctor = multi_drop_scene(experiment)
+    meshes, params, ctor = multi_drop_scene(experiment, device=device if str(device).startswith("cuda") else None)
     if steps is not None:
         ctor["steps"] = int(steps)
     if outdir is not None:

@@ -41,6 +41,51 @@ def diamond(k: float, t: float, pos: np.ndarray):
 _FNS = {"gyroid": gyroid, "diamond": diamond, "primitive": primitive}
 
 
+_KINDS = {"gyroid": 0, "diamond": 1, "primitive": 2}
+
+
+def generate_implicit_points_gpu(implicit_fn: str, k: float, t: float, res: int, device="cuda:0"):
+    """``generate_implicit_points`` on the GPU (csrc/mpm_scene.cuh through ``ffmpm_gen_implicit_points``): the res^3
+    lattice is never materialised, the selected points come back as an ``(N, 3)`` float64 device tensor in the
+    reference's row order.  Two passes over the lattice: count, then write."""
+    import ctypes as C
+
+    import torch
+
+    from ... import _native as N
+    if implicit_fn not in _KINDS:
+        raise ValueError("Invalid implicit function specified")
+    lib, dev = N.lib(), torch.device(device)
+    with torch.cuda.device(dev):
+        nbytes = lib.ffmpm_scene_scratch_bytes(int(res))
+        if nbytes < 0:
+            N.check(int(nbytes))
+        scratch = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        args = (_KINDS[implicit_fn], float(k), float(t), int(res), scratch.data_ptr())
+        N.check(lib.ffmpm_gen_implicit_points(*args, None, 0, stream))
+        count = int(scratch[:8].view(torch.int64).item())
+        out = torch.empty((count, 3), dtype=torch.float64, device=dev)
+        if count:
+            N.check(lib.ffmpm_gen_implicit_points(*args, out.data_ptr(), count, stream))
+    return out
+
+
+def generate_cube_points_gpu(xb, yb, zb, res: int = 10, device="cuda:0"):
+    """``generate_cube_points`` on the GPU: ``(res^3, 3)`` float64 device tensor, rows [z, y, x] with x fastest."""
+    import ctypes as C
+
+    import torch
+
+    from ... import _native as N
+    lib, dev = N.lib(), torch.device(device)
+    bounds = (C.c_double * 6)(float(xb[0]), float(xb[1]), float(yb[0]), float(yb[1]), float(zb[0]), float(zb[1]))
+    with torch.cuda.device(dev):
+        out = torch.empty((int(res) ** 3, 3), dtype=torch.float64, device=dev)
+        N.check(lib.ffmpm_gen_cube_points(bounds, int(res), out.data_ptr(), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return out
+
+
 def generate_implicit_points(implicit_fn: Union[Callable, str], k: float, t: float, res: int) -> np.ndarray:
     """primitives.py:46-61: lattice points with ``f(p) - t > t`` (the reference
     subtracts t inside the function and compares against t again)."""

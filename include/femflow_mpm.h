@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define FFMPM_ABI_VERSION 3
+#define FFMPM_ABI_VERSION 4
 
 enum {
   FFMPM_OK = 0,
@@ -221,6 +221,20 @@ int ffmpm_snapshot(FfMpmHandle* h, double coeff, double* out, void* stream);
  * particles cell-sorted and carries their index in the id plane -- this is the way back for callers that hold
  * their state outside the library (HostSubstepPipeline).  Without an id plane it is a plain copy. */
 int ffmpm_export_state(FfMpmHandle* h, const FfMpmState* dst, void* stream);
+
+/* Scene point generators on the device (the step in front of the path).  No handle needed.
+ *   ffmpm_gen_implicit_points  femflow/simulation/mpm/primitives.py:46-61 generate_implicit_points over the lattice of
+ *                              numerics/geometry.py:101-116 grid((res, res, res)): the points p with f(p) - t > t for
+ *                              f = gyroid (kind 0) / diamond (1) / primitive (2), primitives.py:8-43, in lattice order.
+ *                              Asynchronous; the number of selected points is left as an int64 at scratch[0] (a call
+ *                              with capacity 0 only counts); `out` receives min(count, capacity) rows of 3 doubles.
+ *                              `scratch`: ffmpm_scene_scratch_bytes(res) bytes of device memory, 256-byte aligned.
+ *   ffmpm_gen_cube_points      primitives.py:64-76 generate_cube_points: res^3 rows [z, y, x] (x fastest) of the
+ *                              np.linspace lattices of the three intervals; bounds6 = {x0, x1, y0, y1, z0, z1} (host). */
+int64_t ffmpm_scene_scratch_bytes(int32_t res);
+int ffmpm_gen_implicit_points(int32_t kind, double k, double t, int32_t res, void* scratch, double* out, int64_t capacity,
+                              void* stream);
+int ffmpm_gen_cube_points(const double* bounds6_host, int32_t res, double* out, void* stream);
 
 /* Number of kernel launches issued by this handle so far. */
 int64_t ffmpm_launch_count(const FfMpmHandle* h);

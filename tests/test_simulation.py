@@ -37,6 +37,33 @@ def test_scene_generators_reproduce_the_paper_scene():
 
 
 @pytest.mark.gpu
+def test_scene_generators_on_the_gpu():
+    """csrc/mpm_scene.cuh (ffmpm_gen_implicit_points / ffmpm_gen_cube_points) against the host generators, which are
+    pinned to the reference's own output point for point (test_scene_generators_reproduce_the_paper_scene): every
+    implicit function, resolutions that leave ragged last blocks, the paper scene (8 321 + 27 000 points), res 1."""
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from femflow_b200.simulation.mpm import primitives as P
+    for kind, k, t, res in (("gyroid", 0.2, 0.3, 30), ("gyroid", 0.2, 0.3, 40), ("diamond", 0.35, 0.1, 17),
+                            ("primitive", 0.5, -0.2, 23), ("gyroid", 0.2, 0.3, 1), ("primitive", 1.0, 5.0, 9)):
+        want = P.generate_implicit_points(kind, k, t, res)
+        got = P.generate_implicit_points_gpu(kind, k, t, res).cpu().numpy()
+        assert got.shape == want.shape, (kind, res, got.shape, want.shape)
+        assert np.array_equal(got, want), (kind, res)
+    assert len(P.generate_implicit_points_gpu("gyroid", 0.2, 0.3, 30)) == 8321
+    for bounds, res in ((((0.0, 1.0), (0.1, 0.2050000041723251), (-3.0, 2.5)), 30), (((0.25, 0.75),) * 3, 7), (((1.0, 2.0),) * 3, 1)):
+        want = P.generate_cube_points(*bounds, res)
+        got = P.generate_cube_points_gpu(*bounds, res).cpu().numpy()
+        assert np.array_equal(got, want), (bounds, res)
+    with pytest.raises(ValueError):
+        P.generate_implicit_points_gpu("nope", 0.2, 0.3, 4)
+    # a lattice no host loop would want to walk: 512^3 = 1.3e8 points
+    big = P.generate_implicit_points_gpu("gyroid", 0.2, 0.3, 512)
+    assert 0.2 * 512 ** 3 < len(big) < 0.6 * 512 ** 3 and bool(torch.isfinite(big).all())
+
+
+@pytest.mark.gpu
 def test_mpm_simulation_matches_reference_trajectory(tmp_path):
     torch = pytest.importorskip("torch")
     if not torch.cuda.is_available():
