@@ -12,7 +12,7 @@ FFMPM_E_INVALID, FFMPM_E_CUDA, FFMPM_E_OOB, FFMPM_E_STATE = -1, -2, -3, -4
 FFMPM_F32, FFMPM_F64 = 0, 1
 FFMPM_NEO_HOOKEAN, FFMPM_SNOW = 0, 1
 FFMPM_P2G_AUTO, FFMPM_P2G_SCATTER, FFMPM_P2G_TILED, FFMPM_P2G_FUSED = 0, 1, 2, 3
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class FfMpmConfig(C.Structure):
@@ -60,6 +60,7 @@ PROTOTYPES = {
     "ffmpm_set_colliders": (C.c_int, [H, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int32]),
     "ffmpm_collide": (C.c_int, [H, C.c_void_p]),
     "ffmpm_set_owned_range": (C.c_int, [H, C.c_int32, C.c_int32]),
+    "ffmpm_set_owned_slack": (C.c_int, [H, C.c_int32]),
     "ffmpm_leaver_count_ptr": (C.c_int, [H, C.POINTER(C.c_void_p)]),
     "ffmpm_migrate_rows": (C.c_int32, [H]),
     "ffmpm_migrate_pack": (C.c_int, [H, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),

@@ -157,6 +157,7 @@ int ffmpm_create(const FfMpmConfig* cfg, int32_t device, FfMpmHandle** out) {
   }
   d.own_lo = INT32_MIN;   // single domain: nobody leaves
   d.own_hi = INT32_MAX;
+  d.own_slack = 0;
   d.fp32_stress = 1;   // fp32 build: left-form perturbation series (mpm_math.cuh); FFMPM_FP32_STRESS=0: fp64 stress always
   if (const char* e = getenv("FFMPM_FP32_STRESS")) d.fp32_stress = atoi(e) != 0;
   h->n_nodes = (int64_t)d.n[0] * d.n[1] * d.n[2];
@@ -655,6 +656,12 @@ int ffmpm_set_owned_range(FfMpmHandle* h, int32_t own_lo, int32_t own_hi) {
   if (!h || own_lo > own_hi) return set_err(FFMPM_E_INVALID, "bad owned range");
   h->dev.own_lo = own_lo;
   h->dev.own_hi = own_hi;
+  return FFMPM_OK;
+}
+
+int ffmpm_set_owned_slack(FfMpmHandle* h, int32_t slack) {
+  if (!h || slack < 0) return set_err(FFMPM_E_INVALID, "bad slack");
+  h->dev.own_slack = slack;
   return FFMPM_OK;
 }
 

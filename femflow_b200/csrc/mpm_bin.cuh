@@ -24,7 +24,8 @@ constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 struct BinBuffers {
   int32_t* counters;     // [16]: 0 = n_active_tiles, 1 = p2g work counter, 2 = g2p work counter,
-                         //       3 = particles whose base cell left the rank's owned x range (slabs)
+                         //       3 = particles whose base cell left the rank's owned x range (slabs),
+                         //       4 = those of them more than own_slack cells outside it
   int32_t* cell_count;   // [n_cells + 2] histogram, bin n_cells = out-of-grid
   int32_t* cell_off;     // [n_cells + 2] exclusive scan of cell_count
   int32_t* block_sums;   // [n_scan_blocks + 1]

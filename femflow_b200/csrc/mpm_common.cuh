@@ -16,6 +16,7 @@ struct DevCfg {
   int fp32_stress;   // fp32 build: evaluate the stress in perturbation form in fp32 when the strain allows
   int index_fp32;      // inv_dx is a power of two: cell indexing is exact in fp32 (see base_fx)
   int own_lo, own_hi;  // slabs: GLOBAL base cells [own_lo, own_hi) along x owned by this rank (G2P counts leavers)
+  int own_slack;       // ... and, separately, the leavers that are more than own_slack cells outside it ("urgent")
 };
 
 // Plane colliders of three_d/grid_op.py:50-67 (normals already shifted by 1/|normal|, the

@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_tiled3_kernel(Dev
       const int slot = rbase + threadIdx.x;
       const bool mine = slot >= start && slot < end;
       int next_key = -1;
-      bool leaving = false;
+      bool leaving = false, urgent = false;
       T o[24];
       T cm = 0, cmu = 0, cl = 0, cjp = 0;
       int cid = 0;
@@ -216,6 +216,7 @@ __global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_tiled3_kernel(Dev
         next_key = bin_key_of<T, IDX32>(cfg, B, o[0], o[1], o[2], &gbx);
         B.keys[slot] = next_key;
         leaving = gbx < cfg.own_lo || gbx >= cfg.own_hi;
+        urgent = (long long)gbx - cfg.own_hi >= cfg.own_slack || (long long)cfg.own_lo - gbx > cfg.own_slack;
       }
       // next substep's histogram + within-cell rank (same scheme as bin_count_kernel): the atomic is posted here and
       // its return value is used after the 24 stores below, which cover its round trip to L2
@@ -223,7 +224,13 @@ __global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_tiled3_kernel(Dev
       {
         // slabs: count the particles that now belong to a neighbour rank (read by the migration logic)
         const unsigned lm = __ballot_sync(0xffffffffu, leaving);
-        if (lm && (threadIdx.x & 31) == 0) atomicAdd(&B.counters[3], __popc(lm));
+        if (lm) {          // rare: only near a slab cut
+          const unsigned um = __ballot_sync(lm, leaving && urgent);
+          if ((threadIdx.x & 31) == (unsigned)(__ffs(lm) - 1)) {
+            atomicAdd(&B.counters[3], __popc(lm));
+            if (um) atomicAdd(&B.counters[4], __popc(um));
+          }
+        }
       }
       {
         if (mine) {

@@ -292,6 +292,15 @@ class SlabDriver:
                 raise ValueError("lagged migration (count_leavers_async) needs a halo margin of at least 2 cells")
             if self.migrate_every + 1 > max(2, plan.margin):
                 self.migrate_every = max(1, plan.margin - 1)
+            # Local solvers that also count the URGENT leavers (more than `slack` cells outside the owned range) let
+            # particles stray inside the halo margin and hand them over only when one has used up the slack -- or when
+            # so many have left that the load shifts -- instead of every period.  With the count taken every p
+            # substeps and acted upon one substep late, a particle is at most slack + p cells out when it is moved:
+            # slack + p <= margin - 1.
+            if hasattr(local, "set_leaver_slack") and migrate_every is None:
+                self.migrate_every = max(1, plan.margin // 2)
+                self.slack = max(0, plan.margin - 1 - self.migrate_every)
+                local.set_leaver_slack(self.slack)
 
     # -- halo planes: exchange partial sums with both neighbours ------------------
     def _exchange_halos(self) -> None:
@@ -351,8 +360,9 @@ class SlabDriver:
             if self.steps > k:                      # one substep of GPU work is queued behind the count
                 self._pending = None
                 count = L.read_leaver_count(handle)     # already the max over all ranks
-                if count > 0:
-                    self.migrate(hint=count)
+                leavers, urgent = count if isinstance(count, tuple) else (count, count)
+                if urgent > 0 or leavers >= getattr(L, "leaver_limit", 1):
+                    self.migrate(hint=leavers)
                     migrated_now = True
         # the device counter was filled by this substep's G2P, i.e. BEFORE a migration that has just run: it would
         # still count the particles that were handed over.  Take the next count one period later instead.
@@ -570,6 +580,7 @@ class CudaSlab(LocalSlab):
         # the binned G2P counts the particles that left [own_lo, own_hi) while it advects them
         self.solver.set_owned_range(plan.own_lo if plan.rank > 0 else -(2 ** 31),
                                     plan.own_hi if plan.rank < plan.world - 1 else 2 ** 31 - 1)
+        self.solver.set_owned_slack(getattr(self, "_slack", 0))
 
     @property
     def num_particles(self) -> int:
@@ -667,8 +678,18 @@ class CudaSlab(LocalSlab):
         s.num_particles = n_new
         return {"out_lo": out_l, "out_hi": out_h, "in_lo": got_l, "in_hi": got_h, "n": n_new, "overflow": overflow}
 
+    def set_leaver_slack(self, slack: int) -> None:
+        self._slack = int(slack)
+        self.solver.set_owned_slack(self._slack)
+
+    @property
+    def leaver_limit(self) -> int:
+        """So many strays inside the margin that handing them over is worth a round whatever the slack says."""
+        return max(4096, self.solver.capacity // 64)
+
     def count_leavers_async(self, own_lo: int, own_hi: int):
-        """Device-side count of the particles whose base cell left [own_lo, own_hi)."""
+        """Device-side counts (2,) of the particles whose base cell left [own_lo, own_hi) and of those more than the
+        slack outside it."""
         s = self.solver
         if self._g2p_counts and s.num_particles > 0:
             return s.leaver_count().to(torch.int64)      # filled by the last G2P, no extra pass over x
@@ -676,21 +697,25 @@ class CudaSlab(LocalSlab):
         # domain-end ranks have no neighbour on that side: nothing "leaves" there (a particle outside the global
         # grid is reported by the binning, as the reference raises for it) -- the thresholds of _make_solver
         p = self.plan
+        k = getattr(self, "_slack", 0)
         t_lo = self._threshold(own_lo) if p.rank > 0 else float("-inf")
         t_hi = self._threshold(own_hi) if p.rank < p.world - 1 else float("inf")
-        return torch.count_nonzero((x0 < t_lo) | (x0 >= t_hi)).to(torch.int64).reshape(1)
+        u_lo = self._threshold(own_lo - k) if p.rank > 0 else float("-inf")
+        u_hi = self._threshold(own_hi + k) if p.rank < p.world - 1 else float("inf")
+        return torch.stack([torch.count_nonzero((x0 < t_lo) | (x0 >= t_hi)),
+                            torch.count_nonzero((x0 < u_lo) | (x0 >= u_hi))]).to(torch.int64)
 
     def stage_leaver_count(self, cnt):
         if not hasattr(self, "_cnt_host"):
-            self._cnt_host = torch.zeros(1, dtype=torch.int64).pin_memory()
+            self._cnt_host = torch.zeros(2, dtype=torch.int64).pin_memory()
         self._cnt_host.copy_(cnt, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
         return ev
 
-    def read_leaver_count(self, handle) -> int:
+    def read_leaver_count(self, handle):
         handle.synchronize()
-        return int(self._cnt_host[0])
+        return int(self._cnt_host[0]), int(self._cnt_host[1])
 
     def _threshold(self, cell: int):
         """Smallest value of the storage dtype whose base cell is >= ``cell``."""

@@ -366,12 +366,16 @@ class MpmSolver:
     def set_owned_range(self, own_lo: int, own_hi: int) -> None:
         N.check(self.lib.ffmpm_set_owned_range(self._h, int(own_lo), int(own_hi)))
 
+    def set_owned_slack(self, slack: int) -> None:
+        N.check(self.lib.ffmpm_set_owned_slack(self._h, int(slack)))
+
     def leaver_count(self) -> torch.Tensor:
-        """(1,) int32 view of the device counter the binned G2P fills (see ffmpm_set_owned_range)."""
+        """(2,) int32 view of the device counters the binned G2P fills (see ffmpm_set_owned_range):
+        [particles outside the owned range, those more than the slack outside it]."""
         ptr = C.c_void_p()
         N.check(self.lib.ffmpm_leaver_count_ptr(self._h, C.byref(ptr)))
         off = ptr.value - self.workspace.data_ptr()
-        return self.workspace[off:off + 4].view(torch.int32)
+        return self.workspace[off:off + 8].view(torch.int32)
 
     def collide(self, stream=None) -> None:
         N.check(self.lib.ffmpm_collide(self._h, self._stream(stream)))

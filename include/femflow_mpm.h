@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define FFMPM_ABI_VERSION 4
+#define FFMPM_ABI_VERSION 5
 
 enum {
   FFMPM_OK = 0,
@@ -142,6 +142,10 @@ int ffmpm_grid_op_halo(FfMpmHandle* h, const void* recv_lo, int32_t planes_lo, c
  * device counter (ffmpm_leaver_count_ptr; cleared by the next ffmpm_bin), so the migration logic
  * needs no pass of its own over the positions. */
 int ffmpm_set_owned_range(FfMpmHandle* h, int32_t own_lo, int32_t own_hi);
+/* count[0] = particles outside the owned range, count[1] = those of them MORE than `slack` cells outside it
+ * (ffmpm_set_owned_slack, default 0): a slab driver whose halo margin has room lets particles stray and migrates
+ * only when count[1] > 0, instead of every period. */
+int ffmpm_set_owned_slack(FfMpmHandle* h, int32_t slack);
 int ffmpm_leaver_count_ptr(FfMpmHandle* h, int32_t** count);
 /* Slab migration on the device (new).  One round, all on `stream`, no host involvement:
  *   ffmpm_migrate_pack    every live particle whose GLOBAL base cell along axis 0 (three_d/p2g.py:50) left the owned

@@ -76,6 +76,7 @@ class FakeLib:
         h.table = None
         h.colliders = None
         h.own = (-2 ** 31, 2 ** 31 - 1)
+        h.slack = 0
         self.handles[self.next_id] = h
         out_ref._obj.value = self.next_id
         self.next_id += 1
@@ -133,6 +134,10 @@ class FakeLib:
 
     def ffmpm_set_owned_range(self, h, lo, hi):
         self._h(h).own = (int(_val(lo)), int(_val(hi)))
+        return N.FFMPM_OK
+
+    def ffmpm_set_owned_slack(self, h, slack):
+        self._h(h).slack = int(_val(slack))
         return N.FFMPM_OK
 
     def ffmpm_leaver_count_ptr(self, h, out_ref):
@@ -343,7 +348,8 @@ class FakeLib:
         q["C"][:, :n] = Cm[order].reshape(n, 9).T
         nb, _ = O.base_and_fx(x[ok], h.cfg.inv_dx)
         leavers = int(((nb[:, 0] < h.own[0]) | (nb[:, 0] >= h.own[1])).sum())
-        _view(h.ws + 64, 1, C.c_int32)[0] = leavers
+        urgent = int(((h.own[0] - nb[:, 0] > h.slack) | (nb[:, 0] - h.own[1] >= h.slack)).sum())
+        _view(h.ws + 64, 2, C.c_int32)[:] = (leavers, urgent)
         return N.FFMPM_OK
 
     def ffmpm_scatter(self, h, stream):

@@ -77,6 +77,8 @@ CASES = {
     "lagged-2-planes": dict(world=2, margin=3, migrate_every=2, lagged=True, nmat=300),
     "rebalance-3": dict(world=3, margin=2, migrate_every=1, lagged=True, nmat=3, lopsided=True, rebalance=True, pre=2),
     "symm-2": dict(world=2, margin=2, migrate_every=2, lagged=True, nmat=1, symm=True),
+    # the default cadence: particles may stray `slack` cells into the halo margin, a round runs only when one has used it up
+    "slack-2-margin4": dict(world=2, margin=4, migrate_every=None, lagged=True, nmat=3, steps=9),
     # the unbinned kernels never fill the device leaver counter: the count must come from the positions instead
     "lagged-2-scatter": dict(world=2, margin=2, migrate_every=1, lagged=True, nmat=3, p2g_mode="scatter"),
 }
