@@ -100,23 +100,19 @@ __device__ __forceinline__ void p2g_runs_phase2_adjacent(P2GWarpSlab<float>& S, 
   const unsigned below = (1u << lane) - 1u;
   const int r_lo = __popc(h0 & below) + __popc(h1 & below);
   const unsigned mine0 = (h0 >> lane) & 1u, mine1 = (h1 >> lane) & 1u;
+  if (n_runs * 3 > 32) {
+    // fragmented window (particles that changed cell since the G2P that placed them): merge the fragments
+    const int merged = p2g_sort_window(S, node, cnt, lane);
+    if (merged >= 0) {
+      __syncwarp();
+      p2g_accumulate_runs<float, true>(S, merged, lane, ny, nz, grid);
+      return;
+    }
+  }
   if (mine0) S.run_start[r_lo] = 2 * lane;
   if (mine1) S.run_start[r_lo + mine0] = 2 * lane + 1;
   if (lane == 0) S.run_start[n_runs] = cnt;
   __syncwarp();
-  // Cost of the (run, slab) item mapping in iterations: every pass of 32 items takes as long as its longest run.
-  // Ragged windows (a misaligned particle lattice: 4..12 particles per cell; particles that changed cell since the G2P
-  // that placed them; more than ten runs) go to the chunked walk instead, which takes ceil(3 cnt / 32) iterations plus
-  // its flushes whatever the runs look like.
-  int longest = 0;
-  for (int r = lane; r < n_runs; r += 32) longest = max(longest, S.run_start[r + 1] - S.run_start[r]);
-  longest = __reduce_max_sync(0xffffffffu, longest);
-  const int passes = (n_runs * 3 + 31) >> 5;
-  const int chunk_cost = ((3 * cnt + 31) >> 5) + 3;        // iterations + an allowance for the flushes inside the loop
-  if (passes * longest > chunk_cost) {
-    p2g_accumulate_chunks<float>(S, cnt, lane, ny, nz, grid);
-    return;
-  }
   p2g_accumulate_runs<float>(S, n_runs, lane, ny, nz, grid);
 }
 

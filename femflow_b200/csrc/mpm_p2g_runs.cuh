@@ -44,6 +44,7 @@ struct P2GWarpSlab {
   P2GVec4<T> pay[4][P2G_PADDED];  // {mvx,mvy,mvz,m} {a00,a01,a02,fx} {a10,a11,a12,fy} {a20,a21,a22,fz}, a = affine*dx
   int node0[P2G_WINDOW];          // linear LOCAL node id of the particle's base cell (-1: outside the grid)
   int run_start[P2G_WINDOW + 1];  // window-relative first slot of each run (+ sentinel)
+  unsigned char order[P2G_WINDOW];   // INDIRECT phase 2: position in cell-sorted order -> slot of the window
 };
 
 // Phase 1 tail: park one particle's payload.
@@ -65,14 +66,16 @@ __device__ __forceinline__ int p2g_park(P2GWarpSlab<T>& S, P2GParticle3<T>& q, i
 }
 
 // Phase 2 proper: lane per (run, x-slab) over the run table S.run_start[0 .. n_runs] of a parked window.
-template <typename T>
+// INDIRECT: the runs are runs of the window's particles in CELL-SORTED order (S.order maps a sorted position to its
+// slot) instead of runs of consecutive slots -- see p2g_sort_window.
+template <typename T, bool INDIRECT = false>
 __device__ __forceinline__ void p2g_accumulate_runs(P2GWarpSlab<T>& S, int n_runs, int lane, int ny, int nz,
                                                     T* __restrict__ grid) {
   const int n_items = n_runs * 3;
   for (int item = lane; item < n_items; item += 32) {
     const int r = item / 3, li = item - r * 3;
     const int r0 = S.run_start[r], r1 = S.run_start[r + 1];
-    const int node_r = S.node0[r0];
+    const int node_r = S.node0[INDIRECT ? (int)S.order[r0] : r0];
     if (node_r < 0) continue;   // a run of out-of-grid particles
     const T ci = (T)li;
     // B-spline piece of this slab along x: w = s * (f - c)^2 + o  (three_d/p2g.py:55)
@@ -81,7 +84,7 @@ __device__ __forceinline__ void p2g_accumulate_runs(P2GWarpSlab<T>& S, int n_run
 #pragma unroll
     for (int e = 0; e < 9; ++e) ax[e] = ay[e] = az[e] = am[e] = (T)0;
     for (int qi = r0; qi < r1; ++qi) {
-      const int ph = p2g_pad(qi);
+      const int ph = p2g_pad(INDIRECT ? (int)S.order[qi] : qi);
       const P2GVec4<T> p0 = S.pay[0][ph], p1 = S.pay[1][ph], p2 = S.pay[2][ph], p3 = S.pay[3][ph];
       const T fx = p1.w, fy = p2.w, fz = p3.w;
       T wy[3], wz[3];
@@ -116,77 +119,71 @@ __device__ __forceinline__ void p2g_accumulate_runs(P2GWarpSlab<T>& S, int n_run
   }
 }
 
-// Phase 2 for RAGGED windows: the 3 * cnt (slab, particle) pairs of the window, slab-major, are dealt out to the 32
-// lanes in equal contiguous chunks (6 per lane for a full window) instead of one (run, slab) item per lane.  A lane
-// walks its chunk with the same register accumulation and flushes the nine nodes with vector REDs whenever the base
-// cell (or the slab) changes and at the end of the chunk.  Every lane does the same number of iterations whatever
-// the run lengths are -- with (run, slab) items the pass takes as long as the LONGEST run of the window, and a second
-// pass starts once there are more than ten runs -- at the price of ~2x the REDs (a run is cut wherever a chunk ends).
-// Used when the run table says the item mapping would take more than ~8 iterations (misaligned particle lattices,
-// moving particles, boundary cells); the aligned 8-particles-per-cell window keeps the item mapping (27 REDs per run).
-template <typename T>
-__device__ __forceinline__ void p2g_accumulate_chunks(P2GWarpSlab<T>& S, int cnt, int lane, int ny, int nz, T* __restrict__ grid) {
-  const int total = 3 * cnt;
-  const int per = (total + 31) >> 5;
-  int t = lane * per;
-  const int t_end = min(total, t + per);
-  T ax[9], ay[9], az[9], am[9];
+// Cell-sort of one window inside the warp.  The reordering G2P stores a particle at the slot of the cell it was in
+// BEFORE it was advected, so with particles moving c cells per substep a fraction ~c of a window sits in a
+// neighbouring cell's run: every such particle is a run of its own and cuts another run in two, the (run, slab)
+// items overflow the 32 lanes and phase 2 takes two or three passes of short, ragged runs.  Sorting the window's
+// 64 (base node, slot) pairs -- a bitonic network over two keys per lane, shuffles only -- merges all particles of
+// a cell within the window into ONE run again.  lane l holds the elements 2l and 2l+1; key = node << 6 | slot
+// (nodes are compared relative to the window's smallest: 26 bits), out-of-grid particles sort last.
+// Returns the number of runs and fills S.order / S.run_start, or -1 when the window's nodes span more than 2^26 ids
+// (the caller then keeps the unsorted run table).  ~150 instructions: only called when the unsorted run table would
+// need more than one pass.
+__device__ __forceinline__ int p2g_sort_window(P2GWarpSlab<float>& S, const int (&node)[2], int cnt, int lane) {
+  const unsigned big = 0x03ffffffu;                                    // out of grid / past the end: sorts last
+  unsigned lo = 0xffffffffu, hi = 0u;
 #pragma unroll
-  for (int e = 0; e < 9; ++e) ax[e] = ay[e] = az[e] = am[e] = (T)0;
-  int cur_node = -1, li = 0;
-  T ci = 0, sx = 0, cx_ = 0, ox_ = 0;
-  auto flush = [&]() {
-    if (cur_node >= 0) {
-      T* g = grid + ((long long)cur_node + (long long)li * ny * nz) * 4;
+  for (int h = 0; h < 2; ++h)
+    if (2 * lane + h < cnt && node[h] >= 0) { lo = min(lo, (unsigned)node[h]); hi = max(hi, (unsigned)node[h]); }
+  lo = __reduce_min_sync(0xffffffffu, lo);
+  hi = __reduce_max_sync(0xffffffffu, hi);
+  if (lo != 0xffffffffu && hi - lo >= big) return -1;
+  unsigned key[2];
 #pragma unroll
-      for (int j = 0; j < 3; ++j)
+  for (int h = 0; h < 2; ++h) {
+    const bool live = 2 * lane + h < cnt && node[h] >= 0;
+    const unsigned rel = live ? (unsigned)node[h] - lo : big;
+    key[h] = (rel << 6) | (unsigned)(2 * lane + h);
+  }
 #pragma unroll
-        for (int k = 0; k < 3; ++k)
-          red_add4(g + ((long long)j * nz + k) * 4, ax[j * 3 + k], ay[j * 3 + k], az[j * 3 + k], am[j * 3 + k]);
-    }
+  for (int k = 2; k <= P2G_WINDOW; k <<= 1) {
 #pragma unroll
-    for (int e = 0; e < 9; ++e) ax[e] = ay[e] = az[e] = am[e] = (T)0;
-  };
-  for (; t < t_end; ++t) {
-    const int slab = t >= 2 * cnt ? 2 : (t >= cnt ? 1 : 0);
-    const int qi = t - slab * cnt;
-    const int node = S.node0[qi];
-    if (node != cur_node || slab != li) {
-      flush();
-      cur_node = node;
-      li = slab;
-      ci = (T)li;
-      // B-spline piece of this slab along x: w = s * (f - c)^2 + o  (three_d/p2g.py:55)
-      sx = li == 1 ? (T)-1 : (T)0.5; cx_ = (T)1.5 - (T)0.5 * ci; ox_ = li == 1 ? (T)0.75 : (T)0;
-    }
-    if (node < 0) continue;      // outside the grid: contributes nothing
-    const int ph = p2g_pad(qi);
-    const P2GVec4<T> p0 = S.pay[0][ph], p1 = S.pay[1][ph], p2 = S.pay[2][ph], p3 = S.pay[3][ph];
-    const T fx = p1.w, fy = p2.w, fz = p3.w;
-    T wy[3], wz[3];
-    bspline(fy, wy[0], wy[1], wy[2]);
-    bspline(fz, wz[0], wz[1], wz[2]);
-    const T tx_ = fx - cx_;
-    const T wxi = sx * tx_ * tx_ + ox_;
-    const T dpx = ci - fx;
-    const T bx = p0.x + p1.x * dpx, by = p0.y + p2.x * dpx, bz = p0.z + p3.x * dpx;
-    const T dz[3] = {-fz, (T)1 - fz, (T)2 - fz};
+    for (int j = k >> 1; j >= 1; j >>= 1) {
+      if (j == 1) {
+        // partner = the lane's other element; ascending iff bit k of the element index is clear
+        const bool up = ((2 * lane) & k) == 0;
+        const unsigned a = min(key[0], key[1]), b = max(key[0], key[1]);
+        key[0] = up ? a : b;
+        key[1] = up ? b : a;
+      } else {
+        const int lj = j >> 1;                                         // partner lane distance
+        const bool lower = (lane & lj) == 0;                           // this lane holds the lower element index
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const T dpy = (T)j - fy;
-      const T wij = wxi * wy[j];
-      const T cxj = bx + p1.y * dpy, cyj = by + p2.y * dpy, czj = bz + p3.y * dpy;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const T w = wij * wz[k];
-        ax[j * 3 + k] += w * (cxj + p1.z * dz[k]);
-        ay[j * 3 + k] += w * (cyj + p2.z * dz[k]);
-        az[j * 3 + k] += w * (czj + p3.z * dz[k]);
-        am[j * 3 + k] += w * p0.w;
+        for (int h = 0; h < 2; ++h) {
+          const unsigned other = __shfl_xor_sync(0xffffffffu, key[h], lj);
+          const bool up = ((2 * lane + h) & k) == 0;
+          key[h] = (lower == up) ? min(key[h], other) : max(key[h], other);
+        }
       }
     }
   }
-  flush();
+  // sorted position 2l + h holds key[h]
+  S.order[2 * lane] = (unsigned char)(key[0] & 63u);
+  S.order[2 * lane + 1] = (unsigned char)(key[1] & 63u);
+  const unsigned c0 = key[0] >> 6, c1 = key[1] >> 6;
+  unsigned prev = __shfl_up_sync(0xffffffffu, c1, 1);
+  if (lane == 0) prev = 0xffffffffu;
+  // elements past `cnt` carry the `big` key and sort behind everything: position < cnt <=> a real particle
+  const unsigned h0 = __ballot_sync(0xffffffffu, 2 * lane < cnt && c0 != prev);
+  const unsigned h1 = __ballot_sync(0xffffffffu, 2 * lane + 1 < cnt && c1 != c0);
+  const unsigned below = (1u << lane) - 1u;
+  const int r_lo = __popc(h0 & below) + __popc(h1 & below);
+  const unsigned mine0 = (h0 >> lane) & 1u, mine1 = (h1 >> lane) & 1u;
+  if (mine0) S.run_start[r_lo] = 2 * lane;
+  if (mine1) S.run_start[r_lo + mine0] = 2 * lane + 1;
+  const int n_runs = __popc(h0) + __popc(h1);
+  if (lane == 0) S.run_start[n_runs] = cnt;
+  return n_runs;
 }
 
 // Runs + phase 2 over a parked window (call after a __syncwarp() that follows phase 1); lane l owns the
