@@ -82,7 +82,11 @@ PROTOTYPES = {
 
 def load_library(path: str = "") -> C.CDLL:
     # FEMFLOW_MPM_LIB: load another build of the same ABI (A/B runs of kernel variants on one box)
-    path = path or os.environ.get("FEMFLOW_MPM_LIB") or LIBPATH
+    override = os.environ.get("FEMFLOW_MPM_LIB")
+    if not path and override:
+        import sys
+        print(f"femflow_b200: loading the CUDA library from FEMFLOW_MPM_LIB={override} instead of {LIBPATH}", file=sys.stderr)
+    path = path or override or LIBPATH
     if not os.path.exists(path):
         raise ImportError(
             f"{path} is missing: the femflow_b200 CUDA library has not been built. "

@@ -120,6 +120,9 @@ class MPMSimulation(SimulationBase):
                                 capacity=max(n, 1), dx=self.dx, inv_dx=self.inv_dx, dtype=tdtype, device=self.device)
         self.solver.set_particles(self.particles.pos, self.v, self.F, self.C, None, self.particles.mass,
                                   self.particles.mu_0, self.particles.lambda_0)
+        # the uploads above ran on this thread's current stream; the substeps run on a stream of the simulation thread
+        # (start()): make the state visible to whatever stream comes next
+        torch.cuda.synchronize(self.solver.device)
         self.loaded = True
         logger.success("Simulation loaded")
 
