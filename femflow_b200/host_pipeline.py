@@ -64,7 +64,7 @@ class HostSubstepPipeline:
         n = host_in["x"].shape[-1]
         run = torch.cuda.current_stream(s.device)
         if self._saved is None:
-            self._saved = (list(s.buffers), s.num_particles)
+            self._saved = (list(s.buffers), s.num_particles, s.live_index)
         with torch.cuda.stream(self.s_in):
             if not first:
                 self.s_in.wait_event(self.drained[j])          # the slot's previous result has left the device
@@ -101,6 +101,6 @@ class HostSubstepPipeline:
             ev.synchronize()
         if self._saved is not None:
             s = self.solver
-            s.buffers, n = self._saved
-            s._bind(n)
+            s.buffers, n, live = self._saved
+            s._bind(n, cur=live)                 # the buffer that held the solver's own live state is live again
             self._saved = None

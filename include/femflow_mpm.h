@@ -22,6 +22,15 @@
  *                      femflow/solvers/mpm/three_d/grid_op.py:50-67  check_collision_points
  *   ffmpm_scatter / ffmpm_gather / ffmpm_grid_op_halo
  *                      (new) the halves of a substep around the grid update, for slab drivers
+ *   ffmpm_migrate_pack / ffmpm_migrate_unpack / ffmpm_set_owned_range / ffmpm_set_owned_slack
+ *                      (new) slab ownership by base cell (three_d/p2g.py:50) and particle hand-over between slabs
+ *   ffmpm_export_state (new) the live state back in the caller's particle order: the reference updates the caller's
+ *                      arrays in place, particle i stays particle i (three_d/g2p.py:43-59)
+ *   ffmpm_gen_implicit_points / ffmpm_gen_cube_points
+ *                      femflow/simulation/mpm/primitives.py:46-76, numerics/geometry.py:101-116 (scene generators)
+ *   ffmpm_g2p with model = FFMPM_SNOW in 3D is REFUSED (FFMPM_E_INVALID): three_d/g2p.py:48-58 multiplies by Vh^T of a
+ *                      LAPACK SVD, so its result depends on LAPACK's singular-vector signs; the reference's own driver
+ *                      never reaches it (mls_mpm.py:58).  2D snow and the 3D snow hardening of P2G are implemented.
  *
  * Conventions
  *   - Plain C, no torch types.  All array arguments are DEVICE pointers owned by

@@ -571,6 +571,55 @@ def test_dense_cells_vs_oracle(ppc_side):
     s.close()
 
 
+@pytest.mark.parametrize("substeps", [1, 2])
+def test_host_pipeline_returns_callers_order(substeps):
+    """femflow_b200.host_pipeline.HostSubstepPipeline: seven independent host-side states through three device slots
+    (uploads under downloads), every result in the CALLER's particle order (ffmpm_export_state undoes the cell sort),
+    equal to the blocking path (set_particles -> substep -> get_particles) up to the order of the grid atomics, and to
+    the oracle within the bar; the solver gets its own buffers back."""
+    from femflow_b200 import scenes
+    from femflow_b200.host_pipeline import HostSubstepPipeline
+    from femflow_b200.mpm import MpmSolver
+    from oracle import native as ON
+    sc = scenes.elastic_block(3, 64, 16, 2, seed=2)
+    n = sc.n
+    rng = np.random.default_rng(2)
+    order = rng.permutation(n)                       # the caller's order is NOT cell order
+    s = MpmSolver(3, sc.res, sc.dt, sc.volume, sc.gravity, sc.hardening, capacity=n)
+    s.set_particles(sc.x[order], sc.v[order], sc.F[order], sc.C[order], None, sc.mass, sc.mu_0, sc.lambda_0)
+    s.substep(1)
+    own = {k: t.clone() for k, t in s.get_particles().items()}
+    calls = []
+    for k in range(7):
+        x = (sc.x[order] + np.float32(0.002 * k)).astype(np.float32)
+        v = (sc.v[order] * np.float32(1 + 0.1 * k)).astype(np.float32)
+        calls.append((x, v, sc.F[order], sc.C[order]))
+
+    def soa(a):
+        return torch.from_numpy(np.ascontiguousarray(a.reshape(n, -1).T)).pin_memory()
+    ins = [{"x": soa(x), "v": soa(v), "F": soa(F), "C": soa(C)} for x, v, F, C in calls]
+    outs = [{k: torch.empty_like(t).pin_memory() for k, t in d.items()} for d in ins]
+    pipe = HostSubstepPipeline(s, depth=3, substeps_per_call=substeps)
+    for d_in, d_out in zip(ins, outs):
+        pipe.submit(d_in, d_out)
+    pipe.drain()
+    back = s.get_particles()
+    for k in own:
+        assert torch.equal(own[k], back[k]), k               # the solver's own state is untouched
+    m = np.full(n, sc.mass); mu = np.full(n, sc.mu_0); lam = np.full(n, sc.lambda_0)
+    for (x, v, F, C), d_out in zip(calls, outs):
+        xo, vo, Fo, Co = (a.astype(np.float64) for a in (x, v, F, C))
+        for _ in range(substeps):
+            ON.solve_mls_mpm_3d(sc.res, float(sc.res), sc.hardening, 1 / sc.res, sc.dt, sc.volume, sc.gravity, xo, m, mu, lam, vo, Fo, Co)
+        V = max(np.abs(vo).max(), sc.dt * 9.8)
+        got = {k: t.numpy().T.astype(np.float64) for k, t in d_out.items()}
+        assert rel_err(got["x"], xo, 1.0) < 1e-5 * substeps
+        assert np.abs(got["v"] - vo).max() / V < 1e-5 * substeps
+        assert rel_err(got["F"].reshape(n, 3, 3), Fo, 1.0) < 1e-5 * substeps
+        assert np.abs(got["C"].reshape(n, 3, 3) - Co).max() / (4 * sc.res * V) < 1e-5 * substeps
+    s.close()
+
+
 def test_graph_replay_matches_eager_substeps():
     """MpmSolver.make_graph: 3 replays of a captured pair of substeps (internal binning stream and both
     ping-pong halves inside the capture) against the same 6 substeps launched one by one, from the same
