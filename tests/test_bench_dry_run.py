@@ -90,12 +90,13 @@ class FakeSolver:
         FakeSolver.instances.append(self)
 
     live = property(lambda self: self.buffers[self._live])
+    live_index = property(lambda self: self._live)
 
     def set_particles(self, x, *a, **k):
         self.num_particles = len(x)
 
     def _bind(self, n, cur=0):
-        self.num_particles, self._live, self.binds = n, 0, self.binds + 1
+        self.num_particles, self._live, self.binds = n, cur, self.binds + 1
 
     def substep(self, n=1):
         self.steps_run += n
