@@ -120,58 +120,6 @@ p2g_runs2_kernel(DevCfg cfg, StateView<T> s, long long n, T* __restrict__ grid, 
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// G2P of one 2D particle (two_d/g2p.py:17-47): shared by the in-place gather kernel and the reordering one.
-// ---------------------------------------------------------------------------------------------------------------
-template <typename T>
-struct G2POut2 {
-  T x0, x1, v0, v1, c00, c01, c10, c11, f00, f01, f10, f11, jp;
-};
-
-template <typename T>
-__device__ __forceinline__ void g2p_particle2(const DevCfg& cfg, const T* __restrict__ grid, int bx, int by, T fx, T fy, T x0, T x1,
-                                              T f00, T f01, T f10, T f11, T jp_in, bool has_jp, G2POut2<T>& o) {
-  T wx[3], wy[3];
-  bspline(fx, wx[0], wx[1], wx[2]);
-  bspline(fy, wy[0], wy[1], wy[2]);
-  const long long ny = cfg.n[1];
-  T vx = 0, vy = 0, c00 = 0, c01 = 0, c10 = 0, c11 = 0;
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const T dpx = (T)i - fx;
-    const T* row = grid + ((long long)(bx + i) * ny + by) * 4;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const T dpy = (T)j - fy;
-      const T w = wx[i] * wy[j];
-      const auto g = ld_node(row + 4 * j);
-      const T ux = w * g.x, uy = w * g.y;
-      vx += ux; vy += uy;
-      c00 += ux * dpx; c01 += ux * dpy; c10 += uy * dpx; c11 += uy * dpy;
-    }
-  }
-  const T s4 = (T)(4.0 * cfg.inv_dx);
-  c00 *= s4; c01 *= s4; c10 *= s4; c11 *= s4;
-  const T dt = (T)cfg.dt;
-  const T m00 = (T)1 + dt * c00, m01 = dt * c01, m10 = dt * c10, m11 = (T)1 + dt * c11;
-  Mat2<double> Fn;
-  Fn.a00 = m00 * f00 + m01 * f10; Fn.a01 = m00 * f01 + m01 * f11;
-  Fn.a10 = m10 * f00 + m11 * f10; Fn.a11 = m10 * f01 + m11 * f11;
-  // two_d/g2p.py:37-47: SVD round trip and Jp update for every model (quirk 7)
-  const double old_J = Fn.a00 * Fn.a11 - Fn.a01 * Fn.a10;
-  double det_new;
-  const Mat2<double> Fr = svd_roundtrip2(Fn, cfg.model == 1, det_new);
-  o.jp = jp_in;
-  if (has_jp) {
-    const double jp = (double)jp_in * old_J / (det_new + 1e-10);
-    o.jp = (T)fmin(fmax(jp, 0.6), 20.0);
-  }
-  o.f00 = (T)Fr.a00; o.f01 = (T)Fr.a01; o.f10 = (T)Fr.a10; o.f11 = (T)Fr.a11;
-  o.c00 = c00; o.c01 = c01; o.c10 = c10; o.c11 = c11;
-  o.v0 = vx; o.v1 = vy;
-  o.x0 = x0 + dt * vx; o.x1 = x1 + dt * vy;
-}
-
 template <typename T>
 __global__ void __launch_bounds__(256) g2p_reorder2_kernel(DevCfg cfg, StateView<T> src, StateView<T> dst, long long n, BinBuffers B,
                                                            const T* __restrict__ grid, ErrRec* err) {

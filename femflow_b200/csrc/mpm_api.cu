@@ -404,8 +404,11 @@ static int p2g_t(FfMpmHandle* h, cudaStream_t s) {
   unsigned blocks = (unsigned)((h->n + 127) / 128);
   if (h->cfg.dim == 3)
     p2g_scatter3_kernel<T><<<blocks, 128, 0, s>>>(h->dev, sv, h->n, (T*)h->grid, h->err);
-  else
-    p2g_scatter2_kernel<T><<<blocks, 128, 0, s>>>(h->dev, sv, h->n, (T*)h->grid, h->err);
+  else {
+    static const bool nored = getenv("FFMPM_DEBUG_NORED") != nullptr;   // measurement only: WRONG results
+    if (nored) p2g_scatter2_kernel<T, true><<<blocks, 128, 0, s>>>(h->dev, sv, h->n, (T*)h->grid, h->err);
+    else p2g_scatter2_kernel<T><<<blocks, 128, 0, s>>>(h->dev, sv, h->n, (T*)h->grid, h->err);
+  }
   return check_launch(h, 1);
 }
 

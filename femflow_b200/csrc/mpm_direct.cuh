@@ -132,12 +132,26 @@ __device__ __forceinline__ P2GParticle2<T> p2g_prepare2(const DevCfg& cfg, const
   double e = cfg.hardening;
   if (cfg.model == 1) e = exp(cfg.hardening * (1.0 - (double)s.Jp[p]));
   mu *= e; lam *= e;
-  Mat2<double> F, C;
-  F.a00 = s.F[p]; F.a01 = s.F[st + p]; F.a10 = s.F[2 * st + p]; F.a11 = s.F[3 * st + p];
-  C.a00 = s.C[p]; C.a01 = s.C[st + p]; C.a10 = s.C[2 * st + p]; C.a11 = s.C[3 * st + p];
-  double k = (cfg.dt * cfg.volume) * (4.0 * cfg.inv_dx * cfg.inv_dx);
-  Mat2<double> A = fixed_corotated_affine2(F, C, mu, lam, mass, k);
-  q.a00 = (T)A.a00; q.a01 = (T)A.a01; q.a10 = (T)A.a10; q.a11 = (T)A.a11;
+  const double k = (cfg.dt * cfg.volume) * (4.0 * cfg.inv_dx * cfg.inv_dx);
+  const T f00 = s.F[p], f01 = s.F[st + p], f10 = s.F[2 * st + p], f11 = s.F[3 * st + p];
+  const T c00 = s.C[p], c01 = s.C[st + p], c10 = s.C[2 * st + p], c11 = s.C[3 * st + p];
+  bool done = false;
+  if constexpr (sizeof(T) == 4) {
+    // fp32 build: the cancellation-free closed form (mpm_math.cuh), the reference's 1e-10 restored analytically
+    if (cfg.fp32_stress) {
+      Mat2<float> Af;
+      done = fixed_corotated_affine2_f32(Mat2<float>{f00, f01, f10, f11}, Mat2<float>{c00, c01, c10, c11}, (float)mu, (float)lam,
+                                         (float)mass, (float)k, Af);
+      if (done) { q.a00 = Af.a00; q.a01 = Af.a01; q.a10 = Af.a10; q.a11 = Af.a11; }
+    }
+  }
+  if (!done) {
+    Mat2<double> F, C;
+    F.a00 = f00; F.a01 = f01; F.a10 = f10; F.a11 = f11;
+    C.a00 = c00; C.a01 = c01; C.a10 = c10; C.a11 = c11;
+    Mat2<double> A = fixed_corotated_affine2(F, C, mu, lam, mass, k);
+    q.a00 = (T)A.a00; q.a01 = (T)A.a01; q.a10 = (T)A.a10; q.a11 = (T)A.a11;
+  }
   q.m = (T)mass;
   q.mvx = (T)(mass * (double)s.v[p]); q.mvy = (T)(mass * (double)s.v[st + p]);
   return q;
@@ -180,7 +194,7 @@ __global__ void __launch_bounds__(128) p2g_scatter3_kernel(DevCfg cfg, StateView
   }
 }
 
-template <typename T>
+template <typename T, bool NORED = false>
 __global__ void __launch_bounds__(128) p2g_scatter2_kernel(DevCfg cfg, StateView<T> s, long long n, T* __restrict__ grid,
                                                            ErrRec* err) {
   long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -202,7 +216,11 @@ __global__ void __launch_bounds__(128) p2g_scatter2_kernel(DevCfg cfg, StateView
       T w = wx[i] * wy[j];
       T mx = q.mvx + (q.a00 * dpx + q.a01 * dpy);
       T my = q.mvy + (q.a10 * dpx + q.a11 * dpy);
-      red_add4(row + 4 * j, w * mx, w * my, w * q.m, (T)0);
+      if (NORED) {   // measurement only (FFMPM_DEBUG_NORED): the same arithmetic, the reductions never issued
+        if (w * mx == (T)123456.789) red_add4(row + 4 * j, w * mx, w * my, w * q.m, (T)0);
+      } else {
+        red_add4(row + 4 * j, w * mx, w * my, w * q.m, (T)0);
+      }
     }
   }
 }
@@ -441,6 +459,74 @@ __global__ void __launch_bounds__(128) g2p_gather3_kernel(DevCfg cfg, StateView<
   s.x[p] = x0 + dt * vx; s.x[st + p] = x1 + dt * vy; s.x[2 * st + p] = x2 + dt * vz;
 }
 
+// ----------------------------------------------------------------------------
+// G2P of one 2D particle (two_d/g2p.py:17-47): shared by the in-place gather kernel and the reordering one.
+// ----------------------------------------------------------------------------
+template <typename T>
+struct G2POut2 {
+  T x0, x1, v0, v1, c00, c01, c10, c11, f00, f01, f10, f11, jp;
+};
+
+template <typename T>
+__device__ __forceinline__ void g2p_particle2(const DevCfg& cfg, const T* __restrict__ grid, int bx, int by, T fx, T fy, T x0, T x1,
+                                              T f00, T f01, T f10, T f11, T jp_in, bool has_jp, G2POut2<T>& o) {
+  T wx[3], wy[3];
+  bspline(fx, wx[0], wx[1], wx[2]);
+  bspline(fy, wy[0], wy[1], wy[2]);
+  const long long ny = cfg.n[1];
+  T vx = 0, vy = 0, c00 = 0, c01 = 0, c10 = 0, c11 = 0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const T dpx = (T)i - fx;
+    const T* row = grid + ((long long)(bx + i) * ny + by) * 4;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const T dpy = (T)j - fy;
+      const T w = wx[i] * wy[j];
+      const auto g = ld_node(row + 4 * j);
+      const T ux = w * g.x, uy = w * g.y;
+      vx += ux; vy += uy;
+      c00 += ux * dpx; c01 += ux * dpy; c10 += uy * dpx; c11 += uy * dpy;
+    }
+  }
+  const T s4 = (T)(4.0 * cfg.inv_dx);
+  c00 *= s4; c01 *= s4; c10 *= s4; c11 *= s4;
+  const T dt = (T)cfg.dt;
+  const T m00 = (T)1 + dt * c00, m01 = dt * c01, m10 = dt * c10, m11 = (T)1 + dt * c11;
+  const T n00 = m00 * f00 + m01 * f10, n01 = m00 * f01 + m01 * f11, n10 = m10 * f00 + m11 * f10, n11 = m10 * f01 + m11 * f11;
+  o.jp = jp_in;
+  bool done = false;
+  if constexpr (sizeof(T) == 4) {
+    // two_d/g2p.py:37-47 for det F > 0 without plasticity: U diag(sig) Vh^T is F itself (LAPACK's 2x2 Vh is symmetric
+    // there), and Jp <- clip(Jp * J / (J + 1e-10)): no SVD, no fp64 in the fp32 build.  det F <= 0
+    // (the V.T quirk rotates F) and snow (singular values clamped) take the closed forms of svd_roundtrip2 in fp64.
+    // "safely positive": the fp32 determinant cannot have the wrong sign when it exceeds 1e-3 of its own terms
+    const float p0 = n00 * n11, p1 = n01 * n10;
+    const float old_J = p0 - p1;
+    if (cfg.model != 1 && old_J > 1e-3f * (fabsf(p0) + fabsf(p1))) {
+      o.f00 = n00; o.f01 = n01; o.f10 = n10; o.f11 = n11;
+      if (has_jp) o.jp = fminf(fmaxf(jp_in * (old_J / (old_J + 1e-10f)), 0.6f), 20.0f);
+      done = true;
+    }
+  }
+  if (!done) {
+    Mat2<double> Fn;
+    Fn.a00 = n00; Fn.a01 = n01; Fn.a10 = n10; Fn.a11 = n11;
+    // two_d/g2p.py:37-47: SVD round trip and Jp update for every model (quirk 7)
+    const double old_J = Fn.a00 * Fn.a11 - Fn.a01 * Fn.a10;
+    double det_new;
+    const Mat2<double> Fr = svd_roundtrip2(Fn, cfg.model == 1, det_new);
+    if (has_jp) {
+      const double jp = (double)jp_in * old_J / (det_new + 1e-10);
+      o.jp = (T)fmin(fmax(jp, 0.6), 20.0);
+    }
+    o.f00 = (T)Fr.a00; o.f01 = (T)Fr.a01; o.f10 = (T)Fr.a10; o.f11 = (T)Fr.a11;
+  }
+  o.c00 = c00; o.c01 = c01; o.c10 = c10; o.c11 = c11;
+  o.v0 = vx; o.v1 = vy;
+  o.x0 = x0 + dt * vx; o.x1 = x1 + dt * vy;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(128) g2p_gather2_kernel(DevCfg cfg, StateView<T> s, long long n, const T* __restrict__ grid,
                                                           ErrRec* err) {
@@ -455,45 +541,14 @@ __global__ void __launch_bounds__(128) g2p_gather2_kernel(DevCfg cfg, StateView<
   int bx = gx - cfg.origin[0], by = gy - cfg.origin[1];
   bool ok = !(isnan((double)x0) || isnan((double)x1)) && bx >= 0 && by >= 0 && bx + 2 < cfg.n[0] && by + 2 < cfg.n[1];
   if (!ok) { atomicAdd(&err->n_oob, 1ULL); return; }
-  T wx[3], wy[3];
-  bspline(fx, wx[0], wx[1], wx[2]);
-  bspline(fy, wy[0], wy[1], wy[2]);
-  const long long ny = cfg.n[1];
-  T vx = 0, vy = 0, c00 = 0, c01 = 0, c10 = 0, c11 = 0;
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    T dpx = (T)i - fx;
-    const T* row = grid + ((long long)(bx + i) * ny + by) * 4;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      T dpy = (T)j - fy;
-      T w = wx[i] * wy[j];
-      auto g = ld_node(row + 4 * j);
-      T ux = w * g.x, uy = w * g.y;
-      vx += ux; vy += uy;
-      c00 += ux * dpx; c01 += ux * dpy; c10 += uy * dpx; c11 += uy * dpy;
-    }
-  }
-  const T s4 = (T)(4.0 * cfg.inv_dx);
-  c00 *= s4; c01 *= s4; c10 *= s4; c11 *= s4;
-  const T dt = (T)cfg.dt;
-  T f00 = s.F[p], f01 = s.F[st + p], f10 = s.F[2 * st + p], f11 = s.F[3 * st + p];
-  T m00 = (T)1 + dt * c00, m01 = dt * c01, m10 = dt * c10, m11 = (T)1 + dt * c11;
-  Mat2<double> Fn;
-  Fn.a00 = m00 * f00 + m01 * f10; Fn.a01 = m00 * f01 + m01 * f11;
-  Fn.a10 = m10 * f00 + m11 * f10; Fn.a11 = m10 * f01 + m11 * f11;
-  // two_d/g2p.py:37-47: SVD round trip and Jp update for every model (quirk 7)
-  double old_J = Fn.a00 * Fn.a11 - Fn.a01 * Fn.a10;
-  double det_new;
-  Mat2<double> Fr = svd_roundtrip2(Fn, cfg.model == 1, det_new);
-  if (s.Jp) {
-    double jp = (double)s.Jp[p] * old_J / (det_new + 1e-10);
-    s.Jp[p] = (T)fmin(fmax(jp, 0.6), 20.0);
-  }
-  s.F[p] = (T)Fr.a00; s.F[st + p] = (T)Fr.a01; s.F[2 * st + p] = (T)Fr.a10; s.F[3 * st + p] = (T)Fr.a11;
-  s.C[p] = c00; s.C[st + p] = c01; s.C[2 * st + p] = c10; s.C[3 * st + p] = c11;
-  s.v[p] = vx; s.v[st + p] = vy;
-  s.x[p] = x0 + dt * vx; s.x[st + p] = x1 + dt * vy;
+  G2POut2<T> o;
+  g2p_particle2<T>(cfg, grid, bx, by, fx, fy, x0, x1, s.F[p], s.F[st + p], s.F[2 * st + p], s.F[3 * st + p],
+                   s.Jp ? s.Jp[p] : (T)1, s.Jp != nullptr, o);
+  if (s.Jp) s.Jp[p] = o.jp;
+  s.F[p] = o.f00; s.F[st + p] = o.f01; s.F[2 * st + p] = o.f10; s.F[3 * st + p] = o.f11;
+  s.C[p] = o.c00; s.C[st + p] = o.c01; s.C[2 * st + p] = o.c10; s.C[3 * st + p] = o.c11;
+  s.v[p] = o.v0; s.v[st + p] = o.v1;
+  s.x[p] = o.x0; s.x[st + p] = o.x1;
 }
 
 }  // namespace ffmpm

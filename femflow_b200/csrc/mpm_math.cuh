@@ -262,6 +262,41 @@ FFMPM_HD Mat2<double> fixed_corotated_affine2(const Mat2<double>& F, const Mat2<
   return A;
 }
 
+// The same in fp32 WITHOUT cancellation (fp32 build, 2D): every term is formed from E = F - I.
+//   x = F00 + F11 = 2 + tr E,  w = F10 - F01 = E10 - E01,  r = sqrt(x^2 + w^2),  R0 = [[x, -w], [w, x]] / r
+//   q = r - 2 = (r^2 - 4) / (r + 2) = (4 tr E + (tr E)^2 + w^2) / (r + 2)
+//   r (F - R0) = q F + D,  D = [[E00 - E11, E01 + E10], [E01 + E10, E11 - E00]]     (2 F - [[x, -w], [w, x]] = D)
+// so F - R0 is built from the strain-sized numbers q and D only: D is exact for a pure rotation (Sterbenz) and the
+// error of q is second order in the rotation angle -- no difference of O(1) (or O(angle)) numbers anywhere.
+//   The reference's  scale = 1 / (r + 1e-10)  (numerics/linear_algebra.py:108-113, quirks 3, 12) gives
+//   R = R0 (1 - e),  e = 1e-10 / (r + 1e-10),  so  F - R = (q F + D + e [[x, -w], [w, x]]) / r:
+// the spurious isotropic stress of the reference is ADDED analytically instead of being lost below fp32 resolution.
+//   J - 1 = tr E + det E.
+// Returns false when r is not safely positive (F close to a reflection, or NaN) -- the caller takes the fp64 form.
+// This removes a double-precision square root and division from the latency chain of every 2D particle.
+FFMPM_HD bool fixed_corotated_affine2_f32(const Mat2<float>& F, const Mat2<float>& C, float mu, float lam, float mass,
+                                          float dt_vol_dinv, Mat2<float>& A) {
+  const float e00 = F.a00 - 1.0f, e01 = F.a01, e10 = F.a10, e11 = F.a11 - 1.0f;
+  const float tr = e00 + e11, w = e10 - e01, sy = e10 + e01, dd = e00 - e11;
+  const float x = 2.0f + tr;
+  const float r = sqrtf(x * x + w * w);
+  if (!(r > 1e-3f)) return false;
+  const float inv_r = 1.0f / r;
+  const float q = (4.0f * tr + tr * tr + w * w) / (r + 2.0f);
+  const float e = 1e-10f / (r + 1e-10f);
+  const float ex = e * x, ew = e * w;
+  const float d00 = (q * F.a00 + dd + ex) * inv_r, d01 = (q * e01 + sy - ew) * inv_r;
+  const float d10 = (q * e10 + sy + ew) * inv_r, d11 = (q * F.a11 - dd + ex) * inv_r;
+  const float jm1 = tr + (e00 * e11 - e01 * e10);
+  const float l = lam * jm1 * (1.0f + jm1);        // lam (J-1) J, on ALL entries (quirk 2)
+  const float m2 = 2.0f * mu;
+  A.a00 = -dt_vol_dinv * (m2 * (d00 * F.a00 + d01 * F.a01) + l) + mass * C.a00;
+  A.a01 = -dt_vol_dinv * (m2 * (d00 * F.a10 + d01 * F.a11) + l) + mass * C.a01;
+  A.a10 = -dt_vol_dinv * (m2 * (d10 * F.a00 + d11 * F.a01) + l) + mass * C.a10;
+  A.a11 = -dt_vol_dinv * (m2 * (d10 * F.a10 + d11 * F.a11) + l) + mass * C.a11;
+  return true;
+}
+
 // 2x2 SVD round trip of two_d/g2p.py:37-43: F <- U diag(sig) Vh^T with (U, sig, Vh)
 // LAPACK's SVD and "V.T" applied to what is already Vh.  Measured convention of
 // dgesdd on 2x2 input (tests/golden/quirk2d.npz): U is always a reflection; Vh is a

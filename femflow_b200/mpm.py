@@ -9,6 +9,7 @@ the reference's fixed particle order.
 """
 from __future__ import annotations
 
+import os
 import ctypes as C
 from typing import Dict, Optional, Sequence
 
@@ -123,7 +124,7 @@ class MpmSolver:
             # 3D: binned pipeline, G2P writes the state back cell-sorted.  2D (1 M particles, state resident in L2) is
             # fastest unbinned (measured: profiles/r02e_g2p_packed_and_binned_2d_ab.json); the binned 2D pipeline stays
             # selectable with reorder=True
-            reorder = self.dim == 3 and p2g_mode != "scatter"
+            reorder = (self.dim == 3 or os.environ.get("FFMPM_2D_BINNED") == "1") and p2g_mode != "scatter"
         self.reorder = bool(reorder)
         cfg = N.FfMpmConfig()
         cfg.dim = self.dim

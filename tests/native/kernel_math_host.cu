@@ -138,6 +138,15 @@ void km_affine2(long long n, const double* F, const double* C, double mu, double
   }
 }
 
+// fp32 closed form of the 2D stress (fp32 build): 1 per particle where it accepted the strain
+void km_affine2_f32(long long n, const float* F, const float* C, float mu, float lam, float mass, float k, float* A, int* took) {
+  for (long long p = 0; p < n; ++p) {
+    Mat2<float> f{F[4 * p], F[4 * p + 1], F[4 * p + 2], F[4 * p + 3]}, c{C[4 * p], C[4 * p + 1], C[4 * p + 2], C[4 * p + 3]}, a{};
+    took[p] = fixed_corotated_affine2_f32(f, c, mu, lam, mass, k, a) ? 1 : 0;
+    A[4 * p] = a.a00; A[4 * p + 1] = a.a01; A[4 * p + 2] = a.a10; A[4 * p + 3] = a.a11;
+  }
+}
+
 void km_svd_roundtrip2(long long n, const double* F, int snow, double* G, double* det) {
   for (long long p = 0; p < n; ++p) {
     Mat2<double> f{F[4 * p], F[4 * p + 1], F[4 * p + 2], F[4 * p + 3]};

@@ -243,6 +243,51 @@ def test_2d_stress_and_svd_roundtrip(km):
         assert np.abs(det[sel] - np.linalg.det(wantG[sel])).max() < 1e-9, snow
 
 
+@pytest.mark.parametrize("angle", [0.0, 1e-3, 0.1, 1.4, 3.1])
+@pytest.mark.parametrize("strain", [0.0, 1e-7, 1e-5, 1e-3, 3e-2, 0.3, 1.2])
+def test_2d_fp32_closed_form_stress(km, strain, angle):
+    """The cancellation-free fp32 form of the 2D stress (fixed_corotated_affine2_f32: the default of the fp32 build)
+    against the fp64 oracle of utils.py:53-92 on the same fp32 inputs (C = 0, so nothing hides the stress): to 1e-5 of
+    the batch's largest stress entry, plus the fp32 resolution of the ROTATION, 4 eps angle^2 as a strain (the form
+    has no first-order sensitivity to the angle: a block rotated by 0.1 rad resolves strains of 5e-9) -- and the
+    reference's spurious 1e-10 stress at F = I (quirks 3, 12), which plain fp32 arithmetic would lose, to 1e-5 of
+    itself."""
+    rng = np.random.default_rng(21)
+    n = 6000
+    th = rng.uniform(-angle, angle, size=n)
+    R = np.stack([np.stack([np.cos(th), -np.sin(th)], -1), np.stack([np.sin(th), np.cos(th)], -1)], -2)
+    F = f32(R @ (np.eye(2) + strain * rng.uniform(-1, 1, size=(n, 2, 2))))
+    F[0] = np.eye(2)
+    Z = np.zeros((n, 2, 2))
+    mu, lam, mass, dt, vol, inv_dx = float(f32(4166.67)), float(f32(2777.78)), 1.0, 1e-4, 1.0, 1024.0
+    k = float(f32(dt * vol * 4 * inv_dx * inv_dx))
+    A = np.zeros((n, 4), np.float32); took = np.zeros(n, np.int32)
+    km.km_affine2_f32(C.c_longlong(n), ptr(np.ascontiguousarray(F.reshape(n, 4), dtype=np.float32)), ptr(np.zeros((n, 4), np.float32)),
+                      C.c_float(mu), C.c_float(lam), C.c_float(mass), C.c_float(k), ptr(A), ptr(took))
+    want = O.fixed_corotated_stress_2d(F, inv_dx, np.full(n, mu), np.full(n, lam), dt, vol, np.full(n, mass), Z)
+    want = want * (k / (dt * vol * 4 * inv_dx * inv_dx))
+    t = took.astype(bool)
+    assert t.mean() > 0.999                             # declines only next to a reflection (r < 1e-3)
+    scale = np.abs(want[t]).max()
+    floor = 2 * mu * k * 4 * np.finfo(np.float32).eps * angle ** 2
+    assert np.abs(A.reshape(n, 2, 2) - want)[t].max() < 1e-5 * scale + floor, (strain, angle)
+    # F = I: the reference's 1e-10 in the polar norm leaves a stress of 2 mu * 5e-11 on the diagonal
+    assert want[0, 0, 0] != 0 and abs(A[0, 0] - want[0, 0, 0]) < 1e-5 * abs(want[0, 0, 0])
+    assert abs(A[0, 1] - want[0, 0, 1]) < 1e-5 * abs(want[0, 0, 0])
+
+
+def test_2d_fp32_closed_form_declines_next_to_a_reflection(km):
+    """r = |(tr F, F10 - F01)| ~ 0 (F close to a reflection: the reference's own R degenerates to ~0 there) or NaN:
+    the closed form declines and the kernel takes the fp64 form."""
+    F = np.array([[[1.0, 0.0], [0.0, -1.0]], [[0.3, 0.7], [0.7, -0.3]], [[1.0, 0.0], [0.0, 1.0]], [[np.nan, 0.0], [0.0, 1.0]],
+                  [[-1.0, 0.0], [0.0, -1.0]]], np.float32)
+    n = len(F)
+    A = np.zeros((n, 4), np.float32); took = np.zeros(n, np.int32)
+    km.km_affine2_f32(C.c_longlong(n), ptr(np.ascontiguousarray(F.reshape(n, 4))), ptr(np.zeros((n, 4), np.float32)),
+                      C.c_float(1.0), C.c_float(1.0), C.c_float(1.0), C.c_float(1.0), ptr(A), ptr(took))
+    assert took.tolist() == [0, 0, 1, 0, 1]
+
+
 @pytest.mark.parametrize("dtype,tol", [("f32", 2e-6), ("f64", 1e-14)])
 def test_grid_update_walls_clamp_colliders_and_halo_sum(km, dtype, tol):
     """grid_op3_node, the body of every 3D grid-update kernel (three_d/grid_op.py:25-67): momentum -> velocity,
