@@ -1,8 +1,7 @@
 // The binned 2D pipeline: the architecture of the 3D one for two_d/{p2g,grid_op,g2p}.py, selectable with
 // MpmSolver(reorder=True).  At BASELINE configs[1] (1 M particles on 1024^2: 54 MB of state, resident in L2) it is SLOWER
-// than the thread-per-particle kernels of mpm_direct.cuh (88.7 us against 62.6 us per substep under CUDA-graph replay,
-// profiles/r02e_g2p_packed_and_binned_2d_ab.json), so those stay the 2D default; this path is for scenes whose state
-// does not fit L2.
+// than the unbinned kernels (86.8 us against 43.0 us per substep for the warp-window kernels of mpm_2d_window.cuh,
+// profiles/r02s_2d_series.json), so those stay the 2D default; this path is for scenes whose state does not fit L2.
 //   p2g_runs2_kernel     warp-autonomous P2G in physical order (two_d/p2g.py:49-76): lane per particle -> runs of equal
 //                        base cell -> lane per (run, x-slab) accumulating the slab's three nodes in registers -> ONE
 //                        vector RED per node and run;

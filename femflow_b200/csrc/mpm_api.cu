@@ -18,6 +18,7 @@
 #include "mpm_g2p2g.cuh"
 #include "mpm_migrate.cuh"
 #include "mpm_2d.cuh"
+#include "mpm_2d_window.cuh"
 #include "mpm_scene.cuh"
 
 using namespace ffmpm;
@@ -54,6 +55,7 @@ struct FfMpmHandle {
   bool grid_clean[2];  // known to be all-zero
   bool scatter_ahead;  // grids[grid_cur ^ 1] already holds P2G of the live state (fused G2P2G)
   int fuse;            // FFMPM_FUSE=0 disables the fused G2P2G kernel
+  int win2;            // 2D fp32, unbinned: warp-window kernels of mpm_2d_window.cuh (FFMPM_2D_WINDOW=0: thread per particle)
   int gg_blocks_per_sm;
   bool bin_pending;    // the binning of this substep is in flight on `aux` (ev_join)
   cudaStream_t aux;    // internal stream for work that overlaps the compute-bound P2G
@@ -168,6 +170,8 @@ int ffmpm_create(const FfMpmConfig* cfg, int32_t device, FfMpmHandle** out) {
   // separate kernels whose binning/clear additionally hide under P2G, so it is not the default.
   h->fuse = cfg->p2g_mode == FFMPM_P2G_FUSED ? 1 : 0;
   if (const char* e = getenv("FFMPM_FUSE")) h->fuse = atoi(e) != 0;
+  h->win2 = 1;
+  if (const char* e = getenv("FFMPM_2D_WINDOW")) h->win2 = atoi(e) != 0;
   h->gg_blocks_per_sm = 4;
   if (const char* e = getenv("FFMPM_GG_BPS")) { int v = atoi(e); if (v > 0 && v <= 32) h->gg_blocks_per_sm = v; }
   {
@@ -401,14 +405,18 @@ static int p2g_t(FfMpmHandle* h, cudaStream_t s) {
     int nl = p2g_runs<T>(h->dev, sv, h->n, h->bin, (T*)h->grid, h->err, h->sm_count, h->p2g_blocks_per_sm, use_perm, s);
     return check_launch(h, nl);
   }
+  if constexpr (sizeof(T) == 4) {
+    if (h->win2 && w2_eligible(h->dev, sv)) {
+      if (!p2g_window2_launch(h->dev, sv, h->n, (T*)h->grid, h->err, h->sm_count, s))
+        return set_err(FFMPM_E_CUDA, "could not configure the 2D window P2G kernel");
+      return check_launch(h, 1);
+    }
+  }
   unsigned blocks = (unsigned)((h->n + 127) / 128);
   if (h->cfg.dim == 3)
     p2g_scatter3_kernel<T><<<blocks, 128, 0, s>>>(h->dev, sv, h->n, (T*)h->grid, h->err);
-  else {
-    static const bool nored = getenv("FFMPM_DEBUG_NORED") != nullptr;   // measurement only: WRONG results
-    if (nored) p2g_scatter2_kernel<T, true><<<blocks, 128, 0, s>>>(h->dev, sv, h->n, (T*)h->grid, h->err);
-    else p2g_scatter2_kernel<T><<<blocks, 128, 0, s>>>(h->dev, sv, h->n, (T*)h->grid, h->err);
-  }
+  else
+    p2g_scatter2_kernel<T><<<blocks, 128, 0, s>>>(h->dev, sv, h->n, (T*)h->grid, h->err);
   return check_launch(h, 1);
 }
 
@@ -445,8 +453,18 @@ static int grid_op_t(FfMpmHandle* h, cudaStream_t s, const void* halo_lo = nullp
   } else if (h->cfg.dim == 3)
     grid_op3_kernel<T><<<blocks, 256, 0, s>>>(h->dev, (T*)h->grid, h->n_nodes, (const T*)halo_lo, nodes_lo,
                                                (const T*)halo_hi, nodes_hi, h->colliders);
-  else
-    grid_op2_kernel<T><<<blocks, 256, 0, s>>>(h->dev, (T*)h->grid, h->n_nodes);
+  else {
+    // 2D, dense: the same pass zeroes the IDLE grid (last read by the previous substep's G2P), which the next
+    // ffmpm_scatter then switches to -- no separate clear on the critical path of a 2D substep
+    const int idle = h->grid_cur ^ 1;
+    T* clear = nullptr;
+    if (h->win2 && !h->grid_clean[idle]) {
+      clear = (T*)h->grids[idle];
+      h->grid_clean[idle] = true;
+      h->grid_listed[idle] = false;
+    }
+    grid_op2_kernel<T><<<blocks, 256, 0, s>>>(h->dev, (T*)h->grid, h->n_nodes, clear);
+  }
   return check_launch(h, 1);
 }
 
@@ -493,13 +511,20 @@ static int g2p_t(FfMpmHandle* h, cudaStream_t s) {
     h->prebinned = true;  // ... but keys, ranks and the histogram of the new live buffer are ready
     return check_launch(h, nl);
   }
+  h->binned = false;
+  h->prebinned = false;
+  if constexpr (sizeof(T) == 4) {
+    if (h->win2 && w2_eligible(h->dev, sv)) {
+      if (!g2p_window2_launch(h->dev, sv, h->n, (const T*)h->grid, h->err, h->sm_count, s))
+        return set_err(FFMPM_E_CUDA, "could not configure the 2D window G2P kernel");
+      return check_launch(h, 1);
+    }
+  }
   unsigned blocks = (unsigned)((h->n + 127) / 128);
   if (h->cfg.dim == 3)
     g2p_gather3_kernel<T><<<blocks, 128, 0, s>>>(h->dev, sv, h->n, (const T*)h->grid, h->err);
   else
     g2p_gather2_kernel<T><<<blocks, 128, 0, s>>>(h->dev, sv, h->n, (const T*)h->grid, h->err);
-  h->binned = false;
-  h->prebinned = false;
   return check_launch(h, 1);
 }
 

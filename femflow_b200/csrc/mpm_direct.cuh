@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(128) p2g_scatter3_kernel(DevCfg cfg, StateView
   }
 }
 
-template <typename T, bool NORED = false>
+template <typename T>
 __global__ void __launch_bounds__(128) p2g_scatter2_kernel(DevCfg cfg, StateView<T> s, long long n, T* __restrict__ grid,
                                                            ErrRec* err) {
   long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -216,11 +216,7 @@ __global__ void __launch_bounds__(128) p2g_scatter2_kernel(DevCfg cfg, StateView
       T w = wx[i] * wy[j];
       T mx = q.mvx + (q.a00 * dpx + q.a01 * dpy);
       T my = q.mvy + (q.a10 * dpx + q.a11 * dpy);
-      if (NORED) {   // measurement only (FFMPM_DEBUG_NORED): the same arithmetic, the reductions never issued
-        if (w * mx == (T)123456.789) red_add4(row + 4 * j, w * mx, w * my, w * q.m, (T)0);
-      } else {
-        red_add4(row + 4 * j, w * mx, w * my, w * q.m, (T)0);
-      }
+      red_add4(row + 4 * j, w * mx, w * my, w * q.m, (T)0);
     }
   }
 }
@@ -346,11 +342,17 @@ __global__ void __launch_bounds__(256) collide3_kernel(DevCfg cfg, T* __restrict
 
 // 2D (two_d/grid_op.py:13-24): only nodes with mass > 0; walls are f64 predicates on
 // i/R against 0.05 and 1-0.05, evaluated here in f64 exactly as the reference (quirk 6).
+// `clear` (optional): a second grid of the same shape that this pass zeroes on the way (the idle one of the ping-pong pair).
 template <typename T>
-__global__ void __launch_bounds__(256) grid_op2_kernel(DevCfg cfg, T* __restrict__ grid, long long n_nodes) {
+__global__ void __launch_bounds__(256) grid_op2_kernel(DevCfg cfg, T* __restrict__ grid, long long n_nodes, T* __restrict__ clear) {
   long long node = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (node >= n_nodes) return;
   using V4 = typename Vec4<T>::type;
+  if (clear) {
+    V4 z;
+    z.x = z.y = z.z = z.w = (T)0;
+    reinterpret_cast<V4*>(clear)[node] = z;
+  }
   V4 g = reinterpret_cast<V4*>(grid)[node];
   if (!(g.z > (T)0)) return;
   int j = (int)(node % cfg.n[1]);

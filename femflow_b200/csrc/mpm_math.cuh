@@ -279,11 +279,22 @@ FFMPM_HD bool fixed_corotated_affine2_f32(const Mat2<float>& F, const Mat2<float
   const float e00 = F.a00 - 1.0f, e01 = F.a01, e10 = F.a10, e11 = F.a11 - 1.0f;
   const float tr = e00 + e11, w = e10 - e01, sy = e10 + e01, dd = e00 - e11;
   const float x = 2.0f + tr;
-  const float r = sqrtf(x * x + w * w);
+  const float s2 = x * x + w * w;
+#ifdef __CUDA_ARCH__
+  // device: the approximate unit (MUFU.RSQ / MUFU.RCP, 2 ulp) -- every quantity formed with them is strain-sized or
+  // multiplies one, so 2e-7 relative is far inside the 1e-5 bar; IEEE sqrt and three IEEE divisions cost ~30 instructions
+  const float r = s2 * rsqrtf(s2);               // s2 == 0: NaN, declined below
+  if (!(r > 1e-3f)) return false;
+  const float inv_r = __fdividef(1.0f, r);
+  const float q = __fdividef(4.0f * tr + tr * tr + w * w, r + 2.0f);
+  const float e = __fdividef(1e-10f, r + 1e-10f);
+#else
+  const float r = sqrtf(s2);
   if (!(r > 1e-3f)) return false;
   const float inv_r = 1.0f / r;
   const float q = (4.0f * tr + tr * tr + w * w) / (r + 2.0f);
   const float e = 1e-10f / (r + 1e-10f);
+#endif
   const float ex = e * x, ew = e * w;
   const float d00 = (q * F.a00 + dd + ex) * inv_r, d01 = (q * e01 + sy - ew) * inv_r;
   const float d10 = (q * e10 + sy + ew) * inv_r, d11 = (q * F.a11 - dd + ex) * inv_r;

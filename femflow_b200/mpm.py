@@ -122,8 +122,8 @@ class MpmSolver:
             self.material_layout = "planes"
         if reorder is None:
             # 3D: binned pipeline, G2P writes the state back cell-sorted.  2D (1 M particles, state resident in L2) is
-            # fastest unbinned (measured: profiles/r02e_g2p_packed_and_binned_2d_ab.json); the binned 2D pipeline stays
-            # selectable with reorder=True
+            # fastest unbinned (warp-window kernels, csrc/mpm_2d_window.cuh; measured: profiles/r02s_2d_series.json); the
+            # binned 2D pipeline stays selectable with reorder=True (or FFMPM_2D_BINNED=1)
             reorder = (self.dim == 3 or os.environ.get("FFMPM_2D_BINNED") == "1") and p2g_mode != "scatter"
         self.reorder = bool(reorder)
         cfg = N.FfMpmConfig()
@@ -343,9 +343,10 @@ class MpmSolver:
         N.check(self.lib.ffmpm_substep(self._h, int(n_substeps), self._stream(stream)))
 
     def make_graph(self, n_substeps: int) -> "torch.cuda.CUDAGraph":
-        """Capture ``n_substeps`` substeps (rounded up to an even count when the state
-        ping-pongs, so that replay starts from the same buffer) in a CUDA graph."""
-        if self.reorder and n_substeps % 2:
+        """Capture ``n_substeps`` substeps in a CUDA graph, rounded up to an even count: the state buffers (reordering
+        pipelines) and the two grids (every pipeline whose grid update clears the idle grid) ping-pong, so that only an
+        even number of substeps ends where it started and can be replayed back to back."""
+        if n_substeps % 2:
             n_substeps += 1
         self.graph_substeps = n_substeps
         torch.cuda.synchronize(self.device)

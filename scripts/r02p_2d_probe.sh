@@ -8,10 +8,9 @@ timeout 300 python -m pytest tests -m gpu -x -q -k "2d or c2 or snow or quirk" >
 tail -3 $out/pytest_2d.txt
 B="python bench.py --workload 2d1m --no-cpu-baseline --e2e-steps 1"
 timeout 120 $B --steps 400 --warmup 10 > $out/bench_2d.json 2> $out/bench_2d.err
-FFMPM_FP32_STRESS=0 timeout 120 $B --steps 400 --warmup 10 > $out/bench_2d_fp64stress.json 2> $out/bench_2d_fp64stress.err
 FFMPM_DEBUG_NORED=1 timeout 120 $B --steps 400 --warmup 10 --no-parity > $out/bench_2d_nored.json 2> $out/bench_2d_nored.err
 FFMPM_2D_BINNED=1 timeout 120 $B --steps 400 --warmup 10 > $out/bench_2d_binned.json 2> $out/bench_2d_binned.err
-for f in bench_2d bench_2d_fp64stress bench_2d_nored bench_2d_binned; do
+for f in bench_2d bench_2d_nored bench_2d_binned; do
 python - <<PY
 import json
 try:

@@ -451,6 +451,105 @@ def test_2d_multi_substep_pipelines_vs_oracle(pipeline, model, dtype):
     s.close()
 
 
+@pytest.mark.parametrize("order", ["lattice", "shuffled", "cell_sorted"])
+def test_2d_window_kernels_any_particle_order(order, monkeypatch):
+    """The warp-window 2D kernels (csrc/mpm_2d_window.cuh, the fp32 default) against the thread-per-particle kernels
+    (FFMPM_2D_WINDOW=0) and the C port of two_d/{p2g,grid_op,g2p}.py: 9 particles per cell in lattice order (coherent
+    windows: the shared-memory node tile), shuffled (bounding box too large: direct reductions) and sorted by base cell
+    (up to 9 lanes share a cell: they take turns on the tile); a particle count that is not a multiple of the window,
+    two particles outside the grid, one NaN; the raw grid after P2G and the state after 3 substeps (odd: both grids of
+    the ping-pong pair get used)."""
+    from femflow_b200 import scenes
+    from femflow_b200.mpm import MpmSolver
+    from oracle import native as ON
+    sc = scenes.elastic_block(2, 128, 90, 3, seed=8)
+    rng = np.random.default_rng(8)
+    n = sc.n - 37
+    x, v, F, C = (a[:n].astype(np.float64) for a in (sc.x, sc.v, sc.F, sc.C))
+    speed = 0.15 / sc.res / sc.dt
+    v = np.float32(v + speed * np.array([-0.6, 1.0])).astype(np.float64)
+    if order == "shuffled":
+        perm = rng.permutation(n)
+    elif order == "cell_sorted":
+        base = np.floor(np.float32(x) * np.float32(sc.res) - np.float32(0.5)).astype(np.int64)
+        perm = np.argsort(base[:, 0] * (sc.res + 1) + base[:, 1], kind="stable")
+    else:
+        perm = np.arange(n)
+    x, v, F, C = x[perm], v[perm], F[perm], C[perm]
+    Jp = np.ones((n, 1))
+
+    def make(window):
+        monkeypatch.setenv("FFMPM_2D_WINDOW", "1" if window else "0")
+        s = MpmSolver(2, sc.res, sc.dt, sc.volume, sc.gravity, 1.0, capacity=n, mass=sc.mass, mu_0=sc.mu_0, lambda_0=sc.lambda_0)
+        s.set_particles(x, v, F, C, Jp)
+        return s
+    a, b = make(True), make(False)
+    # raw grid {momentum, mass} after P2G
+    grids = []
+    for s in (a, b):
+        s.clear_grid(); s.p2g()
+        grids.append(s.grid(readonly=True).double().cpu().numpy().reshape(sc.res + 1, sc.res + 1, 4).copy())
+    gv = np.zeros((sc.res + 1, sc.res + 1, 2)); gm = np.zeros((sc.res + 1, sc.res + 1, 1))
+    O.p2g_2d(float(sc.res), 1.0, sc.mu_0, sc.lambda_0, sc.mass, 1 / sc.res, sc.dt, sc.volume, gv, gm, x, v, F, C, Jp)
+    V = max(np.abs(v).max(), sc.dt * 9.8)
+    for g in grids:
+        assert rel_err(g[..., 2:3], gm) < 1e-5
+        assert rel_err(g[..., :2], gv, gm.max() * V) < 1e-5
+        assert np.all(g[..., 3] == 0)
+    # three substeps; then out-of-grid particles are flagged, not scattered
+    for s in (a, b):
+        s.substep(3)
+        s.check_errors()
+    for _ in range(3):
+        ON.solve_mls_mpm_2d(sc.res, float(sc.res), 1.0, sc.mu_0, sc.lambda_0, sc.mass, 1 / sc.res, sc.dt, sc.volume,
+                            sc.gravity, x, v, F, C, Jp)
+    V = max(np.abs(v).max(), sc.dt * 9.8)
+    for s in (a, b):
+        out = {k: t.double().cpu().numpy() for k, t in s.get_particles().items()}
+        assert rel_err(out["x"], x, 1.0) < 3e-5
+        assert np.abs(out["v"] - v).max() / V < 3e-5
+        assert rel_err(out["F"], F, 1.0) < 3e-5
+        assert np.abs(out["C"] - C).max() / (4 * sc.res * V) < 3e-5
+        assert rel_err(out["Jp"], Jp, 1.0) < 3e-5
+    bad = x.copy()
+    bad[5] = [1.5, 0.5]; bad[n - 1] = [0.5, -0.2]; bad[100] = [np.nan, 0.5]
+    for s in (a, b):
+        s.set_particles(bad, v, F, C, Jp)
+        s.clear_grid(); s.p2g()
+        with pytest.raises(RuntimeError):
+            s.check_errors()
+        s.close()
+
+
+def test_2d_graph_replay_matches_eager_substeps():
+    """2D: a captured pair of substeps (P2G, grid update that also clears the idle grid, G2P -- the two grids ping-pong
+    inside the capture) replayed three times against six eager substeps; an odd request is rounded up to an even count."""
+    from femflow_b200 import scenes
+    from femflow_b200.mpm import MpmSolver
+    sc = scenes.elastic_block(2, 256, 128, 2, seed=2)
+
+    def make():
+        s = MpmSolver(2, sc.res, sc.dt, sc.volume, sc.gravity, 1.0, capacity=sc.n, mass=sc.mass, mu_0=sc.mu_0, lambda_0=sc.lambda_0)
+        s.set_particles(sc.x, sc.v, sc.F, sc.C, np.ones((sc.n, 1)))
+        return s
+    a, b = make(), make()
+    a.substep(9)
+    b.substep(3)
+    g = b.make_graph(1)
+    assert b.graph_substeps == 2 and b.graph_launches == 6
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    a.check_errors(); b.check_errors()
+    pa, pb = a.get_particles(), b.get_particles()
+    V = max(float(pa["v"].abs().max()), sc.dt * 9.8)
+    assert float((pa["x"] - pb["x"]).abs().max()) < 1e-5
+    assert float((pa["v"] - pb["v"]).abs().max()) / V < 1e-4
+    assert float((pa["F"] - pb["F"]).abs().max()) < 1e-5
+    assert float((pa["C"] - pb["C"]).abs().max()) / (4 * sc.res * V) < 1e-4
+    a.close(); b.close()
+
+
 @pytest.mark.parametrize("variant", [0, 1, 5])
 @pytest.mark.parametrize("n_materials", [1, 3, 300])
 def test_p2g_kernel_variants(variant, n_materials, monkeypatch):
