@@ -182,7 +182,13 @@ int ffmpm_migrate_unpack(FfMpmHandle* h, const void* in_lo, const void* in_hi, i
  * Both are ordered on `stream` like any other call. */
 int ffmpm_scatter(FfMpmHandle* h, void* stream);
 int ffmpm_gather(FfMpmHandle* h, void* stream);
-/* n_substeps x (scatter, grid_op, gather). */
+/* n_substeps x (scatter, grid_op, gather).
+ * The grid of a substep is one of TWO the library keeps (ffmpm_grid_ptr / ffmpm_grid_view return the current one: ask
+ * again after every call that scatters).  3D: the idle grid is cleared on the internal stream underneath P2G.  2D:
+ * ffmpm_grid_op zeroes the idle grid in the same pass, so a 2D substep is three launches (P2G, grid update, G2P:
+ * two_d/{p2g,grid_op,g2p}.py) and an EVEN number of substeps ends on the grid it started from (what CUDA-graph
+ * capture needs).  2D fp32 states whose x, v, C, F planes sit back to back at one stride run the warp-window kernels
+ * (csrc/mpm_2d_window.cuh; FFMPM_2D_WINDOW=0 in the environment selects the thread-per-particle ones). */
 int ffmpm_substep(FfMpmHandle* h, int32_t n_substeps, void* stream);
 
 /* Material table (femflow/solvers/mpm/particle.py:7-13: every Particle carries mass, mu_0 and
