@@ -20,6 +20,7 @@
 #include "mpm_2d.cuh"
 #include "mpm_2d_window.cuh"
 #include "mpm_scene.cuh"
+#include "mpm_svd3.cuh"
 
 using namespace ffmpm;
 
@@ -509,6 +510,10 @@ static int g2p_t(FfMpmHandle* h, cudaStream_t s) {
     h->live ^= 1;
     h->binned = false;  // positions moved: perm / cell offsets are stale ...
     h->prebinned = true;  // ... but keys, ranks and the histogram of the new live buffer are ready
+    if (h->cfg.model == FFMPM_SNOW) {   // three_d/g2p.py:48-58 on the F the kernel carried over unchanged
+      snow_project3_kernel<T><<<(unsigned)((h->n + 127) / 128), 128, 0, s>>>(h->dev, dst, h->n);
+      ++nl;
+    }
     return check_launch(h, nl);
   }
   h->binned = false;
@@ -521,6 +526,11 @@ static int g2p_t(FfMpmHandle* h, cudaStream_t s) {
     }
   }
   unsigned blocks = (unsigned)((h->n + 127) / 128);
+  if (h->cfg.dim == 3 && h->cfg.model == FFMPM_SNOW) {
+    g2p_gather3_kernel<T, true><<<blocks, 128, 0, s>>>(h->dev, sv, h->n, (const T*)h->grid, h->err);
+    snow_project3_kernel<T><<<blocks, 128, 0, s>>>(h->dev, sv, h->n);
+    return check_launch(h, 2);
+  }
   if (h->cfg.dim == 3)
     g2p_gather3_kernel<T><<<blocks, 128, 0, s>>>(h->dev, sv, h->n, (const T*)h->grid, h->err);
   else
@@ -531,10 +541,6 @@ static int g2p_t(FfMpmHandle* h, cudaStream_t s) {
 int ffmpm_g2p(FfMpmHandle* h, void* stream) {
   int rc = ready(h);
   if (rc) return rc;
-  if (h->cfg.dim == 3 && h->cfg.model == FFMPM_SNOW)
-    return set_err(FFMPM_E_INVALID,
-                   "3D snow G2P is not reproducible: three_d/g2p.py:55 multiplies by Vh^T, which depends on LAPACK's "
-                   "singular-vector signs (unreachable from solve_mls_mpm_3d, mls_mpm.py:58)");
   if (h->n == 0) return FFMPM_OK;
   return h->cfg.dtype == FFMPM_F64 ? g2p_t<double>(h, (cudaStream_t)stream) : g2p_t<float>(h, (cudaStream_t)stream);
 }

@@ -414,7 +414,8 @@ FFMPM_HD void g2p_accumulate3(Fetch fetch, T fx, T fy, T fz, T& vx, T& vy, T& vz
 // ----------------------------------------------------------------------------
 // G2P, gather form (in place)
 // ----------------------------------------------------------------------------
-template <typename T>
+// KEEPF (3D snow): F is left as it was; snow_project3_kernel forms (I + dt C) F in fp64 and projects it.
+template <typename T, bool KEEPF = false>
 __global__ void __launch_bounds__(128) g2p_gather3_kernel(DevCfg cfg, StateView<T> s, long long n, const T* __restrict__ grid,
                                                           ErrRec* err) {
   long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -445,15 +446,17 @@ __global__ void __launch_bounds__(128) g2p_gather3_kernel(DevCfg cfg, StateView<
   T m00 = (T)1 + dt * c00, m01 = dt * c01, m02 = dt * c02;
   T m10 = dt * c10, m11 = (T)1 + dt * c11, m12 = dt * c12;
   T m20 = dt * c20, m21 = dt * c21, m22 = (T)1 + dt * c22;
-  s.F[0 * st + p] = m00 * f00 + m01 * f10 + m02 * f20;
-  s.F[1 * st + p] = m00 * f01 + m01 * f11 + m02 * f21;
-  s.F[2 * st + p] = m00 * f02 + m01 * f12 + m02 * f22;
-  s.F[3 * st + p] = m10 * f00 + m11 * f10 + m12 * f20;
-  s.F[4 * st + p] = m10 * f01 + m11 * f11 + m12 * f21;
-  s.F[5 * st + p] = m10 * f02 + m11 * f12 + m12 * f22;
-  s.F[6 * st + p] = m20 * f00 + m21 * f10 + m22 * f20;
-  s.F[7 * st + p] = m20 * f01 + m21 * f11 + m22 * f21;
-  s.F[8 * st + p] = m20 * f02 + m21 * f12 + m22 * f22;
+  if constexpr (!KEEPF) {
+    s.F[0 * st + p] = m00 * f00 + m01 * f10 + m02 * f20;
+    s.F[1 * st + p] = m00 * f01 + m01 * f11 + m02 * f21;
+    s.F[2 * st + p] = m00 * f02 + m01 * f12 + m02 * f22;
+    s.F[3 * st + p] = m10 * f00 + m11 * f10 + m12 * f20;
+    s.F[4 * st + p] = m10 * f01 + m11 * f11 + m12 * f21;
+    s.F[5 * st + p] = m10 * f02 + m11 * f12 + m12 * f22;
+    s.F[6 * st + p] = m20 * f00 + m21 * f10 + m22 * f20;
+    s.F[7 * st + p] = m20 * f01 + m21 * f11 + m22 * f21;
+    s.F[8 * st + p] = m20 * f02 + m21 * f12 + m22 * f22;
+  }
   s.C[0 * st + p] = c00; s.C[1 * st + p] = c01; s.C[2 * st + p] = c02;
   s.C[3 * st + p] = c10; s.C[4 * st + p] = c11; s.C[5 * st + p] = c12;
   s.C[6 * st + p] = c20; s.C[7 * st + p] = c21; s.C[8 * st + p] = c22;

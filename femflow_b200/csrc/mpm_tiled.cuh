@@ -50,7 +50,9 @@ __device__ __forceinline__ void cp_async4(void* sdst, const void* gsrc) {
 // ROWS: the state carries 1-byte material rows (table mode); compiled out otherwise, the kernel sits
 // exactly at its 64-register budget.
 // IDX32: exact fp32 cell indexing known at compile time (cfg.index_fp32; see base_fx).
-template <typename T, int MIN_BLOCKS, bool PRE = false, bool ROWS = false, bool IDX32 = false>
+// KEEPF (3D snow): F moves to its new slot unchanged; snow_project3_kernel (mpm_svd3.cuh) forms (I + dt C) F in fp64
+// from it and the new C and projects it.  The instantiations of the neo-hookean path are untouched by the flag.
+template <typename T, int MIN_BLOCKS, bool PRE = false, bool ROWS = false, bool IDX32 = false, bool KEEPF = false>
 __global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_tiled3_kernel(DevCfg cfg, StateView<T> src, StateView<T> dst,
                                                                  BinBuffers B, const T* __restrict__ grid, ErrRec* err) {
   using V4 = typename Vec4<T>::type;
@@ -203,15 +205,19 @@ __global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_tiled3_kernel(Dev
         o[0] = x0 + dt * vx; o[1] = x1 + dt * vy; o[2] = x2 + dt * vz;   // three_d/g2p.py:45
         o[3] = vx; o[4] = vy; o[5] = vz;
         o[6] = c00; o[7] = c01; o[8] = c02; o[9] = c10; o[10] = c11; o[11] = c12; o[12] = c20; o[13] = c21; o[14] = c22;
-        o[15] = m00 * f00 + m01 * f10 + m02 * f20;
-        o[16] = m00 * f01 + m01 * f11 + m02 * f21;
-        o[17] = m00 * f02 + m01 * f12 + m02 * f22;
-        o[18] = m10 * f00 + m11 * f10 + m12 * f20;
-        o[19] = m10 * f01 + m11 * f11 + m12 * f21;
-        o[20] = m10 * f02 + m11 * f12 + m12 * f22;
-        o[21] = m20 * f00 + m21 * f10 + m22 * f20;
-        o[22] = m20 * f01 + m21 * f11 + m22 * f21;
-        o[23] = m20 * f02 + m21 * f12 + m22 * f22;
+        if constexpr (KEEPF) {
+          o[15] = f00; o[16] = f01; o[17] = f02; o[18] = f10; o[19] = f11; o[20] = f12; o[21] = f20; o[22] = f21; o[23] = f22;
+        } else {
+          o[15] = m00 * f00 + m01 * f10 + m02 * f20;
+          o[16] = m00 * f01 + m01 * f11 + m02 * f21;
+          o[17] = m00 * f02 + m01 * f12 + m02 * f22;
+          o[18] = m10 * f00 + m11 * f10 + m12 * f20;
+          o[19] = m10 * f01 + m11 * f11 + m12 * f21;
+          o[20] = m10 * f02 + m11 * f12 + m12 * f22;
+          o[21] = m20 * f00 + m21 * f10 + m22 * f20;
+          o[22] = m20 * f01 + m21 * f11 + m22 * f21;
+          o[23] = m20 * f02 + m21 * f12 + m22 * f22;
+        }
         int gbx = 0;
         next_key = bin_key_of<T, IDX32>(cfg, B, o[0], o[1], o[2], &gbx);
         B.keys[slot] = next_key;
@@ -261,6 +267,12 @@ int g2p_tiled(const DevCfg& cfg, const StateView<T>& src, const StateView<T>& ds
   (void)n;
   cudaMemsetAsync(&B.counters[2], 0, sizeof(int32_t), st);
   int blocks = min(B.n_tiles + 1, sm_count * blocks_per_sm);
+  if (cfg.model == 1) {   // snow: F is carried unchanged, the caller projects it afterwards (mpm_svd3.cuh)
+    constexpr int MB = sizeof(T) == 4 ? 8 : 4;
+    if (src.material) g2p_tiled3_kernel<T, MB, false, true, false, true><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
+    else g2p_tiled3_kernel<T, MB, false, false, false, true><<<blocks, G2P_THREADS, 0, st>>>(cfg, src, dst, B, grid, err);
+    return 1;
+  }
   if constexpr (sizeof(T) == 4) {
     // FFMPM_G2P_PRE=0 disables the cp.async input prefetch (64 registers, 8 CTAs per SM either way)
     static int prefetch = [] { const char* e = getenv("FFMPM_G2P_PRE"); return e ? atoi(e) : 1; }();

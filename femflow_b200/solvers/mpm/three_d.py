@@ -80,7 +80,8 @@ def check_collision_points(points, normals, grid_resolution, dx, grid_velocity):
 
 
 def g2p(inv_dx, dt, grid_velocity, particles, v, F, C, Jp, model: str = "neo_hookean"):
-    """three_d/g2p.py:9-59: mutates ``particles[i].pos``, ``v``, ``F``, ``C`` in place."""
+    """three_d/g2p.py:9-59: mutates ``particles[i].pos``, ``v``, ``F``, ``C`` (and ``Jp`` for ``model="snow"``,
+    g2p.py:48-58, with LAPACK's singular-vector signs: csrc/mpm_svd3.cuh) in place."""
     soa = particles_to_soa(particles)
     G = grid_velocity.shape[0]
     s = _solver(G - 1, len(soa), inv_dx, 1.0 / inv_dx, dt, 1.0, 0.0, 1.0, model)
@@ -95,3 +96,5 @@ def g2p(inv_dx, dt, grid_velocity, particles, v, F, C, Jp, model: str = "neo_hoo
     v[...] = out["v"].double().cpu().numpy()
     F[...] = out["F"].double().cpu().numpy()
     C[...] = out["C"].double().cpu().numpy()
+    if model == "snow":
+        Jp[...] = out["Jp"].double().cpu().numpy().reshape(np.shape(Jp))

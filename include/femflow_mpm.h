@@ -28,9 +28,12 @@
  *                      arrays in place, particle i stays particle i (three_d/g2p.py:43-59)
  *   ffmpm_gen_implicit_points / ffmpm_gen_cube_points
  *                      femflow/simulation/mpm/primitives.py:46-76, numerics/geometry.py:101-116 (scene generators)
- *   ffmpm_g2p with model = FFMPM_SNOW in 3D is REFUSED (FFMPM_E_INVALID): three_d/g2p.py:48-58 multiplies by Vh^T of a
- *                      LAPACK SVD, so its result depends on LAPACK's singular-vector signs; the reference's own driver
- *                      never reaches it (mls_mpm.py:58).  2D snow and the 3D snow hardening of P2G are implemented.
+ *   ffmpm_g2p with model = FFMPM_SNOW in 3D: three_d/g2p.py:48-58 forms U clip(sig) Vh^T -- numpy's Vh transposed once
+ *                      more -- so its result depends on the SIGNS of LAPACK's singular vectors.  csrc/mpm_svd3.cuh walks
+ *                      DGESDD's operation sequence for 3x3 input (Householder bidiagonalisation, DBDSQR sweeps, the sign
+ *                      flip and the sort, DORMBR) in fp64 and is pinned against np.linalg.svd itself and the reference's
+ *                      own F_out / Jp_out (tests/golden/snow3d.npz).  It runs as a second launch after the G2P, which
+ *                      carries F unchanged; the reference's driver never reaches this branch (mls_mpm.py:58).
  *
  * Conventions
  *   - Plain C, no torch types.  All array arguments are DEVICE pointers owned by

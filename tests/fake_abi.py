@@ -317,8 +317,7 @@ class FakeLib:
             return N.FFMPM_OK
         if h.cfg.dim == 2:
             return self._g2p_2d(h)
-        if h.cfg.model == N.FFMPM_SNOW:
-            return self._fail(N.FFMPM_E_INVALID, "3D snow G2P is not reproducible")
+        snow = h.cfg.model == N.FFMPM_SNOW
         p, n = self._planes(h, h.live), h.n
         x = p["x"][:, :n].T.astype(np.float64)
         v = p["v"][:, :n].T.astype(np.float64)
@@ -328,8 +327,11 @@ class FakeLib:
         h.n_oob += int((~ok).sum())
         gv, _, _ = self._embed(h)
         xo, vo, Fo, Co = x[ok], v[ok], F[ok], Cm[ok]
-        O.g2p_3d(h.cfg.inv_dx, h.cfg.dt, gv, xo, vo, Fo, Co, np.ones((len(xo), 1)))
+        jpo = p["Jp"][:n][ok].astype(np.float64)[:, None] if snow else np.ones((len(xo), 1))
+        O.g2p_3d(h.cfg.inv_dx, h.cfg.dt, gv, xo, vo, Fo, Co, jpo, "snow" if snow else "neo_hookean")
         x[ok], v[ok], F[ok], Cm[ok] = xo, vo, Fo, Co
+        if snow:     # three_d/g2p.py:58, before the planes are carried into the other buffer
+            p["Jp"][:n][ok] = jpo[:, 0]
         if h.st[1] is not None:
             # the reordering G2P: cell-sorted into the other buffer, out-of-grid particles last, planes carried along
             G = gv.shape[0]

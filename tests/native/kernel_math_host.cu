@@ -5,6 +5,7 @@
 // infrastructure only: nothing in the product links this file.
 #include "../../femflow_b200/csrc/mpm_direct.cuh"
 #include "../../femflow_b200/csrc/mpm_bin.cuh"
+#include "../../femflow_b200/csrc/mpm_svd3.cuh"
 
 using namespace ffmpm;
 
@@ -217,6 +218,21 @@ int km_bin_keys_f32(int dim, const int* n, int origin0, double inv_dx, int index
   for (long long p = 0; p < count; ++p)
     keys[p] = bin_key_of<float>(c, B, x[3 * p], x[3 * p + 1], x[3 * p + 2], base_x + p);
   return B.n_cells;
+}
+
+// 3x3 SVD with LAPACK's singular-vector signs (mpm_svd3.cuh): row-major A -> U, sig, Vh
+void km_svd3_lapack(long long n, const double* A, double* U, double* S, double* Vh, int* ok) {
+  for (long long p = 0; p < n; ++p) {
+    double a[3][3], u[3][3], vt[3][3];
+    for (int i = 0; i < 9; ++i) a[i / 3][i % 3] = A[9 * p + i];
+    ok[p] = svd3_lapack(a, u, S + 3 * p, vt) ? 1 : 0;
+    for (int i = 0; i < 9; ++i) { U[9 * p + i] = u[i / 3][i % 3]; Vh[9 * p + i] = vt[i / 3][i % 3]; }
+  }
+}
+
+// three_d/g2p.py:46-59, snow: F (old), C (new), Jp -> F, Jp
+void km_snow_return_map3(long long n, double dt, const double* F, const double* Cm, const double* jp, double* Fout, double* jp_out) {
+  for (long long p = 0; p < n; ++p) snow_return_map3(F + 9 * p, Cm + 9 * p, dt, jp[p], Fout + 9 * p, jp_out[p]);
 }
 
 }  // extern "C"

@@ -279,6 +279,66 @@ def test_snow_p2g_3d(dtype):
     assert rel_err(gv, dense_grid(g, "grid_momentum")) < TOL[dtype]
 
 
+def test_snow_g2p_3d(dtype, kernels):
+    """3D snow G2P (three_d/g2p.py:48-58): F <- U clip(sig) Vh^T -- the reference transposes numpy's Vh once more, so
+    the result depends on the SIGNS of LAPACK's singular vectors (csrc/mpm_svd3.cuh walks DGESDD's operation sequence) --
+    and Jp <- clip(Jp det(F_) / (det F + 1e-10), 0.6, 20), against the reference's own F_out / Jp_out, through the
+    thread-per-particle and the reordering kernel."""
+    from femflow_b200.solvers.mpm import three_d
+    from femflow_b200.solvers.mpm.particle import ParticleArray
+    g = load_golden("snow3d")
+    p = _p3(g)
+    gv = dense_grid(g, "grid_momentum").copy(); gm = dense_grid(g, "grid_mass").copy()
+    O.grid_op_3d(p["res"], p["dx"], p["dt"], p["gravity"], gv, gm)          # the pinned oracle: g2p is judged on its own
+    fl = _floors(p, g["mass"], gv)
+    particles = ParticleArray(g["x"].copy(), g["mass"], g["lam0"], g["mu0"])
+    v, F, C, Jp = (g[k].copy() for k in ("v", "F", "C", "Jp"))
+    three_d.g2p(p["inv_dx"], p["dt"], gv, particles, v, F, C, Jp, "snow")
+    tol = TOL[dtype]
+    assert rel_err(particles.pos, g["x_out"], 1.0) < tol
+    assert rel_err(v, g["v_out"], fl["vel"]) < tol
+    assert rel_err(C, g["C_out"], fl["C"]) < tol
+    assert rel_err(F, g["F_out"], 1.0) < tol
+    assert rel_err(Jp, g["Jp_out"], 1.0) < tol
+    assert np.abs(g["F_out"] - g["F"]).max() > 1e-3        # the return map did something to compare
+
+
+def test_3d_snow_substeps_vs_oracle(device="cuda"):
+    """ffmpm_substep with model = snow in 3D (binning, bulk/runs P2G with snow hardening, grid update, reordering G2P
+    that carries F, the fp64 return map of csrc/mpm_svd3.cuh): three substeps against the chained oracle phases
+    (three_d/p2g.py, grid_op.py, g2p.py with model="snow" -- a path the reference's own driver never takes,
+    mls_mpm.py:58).  fp64 build only: once the clamp has made two singular values equal, the next substep's singular
+    vectors hang on a perturbation of size dt*C, and what the reference then computes (U S Vh^T, not U S Vh) amplifies
+    storage rounding by 1/gap -- the fp32 build is held to the reference on the single-substep golden instead."""
+    from femflow_b200 import scenes
+    from femflow_b200.mpm import MpmSolver
+    sc = scenes.elastic_block(3, 32, 10, 2, seed=4)
+    n = sc.n
+    x, v, F, C = (a.astype(np.float64) for a in (sc.x, sc.v, sc.F, sc.C))
+    Jp = np.ones((n, 1))
+    hard = 3.0
+    s = MpmSolver(3, sc.res, sc.dt, sc.volume, sc.gravity, hard, capacity=n, model="snow", dtype=torch.float64, device=device)
+    s.set_particles(x, v, F, C, Jp, sc.mass, sc.mu_0, sc.lambda_0)
+    m = np.full(n, sc.mass); mu = np.full(n, sc.mu_0); lam = np.full(n, sc.lambda_0)
+    G = sc.res + 1
+    steps = 3
+    s.substep(steps)
+    s.check_errors()
+    for _ in range(steps):
+        gv = np.zeros((G, G, G, 3)); gm = np.zeros((G, G, G, 1))
+        O.p2g_3d(float(sc.res), hard, 1.0 / sc.res, sc.dt, sc.volume, gv, gm, x, m, mu, lam, v, F, C, Jp, "snow")
+        O.grid_op_3d(sc.res, 1.0 / sc.res, sc.dt, sc.gravity, gv, gm)
+        O.g2p_3d(float(sc.res), sc.dt, gv, x, v, F, C, Jp, "snow")
+    out = {k: t.double().cpu().numpy() for k, t in s.get_particles().items()}
+    V = max(np.abs(v).max(), sc.dt * 9.8)
+    assert rel_err(out["x"], x, 1.0) < 1e-10
+    assert np.abs(out["v"] - v).max() / V < 1e-8
+    assert rel_err(out["F"], F, 1.0) < 1e-8
+    assert rel_err(out["Jp"], Jp, 1.0) < 1e-8
+    assert np.abs(Jp - 1.0).max() > 1e-4 and np.abs(F - sc.F).max() > 1e-3
+    s.close()
+
+
 def test_oob_raises_runtime_error(dtype):
     """three_d/p2g.py:51-52: a stencil outside [0, R] is a RuntimeError."""
     from femflow_b200.solvers.mpm.mls_mpm import make_mls_mpm_coefficients, solve_mls_mpm_3d

@@ -245,3 +245,11 @@ def test_2d_snow_quirk_and_3d_snow_wrappers(gpu_test_bodies):
     gpu_test_bodies.test_2d_snow_matches_reference("float64")
     gpu_test_bodies.test_2d_svd_roundtrip_quirk("float64")
     gpu_test_bodies.test_snow_p2g_3d("float64")
+    gpu_test_bodies.test_3d_snow_substeps_vs_oracle(device="cpu")
+    from femflow_b200.solvers.mpm import three_d
+    for kind in ("direct", "production"):
+        prev = three_d.set_kernels(kind)
+        try:
+            gpu_test_bodies.test_snow_g2p_3d("float64", kind)
+        finally:
+            three_d.set_kernels(prev)
