@@ -7,10 +7,9 @@
 // column 1, G1 on row 1, H2 on column 2; H3 and G2 are identities), DBDSQR through DBDSDC -> DLASDQ (n <= 25: zero-shift
 // and implicit-shift QR sweeps in the direction of the larger end, DLASV2 on 2x2 blocks, negative singular values made
 // positive by negating rows of VT, sort), DORMBR back-transformation.  DLARTG is LAPACK >= 3.10's (c >= 0).  LAPACK is
-// not part of /root/reference (numpy links OpenBLAS 0.3.30 there); oracle/lapack_svd3.py is the scalar restatement this
-// file was written from, pinned against np.linalg.svd itself on 10^5 matrices (signs and values), and
-// tests/golden/snow3d.npz holds the reference's own F_out / Jp_out.  fp64 throughout; plain arithmetic, compiles for
-// the host as well (tests/native/kernel_math_host.cu).
+// not part of /root/reference (numpy links OpenBLAS 0.3.30 there).  tests/test_lapack_svd3.py compiles this file for the
+// host and pins it against np.linalg.svd itself on 10^5 matrices (signs and values) and against the reference's own
+// F_out / Jp_out in tests/golden/snow3d.npz.  fp64 throughout; plain arithmetic (tests/native/kernel_math_host.cu).
 #pragma once
 #include "mpm_math.cuh"
 
