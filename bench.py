@@ -60,52 +60,120 @@ def make_scene(workload: str, seed: int = 0, cells_x=None, res_x=None):
 
 # ----------------------------------------------------------------------------- #
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and clock-event (throttle) reasons sampled DURING the timed region.
 
+    NVML in-process (pynvml), one sample every ~2 ms from a thread: the driver's line times 20 substeps = 27 ms, which
+    an ``nvidia-smi -lms 50`` child (hundreds of ms to start, 50 ms period) cannot resolve -- it is kept as the fallback
+    where pynvml is missing, started before the warm-up.  ``mark_begin`` / ``mark_end`` bracket the timed region on
+    the host clock; only samples between them count (``window`` says so; if the region was too short for a single
+    sample, the ones taken in the 150 ms after it -- clocks do not drop that fast -- are reported and labelled)."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
-        self.rows = []
+    def __init__(self, gpu_index: int, uuid=None):
+        self.rows = []            # (t, sm_mhz, reasons bitmask)
         self.proc = None
-        self.gpu = gpu_index
+        self.gpu, self.uuid = gpu_index, uuid
+        self.nvml = None
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self.t0 = self.t1 = None
+        self.source = None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        h = None
+        if self.uuid:
+            for cand in (f"GPU-{self.uuid}", str(self.uuid)):
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(cand if isinstance(cand, bytes) else cand.encode())
+                    break
+                except Exception:
+                    h = None
+        if h is None:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+        return pynvml, h
 
     def start(self):
         try:
+            pynvml, h = self._nvml_handle()
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        self.rows.append((time.perf_counter(), float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)),
+                                          int(reasons_fn(h))))
+                    except Exception:
+                        pass
+                    self._stop.wait(0.002)
+            self.nvml = pynvml
+            self.source = "nvml"
+            self.t = threading.Thread(target=poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            self.source = "nvidia-smi"
+            self.t = threading.Thread(target=self._read_smi, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
+    def _read_smi(self):
+        bits = [0x8, 0x40, 0x20, 0x4]
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+            r = [c.strip() for c in line.split(",")]
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-                for nm, val in zip(names, r[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(nm)
+                mask = sum(b for b, val in zip(bits, r[5:9]) if val.lower().startswith("active"))
+                self.rows.append((time.perf_counter(), float(r[1]), mask))
+                self.max_mhz = max(self.max_mhz or 0.0, float(r[2]))
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
+
+    def stop(self):
+        if self.nvml is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["clock sampling unavailable (no pynvml, no nvidia-smi)"]}
+        time.sleep(0.15)
+        self._stop.set()
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        t0 = self.t0 if self.t0 is not None else -float("inf")
+        t1 = self.t1 if self.t1 is not None else float("inf")
+        inside = [r for r in self.rows if t0 <= r[0] <= t1]
+        window = "timed region"
+        if not inside:
+            inside = [r for r in self.rows if t1 < r[0] <= t1 + 0.15] or self.rows[-3:]
+            window = "no sample fell inside the timed region: the 150 ms after it"
+        mask = 0
+        for r in inside:
+            mask |= r[2]
+        sm = [r[1] for r in inside]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": min(sm) if sm else None, "sm_max_mhz": self.max_mhz,
+                "samples": len(sm), "reasons": sorted(nm for b, nm in self.REASONS.items() if mask & b),
+                "window": window, "source": self.source,
+                "region_ms_host": None if self.t0 is None or self.t1 is None else round((self.t1 - self.t0) * 1e3, 2)}
 
 
 # ----------------------------------------------------------------------------- #
@@ -360,6 +428,13 @@ def main():
             raise SystemExit("pre-steps left particles outside the grid")
 
     # ---- warm-up ----
+    try:
+        gpu_uuid = getattr(torch.cuda.get_device_properties(dev), "uuid", None)
+    except Exception:
+        gpu_uuid = None
+    sampler = ClockSampler(local_rank, uuid=gpu_uuid)
+    if rank == 0:
+        sampler.start()          # before the warm-up: the sampler is up and streaming when the timed region begins
     for _ in range(args.warmup):
         solver.substep(1)
     if world > 1:
@@ -372,9 +447,6 @@ def main():
         raise SystemExit("warm-up left particles outside the grid")
 
     # ---- timed region: K substeps, state resident in HBM ----
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     graph = None
     if scene.dim == 2 and world == 1 and args.steps % 10 == 0:
         args.graph = True      # a 2D substep is four kernels of ~15 us: replayed as CUDA graphs by default (-11 %)
@@ -383,6 +455,7 @@ def main():
     l0 = solver.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     ev0.record()
     if graph is not None:
         for _ in range(args.steps // 10):
@@ -400,6 +473,7 @@ def main():
                 marks[-1][1].record()
     ev1.record()
     barrier()
+    sampler.mark_end()
     ms = ev0.elapsed_time(ev1)
     samples = []
     if graph is None:

@@ -101,4 +101,4 @@ def test_snow_return_map_matches_reference_outputs(km):
     C32 = g["C_out"].astype(np.float32).astype(np.float64).reshape(n, 9)
     km.km_snow_return_map3(C.c_longlong(n), C.c_double(float(g["dt"])), ptr(np.ascontiguousarray(F32)), ptr(np.ascontiguousarray(C32)),
                            ptr(np.ascontiguousarray(g["Jp"][:, 0])), ptr(Fout), ptr(jp_out))
-    print("fp32-storage return map: max |dF|", np.abs(Fout.reshape(n, 3, 3) - g["F_out"]).max())
+    assert np.abs(Fout.reshape(n, 3, 3) - g["F_out"]).max() < 1e-7 and np.abs(jp_out - g["Jp_out"][:, 0]).max() < 1e-6
