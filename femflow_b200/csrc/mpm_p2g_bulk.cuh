@@ -300,7 +300,10 @@ static bool p2g_bulk_launch_t(const DevCfg& cfg, const StateView<float>& s, long
     configured[dev] = true;
   }
   long long windows = (n + P2G_WINDOW - 1) / P2G_WINDOW;
-  static int wpw = [] { const char* e = getenv("FFMPM_P2G_WPW"); return e ? atoi(e) : 16; }();
+  // work item = WARPS * wpw windows per CTA.  8 measured best on the 16.8 M-particle block: 4 / 6 / 8 / 10 / 16 windows per warp
+  // -> 1.363 / 1.359 / 1.355 / 1.356 / 1.366 ms per substep (profiles/r02u_p2g_work_item_sweep.json): smaller items retire
+  // CTAs more often, which lets the binning kernels of the internal stream in earlier
+  static int wpw = [] { const char* e = getenv("FFMPM_P2G_WPW"); return e ? atoi(e) : 8; }();
   int blocks;
   if (wpw > 0) {
     blocks = (int)((windows + (long long)WARPS * wpw - 1) / ((long long)WARPS * wpw));
